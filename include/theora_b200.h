@@ -1,0 +1,213 @@
+/* theora_b200.h -- C ABI of the B200 (sm_100a) back-end for libtheora's
+ * per-fragment 8x8 block pipeline.
+ *
+ * This is the drop-in boundary.  Everything above it (bit reader, Huffman,
+ * token unpack, DC un-prediction, mode decision, rate control) stays host C in
+ * the reference; everything below it is hand-written CUDA.  The reference-side
+ * binding is theora_b200/backend/ocg_hooks.h + ocg_backend.c (see
+ * INTEGRATION.md): it fills oc_base_opt_vtable (reference lib/state.h:352-370)
+ * and oc_enc_opt_vtable (lib/encint.h:292-326) with recorders and flushes one
+ * frame's lists through the entry points declared here.
+ *
+ * Conventions shared with the reference:
+ *   - frame buffers use the reference's exact padded layout (state.c:545-671):
+ *     nrefs consecutive buffers of ref_frame_sz bytes, each luma | Cb | Cr with
+ *     16/8-pixel aprons; pixel addressing is bottom-up (negative row stride)
+ *     relative to `base_off`, the byte offset of the bottom-left luma pixel,
+ *     so state->frag_buf_offs[] and state->ref_ystride[] apply verbatim.
+ *   - coefficients are int16 in natural (row-major) order, AC already
+ *     dequantised (decode.c:1573-1574), DC raw (state.c:972,978 applies
+ *     dc_quant on the device).
+ *   - plain pointers and sizes only; every call returns 0 or a negative
+ *     OCG_E* code and never throws; a missing/failed CUDA device is an error,
+ *     there is no CPU fallback.
+ */
+#ifndef THEORA_B200_H
+#define THEORA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+# define OCG_API __attribute__((visibility("default")))
+#else
+# define OCG_API
+#endif
+
+#define OCG_OK        0
+#define OCG_EFAULT   (-1)   /* NULL argument (TH_EFAULT, codec.h:77) */
+#define OCG_EINVAL   (-10)  /* bad argument  (TH_EINVAL, codec.h:79) */
+#define OCG_EIMPL    (-23)  /* unsupported   (TH_EIMPL,  codec.h:87) */
+#define OCG_ECUDA    (-100) /* CUDA runtime failure; ocg_last_error() has the text */
+#define OCG_ENOMEM   (-101)
+
+/* Reference-frame roles, same numbering as OC_FRAME_* (state.h:270-282). */
+#define OCG_FRAME_GOLD 0
+#define OCG_FRAME_PREV 1
+#define OCG_FRAME_SELF 2
+
+/* Sparsity classes of a coded fragment, selected from last_zzi exactly as
+   oc_state_frag_recon_c (state.c:967) and oc_idct8x8_c (idct.c:327-329) do. */
+#define OCG_CLS_DC    0   /* last_zzi<2 : (dc*dc_quant+15)>>5, no iDCT        */
+#define OCG_CLS_3     1   /* last_zzi<=3 : coefficients in the top-left 2x2    */
+#define OCG_CLS_10    2   /* last_zzi<=10: coefficients in the top-left 4x4    */
+#define OCG_CLS_FULL  3   /* everything else: full 8x8                         */
+#define OCG_NCLS      4
+
+typedef struct ocg_plane_geom {
+  int32_t  nhfrags;    /* fragments per row        (state.h oc_fragment_plane) */
+  int32_t  nvfrags;    /* fragment rows                                          */
+  int32_t  froffset;   /* index of the plane's first fragment                    */
+  int32_t  nfrags;
+  int32_t  ystride;    /* NEGATIVE byte stride, == state->ref_ystride[pli]       */
+  int32_t  width;      /* plane width/height in pixels (coded frame)             */
+  int32_t  height;
+  int32_t  hpad;       /* apron width / height in pixels                         */
+  int32_t  vpad;
+  int64_t  plane_off;  /* bottom-left pixel of the plane relative to base_off
+                          (== frag_buf_offs[froffset])                           */
+} ocg_plane_geom;
+
+typedef struct ocg_geometry {
+  int32_t        frame_width;   /* coded size, multiples of 16 */
+  int32_t        frame_height;
+  int32_t        pixel_fmt;     /* TH_PF_420=0, TH_PF_422=2, TH_PF_444=3 (codec.h:94-107) */
+  int32_t        nrefs;         /* 3 for a decoder, 6 for an encoder (state.c:545) */
+  int32_t        nfrags;
+  int32_t        reserved;
+  int64_t        ref_frame_sz;  /* bytes per buffer   (state.c:582)                */
+  int64_t        base_off;      /* ref_frame_bufs[0][0].data - ref_frame_handle
+                                   after the flip (state.c:622-629)               */
+  ocg_plane_geom planes[3];
+} ocg_geometry;
+
+/* One coded fragment (16 bytes).  Replaces the argument list of
+   oc_state_frag_recon (state.h:361-362, state.c:959). */
+typedef struct ocg_frag_rec {
+  int32_t  buf_off;    /* state->frag_buf_offs[fragi]                             */
+  int16_t  mv;         /* state->frag_mvs[fragi]: dx=(int8)mv, dy=mv>>8           */
+  int16_t  dc;         /* frags[fragi].dc after DC un-prediction (decode.c:1392)  */
+  uint32_t coeff_row;  /* index of this fragment's first stored row in coeff_rows */
+  uint8_t  rowmask;    /* bit j: natural-order row j is stored (16 B per row)     */
+  uint8_t  last_zzi;   /* as handed to oc_state_frag_recon, 0..64                 */
+  uint8_t  refi;       /* OCG_FRAME_*: SELF = intra                               */
+  uint8_t  pli_qti;    /* pli | qti<<2                                            */
+} ocg_frag_rec;
+
+/* One frame of decoder-side block work.  Replaces the per-MCU sequence
+   oc_dec_frags_recon_mcu_plane -> oc_state_frag_recon / oc_frag_copy_list ->
+   oc_state_loop_filter_frag_rows -> oc_state_borders_fill_* of
+   decode.c:2858-2945.  Pointers are host pointers for ocg_dec_submit and
+   device pointers inside a resident pack. */
+typedef struct ocg_dec_frame {
+  int32_t             ref_idx[3];      /* buffer playing GOLD, PREV, SELF          */
+  int32_t             lf_limit;        /* loop_filter_limits[qis[0]]; 0 = no filter */
+  uint16_t            dc_quant[3][2];  /* dequant[pli][0][qti][0] (decode.c:1534)  */
+  int32_t             ncls[OCG_NCLS];  /* recs are sorted by class; counts per class */
+  int32_t             nuncoded;
+  int32_t             ncoeff_rows;
+  const ocg_frag_rec *recs;
+  const int16_t      *coeff_rows;      /* ncoeff_rows x 8 int16                    */
+  const int32_t      *uncoded_offs;    /* frag_buf_offs[] of uncoded fragments     */
+  const uint8_t      *coded_map;       /* nfrags bytes, frags[i].coded             */
+} ocg_dec_frame;
+
+typedef struct ocg_ctx  ocg_ctx;    /* per th_dec_ctx / th_enc_ctx device state   */
+typedef struct ocg_pack ocg_pack;   /* device-resident copy of a run of frames    */
+
+/* ---- library ----------------------------------------------------------- */
+OCG_API const char *ocg_version(void);
+OCG_API const char *ocg_last_error(void);
+OCG_API int         ocg_device_count(void);
+
+/* ---- geometry (restates oc_state_frarray_init/ref_bufs_init, state.c:424-671) */
+OCG_API int  ocg_geometry_init(ocg_geometry *g, int frame_width, int frame_height,
+                               int pixel_fmt, int nrefs);
+OCG_API void ocg_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs /* nfrags */);
+
+/* ---- context ------------------------------------------------------------ */
+OCG_API int  ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device);
+OCG_API void ocg_ctx_destroy(ocg_ctx *ctx);
+OCG_API const ocg_geometry *ocg_ctx_geometry(const ocg_ctx *ctx);
+OCG_API int  ocg_ctx_sync(ocg_ctx *ctx);
+OCG_API void *ocg_ctx_stream(ocg_ctx *ctx);                 /* cudaStream_t */
+OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *ctx, int buf);  /* device address of buffer `buf` */
+/* Whole padded buffer, host <-> device (ref_frame_sz bytes). */
+OCG_API int  ocg_ctx_upload_frame(ocg_ctx *ctx, int buf, const uint8_t *host_buf);
+OCG_API int  ocg_ctx_download_frame(ocg_ctx *ctx, int buf, uint8_t *host_buf);
+OCG_API int  ocg_ctx_fill_frame(ocg_ctx *ctx, int buf, int value);  /* oc_dec_init_dummy_frame, decode.c:2053 */
+
+/* ---- decode: one frame, host lists (the call the vtable back-end makes) -- */
+/* Pinned staging owned by the ctx; the recorder writes straight into it.
+   Capacities: nfrags recs, nfrags*8 rows, nfrags uncoded, nfrags map bytes. */
+OCG_API int  ocg_dec_staging(ocg_ctx *ctx, ocg_frag_rec **recs, int16_t **coeff_rows,
+                             int32_t **uncoded_offs, uint8_t **coded_map);
+/* H2D of the lists + recon/copy + loop filter + border fill on the ctx stream.
+   Asynchronous; pointers in `f` may be the staging pointers (no extra copy) or
+   any host memory (copied into staging first).  If host_out!=NULL the finished
+   SELF buffer is also copied back (ref_frame_sz bytes) on the same stream. */
+OCG_API int  ocg_dec_submit(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_out);
+
+/* ---- decode: device-resident frames, batched over independent streams ---- */
+OCG_API int  ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int device);
+OCG_API void ocg_pack_destroy(ocg_pack *p);
+OCG_API int  ocg_pack_nframes(const ocg_pack *p);
+/* One launch set for n independent (ctx, pack, frame) jobs of equal geometry on
+   `stream` (cudaStream_t, NULL = ctx[0]'s stream).  Asynchronous. */
+OCG_API int  ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs,
+                               const int32_t *frame_idx, int n, void *stream);
+/* Stage selection for profiling/tests: bit0 recon+copy, bit1 loop filter,
+   bit2 border fill.  Default 7. */
+OCG_API void ocg_set_stage_mask(int mask);
+OCG_API long ocg_launch_count(void);   /* kernels launched by this library so far */
+
+/* ---- encode-side batched block kernels (encint.h:292-326) ---------------- */
+/* Fragment descriptor for the encoder kernels: where the source block is, and
+   (optionally) one or two predictor blocks (frag_sub / frag_satd2 style). */
+typedef struct ocg_enc_frag {
+  int32_t src_off;     /* byte offset of the block's row 0 in the source buffer  */
+  int32_t ref_off0;    /* predictor 1 offset, or INT32_MIN for intra (sub_128)   */
+  int32_t ref_off1;    /* predictor 2 offset, or INT32_MIN for single-tap        */
+  int32_t aux;         /* quantiser selector: pli | qti<<2 | qii<<3              */
+} ocg_enc_frag;
+
+/* metric selector for ocg_enc_metrics_batch */
+#define OCG_MET_SAD        0  /* oc_enc_frag_sad_c / sad2 when ref_off1 valid (encfrag.c:42-90, no early out) */
+#define OCG_MET_SATD       1  /* oc_enc_frag_satd_c / satd2_c (encfrag.c:306-320): out = satd, dc         */
+#define OCG_MET_INTRA_SATD 2  /* oc_enc_frag_intra_satd_c (encfrag.c:322)                                  */
+#define OCG_MET_SSD        3  /* oc_enc_frag_ssd_c (encfrag.c:338)                                         */
+#define OCG_MET_INTRA_SAD  4  /* oc_enc_frag_intra_sad_c (encfrag.c:86)                                    */
+
+/* All encoder entry points take DEVICE pointers for frames and lists (the
+   caller owns residency) and run on `stream`. */
+OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uint8_t *ref_base,
+                                  int ystride, const ocg_enc_frag *frags, int n,
+                                  uint32_t *out_val, int32_t *out_dc, void *stream);
+/* sub/sub_128 -> fDCT (fdct.c:128) -> quantise (enquant.c:220): writes dct[n][64]
+   and qdct[n][64] in zig-zag order plus the last nonzero zzi per block.
+   dequant/enquant tables: [3 pli][2 qti][3 qii][64] u16 and {m,l} int16 pairs. */
+OCG_API int ocg_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                     const ocg_enc_frag *frags, int n,
+                                     const uint16_t *dequant, const int16_t *enquant,
+                                     int16_t *dct, int16_t *qdct, int32_t *nonzero, void *stream);
+/* One step of oc_mcenc_search_frame's square-pattern descent (mcenc.c:268-440)
+   for every macro block at once: evaluates the pattern sites around each MB's
+   current best vector with 4-block SAD on the ORIGINAL frames and moves to the
+   best site.  State arrays are per-MB. */
+typedef struct ocg_mb_search {
+  int32_t src_off[4];   /* luma block offsets of the macro block (mb_maps[mbi][0]) */
+  int16_t best_dx, best_dy;   /* current best full-pel vector                     */
+  uint32_t best_err;          /* its 16x16 SAD                                     */
+  int32_t  site;              /* last move (index into OC_SQUARE_SITES), 4 = start */
+  int32_t  done;
+} ocg_mb_search;
+OCG_API int ocg_mcenc_search_step(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                  ocg_mb_search *mbs, int nmbs, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEORA_B200_H */

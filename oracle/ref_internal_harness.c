@@ -1,0 +1,98 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/): thin wrappers that let Python call the
+ * reference's *internal* state-taking routines on caller-provided pixels, so
+ * unit-level golden vectors can be produced by the real reference code:
+ *   oc_state_get_mv_offsets            lib/state.c:846
+ *   oc_state_frag_recon_c              lib/state.c:959
+ *   oc_state_loop_filter_frag_rows_c   lib/state.c:1055
+ *   oc_state_borders_fill_rows/caps    lib/state.c:770,803
+ * Each wrapper builds the minimal oc_theora_state those routines read.  This
+ * file includes the reference's private headers, so it only builds where
+ * /root/reference is present; its objects live in oracle/_ref/.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "state.h"
+
+#define REFH_API __attribute__((visibility("default")))
+
+static oc_theora_state *refh_fake_state(int pixel_fmt) {
+  oc_theora_state *st = (oc_theora_state *)calloc(1, sizeof(*st));
+  st->info.pixel_fmt = (th_pixel_fmt)pixel_fmt;
+  oc_state_accel_init_c(st);
+  return st;
+}
+
+REFH_API int refh_mv_offsets(int pixel_fmt, int ystride, int pli, int mv, int offs[2]) {
+  oc_theora_state *st = refh_fake_state(pixel_fmt);
+  int n;
+  st->ref_ystride[pli] = ystride;
+  offs[0] = offs[1] = 0;
+  n = oc_state_get_mv_offsets(st, offs, pli, (oc_mv)mv);
+  free(st);
+  return n;
+}
+
+/* dst/ref point at the frames' bottom-left pixel (offset 0); buf_off locates
+   the fragment. */
+REFH_API void refh_state_frag_recon(unsigned char *dst_frame, const unsigned char *ref_frame, long buf_off,
+                                    int ystride, int pli, int pixel_fmt, int intra, int mv,
+                                    ogg_int16_t coeffs[128], int last_zzi, int dc_quant) {
+  oc_theora_state *st = refh_fake_state(pixel_fmt);
+  oc_fragment frag;
+  ptrdiff_t off = buf_off;
+  oc_mv fmv = (oc_mv)mv;
+  memset(&frag, 0, sizeof(frag));
+  frag.coded = 1;
+  frag.refi = intra ? OC_FRAME_SELF : OC_FRAME_PREV;
+  st->frags = &frag;
+  st->frag_buf_offs = &off;
+  st->frag_mvs = &fmv;
+  st->ref_ystride[pli] = ystride;
+  st->ref_frame_data[OC_FRAME_SELF] = dst_frame;
+  st->ref_frame_data[OC_FRAME_PREV] = (unsigned char *)ref_frame;
+  oc_state_frag_recon_c(st, 0, pli, coeffs, last_zzi, (ogg_uint16_t)dc_quant);
+  free(st);
+}
+
+/* pix = bottom-left pixel of a plane of nhfrags x nvfrags fragments. */
+REFH_API void refh_loop_filter_plane(unsigned char *pix, int ystride, int nhfrags, int nvfrags,
+                                     const unsigned char *coded, int limit) {
+  oc_theora_state *st = refh_fake_state(TH_PF_444);
+  ptrdiff_t n = (ptrdiff_t)nhfrags * nvfrags, i;
+  signed char bv[256];
+  st->fplanes[0].nhfrags = nhfrags;
+  st->fplanes[0].nvfrags = nvfrags;
+  st->fplanes[0].froffset = 0;
+  st->fplanes[0].nfrags = n;
+  st->frags = (oc_fragment *)calloc((size_t)n, sizeof(oc_fragment));
+  st->frag_buf_offs = (ptrdiff_t *)calloc((size_t)n, sizeof(ptrdiff_t));
+  for (i = 0; i < n; i++) {
+    st->frags[i].coded = coded[i] != 0;
+    st->frag_buf_offs[i] = (i / nhfrags) * 8 * (ptrdiff_t)ystride + (i % nhfrags) * 8;
+  }
+  st->ref_ystride[0] = ystride;
+  st->ref_frame_data[OC_FRAME_SELF] = pix;
+  if (limit) {
+    oc_loop_filter_init_c(bv, limit);
+    oc_state_loop_filter_frag_rows_c(st, bv, OC_FRAME_SELF, 0, 0, nvfrags);
+  }
+  free(st->frags);
+  free(st->frag_buf_offs);
+  free(st);
+}
+
+REFH_API void refh_loop_filter_table(signed char bv[256], int limit) { oc_loop_filter_init_c(bv, limit); }
+
+/* pix = TOP-left pixel, positive stride (borders_fill works on the un-flipped
+   th_img_plane as well: state.c:787 "allows the stride to be negative"). */
+REFH_API void refh_borders_fill(unsigned char *pix_bottom_left, int ystride, int width, int height,
+                                int pli, int pixel_fmt) {
+  oc_theora_state *st = refh_fake_state(pixel_fmt);
+  st->ref_frame_bufs[0][pli].width = width;
+  st->ref_frame_bufs[0][pli].height = height;
+  st->ref_frame_bufs[0][pli].stride = ystride;
+  st->ref_frame_bufs[0][pli].data = pix_bottom_left;
+  oc_state_borders_fill_rows(st, 0, pli, 0, height);
+  oc_state_borders_fill_caps(st, 0, pli);
+  free(st);
+}

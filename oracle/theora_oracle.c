@@ -1,0 +1,674 @@
+/* TEST INFRASTRUCTURE ONLY -- see theora_oracle.h.
+ *
+ * CPU restatement of libtheora's per-fragment 8x8 block pipeline.  Every
+ * function cites the reference file:line whose behaviour it restates; the
+ * arithmetic (16-bit wrap-arounds, arithmetic right shifts, rounding biases)
+ * is normative and therefore identical, the code structure is our own.
+ * Parity with the compiled reference is enforced by tests/test_oracle_*.py.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+#include "theora_oracle.h"
+
+#define OCO_EXPORT __attribute__((visibility("default")))
+
+/* cos(k*pi/16)*65536, reference lib/dct.h:21-28 */
+enum { K1 = 64277, K2 = 60547, K3 = 54491, K4 = 46341, K5 = 36410, K6 = 25080, K7 = 12785 };
+
+static inline int32_t mulhi16(int32_t k, int32_t v) { return (k * v) >> 16; }
+static inline int16_t wrap16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
+static inline uint8_t clamp255(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* One 8-point pass of idct.c:30-81 (idct8).  The reduced variants idct8_1..4
+   (idct.c:91-203) are this routine with the trailing inputs equal to zero, so
+   callers zero what the reference ignores instead of duplicating them. */
+static void idct8_pass(int16_t *out, int ostep, const int16_t in[8]) {
+  int32_t e0 = mulhi16(K4, wrap16(in[0] + in[4]));
+  int32_t e1 = mulhi16(K4, wrap16(in[0] - in[4]));
+  int32_t e2 = mulhi16(K6, in[2]) - mulhi16(K2, in[6]);
+  int32_t e3 = mulhi16(K2, in[2]) + mulhi16(K6, in[6]);
+  int32_t o4 = mulhi16(K7, in[1]) - mulhi16(K1, in[7]);
+  int32_t o5 = mulhi16(K3, in[5]) - mulhi16(K5, in[3]);
+  int32_t o6 = mulhi16(K5, in[5]) + mulhi16(K3, in[3]);
+  int32_t o7 = mulhi16(K1, in[1]) + mulhi16(K7, in[7]);
+  int32_t s4 = o4 + o5;
+  int32_t s5 = mulhi16(K4, wrap16(o4 - o5));
+  int32_t s7 = o7 + o6;
+  int32_t s6 = mulhi16(K4, wrap16(o7 - o6));
+  int32_t a0 = e0 + e3, a3 = e0 - e3;
+  int32_t a1 = e1 + e2, a2 = e1 - e2;
+  int32_t b6 = s6 + s5, b5 = s6 - s5;
+  out[0 * ostep] = wrap16(a0 + s7);
+  out[1 * ostep] = wrap16(a1 + b6);
+  out[2 * ostep] = wrap16(a2 + b5);
+  out[3 * ostep] = wrap16(a3 + s4);
+  out[4 * ostep] = wrap16(a3 - s4);
+  out[5 * ostep] = wrap16(a2 - b5);
+  out[6 * ostep] = wrap16(a1 - b6);
+  out[7 * ostep] = wrap16(a0 - s7);
+}
+
+/* idct.c:301-330.  Class selection by last_zzi, row pass into columns of w,
+   column pass, (v+8)>>4, and the input-clearing side effect the decoder relies
+   on (decode.c:1385). */
+OCO_EXPORT void oco_idct8x8(int16_t y[64], int16_t x[64], int last_zzi) {
+  /* number of leading coefficients the reference reads in each row */
+  static const uint8_t used3[8] = {2, 1, 0, 0, 0, 0, 0, 0};
+  static const uint8_t used10[8] = {4, 3, 2, 1, 0, 0, 0, 0};
+  static const uint8_t usedall[8] = {8, 8, 8, 8, 8, 8, 8, 8};
+  const uint8_t *used = last_zzi <= 3 ? used3 : (last_zzi <= 10 ? used10 : usedall);
+  int ncols = last_zzi <= 3 ? 2 : (last_zzi <= 10 ? 4 : 8);
+  int16_t w[64];
+  int16_t row[8];
+  int i, j;
+  memset(w, 0, sizeof(w));
+  for (i = 0; i < 8; i++) {
+    if (used[i] == 0) continue;
+    for (j = 0; j < 8; j++) row[j] = j < used[i] ? x[i * 8 + j] : 0;
+    idct8_pass(w + i, 8, row);
+  }
+  for (i = 0; i < 8; i++) {
+    for (j = 0; j < 8; j++) row[j] = j < ncols ? w[i * 8 + j] : 0;
+    idct8_pass(y + i, 8, row);
+  }
+  for (i = 0; i < 64; i++) y[i] = wrap16((y[i] + 8) >> 4);
+  for (i = 0; i < 8; i++)
+    for (j = 0; j < used[i]; j++) x[i * 8 + j] = 0;
+}
+
+/* fragment.c:49-57 */
+OCO_EXPORT void oco_frag_recon_intra(uint8_t *dst, int ystride, const int16_t res[64]) {
+  int r, c;
+  for (r = 0; r < 8; r++, dst += ystride)
+    for (c = 0; c < 8; c++) dst[c] = clamp255(res[r * 8 + c] + 128);
+}
+
+/* fragment.c:59-68 */
+OCO_EXPORT void oco_frag_recon_inter(uint8_t *dst, const uint8_t *src, int ystride, const int16_t res[64]) {
+  int r, c;
+  for (r = 0; r < 8; r++, dst += ystride, src += ystride)
+    for (c = 0; c < 8; c++) dst[c] = clamp255(res[r * 8 + c] + src[c]);
+}
+
+/* fragment.c:70-80 */
+OCO_EXPORT void oco_frag_recon_inter2(uint8_t *dst, const uint8_t *s1, const uint8_t *s2, int ystride,
+                                      const int16_t res[64]) {
+  int r, c;
+  for (r = 0; r < 8; r++, dst += ystride, s1 += ystride, s2 += ystride)
+    for (c = 0; c < 8; c++) dst[c] = clamp255(res[r * 8 + c] + ((s1[c] + s2[c]) >> 1));
+}
+
+/* fragment.c:20-27 */
+OCO_EXPORT void oco_frag_copy(uint8_t *dst, const uint8_t *src, int ystride) {
+  int r;
+  for (r = 0; r < 8; r++, dst += ystride, src += ystride) memcpy(dst, src, 8);
+}
+
+/* state.c:846-957.  Closed form of the OC_MVMAP/OC_MVMAP2 tables: the first
+   tap truncates the vector towards zero at half-pel (quarter-pel in a
+   decimated chroma direction), the second tap -- present when either component
+   has a fractional part -- is one step further away from zero. */
+static void mv_component(int d, int qpel, int *ipart, int *step) {
+  int mag = d < 0 ? -d : d;
+  int sgn = d < 0 ? -1 : 1;
+  int frac = qpel ? (mag & 3) : (mag & 1);
+  *ipart = sgn * (mag >> (qpel ? 2 : 1));
+  *step = frac ? sgn : 0;
+}
+
+OCO_EXPORT int oco_mv_offsets(int offs[2], int ystride, int pli, int pixel_fmt, int16_t mv) {
+  int dx = (signed char)(mv & 0xFF);
+  int dy = mv >> 8;
+  int qx = pli != 0 && !(pixel_fmt & 1);
+  int qy = pli != 0 && !(pixel_fmt & 2);
+  int mx, my, mx2, my2;
+  mv_component(dx, qx, &mx, &mx2);
+  mv_component(dy, qy, &my, &my2);
+  offs[0] = my * ystride + mx;
+  if (mx2 || my2) {
+    offs[1] = offs[0] + my2 * ystride + mx2;
+    return 2;
+  }
+  return 1;
+}
+
+/* state.c:959-1000 */
+OCO_EXPORT void oco_state_frag_recon(uint8_t *dst_frame, const uint8_t *ref_frame, int32_t buf_off,
+                                     int ystride, int pli, int pixel_fmt, int intra, int16_t mv,
+                                     int16_t coeffs[128], int last_zzi, uint16_t dc_quant) {
+  uint8_t *dst = dst_frame + buf_off;
+  int i;
+  if (last_zzi < 2) {
+    int16_t p = wrap16((coeffs[0] * (int32_t)dc_quant + 15) >> 5);
+    for (i = 0; i < 64; i++) coeffs[64 + i] = p;
+  } else {
+    coeffs[0] = wrap16(coeffs[0] * (int32_t)dc_quant);
+    oco_idct8x8(coeffs + 64, coeffs, last_zzi);
+  }
+  if (intra) oco_frag_recon_intra(dst, ystride, coeffs + 64);
+  else {
+    const uint8_t *ref = ref_frame + buf_off;
+    int offs[2];
+    if (oco_mv_offsets(offs, ystride, pli, pixel_fmt, mv) > 1)
+      oco_frag_recon_inter2(dst, ref + offs[0], ref + offs[1], ystride, coeffs + 64);
+    else oco_frag_recon_inter(dst, ref + offs[0], ystride, coeffs + 64);
+  }
+}
+
+/* Closed form of the bounding-value table built by state.c:1036-1045. */
+OCO_EXPORT int oco_lflim(int r, int limit) {
+  int a = r < 0 ? -r : r;
+  int v;
+  if (a < limit) v = a;
+  else if (a < 2 * limit) v = 2 * limit - a;
+  else v = 0;
+  return r < 0 ? -v : v;
+}
+
+/* state.c:1036-1045, table form (kept to pin the closed form above). */
+OCO_EXPORT void oco_loop_filter_init(signed char bv[256], int limit) {
+  int r;
+  for (r = -127; r <= 128; r++) bv[127 + r] = (signed char)oco_lflim(r, limit);
+}
+
+/* One line of loop_filter_h / loop_filter_v (state.c:1002-1031): p[0..3*step]
+   straddle the edge; the middle two samples are corrected. */
+static inline void lf_line(uint8_t *p, ptrdiff_t step, int limit) {
+  int f = p[0] - p[3 * step] + 3 * (p[2 * step] - p[step]);
+  f = oco_lflim((f + 4) >> 3, limit);
+  p[step] = clamp255(p[step] + f);
+  p[2 * step] = clamp255(p[2 * step] - f);
+}
+
+/* Filter across the vertical edge at `pix` (left column of a fragment), rows
+   0..7: loop_filter_h. */
+static void lf_vedge(uint8_t *pix, int ystride, int limit) {
+  int r;
+  for (r = 0; r < 8; r++) lf_line(pix - 2 + (ptrdiff_t)r * ystride, 1, limit);
+}
+
+/* Filter across the horizontal edge at row `pix`: loop_filter_v. */
+static void lf_hedge(uint8_t *pix, int ystride, int limit) {
+  int c;
+  for (c = 0; c < 8; c++) lf_line(pix + c - 2 * (ptrdiff_t)ystride, ystride, limit);
+}
+
+/* state.c:1055-1105: raster over fragments from row 0 (bottom); a coded
+   fragment filters its left and lower edges, and its right/upper edges only
+   when that neighbour is not coded. */
+OCO_EXPORT void oco_loop_filter_plane_seq(uint8_t *pix, int ystride, int nhfrags, int nvfrags,
+                                          const uint8_t *coded, int limit) {
+  int fx, fy;
+  if (limit == 0) return;
+  for (fy = 0; fy < nvfrags; fy++) {
+    for (fx = 0; fx < nhfrags; fx++) {
+      uint8_t *p;
+      if (!coded[fy * nhfrags + fx]) continue;
+      p = pix + (ptrdiff_t)fy * 8 * ystride + fx * 8;
+      if (fx > 0) lf_vedge(p, ystride, limit);
+      if (fy > 0) lf_hedge(p, ystride, limit);
+      if (fx + 1 < nhfrags && !coded[fy * nhfrags + fx + 1]) lf_vedge(p + 8, ystride, limit);
+      if (fy + 1 < nvfrags && !coded[(fy + 1) * nhfrags + fx]) lf_hedge(p + 8 * (ptrdiff_t)ystride, ystride, limit);
+    }
+  }
+}
+
+/* Order-free form.  Every filter line lies inside exactly one 8x8 "cell"
+   centred on a fragment corner (pixel columns [8cx-4,8cx+4), rows
+   [8cy-4,8cy+4)).  Lines that do not cross the central 4x4 patch touch pixels
+   no other line touches; the (up to) eight lines inside the patch are applied
+   in the order the raster scan of state.c:1083-1104 would reach them:
+     A=(cx-1,cy-1) B=(cx,cy-1) C=(cx-1,cy) D=(cx,cy)
+     Vd: vertical edge A|B   Hl: horizontal edge A/C
+     Vu: vertical edge C|D   Hr: horizontal edge B/D
+     1 Vd if !B&&A   2 Hl if !C&&A   3 Vd if B   4 Hr if !D&&B
+     5 Hl if C       6 Vu if !D&&C   7 Vu if D   8 Hr if D            */
+static int cell_coded(const uint8_t *coded, int nh, int nv, int fx, int fy) {
+  if (fx < 0 || fy < 0 || fx >= nh || fy >= nv) return 0;
+  return coded[fy * nh + fx] != 0;
+}
+
+OCO_EXPORT void oco_loop_filter_plane_cells(uint8_t *pix, int ystride, int nhfrags, int nvfrags,
+                                            const uint8_t *coded, int limit) {
+  int cx, cy, k;
+  if (limit == 0) return;
+  for (cy = 0; cy <= nvfrags; cy++) {
+    for (cx = 0; cx <= nhfrags; cx++) {
+      int a = cell_coded(coded, nhfrags, nvfrags, cx - 1, cy - 1);
+      int b = cell_coded(coded, nhfrags, nvfrags, cx, cy - 1);
+      int c = cell_coded(coded, nhfrags, nvfrags, cx - 1, cy);
+      int d = cell_coded(coded, nhfrags, nvfrags, cx, cy);
+      /* which of the four edges meeting here exist and are filtered */
+      int vd = cx > 0 && cx < nhfrags && cy > 0 && (a || b);
+      int vu = cx > 0 && cx < nhfrags && cy < nvfrags && (c || d);
+      int hl = cy > 0 && cy < nvfrags && cx > 0 && (a || c);
+      int hr = cy > 0 && cy < nvfrags && cx < nhfrags && (b || d);
+      uint8_t *o = pix + (ptrdiff_t)cy * 8 * ystride + cx * 8; /* corner pixel (8cx,8cy) */
+      int slot;
+      /* independent lines: rows -4,-3 of Vd, rows 2,3 of Vu, cols -4,-3 of Hl, cols 2,3 of Hr */
+      if (vd) for (k = -4; k < -2; k++) lf_line(o - 2 + (ptrdiff_t)k * ystride, 1, limit);
+      if (vu) for (k = 2; k < 4; k++) lf_line(o - 2 + (ptrdiff_t)k * ystride, 1, limit);
+      if (hl) for (k = -4; k < -2; k++) lf_line(o + k - 2 * (ptrdiff_t)ystride, ystride, limit);
+      if (hr) for (k = 2; k < 4; k++) lf_line(o + k - 2 * (ptrdiff_t)ystride, ystride, limit);
+      /* ordered lines inside the central patch */
+      for (slot = 1; slot <= 8; slot++) {
+        int run_vd = (slot == 1 && vd && !b && a) || (slot == 3 && vd && b);
+        int run_hl = (slot == 2 && hl && !c && a) || (slot == 5 && hl && c);
+        int run_hr = (slot == 4 && hr && !d && b) || (slot == 8 && hr && d);
+        int run_vu = (slot == 6 && vu && !d && c) || (slot == 7 && vu && d);
+        if (run_vd) for (k = -2; k < 0; k++) lf_line(o - 2 + (ptrdiff_t)k * ystride, 1, limit);
+        if (run_vu) for (k = 0; k < 2; k++) lf_line(o - 2 + (ptrdiff_t)k * ystride, 1, limit);
+        if (run_hl) for (k = -2; k < 0; k++) lf_line(o + k - 2 * (ptrdiff_t)ystride, ystride, limit);
+        if (run_hr) for (k = 0; k < 2; k++) lf_line(o + k - 2 * (ptrdiff_t)ystride, ystride, limit);
+      }
+    }
+  }
+}
+
+/* state.c:770-835: left/right replication per row, then top/bottom rows
+   (full padded width).  `pix` is the bottom-left pixel, ystride negative. */
+OCO_EXPORT void oco_borders_fill_plane(uint8_t *pix, int ystride, int width, int height, int hpad, int vpad) {
+  int y;
+  for (y = 0; y < height; y++) {
+    uint8_t *row = pix + (ptrdiff_t)y * ystride;
+    memset(row - hpad, row[0], (size_t)hpad);
+    memset(row + width, row[width - 1], (size_t)hpad);
+  }
+  for (y = 1; y <= vpad; y++) {
+    memcpy(pix - hpad - (ptrdiff_t)y * ystride, pix - hpad, (size_t)(width + 2 * hpad));
+    memcpy(pix - hpad + (ptrdiff_t)(height - 1 + y) * ystride,
+           pix - hpad + (ptrdiff_t)(height - 1) * ystride, (size_t)(width + 2 * hpad));
+  }
+}
+
+/* ---------------------------------------------------------------------- */
+/* state.c:424-470 (fragment planes) and 545-671 (padded buffers, flip,
+   frag_buf_offs). */
+OCO_EXPORT int oco_geometry_init(ocg_geometry *g, int fw, int fh, int pixel_fmt, int nrefs) {
+  int hdec = !(pixel_fmt & 1), vdec = !(pixel_fmt & 2);
+  int64_t ystr = fw + 32, yrows = fh + 32;
+  int64_t cstr = ((ystr >> hdec) + 15) & ~(int64_t)15, crows = yrows >> vdec;
+  int64_t ysz = ystr * yrows, csz = cstr * crows;
+  int64_t yoff = 16 + 16 * ystr;
+  int64_t coff = (16 >> hdec) + (16 >> vdec) * cstr;
+  int64_t align = (-coff) & 15;
+  int64_t top_left[3];
+  int pli, fro = 0;
+  if ((fw & 15) || (fh & 15) || fw <= 0 || fh <= 0 || pixel_fmt == 1 || pixel_fmt < 0 || pixel_fmt > 3 ||
+      nrefs < 3 || nrefs > 6)
+    return OCG_EINVAL;
+  memset(g, 0, sizeof(*g));
+  g->frame_width = fw;
+  g->frame_height = fh;
+  g->pixel_fmt = pixel_fmt;
+  g->nrefs = nrefs;
+  g->ref_frame_sz = ysz + 2 * csz + 16;
+  top_left[0] = yoff;
+  top_left[1] = ysz + align + coff;
+  top_left[2] = ysz + align + csz + coff;
+  g->base_off = yoff + (int64_t)(fh - 1) * ystr;
+  for (pli = 0; pli < 3; pli++) {
+    ocg_plane_geom *p = &g->planes[pli];
+    int w = pli ? fw >> hdec : fw, h = pli ? fh >> vdec : fh;
+    int64_t str = pli ? cstr : ystr;
+    p->width = w;
+    p->height = h;
+    p->nhfrags = w >> 3;
+    p->nvfrags = h >> 3;
+    p->froffset = fro;
+    p->nfrags = p->nhfrags * p->nvfrags;
+    p->ystride = (int32_t)-str;
+    p->hpad = pli ? 16 >> hdec : 16;
+    p->vpad = pli ? 16 >> vdec : 16;
+    p->plane_off = top_left[pli] + (int64_t)(h - 1) * str - g->base_off;
+    fro += p->nfrags;
+  }
+  g->nfrags = fro;
+  return 0;
+}
+
+OCO_EXPORT void oco_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs) {
+  int pli, fx, fy;
+  for (pli = 0; pli < 3; pli++) {
+    const ocg_plane_geom *p = &g->planes[pli];
+    for (fy = 0; fy < p->nvfrags; fy++)
+      for (fx = 0; fx < p->nhfrags; fx++)
+        offs[p->froffset + fy * p->nhfrags + fx] =
+            (int32_t)(p->plane_off + (int64_t)fy * 8 * p->ystride + fx * 8);
+  }
+}
+
+/* Planes are consecutive in memory (luma, Cb, Cr), so the plane -- hence the
+   row stride -- of a fragment follows from its buffer offset. */
+static int plane_of_offset(const ocg_geometry *g, int64_t off) {
+  int pli;
+  for (pli = 2; pli > 0; pli--) {
+    const ocg_plane_geom *p = &g->planes[pli];
+    if (off >= p->plane_off + (int64_t)(p->height - 1) * p->ystride) break;
+  }
+  return pli;
+}
+
+/* The whole-frame sequence of decode.c:2858-2945 driven from the C-ABI frame
+   description: recon of coded fragments (decode.c:1584 -> state.c:959), copy
+   of uncoded ones (decode.c:1599), loop filter over all rows (2882), borders
+   (2890, 2945). */
+OCO_EXPORT void oco_dec_frame(const ocg_geometry *g, uint8_t *frames, const ocg_dec_frame *f, int stage_mask) {
+  uint8_t *base[3];
+  int ncoded = 0, i, r, c, pli;
+  for (i = 0; i < 3; i++)
+    base[i] = f->ref_idx[i] >= 0 ? frames + (int64_t)f->ref_idx[i] * g->ref_frame_sz + g->base_off : NULL;
+  for (i = 0; i < OCG_NCLS; i++) ncoded += f->ncls[i];
+  if (stage_mask & 1) {
+    for (i = 0; i < ncoded; i++) {
+      const ocg_frag_rec *rec = &f->recs[i];
+      int16_t blk[128];
+      const int16_t *rows = f->coeff_rows + (size_t)rec->coeff_row * 8;
+      int pl = rec->pli_qti & 3, qti = rec->pli_qti >> 2 & 1;
+      memset(blk, 0, sizeof(blk));
+      for (r = 0; r < 8; r++) {
+        if (!(rec->rowmask >> r & 1)) continue;
+        for (c = 0; c < 8; c++) blk[r * 8 + c] = rows[c];
+        rows += 8;
+      }
+      blk[0] = rec->dc;
+      oco_state_frag_recon(base[OCG_FRAME_SELF], rec->refi == OCG_FRAME_SELF ? NULL : base[rec->refi],
+                           rec->buf_off, g->planes[pl].ystride, pl, g->pixel_fmt,
+                           rec->refi == OCG_FRAME_SELF, rec->mv, blk, rec->last_zzi, f->dc_quant[pl][qti]);
+    }
+    for (i = 0; i < f->nuncoded; i++) {
+      int32_t off = f->uncoded_offs[i];
+      pli = plane_of_offset(g, off);
+      oco_frag_copy(base[OCG_FRAME_SELF] + off, base[OCG_FRAME_PREV] + off, g->planes[pli].ystride);
+    }
+  }
+  for (pli = 0; pli < 3; pli++) {
+    const ocg_plane_geom *p = &g->planes[pli];
+    uint8_t *pix = base[OCG_FRAME_SELF] + p->plane_off;
+    if ((stage_mask & 2) && f->lf_limit)
+      oco_loop_filter_plane_seq(pix, p->ystride, p->nhfrags, p->nvfrags, f->coded_map + p->froffset, f->lf_limit);
+    if (stage_mask & 4) oco_borders_fill_plane(pix, p->ystride, p->width, p->height, p->hpad, p->vpad);
+  }
+}
+
+/* ---------------------------------------------------------------------- */
+/* encoder block kernels */
+
+/* fdct.c:28-120 (oc_fdct8): input every `istep`-th sample, output 8 in a row. */
+static inline int fd_exp(int t, int bias) { return ((27146 * t + bias) >> 16) + t + (t != 0); }
+
+static void fdct8_pass(int16_t out[8], const int16_t *in, int istep) {
+  int x0 = in[0], x1 = in[istep], x2 = in[2 * istep], x3 = in[3 * istep];
+  int x4 = in[4 * istep], x5 = in[5 * istep], x6 = in[6 * istep], x7 = in[7 * istep];
+  /* stage 1 */
+  int a0 = x0 + x7, a7 = x0 - x7, a1 = x1 + x6, a6 = x1 - x6;
+  int a2 = x2 + x5, a5 = x2 - x5, a3 = x3 + x4, a4 = x3 - x4;
+  /* stage 2 */
+  int b0 = a0 + a3, b3 = a0 - a3, b1 = a1 + a2, b2 = a1 - a2;
+  int b6 = a6 + a5, b5 = a6 - a5;
+  /* stage 3 */
+  int s = fd_exp(b5, 0xB500) >> 1;
+  int c4 = a4 + s, c5 = a4 - s;
+  int c7, c6, r, u, v;
+  s = fd_exp(b6, 0xB500) >> 1;
+  c7 = a7 + s;
+  c6 = a7 - s;
+  /* stage 4 */
+  r = fd_exp(b0, 0x4000);
+  s = fd_exp(b1, 0xB500);
+  u = (r + s) >> 1;
+  out[0] = (int16_t)u;
+  out[4] = (int16_t)(r - u);
+  u = ((K6 * b2 + K2 * b3 + 0x6CB7) >> 16) + (b3 != 0);
+  s = (K6 * u >> 16) - b2;
+  v = ((s * 21600 + 0x2800) >> 18) + s + (s != 0);
+  out[2] = (int16_t)u;
+  out[6] = (int16_t)v;
+  u = ((K5 * c6 + K3 * c5 + 0x0E3D) >> 16) + (c5 != 0);
+  s = c6 - (K5 * u >> 16);
+  v = ((s * 26568 + 0x3400) >> 17) + s + (s != 0);
+  out[5] = (int16_t)u;
+  out[3] = (int16_t)v;
+  u = ((K7 * c4 + K1 * c7 + 0x7B1B) >> 16) + (c7 != 0);
+  s = (K7 * u >> 16) - c4;
+  v = ((s * 20539 + 0x3000) >> 20) + s + (s != 0);
+  out[1] = (int16_t)u;
+  out[7] = (int16_t)v;
+}
+
+/* zig-zag position -> natural index (internal.c:27-44, first 64 entries);
+   generated, not tabulated: walk the anti-diagonals. */
+static void zigzag_table(uint8_t fz[64]) {
+  int d, k = 0;
+  for (d = 0; d < 15; d++) {
+    int lo = d < 8 ? 0 : d - 7, hi = d < 8 ? d : 7, i;
+    for (i = lo; i <= hi; i++) {
+      /* odd diagonals run top-right -> bottom-left, even ones the other way */
+      int r = (d & 1) ? i : d - i;
+      fz[k++] = (uint8_t)(r * 8 + (d - r));
+    }
+  }
+}
+
+/* fdct.c:128-150 */
+OCO_EXPORT void oco_fdct8x8(int16_t y[64], const int16_t x[64]) {
+  static uint8_t fz[64];
+  static int fz_ready = 0;
+  int16_t w[64], t[64];
+  int i;
+  if (!fz_ready) { zigzag_table(fz); fz_ready = 1; }
+  for (i = 0; i < 64; i++) w[i] = (int16_t)(x[i] << 2);
+  w[0] = (int16_t)(w[0] + (w[0] != 0) + 1);
+  w[1]++;
+  w[8]--;
+  for (i = 0; i < 8; i++) fdct8_pass(t + i * 8, w + i, 8);
+  for (i = 0; i < 8; i++) fdct8_pass(w + i * 8, t + i, 8);
+  for (i = 0; i < 64; i++) y[i] = (int16_t)((w[fz[i]] + 2) >> 2);
+}
+
+/* enquant.c:184-208: per coefficient {m,l} with x/d == ((x*m>>16)+x>>l)+(x<0). */
+OCO_EXPORT void oco_enquant_init(int16_t enq[128], const uint16_t dequant[64]) {
+  int zzi;
+  for (zzi = 0; zzi < 64; zzi++) {
+    uint32_t d = (uint32_t)dequant[zzi] << 1;
+    int l = 31 - __builtin_clz(d);
+    uint32_t t = 1 + ((uint32_t)1 << (16 + l)) / d;
+    enq[2 * zzi] = (int16_t)(t - 0x10000);
+    enq[2 * zzi + 1] = (int16_t)l;
+  }
+}
+
+/* enquant.c:220-249 */
+OCO_EXPORT int oco_quantize(int16_t q[64], const int16_t dct[64], const uint16_t dequant[64],
+                            const int16_t enq[128]) {
+  int zzi, last = 0;
+  for (zzi = 0; zzi < 64; zzi++) {
+    int v = dct[zzi] << 1, d = dequant[zzi];
+    if (abs(v) >= d) {
+      int s = v < 0 ? -1 : 0;
+      v += (d + s) ^ s;
+      v = (((enq[2 * zzi] * (int32_t)v >> 16) + v) >> enq[2 * zzi + 1]) - s;
+      q[zzi] = (int16_t)v;
+      last = zzi;
+    } else q[zzi] = 0;
+  }
+  return last;
+}
+
+OCO_EXPORT void oco_frag_sub(int16_t d[64], const uint8_t *src, const uint8_t *ref, int ystride) {
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride, ref += ystride)
+    for (c = 0; c < 8; c++) d[r * 8 + c] = (int16_t)(src[c] - ref[c]);
+}
+
+OCO_EXPORT void oco_frag_sub_128(int16_t d[64], const uint8_t *src, int ystride) {
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride)
+    for (c = 0; c < 8; c++) d[r * 8 + c] = (int16_t)(src[c] - 128);
+}
+
+OCO_EXPORT unsigned oco_frag_sad(const uint8_t *src, const uint8_t *ref, int ystride) {
+  unsigned s = 0;
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride, ref += ystride)
+    for (c = 0; c < 8; c++) s += (unsigned)abs(src[c] - ref[c]);
+  return s;
+}
+
+/* encfrag.c:56-69: row-granular early out once the running sum exceeds thresh. */
+OCO_EXPORT unsigned oco_frag_sad_thresh(const uint8_t *src, const uint8_t *ref, int ystride, unsigned thresh) {
+  unsigned s = 0;
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride, ref += ystride) {
+    for (c = 0; c < 8; c++) s += (unsigned)abs(src[c] - ref[c]);
+    if (s > thresh) break;
+  }
+  return s;
+}
+
+OCO_EXPORT unsigned oco_frag_sad2_thresh(const uint8_t *src, const uint8_t *r1, const uint8_t *r2, int ystride,
+                                         unsigned thresh) {
+  unsigned s = 0;
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride, r1 += ystride, r2 += ystride) {
+    for (c = 0; c < 8; c++) s += (unsigned)abs(src[c] - ((r1[c] + r2[c]) >> 1));
+    if (s > thresh) break;
+  }
+  return s;
+}
+
+OCO_EXPORT unsigned oco_frag_intra_sad(const uint8_t *src, int ystride) {
+  const uint8_t *p = src;
+  unsigned s = 0;
+  int r, c, dc = 0;
+  for (r = 0; r < 8; r++, p += ystride)
+    for (c = 0; c < 8; c++) dc += p[c];
+  dc = (dc + 32) >> 6;
+  for (r = 0, p = src; r < 8; r++, p += ystride)
+    for (c = 0; c < 8; c++) s += (unsigned)abs(p[c] - dc);
+  return s;
+}
+
+/* 8-point Hadamard butterfly network shared by encfrag.c:109-304. */
+static void hadamard8(int t[8]) {
+  int a0 = t[0] + t[4], a4 = t[0] - t[4], a1 = t[1] + t[5], a5 = t[1] - t[5];
+  int a2 = t[2] + t[6], a6 = t[2] - t[6], a3 = t[3] + t[7], a7 = t[3] - t[7];
+  int b0 = a0 + a2, b2 = a0 - a2, b1 = a1 + a3, b3 = a1 - a3;
+  int b4 = a4 + a6, b6 = a4 - a6, b5 = a5 + a7, b7 = a5 - a7;
+  t[0] = b0 + b1; t[1] = b0 - b1; t[2] = b2 + b3; t[3] = b2 - b3;
+  t[4] = b4 + b5; t[5] = b4 - b5; t[6] = b6 + b7; t[7] = b6 - b7;
+}
+
+/* encfrag.c:262-304 (oc_hadamard_sad) applied to the row-transformed, 16-bit
+   truncated, transposed buffer produced by encfrag.c:109-260. */
+static unsigned hadamard_sad(int *dc, int16_t buf[64]) {
+  unsigned sad = 0;
+  int i, k, t[8];
+  for (i = 0; i < 8; i++) {
+    for (k = 0; k < 8; k++) t[k] = buf[i * 8 + k];
+    hadamard8(t);
+    for (k = 0; k < 8; k++) if (i > 0 || k > 0) sad += (unsigned)abs(t[k]);
+  }
+  *dc = buf[0] + buf[1] + buf[2] + buf[3] + buf[4] + buf[5] + buf[6] + buf[7];
+  return sad;
+}
+
+static unsigned satd_core(int *dc, const uint8_t *src, const uint8_t *r1, const uint8_t *r2, int ystride) {
+  int16_t buf[64];
+  int r, c, t[8];
+  for (r = 0; r < 8; r++) {
+    for (c = 0; c < 8; c++) {
+      int pred = r1 == NULL ? 0 : (r2 == NULL ? r1[c] : (r1[c] + r2[c]) >> 1);
+      t[c] = src[c] - pred;
+    }
+    hadamard8(t);
+    for (c = 0; c < 8; c++) buf[c * 8 + r] = (int16_t)t[c];
+    src += ystride;
+    if (r1) r1 += ystride;
+    if (r2) r2 += ystride;
+  }
+  return hadamard_sad(dc, buf);
+}
+
+OCO_EXPORT unsigned oco_frag_satd(int *dc, const uint8_t *src, const uint8_t *ref, int ystride) {
+  return satd_core(dc, src, ref, NULL, ystride);
+}
+OCO_EXPORT unsigned oco_frag_satd2(int *dc, const uint8_t *src, const uint8_t *r1, const uint8_t *r2, int ystride) {
+  return satd_core(dc, src, r1, r2, ystride);
+}
+OCO_EXPORT unsigned oco_frag_intra_satd(int *dc, const uint8_t *src, int ystride) {
+  return satd_core(dc, src, NULL, NULL, ystride);
+}
+
+OCO_EXPORT unsigned oco_frag_ssd(const uint8_t *src, const uint8_t *ref, int ystride) {
+  unsigned s = 0;
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride, ref += ystride)
+    for (c = 0; c < 8; c++) s += (unsigned)((src[c] - ref[c]) * (src[c] - ref[c]));
+  return s;
+}
+
+OCO_EXPORT unsigned oco_frag_border_ssd(const uint8_t *src, const uint8_t *ref, int ystride, int64_t mask) {
+  unsigned s = 0;
+  int r, c;
+  for (r = 0; r < 8; r++, src += ystride, ref += ystride)
+    for (c = 0; c < 8; c++)
+      if ((uint64_t)mask >> (r * 8 + c) & 1) s += (unsigned)((src[c] - ref[c]) * (src[c] - ref[c]));
+  return s;
+}
+
+OCO_EXPORT void oco_frag_copy2(uint8_t *dst, const uint8_t *s1, const uint8_t *s2, int ystride) {
+  int r, c;
+  for (r = 0; r < 8; r++, dst += ystride, s1 += ystride, s2 += ystride)
+    for (c = 0; c < 8; c++) dst[c] = (uint8_t)((s1[c] + s2[c]) >> 1);
+}
+
+/* ---- batch forms mirroring the C-ABI ---- */
+OCO_EXPORT void oco_enc_metrics_batch(int metric, const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                      const ocg_enc_frag *frags, int n, uint32_t *out_val, int32_t *out_dc) {
+  int i;
+  for (i = 0; i < n; i++) {
+    const uint8_t *src = src_base + frags[i].src_off;
+    const uint8_t *r0 = frags[i].ref_off0 == INT32_MIN ? NULL : ref_base + frags[i].ref_off0;
+    const uint8_t *r1 = frags[i].ref_off1 == INT32_MIN ? NULL : ref_base + frags[i].ref_off1;
+    int dc = 0;
+    unsigned v = 0;
+    switch (metric) {
+      case OCG_MET_SAD: v = r1 ? oco_frag_sad2_thresh(src, r0, r1, ystride, UINT_MAX) : oco_frag_sad(src, r0, ystride); break;
+      case OCG_MET_SATD: v = r1 ? oco_frag_satd2(&dc, src, r0, r1, ystride) : oco_frag_satd(&dc, src, r0, ystride); break;
+      case OCG_MET_INTRA_SATD: v = oco_frag_intra_satd(&dc, src, ystride); break;
+      case OCG_MET_SSD: v = oco_frag_ssd(src, r0, ystride); break;
+      case OCG_MET_INTRA_SAD: v = oco_frag_intra_sad(src, ystride); break;
+      default: break;
+    }
+    out_val[i] = v;
+    if (out_dc) out_dc[i] = dc;
+  }
+}
+
+/* analyze.c:725-778: sub / sub_128 / copy2+sub, fDCT, quantise. */
+OCO_EXPORT void oco_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                         const ocg_enc_frag *frags, int n, const uint16_t *dequant,
+                                         const int16_t *enquant, int16_t *dct, int16_t *qdct, int32_t *nonzero) {
+  int i;
+  for (i = 0; i < n; i++) {
+    const uint8_t *src = src_base + frags[i].src_off;
+    int pli = frags[i].aux & 3, qti = frags[i].aux >> 2 & 1, qii = frags[i].aux >> 3 & 3;
+    int tab = ((pli * 2 + qti) * 3 + qii);
+    int16_t diff[64];
+    if (frags[i].ref_off0 == INT32_MIN) oco_frag_sub_128(diff, src, ystride);
+    else if (frags[i].ref_off1 == INT32_MIN) oco_frag_sub(diff, src, ref_base + frags[i].ref_off0, ystride);
+    else {
+      const uint8_t *r0 = ref_base + frags[i].ref_off0, *r1 = ref_base + frags[i].ref_off1;
+      int r, c;
+      for (r = 0; r < 8; r++)
+        for (c = 0; c < 8; c++)
+          diff[r * 8 + c] = (int16_t)(src[(ptrdiff_t)r * ystride + c] -
+                                      ((r0[(ptrdiff_t)r * ystride + c] + r1[(ptrdiff_t)r * ystride + c]) >> 1));
+    }
+    oco_fdct8x8(dct + (size_t)i * 64, diff);
+    nonzero[i] = oco_quantize(qdct + (size_t)i * 64, dct + (size_t)i * 64, dequant + (size_t)tab * 64,
+                              enquant + (size_t)tab * 128);
+  }
+}

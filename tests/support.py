@@ -1,0 +1,310 @@
+"""Shared test plumbing: ctypes views of the oracle, the compiled reference
+(oracle/_ref, when present) and the product C-ABI library.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may touch
+oracle/; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+u8p = C.POINTER(C.c_uint8)
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+u16p = C.POINTER(C.c_uint16)
+u32p = C.POINTER(C.c_uint32)
+
+
+def ptr(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+# ---- C-ABI structs (include/theora_b200.h) ---------------------------------
+class PlaneGeom(C.Structure):
+    _fields_ = [("nhfrags", C.c_int32), ("nvfrags", C.c_int32), ("froffset", C.c_int32),
+                ("nfrags", C.c_int32), ("ystride", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("hpad", C.c_int32), ("vpad", C.c_int32),
+                ("plane_off", C.c_int64)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("frame_width", C.c_int32), ("frame_height", C.c_int32), ("pixel_fmt", C.c_int32),
+                ("nrefs", C.c_int32), ("nfrags", C.c_int32), ("reserved", C.c_int32),
+                ("ref_frame_sz", C.c_int64), ("base_off", C.c_int64), ("planes", PlaneGeom * 3)]
+
+
+REC_DTYPE = np.dtype([("buf_off", "<i4"), ("mv", "<i2"), ("dc", "<i2"), ("coeff_row", "<u4"),
+                      ("rowmask", "u1"), ("last_zzi", "u1"), ("refi", "u1"), ("pli_qti", "u1")])
+assert REC_DTYPE.itemsize == 16
+
+ENC_FRAG_DTYPE = np.dtype([("src_off", "<i4"), ("ref_off0", "<i4"), ("ref_off1", "<i4"), ("aux", "<i4")])
+INT32_MIN = -2 ** 31
+
+
+class DecFrame(C.Structure):
+    _fields_ = [("ref_idx", C.c_int32 * 3), ("lf_limit", C.c_int32), ("dc_quant", (C.c_uint16 * 2) * 3),
+                ("ncls", C.c_int32 * 4), ("nuncoded", C.c_int32), ("ncoeff_rows", C.c_int32),
+                ("recs", C.c_void_p), ("coeff_rows", C.c_void_p), ("uncoded_offs", C.c_void_p),
+                ("coded_map", C.c_void_p)]
+
+
+class FrameWork:
+    """One frame of decoder block work held in numpy arrays (keeps them alive)."""
+
+    def __init__(self, ref_idx, lf_limit, dc_quant, ncls, recs, rows, uncoded, coded_map):
+        self.ref_idx = tuple(int(x) for x in ref_idx)
+        self.lf_limit = int(lf_limit)
+        self.dc_quant = np.asarray(dc_quant, dtype=np.uint16).reshape(3, 2)
+        self.ncls = tuple(int(x) for x in ncls)
+        self.recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int16).reshape(-1, 8)
+        self.uncoded = np.ascontiguousarray(uncoded, dtype=np.int32)
+        self.coded_map = np.ascontiguousarray(coded_map, dtype=np.uint8)
+        assert sum(self.ncls) == len(self.recs)
+
+    def as_struct(self):
+        f = DecFrame()
+        for i in range(3):
+            f.ref_idx[i] = self.ref_idx[i]
+            for j in range(2):
+                f.dc_quant[i][j] = int(self.dc_quant[i, j])
+        f.lf_limit = self.lf_limit
+        for i in range(4):
+            f.ncls[i] = self.ncls[i]
+        f.nuncoded = len(self.uncoded)
+        f.ncoeff_rows = len(self.rows)
+        f.recs = self.recs.ctypes.data
+        f.coeff_rows = self.rows.ctypes.data
+        f.uncoded_offs = self.uncoded.ctypes.data
+        f.coded_map = self.coded_map.ctypes.data
+        return f
+
+    def to_dict(self, prefix):
+        return {prefix + "ref_idx": np.array(self.ref_idx, np.int32), prefix + "lf": np.array([self.lf_limit], np.int32),
+                prefix + "dcq": self.dc_quant, prefix + "ncls": np.array(self.ncls, np.int32),
+                prefix + "recs": self.recs, prefix + "rows": self.rows, prefix + "unc": self.uncoded,
+                prefix + "map": self.coded_map}
+
+    @staticmethod
+    def from_dict(d, prefix):
+        return FrameWork(d[prefix + "ref_idx"], d[prefix + "lf"][0], d[prefix + "dcq"], d[prefix + "ncls"],
+                         d[prefix + "recs"], d[prefix + "rows"], d[prefix + "unc"], d[prefix + "map"])
+
+
+# ---- library loading ------------------------------------------------------
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = os.path.join(ORACLE_DIR, "theora_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        L = C.CDLL(build_oracle())
+        L.oco_idct8x8.argtypes = [i16p, i16p, C.c_int]
+        L.oco_mv_offsets.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int16]
+        L.oco_state_frag_recon.argtypes = [u8p, u8p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int16,
+                                           i16p, C.c_int, C.c_uint16]
+        L.oco_lflim.argtypes = [C.c_int, C.c_int]
+        L.oco_loop_filter_init.argtypes = [C.POINTER(C.c_byte), C.c_int]
+        for fn in (L.oco_loop_filter_plane_seq, L.oco_loop_filter_plane_cells):
+            fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.oco_borders_fill_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oco_geometry_init.argtypes = [C.POINTER(Geometry), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oco_geometry_frag_buf_offs.argtypes = [C.POINTER(Geometry), i32p]
+        L.oco_dec_frame.argtypes = [C.POINTER(Geometry), u8p, C.POINTER(DecFrame), C.c_int]
+        L.oco_fdct8x8.argtypes = [i16p, i16p]
+        L.oco_enquant_init.argtypes = [i16p, u16p]
+        L.oco_quantize.argtypes = [i16p, i16p, u16p, i16p]
+        L.oco_frag_sub.argtypes = [i16p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oco_frag_sub_128.argtypes = [i16p, C.c_void_p, C.c_int]
+        for name in ("oco_frag_sad", "oco_frag_ssd"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            getattr(L, name).restype = C.c_uint
+        L.oco_frag_sad_thresh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
+        L.oco_frag_sad_thresh.restype = C.c_uint
+        L.oco_frag_sad2_thresh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
+        L.oco_frag_sad2_thresh.restype = C.c_uint
+        L.oco_frag_intra_sad.argtypes = [C.c_void_p, C.c_int]
+        L.oco_frag_intra_sad.restype = C.c_uint
+        L.oco_frag_satd.argtypes = [C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int]
+        L.oco_frag_satd.restype = C.c_uint
+        L.oco_frag_satd2.argtypes = [C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oco_frag_satd2.restype = C.c_uint
+        L.oco_frag_intra_satd.argtypes = [C.POINTER(C.c_int), C.c_void_p, C.c_int]
+        L.oco_frag_intra_satd.restype = C.c_uint
+        L.oco_frag_border_ssd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64]
+        L.oco_frag_border_ssd.restype = C.c_uint
+        L.oco_frag_copy2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oco_enc_metrics_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, u32p, i32p]
+        L.oco_enc_fdct_quant_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, u16p, i16p,
+                                               i16p, i16p, i32p]
+        _oracle = L
+    return _oracle
+
+
+def _bind_harness(L):
+    L.refh_encode_synth.restype = C.c_void_p
+    L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
+    L.refh_stream_free.argtypes = [C.c_void_p]
+    L.refh_stream_npackets.argtypes = [C.c_void_p]
+    L.refh_stream_packet_size.argtypes = [C.c_void_p, C.c_int]
+    L.refh_stream_packet_size.restype = C.c_long
+    L.refh_stream_blob_size.argtypes = [C.c_void_p]
+    L.refh_stream_blob_size.restype = C.c_long
+    L.refh_stream_to_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    L.refh_stream_to_blob.restype = C.c_long
+    L.refh_stream_from_blob.argtypes = [C.c_void_p, C.c_long]
+    L.refh_stream_from_blob.restype = C.c_void_p
+    L.refh_stream_append_data.argtypes = [C.c_void_p, C.c_void_p]
+    L.refh_dec_open.restype = C.c_void_p
+    L.refh_dec_open.argtypes = [C.c_void_p]
+    L.refh_dec_close.argtypes = [C.c_void_p]
+    L.refh_dec_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.refh_dec_next.argtypes = [C.c_void_p]
+    L.refh_dec_rewind.argtypes = [C.c_void_p]
+    L.refh_dec_hash.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.refh_dec_copy_frame.argtypes = [C.c_void_p, C.c_void_p]
+    L.refh_dec_copy_frame.restype = C.c_long
+    L.refh_dec_ctx.argtypes = [C.c_void_p]
+    L.refh_dec_ctx.restype = C.c_void_p
+    L.refh_decode_time.restype = C.c_double
+    L.refh_decode_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    L.refh_encode_time.restype = C.c_double
+    L.refh_encode_time.argtypes = [C.c_int] * 7 + [C.c_uint, C.POINTER(C.c_long)]
+    L.refh_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+_ref = {}
+
+
+def ref_available(kind="c"):
+    return os.path.exists(os.path.join(REF_DIR, "libth_%s.so" % kind))
+
+
+def ref(kind="c"):
+    """The compiled, unmodified reference (+ harness). kind: 'c' or 'asm'."""
+    if kind not in _ref:
+        L = _bind_harness(C.CDLL(os.path.join(REF_DIR, "libth_%s.so" % kind)))
+        if kind == "c":
+            L.oc_idct8x8_c.argtypes = [i16p, i16p, C.c_int]
+            L.oc_enc_fdct8x8_c.argtypes = [i16p, i16p]
+            L.oc_enc_enquant_table_init_c.argtypes = [C.c_void_p, u16p]
+            L.oc_enc_quantize_c.argtypes = [i16p, i16p, u16p, C.c_void_p]
+            L.refh_mv_offsets.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+            L.refh_state_frag_recon.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, i16p, C.c_int, C.c_int]
+            L.refh_loop_filter_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+            L.refh_loop_filter_table.argtypes = [C.POINTER(C.c_byte), C.c_int]
+            L.refh_borders_fill.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _ref[kind] = L
+    return _ref[kind]
+
+
+class Stream:
+    """Packets of one Theora stream held by a harness library."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+
+    @staticmethod
+    def encode(lib, w, h, nframes, quality=48, kf=64, speed=1, noise_shift=30, seed=12345, f0=0):
+        hnd = lib.refh_encode_synth(w, h, f0, nframes, quality, kf, speed, noise_shift, seed)
+        assert hnd, "encoder failed"
+        return Stream(lib, hnd)
+
+    def to_bytes(self):
+        n = self.lib.refh_stream_blob_size(self.h)
+        buf = (C.c_uint8 * n)()
+        assert self.lib.refh_stream_to_blob(self.h, buf, n) == n
+        return bytes(buf)
+
+    @staticmethod
+    def from_bytes(lib, blob):
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        hnd = lib.refh_stream_from_blob(buf, len(blob))
+        assert hnd, "bad stream blob"
+        return Stream(lib, hnd)
+
+    @property
+    def nframes(self):
+        return self.lib.refh_stream_npackets(self.h) - 3
+
+    def packet_sizes(self):
+        return [self.lib.refh_stream_packet_size(self.h, i) for i in range(self.lib.refh_stream_npackets(self.h))]
+
+    def free(self):
+        if self.h:
+            self.lib.refh_stream_free(self.h)
+            self.h = None
+
+
+class Decoder:
+    def __init__(self, lib, stream):
+        self.lib = lib
+        self.d = lib.refh_dec_open(stream.h)
+        assert self.d, "decoder open failed"
+        info = (C.c_int * 8)()
+        lib.refh_dec_info(self.d, info)
+        (self.fw, self.fh, self.pw, self.ph, self.px, self.py, self.fmt, self.nframes) = list(info)
+
+    def next(self):
+        return self.lib.refh_dec_next(self.d)
+
+    def hashes(self):
+        h = (C.c_uint64 * 3)()
+        self.lib.refh_dec_hash(self.d, h)
+        return tuple(int(x) for x in h)
+
+    def frame(self):
+        cw = self.fw >> (0 if self.fmt & 1 else 1)
+        ch = self.fh >> (0 if self.fmt & 2 else 1)
+        out = np.empty(self.fw * self.fh + 2 * cw * ch, np.uint8)
+        n = self.lib.refh_dec_copy_frame(self.d, out.ctypes.data)
+        assert n == out.size
+        return out
+
+    def close(self):
+        if self.d:
+            self.lib.refh_dec_close(self.d)
+            self.d = None
+
+
+def fnv1a64(arr):
+    """FNV-1a 64 over a uint8 array (vectorised in blocks is not possible; small inputs only)."""
+    h = 14695981039346656037
+    for b in np.asarray(arr, np.uint8).ravel().tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def make_geometry(fw, fh, fmt=0, nrefs=3):
+    g = Geometry()
+    r = oracle().oco_geometry_init(C.byref(g), fw, fh, fmt, nrefs)
+    assert r == 0, r
+    return g
+
+
+def planes_from_buffer(g, buf):
+    """Top-down picture planes (frame_width x frame_height etc.) out of one padded buffer."""
+    out = []
+    for pli in range(3):
+        p = g.planes[pli]
+        stride = -p.ystride
+        top_left = g.base_off + p.plane_off + (p.height - 1) * p.ystride
+        rows = np.lib.stride_tricks.as_strided(buf[top_left:], shape=(p.height, p.width), strides=(stride, 1))
+        out.append(np.ascontiguousarray(rows))
+    return out
