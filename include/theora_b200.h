@@ -141,18 +141,28 @@ OCG_API int  ocg_ctx_download_frame(ocg_ctx *ctx, int buf, uint8_t *host_buf);
 OCG_API int  ocg_ctx_fill_frame(ocg_ctx *ctx, int buf, int value);  /* oc_dec_init_dummy_frame, decode.c:2053 */
 
 /* ---- decode: one frame, host lists (the call the vtable back-end makes) -- */
-/* Pinned staging owned by the ctx; the recorder writes straight into it.
-   Capacities: nfrags recs, nfrags*8 rows, nfrags uncoded, nfrags map bytes. */
-OCG_API int  ocg_dec_staging(ocg_ctx *ctx, ocg_frag_rec **recs, int16_t **coeff_rows,
-                             int32_t **uncoded_offs, uint8_t **coded_map);
+/* Pinned staging owned by the ctx; the recorder writes straight into it (no
+   extra host copy).  One rec region per sparsity class, each with room for
+   nfrags records; nfrags*8 coefficient rows, nfrags uncoded offsets, nfrags
+   map bytes.  Valid until the next ocg_dec_submit on this ctx. */
+typedef struct ocg_staging {
+  ocg_frag_rec *recs[OCG_NCLS];
+  int16_t      *coeff_rows;
+  int32_t      *uncoded_offs;
+  uint8_t      *coded_map;
+} ocg_staging;
+OCG_API int  ocg_dec_staging(ocg_ctx *ctx, ocg_staging *out);
 /* H2D of the lists + recon/copy + loop filter + border fill on the ctx stream.
-   Asynchronous; pointers in `f` may be the staging pointers (no extra copy) or
-   any host memory (copied into staging first).  If host_out!=NULL the finished
-   SELF buffer is also copied back (ref_frame_sz bytes) on the same stream. */
+   Asynchronous.  With f->recs==NULL the lists are taken from the staging
+   regions handed out by the preceding ocg_dec_staging call (counts from `f`);
+   otherwise f's host arrays are copied into staging first.  If host_out!=NULL
+   the finished SELF buffer is also copied back (ref_frame_sz bytes) on the same
+   stream; call ocg_ctx_sync before reading it. */
 OCG_API int  ocg_dec_submit(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_out);
 
 /* ---- decode: device-resident frames, batched over independent streams ---- */
-OCG_API int  ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int device);
+OCG_API int  ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int nfrags,
+                             int device);
 OCG_API void ocg_pack_destroy(ocg_pack *p);
 OCG_API int  ocg_pack_nframes(const ocg_pack *p);
 /* One launch set for n independent (ctx, pack, frame) jobs of equal geometry on
@@ -193,20 +203,6 @@ OCG_API int ocg_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref
                                      const ocg_enc_frag *frags, int n,
                                      const uint16_t *dequant, const int16_t *enquant,
                                      int16_t *dct, int16_t *qdct, int32_t *nonzero, void *stream);
-/* One step of oc_mcenc_search_frame's square-pattern descent (mcenc.c:268-440)
-   for every macro block at once: evaluates the pattern sites around each MB's
-   current best vector with 4-block SAD on the ORIGINAL frames and moves to the
-   best site.  State arrays are per-MB. */
-typedef struct ocg_mb_search {
-  int32_t src_off[4];   /* luma block offsets of the macro block (mb_maps[mbi][0]) */
-  int16_t best_dx, best_dy;   /* current best full-pel vector                     */
-  uint32_t best_err;          /* its 16x16 SAD                                     */
-  int32_t  site;              /* last move (index into OC_SQUARE_SITES), 4 = start */
-  int32_t  done;
-} ocg_mb_search;
-OCG_API int ocg_mcenc_search_step(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
-                                  ocg_mb_search *mbs, int nmbs, void *stream);
-
 #ifdef __cplusplus
 }
 #endif

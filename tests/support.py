@@ -7,12 +7,16 @@ oracle/; the product package never does.
 import ctypes as C
 import os
 import subprocess
+import sys
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 u8p = C.POINTER(C.c_uint8)
 i16p = C.POINTER(C.c_int16)
@@ -25,76 +29,9 @@ def ptr(a, typ):
     return a.ctypes.data_as(typ)
 
 
-# ---- C-ABI structs (include/theora_b200.h) ---------------------------------
-class PlaneGeom(C.Structure):
-    _fields_ = [("nhfrags", C.c_int32), ("nvfrags", C.c_int32), ("froffset", C.c_int32),
-                ("nfrags", C.c_int32), ("ystride", C.c_int32), ("width", C.c_int32),
-                ("height", C.c_int32), ("hpad", C.c_int32), ("vpad", C.c_int32),
-                ("plane_off", C.c_int64)]
-
-
-class Geometry(C.Structure):
-    _fields_ = [("frame_width", C.c_int32), ("frame_height", C.c_int32), ("pixel_fmt", C.c_int32),
-                ("nrefs", C.c_int32), ("nfrags", C.c_int32), ("reserved", C.c_int32),
-                ("ref_frame_sz", C.c_int64), ("base_off", C.c_int64), ("planes", PlaneGeom * 3)]
-
-
-REC_DTYPE = np.dtype([("buf_off", "<i4"), ("mv", "<i2"), ("dc", "<i2"), ("coeff_row", "<u4"),
-                      ("rowmask", "u1"), ("last_zzi", "u1"), ("refi", "u1"), ("pli_qti", "u1")])
-assert REC_DTYPE.itemsize == 16
-
-ENC_FRAG_DTYPE = np.dtype([("src_off", "<i4"), ("ref_off0", "<i4"), ("ref_off1", "<i4"), ("aux", "<i4")])
-INT32_MIN = -2 ** 31
-
-
-class DecFrame(C.Structure):
-    _fields_ = [("ref_idx", C.c_int32 * 3), ("lf_limit", C.c_int32), ("dc_quant", (C.c_uint16 * 2) * 3),
-                ("ncls", C.c_int32 * 4), ("nuncoded", C.c_int32), ("ncoeff_rows", C.c_int32),
-                ("recs", C.c_void_p), ("coeff_rows", C.c_void_p), ("uncoded_offs", C.c_void_p),
-                ("coded_map", C.c_void_p)]
-
-
-class FrameWork:
-    """One frame of decoder block work held in numpy arrays (keeps them alive)."""
-
-    def __init__(self, ref_idx, lf_limit, dc_quant, ncls, recs, rows, uncoded, coded_map):
-        self.ref_idx = tuple(int(x) for x in ref_idx)
-        self.lf_limit = int(lf_limit)
-        self.dc_quant = np.asarray(dc_quant, dtype=np.uint16).reshape(3, 2)
-        self.ncls = tuple(int(x) for x in ncls)
-        self.recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
-        self.rows = np.ascontiguousarray(rows, dtype=np.int16).reshape(-1, 8)
-        self.uncoded = np.ascontiguousarray(uncoded, dtype=np.int32)
-        self.coded_map = np.ascontiguousarray(coded_map, dtype=np.uint8)
-        assert sum(self.ncls) == len(self.recs)
-
-    def as_struct(self):
-        f = DecFrame()
-        for i in range(3):
-            f.ref_idx[i] = self.ref_idx[i]
-            for j in range(2):
-                f.dc_quant[i][j] = int(self.dc_quant[i, j])
-        f.lf_limit = self.lf_limit
-        for i in range(4):
-            f.ncls[i] = self.ncls[i]
-        f.nuncoded = len(self.uncoded)
-        f.ncoeff_rows = len(self.rows)
-        f.recs = self.recs.ctypes.data
-        f.coeff_rows = self.rows.ctypes.data
-        f.uncoded_offs = self.uncoded.ctypes.data
-        f.coded_map = self.coded_map.ctypes.data
-        return f
-
-    def to_dict(self, prefix):
-        return {prefix + "ref_idx": np.array(self.ref_idx, np.int32), prefix + "lf": np.array([self.lf_limit], np.int32),
-                prefix + "dcq": self.dc_quant, prefix + "ncls": np.array(self.ncls, np.int32),
-                prefix + "recs": self.recs, prefix + "rows": self.rows, prefix + "unc": self.uncoded,
-                prefix + "map": self.coded_map}
-
-    @staticmethod
-    def from_dict(d, prefix):
-        return FrameWork(d[prefix + "ref_idx"], d[prefix + "lf"][0], d[prefix + "dcq"], d[prefix + "ncls"],
-                         d[prefix + "recs"], d[prefix + "rows"], d[prefix + "unc"], d[prefix + "map"])
+# ---- C-ABI structs come from the product package ---------------------------
+from theora_b200.abi import (DecFrame, ENC_FRAG_DTYPE, FrameWork, Geometry, INT32_MIN, PlaneGeom,  # noqa: E402,F401
+                             REC_DTYPE, cls_of_last_zzi)
 
 
 # ---- library loading ------------------------------------------------------

@@ -1,0 +1,168 @@
+"""ctypes view of include/theora_b200.h (structs, dtypes, prototypes).
+
+The shared library is the product; this module only describes its C ABI so
+Python callers (tests, bench.py, the stream driver) can reach it.  There is no
+Python or CPU implementation of any kernel here: if libtheora_b200.so is
+missing, or no CUDA device is present, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libtheora_b200.so")
+
+OCG_FRAME_GOLD, OCG_FRAME_PREV, OCG_FRAME_SELF = 0, 1, 2
+OCG_CLS_DC, OCG_CLS_3, OCG_CLS_10, OCG_CLS_FULL, OCG_NCLS = 0, 1, 2, 3, 4
+OCG_MET_SAD, OCG_MET_SATD, OCG_MET_INTRA_SATD, OCG_MET_SSD, OCG_MET_INTRA_SAD = 0, 1, 2, 3, 4
+INT32_MIN = -2 ** 31
+
+
+class PlaneGeom(C.Structure):
+    _fields_ = [("nhfrags", C.c_int32), ("nvfrags", C.c_int32), ("froffset", C.c_int32),
+                ("nfrags", C.c_int32), ("ystride", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("hpad", C.c_int32), ("vpad", C.c_int32),
+                ("plane_off", C.c_int64)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("frame_width", C.c_int32), ("frame_height", C.c_int32), ("pixel_fmt", C.c_int32),
+                ("nrefs", C.c_int32), ("nfrags", C.c_int32), ("reserved", C.c_int32),
+                ("ref_frame_sz", C.c_int64), ("base_off", C.c_int64), ("planes", PlaneGeom * 3)]
+
+
+class DecFrame(C.Structure):
+    _fields_ = [("ref_idx", C.c_int32 * 3), ("lf_limit", C.c_int32), ("dc_quant", (C.c_uint16 * 2) * 3),
+                ("ncls", C.c_int32 * 4), ("nuncoded", C.c_int32), ("ncoeff_rows", C.c_int32),
+                ("recs", C.c_void_p), ("coeff_rows", C.c_void_p), ("uncoded_offs", C.c_void_p),
+                ("coded_map", C.c_void_p)]
+
+
+class Staging(C.Structure):
+    _fields_ = [("recs", C.c_void_p * 4), ("coeff_rows", C.c_void_p), ("uncoded_offs", C.c_void_p),
+                ("coded_map", C.c_void_p)]
+
+
+REC_DTYPE = np.dtype([("buf_off", "<i4"), ("mv", "<i2"), ("dc", "<i2"), ("coeff_row", "<u4"),
+                      ("rowmask", "u1"), ("last_zzi", "u1"), ("refi", "u1"), ("pli_qti", "u1")])
+ENC_FRAG_DTYPE = np.dtype([("src_off", "<i4"), ("ref_off0", "<i4"), ("ref_off1", "<i4"), ("aux", "<i4")])
+assert REC_DTYPE.itemsize == 16 and ENC_FRAG_DTYPE.itemsize == 16
+
+
+def cls_of_last_zzi(last_zzi):
+    """state.c:967 / idct.c:327-329 class selection."""
+    lz = np.asarray(last_zzi)
+    return np.where(lz < 2, 0, np.where(lz <= 3, 1, np.where(lz <= 10, 2, 3))).astype(np.int32)
+
+
+class FrameWork:
+    """One frame of decoder block work held in numpy arrays (keeps them alive)."""
+
+    def __init__(self, ref_idx, lf_limit, dc_quant, ncls, recs, rows, uncoded, coded_map):
+        self.ref_idx = tuple(int(x) for x in ref_idx)
+        self.lf_limit = int(lf_limit)
+        self.dc_quant = np.asarray(dc_quant, dtype=np.uint16).reshape(3, 2).copy()
+        self.ncls = tuple(int(x) for x in ncls)
+        self.recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int16).reshape(-1, 8)
+        self.uncoded = np.ascontiguousarray(uncoded, dtype=np.int32)
+        self.coded_map = np.ascontiguousarray(coded_map, dtype=np.uint8)
+        assert sum(self.ncls) == len(self.recs)
+
+    def as_struct(self):
+        f = DecFrame()
+        for i in range(3):
+            f.ref_idx[i] = self.ref_idx[i]
+            for j in range(2):
+                f.dc_quant[i][j] = int(self.dc_quant[i, j])
+        f.lf_limit = self.lf_limit
+        for i in range(4):
+            f.ncls[i] = self.ncls[i]
+        f.nuncoded = len(self.uncoded)
+        f.ncoeff_rows = len(self.rows)
+        f.recs = self.recs.ctypes.data if len(self.recs) else None
+        f.coeff_rows = self.rows.ctypes.data if len(self.rows) else None
+        f.uncoded_offs = self.uncoded.ctypes.data if len(self.uncoded) else None
+        f.coded_map = self.coded_map.ctypes.data
+        return f
+
+    @property
+    def ncoded(self):
+        return len(self.recs)
+
+    def with_refs(self, ref_idx):
+        return FrameWork(ref_idx, self.lf_limit, self.dc_quant, self.ncls, self.recs, self.rows, self.uncoded,
+                         self.coded_map)
+
+    def to_dict(self, prefix):
+        return {prefix + "ref_idx": np.array(self.ref_idx, np.int32), prefix + "lf": np.array([self.lf_limit], np.int32),
+                prefix + "dcq": self.dc_quant, prefix + "ncls": np.array(self.ncls, np.int32),
+                prefix + "recs": self.recs, prefix + "rows": self.rows, prefix + "unc": self.uncoded,
+                prefix + "map": self.coded_map}
+
+    @staticmethod
+    def from_dict(d, prefix):
+        return FrameWork(d[prefix + "ref_idx"], d[prefix + "lf"][0], d[prefix + "dcq"], d[prefix + "ncls"],
+                         d[prefix + "recs"], d[prefix + "rows"], d[prefix + "unc"], d[prefix + "map"])
+
+
+_PROTOS = {
+    "ocg_version": (C.c_char_p, []),
+    "ocg_last_error": (C.c_char_p, []),
+    "ocg_device_count": (C.c_int, []),
+    "ocg_geometry_init": (C.c_int, [C.POINTER(Geometry), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ocg_geometry_frag_buf_offs": (None, [C.POINTER(Geometry), C.c_void_p]),
+    "ocg_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Geometry), C.c_int]),
+    "ocg_ctx_destroy": (None, [C.c_void_p]),
+    "ocg_ctx_geometry": (C.POINTER(Geometry), [C.c_void_p]),
+    "ocg_ctx_sync": (C.c_int, [C.c_void_p]),
+    "ocg_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "ocg_ctx_frame_devptr": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "ocg_ctx_upload_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ocg_ctx_download_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ocg_ctx_fill_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ocg_dec_staging": (C.c_int, [C.c_void_p, C.POINTER(Staging)]),
+    "ocg_dec_submit": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p]),
+    "ocg_pack_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecFrame), C.c_int, C.c_int, C.c_int]),
+    "ocg_pack_destroy": (None, [C.c_void_p]),
+    "ocg_pack_nframes": (C.c_int, [C.c_void_p]),
+    "ocg_dec_run_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int,
+                                    C.c_void_p]),
+    "ocg_set_stage_mask": (None, [C.c_int]),
+    "ocg_launch_count": (C.c_long, []),
+    "ocg_enc_metrics_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "ocg_enc_fdct_quant_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_PROTOS))
+
+_lib = None
+
+
+def lib():
+    """Loads libtheora_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C theora_b200/csrc` (this package has no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class OcgError(RuntimeError):
+    pass
+
+
+def check(code, what=""):
+    if code < 0:
+        raise OcgError("%s failed (%d): %s" % (what or "ocg call", code, lib().ocg_last_error().decode()))
+    return code

@@ -1,0 +1,527 @@
+/* C-ABI implementation: contexts, pinned staging, device-resident packs and the
+ * launch sequences.  See include/theora_b200.h for the contract. */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <new>
+#include <vector>
+#include "ocg_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long> g_launches{0};
+std::atomic<int> g_stage_mask{7};
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+
+#define CU(call)                                              \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return fail(OCG_ECUDA, #call, e_); \
+  } while (0)
+
+constexpr int kSlots = 2;
+
+struct Slot {
+  ocg_frag_rec *recs[OCG_NCLS] = {nullptr, nullptr, nullptr, nullptr};
+  int16_t *rows = nullptr;
+  int32_t *unc = nullptr;
+  uint8_t *map = nullptr;
+  OcgJobDev *job = nullptr; /* pinned */
+  cudaEvent_t consumed = nullptr;
+  bool busy = false;
+};
+
+} /* namespace */
+
+struct ocg_ctx {
+  ocg_geometry geom;
+  OcgGeomDev gdev;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t *frames = nullptr; /* nrefs * ref_frame_sz (+slack) */
+  /* device-side lists for single-frame submits */
+  ocg_frag_rec *d_recs = nullptr;
+  int16_t *d_rows = nullptr;
+  int32_t *d_unc = nullptr;
+  uint8_t *d_map = nullptr;
+  OcgJobDev *d_job = nullptr;
+  Slot slots[kSlots];
+  int cur_slot = 0;      /* slot handed out by the last ocg_dec_staging */
+  bool staged = false;
+};
+
+struct ocg_pack {
+  int device = 0;
+  int nframes = 0;
+  std::vector<ocg_dec_frame> frames; /* pointers are device pointers */
+  uint8_t *blob = nullptr;
+  size_t blob_sz = 0;
+};
+
+void ocg_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+/* ------------------------------------------------------------------------ */
+static void geom_to_dev(const ocg_geometry &g, OcgGeomDev &d) {
+  memset(&d, 0, sizeof(d));
+  int cell_rows = 0, border_rows = 0, maxcx = 0;
+  for (int pli = 0; pli < 3; pli++) {
+    const ocg_plane_geom &p = g.planes[pli];
+    OcgPlaneDev &q = d.p[pli];
+    q.nhfrags = p.nhfrags;
+    q.nvfrags = p.nvfrags;
+    q.froffset = p.froffset;
+    q.ystride = p.ystride;
+    q.width = p.width;
+    q.height = p.height;
+    q.hpad = p.hpad;
+    q.vpad = p.vpad;
+    q.plane_off = (int32_t)p.plane_off;
+    q.lo_off = (int32_t)(p.plane_off + (int64_t)(p.height - 1) * p.ystride);
+    q.cell_row0 = cell_rows;
+    cell_rows += p.nvfrags + 1;
+    border_rows += p.height + 2 * p.vpad;
+    if (p.nhfrags + 1 > maxcx) maxcx = p.nhfrags + 1;
+  }
+  d.qx = !(g.pixel_fmt & 1);
+  d.qy = !(g.pixel_fmt & 2);
+  d.cell_rows = cell_rows;
+  d.max_cells_x = maxcx;
+  d.border_rows = border_rows;
+}
+
+static void fill_job(OcgJobDev &j, uint8_t *frames, const ocg_geometry &g, const ocg_dec_frame &f,
+                     const ocg_frag_rec *recs, const int16_t *rows, const int32_t *unc, const uint8_t *map) {
+  memset(&j, 0, sizeof(j));
+  for (int i = 0; i < 3; i++)
+    j.base[i] = f.ref_idx[i] >= 0 ? frames + (int64_t)f.ref_idx[i] * g.ref_frame_sz + g.base_off : nullptr;
+  j.recs = recs;
+  j.rows = rows;
+  j.unc = unc;
+  j.coded = map;
+  int blk = 0, rec = 0;
+  const int per = OCG_RECON_THREADS / 4;
+  for (int c = 0; c < OCG_NCLS; c++) {
+    j.rec_start[c] = rec;
+    j.ncls[c] = f.ncls[c];
+    rec += f.ncls[c];
+    blk += (f.ncls[c] + per - 1) / per;
+    j.blk_end[c] = blk;
+  }
+  j.nunc = f.nuncoded;
+  blk += (f.nuncoded + per - 1) / per;
+  j.blk_end[4] = blk;
+  j.lf_limit = f.lf_limit;
+  for (int p = 0; p < 3; p++)
+    for (int q = 0; q < 2; q++) j.dcq[p][q] = f.dc_quant[p][q];
+}
+
+static int check_frame(const ocg_geometry &g, const ocg_dec_frame &f) {
+  long ncoded = 0;
+  for (int c = 0; c < OCG_NCLS; c++) {
+    if (f.ncls[c] < 0) return fail(OCG_EINVAL, "negative class count");
+    ncoded += f.ncls[c];
+  }
+  if (ncoded > g.nfrags || f.nuncoded < 0 || f.nuncoded > g.nfrags) return fail(OCG_EINVAL, "more fragments than the frame holds");
+  if (f.ncoeff_rows < 0 || f.ncoeff_rows > (long)g.nfrags * 8) return fail(OCG_EINVAL, "coefficient row count out of range");
+  if (f.ref_idx[OCG_FRAME_SELF] < 0 || f.ref_idx[OCG_FRAME_SELF] >= g.nrefs) return fail(OCG_EINVAL, "bad SELF buffer index");
+  for (int i = 0; i < 2; i++)
+    if (f.ref_idx[i] >= g.nrefs) return fail(OCG_EINVAL, "bad reference buffer index");
+  if (f.lf_limit < 0 || f.lf_limit > 127) return fail(OCG_EINVAL, "loop filter limit out of range");
+  return OCG_OK;
+}
+
+static void launch_stages(const OcgGeomDev &gd, const OcgJobDev *jobs, int njobs, int max_blocks, bool any_lf,
+                          cudaStream_t st) {
+  const int mask = g_stage_mask.load(std::memory_order_relaxed);
+  if (mask & 1) ocg_launch_recon(gd, jobs, njobs, max_blocks, st);
+  if ((mask & 2) && any_lf) ocg_launch_loop_filter(gd, jobs, njobs, st);
+  if (mask & 4) ocg_launch_borders(gd, jobs, njobs, st);
+}
+
+/* ------------------------------------------------------------------------ */
+extern "C" {
+
+OCG_API const char *ocg_version(void) { return "theora_b200 0.1 (sm_100a)"; }
+OCG_API const char *ocg_last_error(void) { return g_err; }
+
+OCG_API int ocg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
+OCG_API long ocg_launch_count(void) { return g_launches.load(); }
+
+/* state.c:424-470 (fragment planes), 545-671 (padded buffers + flip). */
+OCG_API int ocg_geometry_init(ocg_geometry *g, int fw, int fh, int pixel_fmt, int nrefs) {
+  if (g == nullptr) return fail(OCG_EFAULT, "NULL geometry");
+  if (fw <= 0 || fh <= 0 || (fw & 15) || (fh & 15) || fw >= 0x100000 || fh >= 0x100000)
+    return fail(OCG_EINVAL, "frame size must be a positive multiple of 16");
+  if (pixel_fmt != 0 && pixel_fmt != 2 && pixel_fmt != 3) return fail(OCG_EINVAL, "unknown pixel format");
+  if (nrefs < 3 || nrefs > 6) return fail(OCG_EINVAL, "nrefs must be 3..6");
+  const int hdec = !(pixel_fmt & 1), vdec = !(pixel_fmt & 2);
+  const int64_t ys = (int64_t)fw + 32, yr = (int64_t)fh + 32;
+  const int64_t cs = ((ys >> hdec) + 15) & ~(int64_t)15, cr = yr >> vdec;
+  const int64_t ysz = ys * yr, csz = cs * cr;
+  const int64_t yorg = 16 + 16 * ys;                          /* luma picture origin          */
+  const int64_t corg = (16 >> hdec) + (int64_t)(16 >> vdec) * cs; /* chroma origin inside its plane */
+  const int64_t adj = (-corg) & 15;                           /* keeps chroma data 16-aligned */
+  memset(g, 0, sizeof(*g));
+  g->frame_width = fw;
+  g->frame_height = fh;
+  g->pixel_fmt = pixel_fmt;
+  g->nrefs = nrefs;
+  g->ref_frame_sz = ysz + 2 * csz + 16;
+  if (g->ref_frame_sz * nrefs > ((int64_t)1 << 31) - 65536)
+    return fail(OCG_EIMPL, "frame pool exceeds 32-bit fragment offsets");
+  g->base_off = yorg + (int64_t)(fh - 1) * ys;
+  const int64_t origin[3] = {yorg, ysz + adj + corg, ysz + adj + csz + corg};
+  int fro = 0;
+  for (int pli = 0; pli < 3; pli++) {
+    ocg_plane_geom &p = g->planes[pli];
+    p.width = pli ? fw >> hdec : fw;
+    p.height = pli ? fh >> vdec : fh;
+    p.nhfrags = p.width >> 3;
+    p.nvfrags = p.height >> 3;
+    p.froffset = fro;
+    p.nfrags = p.nhfrags * p.nvfrags;
+    p.ystride = (int32_t)-(pli ? cs : ys);
+    p.hpad = pli ? 16 >> hdec : 16;
+    p.vpad = pli ? 16 >> vdec : 16;
+    /* bottom-left pixel (the reference addresses frames bottom-up) */
+    p.plane_off = origin[pli] + (int64_t)(p.height - 1) * (pli ? cs : ys) - g->base_off;
+    fro += p.nfrags;
+  }
+  g->nfrags = fro;
+  return OCG_OK;
+}
+
+OCG_API void ocg_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs) {
+  for (int pli = 0; pli < 3; pli++) {
+    const ocg_plane_geom &p = g->planes[pli];
+    int32_t *o = offs + p.froffset;
+    for (int fy = 0; fy < p.nvfrags; fy++)
+      for (int fx = 0; fx < p.nhfrags; fx++)
+        *o++ = (int32_t)(p.plane_off + (int64_t)fy * 8 * p.ystride + fx * 8);
+  }
+}
+
+/* ---- context ------------------------------------------------------------ */
+OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (Slot &s : c->slots) {
+    for (int k = 0; k < OCG_NCLS; k++) if (s.recs[k]) cudaFreeHost(s.recs[k]);
+    if (s.rows) cudaFreeHost(s.rows);
+    if (s.unc) cudaFreeHost(s.unc);
+    if (s.map) cudaFreeHost(s.map);
+    if (s.job) cudaFreeHost(s.job);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+  }
+  cudaFree(c->frames);
+  cudaFree(c->d_recs);
+  cudaFree(c->d_rows);
+  cudaFree(c->d_unc);
+  cudaFree(c->d_map);
+  cudaFree(c->d_job);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
+  if (out == nullptr || g == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(OCG_ECUDA, "no CUDA device (this library has no CPU fallback)", e);
+  if (device < 0 || device >= ndev) return fail(OCG_EINVAL, "device index out of range");
+  ocg_geometry chk;
+  int r = ocg_geometry_init(&chk, g->frame_width, g->frame_height, g->pixel_fmt, g->nrefs);
+  if (r < 0) return r;
+  if (memcmp(&chk, g, sizeof(chk)) != 0) return fail(OCG_EINVAL, "geometry was not produced by ocg_geometry_init");
+  CU(cudaSetDevice(device));
+  ocg_ctx *c = new (std::nothrow) ocg_ctx();
+  if (c == nullptr) return fail(OCG_ENOMEM, "out of memory");
+  c->geom = *g;
+  c->device = device;
+  geom_to_dev(*g, c->gdev);
+  const size_t nf = (size_t)g->nfrags;
+  const size_t pool = (size_t)g->ref_frame_sz * g->nrefs + 256;
+#define CUX(call)                                  \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) {                       \
+      ocg_ctx_destroy(c);                          \
+      return fail(OCG_ECUDA, #call, e_);           \
+    }                                              \
+  } while (0)
+  CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUX(cudaMalloc(&c->frames, pool));
+  CUX(cudaMemsetAsync(c->frames, 0x80, pool, c->stream));
+  CUX(cudaMalloc(&c->d_recs, nf * sizeof(ocg_frag_rec)));
+  CUX(cudaMalloc(&c->d_rows, nf * 8 * 16));
+  CUX(cudaMalloc(&c->d_unc, nf * sizeof(int32_t)));
+  CUX(cudaMalloc(&c->d_map, nf));
+  CUX(cudaMalloc(&c->d_job, sizeof(OcgJobDev)));
+  for (Slot &s : c->slots) {
+    for (int k = 0; k < OCG_NCLS; k++) CUX(cudaHostAlloc(&s.recs[k], nf * sizeof(ocg_frag_rec), cudaHostAllocDefault));
+    CUX(cudaHostAlloc(&s.rows, nf * 8 * 16, cudaHostAllocDefault));
+    CUX(cudaHostAlloc(&s.unc, nf * sizeof(int32_t), cudaHostAllocDefault));
+    CUX(cudaHostAlloc(&s.map, nf, cudaHostAllocDefault));
+    CUX(cudaHostAlloc(&s.job, sizeof(OcgJobDev), cudaHostAllocDefault));
+    CUX(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+  }
+  CUX(cudaStreamSynchronize(c->stream));
+#undef CUX
+  *out = c;
+  return OCG_OK;
+}
+
+OCG_API const ocg_geometry *ocg_ctx_geometry(const ocg_ctx *c) { return c ? &c->geom : nullptr; }
+OCG_API void *ocg_ctx_stream(ocg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *c, int buf) {
+  if (c == nullptr || buf < 0 || buf >= c->geom.nrefs) return nullptr;
+  return c->frames + (size_t)buf * c->geom.ref_frame_sz;
+}
+
+OCG_API int ocg_ctx_sync(ocg_ctx *c) {
+  if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (Slot &s : c->slots) s.busy = false;
+  return OCG_OK;
+}
+
+OCG_API int ocg_ctx_upload_frame(ocg_ctx *c, int buf, const uint8_t *host) {
+  if (c == nullptr || host == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->frames + (size_t)buf * c->geom.ref_frame_sz, host, (size_t)c->geom.ref_frame_sz,
+                     cudaMemcpyHostToDevice, c->stream));
+  return OCG_OK;
+}
+
+OCG_API int ocg_ctx_download_frame(ocg_ctx *c, int buf, uint8_t *host) {
+  if (c == nullptr || host == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(host, c->frames + (size_t)buf * c->geom.ref_frame_sz, (size_t)c->geom.ref_frame_sz,
+                     cudaMemcpyDeviceToHost, c->stream));
+  return OCG_OK;
+}
+
+OCG_API int ocg_ctx_fill_frame(ocg_ctx *c, int buf, int value) {
+  if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
+  if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->frames + (size_t)buf * c->geom.ref_frame_sz, value, (size_t)c->geom.ref_frame_sz, c->stream));
+  return OCG_OK;
+}
+
+/* ---- single-frame decode ------------------------------------------------ */
+static int acquire_slot(ocg_ctx *c) {
+  const int si = (c->cur_slot + 1) % kSlots;
+  Slot &s = c->slots[si];
+  if (s.busy) {
+    cudaError_t e = cudaEventSynchronize(s.consumed);
+    if (e != cudaSuccess) return fail(OCG_ECUDA, "cudaEventSynchronize", e);
+    s.busy = false;
+  }
+  c->cur_slot = si;
+  return OCG_OK;
+}
+
+OCG_API int ocg_dec_staging(ocg_ctx *c, ocg_staging *out) {
+  if (c == nullptr || out == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  int r = acquire_slot(c);
+  if (r < 0) return r;
+  Slot &s = c->slots[c->cur_slot];
+  for (int k = 0; k < OCG_NCLS; k++) out->recs[k] = s.recs[k];
+  out->coeff_rows = s.rows;
+  out->uncoded_offs = s.unc;
+  out->coded_map = s.map;
+  c->staged = true;
+  return OCG_OK;
+}
+
+OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out) {
+  if (c == nullptr || f == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  int r = check_frame(c->geom, *f);
+  if (r < 0) return r;
+  CU(cudaSetDevice(c->device));
+  long ncoded = 0;
+  for (int k = 0; k < OCG_NCLS; k++) ncoded += f->ncls[k];
+  const bool from_staging = c->staged && f->recs == nullptr && f->coeff_rows == nullptr &&
+                            f->uncoded_offs == nullptr && f->coded_map == nullptr;
+  if (!from_staging) {
+    if ((ncoded && !f->recs) || (f->ncoeff_rows && !f->coeff_rows) || (f->nuncoded && !f->uncoded_offs) ||
+        (f->lf_limit && !f->coded_map))
+      return fail(OCG_EFAULT, "NULL list pointer (and no staged lists)");
+    r = acquire_slot(c);
+    if (r < 0) return r;
+  }
+  Slot &s = c->slots[c->cur_slot];
+  c->staged = false;
+  cudaStream_t st = c->stream;
+  /* H2D: per-class rec regions land contiguously, sorted by class. */
+  size_t rec_at = 0;
+  for (int k = 0; k < OCG_NCLS; k++) {
+    const size_t n = (size_t)f->ncls[k];
+    if (n == 0) continue;
+    if (!from_staging) memcpy(s.recs[k], f->recs + rec_at, n * sizeof(ocg_frag_rec));
+    CU(cudaMemcpyAsync(c->d_recs + rec_at, s.recs[k], n * sizeof(ocg_frag_rec), cudaMemcpyHostToDevice, st));
+    rec_at += n;
+  }
+  if (f->ncoeff_rows) {
+    if (!from_staging) memcpy(s.rows, f->coeff_rows, (size_t)f->ncoeff_rows * 16);
+    CU(cudaMemcpyAsync(c->d_rows, s.rows, (size_t)f->ncoeff_rows * 16, cudaMemcpyHostToDevice, st));
+  }
+  if (f->nuncoded) {
+    if (!from_staging) memcpy(s.unc, f->uncoded_offs, (size_t)f->nuncoded * 4);
+    CU(cudaMemcpyAsync(c->d_unc, s.unc, (size_t)f->nuncoded * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (f->lf_limit) {
+    if (!from_staging) memcpy(s.map, f->coded_map, (size_t)c->geom.nfrags);
+    CU(cudaMemcpyAsync(c->d_map, s.map, (size_t)c->geom.nfrags, cudaMemcpyHostToDevice, st));
+  }
+  fill_job(*s.job, c->frames, c->geom, *f, c->d_recs, c->d_rows, c->d_unc, c->d_map);
+  CU(cudaMemcpyAsync(c->d_job, s.job, sizeof(OcgJobDev), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(s.consumed, st));
+  s.busy = true;
+  launch_stages(c->gdev, c->d_job, 1, s.job->blk_end[4], f->lf_limit != 0, st);
+  CU(cudaGetLastError());
+  if (host_out != nullptr) {
+    CU(cudaMemcpyAsync(host_out, c->frames + (size_t)f->ref_idx[OCG_FRAME_SELF] * c->geom.ref_frame_sz,
+                       (size_t)c->geom.ref_frame_sz, cudaMemcpyDeviceToHost, st));
+  }
+  return OCG_OK;
+}
+
+/* ---- device-resident packs ---------------------------------------------- */
+OCG_API void ocg_pack_destroy(ocg_pack *p) {
+  if (p == nullptr) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->blob);
+  delete p;
+}
+
+OCG_API int ocg_pack_nframes(const ocg_pack *p) { return p ? p->nframes : 0; }
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+OCG_API int ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int nfrags, int device) {
+  if (out == nullptr || frames == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  *out = nullptr;
+  if (nframes <= 0 || nfrags <= 0) return fail(OCG_EINVAL, "empty pack");
+  CU(cudaSetDevice(device));
+  size_t total = 0;
+  for (int i = 0; i < nframes; i++) {
+    const ocg_dec_frame &f = frames[i];
+    size_t nrec = 0;
+    for (int k = 0; k < OCG_NCLS; k++) nrec += (size_t)f.ncls[k];
+    total += align256(nrec * sizeof(ocg_frag_rec)) + align256((size_t)f.ncoeff_rows * 16) +
+             align256((size_t)f.nuncoded * 4) + align256((size_t)nfrags);
+  }
+  ocg_pack *p = new (std::nothrow) ocg_pack();
+  if (p == nullptr) return fail(OCG_ENOMEM, "out of memory");
+  p->device = device;
+  p->nframes = nframes;
+  p->blob_sz = total;
+  cudaError_t e = cudaMalloc(&p->blob, total ? total : 256);
+  if (e != cudaSuccess) { delete p; return fail(OCG_ECUDA, "cudaMalloc(pack)", e); }
+  size_t at = 0;
+  p->frames.resize((size_t)nframes);
+  for (int i = 0; i < nframes; i++) {
+    const ocg_dec_frame &f = frames[i];
+    ocg_dec_frame d = f;
+    size_t nrec = 0;
+    for (int k = 0; k < OCG_NCLS; k++) nrec += (size_t)f.ncls[k];
+    struct Part { const void *src; size_t n; const void **dst; } parts[4] = {
+        {f.recs, nrec * sizeof(ocg_frag_rec), (const void **)&d.recs},
+        {f.coeff_rows, (size_t)f.ncoeff_rows * 16, (const void **)&d.coeff_rows},
+        {f.uncoded_offs, (size_t)f.nuncoded * 4, (const void **)&d.uncoded_offs},
+        {f.coded_map, (size_t)nfrags, (const void **)&d.coded_map}};
+    for (Part &pt : parts) {
+      *pt.dst = p->blob + at;
+      if (pt.n) {
+        if (pt.src == nullptr) { ocg_pack_destroy(p); return fail(OCG_EFAULT, "NULL list pointer in pack frame"); }
+        e = cudaMemcpy(p->blob + at, pt.src, pt.n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { ocg_pack_destroy(p); return fail(OCG_ECUDA, "cudaMemcpy(pack)", e); }
+      }
+      at += align256(pt.n);
+    }
+    p->frames[(size_t)i] = d;
+  }
+  *out = p;
+  return OCG_OK;
+}
+
+struct BatchScratch {
+  OcgJobDev *h = nullptr; /* pinned */
+  OcgJobDev *d = nullptr;
+  int cap = 0;
+  int device = -1;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+static thread_local BatchScratch g_bs[2];
+static thread_local int g_bs_i = 0;
+
+OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, const int32_t *frame_idx, int n,
+                              void *stream) {
+  if (ctxs == nullptr || packs == nullptr || frame_idx == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  if (n <= 0) return fail(OCG_EINVAL, "empty batch");
+  ocg_ctx *c0 = ctxs[0];
+  if (c0 == nullptr) return fail(OCG_EFAULT, "NULL context");
+  CU(cudaSetDevice(c0->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c0->stream;
+  g_bs_i ^= 1;
+  BatchScratch &bs = g_bs[g_bs_i];
+  if (bs.pending) { CU(cudaEventSynchronize(bs.done)); bs.pending = false; }
+  if (bs.cap < n || bs.device != c0->device) {
+    if (bs.h) cudaFreeHost(bs.h);
+    if (bs.d) cudaFree(bs.d);
+    bs.h = nullptr; bs.d = nullptr; bs.cap = 0;
+    CU(cudaHostAlloc(&bs.h, sizeof(OcgJobDev) * (size_t)n, cudaHostAllocDefault));
+    CU(cudaMalloc(&bs.d, sizeof(OcgJobDev) * (size_t)n));
+    if (bs.done == nullptr) CU(cudaEventCreateWithFlags(&bs.done, cudaEventDisableTiming));
+    bs.cap = n;
+    bs.device = c0->device;
+  }
+  int max_blocks = 0;
+  bool any_lf = false;
+  for (int i = 0; i < n; i++) {
+    ocg_ctx *c = ctxs[i];
+    ocg_pack *p = packs[i];
+    if (c == nullptr || p == nullptr) return fail(OCG_EFAULT, "NULL job");
+    if (c->device != c0->device || p->device != c0->device) return fail(OCG_EINVAL, "batch spans devices");
+    if (memcmp(&c->geom, &c0->geom, sizeof(ocg_geometry)) != 0) return fail(OCG_EINVAL, "batch mixes geometries");
+    if (frame_idx[i] < 0 || frame_idx[i] >= p->nframes) return fail(OCG_EINVAL, "frame index out of range");
+    const ocg_dec_frame &f = p->frames[(size_t)frame_idx[i]];
+    int r = check_frame(c->geom, f);
+    if (r < 0) return r;
+    fill_job(bs.h[i], c->frames, c->geom, f, f.recs, f.coeff_rows, f.uncoded_offs, f.coded_map);
+    if (bs.h[i].blk_end[4] > max_blocks) max_blocks = bs.h[i].blk_end[4];
+    any_lf |= f.lf_limit != 0;
+  }
+  CU(cudaMemcpyAsync(bs.d, bs.h, sizeof(OcgJobDev) * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_stages(c0->gdev, bs.d, n, max_blocks, any_lf, st);
+  CU(cudaGetLastError());
+  /* the job table (host and device copy) is free again once the kernels ran */
+  CU(cudaEventRecord(bs.done, st));
+  bs.pending = true;
+  return OCG_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,456 @@
+/* Decode-side kernels for sm_100a.
+ *
+ *  ocg_recon_kernel   fused DC dequant + 8x8 iDCT + intra/inter/inter2
+ *                     reconstruction, plus the uncoded-fragment copy, one
+ *                     launch per batch of (stream, frame) jobs.  Replaces
+ *                     oc_state_frag_recon (reference lib/state.c:959),
+ *                     oc_idct8x8 (idct.c:301), oc_frag_recon_* (fragment.c:49-80)
+ *                     and oc_frag_copy_list (fragment.c:37).
+ *  ocg_lf_kernel      the normative loop filter (state.c:1002-1105) in its
+ *                     order-free "corner cell" form.
+ *  ocg_border_kernel  apron replication (state.c:770-835).
+ *
+ * Work mapping of the recon kernel: a fragment is handled by 4 adjacent lanes,
+ * lane l owning rows 2l and 2l+1, so a warp covers 8 fragments and a 256-thread
+ * CTA 64.  The two 1-D passes run in registers; the transposes between them
+ * are two __shfl_xor stages on 16-bit pairs; the final add/clamp uses the
+ * packed-halfword DPX instructions (VIADDMNMX.S16x2.RELU / VIMNMX.S16x2).
+ * All loads/stores are 64- or 128-bit.  There is no dense contraction here, so
+ * tensor cores are not used.
+ */
+#include "ocg_internal.h"
+
+namespace {
+
+constexpr int K1 = 64277, K2 = 60547, K3 = 54491, K4 = 46341, K5 = 36410, K6 = 25080, K7 = 12785;
+
+__device__ __forceinline__ int sext16(int v) { return (int)(short)v; }
+__device__ __forceinline__ int mulhi16(int k, int v) { return (k * v) >> 16; }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+__device__ __forceinline__ int lo16(uint32_t p) { return (int)(short)(p & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t p) { return (int)p >> 16; }
+
+/* idct.c:30-203.  NR = number of leading inputs that may be non-zero (the
+   reduced reference variants idct8_2/3/4 are exactly this with the trailing
+   inputs dropped).  Inputs are sign-extended int16; outputs are 32-bit sums
+   whose low 16 bits are the reference's (ogg_int16_t) results. */
+template <int NR>
+__device__ __forceinline__ void idct8(const int (&x)[8], int (&y)[8]) {
+  const int x0 = x[0];
+  const int x1 = NR > 1 ? x[1] : 0;
+  const int x2 = NR > 2 ? x[2] : 0;
+  const int x3 = NR > 3 ? x[3] : 0;
+  const int x4 = NR > 4 ? x[4] : 0;
+  const int x5 = NR > 5 ? x[5] : 0;
+  const int x6 = NR > 6 ? x[6] : 0;
+  const int x7 = NR > 7 ? x[7] : 0;
+  int e0, e1;
+  if (NR > 4) {
+    e0 = mulhi16(K4, sext16(x0 + x4));
+    e1 = mulhi16(K4, sext16(x0 - x4));
+  } else {
+    e0 = e1 = mulhi16(K4, x0);
+  }
+  const int e2 = mulhi16(K6, x2) - mulhi16(K2, x6);
+  const int e3 = mulhi16(K2, x2) + mulhi16(K6, x6);
+  const int o4 = mulhi16(K7, x1) - mulhi16(K1, x7);
+  const int o5 = mulhi16(K3, x5) - mulhi16(K5, x3);
+  const int o6 = mulhi16(K5, x5) + mulhi16(K3, x3);
+  const int o7 = mulhi16(K1, x1) + mulhi16(K7, x7);
+  const int s4 = o4 + o5;
+  const int s5 = mulhi16(K4, NR > 3 ? sext16(o4 - o5) : o4);
+  const int s7 = o7 + o6;
+  const int s6 = mulhi16(K4, NR > 3 ? sext16(o7 - o6) : o7);
+  const int a0 = e0 + e3, a3 = e0 - e3;
+  const int a1 = e1 + e2, a2 = e1 - e2;
+  const int b6 = s6 + s5, b5 = s6 - s5;
+  y[0] = a0 + s7;
+  y[1] = a1 + b6;
+  y[2] = a2 + b5;
+  y[3] = a3 + s4;
+  y[4] = a3 - s4;
+  y[5] = a2 - b5;
+  y[6] = a1 - b6;
+  y[7] = a0 - s7;
+}
+
+/* Register layout conventions for the 4-lane fragment group (lane l = 0..3):
+     L_row: lane owns rows 2l,2l+1; q[2m+r0] = (v[2l+r0][2m], v[2l+r0][2m+1])
+     L_col: lane owns cols 2l,2l+1; q[r]     = (v[r][2l],     v[r][2l+1])
+   The same two-stage exchange converts either layout into the other. */
+__device__ __forceinline__ void xpose(uint32_t (&q)[8], unsigned gmask, int l) {
+  const bool hi1 = (l & 2) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t s = hi1 ? q[i] : q[i + 4];
+    uint32_t r = __shfl_xor_sync(gmask, s, 2);
+    if (hi1) q[i] = r; else q[i + 4] = r;
+  }
+  const bool hi0 = (l & 1) != 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = (j & 1) | ((j & 2) << 1); /* 0,1,4,5 */
+    uint32_t s = hi0 ? q[i] : q[i | 2];
+    uint32_t r = __shfl_xor_sync(gmask, s, 1);
+    if (hi0) q[i] = r; else q[i | 2] = r;
+  }
+}
+
+/* 8 bytes at an arbitrary byte address out of the enclosing 16-byte window
+   (two aligned 64-bit loads, then byte permutes). */
+__device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p) {
+  const uintptr_t a = (uintptr_t)p;
+  const uint2 *w = (const uint2 *)(a & ~(uintptr_t)7);
+  const unsigned sh = (unsigned)(a & 7);
+  const uint2 w0 = __ldg(w);
+  if (sh == 0) return w0;
+  const uint2 w1 = __ldg(w + 1);
+  const unsigned sel = 0x3210u + 0x1111u * (sh & 3);
+  uint2 r;
+  if (sh < 4) {
+    r.x = __byte_perm(w0.x, w0.y, sel);
+    r.y = __byte_perm(w0.y, w1.x, sel);
+  } else {
+    r.x = __byte_perm(w0.y, w1.x, sel);
+    r.y = __byte_perm(w1.x, w1.y, sel);
+  }
+  return r;
+}
+
+/* state.c:846-957 in closed form: first tap truncates towards zero, second tap
+   (present iff a component has a fractional part) one step away from zero. */
+__device__ __forceinline__ void mv_taps(int mv, int qx, int qy, int ystride, int &off0, int &off1, bool &two) {
+  const int dx = (int)(signed char)(mv & 0xFF);
+  const int dy = mv >> 8;
+  const int ax = abs(dx), ay = abs(dy);
+  const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+  const int mx = sx * (ax >> (1 + qx)), my = sy * (ay >> (1 + qy));
+  const int fx = (ax & (qx ? 3 : 1)) ? sx : 0;
+  const int fy = (ay & (qy ? 3 : 1)) ? sy : 0;
+  off0 = my * ystride + mx;
+  off1 = off0 + fy * ystride + fx;
+  two = (fx | fy) != 0;
+}
+
+/* clamp255(res + pred) for one row held as four (even,odd) halfword pairs.
+   fragment.c:49-80.  The residue is first limited to <=255 so the packed add
+   cannot wrap; values above 255 saturate the result either way. */
+__device__ __forceinline__ uint2 recon_row(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint2 pred) {
+  const uint32_t c255 = 0x00FF00FFu;
+  const uint32_t p0 = __byte_perm(pred.x, 0, 0x4140), p1 = __byte_perm(pred.x, 0, 0x4342);
+  const uint32_t p2 = __byte_perm(pred.y, 0, 0x4140), p3 = __byte_perm(pred.y, 0, 0x4342);
+  const uint32_t o0 = __viaddmin_s16x2_relu(__vmins2(r0, c255), p0, c255);
+  const uint32_t o1 = __viaddmin_s16x2_relu(__vmins2(r1, c255), p1, c255);
+  const uint32_t o2 = __viaddmin_s16x2_relu(__vmins2(r2, c255), p2, c255);
+  const uint32_t o3 = __viaddmin_s16x2_relu(__vmins2(r3, c255), p3, c255);
+  return make_uint2(__byte_perm(o0, o1, 0x6420), __byte_perm(o2, o3, 0x6420));
+}
+
+__device__ __forceinline__ int plane_of(const OcgGeomDev &g, int off) {
+  return off >= g.p[2].lo_off ? 2 : (off >= g.p[1].lo_off ? 1 : 0);
+}
+
+/* One coded fragment.  CLS follows state.c:967 / idct.c:327-329. */
+template <int CLS>
+__device__ __forceinline__ void recon_fragment(const OcgGeomDev &g, const OcgJobDev &job, int reci, int l,
+                                               unsigned gmask) {
+  const int4 rw = __ldg((const int4 *)(job.recs + reci));
+  const int buf_off = rw.x;
+  const int mv = rw.y << 16 >> 16;
+  const int dc = rw.y >> 16;
+  const unsigned coeff_row = (unsigned)rw.z;
+  const unsigned rowmask = (unsigned)rw.w & 0xFFu;
+  const int refi = (rw.w >> 16) & 0xFF;
+  const int pli = (rw.w >> 24) & 3;
+  const int qti = (rw.w >> 26) & 1;
+  const int ystride = g.p[pli].ystride;
+  const int dcq = job.dcq[pli][qti];
+  uint32_t q[8];
+
+  if (CLS == OCG_CLS_DC) {
+    /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block. */
+    const int p = sext16((dc * dcq + 15) >> 5);
+    const uint32_t pp = pack16(p, p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = pp;
+  } else {
+    constexpr int NR = CLS == OCG_CLS_3 ? 2 : (CLS == OCG_CLS_10 ? 4 : 8);
+    /* ---- load this lane's two coefficient rows (if stored) ---- */
+    int xa[8], xb[8];
+    {
+      const int ra = 2 * l, rb = 2 * l + 1;
+      uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+      const bool row_in_class = ra < NR;
+      if (row_in_class) {
+        const uint4 *rows = (const uint4 *)job.rows + coeff_row;
+        if (rowmask >> ra & 1) wa = __ldg(rows + __popc(rowmask & ((1u << ra) - 1u)));
+        if (rowmask >> rb & 1) wb = __ldg(rows + __popc(rowmask & ((1u << rb) - 1u)));
+      }
+      xa[0] = lo16(wa.x); xa[1] = hi16(wa.x); xa[2] = lo16(wa.y); xa[3] = hi16(wa.y);
+      xa[4] = lo16(wa.z); xa[5] = hi16(wa.z); xa[6] = lo16(wa.w); xa[7] = hi16(wa.w);
+      xb[0] = lo16(wb.x); xb[1] = hi16(wb.x); xb[2] = lo16(wb.y); xb[3] = hi16(wb.y);
+      xb[4] = lo16(wb.z); xb[5] = hi16(wb.z); xb[6] = lo16(wb.w); xb[7] = hi16(wb.w);
+      /* The reduced transforms read a triangular footprint only
+         (idct.c:213-275): row r uses its first NR-r coefficients. */
+      if (CLS == OCG_CLS_3) {
+        xb[1] = 0;
+      } else if (CLS == OCG_CLS_10) {
+        if (l == 0) { xb[3] = 0; }
+        else { xa[2] = 0; xa[3] = 0; xb[1] = 0; xb[2] = 0; xb[3] = 0; }
+      }
+      /* DC dequant, state.c:978 */
+      if (l == 0) xa[0] = sext16(dc * dcq);
+    }
+    /* ---- row pass (idct.c:313: rows of x into columns of w) ---- */
+    int ya[8], yb[8];
+    idct8<NR>(xa, ya);
+    idct8<NR>(xb, yb);
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      q[2 * m] = pack16(ya[2 * m], ya[2 * m + 1]);
+      q[2 * m + 1] = pack16(yb[2 * m], yb[2 * m + 1]);
+    }
+    xpose(q, gmask, l);
+    /* ---- column pass + (v+8)>>4 (idct.c:315-317) ---- */
+#pragma unroll
+    for (int r = 0; r < 8; r++) { xa[r] = lo16(q[r]); xb[r] = hi16(q[r]); }
+    idct8<NR>(xa, ya);
+    idct8<NR>(xb, yb);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int va = (sext16(ya[r]) + 8) >> 4;
+      const int vb = (sext16(yb[r]) + 8) >> 4;
+      q[r] = pack16(va, vb);
+    }
+    xpose(q, gmask, l);
+  }
+
+  /* ---- prediction + clamp + store, rows 2l and 2l+1 ---- */
+  uint8_t *dst = job.base[OCG_FRAME_SELF] + buf_off + (2 * l) * ystride;
+  uint2 pa, pb;
+  if (refi == OCG_FRAME_SELF) {
+    pa = pb = make_uint2(0x80808080u, 0x80808080u);
+  } else {
+    const uint8_t *ref = job.base[refi] + buf_off + (2 * l) * ystride;
+    int off0, off1;
+    bool two;
+    mv_taps(mv, pli ? g.qx : 0, pli ? g.qy : 0, ystride, off0, off1, two);
+    pa = load8_unaligned(ref + off0);
+    pb = load8_unaligned(ref + off0 + ystride);
+    if (two) {
+      const uint2 ta = load8_unaligned(ref + off1);
+      const uint2 tb = load8_unaligned(ref + off1 + ystride);
+      pa.x = __vhaddu4(pa.x, ta.x); pa.y = __vhaddu4(pa.y, ta.y);
+      pb.x = __vhaddu4(pb.x, tb.x); pb.y = __vhaddu4(pb.y, tb.y);
+    }
+  }
+  const uint2 oa = recon_row(q[0], q[2], q[4], q[6], pa);
+  const uint2 ob = recon_row(q[1], q[3], q[5], q[7], pb);
+  *(uint2 *)dst = oa;
+  *(uint2 *)(dst + ystride) = ob;
+}
+
+__global__ void __launch_bounds__(OCG_RECON_THREADS)
+ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  const OcgJobDev &job = jobs[blockIdx.y];
+  const int b = (int)blockIdx.x;
+  if (b >= job.blk_end[4]) return;
+  const int lane = threadIdx.x & 31;
+  const int l = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  const int slot = threadIdx.x >> 2; /* fragment slot inside the CTA, 0..63 */
+  int cls = 0;
+  while (b >= job.blk_end[cls]) cls++;
+  const int idx = (b - (cls ? job.blk_end[cls - 1] : 0)) * (OCG_RECON_THREADS / 4) + slot;
+  if (cls == 4) {
+    /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
+    if (idx >= job.nunc) return;
+    const int off = __ldg(job.unc + idx);
+    const int ystride = g.p[plane_of(g, off)].ystride;
+    const uint8_t *src = job.base[OCG_FRAME_PREV] + off + (2 * l) * ystride;
+    uint8_t *dst = job.base[OCG_FRAME_SELF] + off + (2 * l) * ystride;
+    const uint2 a = __ldg((const uint2 *)src);
+    const uint2 c = __ldg((const uint2 *)(src + ystride));
+    *(uint2 *)dst = a;
+    *(uint2 *)(dst + ystride) = c;
+    return;
+  }
+  if (idx >= job.ncls[cls]) return;
+  const int reci = job.rec_start[cls] + idx;
+  switch (cls) {
+    case OCG_CLS_DC: recon_fragment<OCG_CLS_DC>(g, job, reci, l, gmask); break;
+    case OCG_CLS_3: recon_fragment<OCG_CLS_3>(g, job, reci, l, gmask); break;
+    case OCG_CLS_10: recon_fragment<OCG_CLS_10>(g, job, reci, l, gmask); break;
+    default: recon_fragment<OCG_CLS_FULL>(g, job, reci, l, gmask); break;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Loop filter.  One thread per 8x8 "cell" centred on a fragment corner
+   (pixel columns [8cx-4,8cx+4), rows [8cy-4,8cy+4) of a plane).  Every filter
+   line of state.c:1002-1031 lies inside exactly one cell; the lines through
+   the central 4x4 patch are applied in the order the raster scan of
+   state.c:1083-1104 reaches them, everything else is independent. */
+
+__device__ __forceinline__ int lflim(int r, int lim) {
+  /* closed form of the table built by oc_loop_filter_init_c, state.c:1036 */
+  const int a = abs(r);
+  const int v = a < lim ? a : max(2 * lim - a, 0);
+  return r < 0 ? -v : v;
+}
+
+/* One filter line on four samples a,b,c,d straddling the edge (b|c adjacent). */
+__device__ __forceinline__ void lf4(int a, int &b, int &c, int d, int lim) {
+  const int f = lflim((a - d + 3 * (c - b) + 4) >> 3, lim);
+  b = min(max(b + f, 0), 255);
+  c = min(max(c - f, 0), 255);
+}
+
+struct Cell {
+  uint32_t w[8][2]; /* w[row][0] = cols 0..3, w[row][1] = cols 4..7 (cell-local) */
+};
+
+__device__ __forceinline__ int getb(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xFFu); }
+__device__ __forceinline__ uint32_t setb(uint32_t w, int i, int v) {
+  return (w & ~(0xFFu << (8 * i))) | ((uint32_t)v << (8 * i));
+}
+
+/* vertical edge through the cell centre, cell rows [r0,r1) : samples cols 2..5 */
+__device__ __forceinline__ void cell_vline(Cell &c, int r, int lim) {
+  int a = getb(c.w[r][0], 2), b = getb(c.w[r][0], 3), cc = getb(c.w[r][1], 0), d = getb(c.w[r][1], 1);
+  lf4(a, b, cc, d, lim);
+  c.w[r][0] = setb(c.w[r][0], 3, b);
+  c.w[r][1] = setb(c.w[r][1], 0, cc);
+}
+
+/* horizontal edge through the cell centre, cell column col: samples rows 2..5.
+   Bottom-up rows: row index grows with the fragment row, and loop_filter_v
+   reads pix[-2*ystride .. +ystride], i.e. cell rows 2,3 | 4,5. */
+template <int COL>
+__device__ __forceinline__ void cell_hline(Cell &c, int lim) {
+  constexpr int h = COL >> 2, i = COL & 3;
+  int a = getb(c.w[2][h], i), b = getb(c.w[3][h], i), cc = getb(c.w[4][h], i), d = getb(c.w[5][h], i);
+  lf4(a, b, cc, d, lim);
+  c.w[3][h] = setb(c.w[3][h], i, b);
+  c.w[4][h] = setb(c.w[4][h], i, cc);
+}
+
+__global__ void __launch_bounds__(64)
+ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  const OcgJobDev &job = jobs[blockIdx.z];
+  const int lim = job.lf_limit;
+  if (lim == 0) return;
+  const int crow = (int)blockIdx.y;
+  const int pli = crow >= g.p[2].cell_row0 ? 2 : (crow >= g.p[1].cell_row0 ? 1 : 0);
+  const OcgPlaneDev &P = g.p[pli];
+  const int cy = crow - P.cell_row0;
+  const int cx = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int nh = P.nhfrags, nv = P.nvfrags;
+  if (cx > nh) return;
+  /* coded flags of the four fragments around the corner */
+  const uint8_t *cm = job.coded + P.froffset;
+  const bool inl = cx > 0, inr = cx < nh, ind = cy > 0, inu = cy < nv;
+  const bool A = inl && ind && cm[(cy - 1) * nh + cx - 1];
+  const bool B = inr && ind && cm[(cy - 1) * nh + cx];
+  const bool Cc = inl && inu && cm[cy * nh + cx - 1];
+  const bool D = inr && inu && cm[cy * nh + cx];
+  const bool vd = inl && inr && ind && (A || B);   /* vertical edge below the corner   */
+  const bool vu = inl && inr && inu && (Cc || D);  /* vertical edge above the corner   */
+  const bool hl = ind && inu && inl && (A || Cc);  /* horizontal edge left of corner   */
+  const bool hr = ind && inu && inr && (B || D);   /* horizontal edge right of corner  */
+  if (!(vd || vu || hl || hr)) return;
+  const int ystride = P.ystride;
+  uint8_t *o = job.base[OCG_FRAME_SELF] + P.plane_off + (cy * 8 - 4) * ystride + (cx * 8 - 4);
+  /* rows/cols of the cell that exist inside the plane */
+  const int rlo = ind ? 0 : 4, rhi = inu ? 8 : 4;
+  Cell c;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    c.w[r][0] = c.w[r][1] = 0;
+    if (r >= rlo && r < rhi) {
+      const uint32_t *row = (const uint32_t *)(o + r * ystride);
+      if (inl) c.w[r][0] = row[0];
+      if (inr) c.w[r][1] = row[1];
+    }
+  }
+  /* independent lines */
+  if (vd) { cell_vline(c, 0, lim); cell_vline(c, 1, lim); }
+  if (vu) { cell_vline(c, 6, lim); cell_vline(c, 7, lim); }
+  if (hl) { cell_hline<0>(c, lim); cell_hline<1>(c, lim); }
+  if (hr) { cell_hline<6>(c, lim); cell_hline<7>(c, lim); }
+  /* ordered lines through the central patch ("loop filter order") */
+  if (vd && !B) { cell_vline(c, 2, lim); cell_vline(c, 3, lim); }
+  if (hl && !Cc) { cell_hline<2>(c, lim); cell_hline<3>(c, lim); }
+  if (vd && B) { cell_vline(c, 2, lim); cell_vline(c, 3, lim); }
+  if (hr && !D) { cell_hline<4>(c, lim); cell_hline<5>(c, lim); }
+  if (hl && Cc) { cell_hline<2>(c, lim); cell_hline<3>(c, lim); }
+  if (vu && !D) { cell_vline(c, 4, lim); cell_vline(c, 5, lim); }
+  if (vu && D) { cell_vline(c, 4, lim); cell_vline(c, 5, lim); }
+  if (hr && D) { cell_hline<4>(c, lim); cell_hline<5>(c, lim); }
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (r >= rlo && r < rhi) {
+      uint32_t *row = (uint32_t *)(o + r * ystride);
+      if (inl) row[0] = c.w[r][0];
+      if (inr) row[1] = c.w[r][1];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Apron replication, state.c:770-835: every apron byte takes the nearest
+   picture pixel (rows first, then full-width caps == clamp in both axes).
+   One thread per 4 apron/plane bytes of a padded row; rows of all three planes
+   are fused into blockIdx.y. */
+__global__ void __launch_bounds__(128)
+ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  const OcgJobDev &job = jobs[blockIdx.z];
+  int prow = (int)blockIdx.y;
+  int pli = 0;
+  while (pli < 2 && prow >= g.p[pli].height + 2 * g.p[pli].vpad) {
+    prow -= g.p[pli].height + 2 * g.p[pli].vpad;
+    pli++;
+  }
+  const OcgPlaneDev &P = g.p[pli];
+  const int y = prow - P.vpad;                 /* bottom-up row, may be outside [0,height) */
+  const int ys = min(max(y, 0), P.height - 1); /* source row */
+  const bool cap = y != ys;
+  const int fullw = P.width + 2 * P.hpad;
+  uint8_t *base = job.base[OCG_FRAME_SELF] + P.plane_off;
+  const uint8_t *srow = base + ys * P.ystride;
+  uint8_t *drow = base + y * P.ystride;
+  const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4 - P.hpad;
+  if (x4 >= P.width + P.hpad) return;
+  (void)fullw;
+  const bool side = x4 < 0 || x4 >= P.width;
+  if (!cap && !side) return; /* interior pixel of a picture row: nothing to do */
+  uint32_t v;
+  if (x4 < 0) v = 0x01010101u * srow[0];
+  else if (x4 >= P.width) v = 0x01010101u * srow[P.width - 1];
+  else v = *(const uint32_t *)(srow + x4);
+  *(uint32_t *)(drow + x4) = v;
+}
+
+} /* namespace */
+
+void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, int max_blocks, cudaStream_t st) {
+  if (max_blocks <= 0 || njobs <= 0) return;
+  dim3 grid((unsigned)max_blocks, (unsigned)njobs);
+  ocg_recon_kernel<<<grid, OCG_RECON_THREADS, 0, st>>>(g, jobs);
+  ocg_count_launch(1);
+}
+
+void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return;
+  dim3 grid((unsigned)((g.max_cells_x + 63) / 64), (unsigned)g.cell_rows, (unsigned)njobs);
+  ocg_lf_kernel<<<grid, 64, 0, st>>>(g, jobs);
+  ocg_count_launch(1);
+}
+
+void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return;
+  const int maxw4 = (g.p[0].width + 2 * g.p[0].hpad + 3) / 4;
+  dim3 grid((unsigned)((maxw4 + 127) / 128), (unsigned)g.border_rows, (unsigned)njobs);
+  ocg_border_kernel<<<grid, 128, 0, st>>>(g, jobs);
+  ocg_count_launch(1);
+}

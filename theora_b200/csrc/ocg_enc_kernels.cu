@@ -1,0 +1,320 @@
+/* Encode-side batch kernels for sm_100a (reference lib/encint.h:292-326).
+ *
+ *  ocg_enc_metrics_kernel     SAD / SAD2, SATD / SATD2, intra SATD, SSD and
+ *                             intra SAD of 8x8 blocks (encfrag.c:42-366), one
+ *                             block per 8-lane warp slice (lane = pixel row),
+ *                             VABSDIFF4 for the SADs, shuffle butterflies for
+ *                             the column Hadamard and the reductions.
+ *  ocg_enc_fdct_quant_kernel  frag_sub / sub_128 / copy2+sub (encfrag.c:21-40,
+ *                             368) -> oc_enc_fdct8x8 (fdct.c:128) ->
+ *                             oc_enc_quantize (enquant.c:220), zig-zag order
+ *                             output staged through shared memory so global
+ *                             stores are 128-bit.
+ * The serial mode decision / tokeniser that consumes these results stays on
+ * the host (analyze.c, tokenize.c).
+ */
+#include <climits>
+#include "ocg_internal.h"
+
+namespace {
+
+constexpr int K1 = 64277, K2 = 60547, K3 = 54491, K5 = 36410, K6 = 25080, K7 = 12785;
+
+__device__ __forceinline__ uint2 ld8u(const uint8_t *p) {
+  const uintptr_t a = (uintptr_t)p;
+  const uint2 *w = (const uint2 *)(a & ~(uintptr_t)7);
+  const unsigned sh = (unsigned)(a & 7);
+  const uint2 w0 = __ldg(w);
+  if (sh == 0) return w0;
+  const uint2 w1 = __ldg(w + 1);
+  const unsigned sel = 0x3210u + 0x1111u * (sh & 3);
+  uint2 r;
+  if (sh < 4) { r.x = __byte_perm(w0.x, w0.y, sel); r.y = __byte_perm(w0.y, w1.x, sel); }
+  else { r.x = __byte_perm(w0.y, w1.x, sel); r.y = __byte_perm(w1.x, w1.y, sel); }
+  return r;
+}
+
+__device__ __forceinline__ void unpack8(uint2 v, int (&o)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    o[i] = (int)((v.x >> (8 * i)) & 0xFF);
+    o[4 + i] = (int)((v.y >> (8 * i)) & 0xFF);
+  }
+}
+
+/* predictor row: none (0), one tap, or (a+b)>>1 of two taps */
+__device__ __forceinline__ bool load_pred_row(const uint8_t *ref_base, const ocg_enc_frag &f, int row, int ystride,
+                                              uint2 &pred) {
+  if (f.ref_off0 == INT_MIN) { pred = make_uint2(0, 0); return false; }
+  pred = ld8u(ref_base + f.ref_off0 + row * ystride);
+  if (f.ref_off1 != INT_MIN) {
+    const uint2 t = ld8u(ref_base + f.ref_off1 + row * ystride);
+    pred.x = __vhaddu4(pred.x, t.x);
+    pred.y = __vhaddu4(pred.y, t.y);
+  }
+  return true;
+}
+
+__device__ __forceinline__ void hadamard8(int (&t)[8]) {
+  const int a0 = t[0] + t[4], a4 = t[0] - t[4], a1 = t[1] + t[5], a5 = t[1] - t[5];
+  const int a2 = t[2] + t[6], a6 = t[2] - t[6], a3 = t[3] + t[7], a7 = t[3] - t[7];
+  const int b0 = a0 + a2, b2 = a0 - a2, b1 = a1 + a3, b3 = a1 - a3;
+  const int b4 = a4 + a6, b6 = a4 - a6, b5 = a5 + a7, b7 = a5 - a7;
+  t[0] = b0 + b1; t[1] = b0 - b1; t[2] = b2 + b3; t[3] = b2 - b3;
+  t[4] = b4 + b5; t[5] = b4 - b5; t[6] = b6 + b7; t[7] = b6 - b7;
+}
+
+__device__ __forceinline__ int group_sum8(int v, unsigned gmask) {
+  v += __shfl_xor_sync(gmask, v, 4);
+  v += __shfl_xor_sync(gmask, v, 2);
+  v += __shfl_xor_sync(gmask, v, 1);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base,
+                       int ystride, const ocg_enc_frag *__restrict__ frags, int n, uint32_t *__restrict__ out_val,
+                       int32_t *__restrict__ out_dc) {
+  const int fi = (int)(blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3));
+  if (fi >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int row = lane & 7;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int4 fw = __ldg((const int4 *)(frags + fi));
+  ocg_enc_frag f;
+  f.src_off = fw.x; f.ref_off0 = fw.y; f.ref_off1 = fw.z; f.aux = fw.w;
+  const uint2 s = ld8u(src_base + f.src_off + row * ystride);
+  uint2 p;
+  uint32_t val = 0;
+  int dc = 0;
+  if (metric == OCG_MET_SAD) {
+    load_pred_row(ref_base, f, row, ystride, p);
+    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, p.x) + __vsadu4(s.y, p.y)), gmask);
+  } else if (metric == OCG_MET_SSD) {
+    load_pred_row(ref_base, f, row, ystride, p);
+    int a[8], b[8], acc = 0;
+    unpack8(s, a);
+    unpack8(p, b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc += (a[i] - b[i]) * (a[i] - b[i]);
+    val = (uint32_t)group_sum8(acc, gmask);
+  } else if (metric == OCG_MET_INTRA_SAD) {
+    /* encfrag.c:88-107: dc=(sum+32)>>6, then sum |src-dc| */
+    const int tot = group_sum8((int)(__vsadu4(s.x, 0) + __vsadu4(s.y, 0)), gmask);
+    const uint32_t m = 0x01010101u * (uint32_t)((tot + 32) >> 6);
+    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, m) + __vsadu4(s.y, m)), gmask);
+  } else {
+    /* SATD family, encfrag.c:109-336: 2-D Hadamard of the residual, sum of
+       magnitudes without the DC term, DC returned separately. */
+    if (metric == OCG_MET_INTRA_SATD) p = make_uint2(0, 0);
+    else load_pred_row(ref_base, f, row, ystride, p);
+    int a[8], b[8];
+    unpack8(s, a);
+    unpack8(p, b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] -= b[i];
+    hadamard8(a);
+    /* column transform across the 8 lanes of the slice */
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) {
+      const bool up = (row & d) != 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int o = __shfl_xor_sync(gmask, a[i], d);
+        a[i] = up ? o - a[i] : a[i] + o;
+      }
+    }
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc += abs(a[i]);
+    if (row == 0) { dc = a[0]; acc -= abs(a[0]); }
+    val = (uint32_t)group_sum8(acc, gmask);
+  }
+  if (row == 0) {
+    out_val[fi] = val;
+    if (out_dc != nullptr) out_dc[fi] = dc;
+  }
+}
+
+/* fdct.c:28-120 */
+__device__ __forceinline__ int fd_exp(int t, int bias) { return ((27146 * t + bias) >> 16) + t + (t != 0); }
+
+__device__ __forceinline__ void fdct8(const int (&x)[8], int (&y)[8]) {
+  const int a0 = x[0] + x[7], a7 = x[0] - x[7], a1 = x[1] + x[6], a6 = x[1] - x[6];
+  const int a2 = x[2] + x[5], a5 = x[2] - x[5], a3 = x[3] + x[4], a4 = x[3] - x[4];
+  const int b0 = a0 + a3, b3 = a0 - a3, b1 = a1 + a2, b2 = a1 - a2;
+  const int b6 = a6 + a5, b5 = a6 - a5;
+  int s = fd_exp(b5, 0xB500) >> 1;
+  const int c4 = a4 + s, c5 = a4 - s;
+  s = fd_exp(b6, 0xB500) >> 1;
+  const int c7 = a7 + s, c6 = a7 - s;
+  const int r = fd_exp(b0, 0x4000);
+  s = fd_exp(b1, 0xB500);
+  int u = (r + s) >> 1;
+  y[0] = u;
+  y[4] = r - u;
+  u = ((K6 * b2 + K2 * b3 + 0x6CB7) >> 16) + (b3 != 0);
+  s = ((K6 * u) >> 16) - b2;
+  y[2] = u;
+  y[6] = ((s * 21600 + 0x2800) >> 18) + s + (s != 0);
+  u = ((K5 * c6 + K3 * c5 + 0x0E3D) >> 16) + (c5 != 0);
+  s = c6 - ((K5 * u) >> 16);
+  y[5] = u;
+  y[3] = ((s * 26568 + 0x3400) >> 17) + s + (s != 0);
+  u = ((K7 * c4 + K1 * c7 + 0x7B1B) >> 16) + (c7 != 0);
+  s = ((K7 * u) >> 16) - c4;
+  y[1] = u;
+  y[7] = ((s * 20539 + 0x3000) >> 20) + s + (s != 0);
+}
+
+/* 8x8 transpose of 16-bit values over an 8-lane slice; p[k] = (v[2k], v[2k+1]). */
+__device__ __forceinline__ void xpose8(uint32_t (&p)[4], unsigned gmask, int g) {
+  {
+    const bool up = (g & 4) != 0;
+    const uint32_t s0 = up ? p[0] : p[2], s1 = up ? p[1] : p[3];
+    const uint32_t r0 = __shfl_xor_sync(gmask, s0, 4), r1 = __shfl_xor_sync(gmask, s1, 4);
+    if (up) { p[0] = r0; p[1] = r1; } else { p[2] = r0; p[3] = r1; }
+  }
+  {
+    const bool up = (g & 2) != 0;
+    const uint32_t s0 = up ? p[0] : p[1], s1 = up ? p[2] : p[3];
+    const uint32_t r0 = __shfl_xor_sync(gmask, s0, 2), r1 = __shfl_xor_sync(gmask, s1, 2);
+    if (up) { p[0] = r0; p[2] = r1; } else { p[1] = r0; p[3] = r1; }
+  }
+  {
+    const bool up = (g & 1) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t r = __shfl_xor_sync(gmask, p[k], 1);
+      p[k] = up ? __byte_perm(p[k], r, 0x3276) : __byte_perm(p[k], r, 0x5410);
+    }
+  }
+}
+
+__device__ __forceinline__ void pack8(const int (&v)[8], uint32_t (&p)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) p[k] = __byte_perm((uint32_t)v[2 * k], (uint32_t)v[2 * k + 1], 0x5410);
+}
+__device__ __forceinline__ void unpack16(const uint32_t (&p)[4], int (&v)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[2 * k] = (int)(short)(p[k] & 0xFFFF); v[2 * k + 1] = (int)p[k] >> 16; }
+}
+
+/* natural index -> zig-zag position (internal.c:46-55) */
+__constant__ uint8_t c_izig[64] = {
+    0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+    41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+    46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+__global__ void __launch_bounds__(256)
+ocg_enc_fdct_quant_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base, int ystride,
+                          const ocg_enc_frag *__restrict__ frags, int n, const uint16_t *__restrict__ dequant,
+                          const int16_t *__restrict__ enquant, int16_t *__restrict__ dct,
+                          int16_t *__restrict__ qdct, int32_t *__restrict__ nonzero) {
+  __shared__ __align__(16) int16_t zz[32][64]; /* per fragment slot, zig-zag order */
+  const int slot = threadIdx.x >> 3;
+  const int fi = (int)(blockIdx.x * 32 + slot);
+  if (fi >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int row = lane & 7;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int4 fw = __ldg((const int4 *)(frags + fi));
+  ocg_enc_frag f;
+  f.src_off = fw.x; f.ref_off0 = fw.y; f.ref_off1 = fw.z; f.aux = fw.w;
+  const uint2 s = ld8u(src_base + f.src_off + row * ystride);
+  uint2 p;
+  int v[8], b[8], y[8];
+  unpack8(s, v);
+  if (load_pred_row(ref_base, f, row, ystride, p)) {
+    unpack8(p, b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] -= b[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] -= 128;
+  }
+  /* fdct.c:135-142: two extra bits of precision and the round-trip biases */
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (int)(short)(v[i] << 2);
+  if (row == 0) { v[0] = (int)(short)(v[0] + (v[0] != 0) + 1); v[1] = (int)(short)(v[1] + 1); }
+  if (row == 1) v[0] = (int)(short)(v[0] - 1);
+  uint32_t pk[4];
+  pack8(v, pk);
+  xpose8(pk, gmask, row); /* lane c now holds column c */
+  unpack16(pk, v);
+  fdct8(v, y);            /* vertical frequencies of column c */
+  pack8(y, pk);
+  xpose8(pk, gmask, row); /* lane r holds, for vertical frequency r, the 8 columns */
+  unpack16(pk, v);
+  fdct8(v, y);            /* y[k] = coefficient (row r, column k), natural order */
+#pragma unroll
+  for (int k = 0; k < 8; k++) zz[slot][c_izig[row * 8 + k]] = (int16_t)(((int)(short)y[k] + 2) >> 2);
+  __syncwarp(gmask);
+  /* lane handles zig-zag positions 8*row .. 8*row+7 */
+  const uint4 dv = *(const uint4 *)&zz[slot][row * 8];
+  *(uint4 *)(dct + (size_t)fi * 64 + row * 8) = dv;
+  const int pli = f.aux & 3, qti = (f.aux >> 2) & 1, qii = (f.aux >> 3) & 3;
+  const int tab = (pli * 2 + qti) * 3 + qii;
+  const uint4 dq = __ldg((const uint4 *)(dequant + (size_t)tab * 64 + row * 8));
+  const uint4 e0 = __ldg((const uint4 *)(enquant + (size_t)tab * 128 + row * 16));
+  const uint4 e1 = __ldg((const uint4 *)(enquant + (size_t)tab * 128 + row * 16 + 8));
+  const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+  const uint32_t qw[4] = {dq.x, dq.y, dq.z, dq.w};
+  const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+  int q[8], last = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    /* enquant.c:232-246 */
+    const int c = (k & 1) ? (int)dw[k >> 1] >> 16 : (int)(short)(dw[k >> 1] & 0xFFFF);
+    const int d = (int)((qw[k >> 1] >> (16 * (k & 1))) & 0xFFFF);
+    const int m = (int)(short)(ew[k] & 0xFFFF), l = (int)ew[k] >> 16;
+    int val = c << 1;
+    if (abs(val) >= d) {
+      const int sg = val < 0 ? -1 : 0;
+      val += (d + sg) ^ sg;
+      val = ((((m * val) >> 16) + val) >> l) - sg;
+      q[k] = (int)(short)val;
+      last = row * 8 + k;
+    } else q[k] = 0;
+  }
+  uint32_t qp[4];
+  pack8(q, qp);
+  *(uint4 *)(qdct + (size_t)fi * 64 + row * 8) = make_uint4(qp[0], qp[1], qp[2], qp[3]);
+  last = max(last, __shfl_xor_sync(gmask, last, 4));
+  last = max(last, __shfl_xor_sync(gmask, last, 2));
+  last = max(last, __shfl_xor_sync(gmask, last, 1));
+  if (row == 0) nonzero[fi] = last;
+}
+
+} /* namespace */
+
+extern "C" {
+
+OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                  const ocg_enc_frag *frags, int n, uint32_t *out_val, int32_t *out_dc,
+                                  void *stream) {
+  if (src_base == nullptr || frags == nullptr || out_val == nullptr) return OCG_EFAULT;
+  if (metric < OCG_MET_SAD || metric > OCG_MET_INTRA_SAD || n < 0) return OCG_EINVAL;
+  if (n == 0) return OCG_OK;
+  ocg_enc_metrics_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      metric, src_base, ref_base, ystride, frags, n, out_val, out_dc);
+  ocg_count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+OCG_API int ocg_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                     const ocg_enc_frag *frags, int n, const uint16_t *dequant,
+                                     const int16_t *enquant, int16_t *dct, int16_t *qdct, int32_t *nonzero,
+                                     void *stream) {
+  if (src_base == nullptr || frags == nullptr || dequant == nullptr || enquant == nullptr || dct == nullptr ||
+      qdct == nullptr || nonzero == nullptr)
+    return OCG_EFAULT;
+  if (n < 0) return OCG_EINVAL;
+  if (n == 0) return OCG_OK;
+  ocg_enc_fdct_quant_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      src_base, ref_base, ystride, frags, n, dequant, enquant, dct, qdct, nonzero);
+  ocg_count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+} /* extern "C" */

@@ -1,0 +1,52 @@
+/* Internal declarations shared by the C-ABI implementation (ocg_api.cu) and the
+ * kernel translation units.  Not installed. */
+#ifndef OCG_INTERNAL_H
+#define OCG_INTERNAL_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/theora_b200.h"
+
+/* Geometry as the kernels see it (passed by value as a kernel parameter). */
+struct OcgPlaneDev {
+  int32_t nhfrags, nvfrags, froffset;
+  int32_t ystride;    /* negative */
+  int32_t width, height, hpad, vpad;
+  int32_t plane_off;  /* bottom-left pixel relative to the buffer's luma base */
+  int32_t lo_off;     /* lowest offset belonging to this plane (its top-left pixel) */
+  int32_t cell_row0;  /* first loop-filter cell row of this plane in the fused row index */
+};
+
+struct OcgGeomDev {
+  OcgPlaneDev p[3];
+  int32_t qx, qy;       /* chroma decimated horizontally / vertically */
+  int32_t cell_rows;    /* sum over planes of (nvfrags+1) */
+  int32_t max_cells_x;  /* max over planes of (nhfrags+1) */
+  int32_t border_rows;  /* sum over planes of (height + 2*vpad) */
+};
+
+/* One (context, frame) job of a batch; lives in device memory. */
+struct OcgJobDev {
+  uint8_t            *base[3];       /* GOLD, PREV, SELF: buffer + base_off */
+  const ocg_frag_rec *recs;
+  const int16_t      *rows;
+  const int32_t      *unc;
+  const uint8_t      *coded;
+  int32_t             blk_end[5];    /* cumulative 32-fragment block counts: classes 0..3, then copy */
+  int32_t             rec_start[4];  /* first rec of each class */
+  int32_t             ncls[4];
+  int32_t             nunc;
+  int32_t             lf_limit;
+  uint16_t            dcq[3][2];
+  int32_t             pad_;
+};
+
+#define OCG_FRAGS_PER_BLOCK 32
+#define OCG_RECON_THREADS   256
+
+void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, int max_blocks, cudaStream_t st);
+void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
+void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
+
+void ocg_count_launch(int n);
+
+#endif
