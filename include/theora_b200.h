@@ -139,6 +139,10 @@ OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *ctx, int buf);  /* device address of
 OCG_API int  ocg_ctx_upload_frame(ocg_ctx *ctx, int buf, const uint8_t *host_buf);
 OCG_API int  ocg_ctx_download_frame(ocg_ctx *ctx, int buf, uint8_t *host_buf);
 OCG_API int  ocg_ctx_fill_frame(ocg_ctx *ctx, int buf, int value);  /* oc_dec_init_dummy_frame, decode.c:2053 */
+/* Page-locks caller-owned host memory (the reference's ref_frame_handle) so the
+   per-frame D2H runs at full PCIe rate and asynchronously. */
+OCG_API int  ocg_host_register(void *p, size_t bytes);
+OCG_API int  ocg_host_unregister(void *p);
 
 /* ---- decode: one frame, host lists (the call the vtable back-end makes) -- */
 /* Pinned staging owned by the ctx; the recorder writes straight into it (no

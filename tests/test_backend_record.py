@@ -1,0 +1,78 @@
+"""The vtable back-end's recorder + the oracle's whole-frame executor against
+the plain reference decoder on real streams, CPU only.
+
+The integrated library (reference host code + back-end, record mode) produces
+the per-frame lists of include/theora_b200.h; replaying them through
+oco_dec_frame must reproduce, bit for bit, what the unmodified reference decodes
+from the same packets.  This pins the data format, the class binning, the row
+packing and the executor's ordering on real bitstreams."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import support as S
+from theora_b200 import streams
+
+pytestmark = pytest.mark.skipif(not (S.ref_available("c") and streams.available()),
+                                reason="needs oracle/_ref and the integrated build")
+
+CASES = [
+    # w, h, frames, quality, kf, speed, noise_shift
+    (64, 64, 2, 48, 64, 1, 30),      # BASELINE configs[0] size, loop filter off
+    (64, 64, 6, 32, 4, 1, 28),       # loop filter on, several keyframes
+    (176, 144, 8, 20, 64, 1, 28),    # strong loop filter, inter frames
+    (350, 270, 5, 40, 64, 1, 30),    # cropped picture (frame 352x272)
+    (320, 240, 6, 10, 3, 0, 28),     # low quality, speed 0
+    (96, 80, 10, 60, 64, 2, 26),     # high quality / heavy noise: dense blocks
+]
+
+
+def replay_and_compare(case):
+    w, h, n, q, kf, sp, ns = case
+    R = S.ref("c")
+    st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns)
+    blob = st.to_bytes()
+    g, works, _ = streams.capture_stream_work(blob, streams.BACKEND_RECORD)
+    dec = S.Decoder(R, st)
+    frames = np.full(g.nrefs * g.ref_frame_sz, 0x80, np.uint8)
+    assert len(works) == n
+    stats = {"coded": 0, "uncoded": 0, "rows": 0, "cls": [0, 0, 0, 0]}
+    for i, wk in enumerate(works):
+        assert dec.next() >= 0
+        want = dec.frame()
+        if wk is not None:
+            f = wk.as_struct()
+            S.oracle().oco_dec_frame(C.byref(g), S.ptr(frames, S.u8p), C.byref(f), 7)
+            cur = wk.ref_idx[2]
+            stats["coded"] += wk.ncoded
+            stats["uncoded"] += len(wk.uncoded)
+            stats["rows"] += len(wk.rows)
+            for k in range(4):
+                stats["cls"][k] += wk.ncls[k]
+        planes = S.planes_from_buffer(g, frames[cur * g.ref_frame_sz:(cur + 1) * g.ref_frame_sz])
+        got = np.concatenate([p.ravel() for p in planes])
+        assert np.array_equal(got, want), "frame %d differs from the reference decoder" % i
+    dec.close()
+    st.free()
+    return stats
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_recorded_lists_replay_to_reference_frames(case):
+    stats = replay_and_compare(case)
+    assert stats["coded"] > 0
+
+
+def test_every_fragment_is_accounted_for():
+    R = S.ref("c")
+    st = S.Stream.encode(R, 176, 144, 5, quality=32, kf=64, speed=1, noise_shift=28)
+    g, works, _ = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_RECORD)
+    for wk in works:
+        assert wk.ncoded + len(wk.uncoded) == g.nfrags
+        assert int(wk.coded_map.sum()) == wk.ncoded
+        # records are sorted by class and classes follow last_zzi
+        cls = S.cls_of_last_zzi(wk.recs["last_zzi"])
+        assert np.all(np.diff(cls) >= 0)
+        assert [int((cls == k).sum()) for k in range(4)] == list(wk.ncls)
+    st.free()

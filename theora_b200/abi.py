@@ -122,6 +122,8 @@ _PROTOS = {
     "ocg_ctx_upload_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ocg_ctx_download_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ocg_ctx_fill_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ocg_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "ocg_host_unregister": (C.c_int, [C.c_void_p]),
     "ocg_dec_staging": (C.c_int, [C.c_void_p, C.POINTER(Staging)]),
     "ocg_dec_submit": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p]),
     "ocg_pack_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecFrame), C.c_int, C.c_int, C.c_int]),

@@ -1,0 +1,365 @@
+/* ocg_backend.c -- vtable back-end that puts libtheora's decoder block pipeline
+ * on a B200 through the C ABI of include/theora_b200.h.
+ *
+ * Compiled with `-include ocg_hooks.h` against the reference's private headers,
+ * exactly like lib/x86/x86state.c or lib/arm/armstate.c.  The reference host
+ * code (decode.c, state.c, huffdec.c, bitpack.c ...) is consumed unmodified.
+ *
+ * The per-block hooks cannot launch kernels (call granularity),
+ * so they RECORD:
+ *   dc_unpredict_mcu_plane  (decint.h:72)  host DC un-prediction, frame begin
+ *   state_frag_recon        (state.h:361)  -> ocg_frag_rec + coefficient rows
+ *   frag_copy_list          (state.h:356)  -> uncoded offsets
+ *   state_loop_filter_frag_rows            -> nothing (whole-frame on device)
+ *   restore_fpu             (state.h:369)  end of frame (decode.c:2965): FLUSH =
+ *                           one H2D of the lists, recon/copy + loop filter +
+ *                           borders kernels, D2H of the frame into the host
+ *                           reference buffer th_decode_ycbcr_out hands out.
+ * th_decode_alloc / th_decode_free / th_decode_ctl are thin wrappers around
+ * the reference's own functions (renamed at compile time) so device state
+ * follows the decoder's life time, post-processing (which would read stale
+ * host pixels inside the MCU loop, decode.c:2899-2907) is refused with
+ * TH_EIMPL, and the stripe callback is delivered once per frame after flush.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <pthread.h>
+#include "decint.h"
+#include "encint.h"
+#include "ocg_backend.h"
+
+/* the reference's own entry points, renamed on decode.c's command line */
+th_dec_ctx *oc_refimpl_decode_alloc(const th_info *_info, const th_setup_info *_setup);
+void oc_refimpl_decode_free(th_dec_ctx *_dec);
+int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
+
+typedef struct ocg_backend {
+  th_dec_ctx        *dec;
+  ocg_ctx           *ctx;      /* NULL in record mode */
+  ocg_geometry       geom;
+  ocg_staging        st;
+  void              *heap_staging; /* record mode only */
+  int                mode;
+  int                frame_open;
+  int                ncls[OCG_NCLS];
+  int                nrows;
+  int                nunc;
+  int                ref_idx[3];
+  ogg_uint16_t       dcq[3][2];
+  unsigned char      dev_valid[6];
+  int                pinned;
+  th_stripe_callback user_cb;
+  struct ocg_backend *next;
+} ocg_backend;
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static ocg_backend *g_list;
+static int g_mode = OCG_BACKEND_GPU;
+static ocg_capture_fn g_capture;
+static void *g_capture_user;
+static __thread int t_device;
+static __thread ocg_backend *t_cur;
+static __thread ocg_backend_stats t_stats;
+
+OCG_API void ocg_backend_set_mode(int mode) { g_mode = mode; }
+OCG_API void ocg_backend_set_device(int device) { t_device = device; }
+OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user) { g_capture = fn; g_capture_user = user; }
+OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset) {
+  if (out) *out = t_stats;
+  if (reset) memset(&t_stats, 0, sizeof(t_stats));
+}
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static ocg_backend *backend_of(const void *dec) {
+  ocg_backend *b = t_cur;
+  if (b != NULL && (const void *)b->dec == dec) return b;
+  pthread_mutex_lock(&g_lock);
+  for (b = g_list; b != NULL && (const void *)b->dec != dec; b = b->next) {}
+  pthread_mutex_unlock(&g_lock);
+  t_cur = b;
+  return b;
+}
+
+static void backend_fatal(const char *what) {
+  fprintf(stderr, "theora_b200 back-end: %s (%s)\n", what, ocg_last_error());
+  abort();
+}
+
+/* ---- frame life cycle ---------------------------------------------------- */
+static void backend_begin_frame(ocg_backend *b) {
+  const oc_theora_state *st = &b->dec->state;
+  int i;
+  if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
+  memset(b->ncls, 0, sizeof(b->ncls));
+  b->nrows = b->nunc = 0;
+  memset(b->st.coded_map, 0, (size_t)b->geom.nfrags);
+  /* decode.c:2790-2794 has already picked SELF; GOLD/PREV are still the
+     references this frame predicts from (they rotate at 2947-2962). */
+  for (i = 0; i < 3; i++) b->ref_idx[i] = st->ref_frame_idx[i];
+  memset(b->dcq, 0, sizeof(b->dcq));
+  b->frame_open = 1;
+}
+
+static void backend_flush(ocg_backend *b) {
+  oc_theora_state *st = &b->dec->state;
+  ocg_dec_frame f;
+  double t0 = now_s();
+  int i, k;
+  memset(&f, 0, sizeof(f));
+  for (i = 0; i < 3; i++) f.ref_idx[i] = b->ref_idx[i];
+  f.lf_limit = st->loop_filter_limits[st->qis[0]];
+  for (i = 0; i < 3; i++) for (k = 0; k < 2; k++) f.dc_quant[i][k] = b->dcq[i][k];
+  for (k = 0; k < OCG_NCLS; k++) f.ncls[k] = b->ncls[k];
+  f.nuncoded = b->nunc;
+  f.ncoeff_rows = b->nrows;
+  b->frame_open = 0;
+  if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
+  t_stats.frames++;
+  for (k = 0; k < OCG_NCLS; k++) t_stats.coded_frags += b->ncls[k];
+  t_stats.uncoded_frags += b->nunc;
+  t_stats.coeff_rows += b->nrows;
+  if (b->ctx == NULL) return; /* record mode */
+  {
+    unsigned char *host_self = st->ref_frame_handle + (size_t)f.ref_idx[OCG_FRAME_SELF] * (size_t)b->geom.ref_frame_sz;
+    long ncoded = 0;
+    /* A reference the device has never produced (stream starting on an inter
+       frame: oc_dec_init_dummy_frame, decode.c:2053) is taken from the host. */
+    if (st->frame_type != OC_INTRA_FRAME) {
+      for (i = 0; i < 2; i++) {
+        int ri = f.ref_idx[i];
+        if (ri >= 0 && !b->dev_valid[ri]) {
+          if (ocg_ctx_upload_frame(b->ctx, ri, st->ref_frame_handle + (size_t)ri * (size_t)b->geom.ref_frame_sz) < 0)
+            backend_fatal("reference upload failed");
+          b->dev_valid[ri] = 1;
+          t_stats.h2d_bytes += (long)b->geom.ref_frame_sz;
+        }
+      }
+    }
+    if (ocg_dec_submit(b->ctx, &f, host_self) < 0) backend_fatal("ocg_dec_submit failed");
+    if (ocg_ctx_sync(b->ctx) < 0) backend_fatal("ocg_ctx_sync failed");
+    b->dev_valid[f.ref_idx[OCG_FRAME_SELF]] = 1;
+    for (k = 0; k < OCG_NCLS; k++) ncoded += b->ncls[k];
+    t_stats.h2d_bytes += ncoded * 16 + (long)b->nrows * 16 + (long)b->nunc * 4 + (f.lf_limit ? b->geom.nfrags : 0);
+    t_stats.d2h_bytes += (long)b->geom.ref_frame_sz;
+  }
+  t_stats.flush_seconds += now_s() - t0;
+  /* the stripe callback, once, with the whole (now final) frame:
+     decode.c:2936-2940 flips the row range, the telemetry path at 2975 already
+     calls it with the full range. */
+  if (b->user_cb.stripe_decoded != NULL) {
+    th_ycbcr_buffer stripe;
+    oc_ycbcr_buffer_flip(stripe, b->dec->pp_frame_buf);
+    (*b->user_cb.stripe_decoded)(b->user_cb.ctx, stripe, 0, st->fplanes[0].nvfrags);
+  }
+}
+
+/* ---- recorders ----------------------------------------------------------- */
+static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli) {
+  ocg_backend *b = backend_of(_dec);
+  oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
+  if (b != NULL && !b->frame_open) backend_begin_frame(b);
+}
+
+static inline int row_nonzero(const ogg_int16_t *row) {
+  ogg_uint64_t a, c;
+  memcpy(&a, row, 8);
+  memcpy(&c, row + 4, 8);
+  return (a | c) != 0;
+}
+
+static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi, int _pli,
+                                 ogg_int16_t _dct_coeffs[128], int _last_zzi, ogg_uint16_t _dc_quant) {
+  ocg_backend *b = backend_of(_state);
+  const oc_fragment *frag = _state->frags + _fragi;
+  ocg_frag_rec *rec;
+  int cls, nr, r, qti, mask = 0;
+  ogg_int16_t dc = _dct_coeffs[0];
+  if (b == NULL || !b->frame_open) backend_fatal("state_frag_recon outside a frame");
+  /* class selection of state.c:967 and idct.c:327-329 */
+  cls = _last_zzi < 2 ? OCG_CLS_DC : (_last_zzi <= 3 ? OCG_CLS_3 : (_last_zzi <= 10 ? OCG_CLS_10 : OCG_CLS_FULL));
+  nr = cls == OCG_CLS_DC ? 0 : (cls == OCG_CLS_3 ? 2 : (cls == OCG_CLS_10 ? 4 : 8));
+  rec = b->st.recs[cls] + b->ncls[cls]++;
+  rec->coeff_row = (ogg_uint32_t)b->nrows;
+  _dct_coeffs[0] = 0; /* DC travels in the record */
+  for (r = 0; r < nr; r++) {
+    ogg_int16_t *row = _dct_coeffs + r * 8;
+    if (row_nonzero(row)) {
+      memcpy(b->st.coeff_rows + (size_t)b->nrows * 8, row, 16);
+      /* the iDCT contract: leave the coefficients zeroed for the next block
+         (idct.c:245,276,295; decode.c:1385) */
+      memset(row, 0, 16);
+      b->nrows++;
+      mask |= 1 << r;
+    }
+  }
+  qti = frag->mb_mode != OC_MODE_INTRA;
+  rec->buf_off = (ogg_int32_t)_state->frag_buf_offs[_fragi];
+  rec->mv = _state->frag_mvs[_fragi];
+  rec->dc = dc;
+  rec->rowmask = (unsigned char)mask;
+  rec->last_zzi = (unsigned char)_last_zzi;
+  rec->refi = (unsigned char)frag->refi;
+  rec->pli_qti = (unsigned char)(_pli | qti << 2);
+  b->dcq[_pli][qti] = _dc_quant;
+  b->st.coded_map[_fragi] = 1;
+}
+
+static void ocg_frag_copy_list(unsigned char *_dst_frame, const unsigned char *_src_frame, int _ystride,
+                               const ptrdiff_t *_fragis, ptrdiff_t _nfragis, const ptrdiff_t *_frag_buf_offs) {
+  ocg_backend *b = t_cur;
+  ptrdiff_t i;
+  ogg_int32_t *out;
+  (void)_dst_frame; (void)_src_frame; (void)_ystride;
+  if (b == NULL || !b->frame_open) backend_fatal("frag_copy_list outside a frame");
+  out = b->st.uncoded_offs + b->nunc;
+  for (i = 0; i < _nfragis; i++) out[i] = (ogg_int32_t)_frag_buf_offs[_fragis[i]];
+  b->nunc += (int)_nfragis;
+}
+
+static void ocg_state_loop_filter_frag_rows(const oc_theora_state *_state, signed char _bv[256], int _refi,
+                                            int _pli, int _fragy0, int _fragy_end) {
+  /* filtered on the device over the whole frame at flush */
+  (void)_state; (void)_bv; (void)_refi; (void)_pli; (void)_fragy0; (void)_fragy_end;
+}
+
+static void ocg_restore_fpu(void) {
+  ocg_backend *b = t_cur;
+  if (b != NULL && b->frame_open) backend_flush(b);
+}
+
+/* ---- init functions named by ocg_hooks.h --------------------------------- */
+void oc_state_accel_init_ocg(oc_theora_state *_state) {
+  /* shared encoder/decoder table: plain C entries; the decoder init below
+     overrides the ones it offloads (the encoder keeps the C block kernels
+     until its batched analysis front-end lands). */
+  oc_state_accel_init_c(_state);
+}
+
+void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
+  /* encoder table: the reference's C kernels.  The batched GPU encoder kernels
+     (ocg_enc_*_batch) are reached through the C ABI by a restructured caller,
+     not through these synchronous per-block hooks. */
+  oc_enc_accel_init_c(_enc);
+}
+
+static void backend_destroy(ocg_backend *b) {
+  ocg_backend **pp;
+  if (b == NULL) return;
+  pthread_mutex_lock(&g_lock);
+  for (pp = &g_list; *pp != NULL && *pp != b; pp = &(*pp)->next) {}
+  if (*pp == b) *pp = b->next;
+  pthread_mutex_unlock(&g_lock);
+  if (t_cur == b) t_cur = NULL;
+  if (b->ctx != NULL) {
+    ocg_ctx_sync(b->ctx);
+    if (b->pinned) ocg_host_unregister(b->dec->state.ref_frame_handle);
+    ocg_ctx_destroy(b->ctx);
+  }
+  free(b->heap_staging);
+  free(b);
+}
+
+void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
+  oc_theora_state *st = &_dec->state;
+  ocg_backend *b;
+  ptrdiff_t last;
+  oc_dec_accel_init_c(_dec);
+  b = (ocg_backend *)calloc(1, sizeof(*b));
+  if (b == NULL) return;
+  b->dec = _dec;
+  b->mode = g_mode;
+  if (ocg_geometry_init(&b->geom, (int)st->info.frame_width, (int)st->info.frame_height, (int)st->info.pixel_fmt, 3) < 0) {
+    fprintf(stderr, "theora_b200 back-end: %s\n", ocg_last_error());
+    free(b);
+    return;
+  }
+  /* the device mirror must be byte-compatible with state.c:545-671 */
+  last = st->nfrags - 1;
+  if (b->geom.nfrags != st->nfrags || b->geom.planes[0].ystride != st->ref_ystride[0] ||
+      b->geom.planes[1].ystride != st->ref_ystride[1] ||
+      st->ref_frame_bufs[0][0].data - st->ref_frame_handle != b->geom.base_off ||
+      st->ref_frame_bufs[1][0].data - st->ref_frame_bufs[0][0].data != b->geom.ref_frame_sz ||
+      st->frag_buf_offs[last] != b->geom.planes[2].plane_off +
+       (ptrdiff_t)(b->geom.planes[2].nvfrags - 1) * 8 * b->geom.planes[2].ystride + (b->geom.planes[2].nhfrags - 1) * 8) {
+    fprintf(stderr, "theora_b200 back-end: frame layout differs from the reference's\n");
+    free(b);
+    return;
+  }
+  if (b->mode == OCG_BACKEND_GPU) {
+    if (ocg_ctx_create(&b->ctx, &b->geom, t_device) < 0) {
+      fprintf(stderr, "theora_b200 back-end: %s\n", ocg_last_error());
+      free(b);
+      return; /* th_decode_alloc (below) reports the failure; there is no CPU fallback */
+    }
+    b->pinned = ocg_host_register(st->ref_frame_handle, (size_t)b->geom.ref_frame_sz * 3) == 0;
+  } else {
+    size_t nf = (size_t)b->geom.nfrags, off = 0;
+    unsigned char *p = (unsigned char *)malloc(nf * (4 * 16 + 128 + 4 + 1) + 64);
+    int k;
+    if (p == NULL) { free(b); return; }
+    b->heap_staging = p;
+    for (k = 0; k < OCG_NCLS; k++) { b->st.recs[k] = (ocg_frag_rec *)(p + off); off += nf * 16; }
+    b->st.coeff_rows = (int16_t *)(p + off); off += nf * 128;
+    b->st.uncoded_offs = (int32_t *)(p + off); off += nf * 4;
+    b->st.coded_map = p + off;
+  }
+  st->opt_vtable.state_frag_recon = ocg_state_frag_recon;
+  st->opt_vtable.frag_copy_list = ocg_frag_copy_list;
+  st->opt_vtable.state_loop_filter_frag_rows = ocg_state_loop_filter_frag_rows;
+  st->opt_vtable.restore_fpu = ocg_restore_fpu;
+  _dec->opt_vtable.dc_unpredict_mcu_plane = ocg_dc_unpredict_mcu_plane;
+  pthread_mutex_lock(&g_lock);
+  b->next = g_list;
+  g_list = b;
+  pthread_mutex_unlock(&g_lock);
+  t_cur = b;
+}
+
+/* ---- public API wrappers -------------------------------------------------- */
+th_dec_ctx *th_decode_alloc(const th_info *_info, const th_setup_info *_setup) {
+  th_dec_ctx *dec = oc_refimpl_decode_alloc(_info, _setup);
+  if (dec != NULL && backend_of(dec) == NULL) {
+    /* no device / layout mismatch: fail the allocation rather than decode on the CPU */
+    oc_refimpl_decode_free(dec);
+    return NULL;
+  }
+  return dec;
+}
+
+void th_decode_free(th_dec_ctx *_dec) {
+  if (_dec != NULL) backend_destroy(backend_of(_dec));
+  oc_refimpl_decode_free(_dec);
+}
+
+int th_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz) {
+  ocg_backend *b = _dec != NULL ? backend_of(_dec) : NULL;
+  if (b != NULL) {
+    if (_req == TH_DECCTL_SET_PPLEVEL) {
+      if (_buf == NULL) return TH_EFAULT;
+      if (_buf_sz != sizeof(int)) return TH_EINVAL;
+      /* post-processing filters read the reconstructed frame on the host inside
+         the MCU loop (decode.c:2899-2907): not available with record-and-flush */
+      if (*(int *)_buf != 0) return TH_EIMPL;
+    }
+    if (_req == TH_DECCTL_GET_PPLEVEL_MAX) {
+      if (_buf == NULL) return TH_EFAULT;
+      if (_buf_sz != sizeof(int)) return TH_EINVAL;
+      *(int *)_buf = 0;
+      return 0;
+    }
+    if (_req == TH_DECCTL_SET_STRIPE_CB) {
+      if (_buf == NULL) return TH_EFAULT;
+      if (_buf_sz != sizeof(th_stripe_callback)) return TH_EINVAL;
+      b->user_cb = *(th_stripe_callback *)_buf;
+      return 0;
+    }
+  }
+  return oc_refimpl_decode_ctl(_dec, _req, _buf, _buf_sz);
+}

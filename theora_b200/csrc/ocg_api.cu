@@ -328,6 +328,18 @@ OCG_API int ocg_ctx_fill_frame(ocg_ctx *c, int buf, int value) {
   return OCG_OK;
 }
 
+OCG_API int ocg_host_register(void *p, size_t bytes) {
+  if (p == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return OCG_OK;
+}
+
+OCG_API int ocg_host_unregister(void *p) {
+  if (p == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  CU(cudaHostUnregister(p));
+  return OCG_OK;
+}
+
 /* ---- single-frame decode ------------------------------------------------ */
 static int acquire_slot(ocg_ctx *c) {
   const int si = (c->cur_slot + 1) % kSlots;

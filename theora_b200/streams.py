@@ -1,0 +1,163 @@
+"""Driver for the integrated library (theora_b200/backend/libth_ocg.so): the
+reference's own th_decode_* host code with the B200 vtable back-end plugged in.
+
+Used by the tests and bench.py to (a) decode real Theora packets end to end on
+the GPU through the public API and (b) capture the per-frame block work lists
+the back-end uploads, so they can be replayed from HBM (ocg_pack) or checked
+against the oracle.  No codec arithmetic happens in this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import DecFrame, FrameWork, REC_DTYPE, Staging
+
+OCG_LIB = os.path.join(abi.PKG_DIR, "backend", "libth_ocg.so")
+BACKEND_GPU, BACKEND_RECORD = 0, 1
+
+CAPTURE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(DecFrame), C.POINTER(Staging))
+
+
+class BackendStats(C.Structure):
+    _fields_ = [("frames", C.c_long), ("coded_frags", C.c_long), ("uncoded_frags", C.c_long),
+                ("coeff_rows", C.c_long), ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long),
+                ("flush_seconds", C.c_double)]
+
+
+_lib = None
+
+
+def available():
+    return os.path.exists(OCG_LIB) and os.path.exists(abi.LIB_PATH)
+
+
+def lib():
+    """libth_ocg.so with the harness (tools/th_harness.c) and back-end controls bound."""
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("%s not built (needs the reference sources at build time): "
+                               "make -C theora_b200/backend" % OCG_LIB)
+        abi.lib()  # make sure the product library is resolvable first
+        L = C.CDLL(OCG_LIB)
+        L.ocg_backend_set_mode.argtypes = [C.c_int]
+        L.ocg_backend_set_device.argtypes = [C.c_int]
+        L.ocg_backend_set_capture.argtypes = [CAPTURE_FN, C.c_void_p]
+        L.ocg_backend_get_stats.argtypes = [C.POINTER(BackendStats), C.c_int]
+        _bind_harness(L)
+        _lib = L
+    return _lib
+
+
+def _bind_harness(L):
+    L.refh_encode_synth.restype = C.c_void_p
+    L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
+    L.refh_stream_free.argtypes = [C.c_void_p]
+    L.refh_stream_npackets.argtypes = [C.c_void_p]
+    L.refh_stream_packet_size.argtypes = [C.c_void_p, C.c_int]
+    L.refh_stream_packet_size.restype = C.c_long
+    L.refh_stream_blob_size.argtypes = [C.c_void_p]
+    L.refh_stream_blob_size.restype = C.c_long
+    L.refh_stream_to_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    L.refh_stream_to_blob.restype = C.c_long
+    L.refh_stream_from_blob.argtypes = [C.c_void_p, C.c_long]
+    L.refh_stream_from_blob.restype = C.c_void_p
+    L.refh_stream_append_data.argtypes = [C.c_void_p, C.c_void_p]
+    L.refh_dec_open.restype = C.c_void_p
+    L.refh_dec_open.argtypes = [C.c_void_p]
+    L.refh_dec_close.argtypes = [C.c_void_p]
+    L.refh_dec_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.refh_dec_next.argtypes = [C.c_void_p]
+    L.refh_dec_rewind.argtypes = [C.c_void_p]
+    L.refh_dec_hash.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.refh_dec_copy_frame.argtypes = [C.c_void_p, C.c_void_p]
+    L.refh_dec_copy_frame.restype = C.c_long
+    L.refh_decode_time.restype = C.c_double
+    L.refh_decode_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    return L
+
+
+def _copy(ptr, nbytes, dtype):
+    if nbytes == 0 or not ptr:
+        return np.zeros(0, dtype)
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+class Capture:
+    """Collects every flushed frame's lists as FrameWork objects."""
+
+    def __init__(self, nfrags):
+        self.nfrags = nfrags
+        self.frames = []
+        self._cb = CAPTURE_FN(self._on_frame)
+
+    def _on_frame(self, user, fptr, sptr):
+        f, st = fptr.contents, sptr.contents
+        ncls = [f.ncls[k] for k in range(4)]
+        recs = [_copy(st.recs[k], ncls[k] * 16, REC_DTYPE) for k in range(4)]
+        recs = np.concatenate(recs) if sum(ncls) else np.zeros(0, REC_DTYPE)
+        rows = _copy(st.coeff_rows, f.ncoeff_rows * 16, np.int16).reshape(-1, 8)
+        unc = _copy(st.uncoded_offs, f.nuncoded * 4, np.int32)
+        cmap = _copy(st.coded_map, self.nfrags, np.uint8)
+        dcq = [[f.dc_quant[i][j] for j in range(2)] for i in range(3)]
+        self.frames.append(FrameWork([f.ref_idx[i] for i in range(3)], f.lf_limit, dcq, ncls, recs, rows, unc, cmap))
+
+    def install(self):
+        lib().ocg_backend_set_capture(self._cb, None)
+
+    @staticmethod
+    def uninstall():
+        lib().ocg_backend_set_capture(C.cast(None, CAPTURE_FN), None)
+
+
+def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None):
+    """Decodes `stream_blob` (tools/th_harness.c serialisation) through the
+    integrated library and returns (info, [FrameWork per decoded frame],
+    [decoded frame bytes per frame or None in record mode])."""
+    L = lib()
+    L.ocg_backend_set_mode(mode)
+    buf = (C.c_uint8 * len(stream_blob)).from_buffer_copy(stream_blob)
+    sh = L.refh_stream_from_blob(buf, len(stream_blob))
+    assert sh, "bad stream blob"
+    d = L.refh_dec_open(sh)
+    if not d:
+        L.refh_stream_free(sh)
+        L.ocg_backend_set_mode(BACKEND_GPU)
+        raise RuntimeError("th_decode_alloc failed through the B200 back-end: %s" %
+                           abi.lib().ocg_last_error().decode())
+    info = (C.c_int * 8)()
+    L.refh_dec_info(d, info)
+    fw, fh, fmt = info[0], info[1], info[6]
+    g = abi.Geometry()
+    abi.check(abi.lib().ocg_geometry_init(C.byref(g), fw, fh, fmt, 3))
+    cap = Capture(g.nfrags)
+    cap.install()
+    outs = []
+    try:
+        n = 0
+        while max_frames is None or n < max_frames:
+            before = len(cap.frames)
+            ret = L.refh_dec_next(d)
+            if ret == 1000:
+                break
+            assert ret >= 0, "th_decode_packetin returned %d" % ret
+            if len(cap.frames) == before:  # TH_DUPFRAME: nothing to flush
+                cap.frames.append(None)
+            if mode == BACKEND_GPU:
+                cw = fw >> (0 if fmt & 1 else 1)
+                ch = fh >> (0 if fmt & 2 else 1)
+                o = np.empty(fw * fh + 2 * cw * ch, np.uint8)
+                L.refh_dec_copy_frame(d, o.ctypes.data)
+                outs.append(o)
+            else:
+                outs.append(None)
+            n += 1
+    finally:
+        Capture.uninstall()
+        L.refh_dec_close(d)
+        L.refh_stream_free(sh)
+        L.ocg_backend_set_mode(BACKEND_GPU)
+    return g, cap.frames, outs

@@ -1,4 +1,4 @@
-/* TEST INFRASTRUCTURE ONLY (oracle/): ctypes-friendly driver around the
+/* Test/bench tooling: ctypes-friendly driver around the
  * reference's *public* API (include/theora/theoraenc.h:456-537,
  * theoradec.h:234-322).  It is compiled into oracle/_ref/libth_{c,asm}.so next
  * to the unmodified reference objects, and into the integrated build
