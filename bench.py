@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p 4:2:0 Theora decode on B200 (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            our arm
+  python bench.py --impl reference --gpus N --steps K ...  reference CPU arm
+
+Workload: a deterministic synthetic 1920x1080 4:2:0 stream, 300 frames, keyframe
+every 64 (5 intra + 295 inter), quality 32 (loop filter on), speed level 1,
+produced on the box by the reference encoder host code (cached in /tmp).
+
+  value   frames/s of the block pipeline (fused recon+copy, loop filter,
+          borders) with every stream's per-frame lists RESIDENT IN HBM: S
+          independent streams per GPU, one batched launch set per frame index.
+          A step = all 300 frames of all S streams.
+  e2e     frames/s through the reference's public API th_decode_packetin
+          (reference host entropy decode + vtable back-end): packets in host
+          memory -> decoded frame in host memory, H2D of the lists and D2H of
+          the frame inside the timed region, T host threads = T streams.
+  roofline  dominant kernel's algorithmic bytes / CUDA-event time.
+  cpu_baseline  the unmodified reference (x86 SIMD build, oracle/_ref) decoding
+          the same packets on the host cores.
+One process per GPU; ranks share nothing but the setup broadcast of the packets.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+RANK = env_int("RANK", 0)
+WORLD = env_int("WORLD_SIZE", 1)
+LOCAL_RANK = env_int("LOCAL_RANK", 0)
+
+
+def log(*a):
+    print("[bench r%d]" % RANK, *a, file=sys.stderr, flush=True)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.p, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def reference_lib():
+    tdir = os.path.join(ROOT, "tests")  # test infra: the compiled reference lives in oracle/_ref
+    if tdir not in sys.path:
+        sys.path.insert(0, tdir)
+    import support as S
+    kind = "asm" if S.ref_available("asm") else "c"
+    return S.ref(kind), kind
+
+
+def stream_handle(L, blob):
+    buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+    h = L.refh_stream_from_blob(buf, len(blob))
+    assert h, "bad stream blob"
+    return h
+
+
+def time_reference(blob, threads, passes):
+    """Frames/s of the unmodified reference decoding `blob` on `threads` cores."""
+    L, kind = reference_lib()
+    h = stream_handle(L, blob)
+    nframes = L.refh_stream_npackets(h) - 3
+    hsh = C.c_uint64(0)
+    secs = L.refh_decode_time(h, threads, passes, C.byref(hsh))
+    L.refh_stream_free(h)
+    assert secs > 0, "reference decode failed"
+    return threads * passes * nframes / secs, secs, kind, int(hsh.value)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=32, help="independent resident streams per GPU")
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--quality", type=int, default=32)
+    ap.add_argument("--kf", type=int, default=64)
+    ap.add_argument("--threads", type=int, default=0, help="host threads for e2e / CPU arms (0 = all cores)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    ncores = args.threads or host_cores()
+    workload = "1080p 4:2:0 decode, %d synthetic frames (kf=%d, q=%d)" % (args.frames, args.kf, args.quality)
+    if (args.width, args.height) != (1920, 1080):
+        workload = "%dx%d 4:2:0 decode, %d synthetic frames (kf=%d, q=%d)" % (args.width, args.height, args.frames,
+                                                                               args.kf, args.quality)
+
+    from theora_b200 import streams, workload as wl
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if RANK != 0:
+            return 0
+        blob = wl.synth_stream(args.width, args.height, args.frames, args.quality, args.kf)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            fps, secs, kind, _ = time_reference(blob, ncores, 1)
+            if i >= args.warmup:
+                vals.append((fps, secs))
+            if i == 0 and secs > 60:  # keep the arm bounded
+                break
+        if not vals:
+            vals = [(fps, secs)]
+        fps = float(np.mean([v[0] for v in vals]))
+        ms = float(np.mean([v[1] for v in vals])) * 1e3
+        line = {"impl": "reference", "metric": "1080p decode frames/sec", "value": fps, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16",
+                "data": "synthetic", "config": {"workload": workload, "streams": ncores, "frames": args.frames},
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores,
+                                 "kind": "reference" if kind == "asm" else "reference (C path)",
+                                 "sample": "%d streams x %d frames, th_decode_packetin, x86 SIMD build" % (ncores, args.frames)},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    import theora_b200 as T
+    from theora_b200 import abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(LOCAL_RANK)
+    dev = torch.device("cuda", LOCAL_RANK)
+    if WORLD > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if WORLD > 1:
+            dist.barrier()
+
+    # setup: rank 0 synthesises the stream, one NCCL broadcast hands the packets to every rank
+    t0 = time.time()
+    if RANK == 0:
+        blob = wl.synth_stream(args.width, args.height, args.frames, args.quality, args.kf)
+        log("stream ready: %.1f MB in %.1fs" % (len(blob) / 1e6, time.time() - t0))
+    if WORLD > 1:
+        n = torch.tensor([len(blob) if RANK == 0 else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(n, 0)
+        buf = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+        if RANK == 0:
+            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        blob = bytes(buf.cpu().numpy().tobytes())
+
+    # capture the per-frame lists by decoding once through the public API on this GPU
+    Lo = streams.lib()
+    Lo.ocg_backend_set_device(LOCAL_RANK)
+    t0 = time.time()
+    g, works, outs = streams.capture_stream_work(blob, streams.BACKEND_GPU)
+    works = [w for w in works if w is not None]
+    nframes = len(works)
+    outs = None
+    log("captured %d frames of lists in %.1fs" % (nframes, time.time() - t0))
+    alg = [wl.algorithmic_bytes(w) for w in works]
+    recon_bytes_frame = float(np.mean([a[0] for a in alg]))
+    lf_bytes_frame = float(np.mean([a[1] for a in alg]))
+    list_bytes_frame = float(np.mean([w.ncoded * 16 + len(w.rows) * 16 + len(w.uncoded) * 4 + g.nfrags for w in works]))
+
+    # resident state: S contexts + S private copies of the lists
+    S = args.streams
+    t0 = time.time()
+    ctxs = [T.Context(g, LOCAL_RANK) for _ in range(S)]
+    packs = [T.Pack(works, g.nfrags, LOCAL_RANK) for _ in range(S)]
+    torch.cuda.synchronize()
+    log("resident: %d streams, %.2f GB of lists, %.1fs" % (S, S * list_bytes_frame * nframes / 1e9, time.time() - t0))
+    stream = torch.cuda.ExternalStream(ctxs[0].stream, device=dev)
+    L = abi.lib()
+
+    def step():
+        for f in range(nframes):
+            T.run_batch(ctxs, packs, [f] * S, ctxs[0].stream)
+
+    for _ in range(args.warmup):
+        step()
+    ctxs[0].sync()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(LOCAL_RANK)
+    sampler.start()
+    launches0 = L.ocg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+    e1.synchronize()
+    torch.cuda.synchronize()
+    launches = L.ocg_launch_count() - launches0
+    clocks = sampler.stop()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if WORLD > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = WORLD * S * nframes * args.steps / (ms_total * 1e-3)
+
+    # per-kernel device time (CUDA events on the launching stream) for the roofline
+    L.ocg_profile_enable(1)
+    step()
+    ms3, n3 = (C.c_double * 3)(), (C.c_long * 3)()
+    abi.check(L.ocg_profile_collect(ms3, n3))
+    L.ocg_profile_enable(0)
+    peak, peak_src = load_peaks()
+    stage_names = ["recon+copy", "loop_filter", "borders"]
+    stage_bytes = [recon_bytes_frame * S, lf_bytes_frame * S, 0.0]
+    kern = {}
+    for i in range(3):
+        if n3[i]:
+            avg_ms = ms3[i] / n3[i]
+            kern[stage_names[i]] = {"avg_ms": avg_ms, "launches_per_step": int(n3[i]),
+                                    "share": ms3[i] / max(sum(ms3), 1e-9),
+                                    "alg_GBps": stage_bytes[i] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}
+    dom = max(range(3), key=lambda i: ms3[i])
+    achieved = stage_bytes[dom] / (ms3[dom] / n3[dom] * 1e-3) / 1e9 if n3[dom] and stage_bytes[dom] else 0.0
+    roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "alg_bytes_per_launch": stage_bytes[dom], "kernels": kern}
+    for c in ctxs:
+        c.close()
+    for p in packs:
+        p.close()
+
+    # e2e through the public API: T host threads, packets in RAM -> frames in RAM
+    e2e = None
+    if not args.no_e2e:
+        h = stream_handle(Lo, blob)
+        Lo.ocg_backend_set_mode(streams.BACKEND_GPU)
+        st = streams.BackendStats()
+        Lo.refh_decode_time(h, min(ncores, 2), 1, None)  # warm-up (contexts, pinned pools)
+        Lo.ocg_backend_get_stats(C.byref(st), 1)
+        barrier()
+        hsh = C.c_uint64(0)
+        secs = Lo.refh_decode_time(h, ncores, 1, C.byref(hsh))
+        Lo.ocg_backend_get_stats(C.byref(st), 1)
+        Lo.refh_stream_free(h)
+        assert secs > 0, "e2e decode failed"
+        if WORLD > 1:
+            t = torch.tensor([secs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        e2e = {"value": WORLD * ncores * nframes / secs, "unit": "frames/s",
+               "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
+               "host_threads": ncores, "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
+               "flush_ms_per_frame": 1e3 * st.flush_seconds / max(st.frames, 1), "final_frame_hash": int(hsh.value)}
+
+    cpu = None
+    if RANK == 0 and WORLD == 1 and not args.no_cpu:
+        fps, secs, kind, ref_hash = time_reference(blob, ncores, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": ncores,
+               "kind": "reference" if kind == "asm" else "reference (C path)",
+               "sample": "%d streams x %d frames via th_decode_packetin, %.1fs" % (ncores, nframes, secs),
+               "final_frame_hash": ref_hash}
+        if e2e is not None:
+            e2e["parity_with_cpu_baseline"] = bool(e2e["final_frame_hash"] == ref_hash)
+
+    if RANK == 0:
+        line = {"metric": "1080p decode frames/sec", "value": value, "unit": "frames/s", "n_gpus": WORLD,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16",
+                "data": "synthetic",
+                "config": {"workload": workload, "streams_per_gpu": S, "frames_per_stream": nframes,
+                           "frame_units_per_step": S * nframes, "l2": "working set of a launch (%d streams x 3 x %.1f MB "
+                           "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
+                           "parallelism": "independent streams, %d per GPU" % S},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if WORLD > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -177,6 +177,12 @@ OCG_API int  ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs,
    bit2 border fill.  Default 7. */
 OCG_API void ocg_set_stage_mask(int mask);
 OCG_API long ocg_launch_count(void);   /* kernels launched by this library so far */
+/* Per-stage device timing with CUDA events on the launching stream.  While
+   enabled every stage launch (0 recon+copy, 1 loop filter, 2 borders) is
+   bracketed by an event pair; collect() waits for them and returns the summed
+   milliseconds and launch counts since the previous collect. */
+OCG_API void ocg_profile_enable(int on);
+OCG_API int  ocg_profile_collect(double ms[3], long launches[3]);
 
 /* ---- encode-side batched block kernels (encint.h:292-326) ---------------- */
 /* Fragment descriptor for the encoder kernels: where the source block is, and

@@ -59,16 +59,19 @@ static ocg_backend *g_list;
 static int g_mode = OCG_BACKEND_GPU;
 static ocg_capture_fn g_capture;
 static void *g_capture_user;
-static __thread int t_device;
+static int g_device; /* one process per GPU: process-wide */
 static __thread ocg_backend *t_cur;
-static __thread ocg_backend_stats t_stats;
+static ocg_backend_stats g_stats; /* process-wide, updated with atomics */
+static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 
 OCG_API void ocg_backend_set_mode(int mode) { g_mode = mode; }
-OCG_API void ocg_backend_set_device(int device) { t_device = device; }
+OCG_API void ocg_backend_set_device(int device) { g_device = device; }
 OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user) { g_capture = fn; g_capture_user = user; }
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset) {
-  if (out) *out = t_stats;
-  if (reset) memset(&t_stats, 0, sizeof(t_stats));
+  pthread_mutex_lock(&g_stats_lock);
+  if (out) *out = g_stats;
+  if (reset) memset(&g_stats, 0, sizeof(g_stats));
+  pthread_mutex_unlock(&g_stats_lock);
 }
 
 static double now_s(void) {
@@ -90,6 +93,19 @@ static ocg_backend *backend_of(const void *dec) {
 static void backend_fatal(const char *what) {
   fprintf(stderr, "theora_b200 back-end: %s (%s)\n", what, ocg_last_error());
   abort();
+}
+
+static void stats_add(const ocg_backend *b, long h2d, long d2h, double secs) {
+  int k;
+  pthread_mutex_lock(&g_stats_lock);
+  g_stats.frames++;
+  for (k = 0; k < OCG_NCLS; k++) g_stats.coded_frags += b->ncls[k];
+  g_stats.uncoded_frags += b->nunc;
+  g_stats.coeff_rows += b->nrows;
+  g_stats.h2d_bytes += h2d;
+  g_stats.d2h_bytes += d2h;
+  g_stats.flush_seconds += secs;
+  pthread_mutex_unlock(&g_stats_lock);
 }
 
 /* ---- frame life cycle ---------------------------------------------------- */
@@ -121,14 +137,10 @@ static void backend_flush(ocg_backend *b) {
   f.ncoeff_rows = b->nrows;
   b->frame_open = 0;
   if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
-  t_stats.frames++;
-  for (k = 0; k < OCG_NCLS; k++) t_stats.coded_frags += b->ncls[k];
-  t_stats.uncoded_frags += b->nunc;
-  t_stats.coeff_rows += b->nrows;
-  if (b->ctx == NULL) return; /* record mode */
+  if (b->ctx == NULL) { stats_add(b, 0, 0, 0.0); return; } /* record mode */
   {
     unsigned char *host_self = st->ref_frame_handle + (size_t)f.ref_idx[OCG_FRAME_SELF] * (size_t)b->geom.ref_frame_sz;
-    long ncoded = 0;
+    long ncoded = 0, extra_h2d = 0;
     /* A reference the device has never produced (stream starting on an inter
        frame: oc_dec_init_dummy_frame, decode.c:2053) is taken from the host. */
     if (st->frame_type != OC_INTRA_FRAME) {
@@ -138,7 +150,7 @@ static void backend_flush(ocg_backend *b) {
           if (ocg_ctx_upload_frame(b->ctx, ri, st->ref_frame_handle + (size_t)ri * (size_t)b->geom.ref_frame_sz) < 0)
             backend_fatal("reference upload failed");
           b->dev_valid[ri] = 1;
-          t_stats.h2d_bytes += (long)b->geom.ref_frame_sz;
+          extra_h2d += (long)b->geom.ref_frame_sz;
         }
       }
     }
@@ -146,10 +158,9 @@ static void backend_flush(ocg_backend *b) {
     if (ocg_ctx_sync(b->ctx) < 0) backend_fatal("ocg_ctx_sync failed");
     b->dev_valid[f.ref_idx[OCG_FRAME_SELF]] = 1;
     for (k = 0; k < OCG_NCLS; k++) ncoded += b->ncls[k];
-    t_stats.h2d_bytes += ncoded * 16 + (long)b->nrows * 16 + (long)b->nunc * 4 + (f.lf_limit ? b->geom.nfrags : 0);
-    t_stats.d2h_bytes += (long)b->geom.ref_frame_sz;
+    stats_add(b, extra_h2d + ncoded * 16 + (long)b->nrows * 16 + (long)b->nunc * 4 + (f.lf_limit ? b->geom.nfrags : 0),
+              (long)b->geom.ref_frame_sz, now_s() - t0);
   }
-  t_stats.flush_seconds += now_s() - t0;
   /* the stripe callback, once, with the whole (now final) frame:
      decode.c:2936-2940 flips the row range, the telemetry path at 2975 already
      calls it with the full range. */
@@ -293,7 +304,7 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
     return;
   }
   if (b->mode == OCG_BACKEND_GPU) {
-    if (ocg_ctx_create(&b->ctx, &b->geom, t_device) < 0) {
+    if (ocg_ctx_create(&b->ctx, &b->geom, g_device) < 0) {
       fprintf(stderr, "theora_b200 back-end: %s\n", ocg_last_error());
       free(b);
       return; /* th_decode_alloc (below) reports the failure; there is no CPU fallback */

@@ -14,14 +14,14 @@ extern "C" {
 #define OCG_BACKEND_GPU    0
 #define OCG_BACKEND_RECORD 1
 OCG_API void ocg_backend_set_mode(int mode);      /* applies to decoders allocated afterwards */
-OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders allocated afterwards (this thread) */
+OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders allocated afterwards (process-wide: one process per GPU) */
 
 /* Called at every frame flush with the frame description (list pointers NULL)
    and the staged lists, before they are submitted. */
 typedef void (*ocg_capture_fn)(void *user, const ocg_dec_frame *frame, const ocg_staging *lists);
 OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user);
 
-/* Per-thread statistics since the last reset. */
+/* Process-wide statistics since the last reset. */
 typedef struct ocg_backend_stats {
   long   frames;
   long   coded_frags;

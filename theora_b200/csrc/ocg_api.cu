@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 #include "ocg_internal.h"
@@ -137,12 +138,38 @@ static int check_frame(const ocg_geometry &g, const ocg_dec_frame &f) {
   return OCG_OK;
 }
 
+/* Optional per-stage timing with CUDA events on the launching stream (used by
+   bench.py for the roofline numbers; off by default). */
+struct StageSpan { cudaEvent_t a, b; int stage; };
+static std::mutex g_prof_lock;
+static std::vector<StageSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::atomic<int> g_profile{0};
+
+static cudaEvent_t prof_event() {
+  cudaEvent_t e = nullptr;
+  if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+
+template <typename F>
+static void timed_stage(int stage, cudaStream_t st, F &&launch) {
+  if (!g_profile.load(std::memory_order_relaxed)) { launch(); return; }
+  std::lock_guard<std::mutex> lk(g_prof_lock);
+  StageSpan sp{prof_event(), prof_event(), stage};
+  cudaEventRecord(sp.a, st);
+  launch();
+  cudaEventRecord(sp.b, st);
+  g_spans.push_back(sp);
+}
+
 static void launch_stages(const OcgGeomDev &gd, const OcgJobDev *jobs, int njobs, int max_blocks, bool any_lf,
                           cudaStream_t st) {
   const int mask = g_stage_mask.load(std::memory_order_relaxed);
-  if (mask & 1) ocg_launch_recon(gd, jobs, njobs, max_blocks, st);
-  if ((mask & 2) && any_lf) ocg_launch_loop_filter(gd, jobs, njobs, st);
-  if (mask & 4) ocg_launch_borders(gd, jobs, njobs, st);
+  if (mask & 1) timed_stage(0, st, [&] { ocg_launch_recon(gd, jobs, njobs, max_blocks, st); });
+  if ((mask & 2) && any_lf) timed_stage(1, st, [&] { ocg_launch_loop_filter(gd, jobs, njobs, st); });
+  if (mask & 4) timed_stage(2, st, [&] { ocg_launch_borders(gd, jobs, njobs, st); });
 }
 
 /* ------------------------------------------------------------------------ */
@@ -158,6 +185,25 @@ OCG_API int ocg_device_count(void) {
 }
 
 OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
+
+OCG_API void ocg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+
+OCG_API int ocg_profile_collect(double ms[3], long launches[3]) {
+  if (ms == nullptr || launches == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  std::lock_guard<std::mutex> lk(g_prof_lock);
+  for (int i = 0; i < 3; i++) { ms[i] = 0.0; launches[i] = 0; }
+  for (StageSpan &sp : g_spans) {
+    float t = 0.f;
+    CU(cudaEventSynchronize(sp.b));
+    CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms[sp.stage] += (double)t;
+    launches[sp.stage]++;
+    g_event_pool.push_back(sp.a);
+    g_event_pool.push_back(sp.b);
+  }
+  g_spans.clear();
+  return OCG_OK;
+}
 OCG_API long ocg_launch_count(void) { return g_launches.load(); }
 
 /* state.c:424-470 (fragment planes), 545-671 (padded buffers + flip). */

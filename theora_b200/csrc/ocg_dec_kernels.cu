@@ -400,35 +400,46 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
 /* ------------------------------------------------------------------------ */
 /* Apron replication, state.c:770-835: every apron byte takes the nearest
    picture pixel (rows first, then full-width caps == clamp in both axes).
-   One thread per 4 apron/plane bytes of a padded row; rows of all three planes
-   are fused into blockIdx.y. */
+   One thread per 8-byte work item, items enumerated linearly per job:
+     side items  every picture row x {left,right} x hpad/8
+     cap items   every apron row above/below x padded width/8            */
 __global__ void __launch_bounds__(128)
 ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  const OcgJobDev &job = jobs[blockIdx.z];
-  int prow = (int)blockIdx.y;
-  int pli = 0;
-  while (pli < 2 && prow >= g.p[pli].height + 2 * g.p[pli].vpad) {
-    prow -= g.p[pli].height + 2 * g.p[pli].vpad;
-    pli++;
+  const OcgJobDev &job = jobs[blockIdx.y];
+  int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+#pragma unroll
+  for (int pli = 0; pli < 3; pli++) {
+    const OcgPlaneDev &P = g.p[pli];
+    const int hq = P.hpad >> 3;
+    const int nside = P.height * 2 * hq;
+    const int capw = (P.width + 2 * P.hpad) >> 3;
+    const int ncap = 2 * P.vpad * capw;
+    uint8_t *base = job.base[OCG_FRAME_SELF] + P.plane_off;
+    if (t < nside) {
+      const int y = t / (2 * hq), k = t - y * 2 * hq;
+      const bool right = k >= hq;
+      const uint8_t *srow = base + y * P.ystride;
+      const uint32_t v = 0x01010101u * (right ? srow[P.width - 1] : srow[0]);
+      uint8_t *d = base + y * P.ystride + (right ? P.width + 8 * (k - hq) : -P.hpad + 8 * k);
+      *(uint2 *)d = make_uint2(v, v);
+      return;
+    }
+    t -= nside;
+    if (t < ncap) {
+      const int r = t / capw, c = t - r * capw;
+      /* rows 0..vpad-1 below the picture (y=-1-r), the rest above it */
+      const int y = r < P.vpad ? -1 - r : P.height + (r - P.vpad);
+      const uint8_t *srow = base + (r < P.vpad ? 0 : P.height - 1) * P.ystride;
+      const int x = -P.hpad + 8 * c;
+      uint2 v;
+      if (x < 0) { const uint32_t e = 0x01010101u * srow[0]; v = make_uint2(e, e); }
+      else if (x >= P.width) { const uint32_t e = 0x01010101u * srow[P.width - 1]; v = make_uint2(e, e); }
+      else v = *(const uint2 *)(srow + x);
+      *(uint2 *)(base + y * P.ystride + x) = v;
+      return;
+    }
+    t -= ncap;
   }
-  const OcgPlaneDev &P = g.p[pli];
-  const int y = prow - P.vpad;                 /* bottom-up row, may be outside [0,height) */
-  const int ys = min(max(y, 0), P.height - 1); /* source row */
-  const bool cap = y != ys;
-  const int fullw = P.width + 2 * P.hpad;
-  uint8_t *base = job.base[OCG_FRAME_SELF] + P.plane_off;
-  const uint8_t *srow = base + ys * P.ystride;
-  uint8_t *drow = base + y * P.ystride;
-  const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4 - P.hpad;
-  if (x4 >= P.width + P.hpad) return;
-  (void)fullw;
-  const bool side = x4 < 0 || x4 >= P.width;
-  if (!cap && !side) return; /* interior pixel of a picture row: nothing to do */
-  uint32_t v;
-  if (x4 < 0) v = 0x01010101u * srow[0];
-  else if (x4 >= P.width) v = 0x01010101u * srow[P.width - 1];
-  else v = *(const uint32_t *)(srow + x4);
-  *(uint32_t *)(drow + x4) = v;
 }
 
 } /* namespace */
@@ -449,8 +460,10 @@ void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njob
 
 void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return;
-  const int maxw4 = (g.p[0].width + 2 * g.p[0].hpad + 3) / 4;
-  dim3 grid((unsigned)((maxw4 + 127) / 128), (unsigned)g.border_rows, (unsigned)njobs);
+  int items = 0;
+  for (int pli = 0; pli < 3; pli++)
+    items += g.p[pli].height * 2 * (g.p[pli].hpad >> 3) + 2 * g.p[pli].vpad * ((g.p[pli].width + 2 * g.p[pli].hpad) >> 3);
+  dim3 grid((unsigned)((items + 127) / 128), (unsigned)njobs);
   ocg_border_kernel<<<grid, 128, 0, st>>>(g, jobs);
   ocg_count_launch(1);
 }

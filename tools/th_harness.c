@@ -368,6 +368,7 @@ REFH_API th_dec_ctx *refh_dec_ctx(refh_dec *d) { return d->td; }
    passes * nframes. */
 typedef struct refh_job {
   const refh_stream *s;
+  pthread_barrier_t *bar;
   int passes;
   double secs;
   uint64_t hash;
@@ -379,10 +380,12 @@ static void *refh_decode_worker(void *arg) {
   refh_dec *d = refh_dec_open(j->s);
   double t0;
   int p;
-  if (d == NULL) { j->fail = 1; return NULL; }
-  /* warm-up: one packet */
-  refh_dec_next(d);
-  refh_dec_rewind(d);
+  /* every worker finishes its set-up (decoder, device context, warm-up packet)
+     before any starts the clock, and tears down only after all have stopped
+     it, so allocation/free never overlaps a timed region */
+  if (d != NULL) { refh_dec_next(d); refh_dec_rewind(d); }
+  pthread_barrier_wait(j->bar);
+  if (d == NULL) { j->fail = 1; pthread_barrier_wait(j->bar); return NULL; }
   t0 = refh_now();
   for (p = 0; p < j->passes; p++) {
     int ret;
@@ -392,6 +395,7 @@ static void *refh_decode_worker(void *arg) {
     }
   }
   j->secs = refh_now() - t0;
+  pthread_barrier_wait(j->bar);
   {
     uint64_t h[3];
     refh_dec_hash(d, h);
@@ -404,10 +408,13 @@ static void *refh_decode_worker(void *arg) {
 REFH_API double refh_decode_time(const refh_stream *s, int nthreads, int passes, uint64_t *hash_out) {
   pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
   refh_job *jobs = (refh_job *)calloc((size_t)nthreads, sizeof(refh_job));
+  pthread_barrier_t bar;
   double worst = 0.0;
   int i, fail = 0;
+  pthread_barrier_init(&bar, NULL, (unsigned)nthreads);
   for (i = 0; i < nthreads; i++) {
     jobs[i].s = s;
+    jobs[i].bar = &bar;
     jobs[i].passes = passes;
     pthread_create(&th[i], NULL, refh_decode_worker, &jobs[i]);
   }
@@ -417,6 +424,7 @@ REFH_API double refh_decode_time(const refh_stream *s, int nthreads, int passes,
     fail |= jobs[i].fail;
   }
   if (hash_out) *hash_out = jobs[0].hash;
+  pthread_barrier_destroy(&bar);
   free(th);
   free(jobs);
   return fail ? -1.0 : worst;
