@@ -1,0 +1,106 @@
+"""GPU parity for the encoder batch kernels (C ABI) against the CPU oracle:
+SAD/SAD2, SATD/SATD2, intra SATD, SSD, intra SAD; sub -> fDCT -> quantise."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import support as S
+from theora_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+W, H, PAD = 256, 128, 32
+
+
+def make_frames(rng, mode):
+    st = W + 2 * PAD
+    if mode == 0:
+        a = rng.integers(0, 256, size=(H + 2 * PAD, st), dtype=np.uint8)
+        b = rng.integers(0, 256, size=(H + 2 * PAD, st), dtype=np.uint8)
+    elif mode == 1:
+        base = rng.integers(0, 256, size=(H + 2 * PAD, st))
+        a = np.clip(base + rng.integers(-5, 6, size=base.shape), 0, 255).astype(np.uint8)
+        b = np.clip(np.roll(base, 2, axis=1) + rng.integers(-5, 6, size=base.shape), 0, 255).astype(np.uint8)
+    else:
+        a = (rng.integers(0, 2, size=(H + 2 * PAD, st)) * 255).astype(np.uint8)
+        b = (rng.integers(0, 2, size=(H + 2 * PAD, st)) * 255).astype(np.uint8)
+    return a, b, st
+
+
+def make_frags(rng, st, n, taps):
+    """Blocks on the 8x8 grid of the picture with random candidate offsets (bottom-up addressing)."""
+    fr = np.zeros(n, S.ENC_FRAG_DTYPE)
+    ystride = -st
+    base = (PAD + H - 1) * st + PAD  # bottom-left picture pixel
+    fx = rng.integers(0, W // 8, size=n)
+    fy = rng.integers(0, H // 8, size=n)
+    off = fy * 8 * ystride + fx * 8
+    fr["src_off"] = off
+    dx = rng.integers(-16, 17, size=n)
+    dy = rng.integers(-16, 17, size=n)
+    fr["ref_off0"] = off + dy * ystride + dx if taps >= 1 else S.INT32_MIN
+    if taps >= 2:
+        sx = rng.integers(-1, 2, size=n)
+        sy = rng.integers(-1, 2, size=n)
+        fr["ref_off1"] = fr["ref_off0"] + sy * ystride + sx
+    else:
+        fr["ref_off1"] = S.INT32_MIN
+    fr["aux"] = rng.integers(0, 3, size=n) | (rng.integers(0, 2, size=n) << 2) | (rng.integers(0, 3, size=n) << 3)
+    return fr, base, ystride
+
+
+@pytest.mark.parametrize("metric,taps", [(0, 1), (0, 2), (1, 1), (1, 2), (2, 0), (3, 1), (4, 0)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_metrics_batch(metric, taps, mode):
+    rng = np.random.default_rng(metric * 10 + taps * 3 + mode)
+    a, b, st = make_frames(rng, mode)
+    n = 5000
+    fr, base, ystride = make_frags(rng, st, n, taps)
+    want_v, want_dc = np.zeros(n, np.uint32), np.zeros(n, np.int32)
+    S.oracle().oco_enc_metrics_batch(metric, a.ctypes.data + base, b.ctypes.data + base, ystride, fr.ctypes.data, n,
+                                     S.ptr(want_v, S.u32p), S.ptr(want_dc, S.i32p))
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dfr = torch.from_numpy(fr.view(np.int32).reshape(n, 4)).cuda()
+    ov = torch.zeros(n, dtype=torch.int32, device="cuda")
+    odc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    abi.check(abi.lib().ocg_enc_metrics_batch(metric, da.data_ptr() + base, db.data_ptr() + base, ystride,
+                                              dfr.data_ptr(), n, ov.data_ptr(), odc.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(ov.cpu().numpy().view(np.uint32), want_v)
+    assert np.array_equal(odc.cpu().numpy(), want_dc)
+
+
+@pytest.mark.parametrize("taps", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fdct_quant_batch(taps, mode):
+    rng = np.random.default_rng(50 + taps * 3 + mode)
+    a, b, st = make_frames(rng, mode)
+    n = 4000
+    fr, base, ystride = make_frags(rng, st, n, taps)
+    deq = rng.integers(2, 600, size=(18, 64)).astype(np.uint16)
+    deq[3] = rng.integers(1, 30000, size=64)
+    enq = np.zeros((18, 128), np.int16)
+    for t in range(18):
+        S.oracle().oco_enquant_init(S.ptr(enq[t], S.i16p), S.ptr(deq[t], S.u16p))
+    want_d, want_q = np.zeros((n, 64), np.int16), np.zeros((n, 64), np.int16)
+    want_nz = np.zeros(n, np.int32)
+    S.oracle().oco_enc_fdct_quant_batch(a.ctypes.data + base, b.ctypes.data + base, ystride, fr.ctypes.data, n,
+                                        S.ptr(deq, S.u16p), S.ptr(enq, S.i16p), S.ptr(want_d, S.i16p),
+                                        S.ptr(want_q, S.i16p), S.ptr(want_nz, S.i32p))
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dfr = torch.from_numpy(fr.view(np.int32).reshape(n, 4)).cuda()
+    ddeq = torch.from_numpy(deq.view(np.int16)).cuda()
+    denq = torch.from_numpy(enq).cuda()
+    od = torch.zeros((n, 64), dtype=torch.int16, device="cuda")
+    oq = torch.zeros((n, 64), dtype=torch.int16, device="cuda")
+    onz = torch.zeros(n, dtype=torch.int32, device="cuda")
+    abi.check(abi.lib().ocg_enc_fdct_quant_batch(da.data_ptr() + base, db.data_ptr() + base, ystride, dfr.data_ptr(), n,
+                                                 ddeq.data_ptr(), denq.data_ptr(), od.data_ptr(), oq.data_ptr(),
+                                                 onz.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(od.cpu().numpy(), want_d)
+    assert np.array_equal(oq.cpu().numpy(), want_q)
+    assert np.array_equal(onz.cpu().numpy(), want_nz)
