@@ -243,7 +243,7 @@ def main():
     alg = [wl.algorithmic_bytes(w) for w in works]
     recon_bytes_frame = float(np.mean([a[0] for a in alg]))
     lf_bytes_frame = float(np.mean([a[1] for a in alg]))
-    list_bytes_frame = float(np.mean([w.ncoded * 16 + len(w.rows) * 16 + len(w.uncoded) * 4 + g.nfrags for w in works]))
+    list_bytes_frame = float(np.mean([w.list_bytes() for w in works]))
 
     # resident state: S contexts + S private copies of the lists
     S = args.streams

@@ -84,8 +84,15 @@ typedef struct ocg_geometry {
   ocg_plane_geom planes[3];
 } ocg_geometry;
 
-/* One coded fragment (16 bytes).  Replaces the argument list of
-   oc_state_frag_recon (state.h:361-362, state.c:959). */
+/* refi value of a fragment that is NOT coded in this frame: its pixels are
+   copied from the previous reference (oc_frag_copy_list, fragment.c:37). */
+#define OCG_FRAG_UNCODED 3
+
+/* One fragment (16 bytes).  A frame carries exactly nfrags of these, indexed
+   by the reference's fragment index (raster order inside each plane, planes
+   back to back: state.h oc_fragment_plane.froffset).  For coded fragments it
+   replaces the argument list of oc_state_frag_recon (state.h:361-362,
+   state.c:959); uncoded ones only need buf_off and the plane. */
 typedef struct ocg_frag_rec {
   int32_t  buf_off;    /* state->frag_buf_offs[fragi]                             */
   int16_t  mv;         /* state->frag_mvs[fragi]: dx=(int8)mv, dy=mv>>8           */
@@ -93,7 +100,7 @@ typedef struct ocg_frag_rec {
   uint32_t coeff_row;  /* index of this fragment's first stored row in coeff_rows */
   uint8_t  rowmask;    /* bit j: natural-order row j is stored (16 B per row)     */
   uint8_t  last_zzi;   /* as handed to oc_state_frag_recon, 0..64                 */
-  uint8_t  refi;       /* OCG_FRAME_*: SELF = intra                               */
+  uint8_t  refi;       /* OCG_FRAME_* (SELF = intra) or OCG_FRAG_UNCODED          */
   uint8_t  pli_qti;    /* pli | qti<<2                                            */
 } ocg_frag_rec;
 
@@ -106,13 +113,10 @@ typedef struct ocg_dec_frame {
   int32_t             ref_idx[3];      /* buffer playing GOLD, PREV, SELF          */
   int32_t             lf_limit;        /* loop_filter_limits[qis[0]]; 0 = no filter */
   uint16_t            dc_quant[3][2];  /* dequant[pli][0][qti][0] (decode.c:1534)  */
-  int32_t             ncls[OCG_NCLS];  /* recs are sorted by class; counts per class */
-  int32_t             nuncoded;
+  int32_t             ncoded;          /* coded fragments in recs (informational)  */
   int32_t             ncoeff_rows;
-  const ocg_frag_rec *recs;
+  const ocg_frag_rec *recs;            /* nfrags records, fragment-index order     */
   const int16_t      *coeff_rows;      /* ncoeff_rows x 8 int16                    */
-  const int32_t      *uncoded_offs;    /* frag_buf_offs[] of uncoded fragments     */
-  const uint8_t      *coded_map;       /* nfrags bytes, frags[i].coded             */
 } ocg_dec_frame;
 
 typedef struct ocg_ctx  ocg_ctx;    /* per th_dec_ctx / th_enc_ctx device state   */
@@ -146,14 +150,12 @@ OCG_API int  ocg_host_unregister(void *p);
 
 /* ---- decode: one frame, host lists (the call the vtable back-end makes) -- */
 /* Pinned staging owned by the ctx; the recorder writes straight into it (no
-   extra host copy).  One rec region per sparsity class, each with room for
-   nfrags records; nfrags*8 coefficient rows, nfrags uncoded offsets, nfrags
-   map bytes.  Valid until the next ocg_dec_submit on this ctx. */
+   extra host copy): nfrags records (pre-filled with every fragment marked
+   OCG_FRAG_UNCODED, buf_off and plane set) and room for nfrags*8 coefficient
+   rows.  Valid until the next ocg_dec_submit on this ctx. */
 typedef struct ocg_staging {
-  ocg_frag_rec *recs[OCG_NCLS];
+  ocg_frag_rec *recs;
   int16_t      *coeff_rows;
-  int32_t      *uncoded_offs;
-  uint8_t      *coded_map;
 } ocg_staging;
 OCG_API int  ocg_dec_staging(ocg_ctx *ctx, ocg_staging *out);
 /* H2D of the lists + recon/copy + loop filter + border fill on the ctx stream.

@@ -339,57 +339,49 @@ OCO_EXPORT void oco_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs)
   }
 }
 
-/* Planes are consecutive in memory (luma, Cb, Cr), so the plane -- hence the
-   row stride -- of a fragment follows from its buffer offset. */
-static int plane_of_offset(const ocg_geometry *g, int64_t off) {
-  int pli;
-  for (pli = 2; pli > 0; pli--) {
-    const ocg_plane_geom *p = &g->planes[pli];
-    if (off >= p->plane_off + (int64_t)(p->height - 1) * p->ystride) break;
-  }
-  return pli;
-}
-
 /* The whole-frame sequence of decode.c:2858-2945 driven from the C-ABI frame
    description: recon of coded fragments (decode.c:1584 -> state.c:959), copy
    of uncoded ones (decode.c:1599), loop filter over all rows (2882), borders
-   (2890, 2945). */
+   (2890, 2945).  Fragments are visited in fragment-index order; coded ones
+   write only their own 8x8 block of SELF and read other buffers, so the
+   reference's coded order gives the same pixels. */
 OCO_EXPORT void oco_dec_frame(const ocg_geometry *g, uint8_t *frames, const ocg_dec_frame *f, int stage_mask) {
   uint8_t *base[3];
-  int ncoded = 0, i, r, c, pli;
+  uint8_t *coded = (uint8_t *)malloc((size_t)g->nfrags);
+  int i, r, c, pli;
   for (i = 0; i < 3; i++)
     base[i] = f->ref_idx[i] >= 0 ? frames + (int64_t)f->ref_idx[i] * g->ref_frame_sz + g->base_off : NULL;
-  for (i = 0; i < OCG_NCLS; i++) ncoded += f->ncls[i];
+  for (i = 0; i < g->nfrags; i++) coded[i] = f->recs[i].refi != OCG_FRAG_UNCODED;
   if (stage_mask & 1) {
-    for (i = 0; i < ncoded; i++) {
+    for (i = 0; i < g->nfrags; i++) {
       const ocg_frag_rec *rec = &f->recs[i];
-      int16_t blk[128];
-      const int16_t *rows = f->coeff_rows + (size_t)rec->coeff_row * 8;
       int pl = rec->pli_qti & 3, qti = rec->pli_qti >> 2 & 1;
-      memset(blk, 0, sizeof(blk));
-      for (r = 0; r < 8; r++) {
-        if (!(rec->rowmask >> r & 1)) continue;
-        for (c = 0; c < 8; c++) blk[r * 8 + c] = rows[c];
-        rows += 8;
+      if (!coded[i]) {
+        oco_frag_copy(base[OCG_FRAME_SELF] + rec->buf_off, base[OCG_FRAME_PREV] + rec->buf_off, g->planes[pl].ystride);
+      } else {
+        int16_t blk[128];
+        const int16_t *rows = f->coeff_rows + (size_t)rec->coeff_row * 8;
+        memset(blk, 0, sizeof(blk));
+        for (r = 0; r < 8; r++) {
+          if (!(rec->rowmask >> r & 1)) continue;
+          for (c = 0; c < 8; c++) blk[r * 8 + c] = rows[c];
+          rows += 8;
+        }
+        blk[0] = rec->dc;
+        oco_state_frag_recon(base[OCG_FRAME_SELF], rec->refi == OCG_FRAME_SELF ? NULL : base[rec->refi],
+                             rec->buf_off, g->planes[pl].ystride, pl, g->pixel_fmt,
+                             rec->refi == OCG_FRAME_SELF, rec->mv, blk, rec->last_zzi, f->dc_quant[pl][qti]);
       }
-      blk[0] = rec->dc;
-      oco_state_frag_recon(base[OCG_FRAME_SELF], rec->refi == OCG_FRAME_SELF ? NULL : base[rec->refi],
-                           rec->buf_off, g->planes[pl].ystride, pl, g->pixel_fmt,
-                           rec->refi == OCG_FRAME_SELF, rec->mv, blk, rec->last_zzi, f->dc_quant[pl][qti]);
-    }
-    for (i = 0; i < f->nuncoded; i++) {
-      int32_t off = f->uncoded_offs[i];
-      pli = plane_of_offset(g, off);
-      oco_frag_copy(base[OCG_FRAME_SELF] + off, base[OCG_FRAME_PREV] + off, g->planes[pli].ystride);
     }
   }
   for (pli = 0; pli < 3; pli++) {
     const ocg_plane_geom *p = &g->planes[pli];
     uint8_t *pix = base[OCG_FRAME_SELF] + p->plane_off;
     if ((stage_mask & 2) && f->lf_limit)
-      oco_loop_filter_plane_seq(pix, p->ystride, p->nhfrags, p->nvfrags, f->coded_map + p->froffset, f->lf_limit);
+      oco_loop_filter_plane_seq(pix, p->ystride, p->nhfrags, p->nvfrags, coded + p->froffset, f->lf_limit);
     if (stage_mask & 4) oco_borders_fill_plane(pix, p->ystride, p->width, p->height, p->hpad, p->vpad);
   }
+  free(coded);
 }
 
 /* ---------------------------------------------------------------------- */

@@ -46,7 +46,7 @@ def replay_and_compare(case):
             S.oracle().oco_dec_frame(C.byref(g), S.ptr(frames, S.u8p), C.byref(f), 7)
             cur = wk.ref_idx[2]
             stats["coded"] += wk.ncoded
-            stats["uncoded"] += len(wk.uncoded)
+            stats["uncoded"] += wk.nuncoded
             stats["rows"] += len(wk.rows)
             for k in range(4):
                 stats["cls"][k] += wk.ncls[k]
@@ -68,11 +68,17 @@ def test_every_fragment_is_accounted_for():
     R = S.ref("c")
     st = S.Stream.encode(R, 176, 144, 5, quality=32, kf=64, speed=1, noise_shift=28)
     g, works, _ = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_RECORD)
-    for wk in works:
-        assert wk.ncoded + len(wk.uncoded) == g.nfrags
-        assert int(wk.coded_map.sum()) == wk.ncoded
-        # records are sorted by class and classes follow last_zzi
-        cls = S.cls_of_last_zzi(wk.recs["last_zzi"])
-        assert np.all(np.diff(cls) >= 0)
-        assert [int((cls == k).sum()) for k in range(4)] == list(wk.ncls)
+    offs = np.empty(g.nfrags, np.int32)
+    S.oracle().oco_geometry_frag_buf_offs(C.byref(g), S.ptr(offs, S.i32p))
+    for i, wk in enumerate(works):
+        assert len(wk.recs) == g.nfrags
+        assert np.array_equal(wk.recs["buf_off"], offs)
+        for pli in range(3):
+            p = g.planes[pli]
+            assert np.all((wk.recs["pli_qti"][p.froffset:p.froffset + p.nfrags] & 3) == pli)
+        if i == 0:
+            assert wk.nuncoded == 0  # keyframe: everything coded, all intra
+            assert np.all(wk.recs["refi"] == 2)
+        # stored rows are exactly the rows the masks announce
+        assert int(sum(bin(int(m)).count("1") for m in wk.recs["rowmask"][wk.coded_mask])) == len(wk.rows)
     st.free()

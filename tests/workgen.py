@@ -36,20 +36,24 @@ def random_work(g, rng, density=0.7, intra_only=False, lf_limit=0, big=False, de
     coded = rng.random(n) < density
     if intra_only:
         coded[:] = True
+    recs = np.zeros(n, REC_DTYPE)
+    recs["buf_off"] = offs
+    recs["refi"] = 3
+    recs["pli_qti"] = planes
     idx = np.nonzero(coded)[0]
-    rng.shuffle(idx)  # coded order is not raster order in real streams either
     nc = len(idx)
     lz_choices = {0: [0, 1], 1: [2, 3], 2: [4, 7, 10], 3: [11, 20, 40, 63, 64]}
     cls = rng.choice(4, size=nc, p=cls_probs)
     last_zzi = np.array([rng.choice(lz_choices[int(c)]) for c in cls], np.int32)
     assert np.array_equal(cls_of_last_zzi(last_zzi), cls)
-    order = np.argsort(cls, kind="stable")
-    idx, cls, last_zzi = idx[order], cls[order], last_zzi[order]
-    recs = np.zeros(nc, REC_DTYPE)
+    # coefficient rows are appended in a shuffled ("coded") order, not raster order
+    order = rng.permutation(nc)
     rows = []
     nrows = 0
     amp = 32767 if big else 500
-    for i in range(nc):
+    coeff_row = np.zeros(nc, np.uint32)
+    rowmask = np.zeros(nc, np.uint8)
+    for i in order:
         blk = np.zeros(64, np.int16)
         lz = int(last_zzi[i])
         nzmax = 64 if lz > 10 else lz
@@ -67,27 +71,28 @@ def random_work(g, rng, density=0.7, intra_only=False, lf_limit=0, big=False, de
             if keep:
                 mask |= 1 << r
                 rows.append(b[r].copy())
-        recs[i]["coeff_row"] = nrows
+        coeff_row[i] = nrows
         nrows += bin(mask).count("1")
-        recs[i]["rowmask"] = mask
-    recs["buf_off"] = offs[idx]
+        rowmask[i] = mask
+    crec = np.zeros(nc, REC_DTYPE)
+    crec["buf_off"] = offs[idx]
+    crec["coeff_row"] = coeff_row
+    crec["rowmask"] = rowmask
     dx = rng.integers(-mv_range, mv_range + 1, size=nc)
     dy = rng.integers(-mv_range, mv_range + 1, size=nc)
-    recs["mv"] = (((dy & 0xFF) << 8) | (dx & 0xFF)).astype(np.uint16).view(np.int16)
-    recs["dc"] = rng.integers(-32768 if big else -1500, 32768 if big else 1500, size=nc)
-    recs["last_zzi"] = last_zzi
+    crec["mv"] = (((dy & 0xFF) << 8) | (dx & 0xFF)).astype(np.uint16).view(np.int16)
+    crec["dc"] = rng.integers(-32768 if big else -1500, 32768 if big else 1500, size=nc)
+    crec["last_zzi"] = last_zzi
     if intra_only:
-        recs["refi"] = 2
+        crec["refi"] = 2
     else:
-        recs["refi"] = rng.choice([0, 1, 2], size=nc, p=[0.2, 0.6, 0.2])
-    qti = (recs["refi"] != 2).astype(np.uint8)
-    recs["pli_qti"] = planes[idx].astype(np.uint8) | (qti << 2)
-    unc = offs[np.nonzero(~coded)[0]].astype(np.int32)
-    rng.shuffle(unc)
-    ncls = [int((cls == c).sum()) for c in range(4)]
+        crec["refi"] = rng.choice([0, 1, 2], size=nc, p=[0.2, 0.6, 0.2])
+    qti = (crec["refi"] != 2).astype(np.uint8)
+    crec["pli_qti"] = planes[idx].astype(np.uint8) | (qti << 2)
+    recs[idx] = crec
     dcq = rng.integers(8, 65535 if big else 400, size=(3, 2)).astype(np.uint16)
     rows_arr = np.array(rows, np.int16).reshape(-1, 8) if rows else np.zeros((0, 8), np.int16)
-    return FrameWork(ref_idx, lf_limit, dcq, ncls, recs, rows_arr, unc, coded.astype(np.uint8))
+    return FrameWork(ref_idx, lf_limit, dcq, recs, rows_arr)
 
 
 def random_frames(g, rng):

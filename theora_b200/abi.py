@@ -34,14 +34,11 @@ class Geometry(C.Structure):
 
 class DecFrame(C.Structure):
     _fields_ = [("ref_idx", C.c_int32 * 3), ("lf_limit", C.c_int32), ("dc_quant", (C.c_uint16 * 2) * 3),
-                ("ncls", C.c_int32 * 4), ("nuncoded", C.c_int32), ("ncoeff_rows", C.c_int32),
-                ("recs", C.c_void_p), ("coeff_rows", C.c_void_p), ("uncoded_offs", C.c_void_p),
-                ("coded_map", C.c_void_p)]
+                ("ncoded", C.c_int32), ("ncoeff_rows", C.c_int32), ("recs", C.c_void_p), ("coeff_rows", C.c_void_p)]
 
 
 class Staging(C.Structure):
-    _fields_ = [("recs", C.c_void_p * 4), ("coeff_rows", C.c_void_p), ("uncoded_offs", C.c_void_p),
-                ("coded_map", C.c_void_p)]
+    _fields_ = [("recs", C.c_void_p), ("coeff_rows", C.c_void_p)]
 
 
 REC_DTYPE = np.dtype([("buf_off", "<i4"), ("mv", "<i2"), ("dc", "<i2"), ("coeff_row", "<u4"),
@@ -56,19 +53,19 @@ def cls_of_last_zzi(last_zzi):
     return np.where(lz < 2, 0, np.where(lz <= 3, 1, np.where(lz <= 10, 2, 3))).astype(np.int32)
 
 
-class FrameWork:
-    """One frame of decoder block work held in numpy arrays (keeps them alive)."""
+OCG_FRAG_UNCODED = 3
 
-    def __init__(self, ref_idx, lf_limit, dc_quant, ncls, recs, rows, uncoded, coded_map):
+
+class FrameWork:
+    """One frame of decoder block work held in numpy arrays (keeps them alive):
+    `recs` has one record per fragment, in fragment-index order."""
+
+    def __init__(self, ref_idx, lf_limit, dc_quant, recs, rows):
         self.ref_idx = tuple(int(x) for x in ref_idx)
         self.lf_limit = int(lf_limit)
         self.dc_quant = np.asarray(dc_quant, dtype=np.uint16).reshape(3, 2).copy()
-        self.ncls = tuple(int(x) for x in ncls)
         self.recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
         self.rows = np.ascontiguousarray(rows, dtype=np.int16).reshape(-1, 8)
-        self.uncoded = np.ascontiguousarray(uncoded, dtype=np.int32)
-        self.coded_map = np.ascontiguousarray(coded_map, dtype=np.uint8)
-        assert sum(self.ncls) == len(self.recs)
 
     def as_struct(self):
         f = DecFrame()
@@ -77,34 +74,44 @@ class FrameWork:
             for j in range(2):
                 f.dc_quant[i][j] = int(self.dc_quant[i, j])
         f.lf_limit = self.lf_limit
-        for i in range(4):
-            f.ncls[i] = self.ncls[i]
-        f.nuncoded = len(self.uncoded)
+        f.ncoded = self.ncoded
         f.ncoeff_rows = len(self.rows)
-        f.recs = self.recs.ctypes.data if len(self.recs) else None
+        f.recs = self.recs.ctypes.data
         f.coeff_rows = self.rows.ctypes.data if len(self.rows) else None
-        f.uncoded_offs = self.uncoded.ctypes.data if len(self.uncoded) else None
-        f.coded_map = self.coded_map.ctypes.data
         return f
 
     @property
+    def coded_mask(self):
+        return self.recs["refi"] != OCG_FRAG_UNCODED
+
+    @property
     def ncoded(self):
-        return len(self.recs)
+        return int(self.coded_mask.sum())
+
+    @property
+    def nuncoded(self):
+        return len(self.recs) - self.ncoded
+
+    @property
+    def ncls(self):
+        """Coded fragments per sparsity class (state.c:967 / idct.c:327-329)."""
+        cls = cls_of_last_zzi(self.recs["last_zzi"][self.coded_mask])
+        return tuple(int((cls == k).sum()) for k in range(4))
+
+    def list_bytes(self):
+        return self.recs.nbytes + self.rows.nbytes
 
     def with_refs(self, ref_idx):
-        return FrameWork(ref_idx, self.lf_limit, self.dc_quant, self.ncls, self.recs, self.rows, self.uncoded,
-                         self.coded_map)
+        return FrameWork(ref_idx, self.lf_limit, self.dc_quant, self.recs, self.rows)
 
     def to_dict(self, prefix):
         return {prefix + "ref_idx": np.array(self.ref_idx, np.int32), prefix + "lf": np.array([self.lf_limit], np.int32),
-                prefix + "dcq": self.dc_quant, prefix + "ncls": np.array(self.ncls, np.int32),
-                prefix + "recs": self.recs, prefix + "rows": self.rows, prefix + "unc": self.uncoded,
-                prefix + "map": self.coded_map}
+                prefix + "dcq": self.dc_quant, prefix + "recs": self.recs, prefix + "rows": self.rows}
 
     @staticmethod
     def from_dict(d, prefix):
-        return FrameWork(d[prefix + "ref_idx"], d[prefix + "lf"][0], d[prefix + "dcq"], d[prefix + "ncls"],
-                         d[prefix + "recs"], d[prefix + "rows"], d[prefix + "unc"], d[prefix + "map"])
+        return FrameWork(d[prefix + "ref_idx"], d[prefix + "lf"][0], d[prefix + "dcq"], d[prefix + "recs"],
+                         d[prefix + "rows"])
 
 
 _PROTOS = {

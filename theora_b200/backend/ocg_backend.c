@@ -41,11 +41,11 @@ typedef struct ocg_backend {
   ocg_geometry       geom;
   ocg_staging        st;
   void              *heap_staging; /* record mode only */
+  ocg_frag_rec      *heap_tmpl;    /* record mode only */
   int                mode;
   int                frame_open;
-  int                ncls[OCG_NCLS];
+  int                ncoded;
   int                nrows;
-  int                nunc;
   int                ref_idx[3];
   ogg_uint16_t       dcq[3][2];
   unsigned char      dev_valid[6];
@@ -96,11 +96,10 @@ static void backend_fatal(const char *what) {
 }
 
 static void stats_add(const ocg_backend *b, long h2d, long d2h, double secs) {
-  int k;
   pthread_mutex_lock(&g_stats_lock);
   g_stats.frames++;
-  for (k = 0; k < OCG_NCLS; k++) g_stats.coded_frags += b->ncls[k];
-  g_stats.uncoded_frags += b->nunc;
+  g_stats.coded_frags += b->ncoded;
+  g_stats.uncoded_frags += b->geom.nfrags - b->ncoded;
   g_stats.coeff_rows += b->nrows;
   g_stats.h2d_bytes += h2d;
   g_stats.d2h_bytes += d2h;
@@ -112,10 +111,12 @@ static void stats_add(const ocg_backend *b, long h2d, long d2h, double secs) {
 static void backend_begin_frame(ocg_backend *b) {
   const oc_theora_state *st = &b->dec->state;
   int i;
-  if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
-  memset(b->ncls, 0, sizeof(b->ncls));
-  b->nrows = b->nunc = 0;
-  memset(b->st.coded_map, 0, (size_t)b->geom.nfrags);
+  /* staging comes back with every fragment marked uncoded; the recon hook
+     overwrites the coded ones, so oc_frag_copy_list needs no recording */
+  if (b->ctx != NULL) {
+    if (ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
+  } else memcpy(b->st.recs, b->heap_tmpl, (size_t)b->geom.nfrags * sizeof(ocg_frag_rec));
+  b->ncoded = b->nrows = 0;
   /* decode.c:2790-2794 has already picked SELF; GOLD/PREV are still the
      references this frame predicts from (they rotate at 2947-2962). */
   for (i = 0; i < 3; i++) b->ref_idx[i] = st->ref_frame_idx[i];
@@ -132,15 +133,14 @@ static void backend_flush(ocg_backend *b) {
   for (i = 0; i < 3; i++) f.ref_idx[i] = b->ref_idx[i];
   f.lf_limit = st->loop_filter_limits[st->qis[0]];
   for (i = 0; i < 3; i++) for (k = 0; k < 2; k++) f.dc_quant[i][k] = b->dcq[i][k];
-  for (k = 0; k < OCG_NCLS; k++) f.ncls[k] = b->ncls[k];
-  f.nuncoded = b->nunc;
+  f.ncoded = b->ncoded;
   f.ncoeff_rows = b->nrows;
   b->frame_open = 0;
   if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
   if (b->ctx == NULL) { stats_add(b, 0, 0, 0.0); return; } /* record mode */
   {
     unsigned char *host_self = st->ref_frame_handle + (size_t)f.ref_idx[OCG_FRAME_SELF] * (size_t)b->geom.ref_frame_sz;
-    long ncoded = 0, extra_h2d = 0;
+    long extra_h2d = 0;
     /* A reference the device has never produced (stream starting on an inter
        frame: oc_dec_init_dummy_frame, decode.c:2053) is taken from the host. */
     if (st->frame_type != OC_INTRA_FRAME) {
@@ -157,9 +157,8 @@ static void backend_flush(ocg_backend *b) {
     if (ocg_dec_submit(b->ctx, &f, host_self) < 0) backend_fatal("ocg_dec_submit failed");
     if (ocg_ctx_sync(b->ctx) < 0) backend_fatal("ocg_ctx_sync failed");
     b->dev_valid[f.ref_idx[OCG_FRAME_SELF]] = 1;
-    for (k = 0; k < OCG_NCLS; k++) ncoded += b->ncls[k];
-    stats_add(b, extra_h2d + ncoded * 16 + (long)b->nrows * 16 + (long)b->nunc * 4 + (f.lf_limit ? b->geom.nfrags : 0),
-              (long)b->geom.ref_frame_sz, now_s() - t0);
+    stats_add(b, extra_h2d + (long)b->geom.nfrags * 16 + (long)b->nrows * 16, (long)b->geom.ref_frame_sz,
+              now_s() - t0);
   }
   /* the stripe callback, once, with the whole (now final) frame:
      decode.c:2936-2940 flips the row range, the telemetry path at 2975 already
@@ -190,13 +189,13 @@ static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi
   ocg_backend *b = backend_of(_state);
   const oc_fragment *frag = _state->frags + _fragi;
   ocg_frag_rec *rec;
-  int cls, nr, r, qti, mask = 0;
+  int nr, r, qti, mask = 0;
   ogg_int16_t dc = _dct_coeffs[0];
   if (b == NULL || !b->frame_open) backend_fatal("state_frag_recon outside a frame");
-  /* class selection of state.c:967 and idct.c:327-329 */
-  cls = _last_zzi < 2 ? OCG_CLS_DC : (_last_zzi <= 3 ? OCG_CLS_3 : (_last_zzi <= 10 ? OCG_CLS_10 : OCG_CLS_FULL));
-  nr = cls == OCG_CLS_DC ? 0 : (cls == OCG_CLS_3 ? 2 : (cls == OCG_CLS_10 ? 4 : 8));
-  rec = b->st.recs[cls] + b->ncls[cls]++;
+  /* footprint of the transform the reference would run (state.c:967,
+     idct.c:327-329): 0, 2, 4 or 8 leading rows */
+  nr = _last_zzi < 2 ? 0 : (_last_zzi <= 3 ? 2 : (_last_zzi <= 10 ? 4 : 8));
+  rec = b->st.recs + _fragi;
   rec->coeff_row = (ogg_uint32_t)b->nrows;
   _dct_coeffs[0] = 0; /* DC travels in the record */
   for (r = 0; r < nr; r++) {
@@ -211,7 +210,7 @@ static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi
     }
   }
   qti = frag->mb_mode != OC_MODE_INTRA;
-  rec->buf_off = (ogg_int32_t)_state->frag_buf_offs[_fragi];
+  /* buf_off and the plane are already in the record (template) */
   rec->mv = _state->frag_mvs[_fragi];
   rec->dc = dc;
   rec->rowmask = (unsigned char)mask;
@@ -219,19 +218,14 @@ static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi
   rec->refi = (unsigned char)frag->refi;
   rec->pli_qti = (unsigned char)(_pli | qti << 2);
   b->dcq[_pli][qti] = _dc_quant;
-  b->st.coded_map[_fragi] = 1;
+  b->ncoded++;
 }
 
 static void ocg_frag_copy_list(unsigned char *_dst_frame, const unsigned char *_src_frame, int _ystride,
                                const ptrdiff_t *_fragis, ptrdiff_t _nfragis, const ptrdiff_t *_frag_buf_offs) {
-  ocg_backend *b = t_cur;
-  ptrdiff_t i;
-  ogg_int32_t *out;
-  (void)_dst_frame; (void)_src_frame; (void)_ystride;
-  if (b == NULL || !b->frame_open) backend_fatal("frag_copy_list outside a frame");
-  out = b->st.uncoded_offs + b->nunc;
-  for (i = 0; i < _nfragis; i++) out[i] = (ogg_int32_t)_frag_buf_offs[_fragis[i]];
-  b->nunc += (int)_nfragis;
+  /* Uncoded fragments are whatever state_frag_recon did not record: the
+     device copies them PREV -> SELF from the pre-filled records. */
+  (void)_dst_frame; (void)_src_frame; (void)_ystride; (void)_fragis; (void)_nfragis; (void)_frag_buf_offs;
 }
 
 static void ocg_state_loop_filter_frag_rows(const oc_theora_state *_state, signed char _bv[256], int _refi,
@@ -311,15 +305,23 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
     }
     b->pinned = ocg_host_register(st->ref_frame_handle, (size_t)b->geom.ref_frame_sz * 3) == 0;
   } else {
-    size_t nf = (size_t)b->geom.nfrags, off = 0;
-    unsigned char *p = (unsigned char *)malloc(nf * (4 * 16 + 128 + 4 + 1) + 64);
-    int k;
+    size_t nf = (size_t)b->geom.nfrags, i;
+    unsigned char *p = (unsigned char *)malloc(nf * (16 + 16 + 128) + 64);
+    int pli;
     if (p == NULL) { free(b); return; }
     b->heap_staging = p;
-    for (k = 0; k < OCG_NCLS; k++) { b->st.recs[k] = (ocg_frag_rec *)(p + off); off += nf * 16; }
-    b->st.coeff_rows = (int16_t *)(p + off); off += nf * 128;
-    b->st.uncoded_offs = (int32_t *)(p + off); off += nf * 4;
-    b->st.coded_map = p + off;
+    b->st.recs = (ocg_frag_rec *)p;
+    b->heap_tmpl = (ocg_frag_rec *)(p + nf * 16);
+    b->st.coeff_rows = (int16_t *)(p + nf * 32);
+    memset(b->heap_tmpl, 0, nf * 16);
+    for (pli = 0; pli < 3; pli++) {
+      for (i = 0; i < (size_t)b->geom.planes[pli].nfrags; i++) {
+        ocg_frag_rec *rc = b->heap_tmpl + b->geom.planes[pli].froffset + i;
+        rc->buf_off = (ogg_int32_t)st->frag_buf_offs[b->geom.planes[pli].froffset + i];
+        rc->refi = OCG_FRAG_UNCODED;
+        rc->pli_qti = (unsigned char)pli;
+      }
+    }
   }
   st->opt_vtable.state_frag_recon = ocg_state_frag_recon;
   st->opt_vtable.frag_copy_list = ocg_frag_copy_list;

@@ -30,11 +30,9 @@ int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
 constexpr int kSlots = 2;
 
 struct Slot {
-  ocg_frag_rec *recs[OCG_NCLS] = {nullptr, nullptr, nullptr, nullptr};
-  int16_t *rows = nullptr;
-  int32_t *unc = nullptr;
-  uint8_t *map = nullptr;
-  OcgJobDev *job = nullptr; /* pinned */
+  ocg_frag_rec *recs = nullptr; /* pinned, nfrags */
+  int16_t *rows = nullptr;      /* pinned, nfrags*8 rows */
+  OcgJobDev *job = nullptr;     /* pinned */
   cudaEvent_t consumed = nullptr;
   bool busy = false;
 };
@@ -50,9 +48,9 @@ struct ocg_ctx {
   /* device-side lists for single-frame submits */
   ocg_frag_rec *d_recs = nullptr;
   int16_t *d_rows = nullptr;
-  int32_t *d_unc = nullptr;
-  uint8_t *d_map = nullptr;
+  uint8_t *d_map = nullptr;  /* coded map, produced by the recon kernel */
   OcgJobDev *d_job = nullptr;
+  ocg_frag_rec *tmpl = nullptr; /* host: every fragment uncoded, buf_off/plane filled in */
   Slot slots[kSlots];
   int cur_slot = 0;      /* slot handed out by the last ocg_dec_staging */
   bool staged = false;
@@ -61,6 +59,7 @@ struct ocg_ctx {
 struct ocg_pack {
   int device = 0;
   int nframes = 0;
+  int nfrags = 0;
   std::vector<ocg_dec_frame> frames; /* pointers are device pointers */
   uint8_t *blob = nullptr;
   size_t blob_sz = 0;
@@ -71,7 +70,7 @@ void ocg_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed
 /* ------------------------------------------------------------------------ */
 static void geom_to_dev(const ocg_geometry &g, OcgGeomDev &d) {
   memset(&d, 0, sizeof(d));
-  int cell_rows = 0, border_rows = 0, maxcx = 0;
+  int cell_rows = 0, maxcx = 0;
   for (int pli = 0; pli < 3; pli++) {
     const ocg_plane_geom &p = g.planes[pli];
     OcgPlaneDev &q = d.p[pli];
@@ -87,49 +86,31 @@ static void geom_to_dev(const ocg_geometry &g, OcgGeomDev &d) {
     q.lo_off = (int32_t)(p.plane_off + (int64_t)(p.height - 1) * p.ystride);
     q.cell_row0 = cell_rows;
     cell_rows += p.nvfrags + 1;
-    border_rows += p.height + 2 * p.vpad;
     if (p.nhfrags + 1 > maxcx) maxcx = p.nhfrags + 1;
   }
   d.qx = !(g.pixel_fmt & 1);
   d.qy = !(g.pixel_fmt & 2);
   d.cell_rows = cell_rows;
   d.max_cells_x = maxcx;
-  d.border_rows = border_rows;
+  d.nfrags = g.nfrags;
 }
 
-static void fill_job(OcgJobDev &j, uint8_t *frames, const ocg_geometry &g, const ocg_dec_frame &f,
-                     const ocg_frag_rec *recs, const int16_t *rows, const int32_t *unc, const uint8_t *map) {
+static void fill_job(OcgJobDev &j, const ocg_ctx *c, const ocg_dec_frame &f, const ocg_frag_rec *recs,
+                     const int16_t *rows) {
   memset(&j, 0, sizeof(j));
   for (int i = 0; i < 3; i++)
-    j.base[i] = f.ref_idx[i] >= 0 ? frames + (int64_t)f.ref_idx[i] * g.ref_frame_sz + g.base_off : nullptr;
+    j.base[i] = f.ref_idx[i] >= 0 ? c->frames + (int64_t)f.ref_idx[i] * c->geom.ref_frame_sz + c->geom.base_off
+                                  : nullptr;
   j.recs = recs;
   j.rows = rows;
-  j.unc = unc;
-  j.coded = map;
-  int blk = 0, rec = 0;
-  const int per = OCG_RECON_THREADS / 4;
-  for (int c = 0; c < OCG_NCLS; c++) {
-    j.rec_start[c] = rec;
-    j.ncls[c] = f.ncls[c];
-    rec += f.ncls[c];
-    blk += (f.ncls[c] + per - 1) / per;
-    j.blk_end[c] = blk;
-  }
-  j.nunc = f.nuncoded;
-  blk += (f.nuncoded + per - 1) / per;
-  j.blk_end[4] = blk;
+  j.coded = c->d_map;
   j.lf_limit = f.lf_limit;
   for (int p = 0; p < 3; p++)
     for (int q = 0; q < 2; q++) j.dcq[p][q] = f.dc_quant[p][q];
 }
 
 static int check_frame(const ocg_geometry &g, const ocg_dec_frame &f) {
-  long ncoded = 0;
-  for (int c = 0; c < OCG_NCLS; c++) {
-    if (f.ncls[c] < 0) return fail(OCG_EINVAL, "negative class count");
-    ncoded += f.ncls[c];
-  }
-  if (ncoded > g.nfrags || f.nuncoded < 0 || f.nuncoded > g.nfrags) return fail(OCG_EINVAL, "more fragments than the frame holds");
+  if (f.ncoded < 0 || f.ncoded > g.nfrags) return fail(OCG_EINVAL, "coded fragment count out of range");
   if (f.ncoeff_rows < 0 || f.ncoeff_rows > (long)g.nfrags * 8) return fail(OCG_EINVAL, "coefficient row count out of range");
   if (f.ref_idx[OCG_FRAME_SELF] < 0 || f.ref_idx[OCG_FRAME_SELF] >= g.nrefs) return fail(OCG_EINVAL, "bad SELF buffer index");
   for (int i = 0; i < 2; i++)
@@ -164,10 +145,10 @@ static void timed_stage(int stage, cudaStream_t st, F &&launch) {
   g_spans.push_back(sp);
 }
 
-static void launch_stages(const OcgGeomDev &gd, const OcgJobDev *jobs, int njobs, int max_blocks, bool any_lf,
-                          cudaStream_t st) {
+static void launch_stages(const OcgGeomDev &gd, const OcgJobDev *jobs, int njobs, bool any_lf, cudaStream_t st) {
   const int mask = g_stage_mask.load(std::memory_order_relaxed);
-  if (mask & 1) timed_stage(0, st, [&] { ocg_launch_recon(gd, jobs, njobs, max_blocks, st); });
+  if (mask & 1) timed_stage(0, st, [&] { ocg_launch_recon(gd, jobs, njobs, st); });
+  else if ((mask & 2) && any_lf) ocg_launch_codedmap(gd, jobs, njobs, st);
   if ((mask & 2) && any_lf) timed_stage(1, st, [&] { ocg_launch_loop_filter(gd, jobs, njobs, st); });
   if (mask & 4) timed_stage(2, st, [&] { ocg_launch_borders(gd, jobs, njobs, st); });
 }
@@ -266,19 +247,17 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (Slot &s : c->slots) {
-    for (int k = 0; k < OCG_NCLS; k++) if (s.recs[k]) cudaFreeHost(s.recs[k]);
+    if (s.recs) cudaFreeHost(s.recs);
     if (s.rows) cudaFreeHost(s.rows);
-    if (s.unc) cudaFreeHost(s.unc);
-    if (s.map) cudaFreeHost(s.map);
     if (s.job) cudaFreeHost(s.job);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
   cudaFree(c->frames);
   cudaFree(c->d_recs);
   cudaFree(c->d_rows);
-  cudaFree(c->d_unc);
   cudaFree(c->d_map);
   cudaFree(c->d_job);
+  free(c->tmpl);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -315,16 +294,29 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   CUX(cudaMemsetAsync(c->frames, 0x80, pool, c->stream));
   CUX(cudaMalloc(&c->d_recs, nf * sizeof(ocg_frag_rec)));
   CUX(cudaMalloc(&c->d_rows, nf * 8 * 16));
-  CUX(cudaMalloc(&c->d_unc, nf * sizeof(int32_t)));
   CUX(cudaMalloc(&c->d_map, nf));
   CUX(cudaMalloc(&c->d_job, sizeof(OcgJobDev)));
   for (Slot &s : c->slots) {
-    for (int k = 0; k < OCG_NCLS; k++) CUX(cudaHostAlloc(&s.recs[k], nf * sizeof(ocg_frag_rec), cudaHostAllocDefault));
+    CUX(cudaHostAlloc(&s.recs, nf * sizeof(ocg_frag_rec), cudaHostAllocDefault));
     CUX(cudaHostAlloc(&s.rows, nf * 8 * 16, cudaHostAllocDefault));
-    CUX(cudaHostAlloc(&s.unc, nf * sizeof(int32_t), cudaHostAllocDefault));
-    CUX(cudaHostAlloc(&s.map, nf, cudaHostAllocDefault));
     CUX(cudaHostAlloc(&s.job, sizeof(OcgJobDev), cudaHostAllocDefault));
     CUX(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+  }
+  /* record template: every fragment uncoded, offsets and planes filled in */
+  c->tmpl = (ocg_frag_rec *)calloc(nf, sizeof(ocg_frag_rec));
+  if (c->tmpl == nullptr) { ocg_ctx_destroy(c); return fail(OCG_ENOMEM, "out of memory"); }
+  {
+    std::vector<int32_t> offs(nf);
+    ocg_geometry_frag_buf_offs(g, offs.data());
+    for (int pli = 0; pli < 3; pli++) {
+      const ocg_plane_geom &p = g->planes[pli];
+      for (int i = 0; i < p.nfrags; i++) {
+        ocg_frag_rec &rc = c->tmpl[p.froffset + i];
+        rc.buf_off = offs[(size_t)(p.froffset + i)];
+        rc.refi = OCG_FRAG_UNCODED;
+        rc.pli_qti = (uint8_t)pli;
+      }
+    }
   }
   CUX(cudaStreamSynchronize(c->stream));
 #undef CUX
@@ -405,10 +397,9 @@ OCG_API int ocg_dec_staging(ocg_ctx *c, ocg_staging *out) {
   int r = acquire_slot(c);
   if (r < 0) return r;
   Slot &s = c->slots[c->cur_slot];
-  for (int k = 0; k < OCG_NCLS; k++) out->recs[k] = s.recs[k];
+  memcpy(s.recs, c->tmpl, (size_t)c->geom.nfrags * sizeof(ocg_frag_rec));
+  out->recs = s.recs;
   out->coeff_rows = s.rows;
-  out->uncoded_offs = s.unc;
-  out->coded_map = s.map;
   c->staged = true;
   return OCG_OK;
 }
@@ -418,46 +409,27 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
   int r = check_frame(c->geom, *f);
   if (r < 0) return r;
   CU(cudaSetDevice(c->device));
-  long ncoded = 0;
-  for (int k = 0; k < OCG_NCLS; k++) ncoded += f->ncls[k];
-  const bool from_staging = c->staged && f->recs == nullptr && f->coeff_rows == nullptr &&
-                            f->uncoded_offs == nullptr && f->coded_map == nullptr;
+  const bool from_staging = c->staged && f->recs == nullptr && f->coeff_rows == nullptr;
   if (!from_staging) {
-    if ((ncoded && !f->recs) || (f->ncoeff_rows && !f->coeff_rows) || (f->nuncoded && !f->uncoded_offs) ||
-        (f->lf_limit && !f->coded_map))
-      return fail(OCG_EFAULT, "NULL list pointer (and no staged lists)");
+    if (!f->recs || (f->ncoeff_rows && !f->coeff_rows)) return fail(OCG_EFAULT, "NULL list pointer (and no staged lists)");
     r = acquire_slot(c);
     if (r < 0) return r;
   }
   Slot &s = c->slots[c->cur_slot];
   c->staged = false;
   cudaStream_t st = c->stream;
-  /* H2D: per-class rec regions land contiguously, sorted by class. */
-  size_t rec_at = 0;
-  for (int k = 0; k < OCG_NCLS; k++) {
-    const size_t n = (size_t)f->ncls[k];
-    if (n == 0) continue;
-    if (!from_staging) memcpy(s.recs[k], f->recs + rec_at, n * sizeof(ocg_frag_rec));
-    CU(cudaMemcpyAsync(c->d_recs + rec_at, s.recs[k], n * sizeof(ocg_frag_rec), cudaMemcpyHostToDevice, st));
-    rec_at += n;
-  }
+  const size_t nf = (size_t)c->geom.nfrags;
+  if (!from_staging) memcpy(s.recs, f->recs, nf * sizeof(ocg_frag_rec));
+  CU(cudaMemcpyAsync(c->d_recs, s.recs, nf * sizeof(ocg_frag_rec), cudaMemcpyHostToDevice, st));
   if (f->ncoeff_rows) {
     if (!from_staging) memcpy(s.rows, f->coeff_rows, (size_t)f->ncoeff_rows * 16);
     CU(cudaMemcpyAsync(c->d_rows, s.rows, (size_t)f->ncoeff_rows * 16, cudaMemcpyHostToDevice, st));
   }
-  if (f->nuncoded) {
-    if (!from_staging) memcpy(s.unc, f->uncoded_offs, (size_t)f->nuncoded * 4);
-    CU(cudaMemcpyAsync(c->d_unc, s.unc, (size_t)f->nuncoded * 4, cudaMemcpyHostToDevice, st));
-  }
-  if (f->lf_limit) {
-    if (!from_staging) memcpy(s.map, f->coded_map, (size_t)c->geom.nfrags);
-    CU(cudaMemcpyAsync(c->d_map, s.map, (size_t)c->geom.nfrags, cudaMemcpyHostToDevice, st));
-  }
-  fill_job(*s.job, c->frames, c->geom, *f, c->d_recs, c->d_rows, c->d_unc, c->d_map);
+  fill_job(*s.job, c, *f, c->d_recs, c->d_rows);
   CU(cudaMemcpyAsync(c->d_job, s.job, sizeof(OcgJobDev), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(s.consumed, st));
   s.busy = true;
-  launch_stages(c->gdev, c->d_job, 1, s.job->blk_end[4], f->lf_limit != 0, st);
+  launch_stages(c->gdev, c->d_job, 1, f->lf_limit != 0, st);
   CU(cudaGetLastError());
   if (host_out != nullptr) {
     CU(cudaMemcpyAsync(host_out, c->frames + (size_t)f->ref_idx[OCG_FRAME_SELF] * c->geom.ref_frame_sz,
@@ -484,17 +456,13 @@ OCG_API int ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nfr
   if (nframes <= 0 || nfrags <= 0) return fail(OCG_EINVAL, "empty pack");
   CU(cudaSetDevice(device));
   size_t total = 0;
-  for (int i = 0; i < nframes; i++) {
-    const ocg_dec_frame &f = frames[i];
-    size_t nrec = 0;
-    for (int k = 0; k < OCG_NCLS; k++) nrec += (size_t)f.ncls[k];
-    total += align256(nrec * sizeof(ocg_frag_rec)) + align256((size_t)f.ncoeff_rows * 16) +
-             align256((size_t)f.nuncoded * 4) + align256((size_t)nfrags);
-  }
+  for (int i = 0; i < nframes; i++)
+    total += align256((size_t)nfrags * sizeof(ocg_frag_rec)) + align256((size_t)frames[i].ncoeff_rows * 16);
   ocg_pack *p = new (std::nothrow) ocg_pack();
   if (p == nullptr) return fail(OCG_ENOMEM, "out of memory");
   p->device = device;
   p->nframes = nframes;
+  p->nfrags = nfrags;
   p->blob_sz = total;
   cudaError_t e = cudaMalloc(&p->blob, total ? total : 256);
   if (e != cudaSuccess) { delete p; return fail(OCG_ECUDA, "cudaMalloc(pack)", e); }
@@ -503,13 +471,9 @@ OCG_API int ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nfr
   for (int i = 0; i < nframes; i++) {
     const ocg_dec_frame &f = frames[i];
     ocg_dec_frame d = f;
-    size_t nrec = 0;
-    for (int k = 0; k < OCG_NCLS; k++) nrec += (size_t)f.ncls[k];
-    struct Part { const void *src; size_t n; const void **dst; } parts[4] = {
-        {f.recs, nrec * sizeof(ocg_frag_rec), (const void **)&d.recs},
-        {f.coeff_rows, (size_t)f.ncoeff_rows * 16, (const void **)&d.coeff_rows},
-        {f.uncoded_offs, (size_t)f.nuncoded * 4, (const void **)&d.uncoded_offs},
-        {f.coded_map, (size_t)nfrags, (const void **)&d.coded_map}};
+    struct Part { const void *src; size_t n; const void **dst; } parts[2] = {
+        {f.recs, (size_t)nfrags * sizeof(ocg_frag_rec), (const void **)&d.recs},
+        {f.coeff_rows, (size_t)f.ncoeff_rows * 16, (const void **)&d.coeff_rows}};
     for (Part &pt : parts) {
       *pt.dst = p->blob + at;
       if (pt.n) {
@@ -557,7 +521,6 @@ OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, cons
     bs.cap = n;
     bs.device = c0->device;
   }
-  int max_blocks = 0;
   bool any_lf = false;
   for (int i = 0; i < n; i++) {
     ocg_ctx *c = ctxs[i];
@@ -565,16 +528,16 @@ OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, cons
     if (c == nullptr || p == nullptr) return fail(OCG_EFAULT, "NULL job");
     if (c->device != c0->device || p->device != c0->device) return fail(OCG_EINVAL, "batch spans devices");
     if (memcmp(&c->geom, &c0->geom, sizeof(ocg_geometry)) != 0) return fail(OCG_EINVAL, "batch mixes geometries");
+    if (p->nfrags != c->geom.nfrags) return fail(OCG_EINVAL, "pack was built for another geometry");
     if (frame_idx[i] < 0 || frame_idx[i] >= p->nframes) return fail(OCG_EINVAL, "frame index out of range");
     const ocg_dec_frame &f = p->frames[(size_t)frame_idx[i]];
     int r = check_frame(c->geom, f);
     if (r < 0) return r;
-    fill_job(bs.h[i], c->frames, c->geom, f, f.recs, f.coeff_rows, f.uncoded_offs, f.coded_map);
-    if (bs.h[i].blk_end[4] > max_blocks) max_blocks = bs.h[i].blk_end[4];
+    fill_job(bs.h[i], c, f, f.recs, f.coeff_rows);
     any_lf |= f.lf_limit != 0;
   }
   CU(cudaMemcpyAsync(bs.d, bs.h, sizeof(OcgJobDev) * (size_t)n, cudaMemcpyHostToDevice, st));
-  launch_stages(c0->gdev, bs.d, n, max_blocks, any_lf, st);
+  launch_stages(c0->gdev, bs.d, n, any_lf, st);
   CU(cudaGetLastError());
   /* the job table (host and device copy) is free again once the kernels ran */
   CU(cudaEventRecord(bs.done, st));

@@ -10,9 +10,12 @@
  *                     order-free "corner cell" form.
  *  ocg_border_kernel  apron replication (state.c:770-835).
  *
- * Work mapping of the recon kernel: a fragment is handled by 4 adjacent lanes,
- * lane l owning rows 2l and 2l+1, so a warp covers 8 fragments and a 256-thread
- * CTA 64.  The two 1-D passes run in registers; the transposes between them
+ * Work mapping of the recon kernel: a CTA owns 64 consecutive fragments of the
+ * frame's raster-indexed record array, partitions them by work class in shared
+ * memory (stable, so raster neighbours stay neighbours and the 64-bit row
+ * stores of adjacent lanes coalesce), then a fragment is handled by 4 adjacent
+ * lanes, lane l owning rows 2l and 2l+1 (a warp covers 8 fragments).
+ * The two 1-D passes run in registers; the transposes between them
  * are two __shfl_xor stages on 16-bit pairs; the final add/clamp uses the
  * packed-halfword DPX instructions (VIADDMNMX.S16x2.RELU / VIMNMX.S16x2).
  * All loads/stores are 64- or 128-bit.  There is no dense contraction here, so
@@ -146,15 +149,10 @@ __device__ __forceinline__ uint2 recon_row(uint32_t r0, uint32_t r1, uint32_t r2
   return make_uint2(__byte_perm(o0, o1, 0x6420), __byte_perm(o2, o3, 0x6420));
 }
 
-__device__ __forceinline__ int plane_of(const OcgGeomDev &g, int off) {
-  return off >= g.p[2].lo_off ? 2 : (off >= g.p[1].lo_off ? 1 : 0);
-}
-
 /* One coded fragment.  CLS follows state.c:967 / idct.c:327-329. */
 template <int CLS>
-__device__ __forceinline__ void recon_fragment(const OcgGeomDev &g, const OcgJobDev &job, int reci, int l,
+__device__ __forceinline__ void recon_fragment(const OcgGeomDev &g, const OcgJobDev &job, const int4 rw, int l,
                                                unsigned gmask) {
-  const int4 rw = __ldg((const int4 *)(job.recs + reci));
   const int buf_off = rw.x;
   const int mv = rw.y << 16 >> 16;
   const int dc = rw.y >> 16;
@@ -250,39 +248,82 @@ __device__ __forceinline__ void recon_fragment(const OcgGeomDev &g, const OcgJob
   *(uint2 *)(dst + ystride) = ob;
 }
 
+/* Work classes inside a CTA, in processing order. */
+enum { WC_COPY = 0, WC_DC = 1, WC_3 = 2, WC_10 = 3, WC_FULL = 4, WC_NONE = 5 };
+
+__device__ __forceinline__ int work_class(const int4 rw) {
+  const int refi = (rw.w >> 16) & 0xFF, lz = (rw.w >> 8) & 0xFF;
+  if (refi == OCG_FRAG_UNCODED) return WC_COPY;
+  /* state.c:967 and idct.c:327-329 */
+  return lz < 2 ? WC_DC : (lz <= 3 ? WC_3 : (lz <= 10 ? WC_10 : WC_FULL));
+}
+
 __global__ void __launch_bounds__(OCG_RECON_THREADS)
 ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  __shared__ int4 srec[OCG_FRAGS_PER_BLOCK];
+  __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
+  __shared__ int scnt[2][WC_NONE];
   const OcgJobDev &job = jobs[blockIdx.y];
-  const int b = (int)blockIdx.x;
-  if (b >= job.blk_end[4]) return;
-  const int lane = threadIdx.x & 31;
+  const int f0 = (int)blockIdx.x * OCG_FRAGS_PER_BLOCK;
+  const int nvalid = min(OCG_FRAGS_PER_BLOCK, g.nfrags - f0);
+  const int t = (int)threadIdx.x;
+  const int lane = t & 31;
+  /* ---- stage 1: the first two warps fetch the 64 records (1 KB, coalesced),
+          classify them and publish the coded map for the loop filter ---- */
+  int cls = WC_NONE;
+  unsigned mine = 0;
+  if (t < OCG_FRAGS_PER_BLOCK) {
+    if (t < nvalid) {
+      const int4 rw = __ldg((const int4 *)(job.recs + f0 + t));
+      srec[t] = rw;
+      cls = work_class(rw);
+      job.coded[f0 + t] = (unsigned char)(cls != WC_COPY);
+    }
+#pragma unroll
+    for (int c = 0; c < WC_NONE; c++) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+      if (cls == c) mine = m;
+      if (lane == 0) scnt[t >> 5][c] = __popc(m);
+    }
+  }
+  __syncthreads();
+  /* ---- stage 2: stable partition by class (raster order kept inside a class) ---- */
+  if (cls != WC_NONE) {
+    int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
+    for (int c = 0; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
+    sorder[pos] = (unsigned char)t;
+  }
+  __syncthreads();
+  /* ---- stage 3: 4 lanes per fragment ---- */
+  const int gi = t >> 2;
+  if (gi >= nvalid) return;
   const int l = lane & 3;
   const unsigned gmask = 0xFu << (lane & 28);
-  const int slot = threadIdx.x >> 2; /* fragment slot inside the CTA, 0..63 */
-  int cls = 0;
-  while (b >= job.blk_end[cls]) cls++;
-  const int idx = (b - (cls ? job.blk_end[cls - 1] : 0)) * (OCG_RECON_THREADS / 4) + slot;
-  if (cls == 4) {
-    /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
-    if (idx >= job.nunc) return;
-    const int off = __ldg(job.unc + idx);
-    const int ystride = g.p[plane_of(g, off)].ystride;
-    const uint8_t *src = job.base[OCG_FRAME_PREV] + off + (2 * l) * ystride;
-    uint8_t *dst = job.base[OCG_FRAME_SELF] + off + (2 * l) * ystride;
-    const uint2 a = __ldg((const uint2 *)src);
-    const uint2 c = __ldg((const uint2 *)(src + ystride));
-    *(uint2 *)dst = a;
-    *(uint2 *)(dst + ystride) = c;
-    return;
+  const int4 rw = srec[sorder[gi]];
+  switch (work_class(rw)) {
+    case WC_COPY: {
+      /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
+      const int ystride = g.p[(rw.w >> 24) & 3].ystride;
+      const uint8_t *src = job.base[OCG_FRAME_PREV] + rw.x + (2 * l) * ystride;
+      uint8_t *dst = job.base[OCG_FRAME_SELF] + rw.x + (2 * l) * ystride;
+      const uint2 a = __ldg((const uint2 *)src);
+      const uint2 c = __ldg((const uint2 *)(src + ystride));
+      *(uint2 *)dst = a;
+      *(uint2 *)(dst + ystride) = c;
+    } break;
+    case WC_DC: recon_fragment<OCG_CLS_DC>(g, job, rw, l, gmask); break;
+    case WC_3: recon_fragment<OCG_CLS_3>(g, job, rw, l, gmask); break;
+    case WC_10: recon_fragment<OCG_CLS_10>(g, job, rw, l, gmask); break;
+    default: recon_fragment<OCG_CLS_FULL>(g, job, rw, l, gmask); break;
   }
-  if (idx >= job.ncls[cls]) return;
-  const int reci = job.rec_start[cls] + idx;
-  switch (cls) {
-    case OCG_CLS_DC: recon_fragment<OCG_CLS_DC>(g, job, reci, l, gmask); break;
-    case OCG_CLS_3: recon_fragment<OCG_CLS_3>(g, job, reci, l, gmask); break;
-    case OCG_CLS_10: recon_fragment<OCG_CLS_10>(g, job, reci, l, gmask); break;
-    default: recon_fragment<OCG_CLS_FULL>(g, job, reci, l, gmask); break;
-  }
+}
+
+/* Only the coded map (for running the loop filter stage on its own). */
+__global__ void __launch_bounds__(256)
+ocg_codedmap_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  const OcgJobDev &job = jobs[blockIdx.y];
+  const int f = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (f < g.nfrags) job.coded[f] = (unsigned char)(job.recs[f].refi != OCG_FRAG_UNCODED);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -444,10 +485,17 @@ ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
 
 } /* namespace */
 
-void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, int max_blocks, cudaStream_t st) {
-  if (max_blocks <= 0 || njobs <= 0) return;
-  dim3 grid((unsigned)max_blocks, (unsigned)njobs);
+void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return;
+  dim3 grid((unsigned)((g.nfrags + OCG_FRAGS_PER_BLOCK - 1) / OCG_FRAGS_PER_BLOCK), (unsigned)njobs);
   ocg_recon_kernel<<<grid, OCG_RECON_THREADS, 0, st>>>(g, jobs);
+  ocg_count_launch(1);
+}
+
+void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return;
+  dim3 grid((unsigned)((g.nfrags + 255) / 256), (unsigned)njobs);
+  ocg_codedmap_kernel<<<grid, 256, 0, st>>>(g, jobs);
   ocg_count_launch(1);
 }
 

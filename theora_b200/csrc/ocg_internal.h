@@ -21,29 +21,24 @@ struct OcgGeomDev {
   int32_t qx, qy;       /* chroma decimated horizontally / vertically */
   int32_t cell_rows;    /* sum over planes of (nvfrags+1) */
   int32_t max_cells_x;  /* max over planes of (nhfrags+1) */
-  int32_t border_rows;  /* sum over planes of (height + 2*vpad) */
+  int32_t nfrags;
 };
 
 /* One (context, frame) job of a batch; lives in device memory. */
 struct OcgJobDev {
-  uint8_t            *base[3];       /* GOLD, PREV, SELF: buffer + base_off */
-  const ocg_frag_rec *recs;
+  uint8_t            *base[3];   /* GOLD, PREV, SELF: buffer + base_off */
+  const ocg_frag_rec *recs;      /* nfrags, fragment-index order */
   const int16_t      *rows;
-  const int32_t      *unc;
-  const uint8_t      *coded;
-  int32_t             blk_end[5];    /* cumulative 32-fragment block counts: classes 0..3, then copy */
-  int32_t             rec_start[4];  /* first rec of each class */
-  int32_t             ncls[4];
-  int32_t             nunc;
+  uint8_t            *coded;     /* nfrags bytes: written by the recon kernel, read by the loop filter */
   int32_t             lf_limit;
   uint16_t            dcq[3][2];
-  int32_t             pad_;
 };
 
-#define OCG_FRAGS_PER_BLOCK 32
+#define OCG_FRAGS_PER_BLOCK 64
 #define OCG_RECON_THREADS   256
 
-void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, int max_blocks, cudaStream_t st);
+void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
+void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 

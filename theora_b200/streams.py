@@ -96,14 +96,10 @@ class Capture:
 
     def _on_frame(self, user, fptr, sptr):
         f, st = fptr.contents, sptr.contents
-        ncls = [f.ncls[k] for k in range(4)]
-        recs = [_copy(st.recs[k], ncls[k] * 16, REC_DTYPE) for k in range(4)]
-        recs = np.concatenate(recs) if sum(ncls) else np.zeros(0, REC_DTYPE)
+        recs = _copy(st.recs, self.nfrags * 16, REC_DTYPE)
         rows = _copy(st.coeff_rows, f.ncoeff_rows * 16, np.int16).reshape(-1, 8)
-        unc = _copy(st.uncoded_offs, f.nuncoded * 4, np.int32)
-        cmap = _copy(st.coded_map, self.nfrags, np.uint8)
         dcq = [[f.dc_quant[i][j] for j in range(2)] for i in range(3)]
-        self.frames.append(FrameWork([f.ref_idx[i] for i in range(3)], f.lf_limit, dcq, ncls, recs, rows, unc, cmap))
+        self.frames.append(FrameWork([f.ref_idx[i] for i in range(3)], f.lf_limit, dcq, recs, rows))
 
     def install(self):
         lib().ocg_backend_set_capture(self._cb, None)

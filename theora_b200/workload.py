@@ -65,8 +65,10 @@ def algorithmic_bytes(work):
     (recon_stage_bytes, loop_filter_bytes)."""
     if work is None:
         return 0, 0
+    coded = work.coded_mask
     intra = int((work.recs["refi"] == 2).sum())
-    inter = work.ncoded - intra
-    recon = intra * 192 + inter * 256 + len(work.uncoded) * 128
-    lf = (work.ncoded + len(work.uncoded)) * 128 if work.lf_limit else 0
+    ncoded = int(coded.sum())
+    inter = ncoded - intra
+    recon = intra * 192 + inter * 256 + (len(work.recs) - ncoded) * 128
+    lf = len(work.recs) * 128 if work.lf_limit else 0
     return recon, lf
