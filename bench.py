@@ -204,7 +204,7 @@ def main():
     import torch
     import torch.distributed as dist
     import theora_b200 as T
-    from theora_b200 import abi
+    from theora_b200 import abi, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
@@ -222,14 +222,9 @@ def main():
     if RANK == 0:
         blob = wl.synth_stream(args.width, args.height, args.frames, args.quality, args.kf)
         log("stream ready: %.1f MB in %.1fs" % (len(blob) / 1e6, time.time() - t0))
-    if WORLD > 1:
-        n = torch.tensor([len(blob) if RANK == 0 else 0], dtype=torch.int64, device=dev)
-        dist.broadcast(n, 0)
-        buf = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
-        if RANK == 0:
-            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        blob = bytes(buf.cpu().numpy().tobytes())
+    else:
+        blob = b""
+    blob = sharding.broadcast_bytes(blob, 0, dev)
 
     # capture the per-frame lists by decoding once through the public API on this GPU
     Lo = streams.lib()
@@ -278,11 +273,7 @@ def main():
     launches = L.ocg_launch_count() - launches0
     clocks = sampler.stop()
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    if WORLD > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     value = WORLD * S * nframes * args.steps / (ms_total * 1e-3)
 
     # per-kernel device time (CUDA events on the launching stream) for the roofline
@@ -325,10 +316,7 @@ def main():
         Lo.ocg_backend_get_stats(C.byref(st), 1)
         Lo.refh_stream_free(h)
         assert secs > 0, "e2e decode failed"
-        if WORLD > 1:
-            t = torch.tensor([secs], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            secs = float(t.item())
+        secs = sharding.max_over_ranks(secs, dev)
         e2e = {"value": WORLD * ncores * nframes / secs, "unit": "frames/s",
                "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
                "host_threads": ncores, "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",

@@ -150,9 +150,11 @@ OCG_API int  ocg_host_unregister(void *p);
 
 /* ---- decode: one frame, host lists (the call the vtable back-end makes) -- */
 /* Pinned staging owned by the ctx; the recorder writes straight into it (no
-   extra host copy): nfrags records (pre-filled with every fragment marked
-   OCG_FRAG_UNCODED, buf_off and plane set) and room for nfrags*8 coefficient
-   rows.  Valid until the next ocg_dec_submit on this ctx. */
+   extra host copy): nfrags records and room for nfrags*8 coefficient rows.
+   buf_off and the plane bits of pli_qti are filled in once at context creation
+   and must be left alone; for every frame the caller sets `refi` of EVERY
+   fragment (OCG_FRAG_UNCODED or a reference) and the remaining fields of the
+   coded ones.  Valid until the next ocg_dec_submit on this ctx. */
 typedef struct ocg_staging {
   ocg_frag_rec *recs;
   int16_t      *coeff_rows;

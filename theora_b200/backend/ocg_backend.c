@@ -111,11 +111,10 @@ static void stats_add(const ocg_backend *b, long h2d, long d2h, double secs) {
 static void backend_begin_frame(ocg_backend *b) {
   const oc_theora_state *st = &b->dec->state;
   int i;
-  /* staging comes back with every fragment marked uncoded; the recon hook
-     overwrites the coded ones, so oc_frag_copy_list needs no recording */
-  if (b->ctx != NULL) {
-    if (ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
-  } else memcpy(b->st.recs, b->heap_tmpl, (size_t)b->geom.nfrags * sizeof(ocg_frag_rec));
+  /* staging records keep buf_off/plane from context creation; every fragment
+     is visited once per frame by exactly one of the recon and copy-list hooks
+     (decode.c:1584,1601), which refresh the rest */
+  if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
   b->ncoded = b->nrows = 0;
   /* decode.c:2790-2794 has already picked SELF; GOLD/PREV are still the
      references this frame predicts from (they rotate at 2947-2962). */
@@ -223,9 +222,14 @@ static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi
 
 static void ocg_frag_copy_list(unsigned char *_dst_frame, const unsigned char *_src_frame, int _ystride,
                                const ptrdiff_t *_fragis, ptrdiff_t _nfragis, const ptrdiff_t *_frag_buf_offs) {
-  /* Uncoded fragments are whatever state_frag_recon did not record: the
-     device copies them PREV -> SELF from the pre-filled records. */
-  (void)_dst_frame; (void)_src_frame; (void)_ystride; (void)_fragis; (void)_nfragis; (void)_frag_buf_offs;
+  /* mark the listed fragments uncoded; the device copies them PREV -> SELF */
+  ocg_backend *b = t_cur;
+  ocg_frag_rec *recs;
+  ptrdiff_t i;
+  (void)_dst_frame; (void)_src_frame; (void)_ystride; (void)_frag_buf_offs;
+  if (b == NULL || !b->frame_open) backend_fatal("frag_copy_list outside a frame");
+  recs = b->st.recs;
+  for (i = 0; i < _nfragis; i++) recs[_fragis[i]].refi = OCG_FRAG_UNCODED;
 }
 
 static void ocg_state_loop_filter_frag_rows(const oc_theora_state *_state, signed char _bv[256], int _refi,
@@ -322,6 +326,7 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
         rc->pli_qti = (unsigned char)pli;
       }
     }
+    memcpy(b->st.recs, b->heap_tmpl, nf * 16);
   }
   st->opt_vtable.state_frag_recon = ocg_state_frag_recon;
   st->opt_vtable.frag_copy_list = ocg_frag_copy_list;

@@ -318,6 +318,7 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
       }
     }
   }
+  for (Slot &s : c->slots) memcpy(s.recs, c->tmpl, nf * sizeof(ocg_frag_rec));
   CUX(cudaStreamSynchronize(c->stream));
 #undef CUX
   *out = c;
@@ -397,7 +398,6 @@ OCG_API int ocg_dec_staging(ocg_ctx *c, ocg_staging *out) {
   int r = acquire_slot(c);
   if (r < 0) return r;
   Slot &s = c->slots[c->cur_slot];
-  memcpy(s.recs, c->tmpl, (size_t)c->geom.nfrags * sizeof(ocg_frag_rec));
   out->recs = s.recs;
   out->coeff_rows = s.rows;
   c->staged = true;

@@ -80,13 +80,16 @@ __device__ __forceinline__ void idct8(const int (&x)[8], int (&y)[8]) {
 /* Register layout conventions for the 4-lane fragment group (lane l = 0..3):
      L_row: lane owns rows 2l,2l+1; q[2m+r0] = (v[2l+r0][2m], v[2l+r0][2m+1])
      L_col: lane owns cols 2l,2l+1; q[r]     = (v[r][2l],     v[r][2l+1])
-   The same two-stage exchange converts either layout into the other. */
-__device__ __forceinline__ void xpose(uint32_t (&q)[8], unsigned gmask, int l) {
+   The same two-stage exchange converts either layout into the other.  All 32
+   lanes of the warp must call it together (xor 1 and 2 stay inside a group):
+   a full-warp mask keeps the shuffles plain SHFL.BFLY instead of the
+   MATCH/WARPSYNC sequences partial masks compile to. */
+__device__ __forceinline__ void xpose(uint32_t (&q)[8], int l) {
   const bool hi1 = (l & 2) != 0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     uint32_t s = hi1 ? q[i] : q[i + 4];
-    uint32_t r = __shfl_xor_sync(gmask, s, 2);
+    uint32_t r = __shfl_xor_sync(0xFFFFFFFFu, s, 2);
     if (hi1) q[i] = r; else q[i + 4] = r;
   }
   const bool hi0 = (l & 1) != 0;
@@ -94,7 +97,7 @@ __device__ __forceinline__ void xpose(uint32_t (&q)[8], unsigned gmask, int l) {
   for (int j = 0; j < 4; j++) {
     const int i = (j & 1) | ((j & 2) << 1); /* 0,1,4,5 */
     uint32_t s = hi0 ? q[i] : q[i | 2];
-    uint32_t r = __shfl_xor_sync(gmask, s, 1);
+    uint32_t r = __shfl_xor_sync(0xFFFFFFFFu, s, 1);
     if (hi0) q[i] = r; else q[i | 2] = r;
   }
 }
@@ -149,81 +152,158 @@ __device__ __forceinline__ uint2 recon_row(uint32_t r0, uint32_t r1, uint32_t r2
   return make_uint2(__byte_perm(o0, o1, 0x6420), __byte_perm(o2, o3, 0x6420));
 }
 
-/* One coded fragment.  CLS follows state.c:967 / idct.c:327-329. */
-template <int CLS>
-__device__ __forceinline__ void recon_fragment(const OcgGeomDev &g, const OcgJobDev &job, const int4 rw, int l,
-                                               unsigned gmask) {
+/* Work classes inside a CTA, in processing order. */
+enum { WC_NONE = 0, WC_COPY = 1, WC_DC = 2, WC_3 = 3, WC_10 = 4, WC_FULL = 5, WC_COUNT = 6 };
+
+__device__ __forceinline__ int work_class(const int4 rw) {
+  const int refi = (rw.w >> 16) & 0xFF, lz = (rw.w >> 8) & 0xFF;
+  if (refi == OCG_FRAG_UNCODED) return WC_COPY;
+  /* state.c:967 and idct.c:327-329 */
+  return lz < 2 ? WC_DC : (lz <= 3 ? WC_3 : (lz <= 10 ? WC_10 : WC_FULL));
+}
+
+/* Both 1-D passes, the transposes and the (v+8)>>4 rounding for the two rows
+   this lane owns (idct.c:301-330).  Executed by the whole warp with NR chosen
+   from the largest footprint present in the warp; a group whose own footprint
+   is smaller has had the coefficients the reference ignores zeroed, and the
+   reduced reference transforms are exact specialisations of the larger ones. */
+template <int NR>
+__device__ __forceinline__ void idct_rows2(int (&xa)[8], int (&xb)[8], uint32_t (&q)[8], int l) {
+  int ya[8], yb[8];
+  idct8<NR>(xa, ya);
+  idct8<NR>(xb, yb);
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    q[2 * m] = pack16(ya[2 * m], ya[2 * m + 1]);
+    q[2 * m + 1] = pack16(yb[2 * m], yb[2 * m + 1]);
+  }
+  xpose(q, l);
+#pragma unroll
+  for (int r = 0; r < 8; r++) { xa[r] = lo16(q[r]); xb[r] = hi16(q[r]); }
+  idct8<NR>(xa, ya);
+  idct8<NR>(xb, yb);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int va = (sext16(ya[r]) + 8) >> 4;
+    const int vb = (sext16(yb[r]) + 8) >> 4;
+    q[r] = pack16(va, vb);
+  }
+  xpose(q, l);
+}
+
+/* Zeroes the halfwords of a coefficient row the reference's reduced transform
+   would not read: keeps the first `lim` (0..8) coefficients. */
+__device__ __forceinline__ uint4 keep_first(uint4 w, int lim) {
+  const uint32_t m0 = lim >= 2 ? 0xFFFFFFFFu : (lim == 1 ? 0x0000FFFFu : 0u);
+  const uint32_t m1 = lim >= 4 ? 0xFFFFFFFFu : (lim == 3 ? 0x0000FFFFu : 0u);
+  const uint32_t m2 = lim >= 6 ? 0xFFFFFFFFu : (lim == 5 ? 0x0000FFFFu : 0u);
+  const uint32_t m3 = lim >= 8 ? 0xFFFFFFFFu : (lim == 7 ? 0x0000FFFFu : 0u);
+  return make_uint4(w.x & m0, w.y & m1, w.z & m2, w.w & m3);
+}
+
+__global__ void __launch_bounds__(OCG_RECON_THREADS)
+ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  __shared__ int4 srec[OCG_FRAGS_PER_BLOCK];
+  __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
+  __shared__ int scnt[2][WC_COUNT];
+  const OcgJobDev &job = jobs[blockIdx.y];
+  const int f0 = (int)blockIdx.x * OCG_FRAGS_PER_BLOCK;
+  const int nvalid = min(OCG_FRAGS_PER_BLOCK, g.nfrags - f0);
+  const int t = (int)threadIdx.x;
+  const int lane = t & 31;
+  /* ---- stage 1: the first two warps fetch the 64 records (1 KB, coalesced),
+          classify them and publish the coded map for the loop filter ---- */
+  int cls = WC_NONE;
+  unsigned mine = 0;
+  if (t < OCG_FRAGS_PER_BLOCK) {
+    if (t < nvalid) {
+      const int4 rw = __ldg((const int4 *)(job.recs + f0 + t));
+      srec[t] = rw;
+      cls = work_class(rw);
+      job.coded[f0 + t] = (unsigned char)(cls != WC_COPY);
+    }
+#pragma unroll
+    for (int c = 1; c < WC_COUNT; c++) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+      if (cls == c) mine = m;
+      if (lane == 0) scnt[t >> 5][c] = __popc(m);
+    }
+  }
+  __syncthreads();
+  /* ---- stage 2: stable partition by class (raster order kept inside a class) ---- */
+  if (cls != WC_NONE) {
+    int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
+    for (int c = 1; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
+    sorder[pos] = (unsigned char)t;
+  }
+  __syncthreads();
+  /* ---- stage 3: 4 lanes per fragment, 8 fragments per warp ---- */
+  const int gi = t >> 2;
+  const int l = lane & 3;
+  int4 rw = make_int4(0, 0, 0, 0);
+  int my = WC_NONE;
+  if (gi < nvalid) {
+    rw = srec[sorder[gi]];
+    my = work_class(rw);
+  }
+  const int wmax = __reduce_max_sync(0xFFFFFFFFu, my); /* warp-uniform */
+  if (wmax == WC_NONE) return;
   const int buf_off = rw.x;
   const int mv = rw.y << 16 >> 16;
   const int dc = rw.y >> 16;
-  const unsigned coeff_row = (unsigned)rw.z;
-  const unsigned rowmask = (unsigned)rw.w & 0xFFu;
   const int refi = (rw.w >> 16) & 0xFF;
   const int pli = (rw.w >> 24) & 3;
   const int qti = (rw.w >> 26) & 1;
   const int ystride = g.p[pli].ystride;
   const int dcq = job.dcq[pli][qti];
   uint32_t q[8];
-
-  if (CLS == OCG_CLS_DC) {
+  if (wmax >= WC_3) {
+    /* ---- this lane's two coefficient rows (zero unless stored and inside
+            the footprint of the group's own class) ---- */
+    const int nfoot = my == WC_FULL ? 8 : (my == WC_10 ? 4 : (my == WC_3 ? 2 : 0));
+    const int ra = 2 * l, rb = 2 * l + 1;
+    const unsigned rowmask = (unsigned)rw.w & 0xFFu;
+    uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+    if (ra < nfoot) {
+      const uint4 *rows = (const uint4 *)job.rows + (unsigned)rw.z;
+      if (rowmask >> ra & 1) wa = __ldg(rows + __popc(rowmask & ((1u << ra) - 1u)));
+      if (rowmask >> rb & 1) wb = __ldg(rows + __popc(rowmask & ((1u << rb) - 1u)));
+      if (my != WC_FULL) {
+        /* triangular footprint of the reduced transforms (idct.c:213-275) */
+        wa = keep_first(wa, nfoot - ra);
+        wb = keep_first(wb, nfoot - rb);
+      }
+    }
+    int xa[8], xb[8];
+    xa[0] = lo16(wa.x); xa[1] = hi16(wa.x); xa[2] = lo16(wa.y); xa[3] = hi16(wa.y);
+    xa[4] = lo16(wa.z); xa[5] = hi16(wa.z); xa[6] = lo16(wa.w); xa[7] = hi16(wa.w);
+    xb[0] = lo16(wb.x); xb[1] = hi16(wb.x); xb[2] = lo16(wb.y); xb[3] = hi16(wb.y);
+    xb[4] = lo16(wb.z); xb[5] = hi16(wb.z); xb[6] = lo16(wb.w); xb[7] = hi16(wb.w);
+    /* DC dequant, state.c:978 */
+    if (l == 0 && my >= WC_3) xa[0] = sext16(dc * dcq);
+    if (wmax == WC_3) idct_rows2<2>(xa, xb, q, l);
+    else if (wmax == WC_10) idct_rows2<4>(xa, xb, q, l);
+    else idct_rows2<8>(xa, xb, q, l);
+  }
+  if (my == WC_NONE) return;
+  if (my == WC_COPY) {
+    /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
+    const uint8_t *src = job.base[OCG_FRAME_PREV] + buf_off + (2 * l) * ystride;
+    uint8_t *dst = job.base[OCG_FRAME_SELF] + buf_off + (2 * l) * ystride;
+    const uint2 a = __ldg((const uint2 *)src);
+    const uint2 c = __ldg((const uint2 *)(src + ystride));
+    *(uint2 *)dst = a;
+    *(uint2 *)(dst + ystride) = c;
+    return;
+  }
+  if (my == WC_DC) {
     /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block. */
     const int p = sext16((dc * dcq + 15) >> 5);
     const uint32_t pp = pack16(p, p);
 #pragma unroll
     for (int i = 0; i < 8; i++) q[i] = pp;
-  } else {
-    constexpr int NR = CLS == OCG_CLS_3 ? 2 : (CLS == OCG_CLS_10 ? 4 : 8);
-    /* ---- load this lane's two coefficient rows (if stored) ---- */
-    int xa[8], xb[8];
-    {
-      const int ra = 2 * l, rb = 2 * l + 1;
-      uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-      const bool row_in_class = ra < NR;
-      if (row_in_class) {
-        const uint4 *rows = (const uint4 *)job.rows + coeff_row;
-        if (rowmask >> ra & 1) wa = __ldg(rows + __popc(rowmask & ((1u << ra) - 1u)));
-        if (rowmask >> rb & 1) wb = __ldg(rows + __popc(rowmask & ((1u << rb) - 1u)));
-      }
-      xa[0] = lo16(wa.x); xa[1] = hi16(wa.x); xa[2] = lo16(wa.y); xa[3] = hi16(wa.y);
-      xa[4] = lo16(wa.z); xa[5] = hi16(wa.z); xa[6] = lo16(wa.w); xa[7] = hi16(wa.w);
-      xb[0] = lo16(wb.x); xb[1] = hi16(wb.x); xb[2] = lo16(wb.y); xb[3] = hi16(wb.y);
-      xb[4] = lo16(wb.z); xb[5] = hi16(wb.z); xb[6] = lo16(wb.w); xb[7] = hi16(wb.w);
-      /* The reduced transforms read a triangular footprint only
-         (idct.c:213-275): row r uses its first NR-r coefficients. */
-      if (CLS == OCG_CLS_3) {
-        xb[1] = 0;
-      } else if (CLS == OCG_CLS_10) {
-        if (l == 0) { xb[3] = 0; }
-        else { xa[2] = 0; xa[3] = 0; xb[1] = 0; xb[2] = 0; xb[3] = 0; }
-      }
-      /* DC dequant, state.c:978 */
-      if (l == 0) xa[0] = sext16(dc * dcq);
-    }
-    /* ---- row pass (idct.c:313: rows of x into columns of w) ---- */
-    int ya[8], yb[8];
-    idct8<NR>(xa, ya);
-    idct8<NR>(xb, yb);
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-      q[2 * m] = pack16(ya[2 * m], ya[2 * m + 1]);
-      q[2 * m + 1] = pack16(yb[2 * m], yb[2 * m + 1]);
-    }
-    xpose(q, gmask, l);
-    /* ---- column pass + (v+8)>>4 (idct.c:315-317) ---- */
-#pragma unroll
-    for (int r = 0; r < 8; r++) { xa[r] = lo16(q[r]); xb[r] = hi16(q[r]); }
-    idct8<NR>(xa, ya);
-    idct8<NR>(xb, yb);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int va = (sext16(ya[r]) + 8) >> 4;
-      const int vb = (sext16(yb[r]) + 8) >> 4;
-      q[r] = pack16(va, vb);
-    }
-    xpose(q, gmask, l);
   }
-
-  /* ---- prediction + clamp + store, rows 2l and 2l+1 ---- */
+  /* ---- prediction + clamp + store, rows 2l and 2l+1 (fragment.c:49-80) ---- */
   uint8_t *dst = job.base[OCG_FRAME_SELF] + buf_off + (2 * l) * ystride;
   uint2 pa, pb;
   if (refi == OCG_FRAME_SELF) {
@@ -246,76 +326,6 @@ __device__ __forceinline__ void recon_fragment(const OcgGeomDev &g, const OcgJob
   const uint2 ob = recon_row(q[1], q[3], q[5], q[7], pb);
   *(uint2 *)dst = oa;
   *(uint2 *)(dst + ystride) = ob;
-}
-
-/* Work classes inside a CTA, in processing order. */
-enum { WC_COPY = 0, WC_DC = 1, WC_3 = 2, WC_10 = 3, WC_FULL = 4, WC_NONE = 5 };
-
-__device__ __forceinline__ int work_class(const int4 rw) {
-  const int refi = (rw.w >> 16) & 0xFF, lz = (rw.w >> 8) & 0xFF;
-  if (refi == OCG_FRAG_UNCODED) return WC_COPY;
-  /* state.c:967 and idct.c:327-329 */
-  return lz < 2 ? WC_DC : (lz <= 3 ? WC_3 : (lz <= 10 ? WC_10 : WC_FULL));
-}
-
-__global__ void __launch_bounds__(OCG_RECON_THREADS)
-ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  __shared__ int4 srec[OCG_FRAGS_PER_BLOCK];
-  __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
-  __shared__ int scnt[2][WC_NONE];
-  const OcgJobDev &job = jobs[blockIdx.y];
-  const int f0 = (int)blockIdx.x * OCG_FRAGS_PER_BLOCK;
-  const int nvalid = min(OCG_FRAGS_PER_BLOCK, g.nfrags - f0);
-  const int t = (int)threadIdx.x;
-  const int lane = t & 31;
-  /* ---- stage 1: the first two warps fetch the 64 records (1 KB, coalesced),
-          classify them and publish the coded map for the loop filter ---- */
-  int cls = WC_NONE;
-  unsigned mine = 0;
-  if (t < OCG_FRAGS_PER_BLOCK) {
-    if (t < nvalid) {
-      const int4 rw = __ldg((const int4 *)(job.recs + f0 + t));
-      srec[t] = rw;
-      cls = work_class(rw);
-      job.coded[f0 + t] = (unsigned char)(cls != WC_COPY);
-    }
-#pragma unroll
-    for (int c = 0; c < WC_NONE; c++) {
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
-      if (cls == c) mine = m;
-      if (lane == 0) scnt[t >> 5][c] = __popc(m);
-    }
-  }
-  __syncthreads();
-  /* ---- stage 2: stable partition by class (raster order kept inside a class) ---- */
-  if (cls != WC_NONE) {
-    int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
-    for (int c = 0; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
-    sorder[pos] = (unsigned char)t;
-  }
-  __syncthreads();
-  /* ---- stage 3: 4 lanes per fragment ---- */
-  const int gi = t >> 2;
-  if (gi >= nvalid) return;
-  const int l = lane & 3;
-  const unsigned gmask = 0xFu << (lane & 28);
-  const int4 rw = srec[sorder[gi]];
-  switch (work_class(rw)) {
-    case WC_COPY: {
-      /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
-      const int ystride = g.p[(rw.w >> 24) & 3].ystride;
-      const uint8_t *src = job.base[OCG_FRAME_PREV] + rw.x + (2 * l) * ystride;
-      uint8_t *dst = job.base[OCG_FRAME_SELF] + rw.x + (2 * l) * ystride;
-      const uint2 a = __ldg((const uint2 *)src);
-      const uint2 c = __ldg((const uint2 *)(src + ystride));
-      *(uint2 *)dst = a;
-      *(uint2 *)(dst + ystride) = c;
-    } break;
-    case WC_DC: recon_fragment<OCG_CLS_DC>(g, job, rw, l, gmask); break;
-    case WC_3: recon_fragment<OCG_CLS_3>(g, job, rw, l, gmask); break;
-    case WC_10: recon_fragment<OCG_CLS_10>(g, job, rw, l, gmask); break;
-    default: recon_fragment<OCG_CLS_FULL>(g, job, rw, l, gmask); break;
-  }
 }
 
 /* Only the coded map (for running the loop filter stage on its own). */

@@ -64,10 +64,13 @@ __device__ __forceinline__ void hadamard8(int (&t)[8]) {
   t[4] = b4 + b5; t[5] = b4 - b5; t[6] = b6 + b7; t[7] = b6 - b7;
 }
 
-__device__ __forceinline__ int group_sum8(int v, unsigned gmask) {
-  v += __shfl_xor_sync(gmask, v, 4);
-  v += __shfl_xor_sync(gmask, v, 2);
-  v += __shfl_xor_sync(gmask, v, 1);
+/* All shuffles use the full-warp mask (xor 4/2/1 stay inside an 8-lane slice):
+   every lane of the warp takes part, tail slices work on a clamped index and
+   only skip the final store. */
+__device__ __forceinline__ int group_sum8(int v) {
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
   return v;
 }
 
@@ -75,11 +78,11 @@ __global__ void __launch_bounds__(256)
 ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base,
                        int ystride, const ocg_enc_frag *__restrict__ frags, int n, uint32_t *__restrict__ out_val,
                        int32_t *__restrict__ out_dc) {
-  const int fi = (int)(blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3));
-  if (fi >= n) return;
+  const int fi_raw = (int)(blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3));
+  const bool live = fi_raw < n;
+  const int fi = live ? fi_raw : n - 1;
   const int lane = threadIdx.x & 31;
   const int row = lane & 7;
-  const unsigned gmask = 0xFFu << (lane & 24);
   const int4 fw = __ldg((const int4 *)(frags + fi));
   ocg_enc_frag f;
   f.src_off = fw.x; f.ref_off0 = fw.y; f.ref_off1 = fw.z; f.aux = fw.w;
@@ -89,7 +92,7 @@ ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const u
   int dc = 0;
   if (metric == OCG_MET_SAD) {
     load_pred_row(ref_base, f, row, ystride, p);
-    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, p.x) + __vsadu4(s.y, p.y)), gmask);
+    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, p.x) + __vsadu4(s.y, p.y)));
   } else if (metric == OCG_MET_SSD) {
     load_pred_row(ref_base, f, row, ystride, p);
     int a[8], b[8], acc = 0;
@@ -97,12 +100,12 @@ ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const u
     unpack8(p, b);
 #pragma unroll
     for (int i = 0; i < 8; i++) acc += (a[i] - b[i]) * (a[i] - b[i]);
-    val = (uint32_t)group_sum8(acc, gmask);
+    val = (uint32_t)group_sum8(acc);
   } else if (metric == OCG_MET_INTRA_SAD) {
     /* encfrag.c:88-107: dc=(sum+32)>>6, then sum |src-dc| */
-    const int tot = group_sum8((int)(__vsadu4(s.x, 0) + __vsadu4(s.y, 0)), gmask);
+    const int tot = group_sum8((int)(__vsadu4(s.x, 0) + __vsadu4(s.y, 0)));
     const uint32_t m = 0x01010101u * (uint32_t)((tot + 32) >> 6);
-    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, m) + __vsadu4(s.y, m)), gmask);
+    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, m) + __vsadu4(s.y, m)));
   } else {
     /* SATD family, encfrag.c:109-336: 2-D Hadamard of the residual, sum of
        magnitudes without the DC term, DC returned separately. */
@@ -120,7 +123,7 @@ ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const u
       const bool up = (row & d) != 0;
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const int o = __shfl_xor_sync(gmask, a[i], d);
+        const int o = __shfl_xor_sync(0xFFFFFFFFu, a[i], d);
         a[i] = up ? o - a[i] : a[i] + o;
       }
     }
@@ -128,9 +131,9 @@ ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const u
 #pragma unroll
     for (int i = 0; i < 8; i++) acc += abs(a[i]);
     if (row == 0) { dc = a[0]; acc -= abs(a[0]); }
-    val = (uint32_t)group_sum8(acc, gmask);
+    val = (uint32_t)group_sum8(acc);
   }
-  if (row == 0) {
+  if (row == 0 && live) {
     out_val[fi] = val;
     if (out_dc != nullptr) out_dc[fi] = dc;
   }
@@ -168,24 +171,24 @@ __device__ __forceinline__ void fdct8(const int (&x)[8], int (&y)[8]) {
 }
 
 /* 8x8 transpose of 16-bit values over an 8-lane slice; p[k] = (v[2k], v[2k+1]). */
-__device__ __forceinline__ void xpose8(uint32_t (&p)[4], unsigned gmask, int g) {
+__device__ __forceinline__ void xpose8(uint32_t (&p)[4], int g) {
   {
     const bool up = (g & 4) != 0;
     const uint32_t s0 = up ? p[0] : p[2], s1 = up ? p[1] : p[3];
-    const uint32_t r0 = __shfl_xor_sync(gmask, s0, 4), r1 = __shfl_xor_sync(gmask, s1, 4);
+    const uint32_t r0 = __shfl_xor_sync(0xFFFFFFFFu, s0, 4), r1 = __shfl_xor_sync(0xFFFFFFFFu, s1, 4);
     if (up) { p[0] = r0; p[1] = r1; } else { p[2] = r0; p[3] = r1; }
   }
   {
     const bool up = (g & 2) != 0;
     const uint32_t s0 = up ? p[0] : p[1], s1 = up ? p[2] : p[3];
-    const uint32_t r0 = __shfl_xor_sync(gmask, s0, 2), r1 = __shfl_xor_sync(gmask, s1, 2);
+    const uint32_t r0 = __shfl_xor_sync(0xFFFFFFFFu, s0, 2), r1 = __shfl_xor_sync(0xFFFFFFFFu, s1, 2);
     if (up) { p[0] = r0; p[2] = r1; } else { p[1] = r0; p[3] = r1; }
   }
   {
     const bool up = (g & 1) != 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const uint32_t r = __shfl_xor_sync(gmask, p[k], 1);
+      const uint32_t r = __shfl_xor_sync(0xFFFFFFFFu, p[k], 1);
       p[k] = up ? __byte_perm(p[k], r, 0x3276) : __byte_perm(p[k], r, 0x5410);
     }
   }
@@ -213,11 +216,11 @@ ocg_enc_fdct_quant_kernel(const uint8_t *__restrict__ src_base, const uint8_t *_
                           int16_t *__restrict__ qdct, int32_t *__restrict__ nonzero) {
   __shared__ __align__(16) int16_t zz[32][64]; /* per fragment slot, zig-zag order */
   const int slot = threadIdx.x >> 3;
-  const int fi = (int)(blockIdx.x * 32 + slot);
-  if (fi >= n) return;
+  const int fi_raw = (int)(blockIdx.x * 32 + slot);
+  const bool live = fi_raw < n;
+  const int fi = live ? fi_raw : n - 1;
   const int lane = threadIdx.x & 31;
   const int row = lane & 7;
-  const unsigned gmask = 0xFFu << (lane & 24);
   const int4 fw = __ldg((const int4 *)(frags + fi));
   ocg_enc_frag f;
   f.src_off = fw.x; f.ref_off0 = fw.y; f.ref_off1 = fw.z; f.aux = fw.w;
@@ -240,19 +243,19 @@ ocg_enc_fdct_quant_kernel(const uint8_t *__restrict__ src_base, const uint8_t *_
   if (row == 1) v[0] = (int)(short)(v[0] - 1);
   uint32_t pk[4];
   pack8(v, pk);
-  xpose8(pk, gmask, row); /* lane c now holds column c */
+  xpose8(pk, row); /* lane c now holds column c */
   unpack16(pk, v);
   fdct8(v, y);            /* vertical frequencies of column c */
   pack8(y, pk);
-  xpose8(pk, gmask, row); /* lane r holds, for vertical frequency r, the 8 columns */
+  xpose8(pk, row); /* lane r holds, for vertical frequency r, the 8 columns */
   unpack16(pk, v);
   fdct8(v, y);            /* y[k] = coefficient (row r, column k), natural order */
 #pragma unroll
   for (int k = 0; k < 8; k++) zz[slot][c_izig[row * 8 + k]] = (int16_t)(((int)(short)y[k] + 2) >> 2);
-  __syncwarp(gmask);
+  __syncwarp();
   /* lane handles zig-zag positions 8*row .. 8*row+7 */
   const uint4 dv = *(const uint4 *)&zz[slot][row * 8];
-  *(uint4 *)(dct + (size_t)fi * 64 + row * 8) = dv;
+  if (live) *(uint4 *)(dct + (size_t)fi * 64 + row * 8) = dv;
   const int pli = f.aux & 3, qti = (f.aux >> 2) & 1, qii = (f.aux >> 3) & 3;
   const int tab = (pli * 2 + qti) * 3 + qii;
   const uint4 dq = __ldg((const uint4 *)(dequant + (size_t)tab * 64 + row * 8));
@@ -279,11 +282,11 @@ ocg_enc_fdct_quant_kernel(const uint8_t *__restrict__ src_base, const uint8_t *_
   }
   uint32_t qp[4];
   pack8(q, qp);
-  *(uint4 *)(qdct + (size_t)fi * 64 + row * 8) = make_uint4(qp[0], qp[1], qp[2], qp[3]);
-  last = max(last, __shfl_xor_sync(gmask, last, 4));
-  last = max(last, __shfl_xor_sync(gmask, last, 2));
-  last = max(last, __shfl_xor_sync(gmask, last, 1));
-  if (row == 0) nonzero[fi] = last;
+  if (live) *(uint4 *)(qdct + (size_t)fi * 64 + row * 8) = make_uint4(qp[0], qp[1], qp[2], qp[3]);
+  last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, 4));
+  last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, 2));
+  last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, 1));
+  if (row == 0 && live) nonzero[fi] = last;
 }
 
 } /* namespace */
