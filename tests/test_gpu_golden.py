@@ -91,8 +91,9 @@ def test_encoder_kernels_against_golden():
         oq = torch.zeros((1, 64), dtype=torch.int16, device="cuda")
         onz = torch.zeros(1, dtype=torch.int32, device="cuda")
         one = _dev(fr[j:j + 1].view(np.int32).reshape(1, 4))
+        ddeq, denq = _dev(deq.view(np.int16)), _dev(enq)  # keep alive across the launch
         abi.check(L.ocg_enc_fdct_quant_batch(dsrc.data_ptr(), dsrc.data_ptr(), 8, one.data_ptr(), 1,
-                                             _dev(deq.view(np.int16)).data_ptr(), _dev(enq).data_ptr(),
+                                             ddeq.data_ptr(), denq.data_ptr(),
                                              od.data_ptr(), oq.data_ptr(), onz.data_ptr(), st))
         torch.cuda.synchronize()
         assert np.array_equal(od.cpu().numpy()[0], U["fdct_y"][i])
