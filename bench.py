@@ -165,6 +165,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     ncores = args.threads or host_cores()
+    if args.impl == "ours" and WORLD > 1 and not args.threads:
+        ncores = max(1, ncores // WORLD)  # the ranks share the host's cores
     workload = "1080p 4:2:0 decode, %d synthetic frames (kf=%d, q=%d)" % (args.frames, args.kf, args.quality)
     if (args.width, args.height) != (1920, 1080):
         workload = "%dx%d 4:2:0 decode, %d synthetic frames (kf=%d, q=%d)" % (args.width, args.height, args.frames,
@@ -211,6 +213,7 @@ def main():
     torch.cuda.set_device(LOCAL_RANK)
     dev = torch.device("cuda", LOCAL_RANK)
     if WORLD > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
