@@ -350,47 +350,70 @@ __device__ __forceinline__ int lflim(int r, int lim) {
   return r < 0 ? -v : v;
 }
 
-/* One filter line on four samples a,b,c,d straddling the edge (b|c adjacent). */
-__device__ __forceinline__ void lf4(int a, int &b, int &c, int d, int lim) {
-  const int f = lflim((a - d + 3 * (c - b) + 4) >> 3, lim);
-  b = min(max(b + f, 0), 255);
-  c = min(max(c - f, 0), 255);
+/* Two filter lines at once, one per halfword (state.c:1002-1031).
+   a,b,c,d: the four samples straddling the edge, packed as (line0, line1)
+   16-bit pairs, 0..255 each.  Values stay below 2^16 per halfword, so plain
+   32-bit integer arithmetic acts on both lines:
+     F = a + 3c + 1028 - (d + 3b)  ==  (a-d+3(c-b)+4) + 1024   (>= 8 per half)
+     F>>3                           ==  ((f+4)>>3) + 128        (1..256)
+   The bounding function comes from a 257-entry table in shared memory. */
+__device__ __forceinline__ void lf_pair(uint32_t a, uint32_t &b, uint32_t &c, uint32_t d, const signed char *bv) {
+  const uint32_t x = c * 3u + a + 0x04040404u;
+  const uint32_t y = b * 3u + d;
+  const uint32_t u = ((x - y) >> 3) & 0x1FFF1FFFu;
+  const int f0 = bv[u & 0xFFFFu], f1 = bv[u >> 16];
+  const uint32_t ff = __byte_perm((uint32_t)f0, (uint32_t)f1, 0x5410);
+  const uint32_t nf = __vneg2(ff);
+  b = __viaddmin_s16x2_relu(b, ff, 0x00FF00FFu);
+  c = __viaddmin_s16x2_relu(c, nf, 0x00FF00FFu);
 }
 
 struct Cell {
   uint32_t w[8][2]; /* w[row][0] = cols 0..3, w[row][1] = cols 4..7 (cell-local) */
 };
 
-__device__ __forceinline__ int getb(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xFFu); }
-__device__ __forceinline__ uint32_t setb(uint32_t w, int i, int v) {
-  return (w & ~(0xFFu << (8 * i))) | ((uint32_t)v << (8 * i));
+/* Vertical edge through the cell centre, rows R and R+1: samples are cell
+   columns 2,3 | 4,5 (loop_filter_h, state.c:1002). */
+template <int R>
+__device__ __forceinline__ void cell_vpair(Cell &c, const signed char *bv) {
+  const uint32_t m = 0x00FF00FFu;
+  const uint32_t a = __byte_perm(c.w[R][0], c.w[R + 1][0], 0x0602) & m; /* col 2 of both rows */
+  uint32_t b = __byte_perm(c.w[R][0], c.w[R + 1][0], 0x0703) & m;       /* col 3 */
+  uint32_t cc = __byte_perm(c.w[R][1], c.w[R + 1][1], 0x0400) & m;      /* col 4 */
+  const uint32_t d = __byte_perm(c.w[R][1], c.w[R + 1][1], 0x0501) & m; /* col 5 */
+  lf_pair(a, b, cc, d, bv);
+  c.w[R][0] = __byte_perm(c.w[R][0], b, 0x4210);
+  c.w[R + 1][0] = __byte_perm(c.w[R + 1][0], b, 0x6210);
+  c.w[R][1] = __byte_perm(c.w[R][1], cc, 0x3214);
+  c.w[R + 1][1] = __byte_perm(c.w[R + 1][1], cc, 0x3216);
 }
 
-/* vertical edge through the cell centre, cell rows [r0,r1) : samples cols 2..5 */
-__device__ __forceinline__ void cell_vline(Cell &c, int r, int lim) {
-  int a = getb(c.w[r][0], 2), b = getb(c.w[r][0], 3), cc = getb(c.w[r][1], 0), d = getb(c.w[r][1], 1);
-  lf4(a, b, cc, d, lim);
-  c.w[r][0] = setb(c.w[r][0], 3, b);
-  c.w[r][1] = setb(c.w[r][1], 0, cc);
-}
-
-/* horizontal edge through the cell centre, cell column col: samples rows 2..5.
-   Bottom-up rows: row index grows with the fragment row, and loop_filter_v
-   reads pix[-2*ystride .. +ystride], i.e. cell rows 2,3 | 4,5. */
+/* Horizontal edge through the cell centre, cell columns COL and COL+1 (same
+   register): samples are cell rows 2,3 | 4,5 (loop_filter_v, state.c:1018;
+   bottom-up rows). */
 template <int COL>
-__device__ __forceinline__ void cell_hline(Cell &c, int lim) {
-  constexpr int h = COL >> 2, i = COL & 3;
-  int a = getb(c.w[2][h], i), b = getb(c.w[3][h], i), cc = getb(c.w[4][h], i), d = getb(c.w[5][h], i);
-  lf4(a, b, cc, d, lim);
-  c.w[3][h] = setb(c.w[3][h], i, b);
-  c.w[4][h] = setb(c.w[4][h], i, cc);
+__device__ __forceinline__ void cell_hpair(Cell &c, const signed char *bv) {
+  constexpr int h = COL >> 2, i = COL & 3; /* i is 0 or 2 */
+  constexpr unsigned ext = i == 0 ? 0x4140u : 0x4342u; /* (byte i, 0, byte i+1, 0) with a zero second operand */
+  const uint32_t a = __byte_perm(c.w[2][h], 0, ext);
+  uint32_t b = __byte_perm(c.w[3][h], 0, ext);
+  uint32_t cc = __byte_perm(c.w[4][h], 0, ext);
+  const uint32_t d = __byte_perm(c.w[5][h], 0, ext);
+  lf_pair(a, b, cc, d, bv);
+  constexpr unsigned ins = i == 0 ? 0x3264u : 0x6410u; /* put bytes 0,2 of the result at i,i+1 */
+  c.w[3][h] = __byte_perm(c.w[3][h], b, ins);
+  c.w[4][h] = __byte_perm(c.w[4][h], cc, ins);
 }
 
 __global__ void __launch_bounds__(64)
 ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  __shared__ signed char bv[260];
   const OcgJobDev &job = jobs[blockIdx.z];
   const int lim = job.lf_limit;
   if (lim == 0) return;
+  /* bv[u] = lflim(u-128), u = 1..256 (oc_loop_filter_init_c, state.c:1036) */
+  for (int u = (int)threadIdx.x; u < 260; u += (int)blockDim.x) bv[u] = (signed char)lflim(u - 128, lim);
+  __syncthreads();
   const int crow = (int)blockIdx.y;
   const int pli = crow >= g.p[2].cell_row0 ? 2 : (crow >= g.p[1].cell_row0 ? 1 : 0);
   const OcgPlaneDev &P = g.p[pli];
@@ -425,19 +448,19 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
     }
   }
   /* independent lines */
-  if (vd) { cell_vline(c, 0, lim); cell_vline(c, 1, lim); }
-  if (vu) { cell_vline(c, 6, lim); cell_vline(c, 7, lim); }
-  if (hl) { cell_hline<0>(c, lim); cell_hline<1>(c, lim); }
-  if (hr) { cell_hline<6>(c, lim); cell_hline<7>(c, lim); }
-  /* ordered lines through the central patch ("loop filter order") */
-  if (vd && !B) { cell_vline(c, 2, lim); cell_vline(c, 3, lim); }
-  if (hl && !Cc) { cell_hline<2>(c, lim); cell_hline<3>(c, lim); }
-  if (vd && B) { cell_vline(c, 2, lim); cell_vline(c, 3, lim); }
-  if (hr && !D) { cell_hline<4>(c, lim); cell_hline<5>(c, lim); }
-  if (hl && Cc) { cell_hline<2>(c, lim); cell_hline<3>(c, lim); }
-  if (vu && !D) { cell_vline(c, 4, lim); cell_vline(c, 5, lim); }
-  if (vu && D) { cell_vline(c, 4, lim); cell_vline(c, 5, lim); }
-  if (hr && D) { cell_hline<4>(c, lim); cell_hline<5>(c, lim); }
+  if (vd) cell_vpair<0>(c, bv);
+  if (vu) cell_vpair<6>(c, bv);
+  if (hl) cell_hpair<0>(c, bv);
+  if (hr) cell_hpair<6>(c, bv);
+  /* ordered lines through the central patch ("loop filter") */
+  if (vd && !B) cell_vpair<2>(c, bv);
+  if (hl && !Cc) cell_hpair<2>(c, bv);
+  if (vd && B) cell_vpair<2>(c, bv);
+  if (hr && !D) cell_hpair<4>(c, bv);
+  if (hl && Cc) cell_hpair<2>(c, bv);
+  if (vu && !D) cell_vpair<4>(c, bv);
+  if (vu && D) cell_vpair<4>(c, bv);
+  if (hr && D) cell_hpair<4>(c, bv);
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     if (r >= rlo && r < rhi) {
