@@ -114,6 +114,7 @@ typedef struct ocg_dec_frame {
   int32_t             lf_limit;        /* loop_filter_limits[qis[0]]; 0 = no filter */
   uint16_t            dc_quant[3][2];  /* dequant[pli][0][qti][0] (decode.c:1534)  */
   int32_t             ncoded;          /* coded fragments in recs (informational)  */
+  int32_t             intra_frame;     /* 1: key frame, no record references PREV/GOLD */
   int32_t             ncoeff_rows;
   const ocg_frag_rec *recs;            /* nfrags records, fragment-index order     */
   const int16_t      *coeff_rows;      /* ncoeff_rows x 8 int16                    */

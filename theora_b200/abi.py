@@ -34,7 +34,8 @@ class Geometry(C.Structure):
 
 class DecFrame(C.Structure):
     _fields_ = [("ref_idx", C.c_int32 * 3), ("lf_limit", C.c_int32), ("dc_quant", (C.c_uint16 * 2) * 3),
-                ("ncoded", C.c_int32), ("ncoeff_rows", C.c_int32), ("recs", C.c_void_p), ("coeff_rows", C.c_void_p)]
+                ("ncoded", C.c_int32), ("intra_frame", C.c_int32),
+                ("ncoeff_rows", C.c_int32), ("recs", C.c_void_p), ("coeff_rows", C.c_void_p)]
 
 
 class Staging(C.Structure):
@@ -75,6 +76,7 @@ class FrameWork:
                 f.dc_quant[i][j] = int(self.dc_quant[i, j])
         f.lf_limit = self.lf_limit
         f.ncoded = self.ncoded
+        f.intra_frame = int(bool(np.all(self.recs["refi"] == OCG_FRAME_SELF)))
         f.ncoeff_rows = len(self.rows)
         f.recs = self.recs.ctypes.data
         f.coeff_rows = self.rows.ctypes.data if len(self.rows) else None

@@ -133,6 +133,7 @@ static void backend_flush(ocg_backend *b) {
   f.lf_limit = st->loop_filter_limits[st->qis[0]];
   for (i = 0; i < 3; i++) for (k = 0; k < 2; k++) f.dc_quant[i][k] = b->dcq[i][k];
   f.ncoded = b->ncoded;
+  f.intra_frame = st->frame_type == OC_INTRA_FRAME;
   f.ncoeff_rows = b->nrows;
   b->frame_open = 0;
   if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);

@@ -85,6 +85,7 @@ static void geom_to_dev(const ocg_geometry &g, OcgGeomDev &d) {
     q.plane_off = (int32_t)p.plane_off;
     q.lo_off = (int32_t)(p.plane_off + (int64_t)(p.height - 1) * p.ystride);
     q.cell_row0 = cell_rows;
+    q.nh_magic = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)p.nhfrags) + 1u;
     cell_rows += p.nvfrags + 1;
     if (p.nhfrags + 1 > maxcx) maxcx = p.nhfrags + 1;
   }
@@ -105,6 +106,7 @@ static void fill_job(OcgJobDev &j, const ocg_ctx *c, const ocg_dec_frame &f, con
   j.rows = rows;
   j.coded = c->d_map;
   j.lf_limit = f.lf_limit;
+  j.spec_prev = !f.intra_frame && f.ref_idx[OCG_FRAME_PREV] >= 0;
   for (int p = 0; p < 3; p++)
     for (int q = 0; q < 2; q++) j.dcq[p][q] = f.dc_quant[p][q];
 }
@@ -292,6 +294,7 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUX(cudaMalloc(&c->frames, pool));
   CUX(cudaMemsetAsync(c->frames, 0x80, pool, c->stream));
+  ocg_init_device_tables(c->stream);
   CUX(cudaMalloc(&c->d_recs, nf * sizeof(ocg_frag_rec)));
   CUX(cudaMalloc(&c->d_rows, nf * 8 * 16));
   CUX(cudaMalloc(&c->d_map, nf));

@@ -125,17 +125,15 @@ __device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p) {
 
 /* state.c:846-957 in closed form: first tap truncates towards zero, second tap
    (present iff a component has a fractional part) one step away from zero. */
-__device__ __forceinline__ void mv_taps(int mv, int qx, int qy, int ystride, int &off0, int &off1, bool &two) {
+__device__ __forceinline__ void mv_taps(int mv, int qx, int qy, int ystride, int &off0, int &fx, int &fy) {
   const int dx = (int)(signed char)(mv & 0xFF);
   const int dy = mv >> 8;
   const int ax = abs(dx), ay = abs(dy);
   const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
   const int mx = sx * (ax >> (1 + qx)), my = sy * (ay >> (1 + qy));
-  const int fx = (ax & (qx ? 3 : 1)) ? sx : 0;
-  const int fy = (ay & (qy ? 3 : 1)) ? sy : 0;
+  fx = (ax & (qx ? 3 : 1)) ? sx : 0; /* second tap = first + fy*ystride + fx, present iff fx|fy */
+  fy = (ay & (qy ? 3 : 1)) ? sy : 0;
   off0 = my * ystride + mx;
-  off1 = off0 + fy * ystride + fx;
-  two = (fx | fy) != 0;
 }
 
 /* clamp255(res + pred) for one row held as four (even,odd) halfword pairs.
@@ -201,9 +199,17 @@ __device__ __forceinline__ uint4 keep_first(uint4 w, int lim) {
   return make_uint4(w.x & m0, w.y & m1, w.z & m2, w.w & m3);
 }
 
-__global__ void __launch_bounds__(OCG_RECON_THREADS)
+/* Per-fragment work item prepared once by stage 1 (instead of four times by
+   the four lanes of stage 3):
+     x  buf_off                      y  buf_off + first-tap offset (inter only)
+     z  coeff_row
+     w  [15:0] dequantised DC (class >= WC_3) or the DC-only residual (WC_DC)
+        [23:16] rowmask  [26:24] class  [28:27] refi  [30:29] plane
+   stap: second-tap step, bits [1:0] x (0, 1, 3=-1), bits [3:2] y, 0 = single tap */
+__global__ void __launch_bounds__(OCG_RECON_THREADS, 8)
 ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  __shared__ int4 srec[OCG_FRAGS_PER_BLOCK];
+  __shared__ int4 sitem[OCG_FRAGS_PER_BLOCK];
+  __shared__ unsigned char stap[OCG_FRAGS_PER_BLOCK];
   __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
   __shared__ int scnt[2][WC_COUNT];
   const OcgJobDev &job = jobs[blockIdx.y];
@@ -211,61 +217,108 @@ ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const int nvalid = min(OCG_FRAGS_PER_BLOCK, g.nfrags - f0);
   const int t = (int)threadIdx.x;
   const int lane = t & 31;
+  /* ---- stage 0: speculation.  The records decide where pixels come from, so
+          a fragment costs two dependent DRAM round trips (record, then
+          predictor).  In inter frames most fragments are uncoded copies or
+          zero-MV blocks predicted from PREV, whose predictor is the co-located
+          block -- an address known from geometry alone.  Every lane therefore
+          requests "its" two co-located PREV rows right away; they are used if
+          the record agrees and dropped otherwise. ---- */
+  uint2 sa = make_uint2(0, 0), sb = make_uint2(0, 0);
+  int spec_off = 0;
+  bool spec = false;
+  if (job.spec_prev && (t >> 2) < nvalid) {
+    const int fragi = f0 + (t >> 2);
+    const int pl = fragi >= g.p[2].froffset ? 2 : (fragi >= g.p[1].froffset ? 1 : 0);
+    const OcgPlaneDev &P = g.p[pl];
+    const unsigned fi = (unsigned)(fragi - P.froffset);
+    unsigned fy = __umulhi(fi, P.nh_magic);
+    if (fy * (unsigned)P.nhfrags > fi) fy--;
+    const unsigned fx = fi - fy * (unsigned)P.nhfrags;
+    spec_off = P.plane_off + (int)fy * 8 * P.ystride + (int)fx * 8;
+    const uint8_t *src = job.base[OCG_FRAME_PREV] + spec_off + (2 * (lane & 3)) * P.ystride;
+    sa = __ldg((const uint2 *)src);
+    sb = __ldg((const uint2 *)(src + P.ystride));
+    spec = true;
+  }
   /* ---- stage 1: the first two warps fetch the 64 records (1 KB, coalesced),
-          classify them and publish the coded map for the loop filter ---- */
+          classify them, do the per-fragment scalar work (MV -> tap offsets,
+          state.c:846-957; DC dequant, state.c:972,978) and publish the coded
+          map for the loop filter ---- */
   int cls = WC_NONE;
   unsigned mine = 0;
   if (t < OCG_FRAGS_PER_BLOCK) {
     if (t < nvalid) {
       const int4 rw = __ldg((const int4 *)(job.recs + f0 + t));
-      srec[t] = rw;
       cls = work_class(rw);
+      const int mv = rw.y << 16 >> 16, dc = rw.y >> 16;
+      const int refi = (rw.w >> 16) & 3, pli = (rw.w >> 24) & 3, qti = (rw.w >> 26) & 1;
+      const int dcq = job.dcq[pli][qti];
+      const int dcv = cls == WC_DC ? (dc * dcq + 15) >> 5 : dc * dcq;
+      int off0 = 0, fx = 0, fy = 0;
+      if (cls >= WC_DC && refi != OCG_FRAME_SELF) mv_taps(mv, pli ? g.qx : 0, pli ? g.qy : 0, g.p[pli].ystride, off0, fx, fy);
+      int4 it;
+      it.x = rw.x;
+      it.y = rw.x + off0;
+      it.z = rw.z;
+      it.w = (dcv & 0xFFFF) | ((rw.w & 0xFF) << 16) | (cls << 24) | (refi << 27) | (pli << 29);
+      sitem[t] = it;
+      const unsigned tap = (unsigned)(fx & 3) | ((unsigned)(fy & 3) << 2);
+      stap[t] = (unsigned char)tap;
       job.coded[f0 + t] = (unsigned char)(cls != WC_COPY);
     }
+  }
+  /* blocks without any transform class (the common case in inter frames) need
+     no regrouping: copy and DC-only work is uniform enough */
+  const int need_sort = __syncthreads_or(cls >= WC_3);
+  if (need_sort) {
+    if (t < OCG_FRAGS_PER_BLOCK) {
 #pragma unroll
-    for (int c = 1; c < WC_COUNT; c++) {
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
-      if (cls == c) mine = m;
-      if (lane == 0) scnt[t >> 5][c] = __popc(m);
+      for (int c = 1; c < WC_COUNT; c++) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+        if (cls == c) mine = m;
+        if (lane == 0) scnt[t >> 5][c] = __popc(m);
+      }
     }
+    __syncthreads();
+    /* ---- stage 2: stable partition by class (raster order kept inside a class) ---- */
+    if (cls != WC_NONE) {
+      int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
+      for (int c = 1; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
+      sorder[pos] = (unsigned char)t;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  /* ---- stage 2: stable partition by class (raster order kept inside a class) ---- */
-  if (cls != WC_NONE) {
-    int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
-    for (int c = 1; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
-    sorder[pos] = (unsigned char)t;
-  }
-  __syncthreads();
   /* ---- stage 3: 4 lanes per fragment, 8 fragments per warp ---- */
   const int gi = t >> 2;
   const int l = lane & 3;
-  int4 rw = make_int4(0, 0, 0, 0);
-  int my = WC_NONE;
+  int4 it = make_int4(0, 0, 0, 0);
+  unsigned tap = 0;
   if (gi < nvalid) {
-    rw = srec[sorder[gi]];
-    my = work_class(rw);
+    const int slot = need_sort ? (int)sorder[gi] : gi;
+    it = sitem[slot];
+    tap = stap[slot];
   }
+  /* the speculative rows are valid for this group iff it still handles the
+     fragment it guessed (no regrouping) at the guessed address */
+  spec = spec && !need_sort && it.x == spec_off;
+  const int my = (it.w >> 24) & 7;
   const int wmax = __reduce_max_sync(0xFFFFFFFFu, my); /* warp-uniform */
   if (wmax == WC_NONE) return;
-  const int buf_off = rw.x;
-  const int mv = rw.y << 16 >> 16;
-  const int dc = rw.y >> 16;
-  const int refi = (rw.w >> 16) & 0xFF;
-  const int pli = (rw.w >> 24) & 3;
-  const int qti = (rw.w >> 26) & 1;
+  const int pli = (it.w >> 29) & 3;
+  const int refi = (it.w >> 27) & 3;
   const int ystride = g.p[pli].ystride;
-  const int dcq = job.dcq[pli][qti];
+  const int dcv = sext16(it.w);
   uint32_t q[8];
   if (wmax >= WC_3) {
     /* ---- this lane's two coefficient rows (zero unless stored and inside
             the footprint of the group's own class) ---- */
     const int nfoot = my == WC_FULL ? 8 : (my == WC_10 ? 4 : (my == WC_3 ? 2 : 0));
     const int ra = 2 * l, rb = 2 * l + 1;
-    const unsigned rowmask = (unsigned)rw.w & 0xFFu;
+    const unsigned rowmask = ((unsigned)it.w >> 16) & 0xFFu;
     uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
     if (ra < nfoot) {
-      const uint4 *rows = (const uint4 *)job.rows + (unsigned)rw.z;
+      const uint4 *rows = (const uint4 *)job.rows + (unsigned)it.z;
       if (rowmask >> ra & 1) wa = __ldg(rows + __popc(rowmask & ((1u << ra) - 1u)));
       if (rowmask >> rb & 1) wb = __ldg(rows + __popc(rowmask & ((1u << rb) - 1u)));
       if (my != WC_FULL) {
@@ -279,45 +332,49 @@ ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
     xa[4] = lo16(wa.z); xa[5] = hi16(wa.z); xa[6] = lo16(wa.w); xa[7] = hi16(wa.w);
     xb[0] = lo16(wb.x); xb[1] = hi16(wb.x); xb[2] = lo16(wb.y); xb[3] = hi16(wb.y);
     xb[4] = lo16(wb.z); xb[5] = hi16(wb.z); xb[6] = lo16(wb.w); xb[7] = hi16(wb.w);
-    /* DC dequant, state.c:978 */
-    if (l == 0 && my >= WC_3) xa[0] = sext16(dc * dcq);
+    if (l == 0 && my >= WC_3) xa[0] = dcv; /* dequantised DC, state.c:978 */
     if (wmax == WC_3) idct_rows2<2>(xa, xb, q, l);
     else if (wmax == WC_10) idct_rows2<4>(xa, xb, q, l);
     else idct_rows2<8>(xa, xb, q, l);
   }
   if (my == WC_NONE) return;
+  uint8_t *dst = job.base[OCG_FRAME_SELF] + it.x + (2 * l) * ystride;
   if (my == WC_COPY) {
     /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
-    const uint8_t *src = job.base[OCG_FRAME_PREV] + buf_off + (2 * l) * ystride;
-    uint8_t *dst = job.base[OCG_FRAME_SELF] + buf_off + (2 * l) * ystride;
-    const uint2 a = __ldg((const uint2 *)src);
-    const uint2 c = __ldg((const uint2 *)(src + ystride));
+    uint2 a = sa, c = sb;
+    if (!spec) {
+      const uint8_t *src = job.base[OCG_FRAME_PREV] + it.x + (2 * l) * ystride;
+      a = __ldg((const uint2 *)src);
+      c = __ldg((const uint2 *)(src + ystride));
+    }
     *(uint2 *)dst = a;
     *(uint2 *)(dst + ystride) = c;
     return;
   }
   if (my == WC_DC) {
     /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block. */
-    const int p = sext16((dc * dcq + 15) >> 5);
-    const uint32_t pp = pack16(p, p);
+    const uint32_t pp = pack16(dcv, dcv);
 #pragma unroll
     for (int i = 0; i < 8; i++) q[i] = pp;
   }
   /* ---- prediction + clamp + store, rows 2l and 2l+1 (fragment.c:49-80) ---- */
-  uint8_t *dst = job.base[OCG_FRAME_SELF] + buf_off + (2 * l) * ystride;
   uint2 pa, pb;
   if (refi == OCG_FRAME_SELF) {
     pa = pb = make_uint2(0x80808080u, 0x80808080u);
   } else {
-    const uint8_t *ref = job.base[refi] + buf_off + (2 * l) * ystride;
-    int off0, off1;
-    bool two;
-    mv_taps(mv, pli ? g.qx : 0, pli ? g.qy : 0, ystride, off0, off1, two);
-    pa = load8_unaligned(ref + off0);
-    pb = load8_unaligned(ref + off0 + ystride);
-    if (two) {
-      const uint2 ta = load8_unaligned(ref + off1);
-      const uint2 tb = load8_unaligned(ref + off1 + ystride);
+    const uint8_t *ref = job.base[refi] + it.y + (2 * l) * ystride;
+    if (spec && refi == OCG_FRAME_PREV && it.y == it.x) {
+      pa = sa; /* zero motion vector against PREV: the co-located rows */
+      pb = sb;
+    } else {
+      pa = load8_unaligned(ref);
+      pb = load8_unaligned(ref + ystride);
+    }
+    if (tap) {
+      const int fx = (int)(tap << 30) >> 30, fy = (int)(tap << 28) >> 30;
+      const uint8_t *ref2 = ref + fy * ystride + fx;
+      const uint2 ta = load8_unaligned(ref2);
+      const uint2 tb = load8_unaligned(ref2 + ystride);
       pa.x = __vhaddu4(pa.x, ta.x); pa.y = __vhaddu4(pa.y, ta.y);
       pb.x = __vhaddu4(pb.x, tb.x); pb.y = __vhaddu4(pb.y, tb.y);
     }
@@ -405,14 +462,75 @@ __device__ __forceinline__ void cell_hpair(Cell &c, const signed char *bv) {
   c.w[4][h] = __byte_perm(c.w[4][h], cc, ins);
 }
 
+/* Bounding tables for every loop-filter limit, built once per device:
+   g_lf_table[lim][u] = lflim(u-128, lim), u = 0..259 (260 B = 65 words/row). */
+__device__ signed char g_lf_table[128][260];
+
+__global__ void ocg_lf_table_kernel() {
+  const int lim = (int)blockIdx.x;
+  for (int u = (int)threadIdx.x; u < 260; u += (int)blockDim.x) g_lf_table[lim][u] = (signed char)lflim(u - 128, lim);
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void lf_cell(uint8_t *o, int ystride, const signed char *bv, bool inl, bool inr, bool ind,
+                                        bool inu, bool vd, bool vu, bool hl, bool hr, bool B, bool Cc, bool D) {
+  const int rlo = ind ? 0 : 4, rhi = inu ? 8 : 4;
+  Cell c;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (INTERIOR) {
+      const uint32_t *row = (const uint32_t *)(o + r * ystride);
+      c.w[r][0] = row[0];
+      c.w[r][1] = row[1];
+    } else {
+      c.w[r][0] = c.w[r][1] = 0;
+      if (r >= rlo && r < rhi) {
+        const uint32_t *row = (const uint32_t *)(o + r * ystride);
+        if (inl) c.w[r][0] = row[0];
+        if (inr) c.w[r][1] = row[1];
+      }
+    }
+  }
+  /* independent lines */
+  if (vd) cell_vpair<0>(c, bv);
+  if (vu) cell_vpair<6>(c, bv);
+  if (hl) cell_hpair<0>(c, bv);
+  if (hr) cell_hpair<6>(c, bv);
+  /* ordered lines through the central patch (see DESIGN.md, "loop filter") */
+  if (vd && !B) cell_vpair<2>(c, bv);
+  if (hl && !Cc) cell_hpair<2>(c, bv);
+  if (vd && B) cell_vpair<2>(c, bv);
+  if (hr && !D) cell_hpair<4>(c, bv);
+  if (hl && Cc) cell_hpair<2>(c, bv);
+  if (vu && !D) cell_vpair<4>(c, bv);
+  if (vu && D) cell_vpair<4>(c, bv);
+  if (hr && D) cell_hpair<4>(c, bv);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (INTERIOR) {
+      uint32_t *row = (uint32_t *)(o + r * ystride);
+      row[0] = c.w[r][0];
+      row[1] = c.w[r][1];
+    } else if (r >= rlo && r < rhi) {
+      uint32_t *row = (uint32_t *)(o + r * ystride);
+      if (inl) row[0] = c.w[r][0];
+      if (inr) row[1] = c.w[r][1];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(64)
 ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  __shared__ signed char bv[260];
+  __shared__ __align__(4) signed char bv[260];
   const OcgJobDev &job = jobs[blockIdx.z];
   const int lim = job.lf_limit;
   if (lim == 0) return;
-  /* bv[u] = lflim(u-128), u = 1..256 (oc_loop_filter_init_c, state.c:1036) */
-  for (int u = (int)threadIdx.x; u < 260; u += (int)blockDim.x) bv[u] = (signed char)lflim(u - 128, lim);
+  {
+    const uint32_t *src = (const uint32_t *)g_lf_table[lim];
+    uint32_t *dst = (uint32_t *)bv;
+    dst[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x == 0) dst[64] = src[64];
+  }
   __syncthreads();
   const int crow = (int)blockIdx.y;
   const int pli = crow >= g.p[2].cell_row0 ? 2 : (crow >= g.p[1].cell_row0 ? 1 : 0);
@@ -435,40 +553,8 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   if (!(vd || vu || hl || hr)) return;
   const int ystride = P.ystride;
   uint8_t *o = job.base[OCG_FRAME_SELF] + P.plane_off + (cy * 8 - 4) * ystride + (cx * 8 - 4);
-  /* rows/cols of the cell that exist inside the plane */
-  const int rlo = ind ? 0 : 4, rhi = inu ? 8 : 4;
-  Cell c;
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    c.w[r][0] = c.w[r][1] = 0;
-    if (r >= rlo && r < rhi) {
-      const uint32_t *row = (const uint32_t *)(o + r * ystride);
-      if (inl) c.w[r][0] = row[0];
-      if (inr) c.w[r][1] = row[1];
-    }
-  }
-  /* independent lines */
-  if (vd) cell_vpair<0>(c, bv);
-  if (vu) cell_vpair<6>(c, bv);
-  if (hl) cell_hpair<0>(c, bv);
-  if (hr) cell_hpair<6>(c, bv);
-  /* ordered lines through the central patch (see DESIGN.md, "loop filter") */
-  if (vd && !B) cell_vpair<2>(c, bv);
-  if (hl && !Cc) cell_hpair<2>(c, bv);
-  if (vd && B) cell_vpair<2>(c, bv);
-  if (hr && !D) cell_hpair<4>(c, bv);
-  if (hl && Cc) cell_hpair<2>(c, bv);
-  if (vu && !D) cell_vpair<4>(c, bv);
-  if (vu && D) cell_vpair<4>(c, bv);
-  if (hr && D) cell_hpair<4>(c, bv);
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    if (r >= rlo && r < rhi) {
-      uint32_t *row = (uint32_t *)(o + r * ystride);
-      if (inl) row[0] = c.w[r][0];
-      if (inr) row[1] = c.w[r][1];
-    }
-  }
+  if (inl && inr && ind && inu) lf_cell<true>(o, ystride, bv, true, true, true, true, vd, vu, hl, hr, B, Cc, D);
+  else lf_cell<false>(o, ystride, bv, inl, inr, ind, inu, vd, vu, hl, hr, B, Cc, D);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -530,6 +616,10 @@ void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, 
   dim3 grid((unsigned)((g.nfrags + 255) / 256), (unsigned)njobs);
   ocg_codedmap_kernel<<<grid, 256, 0, st>>>(g, jobs);
   ocg_count_launch(1);
+}
+
+void ocg_init_device_tables(cudaStream_t st) {
+  ocg_lf_table_kernel<<<128, 128, 0, st>>>();
 }
 
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {

@@ -14,6 +14,7 @@ struct OcgPlaneDev {
   int32_t plane_off;  /* bottom-left pixel relative to the buffer's luma base */
   int32_t lo_off;     /* lowest offset belonging to this plane (its top-left pixel) */
   int32_t cell_row0;  /* first loop-filter cell row of this plane in the fused row index */
+  uint32_t nh_magic;  /* floor(2^32/nhfrags)+1: fragment index -> row by multiply-high */
 };
 
 struct OcgGeomDev {
@@ -32,6 +33,8 @@ struct OcgJobDev {
   uint8_t            *coded;     /* nfrags bytes: written by the recon kernel, read by the loop filter */
   int32_t             lf_limit;
   uint16_t            dcq[3][2];
+  int32_t             spec_prev; /* inter frame: speculative co-located PREV loads pay off */
+  int32_t             pad_;
 };
 
 #define OCG_FRAGS_PER_BLOCK 64
@@ -41,6 +44,8 @@ void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cud
 void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
+
+void ocg_init_device_tables(cudaStream_t st); /* idempotent; call once per context */
 
 void ocg_count_launch(int n);
 
