@@ -379,6 +379,13 @@ ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
       pb.x = __vhaddu4(pb.x, tb.x); pb.y = __vhaddu4(pb.y, tb.y);
     }
   }
+  if (my == WC_DC && dcv == 0) {
+    /* zero residual (motion-compensated blocks whose prediction was good
+       enough): clamp255(0 + pred) == pred */
+    *(uint2 *)dst = pa;
+    *(uint2 *)(dst + ystride) = pb;
+    return;
+  }
   const uint2 oa = recon_row(q[0], q[2], q[4], q[6], pa);
   const uint2 ob = recon_row(q[1], q[3], q[5], q[7], pb);
   *(uint2 *)dst = oa;
