@@ -218,6 +218,38 @@ OCG_API int ocg_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref
                                      const ocg_enc_frag *frags, int n,
                                      const uint16_t *dequant, const int16_t *enquant,
                                      int16_t *dct, int16_t *qdct, int32_t *nonzero, void *stream);
+/* oc_mcenc_search_frame's full-pel search (mcenc.c:268-515) for a batch of
+   macro blocks whose candidate sets are already known (the candidates depend
+   on already-searched neighbours, mcenc.c:90-164, so the host -- or a
+   wave-front schedule -- supplies them): median predictor, set A, set B, the
+   square-pattern descent ("diamond step", mcenc.c:399-431), the per-block 4MV
+   descent (PREV only, 437-499) and the final SATD on the reconstructed
+   reference (502-513).  SAD on the ORIGINAL frames as in mcenc.c:314-316. */
+typedef struct ocg_mb_search_in {
+  int32_t  frag_off[4];  /* frag_buf_offs[mb_maps[mbi][0][0..3]]                    */
+  int8_t   cand[13][2];  /* oc_mcenc_ctx.candidates, half-pel units, [0] = median   */
+  uint8_t  setb0;        /* end of set A                                            */
+  uint8_t  ncand;        /* end of set B                                            */
+  uint16_t t2_base;      /* max of error[frame] over the MB and its first <=3 cneighbors (mcenc.c:333-337) */
+  uint8_t  is_prev;      /* frame==OC_FRAME_PREV: block vectors + 4MV search        */
+  uint8_t  pad;
+} ocg_mb_search_in;      /* 48 bytes */
+
+typedef struct ocg_mb_search_out {
+  int8_t   best_vec[2];     /* full-pel; analysis_mv[0][frame] = OC_MV(2x,2y)       */
+  uint16_t error;           /* embs[mbi].error[frame]                               */
+  uint32_t satd;            /* embs[mbi].satd[frame]                                */
+  int8_t   block_vec[4][2]; /* block_mv[bi] = OC_MV(2x,2y) (is_prev only)           */
+  uint32_t block_satd[4];   /* block_satd[bi]                (is_prev only)         */
+} ocg_mb_search_out;     /* 32 bytes */
+
+/* Device pointers; src = OC_FRAME_IO, ref_full = the *_ORIG frame searched with
+   SAD, ref_satd = the reconstructed reference used for the final SATD. */
+OCG_API int ocg_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_base,
+                                   const uint8_t *ref_satd_base, int ystride,
+                                   const ocg_mb_search_in *in, ocg_mb_search_out *out, int n,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,3 +96,50 @@ REFH_API void refh_borders_fill(unsigned char *pix_bottom_left, int ystride, int
   oc_state_borders_fill_caps(st, 0, pli);
   free(st);
 }
+
+/* ---------------------------------------------------------------------- */
+/* oc_mcenc_search_frame (lib/mcenc.c:268) on caller-provided frames, with the
+   minimal oc_enc_ctx it reads: one macro block (index 0) plus `ncn` already
+   searched neighbours (indices 1..ncn) that feed the candidate sets. */
+#include "encint.h"
+
+REFH_API void refh_mcenc_search_frame(const unsigned char *src, const unsigned char *ref_full,
+                                      const unsigned char *ref_satd, int ystride, const long frag_off[4],
+                                      int frame, int accum, int ncn, const int *nb_mv, const int *nb_err,
+                                      int mv1, int mv2, int own_err, int sp_level, int out[12]) {
+  oc_enc_ctx *enc = (oc_enc_ctx *)calloc(1, sizeof(*enc));
+  oc_mb_enc_info *embs = (oc_mb_enc_info *)calloc((size_t)ncn + 1, sizeof(*embs));
+  oc_mb_map map;
+  ptrdiff_t offs[4];
+  int i;
+  memset(map, 0xFF, sizeof(map));
+  for (i = 0; i < 4; i++) { map[0][i] = i; offs[i] = frag_off[i]; }
+  enc->mb_info = embs;
+  enc->sp_level = sp_level;
+  enc->state.mb_maps = &map;
+  enc->state.frag_buf_offs = offs;
+  enc->state.ref_ystride[0] = ystride;
+  enc->state.ref_frame_data[OC_FRAME_IO] = (unsigned char *)src;
+  enc->state.ref_frame_data[frame] = (unsigned char *)ref_satd;
+  enc->state.ref_frame_data[frame == OC_FRAME_PREV ? OC_FRAME_PREV_ORIG : OC_FRAME_GOLD_ORIG] = (unsigned char *)ref_full;
+  embs[0].ncneighbors = (unsigned char)ncn;
+  for (i = 0; i < ncn; i++) {
+    embs[0].cneighbors[i] = (unsigned)(i + 1);
+    embs[i + 1].analysis_mv[0][frame] = (oc_mv)nb_mv[i];
+    embs[i + 1].error[frame] = (ogg_uint16_t)nb_err[i];
+  }
+  embs[0].analysis_mv[1][frame] = (oc_mv)mv1;
+  embs[0].analysis_mv[2][frame] = (oc_mv)mv2;
+  embs[0].error[frame] = (ogg_uint16_t)own_err;
+  oc_mcenc_search_frame(enc, (oc_mv)accum, 0, frame,
+                        frame == OC_FRAME_PREV ? OC_FRAME_PREV_ORIG : OC_FRAME_GOLD_ORIG);
+  out[0] = embs[0].analysis_mv[0][frame];
+  out[1] = embs[0].error[frame];
+  out[2] = (int)embs[0].satd[frame];
+  for (i = 0; i < 4; i++) {
+    out[3 + i] = embs[0].block_mv[i];
+    out[7 + i] = (int)embs[0].block_satd[i];
+  }
+  free(embs);
+  free(enc);
+}

@@ -664,3 +664,186 @@ OCO_EXPORT void oco_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t 
                               enquant + (size_t)tab * 128);
   }
 }
+
+/* ---------------------------------------------------------------------- */
+/* mcenc.c:268-515 with the candidate lists supplied by the caller. */
+typedef struct {
+  const uint8_t *src, *ref;
+  int ystride;
+  const int32_t *frag_off;
+  uint32_t hit[31]; /* visited full-pel vectors, mcenc.c:292 */
+  unsigned best_err;
+  int best[2];
+  unsigned blk_err[4];
+  int blk_vec[4][2];
+  int track_blocks;
+} mcs_state;
+
+/* mcenc.c:200-220: 16x16 SAD as four block SADs */
+static unsigned mcs_sad16(const mcs_state *s, int dx, int dy, unsigned berr[4]) {
+  unsigned err = 0;
+  int bi;
+  for (bi = 0; bi < 4; bi++) {
+    berr[bi] = oco_frag_sad(s->src + s->frag_off[bi], s->ref + s->frag_off[bi] + dx + dy * s->ystride, s->ystride);
+    err += berr[bi];
+  }
+  return err;
+}
+
+static int mcs_visited(mcs_state *s, int dx, int dy) {
+  uint32_t bit = (uint32_t)1 << (dx + 15);
+  if (s->hit[dy + 15] & bit) return 1;
+  s->hit[dy + 15] |= bit;
+  return 0;
+}
+
+static void mcs_track_blocks(mcs_state *s, int dx, int dy, const unsigned berr[4]) {
+  int bi;
+  if (!s->track_blocks) return;
+  for (bi = 0; bi < 4; bi++)
+    if (berr[bi] < s->blk_err[bi]) {
+      s->blk_err[bi] = berr[bi];
+      s->blk_vec[bi][0] = dx;
+      s->blk_vec[bi][1] = dy;
+    }
+}
+
+/* sites of the 3x3 square pattern allowed at the +-15 window boundary
+   (mcenc.c:50-87 tabulates the same thing) */
+static int mcs_sites(int x, int y, int sites[8][2]) {
+  int n = 0, dx, dy;
+  for (dy = -1; dy <= 1; dy++)
+    for (dx = -1; dx <= 1; dx++) {
+      if (dx == 0 && dy == 0) continue;
+      if ((x <= -15 && dx < 0) || (x >= 15 && dx > 0) || (y <= -15 && dy < 0) || (y >= 15 && dy > 0)) continue;
+      sites[n][0] = dx;
+      sites[n][1] = dy;
+      n++;
+    }
+  return n;
+}
+
+static int div2_trunc(int v) { return v / 2; }
+
+OCO_EXPORT void oco_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_base,
+                                       const uint8_t *ref_satd_base, int ystride, const ocg_mb_search_in *in,
+                                       ocg_mb_search_out *out, int n) {
+  int i;
+  for (i = 0; i < n; i++) {
+    const ocg_mb_search_in *m = &in[i];
+    mcs_state s;
+    unsigned berr[4], err, t2;
+    int bi, ci, cx, cy;
+    memset(&s, 0, sizeof(s));
+    s.src = src_base;
+    s.ref = ref_full_base;
+    s.ystride = ystride;
+    s.frag_off = m->frag_off;
+    s.track_blocks = m->is_prev != 0;
+    /* median predictor first (mcenc.c:295-316) */
+    cx = div2_trunc(m->cand[0][0]);
+    cy = div2_trunc(m->cand[0][1]);
+    mcs_visited(&s, cx, cy);
+    s.best_err = mcs_sad16(&s, cx, cy, berr);
+    s.best[0] = cx;
+    s.best[1] = cy;
+    for (bi = 0; bi < 4; bi++) {
+      s.blk_err[bi] = berr[bi];
+      s.blk_vec[bi][0] = cx;
+      s.blk_vec[bi][1] = cy;
+    }
+    if (s.best_err > 256) { /* OC_YSAD_THRESH1 */
+      t2 = m->t2_base;
+      t2 += (t2 >> 4) + 64; /* OC_YSAD_THRESH2_SCALE_BITS / _OFFSET */
+      for (ci = 1; ci < m->setb0; ci++) { /* set A */
+        cx = div2_trunc(m->cand[ci][0]);
+        cy = div2_trunc(m->cand[ci][1]);
+        if (mcs_visited(&s, cx, cy)) continue;
+        err = mcs_sad16(&s, cx, cy, berr);
+        if (err < s.best_err) { s.best_err = err; s.best[0] = cx; s.best[1] = cy; }
+        mcs_track_blocks(&s, cx, cy, berr);
+      }
+      if (s.best_err > t2) {
+        for (; ci < m->ncand; ci++) { /* set B */
+          cx = div2_trunc(m->cand[ci][0]);
+          cy = div2_trunc(m->cand[ci][1]);
+          if (mcs_visited(&s, cx, cy)) continue;
+          err = mcs_sad16(&s, cx, cy, berr);
+          if (err < s.best_err) { s.best_err = err; s.best[0] = cx; s.best[1] = cy; }
+          mcs_track_blocks(&s, cx, cy, berr);
+        }
+        if (s.best_err > t2) {
+          int sites[8][2], ns, si, moved;
+          /* square-pattern descent around the macro-block vector (mcenc.c:399-431):
+             the centre moves to the LAST site that improved on the running best */
+          do {
+            int step[2] = {0, 0};
+            moved = 0;
+            ns = mcs_sites(s.best[0], s.best[1], sites);
+            for (si = 0; si < ns; si++) {
+              cx = s.best[0] + sites[si][0];
+              cy = s.best[1] + sites[si][1];
+              if (mcs_visited(&s, cx, cy)) continue;
+              err = mcs_sad16(&s, cx, cy, berr);
+              if (err < s.best_err) { s.best_err = err; step[0] = sites[si][0]; step[1] = sites[si][1]; moved = 1; }
+              mcs_track_blocks(&s, cx, cy, berr);
+            }
+            s.best[0] += step[0];
+            s.best[1] += step[1];
+          } while (moved);
+          /* per-block descents sharing the hit cache (mcenc.c:437-499) */
+          if (s.track_blocks) {
+            unsigned t4 = t2 >> 2;
+            for (bi = 0; bi < 4; bi++) {
+              if (s.blk_err[bi] <= t4) continue;
+              for (;;) {
+                int bx = s.blk_vec[bi][0], by = s.blk_vec[bi][1], bj;
+                ns = mcs_sites(bx, by, sites);
+                for (si = 0; si < ns; si++) {
+                  cx = bx + sites[si][0];
+                  cy = by + sites[si][1];
+                  if (mcs_visited(&s, cx, cy)) continue;
+                  err = mcs_sad16(&s, cx, cy, berr);
+                  if (err < s.best_err) { s.best_err = err; s.best[0] = cx; s.best[1] = cy; }
+                  for (bj = 0; bj < 4; bj++)
+                    if (berr[bj] < s.blk_err[bj]) {
+                      s.blk_err[bj] = berr[bj];
+                      s.blk_vec[bj][0] = cx;
+                      s.blk_vec[bj][1] = cy;
+                    }
+                }
+                if (s.blk_vec[bi][0] == bx && s.blk_vec[bi][1] == by) break;
+              }
+            }
+          }
+        }
+      }
+    }
+    /* results, incl. the SATD of the winner on the reconstructed reference (mcenc.c:500-513) */
+    {
+      ocg_mb_search_out *o = &out[i];
+      unsigned satd = 0;
+      int dc;
+      memset(o, 0, sizeof(*o));
+      o->best_vec[0] = (int8_t)s.best[0];
+      o->best_vec[1] = (int8_t)s.best[1];
+      o->error = (uint16_t)s.best_err;
+      for (bi = 0; bi < 4; bi++) {
+        satd += oco_frag_satd(&dc, src_base + m->frag_off[bi],
+                              ref_satd_base + m->frag_off[bi] + s.best[0] + s.best[1] * ystride, ystride);
+        satd += (unsigned)abs(dc);
+      }
+      o->satd = satd;
+      if (m->is_prev) {
+        for (bi = 0; bi < 4; bi++) {
+          unsigned bs = oco_frag_satd(&dc, src_base + m->frag_off[bi],
+                                      ref_satd_base + m->frag_off[bi] + s.blk_vec[bi][0] + s.blk_vec[bi][1] * ystride,
+                                      ystride);
+          o->block_vec[bi][0] = (int8_t)s.blk_vec[bi][0];
+          o->block_vec[bi][1] = (int8_t)s.blk_vec[bi][1];
+          o->block_satd[bi] = bs + (unsigned)abs(dc);
+        }
+      }
+    }
+  }
+}

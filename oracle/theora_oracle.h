@@ -74,6 +74,9 @@ void oco_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref_base, 
                               const ocg_enc_frag *frags, int n, const uint16_t *dequant,
                               const int16_t *enquant, int16_t *dct, int16_t *qdct, int32_t *nonzero);
 
+void oco_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_base, const uint8_t *ref_satd_base,
+                            int ystride, const ocg_mb_search_in *in, ocg_mb_search_out *out, int n); /* mcenc.c:268-515 */
+
 #ifdef __cplusplus
 }
 #endif

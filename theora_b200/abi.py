@@ -146,6 +146,8 @@ _PROTOS = {
     "ocg_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "ocg_enc_metrics_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "ocg_mcenc_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p]),
     "ocg_enc_fdct_quant_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

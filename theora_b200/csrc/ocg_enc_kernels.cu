@@ -289,6 +289,184 @@ ocg_enc_fdct_quant_kernel(const uint8_t *__restrict__ src_base, const uint8_t *_
   if (row == 0 && live) nonzero[fi] = last;
 }
 
+/* ------------------------------------------------------------------------ */
+/* oc_mcenc_search_frame's full-pel search (mcenc.c:268-515), one warp per
+   macro block.  Lane k handles row (k&7) of luma block (k>>3): a candidate
+   vector costs one unaligned 8-byte load, two VABSDIFF4 and a 5-step shuffle
+   reduction that yields the four block SADs and their sum.  All control state
+   (best vector/error, per-block bests) is warp-uniform; the 31x31 "already
+   visited" bitmap (mcenc.c:292) lives one row per lane. */
+struct McWarp {
+  const uint8_t *ref; /* this lane's row in the searched frame at vector (0,0) */
+  uint2 src;          /* this lane's 8 source pixels */
+  int ystride;
+  uint32_t hit;       /* row (lane) of the visited bitmap */
+  int lane;
+};
+
+/* returns the 16x16 SAD; berr = SAD of this lane's block (group of 8 lanes) */
+__device__ __forceinline__ unsigned mc_sad16(const McWarp &w, int dx, int dy, unsigned &berr) {
+  const uint2 r = ld8u(w.ref + dx + dy * w.ystride);
+  int v = (int)(__vsadu4(w.src.x, r.x) + __vsadu4(w.src.y, r.y));
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+  berr = (unsigned)v;
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+  return (unsigned)v;
+}
+
+/* test-and-set in the visited bitmap; warp-uniform result */
+__device__ __forceinline__ bool mc_visited(McWarp &w, int dx, int dy) {
+  const uint32_t bit = 1u << (dx + 15);
+  const uint32_t row = __shfl_sync(0xFFFFFFFFu, w.hit, dy + 15);
+  if (w.lane == dy + 15) w.hit |= bit;
+  return (row & bit) != 0;
+}
+
+/* sum of |8x8 Hadamard| of (src - ref row) over this lane's block: what
+   oc_mcenc_ysatd_check_*_fullpel accumulate per block, satd + |dc| (mcenc.c:222-266) */
+__device__ __forceinline__ unsigned mc_satd_block(uint2 src, uint2 ref, int row) {
+  int a[8], b[8];
+  unpack8(src, a);
+  unpack8(ref, b);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] -= b[i];
+  hadamard8(a);
+#pragma unroll
+  for (int d = 4; d >= 1; d >>= 1) {
+    const bool up = (row & d) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int o = __shfl_xor_sync(0xFFFFFFFFu, a[i], d);
+      a[i] = up ? o - a[i] : a[i] + o;
+    }
+  }
+  int acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc += abs(a[i]);
+  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+  return (unsigned)acc;
+}
+
+__global__ void __launch_bounds__(128)
+ocg_mcenc_search_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_full,
+                        const uint8_t *__restrict__ ref_satd, int ystride, const ocg_mb_search_in *__restrict__ in,
+                        ocg_mb_search_out *__restrict__ out, int n) {
+  const int mbi = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (mbi >= n) return; /* whole warp */
+  const int lane = threadIdx.x & 31;
+  const int bi = lane >> 3, row = lane & 7;
+  const ocg_mb_search_in *m = in + mbi;
+  const int foff = m->frag_off[bi] + row * ystride;
+  McWarp w;
+  w.ref = ref_full + foff;
+  w.src = ld8u(src_base + foff);
+  w.ystride = ystride;
+  w.hit = 0;
+  w.lane = lane;
+  /* per-block state lives in the block's 8 lanes (warp-uniform inside a group) */
+  unsigned berr, err;
+  int cx = (int)m->cand[0][0] / 2, cy = (int)m->cand[0][1] / 2; /* OC_DIV2: towards zero */
+  mc_visited(w, cx, cy);
+  unsigned best_err = mc_sad16(w, cx, cy, berr);
+  int bx = cx, by = cy;
+  unsigned blk_err = berr; /* this lane's block */
+  int blk_x = cx, blk_y = cy;
+  const bool track = m->is_prev != 0;
+  if (best_err > 256u) {
+    unsigned t2 = m->t2_base;
+    t2 += (t2 >> 4) + 64u;
+    const int setb0 = m->setb0, ncand = m->ncand;
+    int ci = 1;
+    for (; ci < setb0; ci++) {
+      cx = (int)m->cand[ci][0] / 2;
+      cy = (int)m->cand[ci][1] / 2;
+      if (mc_visited(w, cx, cy)) continue;
+      err = mc_sad16(w, cx, cy, berr);
+      if (err < best_err) { best_err = err; bx = cx; by = cy; }
+      if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+    }
+    if (best_err > t2) {
+      for (; ci < ncand; ci++) {
+        cx = (int)m->cand[ci][0] / 2;
+        cy = (int)m->cand[ci][1] / 2;
+        if (mc_visited(w, cx, cy)) continue;
+        err = mc_sad16(w, cx, cy, berr);
+        if (err < best_err) { best_err = err; bx = cx; by = cy; }
+        if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+      }
+      if (best_err > t2) {
+        /* square-pattern descent (mcenc.c:399-431) */
+        for (;;) {
+          int sx = 0, sy = 0;
+          bool moved = false;
+          for (int dy = -1; dy <= 1; dy++) {
+            for (int dx = -1; dx <= 1; dx++) {
+              if ((dx | dy) == 0) continue;
+              if ((bx <= -15 && dx < 0) || (bx >= 15 && dx > 0) || (by <= -15 && dy < 0) || (by >= 15 && dy > 0)) continue;
+              cx = bx + dx;
+              cy = by + dy;
+              if (mc_visited(w, cx, cy)) continue;
+              err = mc_sad16(w, cx, cy, berr);
+              if (err < best_err) { best_err = err; sx = dx; sy = dy; moved = true; }
+              if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+            }
+          }
+          if (!moved) break;
+          bx += sx;
+          by += sy;
+        }
+        /* per-block descents sharing the visited map (mcenc.c:437-499); the
+           block being refined is broadcast from its first lane */
+        if (track) {
+          const unsigned t4 = t2 >> 2;
+          for (int b = 0; b < 4; b++) {
+            if (__shfl_sync(0xFFFFFFFFu, blk_err, b * 8) <= t4) continue;
+            for (;;) {
+              const int ox = __shfl_sync(0xFFFFFFFFu, blk_x, b * 8), oy = __shfl_sync(0xFFFFFFFFu, blk_y, b * 8);
+              for (int dy = -1; dy <= 1; dy++) {
+                for (int dx = -1; dx <= 1; dx++) {
+                  if ((dx | dy) == 0) continue;
+                  if ((ox <= -15 && dx < 0) || (ox >= 15 && dx > 0) || (oy <= -15 && dy < 0) || (oy >= 15 && dy > 0)) continue;
+                  cx = ox + dx;
+                  cy = oy + dy;
+                  if (mc_visited(w, cx, cy)) continue;
+                  err = mc_sad16(w, cx, cy, berr);
+                  if (err < best_err) { best_err = err; bx = cx; by = cy; }
+                  if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+                }
+              }
+              if (__shfl_sync(0xFFFFFFFFu, blk_x, b * 8) == ox && __shfl_sync(0xFFFFFFFFu, blk_y, b * 8) == oy) break;
+            }
+          }
+        }
+      }
+    }
+  }
+  /* final SATDs on the reconstructed reference (mcenc.c:500-513) */
+  const uint8_t *rs = ref_satd + foff;
+  unsigned s_mb = mc_satd_block(w.src, ld8u(rs + bx + by * ystride), row);
+  unsigned s_blk = mc_satd_block(w.src, ld8u(rs + blk_x + blk_y * ystride), row);
+  unsigned tot = s_mb + __shfl_xor_sync(0xFFFFFFFFu, s_mb, 8);
+  tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 16);
+  ocg_mb_search_out *o = out + mbi;
+  if (lane == 0) {
+    o->best_vec[0] = (int8_t)bx;
+    o->best_vec[1] = (int8_t)by;
+    o->error = (uint16_t)best_err;
+    o->satd = tot;
+  }
+  if (row == 0) {
+    o->block_vec[bi][0] = track ? (int8_t)blk_x : (int8_t)0;
+    o->block_vec[bi][1] = track ? (int8_t)blk_y : (int8_t)0;
+    o->block_satd[bi] = track ? s_blk : 0u;
+  }
+}
+
 } /* namespace */
 
 extern "C" {
@@ -316,6 +494,19 @@ OCG_API int ocg_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref
   if (n == 0) return OCG_OK;
   ocg_enc_fdct_quant_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
       src_base, ref_base, ystride, frags, n, dequant, enquant, dct, qdct, nonzero);
+  ocg_count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+OCG_API int ocg_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_base,
+                                   const uint8_t *ref_satd_base, int ystride, const ocg_mb_search_in *in,
+                                   ocg_mb_search_out *out, int n, void *stream) {
+  if (src_base == nullptr || ref_full_base == nullptr || ref_satd_base == nullptr || in == nullptr || out == nullptr)
+    return OCG_EFAULT;
+  if (n < 0) return OCG_EINVAL;
+  if (n == 0) return OCG_OK;
+  ocg_mcenc_search_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      src_base, ref_full_base, ref_satd_base, ystride, in, out, n);
   ocg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
 }
