@@ -49,6 +49,7 @@ struct ocg_ctx {
   ocg_frag_rec *d_recs = nullptr;
   int16_t *d_rows = nullptr;
   uint8_t *d_map = nullptr;  /* coded map, produced by the recon kernel */
+  int32_t *d_xlist = nullptr; /* transform work list + 2 counters behind it */
   OcgJobDev *d_job = nullptr;
   ocg_frag_rec *tmpl = nullptr; /* host: every fragment uncoded, buf_off/plane filled in */
   Slot slots[kSlots];
@@ -85,7 +86,6 @@ static void geom_to_dev(const ocg_geometry &g, OcgGeomDev &d) {
     q.plane_off = (int32_t)p.plane_off;
     q.lo_off = (int32_t)(p.plane_off + (int64_t)(p.height - 1) * p.ystride);
     q.cell_row0 = cell_rows;
-    q.nh_magic = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)p.nhfrags) + 1u;
     cell_rows += p.nvfrags + 1;
     if (p.nhfrags + 1 > maxcx) maxcx = p.nhfrags + 1;
   }
@@ -105,8 +105,9 @@ static void fill_job(OcgJobDev &j, const ocg_ctx *c, const ocg_dec_frame &f, con
   j.recs = recs;
   j.rows = rows;
   j.coded = c->d_map;
+  j.xlist = c->d_xlist;
+  j.xcount = c->d_xlist + c->geom.nfrags;
   j.lf_limit = f.lf_limit;
-  j.spec_prev = !f.intra_frame && f.ref_idx[OCG_FRAME_PREV] >= 0;
   for (int p = 0; p < 3; p++)
     for (int q = 0; q < 2; q++) j.dcq[p][q] = f.dc_quant[p][q];
 }
@@ -153,6 +154,7 @@ static void launch_stages(const OcgGeomDev &gd, const OcgJobDev *jobs, int njobs
   else if ((mask & 2) && any_lf) ocg_launch_codedmap(gd, jobs, njobs, st);
   if ((mask & 2) && any_lf) timed_stage(1, st, [&] { ocg_launch_loop_filter(gd, jobs, njobs, st); });
   if (mask & 4) timed_stage(2, st, [&] { ocg_launch_borders(gd, jobs, njobs, st); });
+  else if (mask & 1) ocg_launch_xlist_reset(jobs, njobs, st);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -258,6 +260,7 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
   cudaFree(c->d_recs);
   cudaFree(c->d_rows);
   cudaFree(c->d_map);
+  cudaFree(c->d_xlist);
   cudaFree(c->d_job);
   free(c->tmpl);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -298,6 +301,8 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   CUX(cudaMalloc(&c->d_recs, nf * sizeof(ocg_frag_rec)));
   CUX(cudaMalloc(&c->d_rows, nf * 8 * 16));
   CUX(cudaMalloc(&c->d_map, nf));
+  CUX(cudaMalloc(&c->d_xlist, (nf + 2) * sizeof(int32_t)));
+  CUX(cudaMemsetAsync(c->d_xlist, 0, (nf + 2) * sizeof(int32_t), c->stream));
   CUX(cudaMalloc(&c->d_job, sizeof(OcgJobDev)));
   for (Slot &s : c->slots) {
     CUX(cudaHostAlloc(&s.recs, nf * sizeof(ocg_frag_rec), cudaHostAllocDefault));

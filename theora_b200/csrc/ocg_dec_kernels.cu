@@ -1,8 +1,11 @@
 /* Decode-side kernels for sm_100a.
  *
- *  ocg_recon_kernel   fused DC dequant + 8x8 iDCT + intra/inter/inter2
- *                     reconstruction, plus the uncoded-fragment copy, one
- *                     launch per batch of (stream, frame) jobs.  Replaces
+ *  ocg_recon_simple_kernel / ocg_recon_xform_kernel
+ *                     fused DC dequant + 8x8 iDCT + intra/inter/inter2
+ *                     reconstruction, plus the uncoded-fragment copy, for a
+ *                     batch of (stream, frame) jobs: pass A moves everything
+ *                     that needs no transform, pass B transforms the rest
+ *                     from a compact list.  Replaces
  *                     oc_state_frag_recon (reference lib/state.c:959),
  *                     oc_idct8x8 (idct.c:301), oc_frag_recon_* (fragment.c:49-80)
  *                     and oc_frag_copy_list (fragment.c:37).
@@ -10,11 +13,10 @@
  *                     order-free "corner cell" form.
  *  ocg_border_kernel  apron replication (state.c:770-835).
  *
- * Work mapping of the recon kernel: a CTA owns 64 consecutive fragments of the
- * frame's raster-indexed record array, partitions them by work class in shared
- * memory (stable, so raster neighbours stay neighbours and the 64-bit row
- * stores of adjacent lanes coalesce), then a fragment is handled by 4 adjacent
- * lanes, lane l owning rows 2l and 2l+1 (a warp covers 8 fragments).
+ * Work mapping: a fragment is handled by 4 adjacent lanes, lane l owning rows 2l
+ * and 2l+1 (a warp covers 8 raster-consecutive fragments, so the 64-bit row
+ * stores of adjacent lanes coalesce).  Pass B partitions each 64-fragment
+ * chunk of its list by footprint class in shared memory (stable) first.
  * The two 1-D passes run in registers; the transposes between them
  * are two __shfl_xor stages on 16-bit pairs; the final add/clamp uses the
  * packed-halfword DPX instructions (VIADDMNMX.S16x2.RELU / VIMNMX.S16x2).
@@ -199,120 +201,20 @@ __device__ __forceinline__ uint4 keep_first(uint4 w, int lim) {
   return make_uint4(w.x & m0, w.y & m1, w.z & m2, w.w & m3);
 }
 
-/* Per-fragment work item prepared once by stage 1 (instead of four times by
-   the four lanes of stage 3):
-     x  buf_off                      y  buf_off + first-tap offset (inter only)
-     z  coeff_row
-     w  [15:0] dequantised DC (class >= WC_3) or the DC-only residual (WC_DC)
-        [23:16] rowmask  [26:24] class  [28:27] refi  [30:29] plane
-   stap: second-tap step, bits [1:0] x (0, 1, 3=-1), bits [3:2] y, 0 = single tap */
-__global__ void __launch_bounds__(OCG_RECON_THREADS, 8)
-ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  __shared__ int4 sitem[OCG_FRAGS_PER_BLOCK];
-  __shared__ unsigned char stap[OCG_FRAGS_PER_BLOCK];
-  __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
-  __shared__ int scnt[2][WC_COUNT];
-  const OcgJobDev &job = jobs[blockIdx.y];
-  const int f0 = (int)blockIdx.x * OCG_FRAGS_PER_BLOCK;
-  const int nvalid = min(OCG_FRAGS_PER_BLOCK, g.nfrags - f0);
-  const int t = (int)threadIdx.x;
-  const int lane = t & 31;
-  /* ---- stage 0: speculation.  The records decide where pixels come from, so
-          a fragment costs two dependent DRAM round trips (record, then
-          predictor).  In inter frames most fragments are uncoded copies or
-          zero-MV blocks predicted from PREV, whose predictor is the co-located
-          block -- an address known from geometry alone.  Every lane therefore
-          requests "its" two co-located PREV rows right away; they are used if
-          the record agrees and dropped otherwise. ---- */
-  uint2 sa = make_uint2(0, 0), sb = make_uint2(0, 0);
-  int spec_off = 0;
-  bool spec = false;
-  if (job.spec_prev && (t >> 2) < nvalid) {
-    const int fragi = f0 + (t >> 2);
-    const int pl = fragi >= g.p[2].froffset ? 2 : (fragi >= g.p[1].froffset ? 1 : 0);
-    const OcgPlaneDev &P = g.p[pl];
-    const unsigned fi = (unsigned)(fragi - P.froffset);
-    unsigned fy = __umulhi(fi, P.nh_magic);
-    if (fy * (unsigned)P.nhfrags > fi) fy--;
-    const unsigned fx = fi - fy * (unsigned)P.nhfrags;
-    spec_off = P.plane_off + (int)fy * 8 * P.ystride + (int)fx * 8;
-    const uint8_t *src = job.base[OCG_FRAME_PREV] + spec_off + (2 * (lane & 3)) * P.ystride;
-    sa = __ldg((const uint2 *)src);
-    sb = __ldg((const uint2 *)(src + P.ystride));
-    spec = true;
-  }
-  /* ---- stage 1: the first two warps fetch the 64 records (1 KB, coalesced),
-          classify them, do the per-fragment scalar work (MV -> tap offsets,
-          state.c:846-957; DC dequant, state.c:972,978) and publish the coded
-          map for the loop filter ---- */
-  int cls = WC_NONE;
-  unsigned mine = 0;
-  if (t < OCG_FRAGS_PER_BLOCK) {
-    if (t < nvalid) {
-      const int4 rw = __ldg((const int4 *)(job.recs + f0 + t));
-      cls = work_class(rw);
-      const int mv = rw.y << 16 >> 16, dc = rw.y >> 16;
-      const int refi = (rw.w >> 16) & 3, pli = (rw.w >> 24) & 3, qti = (rw.w >> 26) & 1;
-      const int dcq = job.dcq[pli][qti];
-      const int dcv = cls == WC_DC ? (dc * dcq + 15) >> 5 : dc * dcq;
-      int off0 = 0, fx = 0, fy = 0;
-      if (cls >= WC_DC && refi != OCG_FRAME_SELF) mv_taps(mv, pli ? g.qx : 0, pli ? g.qy : 0, g.p[pli].ystride, off0, fx, fy);
-      int4 it;
-      it.x = rw.x;
-      it.y = rw.x + off0;
-      it.z = rw.z;
-      it.w = (dcv & 0xFFFF) | ((rw.w & 0xFF) << 16) | (cls << 24) | (refi << 27) | (pli << 29);
-      sitem[t] = it;
-      const unsigned tap = (unsigned)(fx & 3) | ((unsigned)(fy & 3) << 2);
-      stap[t] = (unsigned char)tap;
-      job.coded[f0 + t] = (unsigned char)(cls != WC_COPY);
-    }
-  }
-  /* blocks without any transform class (the common case in inter frames) need
-     no regrouping: copy and DC-only work is uniform enough */
-  const int need_sort = __syncthreads_or(cls >= WC_3);
-  if (need_sort) {
-    if (t < OCG_FRAGS_PER_BLOCK) {
-#pragma unroll
-      for (int c = 1; c < WC_COUNT; c++) {
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
-        if (cls == c) mine = m;
-        if (lane == 0) scnt[t >> 5][c] = __popc(m);
-      }
-    }
-    __syncthreads();
-    /* ---- stage 2: stable partition by class (raster order kept inside a class) ---- */
-    if (cls != WC_NONE) {
-      int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
-      for (int c = 1; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
-      sorder[pos] = (unsigned char)t;
-    }
-    __syncthreads();
-  }
-  /* ---- stage 3: 4 lanes per fragment, 8 fragments per warp ---- */
-  const int gi = t >> 2;
-  const int l = lane & 3;
-  int4 it = make_int4(0, 0, 0, 0);
-  unsigned tap = 0;
-  if (gi < nvalid) {
-    const int slot = need_sort ? (int)sorder[gi] : gi;
-    it = sitem[slot];
-    tap = stap[slot];
-  }
-  /* the speculative rows are valid for this group iff it still handles the
-     fragment it guessed (no regrouping) at the guessed address */
-  spec = spec && !need_sort && it.x == spec_off;
+/* Pass B for one 4-lane group (class bits == WC_NONE for idle groups, which
+   still take part in the warp-wide shuffles). */
+__device__ __forceinline__ void xform_group(const OcgGeomDev &g, const OcgJobDev &job, const int4 it, unsigned tap,
+                                            int l) {
   const int my = (it.w >> 24) & 7;
   const int wmax = __reduce_max_sync(0xFFFFFFFFu, my); /* warp-uniform */
   if (wmax == WC_NONE) return;
   const int pli = (it.w >> 29) & 3;
   const int refi = (it.w >> 27) & 3;
   const int ystride = g.p[pli].ystride;
-  const int dcv = sext16(it.w);
   uint32_t q[8];
-  if (wmax >= WC_3) {
-    /* ---- this lane's two coefficient rows (zero unless stored and inside
-            the footprint of the group's own class) ---- */
+  {
+    /* this lane's two coefficient rows (zero unless stored and inside the
+       footprint of the group's own class) */
     const int nfoot = my == WC_FULL ? 8 : (my == WC_10 ? 4 : (my == WC_3 ? 2 : 0));
     const int ra = 2 * l, rb = 2 * l + 1;
     const unsigned rowmask = ((unsigned)it.w >> 16) & 0xFFu;
@@ -332,44 +234,21 @@ ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
     xa[4] = lo16(wa.z); xa[5] = hi16(wa.z); xa[6] = lo16(wa.w); xa[7] = hi16(wa.w);
     xb[0] = lo16(wb.x); xb[1] = hi16(wb.x); xb[2] = lo16(wb.y); xb[3] = hi16(wb.y);
     xb[4] = lo16(wb.z); xb[5] = hi16(wb.z); xb[6] = lo16(wb.w); xb[7] = hi16(wb.w);
-    if (l == 0 && my >= WC_3) xa[0] = dcv; /* dequantised DC, state.c:978 */
+    if (l == 0 && my != WC_NONE) xa[0] = sext16(it.w); /* dequantised DC, state.c:978 */
     if (wmax == WC_3) idct_rows2<2>(xa, xb, q, l);
     else if (wmax == WC_10) idct_rows2<4>(xa, xb, q, l);
     else idct_rows2<8>(xa, xb, q, l);
   }
   if (my == WC_NONE) return;
   uint8_t *dst = job.base[OCG_FRAME_SELF] + it.x + (2 * l) * ystride;
-  if (my == WC_COPY) {
-    /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
-    uint2 a = sa, c = sb;
-    if (!spec) {
-      const uint8_t *src = job.base[OCG_FRAME_PREV] + it.x + (2 * l) * ystride;
-      a = __ldg((const uint2 *)src);
-      c = __ldg((const uint2 *)(src + ystride));
-    }
-    *(uint2 *)dst = a;
-    *(uint2 *)(dst + ystride) = c;
-    return;
-  }
-  if (my == WC_DC) {
-    /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block. */
-    const uint32_t pp = pack16(dcv, dcv);
-#pragma unroll
-    for (int i = 0; i < 8; i++) q[i] = pp;
-  }
-  /* ---- prediction + clamp + store, rows 2l and 2l+1 (fragment.c:49-80) ---- */
+  /* prediction, rows 2l and 2l+1 (fragment.c:49-80) */
   uint2 pa, pb;
   if (refi == OCG_FRAME_SELF) {
     pa = pb = make_uint2(0x80808080u, 0x80808080u);
   } else {
     const uint8_t *ref = job.base[refi] + it.y + (2 * l) * ystride;
-    if (spec && refi == OCG_FRAME_PREV && it.y == it.x) {
-      pa = sa; /* zero motion vector against PREV: the co-located rows */
-      pb = sb;
-    } else {
-      pa = load8_unaligned(ref);
-      pb = load8_unaligned(ref + ystride);
-    }
+    pa = load8_unaligned(ref);
+    pb = load8_unaligned(ref + ystride);
     if (tap) {
       const int fx = (int)(tap << 30) >> 30, fy = (int)(tap << 28) >> 30;
       const uint8_t *ref2 = ref + fy * ystride + fx;
@@ -379,17 +258,199 @@ ocg_recon_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
       pb.x = __vhaddu4(pb.x, tb.x); pb.y = __vhaddu4(pb.y, tb.y);
     }
   }
-  if (my == WC_DC && dcv == 0) {
-    /* zero residual (motion-compensated blocks whose prediction was good
-       enough): clamp255(0 + pred) == pred */
-    *(uint2 *)dst = pa;
-    *(uint2 *)(dst + ystride) = pb;
-    return;
-  }
   const uint2 oa = recon_row(q[0], q[2], q[4], q[6], pa);
   const uint2 ob = recon_row(q[1], q[3], q[5], q[7], pb);
   *(uint2 *)dst = oa;
   *(uint2 *)(dst + ystride) = ob;
+}
+
+/* ---- recon pass A: everything that needs no transform -------------------
+   Uncoded copies and DC-only fragments (state.c:967-975) are pure data
+   movement (+ one add/clamp); in inter frames they are ~97 % of the work.
+   ONE LANE PER FRAGMENT: a lane loads its fragment's 16-byte record, decodes
+   the motion vector once, and moves all 8 rows (up to 16 independent 64-bit
+   loads in flight per lane).  The 32 lanes of a warp own 32 raster-consecutive
+   fragments, so every row access of the warp is one contiguous 256-byte run.
+   The byte shift of an unaligned predictor is the same for all 8 rows (row
+   strides are multiples of 16), so the permute selectors are computed once.
+   Fragments that need an iDCT are appended to the job's compact work list (one
+   warp-aggregated atomic) for pass B.  Pass A also writes the coded map the
+   loop filter reads. */
+#define OCG_SIMPLE_THREADS 128
+
+struct Rows8 { uint2 r[8]; };
+
+/* rows p, p+ystride, ... : 8 bytes each at an arbitrary byte address */
+__device__ __forceinline__ void load_rows8(const uint8_t *p, int ystride, Rows8 &o) {
+  const uintptr_t a = (uintptr_t)p;
+  const unsigned sh = (unsigned)(a & 7);
+  const uint8_t *base = (const uint8_t *)(a & ~(uintptr_t)7);
+  if (sh == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.r[i] = __ldg((const uint2 *)(base + i * ystride));
+    return;
+  }
+  uint2 w0[8], w1[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    w0[i] = __ldg((const uint2 *)(base + i * ystride));
+    w1[i] = __ldg((const uint2 *)(base + i * ystride) + 1);
+  }
+  const unsigned sel = 0x3210u + 0x1111u * (sh & 3);
+  if (sh < 4) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o.r[i].x = __byte_perm(w0[i].x, w0[i].y, sel);
+      o.r[i].y = __byte_perm(w0[i].y, w1[i].x, sel);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o.r[i].x = __byte_perm(w0[i].y, w1[i].x, sel);
+      o.r[i].y = __byte_perm(w1[i].x, w1[i].y, sel);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(OCG_SIMPLE_THREADS)
+ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  const OcgJobDev &job = jobs[blockIdx.y];
+  const int lane = (int)threadIdx.x & 31;
+  const int fragi = (int)(blockIdx.x * OCG_SIMPLE_THREADS + threadIdx.x);
+  int4 rw = make_int4(0, 0, 0, 0);
+  int cls = WC_NONE;
+  if (fragi < g.nfrags) {
+    rw = __ldg((const int4 *)(job.recs + fragi));
+    cls = work_class(rw);
+    job.coded[fragi] = (unsigned char)(cls != WC_COPY);
+  }
+  /* hand the transform fragments to pass B */
+  const unsigned want = __ballot_sync(0xFFFFFFFFu, cls >= WC_3);
+  if (want) {
+    int base = 0;
+    const int leader = __ffs(want) - 1;
+    if (lane == leader) base = atomicAdd(job.xcount, __popc(want));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (cls >= WC_3) job.xlist[base + __popc(want & ((1u << lane) - 1u))] = fragi;
+  }
+  if (cls != WC_COPY && cls != WC_DC) return;
+  const int pli = (rw.w >> 24) & 3;
+  const int ystride = g.p[pli].ystride;
+  uint8_t *dst = job.base[OCG_FRAME_SELF] + rw.x;
+  Rows8 px;
+  if (cls == WC_COPY) {
+    /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
+    const uint8_t *src = job.base[OCG_FRAME_PREV] + rw.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) px.r[i] = __ldg((const uint2 *)(src + i * ystride));
+  } else {
+    const int refi = (rw.w >> 16) & 3;
+    if (refi == OCG_FRAME_SELF) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) px.r[i] = make_uint2(0x80808080u, 0x80808080u);
+    } else {
+      int off0, fx, fy;
+      mv_taps(rw.y << 16 >> 16, pli ? g.qx : 0, pli ? g.qy : 0, ystride, off0, fx, fy);
+      const uint8_t *ref = job.base[refi] + rw.x + off0;
+      load_rows8(ref, ystride, px);
+      if (fx | fy) {
+        Rows8 t2;
+        load_rows8(ref + fy * ystride + fx, ystride, t2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          px.r[i].x = __vhaddu4(px.r[i].x, t2.r[i].x);
+          px.r[i].y = __vhaddu4(px.r[i].y, t2.r[i].y);
+        }
+      }
+    }
+    /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block */
+    const int p = sext16(((rw.y >> 16) * (int)job.dcq[pli][(rw.w >> 26) & 1] + 15) >> 5);
+    if (p != 0) {
+      const uint32_t pp = pack16(p, p);
+#pragma unroll
+      for (int i = 0; i < 8; i++) px.r[i] = recon_row(pp, pp, pp, pp, px.r[i]);
+    } /* else zero residual: clamp255(0 + pred) == pred */
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) *(uint2 *)(dst + i * ystride) = px.r[i];
+}
+
+/* ---- recon pass B: fragments with an 8x8 iDCT ------------------------------
+   A CTA takes 64 entries of the compact list pass A produced, turns their
+   records into work items (MV -> tap offsets, state.c:846-957; DC dequant,
+   state.c:978), partitions them by footprint class in shared memory (stable,
+   so neighbours stay neighbours) and runs 4 lanes per fragment.
+     item.x  buf_off                 item.y  buf_off + first-tap offset
+     item.z  coeff_row
+     item.w  [15:0] dequantised DC  [23:16] rowmask  [26:24] class
+             [28:27] refi  [30:29] plane
+     stap    second-tap step: bits [1:0] x (0, 1, 3=-1), bits [3:2] y
+   The list counter is cleared by the border kernel (or ocg_xlist_reset_kernel),
+   which always follows in stream order. */
+__global__ void __launch_bounds__(OCG_RECON_THREADS, 6)
+ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  __shared__ int4 sitem[OCG_FRAGS_PER_BLOCK];
+  __shared__ unsigned char stap[OCG_FRAGS_PER_BLOCK];
+  __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
+  __shared__ int scnt[2][WC_COUNT];
+  const OcgJobDev &job = jobs[blockIdx.y];
+  const int t = (int)threadIdx.x;
+  const int lane = t & 31;
+  const int nx = *(volatile const int *)job.xcount;
+  /* the list length is only known on the device: a fixed, small grid strides over it */
+  for (int e0 = (int)blockIdx.x * OCG_FRAGS_PER_BLOCK; e0 < nx; e0 += (int)gridDim.x * OCG_FRAGS_PER_BLOCK) {
+    const int nvalid = min(OCG_FRAGS_PER_BLOCK, nx - e0);
+    int cls = WC_NONE;
+    unsigned mine = 0;
+    if (t < OCG_FRAGS_PER_BLOCK) {
+      if (t < nvalid) {
+        const int fragi = job.xlist[e0 + t];
+        const int4 rw = __ldg((const int4 *)(job.recs + fragi));
+        cls = work_class(rw);
+        const int refi = (rw.w >> 16) & 3, pli = (rw.w >> 24) & 3, qti = (rw.w >> 26) & 1;
+        const int dcv = (rw.y >> 16) * (int)job.dcq[pli][qti];
+        int off0 = 0, fx = 0, fy = 0;
+        if (refi != OCG_FRAME_SELF) mv_taps(rw.y << 16 >> 16, pli ? g.qx : 0, pli ? g.qy : 0, g.p[pli].ystride, off0, fx, fy);
+        int4 it;
+        it.x = rw.x;
+        it.y = rw.x + off0;
+        it.z = rw.z;
+        it.w = (dcv & 0xFFFF) | ((rw.w & 0xFF) << 16) | (cls << 24) | (refi << 27) | (pli << 29);
+        sitem[t] = it;
+        stap[t] = (unsigned char)((unsigned)(fx & 3) | ((unsigned)(fy & 3) << 2));
+      }
+#pragma unroll
+      for (int c = WC_3; c < WC_COUNT; c++) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+        if (cls == c) mine = m;
+        if (lane == 0) scnt[t >> 5][c] = __popc(m);
+      }
+    }
+    __syncthreads();
+    if (cls != WC_NONE) {
+      int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
+      for (int c = WC_3; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
+      sorder[pos] = (unsigned char)t;
+    }
+    __syncthreads();
+    const int gi = t >> 2;
+    int4 it = make_int4(0, 0, 0, 0);
+    unsigned tap = 0;
+    if (gi < nvalid) {
+      const int slot = (int)sorder[gi];
+      it = sitem[slot];
+      tap = stap[slot];
+    }
+    xform_group(g, job, it, tap, lane & 3);
+    __syncthreads(); /* shared arrays are rewritten by the next chunk */
+  }
+}
+
+/* Clears the transform work-list counters of every job (stream-ordered after
+   pass B); used when the border kernel, which normally does it, is not run. */
+__global__ void ocg_xlist_reset_kernel(const OcgJobDev *__restrict__ jobs, int njobs) {
+  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (j < njobs) jobs[j].xcount[0] = 0;
 }
 
 /* Only the coded map (for running the loop filter stage on its own). */
@@ -574,6 +635,7 @@ __global__ void __launch_bounds__(128)
 ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const OcgJobDev &job = jobs[blockIdx.y];
   int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (t == 0) job.xcount[0] = 0; /* recon pass B is done with this frame's work list */
 #pragma unroll
   for (int pli = 0; pli < 3; pli++) {
     const OcgPlaneDev &P = g.p[pli];
@@ -613,8 +675,21 @@ ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
 
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return;
-  dim3 grid((unsigned)((g.nfrags + OCG_FRAGS_PER_BLOCK - 1) / OCG_FRAGS_PER_BLOCK), (unsigned)njobs);
-  ocg_recon_kernel<<<grid, OCG_RECON_THREADS, 0, st>>>(g, jobs);
+  dim3 ga((unsigned)((g.nfrags + OCG_SIMPLE_THREADS - 1) / OCG_SIMPLE_THREADS), (unsigned)njobs);
+  ocg_recon_simple_kernel<<<ga, OCG_SIMPLE_THREADS, 0, st>>>(g, jobs);
+  /* pass B: about six CTAs per SM in total, each striding over its job's list */
+  int per_job = (148 * 6 + njobs - 1) / njobs;
+  const int tiles = (g.nfrags + OCG_FRAGS_PER_BLOCK - 1) / OCG_FRAGS_PER_BLOCK;
+  if (per_job < 8) per_job = 8;
+  if (per_job > tiles) per_job = tiles;
+  dim3 gb((unsigned)per_job, (unsigned)njobs);
+  ocg_recon_xform_kernel<<<gb, OCG_RECON_THREADS, 0, st>>>(g, jobs);
+  ocg_count_launch(2);
+}
+
+void ocg_launch_xlist_reset(const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return;
+  ocg_xlist_reset_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(jobs, njobs);
   ocg_count_launch(1);
 }
 

@@ -14,7 +14,6 @@ struct OcgPlaneDev {
   int32_t plane_off;  /* bottom-left pixel relative to the buffer's luma base */
   int32_t lo_off;     /* lowest offset belonging to this plane (its top-left pixel) */
   int32_t cell_row0;  /* first loop-filter cell row of this plane in the fused row index */
-  uint32_t nh_magic;  /* floor(2^32/nhfrags)+1: fragment index -> row by multiply-high */
 };
 
 struct OcgGeomDev {
@@ -30,17 +29,18 @@ struct OcgJobDev {
   uint8_t            *base[3];   /* GOLD, PREV, SELF: buffer + base_off */
   const ocg_frag_rec *recs;      /* nfrags, fragment-index order */
   const int16_t      *rows;
-  uint8_t            *coded;     /* nfrags bytes: written by the recon kernel, read by the loop filter */
+  uint8_t            *coded;     /* nfrags bytes: written by recon pass A, read by the loop filter */
+  int32_t            *xlist;     /* nfrags: fragments needing a transform (pass A -> pass B) */
+  int32_t            *xcount;    /* [0] list length; 0 between frames (cleared by the border kernel) */
   int32_t             lf_limit;
   uint16_t            dcq[3][2];
-  int32_t             spec_prev; /* inter frame: speculative co-located PREV loads pay off */
-  int32_t             pad_;
 };
 
 #define OCG_FRAGS_PER_BLOCK 64
 #define OCG_RECON_THREADS   256
 
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
+void ocg_launch_xlist_reset(const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
