@@ -587,20 +587,23 @@ __device__ __forceinline__ void lf_cell(uint8_t *o, int ystride, const signed ch
   }
 }
 
-__global__ void __launch_bounds__(64)
+#define OCG_LF_ROWS 1 /* cell rows per CTA (64 cells wide); 4 rows/CTA measured 10 % slower (tail + occupancy) */
+
+__global__ void __launch_bounds__(64 * OCG_LF_ROWS)
 ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   __shared__ __align__(4) signed char bv[260];
   const OcgJobDev &job = jobs[blockIdx.z];
   const int lim = job.lf_limit;
   if (lim == 0) return;
-  {
+  if (threadIdx.y == 0) {
     const uint32_t *src = (const uint32_t *)g_lf_table[lim];
     uint32_t *dst = (uint32_t *)bv;
     dst[threadIdx.x] = src[threadIdx.x];
     if (threadIdx.x == 0) dst[64] = src[64];
   }
   __syncthreads();
-  const int crow = (int)blockIdx.y;
+  const int crow = (int)blockIdx.y * OCG_LF_ROWS + (int)threadIdx.y;
+  if (crow >= g.cell_rows) return;
   const int pli = crow >= g.p[2].cell_row0 ? 2 : (crow >= g.p[1].cell_row0 ? 1 : 0);
   const OcgPlaneDev &P = g.p[pli];
   const int cy = crow - P.cell_row0;
@@ -631,7 +634,7 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
    One thread per 8-byte work item, items enumerated linearly per job:
      side items  every picture row x {left,right} x hpad/8
      cap items   every apron row above/below x padded width/8            */
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const OcgJobDev &job = jobs[blockIdx.y];
   int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -706,8 +709,9 @@ void ocg_init_device_tables(cudaStream_t st) {
 
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return;
-  dim3 grid((unsigned)((g.max_cells_x + 63) / 64), (unsigned)g.cell_rows, (unsigned)njobs);
-  ocg_lf_kernel<<<grid, 64, 0, st>>>(g, jobs);
+  dim3 grid((unsigned)((g.max_cells_x + 63) / 64), (unsigned)((g.cell_rows + OCG_LF_ROWS - 1) / OCG_LF_ROWS),
+            (unsigned)njobs);
+  ocg_lf_kernel<<<grid, dim3(64, OCG_LF_ROWS), 0, st>>>(g, jobs);
   ocg_count_launch(1);
 }
 
@@ -716,7 +720,7 @@ void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, c
   int items = 0;
   for (int pli = 0; pli < 3; pli++)
     items += g.p[pli].height * 2 * (g.p[pli].hpad >> 3) + 2 * g.p[pli].vpad * ((g.p[pli].width + 2 * g.p[pli].hpad) >> 3);
-  dim3 grid((unsigned)((items + 127) / 128), (unsigned)njobs);
-  ocg_border_kernel<<<grid, 128, 0, st>>>(g, jobs);
+  dim3 grid((unsigned)((items + 255) / 256), (unsigned)njobs);
+  ocg_border_kernel<<<grid, 256, 0, st>>>(g, jobs);
   ocg_count_launch(1);
 }
