@@ -147,6 +147,97 @@ def time_reference(blob, threads, passes):
     return threads * passes * nframes / secs, secs, kind, int(hsh.value)
 
 
+def bench_encode_kernels(torch, dev, peak, nframes=16):
+    """Throughput + algorithmic-bytes roofline of the encoder batch kernels on 1080p luma
+    (BASELINE configs[2]/[3] block work; informational, the headline is decode)."""
+    import theora_b200 as T
+    from theora_b200 import abi
+    tdir = os.path.join(ROOT, "tests")
+    if tdir not in sys.path:
+        sys.path.insert(0, tdir)
+    import mcgen as M
+    L = abi.lib()
+    rng = np.random.default_rng(7)
+    w, h = 1920, 1088
+    src, rfull, rsatd, bl, ystride = M.make_scene(rng, w=w, h=h, pad=16, shift=(3, 1), noise=3)
+    fsz = src.size
+    dsrc = torch.from_numpy(np.tile(src.reshape(-1), nframes)).to(dev)
+    dref = torch.from_numpy(np.tile(rfull.reshape(-1), nframes)).to(dev)
+    dsat = torch.from_numpy(np.tile(rsatd.reshape(-1), nframes)).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    nfr = (w // 8) * (h // 8)
+    fy, fx = np.divmod(np.arange(nfr), w // 8)
+    off1 = (fy * 8 * ystride + fx * 8).astype(np.int64)
+    offs = (off1[None, :] + (np.arange(nframes) * fsz)[:, None]).reshape(-1)
+    n = offs.size
+    fr = np.zeros(n, abi.ENC_FRAG_DTYPE)
+    fr["src_off"] = offs
+    fr["ref_off0"] = offs + 3 + 1 * ystride
+    fr["ref_off1"] = abi.INT32_MIN
+    fr["aux"] = 4
+    dfr = torch.from_numpy(fr.view(np.int32).reshape(n, 4)).to(dev)
+    deq = rng.integers(8, 300, size=(18, 64)).astype(np.uint16)
+    enq = np.zeros((18, 128), np.int16)
+    for t in range(18):  # enquant.c:184-192 (m,l) pairs
+        d2 = deq[t].astype(np.int64) << 1
+        lg = np.floor(np.log2(d2)).astype(np.int64)
+        enq[t, 0::2] = ((1 + (1 << (16 + lg)) // d2) - 0x10000).astype(np.int16)
+        enq[t, 1::2] = lg
+    ddeq, denq = torch.from_numpy(deq.view(np.int16)).to(dev), torch.from_numpy(enq).to(dev)
+    od = torch.empty((n, 64), dtype=torch.int16, device=dev)
+    oq = torch.empty((n, 64), dtype=torch.int16, device=dev)
+    onz = torch.empty(n, dtype=torch.int32, device=dev)
+    ov = torch.empty(n, dtype=torch.int32, device=dev)
+    odc = torch.empty(n, dtype=torch.int32, device=dev)
+    nmb = (w // 16) * (h // 16)
+    mb1 = np.zeros(nmb, M.MB_IN)
+    i = 0
+    for my in range(0, h, 16):
+        for mx in range(0, w, 16):
+            mb1[i]["frag_off"] = [(my + by) * ystride + mx + bx for by in (0, 8) for bx in (0, 8)]
+            mb1[i]["cand"][3] = (0, 0)
+            mb1[i]["setb0"], mb1[i]["ncand"], mb1[i]["t2_base"], mb1[i]["is_prev"] = 4, 5, 0, 1
+            i += 1
+    mbs = np.tile(mb1, nframes)
+    mbs["frag_off"] += np.repeat(np.arange(nframes) * fsz, nmb)[:, None].astype(np.int32)
+    dmb = torch.from_numpy(mbs.view(np.uint8).reshape(-1, 48)).to(dev)
+    omb = torch.empty((len(mbs), 32), dtype=torch.uint8, device=dev)
+    bs, br, bt = dsrc.data_ptr() + bl, dref.data_ptr() + bl, dsat.data_ptr() + bl
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    ms = timed(lambda: abi.check(L.ocg_enc_fdct_quant_batch(bs, br, ystride, dfr.data_ptr(), n, ddeq.data_ptr(),
+                                                            denq.data_ptr(), od.data_ptr(), oq.data_ptr(),
+                                                            onz.data_ptr(), st)))
+    out["fdct_quant_inter"] = {"ms": ms, "blocks_per_s": n / (ms * 1e-3), "alg_GBps": n * 384 / (ms * 1e-3) / 1e9,
+                               "frac": n * 384 / (ms * 1e-3) / 1e9 / peak,
+                               "luma_frames_per_s": nframes / (ms * 1e-3)}
+    for name, metric, nbytes in (("sad", 0, 136), ("satd", 1, 136), ("ssd", 3, 136)):
+        ms = timed(lambda: abi.check(L.ocg_enc_metrics_batch(metric, bs, br, ystride, dfr.data_ptr(), n,
+                                                             ov.data_ptr(), odc.data_ptr(), st)))
+        out[name] = {"ms": ms, "blocks_per_s": n / (ms * 1e-3), "alg_GBps": n * nbytes / (ms * 1e-3) / 1e9,
+                     "frac": n * nbytes / (ms * 1e-3) / 1e9 / peak}
+    ms = timed(lambda: abi.check(L.ocg_mcenc_search_batch(bs, br, bt, ystride, dmb.data_ptr(), omb.data_ptr(),
+                                                          len(mbs), st)), reps=5)
+    res = omb.cpu().numpy().view(M.MB_OUT).reshape(-1)
+    out["mcenc_search"] = {"ms": ms, "macro_blocks_per_s": len(mbs) / (ms * 1e-3),
+                           "frames_per_s_one_ref": nframes / (ms * 1e-3),
+                           "found_planted_vector": float(np.mean((res["best_vec"][:, 0] == 3) &
+                                                                 (np.abs(res["best_vec"][:, 1]) == 1)))}
+    out["config"] = "1920x1088 luma, %d frames per launch, inter residual vs (3,1)-displaced reference" % nframes
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +253,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads for e2e / CPU arms (0 = all cores)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-encode-kernels", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     ncores = args.threads or host_cores()
@@ -315,8 +407,15 @@ def main():
         Lo.ocg_backend_get_stats(C.byref(st), 1)
         barrier()
         hsh = C.c_uint64(0)
-        secs = Lo.refh_decode_time(h, ncores, 1, C.byref(hsh))
-        Lo.ocg_backend_get_stats(C.byref(st), 1)
+        runs = []
+        for _ in range(3):  # three passes, median: 16 host threads + PCIe make single passes noisy
+            Lo.ocg_backend_get_stats(C.byref(st), 1)  # reset
+            secs_i = Lo.refh_decode_time(h, ncores, 1, C.byref(hsh))
+            st_i = streams.BackendStats()
+            Lo.ocg_backend_get_stats(C.byref(st_i), 1)
+            runs.append((secs_i, st_i))
+        runs.sort(key=lambda r: r[0])
+        secs, st = runs[1]
         Lo.refh_stream_free(h)
         assert secs > 0, "e2e decode failed"
         secs = sharding.max_over_ranks(secs, dev)
@@ -328,12 +427,21 @@ def main():
     cpu = None
     if RANK == 0 and WORLD == 1 and not args.no_cpu:
         fps, secs, kind, ref_hash = time_reference(blob, ncores, 1)
+        more = [time_reference(blob, ncores, 1) for _ in range(2)]
+        fps, secs = sorted([(fps, secs)] + [(m[0], m[1]) for m in more])[1]
         cpu = {"value": fps, "unit": "frames/s", "cores": ncores,
                "kind": "reference" if kind == "asm" else "reference (C path)",
                "sample": "%d streams x %d frames via th_decode_packetin, %.1fs" % (ncores, nframes, secs),
                "final_frame_hash": ref_hash}
         if e2e is not None:
             e2e["parity_with_cpu_baseline"] = bool(e2e["final_frame_hash"] == ref_hash)
+
+    enc = None
+    if RANK == 0 and not args.no_encode_kernels:
+        try:
+            enc = bench_encode_kernels(torch, dev, peak)
+        except Exception as e:  # informational section: never take the headline down with it
+            enc = {"error": repr(e)}
 
     if RANK == 0:
         line = {"metric": "1080p decode frames/sec", "value": value, "unit": "frames/s", "n_gpus": WORLD,
@@ -344,7 +452,8 @@ def main():
                            "frame_units_per_step": S * nframes, "l2": "working set of a launch (%d streams x 3 x %.1f MB "
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
                            "parallelism": "independent streams, %d per GPU" % S},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
+                "gpu_launches": int(launches),
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     if WORLD > 1:

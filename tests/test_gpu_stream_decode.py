@@ -19,6 +19,7 @@ CASES = [
     (320, 240, 6, 10, 3, 0, 28),
     (96, 80, 10, 60, 64, 2, 26),
     (1920, 1080, 4, 32, 64, 1, 30),
+    (3840, 2160, 3, 32, 64, 2, 30),   # BASELINE configs[4] frame size
 ]
 
 
