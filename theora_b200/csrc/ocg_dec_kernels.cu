@@ -278,41 +278,43 @@ __device__ __forceinline__ void xform_group(const OcgGeomDev &g, const OcgJobDev
    loop filter reads. */
 #define OCG_SIMPLE_THREADS 128
 
-struct Rows8 { uint2 r[8]; };
+#define OCG_A_ROWS 4 /* rows moved per step: 2 steps of 4 keep the kernel at ~32 registers (full occupancy) */
+
+struct RowsN { uint2 r[OCG_A_ROWS]; };
 
 /* rows p, p+ystride, ... : 8 bytes each at an arbitrary byte address */
-__device__ __forceinline__ void load_rows8(const uint8_t *p, int ystride, Rows8 &o) {
+__device__ __forceinline__ void load_rows(const uint8_t *p, int ystride, RowsN &o) {
   const uintptr_t a = (uintptr_t)p;
   const unsigned sh = (unsigned)(a & 7);
   const uint8_t *base = (const uint8_t *)(a & ~(uintptr_t)7);
   if (sh == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) o.r[i] = __ldg((const uint2 *)(base + i * ystride));
+    for (int i = 0; i < OCG_A_ROWS; i++) o.r[i] = __ldg((const uint2 *)(base + i * ystride));
     return;
   }
-  uint2 w0[8], w1[8];
+  uint2 w0[OCG_A_ROWS], w1[OCG_A_ROWS];
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < OCG_A_ROWS; i++) {
     w0[i] = __ldg((const uint2 *)(base + i * ystride));
     w1[i] = __ldg((const uint2 *)(base + i * ystride) + 1);
   }
   const unsigned sel = 0x3210u + 0x1111u * (sh & 3);
   if (sh < 4) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < OCG_A_ROWS; i++) {
       o.r[i].x = __byte_perm(w0[i].x, w0[i].y, sel);
       o.r[i].y = __byte_perm(w0[i].y, w1[i].x, sel);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < OCG_A_ROWS; i++) {
       o.r[i].x = __byte_perm(w0[i].y, w1[i].x, sel);
       o.r[i].y = __byte_perm(w1[i].x, w1[i].y, sel);
     }
   }
 }
 
-__global__ void __launch_bounds__(OCG_SIMPLE_THREADS)
+__global__ void __launch_bounds__(OCG_SIMPLE_THREADS, 12)
 ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const OcgJobDev &job = jobs[blockIdx.y];
   const int lane = (int)threadIdx.x & 31;
@@ -337,42 +339,47 @@ ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) 
   const int pli = (rw.w >> 24) & 3;
   const int ystride = g.p[pli].ystride;
   uint8_t *dst = job.base[OCG_FRAME_SELF] + rw.x;
-  Rows8 px;
-  if (cls == WC_COPY) {
-    /* oc_frag_copy_list, fragment.c:37-47: PREV -> SELF */
-    const uint8_t *src = job.base[OCG_FRAME_PREV] + rw.x;
+  /* source of the block: PREV co-located (copy), a motion-displaced reference
+     (one or two taps), or the constant 128 of intra prediction */
+  const int refi = cls == WC_COPY ? OCG_FRAME_PREV : (rw.w >> 16) & 3;
+  const uint8_t *ref = nullptr;
+  int tap2 = 0;
+  bool two = false;
+  if (refi != OCG_FRAME_SELF) {
+    int off0 = 0, fx = 0, fy = 0;
+    if (cls == WC_DC) mv_taps(rw.y << 16 >> 16, pli ? g.qx : 0, pli ? g.qy : 0, ystride, off0, fx, fy);
+    ref = job.base[refi] + rw.x + off0;
+    tap2 = fy * ystride + fx;
+    two = (fx | fy) != 0;
+  }
+  /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block; 0 for copies */
+  const int p = cls == WC_DC ? sext16(((rw.y >> 16) * (int)job.dcq[pli][(rw.w >> 26) & 1] + 15) >> 5) : 0;
+  const uint32_t pp = pack16(p, p);
+#pragma unroll 1
+  for (int r0 = 0; r0 < 8; r0 += OCG_A_ROWS) {
+    RowsN px;
+    if (ref == nullptr) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) px.r[i] = __ldg((const uint2 *)(src + i * ystride));
-  } else {
-    const int refi = (rw.w >> 16) & 3;
-    if (refi == OCG_FRAME_SELF) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) px.r[i] = make_uint2(0x80808080u, 0x80808080u);
+      for (int i = 0; i < OCG_A_ROWS; i++) px.r[i] = make_uint2(0x80808080u, 0x80808080u);
     } else {
-      int off0, fx, fy;
-      mv_taps(rw.y << 16 >> 16, pli ? g.qx : 0, pli ? g.qy : 0, ystride, off0, fx, fy);
-      const uint8_t *ref = job.base[refi] + rw.x + off0;
-      load_rows8(ref, ystride, px);
-      if (fx | fy) {
-        Rows8 t2;
-        load_rows8(ref + fy * ystride + fx, ystride, t2);
+      load_rows(ref + r0 * ystride, ystride, px);
+      if (two) {
+        RowsN t2;
+        load_rows(ref + r0 * ystride + tap2, ystride, t2);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < OCG_A_ROWS; i++) {
           px.r[i].x = __vhaddu4(px.r[i].x, t2.r[i].x);
           px.r[i].y = __vhaddu4(px.r[i].y, t2.r[i].y);
         }
       }
     }
-    /* state.c:967-975: p=(dc*dc_quant+15)>>5 replicated over the block */
-    const int p = sext16(((rw.y >> 16) * (int)job.dcq[pli][(rw.w >> 26) & 1] + 15) >> 5);
     if (p != 0) {
-      const uint32_t pp = pack16(p, p);
 #pragma unroll
-      for (int i = 0; i < 8; i++) px.r[i] = recon_row(pp, pp, pp, pp, px.r[i]);
-    } /* else zero residual: clamp255(0 + pred) == pred */
+      for (int i = 0; i < OCG_A_ROWS; i++) px.r[i] = recon_row(pp, pp, pp, pp, px.r[i]);
+    } /* else zero residual / copy: clamp255(0 + pred) == pred */
+#pragma unroll
+    for (int i = 0; i < OCG_A_ROWS; i++) *(uint2 *)(dst + (r0 + i) * ystride) = px.r[i];
   }
-#pragma unroll
-  for (int i = 0; i < 8; i++) *(uint2 *)(dst + i * ystride) = px.r[i];
 }
 
 /* ---- recon pass B: fragments with an 8x8 iDCT ------------------------------
