@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -349,13 +349,13 @@ def main():
         for f in range(nframes):
             T.run_batch(ctxs, packs, [f] * S, ctxs[0].stream)
 
+    sampler = ClockSampler(LOCAL_RANK)  # samples through warm-up + timed region (both under the same load)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     ctxs[0].sync()
     torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(LOCAL_RANK)
-    sampler.start()
     launches0 = L.ocg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -389,8 +389,15 @@ def main():
                                     "alg_GBps": stage_bytes[i] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}
     dom = max(range(3), key=lambda i: ms3[i])
     achieved = stage_bytes[dom] / (ms3[dom] / n3[dom] * 1e-3) / 1e9 if n3[dom] and stage_bytes[dom] else 0.0
+    traffic = None
+    try:  # measured DRAM bytes per launch from the committed ncu capture (same streams-per-launch only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        if int(tj["streams_per_launch"]) == S:
+            traffic = tj["dram_bytes_per_launch"].get(stage_names[dom])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                 "alg_bytes_per_launch": stage_bytes[dom], "kernels": kern}
     for c in ctxs:
         c.close()
