@@ -182,6 +182,12 @@ OCG_API int  ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs,
    bit2 border fill.  Default 7. */
 OCG_API void ocg_set_stage_mask(int mask);
 OCG_API long ocg_launch_count(void);   /* kernels launched by this library so far */
+/* Loop-filter variant: 0 (default) = per-thread global loads/stores, 1 = the
+   input tile of each CTA is fetched by one TMA (cp.async.bulk.tensor.2d) into
+   shared memory.  Both are bit-exact; on B200 the TMA variant measured slower
+   (67 vs 48 us per 32-frame launch: 4 KB boxes are too small to amortise the
+   TMA issue cost), so it is opt-in.  Call before creating contexts. */
+OCG_API void ocg_set_lf_tma(int on);
 /* Per-stage device timing with CUDA events on the launching stream.  While
    enabled every stage launch (0 recon+copy, 1 loop filter, 2 borders) is
    bracketed by an event pair; collect() waits for them and returns the summed

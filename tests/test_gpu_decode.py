@@ -78,16 +78,23 @@ def test_each_sparsity_class(cls):
     assert np.array_equal(want, got), first_diff(g, want, got)
 
 
-def test_loop_filter_only_all_limits():
-    """Loop filter + borders on random pixels, every coded pattern, many limits."""
+@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("dims", [(96, 80, 0), (1040, 48, 0), (1024, 32, 2), (560, 64, 3), (80, 96, 3)])
+def test_loop_filter_only_all_limits(tma, dims):
+    """Loop filter + borders on random pixels, every coded pattern, many limits,
+    both kernel variants (TMA tiles through shared memory / per-thread accesses)."""
     rng = np.random.default_rng(5)
-    g = S.make_geometry(96, 80, 0, 3)
-    for lim in (1, 2, 3, 7, 16, 31, 63, 127):
-        frames = W.random_frames(g, rng)
-        work = W.random_work(g, rng, density=float(rng.random()), lf_limit=lim)
-        want = W.oracle_decode(g, frames, work, 6)
-        got = run_gpu(g, frames, work, 6)
-        assert np.array_equal(want, got), (lim, first_diff(g, want, got))
+    g = S.make_geometry(dims[0], dims[1], dims[2], 3)
+    T.lib().ocg_set_lf_tma(tma)  # before the contexts are created: they build the tensor maps
+    try:
+        for lim in (1, 2, 3, 7, 16, 31, 63, 127):
+            frames = W.random_frames(g, rng)
+            work = W.random_work(g, rng, density=float(rng.random()), lf_limit=lim)
+            want = W.oracle_decode(g, frames, work, 6)
+            got = run_gpu(g, frames, work, 6)
+            assert np.array_equal(want, got), (lim, first_diff(g, want, got))
+    finally:
+        T.lib().ocg_set_lf_tma(0)
 
 
 def test_1080p_frame():

@@ -142,6 +142,7 @@ _PROTOS = {
                                     C.c_void_p]),
     "ocg_set_stage_mask": (None, [C.c_int]),
     "ocg_launch_count": (C.c_long, []),
+    "ocg_set_lf_tma": (None, [C.c_int]),
     "ocg_profile_enable": (None, [C.c_int]),
     "ocg_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "ocg_enc_metrics_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

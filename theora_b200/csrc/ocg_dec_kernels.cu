@@ -635,6 +635,127 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   else lf_cell<false>(o, ystride, bv, inl, inr, ind, inu, vd, vu, hl, hr, B, Cc, D);
 }
 
+/* ---- TMA variant ----------------------------------------------------------
+   The cells of one cell row are self-contained 8x8 pixel squares, so the input
+   of a CTA's 64 cells is one tile of the padded plane: thread 0 fetches it with
+   a single cp.async.bulk.tensor.2d (TMA) into shared memory, completion is
+   signalled on an mbarrier, and every thread reads its cell out of shared
+   memory -- no per-thread address arithmetic or predicated global loads, and
+   plane edges need no special casing because the tile lies inside the apron.
+   TMA requires the box to start on a 16-byte boundary in global memory
+   (measured: tools/micro/tma_test.cu faults otherwise) while cells start at
+   8cx-4, so the box is 528 bytes wide (12 bytes of lead-in + 64 cells + 4) and
+   boxes of neighbouring CTAs overlap by 16 bytes; for the same reason the
+   results are written back with per-thread 32-bit stores rather than a TMA
+   store (which would also write the overlap).  Tiles whose 64 cells touch no
+   coded fragment are skipped before the fetch. */
+#define OCG_LF_BOX_WORDS 132
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(64)
+ocg_lf_tma_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  __shared__ __align__(128) uint32_t tile[8][OCG_LF_BOX_WORDS]; /* [memory row][word] */
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(4) signed char bv[260];
+  const OcgJobDev &job = jobs[blockIdx.z];
+  const int lim = job.lf_limit;
+  if (lim == 0) return;
+  const int tid = (int)threadIdx.x;
+  const int crow = (int)blockIdx.y;
+  const int pli = crow >= g.p[2].cell_row0 ? 2 : (crow >= g.p[1].cell_row0 ? 1 : 0);
+  const OcgPlaneDev &P = g.p[pli];
+  const int cy = crow - P.cell_row0;
+  const int cx0 = (int)blockIdx.x * 64;
+  const int cx = cx0 + tid;
+  const int nh = P.nhfrags, nv = P.nvfrags;
+  if (cx0 > nh) return; /* whole CTA beyond this plane's last cell */
+  /* coded flags of the four fragments around the corner */
+  const uint8_t *cm = job.coded + P.froffset;
+  const bool inl = cx > 0 && cx <= nh, inr = cx < nh, ind = cy > 0, inu = cy < nv;
+  const bool A = inl && ind && cm[(cy - 1) * nh + cx - 1];
+  const bool B = inr && ind && cm[(cy - 1) * nh + cx];
+  const bool Cc = inl && inu && cm[cy * nh + cx - 1];
+  const bool D = inr && inu && cm[cy * nh + cx];
+  const bool vd = inl && inr && ind && (A || B);
+  const bool vu = inl && inr && inu && (Cc || D);
+  const bool hl = ind && inu && inl && (A || Cc);
+  const bool hr = ind && inu && inr && (B || D);
+  const bool active = vd || vu || hl || hr;
+  {
+    const uint32_t *src = (const uint32_t *)g_lf_table[lim];
+    uint32_t *dst = (uint32_t *)bv;
+    dst[tid] = src[tid];
+    if (tid == 0) {
+      dst[64] = src[64];
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  if (!__syncthreads_or(active)) return;
+  /* box origin in tensor coordinates (32-bit words / top-down memory rows): the
+     tensor starts 16 bytes left of the picture and vpad rows above it, so the
+     box starts at picture x = 8*cx0 - 16, a multiple of 16 bytes */
+  const int tx = 2 * cx0;
+  const int ty = P.vpad + P.height - 8 * cy - 4;
+  if (tid == 0) {
+    const CUtensorMap *tm = job.lf_tmaps + pli;
+    /* the tensor map lives in global memory (written by the host): acquire it
+       for the tensormap proxy before the TMA unit reads it */
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)),
+                 "r"((unsigned)(OCG_LF_BOX_WORDS * 4 * 8))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(&tile[0][0])),
+        "l"(tm), "r"(tx), "r"(ty), "r"(smem_u32(&mbar))
+        : "memory");
+  }
+  if (!active) return; /* idle cells need not wait for the tile */
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(&mbar)), "r"(0u)
+          : "memory");
+    }
+  }
+  Cell c;
+  /* cell row r (bottom-up) is memory row 7-r of the tile; the cell starts 12 bytes into the box */
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    c.w[r][0] = tile[7 - r][3 + 2 * tid];
+    c.w[r][1] = tile[7 - r][4 + 2 * tid];
+  }
+  if (vd) cell_vpair<0>(c, bv);
+  if (vu) cell_vpair<6>(c, bv);
+  if (hl) cell_hpair<0>(c, bv);
+  if (hr) cell_hpair<6>(c, bv);
+  if (vd && !B) cell_vpair<2>(c, bv);
+  if (hl && !Cc) cell_hpair<2>(c, bv);
+  if (vd && B) cell_vpair<2>(c, bv);
+  if (hr && !D) cell_hpair<4>(c, bv);
+  if (hl && Cc) cell_hpair<2>(c, bv);
+  if (vu && !D) cell_vpair<4>(c, bv);
+  if (vu && D) cell_vpair<4>(c, bv);
+  if (hr && D) cell_hpair<4>(c, bv);
+  /* write back the parts of the cell that lie inside the plane */
+  const int ystride = P.ystride;
+  uint8_t *o = job.base[OCG_FRAME_SELF] + P.plane_off + (cy * 8 - 4) * ystride + (cx * 8 - 4);
+  const int rlo = ind ? 0 : 4, rhi = inu ? 8 : 4;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (r >= rlo && r < rhi) {
+      uint32_t *row = (uint32_t *)(o + r * ystride);
+      if (inl) row[0] = c.w[r][0];
+      if (inr) row[1] = c.w[r][1];
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* Apron replication, state.c:770-835: every apron byte takes the nearest
    picture pixel (rows first, then full-width caps == clamp in both axes).
@@ -714,8 +835,14 @@ void ocg_init_device_tables(cudaStream_t st) {
   ocg_lf_table_kernel<<<128, 128, 0, st>>>();
 }
 
-void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, bool use_tma, cudaStream_t st) {
   if (njobs <= 0) return;
+  if (use_tma) {
+    dim3 grid((unsigned)((g.max_cells_x + 63) / 64), (unsigned)g.cell_rows, (unsigned)njobs);
+    ocg_lf_tma_kernel<<<grid, 64, 0, st>>>(g, jobs);
+    ocg_count_launch(1);
+    return;
+  }
   dim3 grid((unsigned)((g.max_cells_x + 63) / 64), (unsigned)((g.cell_rows + OCG_LF_ROWS - 1) / OCG_LF_ROWS),
             (unsigned)njobs);
   ocg_lf_kernel<<<grid, dim3(64, OCG_LF_ROWS), 0, st>>>(g, jobs);

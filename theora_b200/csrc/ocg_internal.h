@@ -2,6 +2,7 @@
  * kernel translation units.  Not installed. */
 #ifndef OCG_INTERNAL_H
 #define OCG_INTERNAL_H
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/theora_b200.h"
@@ -34,6 +35,7 @@ struct OcgJobDev {
   int32_t            *xcount;    /* [0] list length; 0 between frames (cleared by the border kernel) */
   int32_t             lf_limit;
   uint16_t            dcq[3][2];
+  const CUtensorMap  *lf_tmaps;  /* 3 tensor maps (one per plane) of the SELF buffer, or NULL: no TMA path */
 };
 
 #define OCG_FRAGS_PER_BLOCK 64
@@ -42,7 +44,7 @@ struct OcgJobDev {
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_xlist_reset(const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
-void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
+void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, bool use_tma, cudaStream_t st);
 void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 
 void ocg_init_device_tables(cudaStream_t st); /* idempotent; call once per context */
