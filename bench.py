@@ -238,7 +238,27 @@ def bench_encode_kernels(torch, dev, peak, nframes=16):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything that is not the final JSON line goes to stderr, including text native
+    libraries write straight to fd 1 (NCCL's version banner)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -291,7 +311,7 @@ def main():
                                  "sample": "%d streams x %d frames, th_decode_packetin, x86 SIMD build" % (ncores, args.frames)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -462,7 +482,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
                 "gpu_launches": int(launches),
                 "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if WORLD > 1:
         dist.destroy_process_group()
     return 0
