@@ -147,7 +147,7 @@ def time_reference(blob, threads, passes):
     return threads * passes * nframes / secs, secs, kind, int(hsh.value)
 
 
-def bench_encode_kernels(torch, dev, peak, nframes=16):
+def bench_encode_kernels(torch, dev, peak, nframes=40):
     """Throughput + algorithmic-bytes roofline of the encoder batch kernels on 1080p luma
     (BASELINE configs[2]/[3] block work; informational, the headline is decode)."""
     import theora_b200 as T
@@ -234,7 +234,8 @@ def bench_encode_kernels(torch, dev, peak, nframes=16):
                            "frames_per_s_one_ref": nframes / (ms * 1e-3),
                            "found_planted_vector": float(np.mean((res["best_vec"][:, 0] == 3) &
                                                                  (np.abs(res["best_vec"][:, 1]) == 1)))}
-    out["config"] = "1920x1088 luma, %d frames per launch, inter residual vs (3,1)-displaced reference" % nframes
+    out["config"] = ("1920x1088 luma, %d frames per launch (source + reference = %.0f MB, larger than the 126 MB L2), "
+                     "inter residual vs (3,1)-displaced reference" % (nframes, 2 * nframes * fsz / 1e6))
     return out
 
 

@@ -2,9 +2,9 @@
  *
  *  ocg_enc_metrics_kernel     SAD / SAD2, SATD / SATD2, intra SATD, SSD and
  *                             intra SAD of 8x8 blocks (encfrag.c:42-366), one
- *                             block per 8-lane warp slice (lane = pixel row),
- *                             VABSDIFF4 for the SADs, shuffle butterflies for
- *                             the column Hadamard and the reductions.
+ *                             lane per block: VABSDIFF4 for the SADs, IDP.4A
+ *                             for the SSD, a register-resident 8x8 Hadamard
+ *                             for the SATDs.
  *  ocg_enc_fdct_quant_kernel  frag_sub / sub_128 / copy2+sub (encfrag.c:21-40,
  *                             368) -> oc_enc_fdct8x8 (fdct.c:128) ->
  *                             oc_enc_quantize (enquant.c:220), zig-zag order
@@ -74,69 +74,131 @@ __device__ __forceinline__ int group_sum8(int v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256)
-ocg_enc_metrics_kernel(int metric, const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base,
-                       int ystride, const ocg_enc_frag *__restrict__ frags, int n, uint32_t *__restrict__ out_val,
+/* ---- block metrics: ONE LANE PER 8x8 BLOCK --------------------------------
+   A lane loads its block's descriptor, then all 8 source rows and all 8
+   (motion-displaced, possibly two-tap) predictor rows -- up to 40 independent
+   64-bit loads in flight -- and reduces in registers: no shuffles, no shared
+   memory.  Lists in raster order make the row accesses of a warp contiguous.
+   (The first version used 8 lanes per block with shuffle butterflies: 2-3x
+   more instructions per block.) */
+struct Rows8 { uint2 r[8]; };
+
+__device__ __forceinline__ void load_rows8(const uint8_t *p, int ystride, Rows8 &o) {
+  const uintptr_t a = (uintptr_t)p;
+  const unsigned sh = (unsigned)(a & 7);
+  const uint8_t *base = (const uint8_t *)(a & ~(uintptr_t)7);
+  if (sh == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.r[i] = __ldg((const uint2 *)(base + i * ystride));
+    return;
+  }
+  const unsigned sel = 0x3210u + 0x1111u * (sh & 3);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint2 w0 = __ldg((const uint2 *)(base + i * ystride));
+    const uint2 w1 = __ldg((const uint2 *)(base + i * ystride) + 1);
+    if (sh < 4) {
+      o.r[i].x = __byte_perm(w0.x, w0.y, sel);
+      o.r[i].y = __byte_perm(w0.y, w1.x, sel);
+    } else {
+      o.r[i].x = __byte_perm(w0.y, w1.x, sel);
+      o.r[i].y = __byte_perm(w1.x, w1.y, sel);
+    }
+  }
+}
+
+/* predictor rows: zeros (intra), one tap, or (a+b)>>1 of two taps (encfrag.c:71-84) */
+__device__ __forceinline__ void load_pred8(const uint8_t *ref_base, const ocg_enc_frag &f, int ystride, Rows8 &p) {
+  if (f.ref_off0 == INT_MIN) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) p.r[i] = make_uint2(0, 0);
+    return;
+  }
+  load_rows8(ref_base + f.ref_off0, ystride, p);
+  if (f.ref_off1 != INT_MIN) {
+    Rows8 t;
+    load_rows8(ref_base + f.ref_off1, ystride, t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      p.r[i].x = __vhaddu4(p.r[i].x, t.r[i].x);
+      p.r[i].y = __vhaddu4(p.r[i].y, t.r[i].y);
+    }
+  }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base, int ystride,
+                       const ocg_enc_frag *__restrict__ frags, int n, uint32_t *__restrict__ out_val,
                        int32_t *__restrict__ out_dc) {
-  const int fi_raw = (int)(blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3));
-  const bool live = fi_raw < n;
-  const int fi = live ? fi_raw : n - 1;
-  const int lane = threadIdx.x & 31;
-  const int row = lane & 7;
+  const int fi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (fi >= n) return;
   const int4 fw = __ldg((const int4 *)(frags + fi));
   ocg_enc_frag f;
   f.src_off = fw.x; f.ref_off0 = fw.y; f.ref_off1 = fw.z; f.aux = fw.w;
-  const uint2 s = ld8u(src_base + f.src_off + row * ystride);
-  uint2 p;
+  Rows8 s, p;
+  load_rows8(src_base + f.src_off, ystride, s);
   uint32_t val = 0;
   int dc = 0;
-  if (metric == OCG_MET_SAD) {
-    load_pred_row(ref_base, f, row, ystride, p);
-    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, p.x) + __vsadu4(s.y, p.y)));
-  } else if (metric == OCG_MET_SSD) {
-    load_pred_row(ref_base, f, row, ystride, p);
-    int a[8], b[8], acc = 0;
-    unpack8(s, a);
-    unpack8(p, b);
+  if (METRIC == OCG_MET_SAD) {
+    load_pred8(ref_base, f, ystride, p);
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc += (a[i] - b[i]) * (a[i] - b[i]);
-    val = (uint32_t)group_sum8(acc);
-  } else if (metric == OCG_MET_INTRA_SAD) {
+    for (int i = 0; i < 8; i++) val += __vsadu4(s.r[i].x, p.r[i].x) + __vsadu4(s.r[i].y, p.r[i].y);
+  } else if (METRIC == OCG_MET_SSD) {
+    /* sum (a-b)^2 = sum a^2 + sum b^2 - 2 sum ab, four pixels per IDP.4A;
+       oc_enc_frag_ssd has no two-tap form (encfrag.c:338) */
+    f.ref_off1 = INT_MIN;
+    load_pred8(ref_base, f, ystride, p);
+    unsigned aa = 0, bb = 0, ab = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      aa = __dp4a(s.r[i].x, s.r[i].x, aa); aa = __dp4a(s.r[i].y, s.r[i].y, aa);
+      bb = __dp4a(p.r[i].x, p.r[i].x, bb); bb = __dp4a(p.r[i].y, p.r[i].y, bb);
+      ab = __dp4a(s.r[i].x, p.r[i].x, ab); ab = __dp4a(s.r[i].y, p.r[i].y, ab);
+    }
+    val = aa + bb - 2u * ab;
+  } else if (METRIC == OCG_MET_INTRA_SAD) {
     /* encfrag.c:88-107: dc=(sum+32)>>6, then sum |src-dc| */
-    const int tot = group_sum8((int)(__vsadu4(s.x, 0) + __vsadu4(s.y, 0)));
-    const uint32_t m = 0x01010101u * (uint32_t)((tot + 32) >> 6);
-    val = (uint32_t)group_sum8((int)(__vsadu4(s.x, m) + __vsadu4(s.y, m)));
+    unsigned tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tot += __vsadu4(s.r[i].x, 0) + __vsadu4(s.r[i].y, 0);
+    const uint32_t m = 0x01010101u * ((tot + 32) >> 6);
+#pragma unroll
+    for (int i = 0; i < 8; i++) val += __vsadu4(s.r[i].x, m) + __vsadu4(s.r[i].y, m);
   } else {
     /* SATD family, encfrag.c:109-336: 2-D Hadamard of the residual, sum of
        magnitudes without the DC term, DC returned separately. */
-    if (metric == OCG_MET_INTRA_SATD) p = make_uint2(0, 0);
-    else load_pred_row(ref_base, f, row, ystride, p);
-    int a[8], b[8];
-    unpack8(s, a);
-    unpack8(p, b);
+    if (METRIC == OCG_MET_INTRA_SATD) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) a[i] -= b[i];
-    hadamard8(a);
-    /* column transform across the 8 lanes of the slice */
+      for (int i = 0; i < 8; i++) p.r[i] = make_uint2(0, 0);
+    } else load_pred8(ref_base, f, ystride, p);
+    int h[8][8];
 #pragma unroll
-    for (int d = 4; d >= 1; d >>= 1) {
-      const bool up = (row & d) != 0;
+    for (int i = 0; i < 8; i++) {
+      int a[8], b[8];
+      unpack8(s.r[i], a);
+      unpack8(p.r[i], b);
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int o = __shfl_xor_sync(0xFFFFFFFFu, a[i], d);
-        a[i] = up ? o - a[i] : a[i] + o;
-      }
+      for (int k = 0; k < 8; k++) a[k] -= b[k];
+      hadamard8(a);
+#pragma unroll
+      for (int k = 0; k < 8; k++) h[i][k] = a[k];
     }
     int acc = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc += abs(a[i]);
-    if (row == 0) { dc = a[0]; acc -= abs(a[0]); }
-    val = (uint32_t)group_sum8(acc);
+    for (int k = 0; k < 8; k++) {
+      int t[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) t[i] = h[i][k];
+      hadamard8(t);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc += abs(t[i]);
+      if (k == 0) { dc = t[0]; acc -= abs(t[0]); }
+    }
+    val = (uint32_t)acc;
   }
-  if (row == 0 && live) {
-    out_val[fi] = val;
-    if (out_dc != nullptr) out_dc[fi] = dc;
-  }
+  out_val[fi] = val;
+  if (out_dc != nullptr) out_dc[fi] = dc;
 }
 
 /* fdct.c:28-120 */
@@ -477,8 +539,15 @@ OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uin
   if (src_base == nullptr || frags == nullptr || out_val == nullptr) return OCG_EFAULT;
   if (metric < OCG_MET_SAD || metric > OCG_MET_INTRA_SAD || n < 0) return OCG_EINVAL;
   if (n == 0) return OCG_OK;
-  ocg_enc_metrics_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
-      metric, src_base, ref_base, ystride, frags, n, out_val, out_dc);
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (metric) {
+    case OCG_MET_SAD: ocg_enc_metrics_kernel<OCG_MET_SAD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+    case OCG_MET_SATD: ocg_enc_metrics_kernel<OCG_MET_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+    case OCG_MET_INTRA_SATD: ocg_enc_metrics_kernel<OCG_MET_INTRA_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+    case OCG_MET_SSD: ocg_enc_metrics_kernel<OCG_MET_SSD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+    default: ocg_enc_metrics_kernel<OCG_MET_INTRA_SAD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+  }
   ocg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
 }
