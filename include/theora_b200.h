@@ -256,6 +256,34 @@ OCG_API int ocg_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_f
                                    const ocg_mb_search_in *in, ocg_mb_search_out *out, int n,
                                    void *stream);
 
+/* Intra-frame analysis pre-pass (BASELINE config "intra-only encode").  The
+   per-block encoder hooks return their result synchronously to serial host
+   code (encint.h:292-325), so they cannot launch kernels; but in an INTRA frame
+   every value they return depends on the input frame and the frame's quantiser
+   tables only.  This call, made once per frame from the enquant_table_fixup
+   hook (analyze.c:564, the first hook after the input frame is in place),
+   uploads the padded input frame (OC_FRAME_IO) into pool buffer io_buf and
+   computes, for EVERY fragment of the frame,
+     oc_enc_frag_intra_satd                       (encfrag.c:322)
+     oc_enc_frag_sub_128 + oc_enc_fdct8x8         (encfrag.c:33, fdct.c:128)
+     oc_enc_quantize for each of the nqis quantisers of the frame (enquant.c:220)
+   into pinned host tables owned by the context; the hooks then only look their
+   answers up.  dequant/enquant use the layout of ocg_enc_fdct_quant_batch
+   ([3 pli][2 qti][3 qii][64]); only qti 0 is read.  Synchronous: returns when
+   the tables are complete. */
+typedef struct ocg_enc_intra_tables {
+  const uint32_t *satd;     /* [nfrags]           oc_enc_frag_intra_satd return value   */
+  const int32_t  *satd_dc;  /* [nfrags]           its *_dc output                       */
+  const int16_t  *dct;      /* [nfrags][64]       oc_enc_fdct8x8 output (zig-zag order) */
+  const int16_t  *qdct;     /* [nqis][nfrags][64] oc_enc_quantize output                */
+  const int32_t  *nonzero;  /* [nqis][nfrags]     its return value                      */
+} ocg_enc_intra_tables;
+/* Allocates the pre-pass buffers now instead of on the first frame. */
+OCG_API int ocg_enc_intra_reserve(ocg_ctx *ctx);
+OCG_API int ocg_enc_intra_prepass(ocg_ctx *ctx, int io_buf, const uint8_t *host_frame,
+                                  const uint16_t *dequant, const int16_t *enquant, int nqis,
+                                  ocg_enc_intra_tables *out);
+
 #ifdef __cplusplus
 }
 #endif

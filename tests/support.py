@@ -95,6 +95,10 @@ def oracle():
 def _bind_harness(L):
     L.refh_encode_synth.restype = C.c_void_p
     L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
+    L.refh_encode_synth_recon.restype = C.c_void_p
+    L.refh_encode_synth_recon.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_void_p]
+    L.refh_encode_time_mt.restype = C.c_double
+    L.refh_encode_time_mt.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_long)]
     L.refh_stream_free.argtypes = [C.c_void_p]
     L.refh_stream_npackets.argtypes = [C.c_void_p]
     L.refh_stream_packet_size.argtypes = [C.c_void_p, C.c_int]

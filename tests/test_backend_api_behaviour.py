@@ -124,3 +124,28 @@ def test_stripe_callback_gets_the_whole_final_frame_once_per_frame():
         assert h == int(want[i][0]), i  # the luma handed to the callback is the final frame
     L.refh_dec_close(d)
     L.refh_stream_free(sh)
+
+
+def test_intra_only_encoder_alloc_fails_without_a_device():
+    """keyframe_granule_shift == 0 selects the device encoder: no device, no encoder."""
+    if abi.lib().ocg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    L = streams.lib()
+    assert not L.refh_encode_synth(64, 64, 0, 2, 48, 1, 1, 30, 12345)
+
+
+def test_host_mode_encoder_matches_the_reference_bitstream():
+    """Tooling mode (OCG_ENC_HOST): the integrated build's encoder is the reference's."""
+    if not S.ref_available("c"):
+        pytest.skip("needs oracle/_ref")
+    L = streams.lib()
+    R = S.ref("c")
+    L.ocg_backend_set_enc_mode(streams.ENC_HOST)
+    try:
+        got = S.Stream.encode(L, 64, 64, 3, quality=32, kf=1, speed=1, noise_shift=28)
+    finally:
+        L.ocg_backend_set_enc_mode(streams.ENC_AUTO)
+    want = S.Stream.encode(R, 64, 64, 3, quality=32, kf=1, speed=1, noise_shift=28)
+    assert got.to_bytes() == want.to_bytes()
+    got.free()
+    want.free()

@@ -151,7 +151,18 @@ _PROTOS = {
                                          C.c_void_p]),
     "ocg_enc_fdct_quant_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocg_enc_intra_reserve": (C.c_int, [C.c_void_p]),
+    "ocg_enc_intra_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p]),
 }
+
+
+
+class EncIntraTables(C.Structure):
+    """ocg_enc_intra_tables (include/theora_b200.h): pinned host result tables."""
+    _fields_ = [("satd", C.c_void_p), ("satd_dc", C.c_void_p), ("dct", C.c_void_p), ("qdct", C.c_void_p),
+                ("nonzero", C.c_void_p)]
+
 
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOS))
 

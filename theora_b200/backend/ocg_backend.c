@@ -252,12 +252,8 @@ void oc_state_accel_init_ocg(oc_theora_state *_state) {
   oc_state_accel_init_c(_state);
 }
 
-void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
-  /* encoder table: the reference's C kernels.  The batched GPU encoder kernels
-     (ocg_enc_*_batch) are reached through the C ABI by a restructured caller,
-     not through these synchronous per-block hooks. */
-  oc_enc_accel_init_c(_enc);
-}
+/* oc_enc_accel_init_ocg lives in ocg_enc_backend.c */
+int ocg_backend_device_(void) { return g_device; }
 
 static void backend_destroy(ocg_backend *b) {
   ocg_backend **pp;

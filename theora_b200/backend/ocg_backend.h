@@ -33,6 +33,35 @@ typedef struct ocg_backend_stats {
 } ocg_backend_stats;
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset);
 
+/* ---- encoder ---------------------------------------------------------------
+   OCG_ENC_AUTO: an intra-only encoder (th_info.keyframe_granule_shift == 0, so
+   every frame is a key frame) runs its block pipeline on the device: one batched
+   pre-pass per frame (intra SATD, sub_128 + fDCT, quantiser) served to the
+   per-block hooks as look-ups, and the reconstruction (iDCT + recon + loop
+   filter + borders) recorded and flushed like a decoded frame.  th_encode_alloc
+   returns NULL when no device is usable.  Encoders that can emit inter frames
+   keep the reference's C kernels (their hooks need a restructured caller).
+   OCG_ENC_HOST: every encoder keeps the reference's C kernels -- tooling mode
+   for producing test streams on machines without a GPU. */
+#define OCG_ENC_AUTO 0
+#define OCG_ENC_HOST 1
+OCG_API void ocg_backend_set_enc_mode(int mode);  /* applies to encoders allocated afterwards */
+
+typedef struct ocg_enc_backend_stats {
+  long   frames;            /* frames reconstructed on the device            */
+  long   prepass_frames;    /* analysis passes (>= frames: dry runs, recodes) */
+  long   coeff_rows;
+  long   h2d_bytes;
+  long   d2h_bytes;
+  double prepass_seconds;   /* host wall time inside the pre-pass call        */
+  double flush_seconds;     /* host wall time inside the reconstruction flush */
+} ocg_enc_backend_stats;
+OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset);
+/* Test accessor: copies the encoder's current reconstruction (three top-down
+   planes, frame_width x frame_height, packed); returns the byte count. */
+struct th_enc_ctx;
+OCG_API long ocg_backend_enc_copy_recon(struct th_enc_ctx *enc, unsigned char *dst);
+
 #ifdef __cplusplus
 }
 #endif

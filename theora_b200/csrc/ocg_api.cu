@@ -40,7 +40,19 @@ struct Slot {
 
 } /* namespace */
 
+/* buffers of the intra-frame encoder pre-pass (allocated on first use) */
+struct EncPre {
+  ocg_enc_frag *d_frags = nullptr; /* [3 qii][nfrags] */
+  uint16_t *d_dequant = nullptr;   /* [3][2][3][64] */
+  int16_t *d_enquant = nullptr;    /* [3][2][3][64][2] */
+  uint8_t *d_out = nullptr;        /* one device block mirrored by h_out */
+  uint8_t *h_out = nullptr;        /* pinned */
+  uint8_t *h_tabs = nullptr;       /* pinned staging for the two quantiser tables */
+  size_t off_satd = 0, off_dc = 0, off_dct = 0, off_qdct = 0, off_nz = 0, out_sz = 0;
+};
+
 struct ocg_ctx {
+  EncPre *enc = nullptr;
   ocg_geometry geom;
   OcgGeomDev gdev;
   int device = 0;
@@ -310,6 +322,15 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
     if (s.job) cudaFreeHost(s.job);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
+  if (c->enc != nullptr) {
+    cudaFree(c->enc->d_frags);
+    cudaFree(c->enc->d_dequant);
+    cudaFree(c->enc->d_enquant);
+    cudaFree(c->enc->d_out);
+    if (c->enc->h_out) cudaFreeHost(c->enc->h_out);
+    if (c->enc->h_tabs) cudaFreeHost(c->enc->h_tabs);
+    delete c->enc;
+  }
   cudaFree(c->frames);
   cudaFree(c->d_recs);
   cudaFree(c->d_rows);
@@ -499,6 +520,106 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
     CU(cudaMemcpyAsync(host_out, c->frames + (size_t)f->ref_idx[OCG_FRAME_SELF] * c->geom.ref_frame_sz,
                        (size_t)c->geom.ref_frame_sz, cudaMemcpyDeviceToHost, st));
   }
+  return OCG_OK;
+}
+
+/* ---- intra-frame encoder pre-pass ---------------------------------------- */
+static constexpr size_t kQTabU16 = 3 * 2 * 3 * 64;       /* dequant entries */
+static constexpr size_t kQTabI16 = 3 * 2 * 3 * 64 * 2;   /* enquant {m,l} entries */
+
+static int enc_pre_init(ocg_ctx *c) {
+  EncPre *e = new (std::nothrow) EncPre();
+  if (e == nullptr) return fail(OCG_ENOMEM, "out of memory");
+  c->enc = e; /* owned by the context from here on (freed in ocg_ctx_destroy) */
+  const size_t nf = (size_t)c->geom.nfrags;
+  size_t o = 0;
+  e->off_satd = o; o += nf * 4;
+  e->off_dc = o; o += nf * 4;
+  e->off_nz = o; o += 3 * nf * 4;
+  o = (o + 255) & ~(size_t)255;
+  e->off_dct = o; o += nf * 128;
+  e->off_qdct = o; o += 3 * nf * 128;
+  e->out_sz = o;
+  CU(cudaMalloc(&e->d_frags, 3 * nf * sizeof(ocg_enc_frag)));
+  CU(cudaMalloc(&e->d_dequant, kQTabU16 * 2));
+  CU(cudaMalloc(&e->d_enquant, kQTabI16 * 2));
+  CU(cudaMalloc(&e->d_out, e->out_sz));
+  CU(cudaHostAlloc(&e->h_out, e->out_sz, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_tabs, kQTabU16 * 2 + kQTabI16 * 2, cudaHostAllocDefault));
+  /* the block lists never change: every fragment, intra (no predictor), one copy per qii */
+  std::vector<ocg_enc_frag> fl(3 * nf);
+  for (int qii = 0; qii < 3; qii++)
+    for (size_t i = 0; i < nf; i++) {
+      ocg_enc_frag &f = fl[(size_t)qii * nf + i];
+      f.src_off = c->tmpl[i].buf_off;
+      f.ref_off0 = INT32_MIN;
+      f.ref_off1 = INT32_MIN;
+      f.aux = (c->tmpl[i].pli_qti & 3) | (qii << 3);
+    }
+  CU(cudaMemcpyAsync(e->d_frags, fl.data(), fl.size() * sizeof(ocg_enc_frag), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return OCG_OK;
+}
+
+OCG_API int ocg_enc_intra_reserve(ocg_ctx *c) {
+  if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
+  CU(cudaSetDevice(c->device));
+  return c->enc != nullptr ? OCG_OK : enc_pre_init(c);
+}
+
+OCG_API int ocg_enc_intra_prepass(ocg_ctx *c, int io_buf, const uint8_t *host_frame, const uint16_t *dequant,
+                                  const int16_t *enquant, int nqis, ocg_enc_intra_tables *out) {
+  if (c == nullptr || host_frame == nullptr || dequant == nullptr || enquant == nullptr || out == nullptr)
+    return fail(OCG_EFAULT, "NULL argument");
+  if (io_buf < 0 || io_buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
+  if (nqis < 1 || nqis > 3) return fail(OCG_EINVAL, "nqis must be 1..3");
+  CU(cudaSetDevice(c->device));
+  if (c->enc == nullptr) {
+    int r = enc_pre_init(c);
+    if (r < 0) return r;
+  }
+  EncPre *e = c->enc;
+  cudaStream_t st = c->stream;
+  const size_t nf = (size_t)c->geom.nfrags;
+  const int nluma = c->geom.planes[0].nfrags;
+  const int nchroma = c->geom.nfrags - nluma;
+  uint8_t *frame = c->frames + (size_t)io_buf * c->geom.ref_frame_sz;
+  const uint8_t *base = frame + c->geom.base_off;
+  CU(cudaMemcpyAsync(frame, host_frame, (size_t)c->geom.ref_frame_sz, cudaMemcpyHostToDevice, st));
+  memcpy(e->h_tabs, dequant, kQTabU16 * 2);
+  memcpy(e->h_tabs + kQTabU16 * 2, enquant, kQTabI16 * 2);
+  CU(cudaMemcpyAsync(e->d_dequant, e->h_tabs, kQTabU16 * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(e->d_enquant, e->h_tabs + kQTabU16 * 2, kQTabI16 * 2, cudaMemcpyHostToDevice, st));
+  uint32_t *d_satd = (uint32_t *)(e->d_out + e->off_satd);
+  int32_t *d_dc = (int32_t *)(e->d_out + e->off_dc);
+  int32_t *d_nz = (int32_t *)(e->d_out + e->off_nz);
+  int16_t *d_dct = (int16_t *)(e->d_out + e->off_dct);
+  int16_t *d_qdct = (int16_t *)(e->d_out + e->off_qdct);
+  /* luma and chroma differ in stride: one launch each */
+  const int ys[2] = {c->geom.planes[0].ystride, c->geom.planes[1].ystride};
+  const int first[2] = {0, nluma}, count[2] = {nluma, nchroma};
+  int r;
+  for (int k = 0; k < 2; k++) {
+    r = ocg_enc_metrics_batch(OCG_MET_INTRA_SATD, base, nullptr, ys[k], e->d_frags + first[k], count[k],
+                              d_satd + first[k], d_dc + first[k], st);
+    if (r < 0) return fail(r, "intra SATD launch failed");
+    for (int qii = 0; qii < nqis; qii++) {
+      const size_t at = (size_t)qii * nf + (size_t)first[k];
+      /* the transform does not depend on qii: qii > 0 rewrites the same dct rows */
+      r = ocg_enc_fdct_quant_batch(base, nullptr, ys[k], e->d_frags + at, count[k], e->d_dequant, e->d_enquant,
+                                   d_dct + (size_t)first[k] * 64, d_qdct + at * 64, d_nz + at, st);
+      if (r < 0) return fail(r, "fDCT/quantiser launch failed");
+    }
+  }
+  /* one D2H for the small tables + dct, one for the nqis quantised planes */
+  CU(cudaMemcpyAsync(e->h_out, e->d_out, e->off_dct + nf * 128, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(e->h_out + e->off_qdct, e->d_out + e->off_qdct, (size_t)nqis * nf * 128, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  out->satd = (const uint32_t *)(e->h_out + e->off_satd);
+  out->satd_dc = (const int32_t *)(e->h_out + e->off_dc);
+  out->dct = (const int16_t *)(e->h_out + e->off_dct);
+  out->qdct = (const int16_t *)(e->h_out + e->off_qdct);
+  out->nonzero = (const int32_t *)(e->h_out + e->off_nz);
   return OCG_OK;
 }
 

@@ -26,6 +26,15 @@ class BackendStats(C.Structure):
                 ("flush_seconds", C.c_double)]
 
 
+class EncBackendStats(C.Structure):
+    """ocg_enc_backend_stats (theora_b200/backend/ocg_backend.h)."""
+    _fields_ = [("frames", C.c_long), ("prepass_frames", C.c_long), ("coeff_rows", C.c_long),
+                ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long), ("prepass_seconds", C.c_double),
+                ("flush_seconds", C.c_double)]
+
+
+ENC_AUTO, ENC_HOST = 0, 1
+
 _lib = None
 
 
@@ -46,6 +55,8 @@ def lib():
         L.ocg_backend_set_device.argtypes = [C.c_int]
         L.ocg_backend_set_capture.argtypes = [CAPTURE_FN, C.c_void_p]
         L.ocg_backend_get_stats.argtypes = [C.POINTER(BackendStats), C.c_int]
+        L.ocg_backend_set_enc_mode.argtypes = [C.c_int]
+        L.ocg_backend_get_enc_stats.argtypes = [C.POINTER(EncBackendStats), C.c_int]
         _bind_harness(L)
         _lib = L
     return _lib
@@ -54,6 +65,10 @@ def lib():
 def _bind_harness(L):
     L.refh_encode_synth.restype = C.c_void_p
     L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
+    L.refh_encode_synth_recon.restype = C.c_void_p
+    L.refh_encode_synth_recon.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_void_p]
+    L.refh_encode_time_mt.restype = C.c_double
+    L.refh_encode_time_mt.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_long)]
     L.refh_stream_free.argtypes = [C.c_void_p]
     L.refh_stream_npackets.argtypes = [C.c_void_p]
     L.refh_stream_packet_size.argtypes = [C.c_void_p, C.c_int]

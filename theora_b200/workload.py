@@ -39,8 +39,16 @@ def synth_stream(w=1920, h=1080, nframes=300, quality=32, kf=64, speed=1, noise_
         assert hnd, "encoder failed"
         return hnd
 
-    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
-        handles = list(ex.map(enc, segs))
+    # stream synthesis is tooling: keep the reference's host encoder even for
+    # intra-only streams (the device encoder is what tests/bench measure)
+    if hasattr(L, "ocg_backend_set_enc_mode"):
+        L.ocg_backend_set_enc_mode(streams.ENC_HOST)
+    try:
+        with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+            handles = list(ex.map(enc, segs))
+    finally:
+        if hasattr(L, "ocg_backend_set_enc_mode"):
+            L.ocg_backend_set_enc_mode(streams.ENC_AUTO)
     first = handles[0]
     for hnd in handles[1:]:
         L.refh_stream_append_data(first, hnd)

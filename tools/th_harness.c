@@ -147,8 +147,21 @@ REFH_API void refh_synth_frame(int w, int h, int f, int noise_shift, unsigned se
    w x h (4:2:0).  The coded frame is padded to a multiple of 16 and the picture
    centred the way encoder_example.c:1558-1563 does.  Returns 3 header packets
    followed by nframes data packets. */
+/* only the integrated build (theora_b200/backend) defines this accessor */
+extern long ocg_backend_enc_copy_recon(th_enc_ctx *enc, unsigned char *dst) __attribute__((weak));
+
+REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes, int quality, int kf_interval,
+                                              int speed, int noise_shift, unsigned seed, unsigned char *recon_out);
+
 REFH_API refh_stream *refh_encode_synth(int w, int h, int f0, int nframes, int quality,
                                         int kf_interval, int speed, int noise_shift, unsigned seed) {
+  return refh_encode_synth_recon(w, h, f0, nframes, quality, kf_interval, speed, noise_shift, seed, NULL);
+}
+
+/* As refh_encode_synth; recon_out (optional, integrated build only) receives
+   the encoder's reconstruction of the LAST frame. */
+REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes, int quality, int kf_interval,
+                                              int speed, int noise_shift, unsigned seed, unsigned char *recon_out) {
   th_info ti;
   th_enc_ctx *te;
   th_comment tc;
@@ -196,6 +209,7 @@ REFH_API refh_stream *refh_encode_synth(int w, int h, int f0, int nframes, int q
     if (ret < 0) break;
     while (th_encode_packetout(te, f + 1 >= nframes, &op) > 0) refh_stream_push(s, op.packet, op.bytes);
   }
+  if (recon_out != NULL && ocg_backend_enc_copy_recon != NULL) ocg_backend_enc_copy_recon(te, recon_out);
   free(buf);
   th_encode_free(te);
   th_info_clear(&ti);
@@ -427,5 +441,117 @@ REFH_API double refh_decode_time(const refh_stream *s, int nthreads, int passes,
   pthread_barrier_destroy(&bar);
   free(th);
   free(jobs);
+  return fail ? -1.0 : worst;
+}
+
+/* ---------------------------------------------------------------------- */
+/* Encode timing: `nthreads` independent encoders each encode the same
+   `nframes` pre-generated frames (frames in RAM, packets discarded after
+   hashing).  The first frame of every encoder is encoded before the clock
+   starts (the library codes frame 0 twice to prime its statistics, and device
+   contexts are created lazily), so the timed region is nframes-1 frames per
+   thread.  Returns wall seconds of the slowest thread; the FNV-1a hash of all
+   packet bytes of thread 0 goes to *hash_out. */
+typedef struct refh_enc_job {
+  pthread_barrier_t *bar;
+  const unsigned char *frames;
+  int w, h, nframes, quality, kf_interval, speed;
+  double secs;
+  uint64_t hash;
+  long bytes;
+  int fail;
+} refh_enc_job;
+
+static void *refh_encode_worker(void *arg) {
+  refh_enc_job *j = (refh_enc_job *)arg;
+  th_info ti;
+  th_enc_ctx *te;
+  th_comment tc;
+  th_ycbcr_buffer yuv;
+  ogg_packet op;
+  int w = j->w, h = j->h;
+  int fw = (w + 15) & ~15, fh = (h + 15) & ~15;
+  int cw = w >> 1, ch = h >> 1;
+  size_t fsz = (size_t)w * h + 2 * (size_t)cw * ch;
+  uint64_t hash = 1469598103934665603ULL;
+  ogg_uint32_t kf = (ogg_uint32_t)j->kf_interval;
+  double t0 = 0.0;
+  int f, started = 0;
+  th_info_init(&ti);
+  ti.frame_width = (ogg_uint32_t)fw; ti.frame_height = (ogg_uint32_t)fh;
+  ti.pic_width = (ogg_uint32_t)w; ti.pic_height = (ogg_uint32_t)h;
+  ti.pic_x = (ogg_uint32_t)(((fw - w) >> 1) & ~1); ti.pic_y = (ogg_uint32_t)(((fh - h) >> 1) & ~1);
+  ti.fps_numerator = 30; ti.fps_denominator = 1; ti.aspect_numerator = 1; ti.aspect_denominator = 1;
+  ti.colorspace = TH_CS_UNSPECIFIED; ti.pixel_fmt = TH_PF_420; ti.target_bitrate = 0; ti.quality = j->quality;
+  ti.keyframe_granule_shift = refh_ilog(j->kf_interval > 1 ? (unsigned)(j->kf_interval - 1) : 0);
+  te = th_encode_alloc(&ti);
+  if (te != NULL) {
+    th_encode_ctl(te, TH_ENCCTL_SET_KEYFRAME_FREQUENCY_FORCE, &kf, sizeof(kf));
+    if (j->speed >= 0) th_encode_ctl(te, TH_ENCCTL_SET_SPLEVEL, &j->speed, sizeof(j->speed));
+    th_comment_init(&tc);
+    while (th_encode_flushheader(te, &tc, &op) > 0) {}
+    th_comment_clear(&tc);
+  }
+  yuv[0].width = w; yuv[0].height = h; yuv[0].stride = w;
+  yuv[1].width = cw; yuv[1].height = ch; yuv[1].stride = cw;
+  yuv[2].width = cw; yuv[2].height = ch; yuv[2].stride = cw;
+  for (f = 0; f < j->nframes && te != NULL; f++) {
+    unsigned char *b = (unsigned char *)j->frames + fsz * (size_t)f;
+    long i;
+    if (f == 1) { pthread_barrier_wait(j->bar); started = 1; t0 = refh_now(); }
+    yuv[0].data = b; yuv[1].data = b + (size_t)w * h; yuv[2].data = yuv[1].data + (size_t)cw * ch;
+    if (th_encode_ycbcr_in(te, yuv) < 0) { j->fail = 1; break; }
+    while (th_encode_packetout(te, f + 1 >= j->nframes, &op) > 0) {
+      j->bytes += op.bytes;
+      for (i = 0; i < op.bytes; i++) hash = (hash ^ op.packet[i]) * 1099511628211ULL;
+    }
+  }
+  if (!started) { /* no encoder, fewer than two frames, or frame 0 failed */
+    j->fail = 1;
+    pthread_barrier_wait(j->bar);
+    t0 = refh_now();
+  }
+  j->secs = refh_now() - t0;
+  j->hash = hash;
+  pthread_barrier_wait(j->bar);
+  if (te != NULL) th_encode_free(te);
+  th_info_clear(&ti);
+  return NULL;
+}
+
+REFH_API double refh_encode_time_mt(int w, int h, int nframes, int quality, int kf_interval, int speed,
+                                    int noise_shift, unsigned seed, int nthreads, uint64_t *hash_out,
+                                    long *bytes_out) {
+  pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+  refh_enc_job *jobs = (refh_enc_job *)calloc((size_t)nthreads, sizeof(refh_enc_job));
+  pthread_barrier_t bar;
+  int cw = w >> 1, ch = h >> 1;
+  size_t fsz = (size_t)w * h + 2 * (size_t)cw * ch;
+  unsigned char *buf = (unsigned char *)malloc(fsz * (size_t)nframes);
+  double worst = 0.0;
+  int i, f, fail = 0;
+  for (f = 0; f < nframes; f++) {
+    unsigned char *b = buf + fsz * (size_t)f;
+    refh_synth_frame(w, h, f, noise_shift, seed, b, b + (size_t)w * h, b + (size_t)w * h + (size_t)cw * ch);
+  }
+  pthread_barrier_init(&bar, NULL, (unsigned)nthreads);
+  for (i = 0; i < nthreads; i++) {
+    jobs[i].bar = &bar;
+    jobs[i].frames = buf;
+    jobs[i].w = w; jobs[i].h = h; jobs[i].nframes = nframes;
+    jobs[i].quality = quality; jobs[i].kf_interval = kf_interval; jobs[i].speed = speed;
+    pthread_create(&th[i], NULL, refh_encode_worker, &jobs[i]);
+  }
+  for (i = 0; i < nthreads; i++) {
+    pthread_join(th[i], NULL);
+    if (jobs[i].secs > worst) worst = jobs[i].secs;
+    fail |= jobs[i].fail;
+  }
+  if (hash_out) *hash_out = jobs[0].hash;
+  if (bytes_out) *bytes_out = jobs[0].bytes;
+  pthread_barrier_destroy(&bar);
+  free(th);
+  free(jobs);
+  free(buf);
   return fail ? -1.0 : worst;
 }
