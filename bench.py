@@ -147,6 +147,45 @@ def time_reference(blob, threads, passes):
     return threads * passes * nframes / secs, secs, kind, int(hsh.value)
 
 
+def bench_encode_intra(Lo, threads, width, height, quality, frames=13):
+    """BASELINE configs[2]: intra-only encode through th_encode_ycbcr_in/packetout.
+    `threads` independent encoders (unmodified reference host code) on the B200
+    back-end -- device pre-pass look-ups + recorded reconstruction -- next to the
+    reference x86 SIMD build on the same threads and the same frames; the first
+    frame of every encoder is outside the timed region.  Packets must be
+    byte-identical (hash + size of thread 0's packets)."""
+    out = {"workload": "%dx%d 4:2:0 intra-only encode (keyframe every frame), q=%d, speed 1, %d timed frames x %d threads"
+           % (width, height, quality, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
+
+    def run(L):
+        best = None
+        for _ in range(3):
+            h, b = C.c_uint64(), C.c_long()
+            secs = L.refh_encode_time_mt(width, height, frames, quality, 1, 1, 30, 12345, threads, C.byref(h), C.byref(b))
+            assert secs > 0, "encode failed"
+            if best is None or secs < best[0]:
+                best = (secs, h.value, b.value)
+        return best
+    st = streams.EncBackendStats()
+    Lo.ocg_backend_set_enc_mode(streams.ENC_AUTO)
+    Lo.ocg_backend_get_enc_stats(None, 1)
+    secs, hsh, nbytes = run(Lo)
+    Lo.ocg_backend_get_enc_stats(C.byref(st), 0)
+    out["value"] = (frames - 1) * threads / secs
+    out["api"] = "th_encode_ycbcr_in + th_encode_packetout (reference host code, B200 back-end)"
+    out["device_frames"] = int(st.frames)
+    out["prepass_ms_per_frame"] = 1e3 * st.prepass_seconds / max(st.prepass_frames, 1)
+    out["flush_ms_per_frame"] = 1e3 * st.flush_seconds / max(st.frames, 1)
+    out["h2d_bytes_per_frame"] = int(st.h2d_bytes / max(st.prepass_frames, 1))
+    out["d2h_bytes_per_frame"] = int(st.d2h_bytes / max(st.prepass_frames, 1))
+    R, kind = reference_lib()
+    rsecs, rhsh, rbytes = run(R)
+    out["cpu_baseline"] = {"value": (frames - 1) * threads / rsecs, "cores": threads,
+                           "kind": "reference" if kind == "asm" else "reference (C path)"}
+    out["packets_identical_to_reference"] = bool((hsh, nbytes) == (rhsh, rbytes))
+    return out
+
+
 def bench_encode_kernels(torch, dev, peak, nframes=40):
     """Throughput + algorithmic-bytes roofline of the encoder batch kernels on 1080p luma
     (BASELINE configs[2]/[3] block work; informational, the headline is decode)."""
@@ -234,6 +273,22 @@ def bench_encode_kernels(torch, dev, peak, nframes=40):
                            "frames_per_s_one_ref": nframes / (ms * 1e-3),
                            "found_planted_vector": float(np.mean((res["best_vec"][:, 0] == 3) &
                                                                  (np.abs(res["best_vec"][:, 1]) == 1)))}
+    # half-pel refinement around the vectors the search just found (1MV + 4MV, SATD2)
+    rin = np.zeros(len(mbs), M.REF_IN)
+    rin["frag_off"] = mbs["frag_off"]
+    rin["vec"] = res["best_vec"]
+    rin["block_vec"] = res["block_vec"]
+    rin["satd"] = res["satd"]
+    rin["block_satd"] = res["block_satd"]
+    drin = torch.from_numpy(rin.view(np.uint8).reshape(-1, 48)).to(dev)
+    orf = torch.empty((len(mbs), 32), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: abi.check(L.ocg_mcenc_refine_batch(bs, bt, ystride, drin.data_ptr(), orf.data_ptr(),
+                                                          len(mbs), 3, st)), reps=5)
+    # 64 two-tap 8x8 SATD2 scores per macro block, 200 algorithmic bytes each
+    out["mcenc_refine_1mv_4mv"] = {"ms": ms, "macro_blocks_per_s": len(mbs) / (ms * 1e-3),
+                                   "satd2_blocks_per_s": 64 * len(mbs) / (ms * 1e-3),
+                                   "alg_GBps": 64 * len(mbs) * 200 / (ms * 1e-3) / 1e9,
+                                   "frames_per_s_one_ref": nframes / (ms * 1e-3)}
     out["config"] = ("1920x1088 luma, %d frames per launch (source + reference = %.0f MB, larger than the 126 MB L2), "
                      "inter residual vs (3,1)-displaced reference" % (nframes, 2 * nframes * fsz / 1e6))
     return out
@@ -471,6 +526,13 @@ def main():
         except Exception as e:  # informational section: never take the headline down with it
             enc = {"error": repr(e)}
 
+    enc_intra = None
+    if RANK == 0 and WORLD == 1 and not args.no_e2e and not args.no_cpu:
+        try:
+            enc_intra = bench_encode_intra(Lo, ncores, args.width, args.height, args.quality)
+        except Exception as e:
+            enc_intra = {"error": repr(e)}
+
     if RANK == 0:
         line = {"metric": "1080p decode frames/sec", "value": value, "unit": "frames/s", "n_gpus": WORLD,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -481,6 +543,7 @@ def main():
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
                            "parallelism": "independent streams, %d per GPU" % S},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
+                "encode_intra": enc_intra,
                 "gpu_launches": int(launches),
                 "clocks": clocks}
         emit(line)

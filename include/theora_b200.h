@@ -211,6 +211,8 @@ typedef struct ocg_enc_frag {
 #define OCG_MET_INTRA_SATD 2  /* oc_enc_frag_intra_satd_c (encfrag.c:322)                                  */
 #define OCG_MET_SSD        3  /* oc_enc_frag_ssd_c (encfrag.c:338)                                         */
 #define OCG_MET_INTRA_SAD  4  /* oc_enc_frag_intra_sad_c (encfrag.c:86)                                    */
+#define OCG_MET_BORDER_SSD 5  /* oc_enc_frag_border_ssd_c (encfrag.c:352): the 64-bit pixel mask (bit i = row
+                                 i>>3, column i&7 in traversal order) travels in ref_off1 (low) / aux (high) */
 
 /* All encoder entry points take DEVICE pointers for frames and lists (the
    caller owns residency) and run on `stream`. */
@@ -254,6 +256,40 @@ typedef struct ocg_mb_search_out {
 OCG_API int ocg_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_base,
                                    const uint8_t *ref_satd_base, int ystride,
                                    const ocg_mb_search_in *in, ocg_mb_search_out *out, int n,
+                                   void *stream);
+
+/* Half-pel refinement of the vectors the full-pel search found:
+   oc_mcenc_refine1mv (mcenc.c:661-670, via oc_mcenc_ysatd_halfpel_mbrefine,
+   606-659) and oc_mcenc_refine4mv (mcenc.c:762-791, via ..._brefine, 713-760).
+   Unlike the search, the refinement of a macro block depends on nothing but its
+   own full-pel result, so a whole frame is one batch.  For each of the 8
+   half-pel sites around the full-pel vector the two-tap predictor is scored
+   with SATD2 + |dc| (or SAD2 when OCG_REFINE_SAD is set: speed level >=
+   OC_SP_LEVEL_NOSATD, 1MV only); a site replaces the current best only if it is
+   strictly better, sites visited in the order of OC_SQUARE_SITES[0]. */
+typedef struct ocg_mb_refine_in {
+  int32_t  frag_off[4];     /* frag_buf_offs[mb_maps[mbi][0][0..3]]                      */
+  int8_t   vec[2];          /* OC_DIV2 of analysis_mv[0][frame] (full-pel)               */
+  int8_t   block_vec[4][2]; /* OC_DIV2 of block_mv[bi]                                   */
+  uint8_t  pad[2];
+  uint32_t satd;            /* embs[mbi].satd[frame] on entry                            */
+  uint32_t block_satd[4];   /* embs[mbi].block_satd[bi] on entry                         */
+} ocg_mb_refine_in;         /* 48 bytes */
+
+typedef struct ocg_mb_refine_out {
+  int8_t   mv[2];           /* analysis_mv[0][frame] = OC_MV(mv[0],mv[1]) (half-pel)     */
+  int8_t   ref_mv[4][2];    /* embs[mbi].ref_mv[bi]                        (half-pel)     */
+  uint8_t  pad[2];
+  uint32_t satd;            /* embs[mbi].satd[frame]                                     */
+  uint32_t block_satd[4];   /* embs[mbi].block_satd[bi]                                  */
+} ocg_mb_refine_out;        /* 32 bytes */
+
+#define OCG_REFINE_1MV 1
+#define OCG_REFINE_4MV 2
+#define OCG_REFINE_SAD 4
+/* Device pointers; src = OC_FRAME_IO, ref = the reconstructed reference frame. */
+OCG_API int ocg_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                   const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags,
                                    void *stream);
 
 /* Intra-frame analysis pre-pass (BASELINE config "intra-only encode").  The

@@ -143,3 +143,43 @@ REFH_API void refh_mcenc_search_frame(const unsigned char *src, const unsigned c
   free(embs);
   free(enc);
 }
+
+/* oc_mcenc_refine1mv (lib/mcenc.c:661) and oc_mcenc_refine4mv (lib/mcenc.c:762)
+   on caller-provided frames.  mv / block_mv are oc_mv values in half-pel units
+   as the full-pel search leaves them (even components).
+   out: [0] analysis_mv[0][frame], [1] satd[frame], [2..5] ref_mv[bi],
+        [6..9] block_satd[bi]. */
+REFH_API void refh_mcenc_refine(const unsigned char *src, const unsigned char *ref, int ystride,
+                                const long frag_off[4], int frame, int mv, unsigned satd, const int block_mv[4],
+                                const unsigned block_satd[4], int sp_level, int do4mv, int out[10]) {
+  oc_enc_ctx *enc = (oc_enc_ctx *)calloc(1, sizeof(*enc));
+  oc_mb_enc_info *embs = (oc_mb_enc_info *)calloc(1, sizeof(*embs));
+  oc_mb_map map;
+  ptrdiff_t offs[4];
+  int i;
+  memset(map, 0xFF, sizeof(map));
+  for (i = 0; i < 4; i++) { map[0][i] = i; offs[i] = frag_off[i]; }
+  enc->mb_info = embs;
+  enc->sp_level = sp_level;
+  enc->state.mb_maps = &map;
+  enc->state.frag_buf_offs = offs;
+  enc->state.ref_ystride[0] = ystride;
+  enc->state.ref_frame_data[OC_FRAME_IO] = (unsigned char *)src;
+  enc->state.ref_frame_data[frame] = (unsigned char *)ref;
+  embs[0].analysis_mv[0][frame] = (oc_mv)mv;
+  embs[0].satd[frame] = satd;
+  for (i = 0; i < 4; i++) {
+    embs[0].block_mv[i] = (oc_mv)block_mv[i];
+    embs[0].block_satd[i] = block_satd[i];
+  }
+  oc_mcenc_refine1mv(enc, 0, frame);
+  if (do4mv) oc_mcenc_refine4mv(enc, 0);
+  out[0] = embs[0].analysis_mv[0][frame];
+  out[1] = (int)embs[0].satd[frame];
+  for (i = 0; i < 4; i++) {
+    out[2 + i] = embs[0].ref_mv[i];
+    out[6 + i] = (int)embs[0].block_satd[i];
+  }
+  free(embs);
+  free(enc);
+}

@@ -632,6 +632,10 @@ OCO_EXPORT void oco_enc_metrics_batch(int metric, const uint8_t *src_base, const
       case OCG_MET_INTRA_SATD: v = oco_frag_intra_satd(&dc, src, ystride); break;
       case OCG_MET_SSD: v = oco_frag_ssd(src, r0, ystride); break;
       case OCG_MET_INTRA_SAD: v = oco_frag_intra_sad(src, ystride); break;
+      case OCG_MET_BORDER_SSD:
+        v = oco_frag_border_ssd(src, r0, ystride,
+                                (int64_t)(((uint64_t)(uint32_t)frags[i].aux << 32) | (uint32_t)frags[i].ref_off1));
+        break;
       default: break;
     }
     out_val[i] = v;
@@ -843,6 +847,77 @@ OCO_EXPORT void oco_mcenc_search_batch(const uint8_t *src_base, const uint8_t *r
           o->block_vec[bi][1] = (int8_t)s.blk_vec[bi][1];
           o->block_satd[bi] = bs + (unsigned)abs(dc);
         }
+      }
+    }
+  }
+}
+
+/* ---- half-pel refinement (mcenc.c:606-791) --------------------------------
+   The two taps of half-pel vector 2v+d are found as the reference does at
+   mcenc.c:636-646 (a restatement of oc_state_get_mv_offsets for luma): the
+   component whose half-pel value and step have opposite signs keeps the
+   full-pel tap on the first offset. */
+static void ref_taps(int vx, int vy, int dx, int dy, int ystride, int *o0, int *o1) {
+  int hx = 2 * vx + dx, hy = 2 * vy + dy;
+  int first_x = ((hx ^ dx) < 0) ? dx : 0, second_x = ((hx ^ dx) < 0) ? 0 : dx;
+  int first_y = ((hy ^ dy) < 0) ? dy * ystride : 0, second_y = ((hy ^ dy) < 0) ? 0 : dy * ystride;
+  int base = vx + vy * ystride;
+  *o0 = base + first_x + first_y;
+  *o1 = base + second_x + second_y;
+}
+
+/* visiting order of the 8 sites: OC_SQUARE_SITES[0] = {0,1,2,3,5,6,7,8} over
+   OC_SQUARE_DX/DY (mcenc.c:50-66) */
+static const int k_ref_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+static const int k_ref_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+
+OCO_EXPORT void oco_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                       const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags) {
+  int i, bi, si;
+  for (i = 0; i < n; i++) {
+    const ocg_mb_refine_in *m = &in[i];
+    ocg_mb_refine_out *o = &out[i];
+    if (flags & OCG_REFINE_1MV) {
+      /* oc_mcenc_ysatd_halfpel_mbrefine, mcenc.c:606-659 */
+      unsigned best = m->satd;
+      int bdx = 0, bdy = 0;
+      for (si = 0; si < 8; si++) {
+        int o0, o1, dc;
+        unsigned err = 0;
+        ref_taps(m->vec[0], m->vec[1], k_ref_dx[si], k_ref_dy[si], ystride, &o0, &o1);
+        for (bi = 0; bi < 4; bi++) {
+          const uint8_t *s = src_base + m->frag_off[bi], *r = ref_base + m->frag_off[bi];
+          if (flags & OCG_REFINE_SAD) {
+            /* oc_sad16_halfpel, mcenc.c:166-180: the early-out only ever reports
+               "worse than the current best", the exact sum decides the same */
+            err += oco_frag_sad2_thresh(s, r + o0, r + o1, ystride, UINT_MAX);
+          } else {
+            err += oco_frag_satd2(&dc, s, r + o0, r + o1, ystride);
+            err += (unsigned)abs(dc);
+          }
+        }
+        if (err < best) { best = err; bdx = k_ref_dx[si]; bdy = k_ref_dy[si]; }
+      }
+      o->mv[0] = (int8_t)(2 * m->vec[0] + bdx);
+      o->mv[1] = (int8_t)(2 * m->vec[1] + bdy);
+      o->satd = best;
+    }
+    if (flags & OCG_REFINE_4MV) {
+      /* oc_mcenc_refine4mv + oc_mcenc_ysatd_halfpel_brefine, mcenc.c:713-791 */
+      for (bi = 0; bi < 4; bi++) {
+        const uint8_t *s = src_base + m->frag_off[bi], *r = ref_base + m->frag_off[bi];
+        unsigned best = m->block_satd[bi];
+        int bdx = 0, bdy = 0;
+        for (si = 0; si < 8; si++) {
+          int o0, o1, dc;
+          unsigned err;
+          ref_taps(m->block_vec[bi][0], m->block_vec[bi][1], k_ref_dx[si], k_ref_dy[si], ystride, &o0, &o1);
+          err = oco_frag_satd2(&dc, s, r + o0, r + o1, ystride) + (unsigned)abs(dc);
+          if (err < best) { best = err; bdx = k_ref_dx[si]; bdy = k_ref_dy[si]; }
+        }
+        o->ref_mv[bi][0] = (int8_t)(2 * m->block_vec[bi][0] + bdx);
+        o->ref_mv[bi][1] = (int8_t)(2 * m->block_vec[bi][1] + bdy);
+        o->block_satd[bi] = best;
       }
     }
   }

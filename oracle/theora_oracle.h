@@ -76,6 +76,8 @@ void oco_enc_fdct_quant_batch(const uint8_t *src_base, const uint8_t *ref_base, 
 
 void oco_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_base, const uint8_t *ref_satd_base,
                             int ystride, const ocg_mb_search_in *in, ocg_mb_search_out *out, int n); /* mcenc.c:268-515 */
+void oco_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                            const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags); /* mcenc.c:606-791 */
 
 #ifdef __cplusplus
 }

@@ -92,3 +92,34 @@ def make_cases(rng, n, w=192, h=128, st=None, ystride=None):
         cases.append(dict(offs=offs, ncn=ncn, nb_mvs=nb_mvs, nb_err=nb_err, accum=accum, mv1=mv1, mv2=mv2,
                           own_err=own_err, frame=frame))
     return mb_in, cases
+
+
+REF_IN = np.dtype([("frag_off", "<i4", (4,)), ("vec", "i1", (2,)), ("block_vec", "i1", (4, 2)), ("pad", "u1", (2,)),
+                   ("satd", "<u4"), ("block_satd", "<u4", (4,))])
+REF_OUT = np.dtype([("mv", "i1", (2,)), ("ref_mv", "i1", (4, 2)), ("pad", "u1", (2,)), ("satd", "<u4"),
+                    ("block_satd", "<u4", (4,))])
+assert REF_IN.itemsize == 48 and REF_OUT.itemsize == 32
+
+
+def make_refine_cases(rng, n, w=192, h=128, ystride=None, vmax=15, entry="mixed"):
+    """n macro blocks with random full-pel vectors (window +-vmax) and entry
+    scores: 'mixed' draws them around typical SATD magnitudes so that some
+    sites win and some do not; 0 makes every site lose, 'max' makes the best
+    site always win."""
+    mb = np.zeros(n, REF_IN)
+    for i in range(n):
+        mx = int(rng.integers(0, w // 16)) * 16
+        my = int(rng.integers(0, h // 16)) * 16
+        mb[i]["frag_off"] = [(my + by) * ystride + mx + bx for by in (0, 8) for bx in (0, 8)]
+        mb[i]["vec"] = rng.integers(-vmax, vmax + 1, size=2)
+        mb[i]["block_vec"] = rng.integers(-vmax, vmax + 1, size=(4, 2))
+        if entry == "max":
+            mb[i]["satd"] = 0xFFFFFFF
+            mb[i]["block_satd"] = 0xFFFFFFF
+        elif entry == 0:
+            mb[i]["satd"] = 0
+            mb[i]["block_satd"] = 0
+        else:
+            mb[i]["satd"] = int(rng.integers(2000, 30000))
+            mb[i]["block_satd"] = rng.integers(500, 8000, size=4)
+    return mb

@@ -97,6 +97,8 @@ def _bind_harness(L):
     L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
     L.refh_encode_synth_recon.restype = C.c_void_p
     L.refh_encode_synth_recon.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_void_p]
+    L.refh_encode_synth_fmt.restype = C.c_void_p
+    L.refh_encode_synth_fmt.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_int, C.c_void_p]
     L.refh_encode_time_mt.restype = C.c_double
     L.refh_encode_time_mt.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_long)]
     L.refh_stream_free.argtypes = [C.c_void_p]
@@ -162,8 +164,8 @@ class Stream:
         self.lib, self.h = lib, handle
 
     @staticmethod
-    def encode(lib, w, h, nframes, quality=48, kf=64, speed=1, noise_shift=30, seed=12345, f0=0):
-        hnd = lib.refh_encode_synth(w, h, f0, nframes, quality, kf, speed, noise_shift, seed)
+    def encode(lib, w, h, nframes, quality=48, kf=64, speed=1, noise_shift=30, seed=12345, f0=0, fmt=0):
+        hnd = lib.refh_encode_synth_fmt(w, h, f0, nframes, quality, kf, speed, noise_shift, seed, fmt, None)
         assert hnd, "encoder failed"
         return Stream(lib, hnd)
 

@@ -25,13 +25,16 @@ CASES = [
     (350, 270, 5, 40, 64, 1, 30),    # cropped picture (frame 352x272)
     (320, 240, 6, 10, 3, 0, 28),     # low quality, speed 0
     (96, 80, 10, 60, 64, 2, 26),     # high quality / heavy noise: dense blocks
+    (208, 112, 6, 24, 4, 1, 28, 2),  # TH_PF_422
+    (208, 112, 6, 24, 4, 1, 28, 3),  # TH_PF_444
 ]
 
 
 def replay_and_compare(case):
-    w, h, n, q, kf, sp, ns = case
+    w, h, n, q, kf, sp, ns = case[:7]
+    fmt = case[7] if len(case) > 7 else 0
     R = S.ref("c")
-    st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns)
+    st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns, fmt=fmt)
     blob = st.to_bytes()
     g, works, _ = streams.capture_stream_work(blob, streams.BACKEND_RECORD)
     dec = S.Decoder(R, st)

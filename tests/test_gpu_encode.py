@@ -73,6 +73,37 @@ def test_metrics_batch(metric, taps, mode):
     assert np.array_equal(odc.cpu().numpy(), want_dc)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_border_ssd_batch(mode):
+    """OCG_MET_BORDER_SSD: oc_enc_frag_border_ssd_c, 64-bit pixel mask in ref_off1 (low) / aux (high)."""
+    rng = np.random.default_rng(77 + mode)
+    a, b, st = make_frames(rng, mode)
+    n = 5000
+    fr, base, ystride = make_frags(rng, st, n, 1)
+    masks = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n, dtype=np.uint64)
+    masks[:4] = [0, 0xFFFFFFFFFFFFFFFF, 0x00000000FFFFFFFF, 0x8000000000000001]
+    fr["ref_off1"] = (masks & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+    fr["aux"] = (masks >> 32).astype(np.uint32).view(np.int32)
+    want_v, want_dc = np.zeros(n, np.uint32), np.zeros(n, np.int32)
+    S.oracle().oco_enc_metrics_batch(5, a.ctypes.data + base, b.ctypes.data + base, ystride, fr.ctypes.data, n,
+                                     S.ptr(want_v, S.u32p), S.ptr(want_dc, S.i32p))
+    # cross-check two entries against the scalar oracle routine (itself pinned to the reference)
+    for i in (1, 3, 100):
+        m = int(masks[i])
+        m = m - (1 << 64) if m >= (1 << 63) else m
+        assert want_v[i] == S.oracle().oco_frag_border_ssd(a.ctypes.data + base + int(fr["src_off"][i]),
+                                                           b.ctypes.data + base + int(fr["ref_off0"][i]), ystride, m)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dfr = torch.from_numpy(fr.view(np.int32).reshape(n, 4)).cuda()
+    ov = torch.zeros(n, dtype=torch.int32, device="cuda")
+    abi.check(abi.lib().ocg_enc_metrics_batch(5, da.data_ptr() + base, db.data_ptr() + base, ystride,
+                                              dfr.data_ptr(), n, ov.data_ptr(), None,
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(ov.cpu().numpy().view(np.uint32), want_v)
+    assert want_v[0] == 0
+
+
 @pytest.mark.parametrize("taps", [0, 1, 2])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_fdct_quant_batch(taps, mode):

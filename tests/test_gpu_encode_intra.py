@@ -79,6 +79,21 @@ def test_intra_only_encode_is_bit_identical_and_closed_loop(case):
     got.free()
 
 
+@pytest.mark.parametrize("fmt", [2, 3])
+def test_intra_only_encode_422_444(fmt):
+    R = S.ref("c")
+    G = streams.lib()
+    want = S.Stream.encode(R, 144, 96, 3, quality=24, kf=1, speed=1, noise_shift=28, fmt=fmt)
+    G.ocg_backend_get_enc_stats(None, 1)
+    got = S.Stream.encode(G, 144, 96, 3, quality=24, kf=1, speed=1, noise_shift=28, fmt=fmt)
+    st = streams.EncBackendStats()
+    G.ocg_backend_get_enc_stats(C.byref(st), 0)
+    assert st.frames == 4
+    assert got.to_bytes() == want.to_bytes()
+    want.free()
+    got.free()
+
+
 def test_inter_capable_encoder_keeps_host_kernels():
     """keyframe_granule_shift > 0: not served by the device encoder; the stream
     is still the reference's and the device statistics stay at zero."""

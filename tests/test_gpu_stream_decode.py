@@ -39,6 +39,24 @@ def test_public_api_decode_matches_reference(case):
     st.free()
 
 
+@pytest.mark.parametrize("fmt", [2, 3])
+@pytest.mark.parametrize("q", [20, 48])
+def test_422_and_444_streams_match_reference(fmt, q):
+    """TH_PF_422 / TH_PF_444: full-resolution chroma planes, half-pel chroma vectors
+    (state.c:888-957), luma-sized strides for every plane in 4:4:4."""
+    R = S.ref("c")
+    st = S.Stream.encode(R, 208, 112, 7, quality=q, kf=5, speed=1, noise_shift=28, fmt=fmt)
+    g, works, outs = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_GPU)
+    assert g.pixel_fmt == fmt
+    dec = S.Decoder(R, st)
+    assert len(outs) == 7
+    for i in range(7):
+        assert dec.next() >= 0
+        assert np.array_equal(outs[i], dec.frame()), "frame %d differs" % i
+    dec.close()
+    st.free()
+
+
 def test_stream_starting_on_inter_frame_uses_grey_reference():
     """decode.c:2053 oc_dec_init_dummy_frame: drop the keyframe, decode the rest."""
     import ctypes as C

@@ -186,11 +186,13 @@ static inline int row_nonzero(const ogg_int16_t *row) {
 
 static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi, int _pli,
                                  ogg_int16_t _dct_coeffs[128], int _last_zzi, ogg_uint16_t _dc_quant) {
-  ocg_backend *b = backend_of(_state);
+  ocg_backend *b = t_cur;
   const oc_fragment *frag = _state->frags + _fragi;
   ocg_frag_rec *rec;
+  ogg_int16_t *out;
   int nr, r, qti, mask = 0;
   ogg_int16_t dc = _dct_coeffs[0];
+  if (__builtin_expect(b == NULL || (const void *)b->dec != (const void *)_state, 0)) b = backend_of(_state);
   if (b == NULL || !b->frame_open) backend_fatal("state_frag_recon outside a frame");
   /* footprint of the transform the reference would run (state.c:967,
      idct.c:327-329): 0, 2, 4 or 8 leading rows */
@@ -198,17 +200,24 @@ static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi
   rec = b->st.recs + _fragi;
   rec->coeff_row = (ogg_uint32_t)b->nrows;
   _dct_coeffs[0] = 0; /* DC travels in the record */
+  /* every footprint row is written at the list's end and kept only if it is
+     non-zero (no branch per row; a zero row is overwritten by the next one) */
+  out = b->st.coeff_rows + (size_t)b->nrows * 8;
   for (r = 0; r < nr; r++) {
-    ogg_int16_t *row = _dct_coeffs + r * 8;
-    if (row_nonzero(row)) {
-      memcpy(b->st.coeff_rows + (size_t)b->nrows * 8, row, 16);
-      /* the iDCT contract: leave the coefficients zeroed for the next block
-         (idct.c:245,276,295; decode.c:1385) */
-      memset(row, 0, 16);
-      b->nrows++;
-      mask |= 1 << r;
-    }
+    ogg_uint64_t a, c;
+    int nz;
+    memcpy(&a, _dct_coeffs + r * 8, 8);
+    memcpy(&c, _dct_coeffs + r * 8 + 4, 8);
+    memcpy(out, &a, 8);
+    memcpy(out + 4, &c, 8);
+    nz = (a | c) != 0;
+    out += nz << 3;
+    mask |= nz << r;
   }
+  b->nrows = (int)((out - b->st.coeff_rows) >> 3);
+  /* the iDCT contract: leave the coefficients zeroed for the next block
+     (idct.c:245,276,295; decode.c:1385); the footprint rows are contiguous */
+  memset(_dct_coeffs, 0, (size_t)nr * 16);
   qti = frag->mb_mode != OC_MODE_INTRA;
   /* buf_off and the plane are already in the record (template) */
   rec->mv = _state->frag_mvs[_fragi];

@@ -126,6 +126,38 @@ __device__ __forceinline__ void load_pred8(const uint8_t *ref_base, const ocg_en
   }
 }
 
+/* 2-D 8x8 Hadamard of (s - p), sum of magnitudes without the DC term, DC
+   returned separately (encfrag.c:109-336), all in registers */
+__device__ __forceinline__ uint32_t satd8x8(const Rows8 &s, const Rows8 &p, int &dc) {
+  int h[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int a[8], b[8];
+    unpack8(s.r[i], a);
+    unpack8(p.r[i], b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] -= b[k];
+    hadamard8(a);
+#pragma unroll
+    for (int k = 0; k < 8; k++) h[i][k] = a[k];
+  }
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    int t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = h[i][k];
+    hadamard8(t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc += abs(t[i]);
+    if (k == 0) { dc = t[0]; acc -= abs(t[0]); }
+  }
+  return (uint32_t)acc;
+}
+
+/* four mask bits -> four byte masks */
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return ((n * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
 template <int METRIC>
 __global__ void __launch_bounds__(128)
 ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base, int ystride,
@@ -157,6 +189,23 @@ ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__re
       ab = __dp4a(s.r[i].x, p.r[i].x, ab); ab = __dp4a(s.r[i].y, p.r[i].y, ab);
     }
     val = aa + bb - 2u * ab;
+  } else if (METRIC == OCG_MET_BORDER_SSD) {
+    /* encfrag.c:352-366: only the pixels whose mask bit is set count; masked-out
+       bytes are zeroed in both operands, so they add 0 to every dot product */
+    const uint32_t mlo = (uint32_t)f.ref_off1, mhi = (uint32_t)f.aux;
+    f.ref_off1 = INT_MIN;
+    load_pred8(ref_base, f, ystride, p);
+    unsigned aa = 0, bb = 0, ab = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t m8 = ((i < 4 ? mlo : mhi) >> (8 * (i & 3))) & 0xFFu;
+      const uint32_t m0 = nibble_to_bytes(m8 & 15u), m1 = nibble_to_bytes(m8 >> 4);
+      const uint32_t sx = s.r[i].x & m0, sy = s.r[i].y & m1, px = p.r[i].x & m0, py = p.r[i].y & m1;
+      aa = __dp4a(sx, sx, aa); aa = __dp4a(sy, sy, aa);
+      bb = __dp4a(px, px, bb); bb = __dp4a(py, py, bb);
+      ab = __dp4a(sx, px, ab); ab = __dp4a(sy, py, ab);
+    }
+    val = aa + bb - 2u * ab;
   } else if (METRIC == OCG_MET_INTRA_SAD) {
     /* encfrag.c:88-107: dc=(sum+32)>>6, then sum |src-dc| */
     unsigned tot = 0;
@@ -172,30 +221,7 @@ ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__re
 #pragma unroll
       for (int i = 0; i < 8; i++) p.r[i] = make_uint2(0, 0);
     } else load_pred8(ref_base, f, ystride, p);
-    int h[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      int a[8], b[8];
-      unpack8(s.r[i], a);
-      unpack8(p.r[i], b);
-#pragma unroll
-      for (int k = 0; k < 8; k++) a[k] -= b[k];
-      hadamard8(a);
-#pragma unroll
-      for (int k = 0; k < 8; k++) h[i][k] = a[k];
-    }
-    int acc = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      int t[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) t[i] = h[i][k];
-      hadamard8(t);
-#pragma unroll
-      for (int i = 0; i < 8; i++) acc += abs(t[i]);
-      if (k == 0) { dc = t[0]; acc -= abs(t[0]); }
-    }
-    val = (uint32_t)acc;
+    val = satd8x8(s, p, dc);
   }
   out_val[fi] = val;
   if (out_dc != nullptr) out_dc[fi] = dc;
@@ -529,15 +555,131 @@ ocg_mcenc_search_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__r
   }
 }
 
+/* ------------------------------------------------------------------------ */
+/* Half-pel refinement (mcenc.c:606-791), one warp per macro block, ONE LANE
+   PER (block, site): the 4 blocks x 8 half-pel sites of a macro block are 32
+   independent two-tap 8x8 scores, each computed like a metrics-kernel block
+   (all rows in registers).  1MV: lane = site*4 + block, the four block scores of
+   a site are summed with two shuffles; 4MV: lane = block*8 + site.  The winner
+   is the first site in OC_SQUARE_SITES[0] order that is strictly better than
+   everything before it, i.e. the lexicographic minimum of (score, site order)
+   if that beats the entry score. */
+__constant__ int c_sq_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}; /* OC_SQUARE_SITES[0] = {0,1,2,3,5,6,7,8} */
+__constant__ int c_sq_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+
+__device__ __forceinline__ uint32_t refine_score(const uint8_t *src, const uint8_t *ref, int ystride, int vx, int vy,
+                                                 int dx, int dy, bool use_sad) {
+  /* mcenc.c:636-646: the two taps of half-pel vector (2v+d) */
+  const int xmask = (((vx << 1) + dx) ^ dx) < 0 ? -1 : 0;
+  const int ymask = (((vy << 1) + dy) ^ dy) < 0 ? -1 : 0;
+  const int oy = dy * ystride;
+  const int base = vx + vy * ystride;
+  const int o0 = base + (dx & xmask) + (oy & ymask);
+  const int o1 = base + (dx & ~xmask) + (oy & ~ymask);
+  Rows8 s, p, t;
+  load_rows8(src, ystride, s);
+  load_rows8(ref + o0, ystride, p);
+  load_rows8(ref + o1, ystride, t);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    p.r[i].x = __vhaddu4(p.r[i].x, t.r[i].x);
+    p.r[i].y = __vhaddu4(p.r[i].y, t.r[i].y);
+  }
+  if (use_sad) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v += __vsadu4(s.r[i].x, p.r[i].x) + __vsadu4(s.r[i].y, p.r[i].y);
+    return v;
+  }
+  int dc;
+  const uint32_t v = satd8x8(s, p, dc);
+  return v + (uint32_t)abs(dc);
+}
+
+__global__ void __launch_bounds__(128)
+ocg_mcenc_refine_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base, int ystride,
+                        const ocg_mb_refine_in *__restrict__ in, ocg_mb_refine_out *__restrict__ out, int n,
+                        int flags) {
+  const int lane = threadIdx.x & 31;
+  const int mbi_raw = (int)(blockIdx.x * 4 + (threadIdx.x >> 5));
+  const bool live = mbi_raw < n; /* warp-uniform */
+  if (!live) return;
+  const ocg_mb_refine_in *mb = in + mbi_raw;
+  ocg_mb_refine_out *o = out + mbi_raw;
+  if (flags & OCG_REFINE_1MV) {
+    const int sitei = lane >> 2, bi = lane & 3;
+    const int off = mb->frag_off[bi];
+    const int vx = mb->vec[0], vy = mb->vec[1];
+    uint32_t err = refine_score(src_base + off, ref_base + off, ystride, vx, vy, c_sq_dx[sitei], c_sq_dy[sitei],
+                                (flags & OCG_REFINE_SAD) != 0);
+    err += __shfl_xor_sync(0xFFFFFFFFu, err, 1);
+    err += __shfl_xor_sync(0xFFFFFFFFu, err, 2);
+    /* lexicographic min over the sites of (err, site order) */
+    uint32_t key_e = err;
+    int key_s = sitei;
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      const uint32_t oe = __shfl_xor_sync(0xFFFFFFFFu, key_e, d);
+      const int os = __shfl_xor_sync(0xFFFFFFFFu, key_s, d);
+      if (oe < key_e || (oe == key_e && os < key_s)) { key_e = oe; key_s = os; }
+    }
+    if (lane == 0) {
+      const uint32_t entry = mb->satd;
+      int dx = 0, dy = 0;
+      uint32_t best = entry;
+      if (key_e < entry) { best = key_e; dx = c_sq_dx[key_s]; dy = c_sq_dy[key_s]; }
+      o->mv[0] = (int8_t)((vx << 1) + dx);
+      o->mv[1] = (int8_t)((vy << 1) + dy);
+      o->satd = best;
+    }
+  }
+  if (flags & OCG_REFINE_4MV) {
+    const int bi = lane >> 3, sitei = lane & 7;
+    const int off = mb->frag_off[bi];
+    const int vx = mb->block_vec[bi][0], vy = mb->block_vec[bi][1];
+    const uint32_t err = refine_score(src_base + off, ref_base + off, ystride, vx, vy, c_sq_dx[sitei], c_sq_dy[sitei],
+                                      false);
+    uint32_t key_e = err;
+    int key_s = sitei;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      const uint32_t oe = __shfl_xor_sync(0xFFFFFFFFu, key_e, d);
+      const int os = __shfl_xor_sync(0xFFFFFFFFu, key_s, d);
+      if (oe < key_e || (oe == key_e && os < key_s)) { key_e = oe; key_s = os; }
+    }
+    if (sitei == 0) {
+      const uint32_t entry = mb->block_satd[bi];
+      int dx = 0, dy = 0;
+      uint32_t best = entry;
+      if (key_e < entry) { best = key_e; dx = c_sq_dx[key_s]; dy = c_sq_dy[key_s]; }
+      o->ref_mv[bi][0] = (int8_t)((vx << 1) + dx);
+      o->ref_mv[bi][1] = (int8_t)((vy << 1) + dy);
+      o->block_satd[bi] = best;
+    }
+  }
+}
+
 } /* namespace */
 
 extern "C" {
+
+OCG_API int ocg_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
+                                   const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags,
+                                   void *stream) {
+  if (src_base == nullptr || ref_base == nullptr || in == nullptr || out == nullptr) return OCG_EFAULT;
+  if (n < 0 || (flags & ~7) != 0 || (flags & (OCG_REFINE_1MV | OCG_REFINE_4MV)) == 0) return OCG_EINVAL;
+  if (n == 0) return OCG_OK;
+  ocg_mcenc_refine_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(src_base, ref_base, ystride, in,
+                                                                                     out, n, flags);
+  ocg_count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
 
 OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uint8_t *ref_base, int ystride,
                                   const ocg_enc_frag *frags, int n, uint32_t *out_val, int32_t *out_dc,
                                   void *stream) {
   if (src_base == nullptr || frags == nullptr || out_val == nullptr) return OCG_EFAULT;
-  if (metric < OCG_MET_SAD || metric > OCG_MET_INTRA_SAD || n < 0) return OCG_EINVAL;
+  if (metric < OCG_MET_SAD || metric > OCG_MET_BORDER_SSD || n < 0) return OCG_EINVAL;
   if (n == 0) return OCG_OK;
   const unsigned grid = (unsigned)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
@@ -546,6 +688,7 @@ OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uin
     case OCG_MET_SATD: ocg_enc_metrics_kernel<OCG_MET_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_INTRA_SATD: ocg_enc_metrics_kernel<OCG_MET_INTRA_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_SSD: ocg_enc_metrics_kernel<OCG_MET_SSD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+    case OCG_MET_BORDER_SSD: ocg_enc_metrics_kernel<OCG_MET_BORDER_SSD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     default: ocg_enc_metrics_kernel<OCG_MET_INTRA_SAD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
   }
   ocg_count_launch(1);

@@ -67,6 +67,8 @@ def _bind_harness(L):
     L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
     L.refh_encode_synth_recon.restype = C.c_void_p
     L.refh_encode_synth_recon.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_void_p]
+    L.refh_encode_synth_fmt.restype = C.c_void_p
+    L.refh_encode_synth_fmt.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_int, C.c_void_p]
     L.refh_encode_time_mt.restype = C.c_double
     L.refh_encode_time_mt.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_long)]
     L.refh_stream_free.argtypes = [C.c_void_p]

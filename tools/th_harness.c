@@ -122,10 +122,19 @@ REFH_API void refh_stream_append_data(refh_stream *dst, const refh_stream *src) 
 /* Synthetic content: moving gradient + checker + LCG noise,
    global motion (3,1) px/frame.  The LCG is re-seeded per frame from
    (seed, frame index) so GOP segments can be produced independently. */
+static void refh_synth_frame_fmt(int w, int h, int cw, int ch, int f, int noise_shift, unsigned seed,
+                                 unsigned char *y, unsigned char *cb, unsigned char *cr);
 REFH_API void refh_synth_frame(int w, int h, int f, int noise_shift, unsigned seed,
                                unsigned char *y, unsigned char *cb, unsigned char *cr) {
+  refh_synth_frame_fmt(w, h, w >> 1, h >> 1, f, noise_shift, seed, y, cb, cr);
+}
+
+/* chroma planes of cw x ch samples (4:2:0, 4:2:2 or 4:4:4): the chroma pattern
+   is defined on the 4:2:0 grid and sampled at the plane's own resolution */
+static void refh_synth_frame_fmt(int w, int h, int cw, int ch, int f, int noise_shift, unsigned seed,
+                                 unsigned char *y, unsigned char *cb, unsigned char *cr) {
   uint32_t s = seed ^ ((uint32_t)f * 2654435761u);
-  int cw = w >> 1, ch = h >> 1;
+  int sx = cw == w ? 1 : 0, sy = ch == h ? 1 : 0;
   int x, yy;
   for (yy = 0; yy < h; yy++) {
     for (x = 0; x < w; x++) {
@@ -137,8 +146,8 @@ REFH_API void refh_synth_frame(int w, int h, int f, int noise_shift, unsigned se
   }
   for (yy = 0; yy < ch; yy++) {
     for (x = 0; x < cw; x++) {
-      cb[(size_t)yy * cw + x] = (unsigned char)(128 + (((x + f) >> 3) & 15));
-      cr[(size_t)yy * cw + x] = (unsigned char)(128 - (((yy + 2 * f) >> 3) & 15));
+      cb[(size_t)yy * cw + x] = (unsigned char)(128 + ((((x >> sx) + f) >> 3) & 15));
+      cr[(size_t)yy * cw + x] = (unsigned char)(128 - ((((yy >> sy) + 2 * f) >> 3) & 15));
     }
   }
 }
@@ -152,6 +161,9 @@ extern long ocg_backend_enc_copy_recon(th_enc_ctx *enc, unsigned char *dst) __at
 
 REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes, int quality, int kf_interval,
                                               int speed, int noise_shift, unsigned seed, unsigned char *recon_out);
+REFH_API refh_stream *refh_encode_synth_fmt(int w, int h, int f0, int nframes, int quality, int kf_interval,
+                                            int speed, int noise_shift, unsigned seed, int pixel_fmt,
+                                            unsigned char *recon_out);
 
 REFH_API refh_stream *refh_encode_synth(int w, int h, int f0, int nframes, int quality,
                                         int kf_interval, int speed, int noise_shift, unsigned seed) {
@@ -162,6 +174,14 @@ REFH_API refh_stream *refh_encode_synth(int w, int h, int f0, int nframes, int q
    the encoder's reconstruction of the LAST frame. */
 REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes, int quality, int kf_interval,
                                               int speed, int noise_shift, unsigned seed, unsigned char *recon_out) {
+  return refh_encode_synth_fmt(w, h, f0, nframes, quality, kf_interval, speed, noise_shift, seed, TH_PF_420,
+                               recon_out);
+}
+
+/* As above for any th_pixel_fmt (TH_PF_420 = 0, TH_PF_422 = 2, TH_PF_444 = 3). */
+REFH_API refh_stream *refh_encode_synth_fmt(int w, int h, int f0, int nframes, int quality, int kf_interval,
+                                            int speed, int noise_shift, unsigned seed, int pixel_fmt,
+                                            unsigned char *recon_out) {
   th_info ti;
   th_enc_ctx *te;
   th_comment tc;
@@ -170,7 +190,7 @@ REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes,
   refh_stream *s;
   unsigned char *buf;
   int fw = (w + 15) & ~15, fh = (h + 15) & ~15;
-  int cw = w >> 1, ch = h >> 1;
+  int cw = w >> !(pixel_fmt & 1), ch = h >> !(pixel_fmt & 2);
   int f, ret;
   ogg_uint32_t kf = (ogg_uint32_t)kf_interval;
   th_info_init(&ti);
@@ -185,7 +205,7 @@ REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes,
   ti.aspect_numerator = 1;
   ti.aspect_denominator = 1;
   ti.colorspace = TH_CS_UNSPECIFIED;
-  ti.pixel_fmt = TH_PF_420;
+  ti.pixel_fmt = (th_pixel_fmt)pixel_fmt;
   ti.target_bitrate = 0;
   ti.quality = quality;
   ti.keyframe_granule_shift = refh_ilog(kf_interval > 1 ? (unsigned)(kf_interval - 1) : 0);
@@ -204,7 +224,7 @@ REFH_API refh_stream *refh_encode_synth_recon(int w, int h, int f0, int nframes,
   yuv[1].width = cw; yuv[1].height = ch; yuv[1].stride = cw; yuv[1].data = buf + (size_t)w * h;
   yuv[2].width = cw; yuv[2].height = ch; yuv[2].stride = cw; yuv[2].data = yuv[1].data + (size_t)cw * ch;
   for (f = 0; f < nframes; f++) {
-    refh_synth_frame(w, h, f0 + f, noise_shift, seed, yuv[0].data, yuv[1].data, yuv[2].data);
+    refh_synth_frame_fmt(w, h, cw, ch, f0 + f, noise_shift, seed, yuv[0].data, yuv[1].data, yuv[2].data);
     ret = th_encode_ycbcr_in(te, yuv);
     if (ret < 0) break;
     while (th_encode_packetout(te, f + 1 >= nframes, &op) > 0) refh_stream_push(s, op.packet, op.bytes);
