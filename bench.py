@@ -154,6 +154,7 @@ def bench_encode_intra(Lo, threads, width, height, quality, frames=13):
     reference x86 SIMD build on the same threads and the same frames; the first
     frame of every encoder is outside the timed region.  Packets must be
     byte-identical (hash + size of thread 0's packets)."""
+    from theora_b200 import streams
     out = {"workload": "%dx%d 4:2:0 intra-only encode (keyframe every frame), q=%d, speed 1, %d timed frames x %d threads"
            % (width, height, quality, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
 
@@ -327,6 +328,7 @@ def main():
     ap.add_argument("--quality", type=int, default=32)
     ap.add_argument("--kf", type=int, default=64)
     ap.add_argument("--threads", type=int, default=0, help="host threads for e2e / CPU arms (0 = all cores)")
+    ap.add_argument("--e2e-oversub", type=int, default=2, help="stream threads per core of the second e2e pass (1 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-encode-kernels", action="store_true")
@@ -490,22 +492,39 @@ def main():
         Lo.ocg_backend_get_stats(C.byref(st), 1)
         barrier()
         hsh = C.c_uint64(0)
-        runs = []
-        for _ in range(3):  # three passes, median: 16 host threads + PCIe make single passes noisy
-            Lo.ocg_backend_get_stats(C.byref(st), 1)  # reset
-            secs_i = Lo.refh_decode_time(h, ncores, 1, C.byref(hsh))
-            st_i = streams.BackendStats()
-            Lo.ocg_backend_get_stats(C.byref(st_i), 1)
-            runs.append((secs_i, st_i))
-        runs.sort(key=lambda r: r[0])
-        secs, st = runs[1]
+
+        def e2e_pass(nthreads, blocking):
+            """median of three passes: T host threads + PCIe make single passes noisy"""
+            L.ocg_set_blocking_sync(1 if blocking else 0)
+            runs = []
+            for _ in range(3):
+                Lo.ocg_backend_get_stats(C.byref(st), 1)  # reset
+                secs_i = Lo.refh_decode_time(h, nthreads, 1, C.byref(hsh))
+                st_i = streams.BackendStats()
+                Lo.ocg_backend_get_stats(C.byref(st_i), 1)
+                runs.append((secs_i, st_i))
+            L.ocg_set_blocking_sync(0)
+            runs.sort(key=lambda r: r[0])
+            secs, st_m = runs[1]
+            assert secs > 0, "e2e decode failed"
+            secs = sharding.max_over_ranks(secs, dev)
+            return {"value": WORLD * nthreads * nframes / secs, "unit": "frames/s",
+                    "h2d_bytes_per_step": int(st_m.h2d_bytes), "d2h_bytes_per_step": int(st_m.d2h_bytes),
+                    "host_threads": nthreads, "host_cores": ncores,
+                    "sync": "blocking event (thread sleeps during a flush)" if blocking else "spin",
+                    "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
+                    "flush_ms_per_frame": 1e3 * st_m.flush_seconds / max(st_m.frames, 1),
+                    "final_frame_hash": int(hsh.value)}
+        # (a) one stream thread per core; (b) two per core with sleeping waits, so a core parses another
+        # stream while one waits for its flush (H2D + kernels + D2H).  The better one is the headline.
+        cands = [e2e_pass(ncores, False)]
+        if args.e2e_oversub > 1:
+            cands.append(e2e_pass(ncores * args.e2e_oversub, True))
+        cands.sort(key=lambda r: -r["value"])
+        e2e = cands[0]
+        if len(cands) > 1:
+            e2e["alternative"] = {k: cands[1][k] for k in ("value", "host_threads", "sync", "flush_ms_per_frame")}
         Lo.refh_stream_free(h)
-        assert secs > 0, "e2e decode failed"
-        secs = sharding.max_over_ranks(secs, dev)
-        e2e = {"value": WORLD * ncores * nframes / secs, "unit": "frames/s",
-               "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
-               "host_threads": ncores, "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
-               "flush_ms_per_frame": 1e3 * st.flush_seconds / max(st.frames, 1), "final_frame_hash": int(hsh.value)}
 
     cpu = None
     if RANK == 0 and WORLD == 1 and not args.no_cpu:

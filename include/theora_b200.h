@@ -188,6 +188,11 @@ OCG_API long ocg_launch_count(void);   /* kernels launched by this library so fa
    (67 vs 48 us per 32-frame launch: 4 KB boxes are too small to amortise the
    TMA issue cost), so it is opt-in.  Call before creating contexts. */
 OCG_API void ocg_set_lf_tma(int on);
+/* ocg_ctx_sync wait policy: 0 (default) = cudaStreamSynchronize (the driver
+   spins), 1 = record + wait on a cudaEventBlockingSync event, so the calling
+   thread sleeps and a host that runs more stream threads than cores keeps the
+   cores busy with other streams' entropy decoding during a flush. */
+OCG_API void ocg_set_blocking_sync(int on);
 /* Per-stage device timing with CUDA events on the launching stream.  While
    enabled every stage launch (0 recon+copy, 1 loop filter, 2 borders) is
    bracketed by an event pair; collect() waits for them and returns the summed
@@ -291,6 +296,77 @@ typedef struct ocg_mb_refine_out {
 OCG_API int ocg_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
                                    const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags,
                                    void *stream);
+
+/* ---- whole-frame motion analysis (BASELINE configs[3]) -------------------- */
+/* oc_mcenc_search (mcenc.c:517-548) for EVERY macro block of a frame, in the
+   reference's coding order, with the candidate sets derived on the device from
+   the already-searched neighbours (mcenc.c:90-164) -- the part the per-batch
+   call above leaves to its caller.  The data dependence (a macro block needs
+   analysis_mv[0][frame] and error[frame] of its cneighbors, encode.c:1004-1034,
+   AFTER their half-pel refinement, analyze.c:2486-2489) is honoured by a
+   wave-front: one warp per super-block row and reference frame walks its row
+   in coding order and waits on per-macro-block completion flags of the rows
+   below it; the two reference frames are independent chains.  Per macro block:
+   history rotation (mcenc.c:523-531,534,540-547), sets A/B + median predictor,
+   thresholds (mcenc.c:331-342), square-pattern descent, 4MV descent, final
+   SATD (or SAD at OC_SP_LEVEL_NOSATD), then oc_mcenc_refine1mv where the
+   reference's analysis loop would run it: always against OC_FRAME_PREV in an
+   inter frame (analyze.c:2486), against OC_FRAME_GOLD only for the macro blocks
+   flagged by the caller (that refinement is decided by the host's mode costs,
+   analyze.c:2476-2481).  oc_mcenc_refine4mv (analyze.c:2469) feeds nothing
+   else and runs as one batch for all macro blocks when requested. */
+typedef struct ocg_me_topo {
+  int32_t frag_off[4];   /* frag_buf_offs[mb_maps[mbi][0][0..3]]                        */
+  int32_t cn[4];         /* oc_mb_enc_info.cneighbors (macro-block indices)              */
+  uint8_t ncn;           /* oc_mb_enc_info.ncneighbors                                   */
+  uint8_t valid;         /* mb_modes[mbi]!=OC_MODE_INVALID                               */
+  uint8_t pad[6];
+} ocg_me_topo;           /* 40 bytes */
+
+/* Per-macro-block analysis state, persistent across frames like oc_mb_enc_info
+   (encint.h:352-382).  Vectors use the reference's oc_mv encoding
+   ((x&0xFF)|y*256, half-pel units); index [0] = OC_FRAME_GOLD, [1] = OC_FRAME_PREV. */
+typedef struct ocg_me_mb {
+  int16_t  analysis_mv[3][2]; /* [age][frame]; [0] is refined where refinement ran          */
+  uint16_t error[2];          /* error[frame]: 16x16 SAD of the full-pel winner             */
+  uint32_t satd[2];           /* satd[frame], after refinement where refinement ran         */
+  int16_t  unref_mv[2];       /* analysis_mv[0][frame] as the full-pel search left it       */
+  uint32_t unref_satd[2];     /* satd[frame] as the full-pel search left it                 */
+  int16_t  block_mv[4];       /* full-pel 4MV vectors (OC_FRAME_PREV only)                  */
+  int16_t  ref_mv[4];         /* oc_mcenc_refine4mv result (valid after OCG_ME_REFINE_4MV)  */
+  uint32_t block_satd[4];     /* block_satd[bi] as the full-pel search left it              */
+  uint32_t ref_block_satd[4]; /* block_satd[bi] after oc_mcenc_refine4mv                    */
+  uint8_t  pad[12];
+} ocg_me_mb;                  /* 96 bytes */
+
+#define OCG_ME_REFINE_PREV 1   /* inter frame: oc_mcenc_refine1mv(OC_FRAME_PREV) for every MB   */
+#define OCG_ME_REFINE_4MV  2   /* oc_mcenc_refine4mv for every MB                                */
+#define OCG_ME_NOSATD      4   /* sp_level>=OC_SP_LEVEL_NOSATD: SAD instead of SATD (mcenc.c:233,648) */
+#define OCG_ME_FAST        8   /* sp_level>=OC_SP_LEVEL_FAST_ANALYSIS: no block_mv/block_satd (mcenc.c:506) */
+#define OCG_ME_DROPPED    16   /* _enc->prevframe_dropped (mcenc.c:523)                          */
+
+typedef struct ocg_me ocg_me;
+/* Macro blocks of the frame in the reference's numbering (4 per luma super
+   block, invalid ones included): the array sizes used below. */
+OCG_API int  ocg_me_nmbs(const ocg_geometry *g);
+/* Native restatement of the reference's tables (state.c:300-330 mb_maps,
+   encode.c:967-1048 cneighbors; macro blocks outside the coded region are
+   invalid and never listed as neighbours). */
+OCG_API int  ocg_me_topology(const ocg_geometry *g, ocg_me_topo *topo);
+/* topo may be NULL (derive it) or the caller's copy of the reference's tables. */
+OCG_API int  ocg_me_create(ocg_me **out, ocg_ctx *ctx, const ocg_me_topo *topo);
+OCG_API void ocg_me_destroy(ocg_me *me);
+/* bufs: pool buffer indices of {OC_FRAME_IO, OC_FRAME_PREV_ORIG, OC_FRAME_GOLD_ORIG,
+   OC_FRAME_PREV, OC_FRAME_GOLD}.  gold_refine: HOST array of ocg_me_nmbs bytes
+   (non-zero = refine that macro block's GOLD vector) or NULL.  Asynchronous on
+   the context's stream. */
+OCG_API int  ocg_me_frame(ocg_me *me, const int bufs[5], int flags, const uint8_t *gold_refine);
+/* The same for n independent streams in ONE launch set on `stream`
+   (bufs = n x 5 indices; no GOLD refinement flags). */
+OCG_API int  ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int flags, void *stream);
+/* Copy the state out (after the queued work has finished) / seed it. */
+OCG_API int  ocg_me_read(ocg_me *me, ocg_me_mb *out);
+OCG_API int  ocg_me_write(ocg_me *me, const ocg_me_mb *in);
 
 /* Intra-frame analysis pre-pass (BASELINE config "intra-only encode").  The
    per-block encoder hooks return their result synchronously to serial host

@@ -183,3 +183,117 @@ REFH_API void refh_mcenc_refine(const unsigned char *src, const unsigned char *r
   free(embs);
   free(enc);
 }
+
+/* ---------------------------------------------------------------------- */
+/* Whole-frame motion analysis by the REAL reference: a th_enc_ctx made by
+   th_encode_alloc (its own mb_info/cneighbors, mb_maps, frag_buf_offs), whose
+   six reference buffers are loaded with caller-provided frames, then
+   oc_mcenc_search (lib/mcenc.c:517) for every macro block in coding order and
+   the refinements in the order oc_enc_analyze_inter runs them per macro block
+   (lib/analyze.c:2402, 2469-2489): [refine4mv] [refine1mv GOLD if flagged]
+   [refine1mv PREV].  State (analysis_mv history, error) persists in the
+   context across calls, as in an encoder. */
+typedef struct refh_me_mb {      /* same layout as ocg_me_mb (include/theora_b200.h) */
+  ogg_int16_t  analysis_mv[3][2];
+  ogg_uint16_t error[2];
+  ogg_uint32_t satd[2];
+  ogg_int16_t  unref_mv[2];
+  ogg_uint32_t unref_satd[2];
+  ogg_int16_t  block_mv[4];
+  ogg_int16_t  ref_mv[4];
+  ogg_uint32_t block_satd[4];
+  ogg_uint32_t ref_block_satd[4];
+  unsigned char pad[12];
+} refh_me_mb;
+
+typedef struct refh_me_topo {    /* same layout as ocg_me_topo */
+  ogg_int32_t frag_off[4];
+  ogg_int32_t cn[4];
+  unsigned char ncn, valid, pad[6];
+} refh_me_topo;
+
+REFH_API void *refh_me_open(int fw, int fh, int pixel_fmt) {
+  th_info ti;
+  th_enc_ctx *enc;
+  th_info_init(&ti);
+  ti.frame_width = ti.pic_width = (ogg_uint32_t)fw;
+  ti.frame_height = ti.pic_height = (ogg_uint32_t)fh;
+  ti.fps_numerator = 30; ti.fps_denominator = 1;
+  ti.pixel_fmt = (th_pixel_fmt)pixel_fmt;
+  ti.quality = 32;
+  ti.keyframe_granule_shift = 6;
+  enc = th_encode_alloc(&ti);
+  return enc;
+}
+REFH_API void refh_me_close(void *h) { th_encode_free((th_enc_ctx *)h); }
+REFH_API int refh_me_nmbs(void *h) { return (int)((oc_enc_ctx *)h)->state.nmbs; }
+REFH_API long refh_me_frame_size(void *h) {
+  oc_enc_ctx *enc = (oc_enc_ctx *)h;
+  return (long)(enc->state.ref_frame_bufs[1][0].data - enc->state.ref_frame_bufs[0][0].data);
+}
+
+REFH_API void refh_me_topology(void *h, refh_me_topo *topo) {
+  oc_enc_ctx *enc = (oc_enc_ctx *)h;
+  unsigned mbi;
+  int i;
+  memset(topo, 0, sizeof(*topo) * enc->state.nmbs);
+  for (mbi = 0; mbi < enc->state.nmbs; mbi++) {
+    if (enc->state.mb_modes[mbi] == OC_MODE_INVALID) continue;
+    topo[mbi].valid = 1;
+    for (i = 0; i < 4; i++) topo[mbi].frag_off[i] = (ogg_int32_t)enc->state.frag_buf_offs[enc->state.mb_maps[mbi][0][i]];
+    topo[mbi].ncn = enc->mb_info[mbi].ncneighbors;
+    for (i = 0; i < enc->mb_info[mbi].ncneighbors; i++) topo[mbi].cn[i] = (ogg_int32_t)enc->mb_info[mbi].cneighbors[i];
+  }
+}
+
+/* frames: 5 buffers of refh_me_frame_size bytes in the library's own layout,
+   {IO, PREV_ORIG, GOLD_ORIG, PREV, GOLD}. flags as OCG_ME_*. */
+REFH_API void refh_me_frame(void *h, const unsigned char *const frames[5], int flags,
+                            const unsigned char *gold_refine, refh_me_mb *out) {
+  static const int ROLE[5] = {OC_FRAME_IO, OC_FRAME_PREV_ORIG, OC_FRAME_GOLD_ORIG, OC_FRAME_PREV, OC_FRAME_GOLD};
+  oc_enc_ctx *enc = (oc_enc_ctx *)h;
+  oc_mb_enc_info *embs = enc->mb_info;
+  size_t fsz = (size_t)refh_me_frame_size(h);
+  unsigned mbi;
+  int i;
+  for (i = 0; i < 5; i++) {
+    memcpy(enc->state.ref_frame_handle + (size_t)i * fsz, frames[i], fsz);
+    enc->state.ref_frame_idx[ROLE[i]] = i;
+    enc->state.ref_frame_data[ROLE[i]] = enc->state.ref_frame_bufs[i][0].data;
+  }
+  enc->sp_level = (flags & 4) ? OC_SP_LEVEL_NOSATD : ((flags & 8) ? OC_SP_LEVEL_FAST_ANALYSIS : OC_SP_LEVEL_EARLY_SKIP);
+  enc->prevframe_dropped = (flags & 16) != 0;
+  for (mbi = 0; mbi < enc->state.nmbs; mbi++) {
+    refh_me_mb *o = out + mbi;
+    memset(o, 0, sizeof(*o));
+    if (enc->state.mb_modes[mbi] == OC_MODE_INVALID) continue;
+    oc_mcenc_search(enc, (int)mbi);
+    for (i = 0; i < 2; i++) {
+      o->unref_mv[i] = embs[mbi].analysis_mv[0][i];
+      o->unref_satd[i] = embs[mbi].satd[i];
+    }
+    for (i = 0; i < 4; i++) {
+      o->block_mv[i] = embs[mbi].block_mv[i];
+      o->block_satd[i] = embs[mbi].block_satd[i];
+    }
+    if ((flags & 2) && !(flags & 8)) {
+      oc_mcenc_refine4mv(enc, (int)mbi);
+      for (i = 0; i < 4; i++) {
+        o->ref_mv[i] = embs[mbi].ref_mv[i];
+        o->ref_block_satd[i] = embs[mbi].block_satd[i];
+      }
+    }
+    if (gold_refine != NULL && gold_refine[mbi]) oc_mcenc_refine1mv(enc, (int)mbi, OC_FRAME_GOLD);
+    if (flags & 1) oc_mcenc_refine1mv(enc, (int)mbi, OC_FRAME_PREV);
+  }
+  /* the state the next frame starts from */
+  for (mbi = 0; mbi < enc->state.nmbs; mbi++) {
+    refh_me_mb *o = out + mbi;
+    if (enc->state.mb_modes[mbi] == OC_MODE_INVALID) continue;
+    memcpy(o->analysis_mv, embs[mbi].analysis_mv, sizeof(o->analysis_mv));
+    for (i = 0; i < 2; i++) {
+      o->error[i] = embs[mbi].error[i];
+      o->satd[i] = embs[mbi].satd[i];
+    }
+  }
+}

@@ -46,6 +46,14 @@ REC_DTYPE = np.dtype([("buf_off", "<i4"), ("mv", "<i2"), ("dc", "<i2"), ("coeff_
                       ("rowmask", "u1"), ("last_zzi", "u1"), ("refi", "u1"), ("pli_qti", "u1")])
 ENC_FRAG_DTYPE = np.dtype([("src_off", "<i4"), ("ref_off0", "<i4"), ("ref_off1", "<i4"), ("aux", "<i4")])
 assert REC_DTYPE.itemsize == 16 and ENC_FRAG_DTYPE.itemsize == 16
+ME_TOPO_DTYPE = np.dtype([("frag_off", "<i4", (4,)), ("cn", "<i4", (4,)), ("ncn", "u1"), ("valid", "u1"),
+                          ("pad", "u1", (6,))])
+ME_MB_DTYPE = np.dtype([("analysis_mv", "<i2", (3, 2)), ("error", "<u2", (2,)), ("satd", "<u4", (2,)),
+                        ("unref_mv", "<i2", (2,)), ("unref_satd", "<u4", (2,)), ("block_mv", "<i2", (4,)),
+                        ("ref_mv", "<i2", (4,)), ("block_satd", "<u4", (4,)), ("ref_block_satd", "<u4", (4,)),
+                        ("pad", "u1", (12,))])
+assert ME_TOPO_DTYPE.itemsize == 40 and ME_MB_DTYPE.itemsize == 96
+OCG_ME_REFINE_PREV, OCG_ME_REFINE_4MV, OCG_ME_NOSATD, OCG_ME_FAST, OCG_ME_DROPPED = 1, 2, 4, 8, 16
 
 
 def cls_of_last_zzi(last_zzi):
@@ -143,6 +151,15 @@ _PROTOS = {
     "ocg_set_stage_mask": (None, [C.c_int]),
     "ocg_launch_count": (C.c_long, []),
     "ocg_set_lf_tma": (None, [C.c_int]),
+    "ocg_set_blocking_sync": (None, [C.c_int]),
+    "ocg_me_nmbs": (C.c_int, [C.POINTER(Geometry)]),
+    "ocg_me_topology": (C.c_int, [C.POINTER(Geometry), C.c_void_p]),
+    "ocg_me_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "ocg_me_destroy": (None, [C.c_void_p]),
+    "ocg_me_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
+    "ocg_me_frame_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p]),
+    "ocg_me_read": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocg_me_write": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ocg_profile_enable": (None, [C.c_int]),
     "ocg_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "ocg_enc_metrics_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

@@ -53,6 +53,7 @@ typedef struct ocg_enc_backend {
   int                  ncoded;
   int                  nrows;
   int                  pinned;
+  int                  self_on_device; /* buffer index whose reconstruction has not been copied to the host, or -1 */
   /* source/destination pointer -> fragment index */
   ogg_int32_t         *off2frag;
   ptrdiff_t            off_min;
@@ -158,7 +159,6 @@ static void enc_begin_frame(ocg_enc_backend *b, int nqis) {
 static void enc_flush(ocg_enc_backend *b) {
   oc_theora_state *st = &b->enc->state;
   ocg_dec_frame f;
-  unsigned char *host_self;
   double t0 = enc_now_s();
   int pli;
   b->frame_open = 0;
@@ -174,14 +174,16 @@ static void enc_flush(ocg_enc_backend *b) {
   f.ncoded = b->ncoded;
   f.intra_frame = 1;
   f.ncoeff_rows = b->nrows;
-  host_self = st->ref_frame_handle + (size_t)f.ref_idx[OCG_FRAME_SELF] * (size_t)b->geom.ref_frame_sz;
-  if (ocg_dec_submit(b->ctx, &f, host_self) < 0) enc_fatal("ocg_dec_submit failed");
-  if (ocg_ctx_sync(b->ctx) < 0) enc_fatal("ocg_ctx_sync failed");
+  /* An intra-only encoder never predicts from SELF, so the reconstruction stays
+     on the device (ocg_backend_enc_copy_recon fetches it on demand) and the
+     flush is asynchronous: the staging slots are double-buffered and the next
+     frame's pre-pass queues behind these kernels on the same stream. */
+  if (ocg_dec_submit(b->ctx, &f, NULL) < 0) enc_fatal("ocg_dec_submit failed");
+  b->self_on_device = f.ref_idx[OCG_FRAME_SELF];
   pthread_mutex_lock(&g_estats_lock);
   g_estats.frames++;
   g_estats.coeff_rows += b->nrows;
   g_estats.h2d_bytes += (long)b->geom.nfrags * 16 + (long)b->nrows * 16;
-  g_estats.d2h_bytes += (long)b->geom.ref_frame_sz;
   g_estats.flush_seconds += enc_now_s() - t0;
   pthread_mutex_unlock(&g_estats_lock);
 }
@@ -377,6 +379,7 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   b = (ocg_enc_backend *)calloc(1, sizeof(*b));
   if (b == NULL) return;
   b->enc = _enc;
+  b->self_on_device = -1;
   if (ocg_geometry_init(&b->geom, (int)st->info.frame_width, (int)st->info.frame_height, (int)st->info.pixel_fmt, 6) < 0) {
     fprintf(stderr, "theora_b200 encoder back-end: %s\n", ocg_last_error());
     free(b);
@@ -483,6 +486,15 @@ OCG_API long ocg_backend_enc_copy_recon(th_enc_ctx *_enc, unsigned char *_dst) {
   st = &_enc->state;
   idx = st->ref_frame_idx[OC_FRAME_SELF];
   if (idx < 0) return TH_EINVAL;
+  {
+    ocg_enc_backend *b = enc_backend_of(_enc);
+    if (b != NULL && b->self_on_device == idx) {
+      if (ocg_ctx_download_frame(b->ctx, idx, (unsigned char *)st->ref_frame_handle + (size_t)idx * (size_t)b->geom.ref_frame_sz) < 0 ||
+          ocg_ctx_sync(b->ctx) < 0)
+        return TH_EFAULT;
+      b->self_on_device = -1;
+    }
+  }
   for (pli = 0; pli < 3; pli++) {
     const th_img_plane *p = &st->ref_frame_bufs[idx][pli];
     /* data points at the displayed-bottom row, stride is negative (state.c:622-629) */

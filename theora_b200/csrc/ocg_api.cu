@@ -14,6 +14,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long> g_launches{0};
 std::atomic<int> g_stage_mask{7};
+std::atomic<int> g_blocking_sync{0};
 std::atomic<int> g_use_tma{0}; /* measured slower than per-thread loads on B200 (67 vs 48 us): opt-in */
 
 int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -67,6 +68,7 @@ struct ocg_ctx {
   OcgJobDev *d_job = nullptr;
   ocg_frag_rec *tmpl = nullptr; /* host: every fragment uncoded, buf_off/plane filled in */
   Slot slots[kSlots];
+  cudaEvent_t done = nullptr; /* cudaEventBlockingSync: ocg_ctx_sync can sleep instead of spinning */
   int cur_slot = 0;      /* slot handed out by the last ocg_dec_staging */
   bool staged = false;
 };
@@ -237,6 +239,8 @@ OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
 
 OCG_API void ocg_set_lf_tma(int on) { g_use_tma.store(on ? 1 : 0); }
 
+OCG_API void ocg_set_blocking_sync(int on) { g_blocking_sync.store(on ? 1 : 0); }
+
 OCG_API void ocg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 
 OCG_API int ocg_profile_collect(double ms[3], long launches[3]) {
@@ -331,6 +335,7 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
     if (c->enc->h_tabs) cudaFreeHost(c->enc->h_tabs);
     delete c->enc;
   }
+  if (c->done) cudaEventDestroy(c->done);
   cudaFree(c->frames);
   cudaFree(c->d_recs);
   cudaFree(c->d_rows);
@@ -371,6 +376,7 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
     }                                              \
   } while (0)
   CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUX(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming | cudaEventBlockingSync));
   CUX(cudaMalloc(&c->frames, pool));
   CUX(cudaMemsetAsync(c->frames, 0x80, pool, c->stream));
   ocg_init_device_tables(c->stream);
@@ -421,7 +427,14 @@ OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *c, int buf) {
 OCG_API int ocg_ctx_sync(ocg_ctx *c) {
   if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
   CU(cudaSetDevice(c->device));
-  CU(cudaStreamSynchronize(c->stream));
+  if (g_blocking_sync.load()) {
+    /* the calling thread sleeps until the stream drains: with more stream threads than
+       cores the core runs another stream's entropy decode meanwhile */
+    CU(cudaEventRecord(c->done, c->stream));
+    CU(cudaEventSynchronize(c->done));
+  } else {
+    CU(cudaStreamSynchronize(c->stream));
+  }
   for (Slot &s : c->slots) s.busy = false;
   return OCG_OK;
 }

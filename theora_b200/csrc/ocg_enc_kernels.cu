@@ -14,6 +14,9 @@
  * the host (analyze.c, tokenize.c).
  */
 #include <climits>
+#include <cstring>
+#include <new>
+#include <vector>
 #include "ocg_internal.h"
 
 namespace {
@@ -659,9 +662,549 @@ ocg_mcenc_refine_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__r
   }
 }
 
+/* ------------------------------------------------------------------------ */
+/* Whole-frame motion analysis: oc_mcenc_search (mcenc.c:517-548) for every
+   macro block in coding order, candidates from already-searched neighbours,
+   as a wave-front of warps (one per super-block row and reference frame). */
+struct OcgMeJob {
+  const uint8_t *src;          /* OC_FRAME_IO: buffer + base_off */
+  const uint8_t *ref_full[2];  /* [frame]: the *_ORIG frame searched with SAD */
+  const uint8_t *ref_satd[2];  /* [frame]: the reconstructed reference */
+  const ocg_me_topo *topo;
+  ocg_me_mb *mb;
+  uint32_t *done;              /* [nmbs][2]: == seq once the MB's analysis against that frame is final */
+  const uint8_t *gold_refine;  /* nmbs flags or NULL */
+  int32_t ystride, nhsbs, nvsbs, nmbs, flags;
+  uint32_t seq;
+};
+
+__device__ __forceinline__ int mv_x(int mv) { return (int)(signed char)(mv & 0xFF); }
+__device__ __forceinline__ int mv_y(int mv) { return (int)(short)mv >> 8; }
+__device__ __forceinline__ int mv_make(int x, int y) { return (int)(short)((x & 0xFF) | (y * 256)); }
+__device__ __forceinline__ int mv_add(int a, int b) { return mv_make(mv_x(a) + mv_x(b), mv_y(a) + mv_y(b)); }
+__device__ __forceinline__ int mv_sub(int a, int b) { return mv_make(mv_x(a) - mv_x(b), mv_y(a) - mv_y(b)); }
+__device__ __forceinline__ int clamp31(int v) { return max(-31, min(31, v)); }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+/* oc_mcenc_ysatd_halfpel_mbrefine (mcenc.c:606-664) by the whole warp:
+   lane = site*4 + block.  Returns the refined vector (half-pel) and score. */
+__device__ __forceinline__ void me_refine1(const uint8_t *src, const uint8_t *ref, int ystride, int off,
+                                           int lane, int vx, int vy, uint32_t entry, bool use_sad, int &ox, int &oy,
+                                           uint32_t &oscore) {
+  const int sitei = lane >> 2;
+  uint32_t err = refine_score(src + off, ref + off, ystride, vx, vy, c_sq_dx[sitei], c_sq_dy[sitei], use_sad);
+  err += __shfl_xor_sync(0xFFFFFFFFu, err, 1);
+  err += __shfl_xor_sync(0xFFFFFFFFu, err, 2);
+  uint32_t key_e = err;
+  int key_s = sitei;
+#pragma unroll
+  for (int d = 4; d < 32; d <<= 1) {
+    const uint32_t oe = __shfl_xor_sync(0xFFFFFFFFu, key_e, d);
+    const int os = __shfl_xor_sync(0xFFFFFFFFu, key_s, d);
+    if (oe < key_e || (oe == key_e && os < key_s)) { key_e = oe; key_s = os; }
+  }
+  int dx = 0, dy = 0;
+  oscore = entry;
+  if (key_e < entry) { oscore = key_e; dx = c_sq_dx[key_s]; dy = c_sq_dy[key_s]; }
+  ox = (vx << 1) + dx;
+  oy = (vy << 1) + dy;
+}
+
+__global__ void __launch_bounds__(32)
+ocg_me_wavefront_kernel(const OcgMeJob *__restrict__ jobs) {
+  const OcgMeJob J = jobs[blockIdx.z];
+  const int f = (int)blockIdx.y; /* 0 = OC_FRAME_GOLD, 1 = OC_FRAME_PREV */
+  const int lane = threadIdx.x;
+  const int bi = lane >> 3, row = lane & 7;
+  const int ystride = J.ystride;
+  const bool is_prev = f == 1;
+  const bool nosatd = (J.flags & OCG_ME_NOSATD) != 0;
+  const bool want_blocks = is_prev && (J.flags & OCG_ME_FAST) == 0;
+  const int mbi0 = (int)blockIdx.x * J.nhsbs * 4;
+  for (int k = 0; k < J.nhsbs * 4; k++) {
+    const int mbi = mbi0 + k;
+    const ocg_me_topo *T = J.topo + mbi;
+    if (!T->valid) continue; /* warp-uniform */
+    ocg_me_mb *m = J.mb + mbi;
+    const int off_search = T->frag_off[bi];      /* search: lane = block*8 + row  */
+    const int off_refine = T->frag_off[lane & 3]; /* refine: lane = site*4 + block */
+    const int ncn = T->ncn;
+    /* history rotation, mcenc.c:523-531 / 540-541 (this MB's own values from earlier frames) */
+    const int mv0 = m->analysis_mv[0][f];
+    int mv1 = m->analysis_mv[1][f], mv2 = m->analysis_mv[2][f];
+    int accum;
+    if (is_prev) {
+      accum = (J.flags & OCG_ME_DROPPED) ? mv0 : 0;
+      const int old2 = mv2;
+      mv2 = mv1;
+      mv1 = mv_sub(mv0, old2);
+    } else {
+      accum = mv2;
+      mv2 = mv1;
+      mv1 = mv0;
+      mv1 = mv_sub(mv1, mv2);
+      mv2 = mv_sub(mv2, accum);
+    }
+    unsigned t2 = m->error[f];
+    /* wait for the neighbours' final vectors, then read them around L1 */
+    int cmv = 0;
+    unsigned cerr = 0;
+    if (lane < ncn) {
+      const int n = T->cn[lane];
+      const uint32_t *flag = J.done + (size_t)n * 2 + f;
+      while (ld_acquire_u32(flag) != J.seq) __nanosleep(64);
+      cmv = (int)__ldcg(&J.mb[n].analysis_mv[0][f]);
+      cerr = (unsigned)__ldcg(&J.mb[n].error[f]);
+    }
+    __syncwarp();
+    /* candidate list, one per lane (mcenc.c:90-164): [0] median, [1..ncn] neighbours,
+       accum, clamp(mv1+accum), (0,0) | set B: clamp(2*mv1-mv2+accum) */
+    const int ax = mv_x(accum), ay = mv_y(accum);
+    int candx = 0, candy = 0;
+    if (lane >= 1 && lane <= ncn) {
+      const int v = __shfl_sync(0xFFFFFFFFu, cmv, (lane - 1) & 31);
+      candx = mv_x(v);
+      candy = mv_y(v);
+    } else {
+      (void)__shfl_sync(0xFFFFFFFFu, cmv, 0);
+    }
+    if (lane == ncn + 1) { candx = ax; candy = ay; }
+    if (lane == ncn + 2) { candx = clamp31(mv_x(mv1) + ax); candy = clamp31(mv_y(mv1) + ay); }
+    /* lane ncn+3: (0,0) */
+    const int setb0 = ncn + 4;
+    if (lane == setb0) {
+      candx = clamp31(2 * mv_x(mv1) - mv_x(mv2) + ax);
+      candy = clamp31(2 * mv_y(mv1) - mv_y(mv2) + ay);
+    }
+    const int ncand = setb0 + 1;
+    {
+      /* median of the first three of set A (mcenc.c:130-138) */
+      int a0x = __shfl_sync(0xFFFFFFFFu, candx, 1), a1x = __shfl_sync(0xFFFFFFFFu, candx, 2), a2x = __shfl_sync(0xFFFFFFFFu, candx, 3);
+      int a0y = __shfl_sync(0xFFFFFFFFu, candy, 1), a1y = __shfl_sync(0xFFFFFFFFu, candy, 2), a2y = __shfl_sync(0xFFFFFFFFu, candy, 3);
+      const int medx = max(min(a0x, a1x), min(max(a0x, a1x), a2x));
+      const int medy = max(min(a0y, a1y), min(max(a0y, a1y), a2y));
+      if (lane == 0) { candx = medx; candy = medy; }
+    }
+    /* early-termination threshold base: own previous error and the first <=3 neighbours' (mcenc.c:337-341) */
+    {
+      const int ncs = min(3, ncn);
+      for (int i = 0; i < ncs; i++) t2 = max(t2, __shfl_sync(0xFFFFFFFFu, cerr, i));
+    }
+    /* ---- full-pel search, mcenc.c:305-499 ---- */
+    McWarp w;
+    const int po = off_search + row * ystride;
+    w.ref = J.ref_full[f] + po;
+    w.src = ld8u(J.src + po);
+    w.ystride = ystride;
+    w.hit = 0;
+    w.lane = lane;
+    unsigned berr, err;
+    int cx = __shfl_sync(0xFFFFFFFFu, candx, 0) / 2, cy = __shfl_sync(0xFFFFFFFFu, candy, 0) / 2;
+    mc_visited(w, cx, cy);
+    unsigned best_err = mc_sad16(w, cx, cy, berr);
+    int bx = cx, by = cy;
+    unsigned blk_err = berr;
+    int blk_x = cx, blk_y = cy;
+    if (best_err > 256u) {
+      t2 += (t2 >> 4) + 64u;
+      int ci = 1;
+      for (; ci < setb0; ci++) {
+        cx = __shfl_sync(0xFFFFFFFFu, candx, ci) / 2;
+        cy = __shfl_sync(0xFFFFFFFFu, candy, ci) / 2;
+        if (mc_visited(w, cx, cy)) continue;
+        err = mc_sad16(w, cx, cy, berr);
+        if (err < best_err) { best_err = err; bx = cx; by = cy; }
+        if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+      }
+      if (best_err > t2) {
+        for (; ci < ncand; ci++) {
+          cx = __shfl_sync(0xFFFFFFFFu, candx, ci) / 2;
+          cy = __shfl_sync(0xFFFFFFFFu, candy, ci) / 2;
+          if (mc_visited(w, cx, cy)) continue;
+          err = mc_sad16(w, cx, cy, berr);
+          if (err < best_err) { best_err = err; bx = cx; by = cy; }
+          if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+        }
+        if (best_err > t2) {
+          for (;;) {
+            int sx = 0, sy = 0;
+            bool moved = false;
+            for (int dy = -1; dy <= 1; dy++) {
+              for (int dx = -1; dx <= 1; dx++) {
+                if ((dx | dy) == 0) continue;
+                if ((bx <= -15 && dx < 0) || (bx >= 15 && dx > 0) || (by <= -15 && dy < 0) || (by >= 15 && dy > 0)) continue;
+                cx = bx + dx;
+                cy = by + dy;
+                if (mc_visited(w, cx, cy)) continue;
+                err = mc_sad16(w, cx, cy, berr);
+                if (err < best_err) { best_err = err; sx = dx; sy = dy; moved = true; }
+                if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+              }
+            }
+            if (!moved) break;
+            bx += sx;
+            by += sy;
+          }
+          if (is_prev) {
+            const unsigned t4 = t2 >> 2;
+            for (int b = 0; b < 4; b++) {
+              if (__shfl_sync(0xFFFFFFFFu, blk_err, b * 8) <= t4) continue;
+              for (;;) {
+                const int ox = __shfl_sync(0xFFFFFFFFu, blk_x, b * 8), oy = __shfl_sync(0xFFFFFFFFu, blk_y, b * 8);
+                for (int dy = -1; dy <= 1; dy++) {
+                  for (int dx = -1; dx <= 1; dx++) {
+                    if ((dx | dy) == 0) continue;
+                    if ((ox <= -15 && dx < 0) || (ox >= 15 && dx > 0) || (oy <= -15 && dy < 0) || (oy >= 15 && dy > 0)) continue;
+                    cx = ox + dx;
+                    cy = oy + dy;
+                    if (mc_visited(w, cx, cy)) continue;
+                    err = mc_sad16(w, cx, cy, berr);
+                    if (err < best_err) { best_err = err; bx = cx; by = cy; }
+                    if (berr < blk_err) { blk_err = berr; blk_x = cx; blk_y = cy; }
+                  }
+                }
+                if (__shfl_sync(0xFFFFFFFFu, blk_x, b * 8) == ox && __shfl_sync(0xFFFFFFFFu, blk_y, b * 8) == oy) break;
+              }
+            }
+          }
+        }
+      }
+    }
+    /* ---- final score on the reconstructed reference, mcenc.c:500-514 ---- */
+    const uint8_t *rs = J.ref_satd[f] + po;
+    unsigned s_mb;
+    if (nosatd) {
+      const uint2 r = ld8u(rs + bx + by * ystride);
+      s_mb = __vsadu4(w.src.x, r.x) + __vsadu4(w.src.y, r.y);
+      s_mb += __shfl_xor_sync(0xFFFFFFFFu, s_mb, 4);
+      s_mb += __shfl_xor_sync(0xFFFFFFFFu, s_mb, 2);
+      s_mb += __shfl_xor_sync(0xFFFFFFFFu, s_mb, 1);
+    } else {
+      s_mb = mc_satd_block(w.src, ld8u(rs + bx + by * ystride), row);
+    }
+    unsigned tot = s_mb + __shfl_xor_sync(0xFFFFFFFFu, s_mb, 8);
+    tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 16);
+    unsigned s_blk = 0;
+    if (want_blocks) s_blk = mc_satd_block(w.src, ld8u(rs + blk_x + blk_y * ystride), row); /* warp-uniform branch */
+    int fmv = mv_make(bx * 2, by * 2);
+    uint32_t fsatd = tot;
+    /* history as oc_mcenc_search leaves it (mcenc.c:534, 546-547) */
+    int h1, h2;
+    if (is_prev) { h2 = accum; h1 = mv1; }
+    else { h2 = mv_add(mv2, accum); h1 = mv_add(mv1, h2); }
+    if (lane == 0) {
+      m->analysis_mv[1][f] = (int16_t)h1;
+      m->analysis_mv[2][f] = (int16_t)h2;
+      m->error[f] = (uint16_t)best_err;
+      m->unref_mv[f] = (int16_t)fmv;
+      m->unref_satd[f] = tot;
+    }
+    if (want_blocks && row == 0) {
+      m->block_mv[bi] = (int16_t)mv_make(blk_x * 2, blk_y * 2);
+      m->block_satd[bi] = s_blk;
+    }
+    /* ---- oc_mcenc_refine1mv where the analysis loop runs it (analyze.c:2476-2489) ---- */
+    bool refine = is_prev ? (J.flags & OCG_ME_REFINE_PREV) != 0
+                          : (J.gold_refine != nullptr && J.gold_refine[mbi] != 0);
+    if (refine) {
+      int rx, ry;
+      uint32_t rscore;
+      me_refine1(J.src, J.ref_satd[f], ystride, off_refine, lane, bx, by, tot, nosatd, rx, ry, rscore);
+      fmv = mv_make(rx, ry);
+      fsatd = rscore;
+    }
+    if (lane == 0) {
+      m->analysis_mv[0][f] = (int16_t)fmv;
+      m->satd[f] = fsatd;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_u32(J.done + (size_t)mbi * 2 + f, J.seq);
+  }
+}
+
+/* oc_mcenc_refine4mv (mcenc.c:763-791) for every macro block of the frame:
+   one warp per MB, lane = block*8 + site. */
+__global__ void __launch_bounds__(128)
+ocg_me_refine4_kernel(const OcgMeJob *__restrict__ jobs) {
+  const OcgMeJob J = jobs[blockIdx.y];
+  const int mbi = (int)(blockIdx.x * 4 + (threadIdx.x >> 5));
+  if (mbi >= J.nmbs) return;
+  const ocg_me_topo *T = J.topo + mbi;
+  if (!T->valid) return;
+  const int lane = threadIdx.x & 31;
+  const int bi = lane >> 3, sitei = lane & 7;
+  ocg_me_mb *m = J.mb + mbi;
+  const int off = T->frag_off[bi];
+  const int bmv = m->block_mv[bi];
+  const int vx = mv_x(bmv) / 2, vy = mv_y(bmv) / 2;
+  const uint32_t err = refine_score(J.src + off, J.ref_satd[1] + off, J.ystride, vx, vy, c_sq_dx[sitei], c_sq_dy[sitei], false);
+  uint32_t key_e = err;
+  int key_s = sitei;
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+    const uint32_t oe = __shfl_xor_sync(0xFFFFFFFFu, key_e, d);
+    const int os = __shfl_xor_sync(0xFFFFFFFFu, key_s, d);
+    if (oe < key_e || (oe == key_e && os < key_s)) { key_e = oe; key_s = os; }
+  }
+  if (sitei == 0) {
+    const uint32_t entry = m->block_satd[bi];
+    int dx = 0, dy = 0;
+    uint32_t best = entry;
+    if (key_e < entry) { best = key_e; dx = c_sq_dx[key_s]; dy = c_sq_dy[key_s]; }
+    m->ref_mv[bi] = (int16_t)mv_make((vx << 1) + dx, (vy << 1) + dy);
+    m->ref_block_satd[bi] = best;
+  }
+}
+
 } /* namespace */
 
 extern "C" {
+
+/* ---- whole-frame motion analysis ------------------------------------------ */
+struct ocg_me {
+  ocg_ctx *ctx = nullptr;
+  int nmbs = 0, nhsbs = 0, nvsbs = 0;
+  ocg_me_topo *d_topo = nullptr;
+  ocg_me_mb *d_mb = nullptr;
+  uint32_t *d_done = nullptr;
+  uint8_t *d_gold = nullptr;
+  uint8_t *h_gold = nullptr;   /* pinned */
+  OcgMeJob *d_job = nullptr;
+  OcgMeJob *h_job = nullptr;   /* pinned */
+  cudaEvent_t job_used = nullptr;
+  bool job_busy = false;
+  uint32_t seq = 0;
+};
+
+/* batch scratch (one launch set for many streams), process-wide like the decoder's */
+static struct {
+  OcgMeJob *d = nullptr, *h = nullptr;
+  int cap = 0;
+  cudaEvent_t used = nullptr;
+  bool busy = false;
+} g_me_batch;
+
+OCG_API int ocg_me_nmbs(const ocg_geometry *g) {
+  if (g == nullptr) return OCG_EFAULT;
+  return ((g->planes[0].nhfrags + 3) >> 2) * ((g->planes[0].nvfrags + 3) >> 2) * 4;
+}
+
+OCG_API int ocg_me_topology(const ocg_geometry *g, ocg_me_topo *topo) {
+  if (g == nullptr || topo == nullptr) return OCG_EFAULT;
+  const ocg_plane_geom &p = g->planes[0];
+  const int nhsbs = (p.nhfrags + 3) >> 2, nvsbs = (p.nvfrags + 3) >> 2;
+  const int nhmbs = nhsbs << 1, nvmbs = nvsbs << 1; /* state.c:501-502: counted in whole super blocks */
+  static const unsigned char MBMAP[2][2] = {{0, 3}, {1, 2}};           /* internal.c:63 */
+  static const unsigned char NCN[4] = {4, 3, 2, 4};                    /* encode.c:994 */
+  static const signed char CDX[4][4] = {{-1, 0, 1, -1}, {-1, 0, -1, 0}, {-1, -1, 0, 0}, {-1, 0, 0, 1}};
+  static const signed char CDY[4][4] = {{0, -1, -1, -1}, {0, -1, -1, 0}, {0, -1, 0, 0}, {0, -1, 1, -1}};
+  const int nmbs = nhsbs * nvsbs * 4;
+  memset(topo, 0, sizeof(*topo) * (size_t)nmbs);
+  for (int sby = 0; sby < nvsbs; sby++)
+    for (int sbx = 0; sbx < nhsbs; sbx++)
+      for (int q = 0; q < 4; q++) {
+        const int mbi = (sby * nhsbs + sbx) * 4 + q;
+        const int mbx = 2 * sbx + (q >> 1), mby = 2 * sby + (((q + 1) >> 1) & 1);
+        if (2 * mbx >= p.nhfrags || 2 * mby >= p.nvfrags) continue; /* state.c:318: outside the coded region */
+        ocg_me_topo &t = topo[mbi];
+        t.valid = 1;
+        for (int i = 0; i < 2; i++)
+          for (int j = 0; j < 2; j++)
+            t.frag_off[i << 1 | j] = (int32_t)(p.plane_off + (int64_t)(2 * mby + i) * 8 * p.ystride + (2 * mbx + j) * 8);
+      }
+  for (int sby = 0; sby < nvsbs; sby++)
+    for (int sbx = 0; sbx < nhsbs; sbx++)
+      for (int q = 0; q < 4; q++) {
+        const int mbi = (sby * nhsbs + sbx) * 4 + q;
+        if (!topo[mbi].valid) continue;
+        const int mbx = 2 * sbx + (q >> 1), mby = 2 * sby + (((q + 1) >> 1) & 1);
+        for (int ni = 0; ni < NCN[q]; ni++) {
+          const int nx = mbx + CDX[q][ni], ny = mby + CDY[q][ni];
+          if (nx < 0 || nx >= nhmbs || ny < 0 || ny >= nvmbs) continue;
+          /* encode.c:1031 */
+          const int nmbi = (ny & ~1) * nhmbs + ((nx & ~1) << 1) + MBMAP[ny & 1][nx & 1];
+          if (nmbi < 0 || nmbi >= nmbs || !topo[nmbi].valid) continue;
+          topo[mbi].cn[topo[mbi].ncn++] = nmbi;
+        }
+      }
+  return OCG_OK;
+}
+
+OCG_API void ocg_me_destroy(ocg_me *me) {
+  if (me == nullptr) return;
+  if (me->ctx != nullptr) ocg_ctx_sync(me->ctx);
+  cudaFree(me->d_topo);
+  cudaFree(me->d_mb);
+  cudaFree(me->d_done);
+  cudaFree(me->d_gold);
+  cudaFree(me->d_job);
+  if (me->h_gold) cudaFreeHost(me->h_gold);
+  if (me->h_job) cudaFreeHost(me->h_job);
+  if (me->job_used) cudaEventDestroy(me->job_used);
+  delete me;
+}
+
+#define ME_CU(call)                                   \
+  do {                                                \
+    if ((call) != cudaSuccess) {                      \
+      cudaGetLastError();                             \
+      ocg_me_destroy(me);                             \
+      return OCG_ECUDA;                               \
+    }                                                 \
+  } while (0)
+
+OCG_API int ocg_me_create(ocg_me **out, ocg_ctx *ctx, const ocg_me_topo *topo) {
+  if (out == nullptr || ctx == nullptr) return OCG_EFAULT;
+  *out = nullptr;
+  const ocg_geometry *g = ocg_ctx_geometry(ctx);
+  if (g->nrefs < 5) return OCG_EINVAL; /* IO + two originals + two reconstructions */
+  ocg_me *me = new (std::nothrow) ocg_me();
+  if (me == nullptr) return OCG_ENOMEM;
+  me->ctx = ctx;
+  me->nhsbs = (g->planes[0].nhfrags + 3) >> 2;
+  me->nvsbs = (g->planes[0].nvfrags + 3) >> 2;
+  me->nmbs = me->nhsbs * me->nvsbs * 4;
+  const size_t n = (size_t)me->nmbs;
+  std::vector<ocg_me_topo> own;
+  if (topo == nullptr) {
+    own.resize(n);
+    ocg_me_topology(g, own.data());
+    topo = own.data();
+  }
+  /* the wave-front only ever waits on macro blocks that precede it in coding order */
+  for (size_t i = 0; i < n; i++)
+    for (int k = 0; k < topo[i].ncn; k++)
+      if (topo[i].ncn > 4 || topo[i].cn[k] < 0 || (size_t)topo[i].cn[k] >= i || !topo[topo[i].cn[k]].valid) {
+        delete me;
+        return OCG_EINVAL;
+      }
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(ctx);
+  ME_CU(cudaMalloc(&me->d_topo, n * sizeof(ocg_me_topo)));
+  ME_CU(cudaMalloc(&me->d_mb, n * sizeof(ocg_me_mb)));
+  ME_CU(cudaMalloc(&me->d_done, n * 2 * sizeof(uint32_t)));
+  ME_CU(cudaMalloc(&me->d_gold, n));
+  ME_CU(cudaMalloc(&me->d_job, sizeof(OcgMeJob)));
+  ME_CU(cudaHostAlloc(&me->h_gold, n, cudaHostAllocDefault));
+  ME_CU(cudaHostAlloc(&me->h_job, sizeof(OcgMeJob), cudaHostAllocDefault));
+  ME_CU(cudaEventCreateWithFlags(&me->job_used, cudaEventDisableTiming));
+  ME_CU(cudaMemcpyAsync(me->d_topo, topo, n * sizeof(ocg_me_topo), cudaMemcpyHostToDevice, st));
+  ME_CU(cudaMemsetAsync(me->d_mb, 0, n * sizeof(ocg_me_mb), st));
+  ME_CU(cudaMemsetAsync(me->d_done, 0, n * 2 * sizeof(uint32_t), st));
+  ME_CU(cudaStreamSynchronize(st)); /* `own` goes out of scope */
+  *out = me;
+  return OCG_OK;
+}
+#undef ME_CU
+
+static int me_fill_job(ocg_me *me, const int bufs[5], int flags, bool gold, OcgMeJob *j) {
+  const ocg_geometry *g = ocg_ctx_geometry(me->ctx);
+  const uint8_t *b[5];
+  for (int i = 0; i < 5; i++) {
+    const uint8_t *p = (const uint8_t *)ocg_ctx_frame_devptr(me->ctx, bufs[i]);
+    if (p == nullptr) return OCG_EINVAL;
+    b[i] = p + g->base_off;
+  }
+  j->src = b[0];
+  j->ref_full[1] = b[1]; /* OC_FRAME_PREV <- PREV_ORIG */
+  j->ref_full[0] = b[2]; /* OC_FRAME_GOLD <- GOLD_ORIG */
+  j->ref_satd[1] = b[3];
+  j->ref_satd[0] = b[4];
+  j->topo = me->d_topo;
+  j->mb = me->d_mb;
+  j->done = me->d_done;
+  j->gold_refine = gold ? me->d_gold : nullptr;
+  j->ystride = g->planes[0].ystride;
+  j->nhsbs = me->nhsbs;
+  j->nvsbs = me->nvsbs;
+  j->nmbs = me->nmbs;
+  j->flags = flags;
+  j->seq = ++me->seq;
+  return OCG_OK;
+}
+
+static int me_launch(const OcgMeJob *d_jobs, int n, int nvsbs, int nmbs, int flags, cudaStream_t st) {
+  ocg_me_wavefront_kernel<<<dim3((unsigned)nvsbs, 2, (unsigned)n), 32, 0, st>>>(d_jobs);
+  ocg_count_launch(1);
+  if ((flags & OCG_ME_REFINE_4MV) && !(flags & OCG_ME_FAST)) {
+    ocg_me_refine4_kernel<<<dim3((unsigned)((nmbs + 3) / 4), (unsigned)n), 128, 0, st>>>(d_jobs);
+    ocg_count_launch(1);
+  }
+  return cudaGetLastError() == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+OCG_API int ocg_me_frame(ocg_me *me, const int bufs[5], int flags, const uint8_t *gold_refine) {
+  if (me == nullptr || bufs == nullptr) return OCG_EFAULT;
+  if (flags & ~31) return OCG_EINVAL;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
+  if (me->job_busy) {
+    if (cudaEventSynchronize(me->job_used) != cudaSuccess) return OCG_ECUDA;
+    me->job_busy = false;
+  }
+  int r = me_fill_job(me, bufs, flags, gold_refine != nullptr, me->h_job);
+  if (r < 0) return r;
+  if (gold_refine != nullptr) {
+    memcpy(me->h_gold, gold_refine, (size_t)me->nmbs);
+    if (cudaMemcpyAsync(me->d_gold, me->h_gold, (size_t)me->nmbs, cudaMemcpyHostToDevice, st) != cudaSuccess) return OCG_ECUDA;
+  }
+  if (cudaMemcpyAsync(me->d_job, me->h_job, sizeof(OcgMeJob), cudaMemcpyHostToDevice, st) != cudaSuccess) return OCG_ECUDA;
+  cudaEventRecord(me->job_used, st);
+  me->job_busy = true;
+  return me_launch(me->d_job, 1, me->nvsbs, me->nmbs, flags, st);
+}
+
+OCG_API int ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int flags, void *stream) {
+  if (mes == nullptr || bufs == nullptr) return OCG_EFAULT;
+  if (n <= 0 || (flags & ~31)) return OCG_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_me_batch.busy) {
+    if (cudaEventSynchronize(g_me_batch.used) != cudaSuccess) return OCG_ECUDA;
+    g_me_batch.busy = false;
+  }
+  if (g_me_batch.cap < n) {
+    if (g_me_batch.d) cudaFree(g_me_batch.d);
+    if (g_me_batch.h) cudaFreeHost(g_me_batch.h);
+    g_me_batch.d = g_me_batch.h = nullptr;
+    g_me_batch.cap = 0;
+    if (cudaMalloc(&g_me_batch.d, sizeof(OcgMeJob) * (size_t)n) != cudaSuccess) return OCG_ECUDA;
+    if (cudaHostAlloc(&g_me_batch.h, sizeof(OcgMeJob) * (size_t)n, cudaHostAllocDefault) != cudaSuccess) return OCG_ECUDA;
+    if (g_me_batch.used == nullptr && cudaEventCreateWithFlags(&g_me_batch.used, cudaEventDisableTiming) != cudaSuccess)
+      return OCG_ECUDA;
+    g_me_batch.cap = n;
+  }
+  for (int i = 0; i < n; i++) {
+    if (mes[i] == nullptr || mes[i]->nmbs != mes[0]->nmbs || mes[i]->nvsbs != mes[0]->nvsbs) return OCG_EINVAL;
+    int r = me_fill_job(mes[i], bufs + 5 * i, flags, false, g_me_batch.h + i);
+    if (r < 0) return r;
+  }
+  if (cudaMemcpyAsync(g_me_batch.d, g_me_batch.h, sizeof(OcgMeJob) * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return OCG_ECUDA;
+  cudaEventRecord(g_me_batch.used, st);
+  g_me_batch.busy = true;
+  return me_launch(g_me_batch.d, n, mes[0]->nvsbs, mes[0]->nmbs, flags, st);
+}
+
+OCG_API int ocg_me_read(ocg_me *me, ocg_me_mb *out) {
+  if (me == nullptr || out == nullptr) return OCG_EFAULT;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
+  if (cudaMemcpyAsync(out, me->d_mb, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
+  return cudaStreamSynchronize(st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+OCG_API int ocg_me_write(ocg_me *me, const ocg_me_mb *in) {
+  if (me == nullptr || in == nullptr) return OCG_EFAULT;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
+  if (cudaMemcpyAsync(me->d_mb, in, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyHostToDevice, st) != cudaSuccess) return OCG_ECUDA;
+  return cudaStreamSynchronize(st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
 
 OCG_API int ocg_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
                                    const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags,
