@@ -295,6 +295,125 @@ def bench_encode_kernels(torch, dev, peak, nframes=40):
     return out
 
 
+def bench_me_frame(torch, dev, ncores, streams_n=64, nframes=4):
+    """BASELINE configs[3] analysis front-end: oc_mcenc_search + refinements for EVERY macro block of
+    1080p frames (both reference frames, half-pel refinement, 4MV), `streams_n` independent streams per
+    launch set on the device, next to the unmodified reference running the same loop
+    (oc_mcenc_search/refine1mv/refine4mv inside a th_encode_alloc context) on the host cores.
+    Device inputs are resident in HBM; results are compared bit for bit on stream 0."""
+    import theora_b200 as T
+    from theora_b200 import abi
+    tdir = os.path.join(ROOT, "tests")
+    if tdir not in sys.path:
+        sys.path.insert(0, tdir)
+    import megen
+    import support as S
+    L = abi.lib()
+    fw, fh = 1920, 1088
+    g = S.make_geometry(fw, fh, 0, 6)
+    rng = np.random.default_rng(11)
+    orig, recon = megen.scene_buffers(g, rng, nframes + 1, motion=(3, 1))
+    n = L.ocg_me_nmbs(C.byref(g))
+    flags = abi.OCG_ME_REFINE_PREV | abi.OCG_ME_REFINE_4MV
+    ctxs, mes = [], []
+    for _ in range(streams_n):
+        ctx = T.Context(g, dev.index or 0)
+        me = C.c_void_p()
+        abi.check(L.ocg_me_create(C.byref(me), ctx.h, None), "ocg_me_create")
+        ctxs.append(ctx)
+        mes.append(me)
+    arr = (C.c_void_p * streams_n)(*[m.value for m in mes])
+    bufs = (C.c_int * (5 * streams_n))(*([0, 1, 2, 3, 4] * streams_n))
+    st = ctxs[0].stream
+    stream = torch.cuda.ExternalStream(st, device=dev)
+    zero = np.zeros(n, abi.ME_MB_DTYPE)
+
+    def load(t):
+        for ctx in ctxs:
+            for role, buf in enumerate([orig[t], orig[t - 1], orig[0], recon[t - 1], recon[0]]):
+                ctx.upload_frame(role, buf)
+            ctx.sync()
+
+    # timed: frame t=2 (history from frame 1 present), repeated from the same starting state
+    load(1)
+    abi.check(L.ocg_me_frame_batch(arr, bufs, streams_n, flags, st), "ocg_me_frame_batch")
+    ctxs[0].sync()
+    state1 = np.zeros(n, abi.ME_MB_DTYPE)
+    abi.check(L.ocg_me_read(mes[0], state1.ctypes.data), "read")
+    load(2)
+    times = []
+    for rep in range(5):
+        for me in mes:
+            abi.check(L.ocg_me_write(me, state1.ctypes.data), "write")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            abi.check(L.ocg_me_frame_batch(arr, bufs, streams_n, flags, st), "ocg_me_frame_batch")
+            e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times[1:]))
+    got = np.zeros(n, abi.ME_MB_DTYPE)
+    abi.check(L.ocg_me_read(mes[0], got.ctypes.data), "read")
+    # one stream alone: the latency of the wave-front
+    lat = []
+    one = (C.c_void_p * 1)(mes[0].value)
+    for rep in range(4):
+        abi.check(L.ocg_me_write(mes[0], state1.ctypes.data), "write")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            abi.check(L.ocg_me_frame_batch(one, bufs, 1, flags, st), "ocg_me_frame_batch")
+            e1.record()
+        e1.synchronize()
+        lat.append(e0.elapsed_time(e1))
+    for me in mes:
+        L.ocg_me_destroy(me)
+    for ctx in ctxs:
+        ctx.close()
+    out = {"workload": "1920x1088 luma, %d macro blocks/frame, oc_mcenc_search (PREV+GOLD) + refine1mv(PREV) + refine4mv, "
+           "global motion (3,1) px/frame + noise" % int(n), "streams_per_launch": streams_n,
+           "ms_per_launch": ms, "frames_per_s": streams_n / (ms * 1e-3),
+           "macro_blocks_per_s": streams_n * 8160 / (ms * 1e-3), "single_stream_latency_ms": float(np.median(lat[1:]))}
+    if S.ref_available("c"):
+        kind = "asm" if S.ref_available("asm") else "c"
+        R = megen.bind_ref_me(S.ref(kind))
+        nthr = ncores
+        handles = [R.refh_me_open(fw, fh, 0) for _ in range(nthr)]
+        outs = [np.zeros(n, abi.ME_MB_DTYPE) for _ in range(nthr)]
+
+        def frame(i, t):
+            fr = [orig[t], orig[t - 1], orig[0], recon[t - 1], recon[0]]
+            ptrs = (C.c_void_p * 5)(*[f.ctypes.data for f in fr])
+            R.refh_me_frame(handles[i], ptrs, flags, None, outs[i].ctypes.data)
+
+        def worker(i, secs):
+            frame(i, 1)
+            t0 = time.perf_counter()
+            frame(i, 2)
+            secs[i] = time.perf_counter() - t0
+        secs = [0.0] * nthr
+        th = [threading.Thread(target=worker, args=(i, secs)) for i in range(nthr)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for hnd in handles:
+            R.refh_me_close(hnd)
+        topo = np.zeros(n, abi.ME_TOPO_DTYPE)
+        L.ocg_me_topology(C.byref(g), topo.ctypes.data)
+        try:
+            megen.assert_me_equal(got, outs[0], topo["valid"], flags, "bench")
+            same = True
+        except AssertionError:
+            same = False
+        out["cpu_baseline"] = {"frames_per_s": nthr / max(secs), "cores": nthr, "kind": ("reference" if kind == "asm" else "reference (C path)") +
+                               " (each call also copies the five 3.3 MB frames into the context)", "ms_per_frame_per_core": 1e3 * float(np.mean(secs))}
+        out["identical_to_reference"] = same
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -545,6 +664,13 @@ def main():
         except Exception as e:  # informational section: never take the headline down with it
             enc = {"error": repr(e)}
 
+    me_frame = None
+    if RANK == 0 and not args.no_encode_kernels:
+        try:
+            me_frame = bench_me_frame(torch, dev, ncores)
+        except Exception as e:
+            me_frame = {"error": repr(e)}
+
     enc_intra = None
     if RANK == 0 and WORLD == 1 and not args.no_e2e and not args.no_cpu:
         try:
@@ -562,7 +688,7 @@ def main():
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
                            "parallelism": "independent streams, %d per GPU" % S},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
-                "encode_intra": enc_intra,
+                "encode_intra": enc_intra, "motion_analysis": me_frame,
                 "gpu_launches": int(launches),
                 "clocks": clocks}
         emit(line)

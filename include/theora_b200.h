@@ -218,6 +218,9 @@ typedef struct ocg_enc_frag {
 #define OCG_MET_INTRA_SAD  4  /* oc_enc_frag_intra_sad_c (encfrag.c:86)                                    */
 #define OCG_MET_BORDER_SSD 5  /* oc_enc_frag_border_ssd_c (encfrag.c:352): the 64-bit pixel mask (bit i = row
                                  i>>3, column i&7 in traversal order) travels in ref_off1 (low) / aux (high) */
+#define OCG_MET_ACTIVITY   6  /* oc_mb_activity per luma block (analyze.c:1167-1234): out = activity (flat clamp,
+                                 edge test, act_th*(act/act_th)^0.7 via mathops.c:294-313), dc = pixel sum (the
+                                 block's share of the function's `luma` return value); reads a 10x10 window */
 
 /* All encoder entry points take DEVICE pointers for frames and lists (the
    caller owns residency) and run on `stream`. */

@@ -617,6 +617,57 @@ OCO_EXPORT void oco_frag_copy2(uint8_t *dst, const uint8_t *s1, const uint8_t *s
 }
 
 /* ---- batch forms mirroring the C-ABI ---- */
+
+/* mathops.c:294-313 */
+static uint32_t oco_bexp32_q10(int z) {
+  int ipart = z >> 10;
+  unsigned n = (unsigned)(z & 1023) << 4;
+  n = (n * ((n * ((n * ((n * 3548u >> 15) + 6817u) >> 15) + 15823u) >> 15) + 22708u) >> 15) + 16384u;
+  return 14 - ipart > 0 ? (n + (1u << (13 - ipart))) >> (14 - ipart) : n << (ipart - 14);
+}
+static int oco_blog32_q10(uint32_t w) {
+  int ipart = 0, n, fpart;
+  uint32_t v = w;
+  if (w == 0) return -1;
+  while (v) { ipart++; v >>= 1; }
+  n = (int)(ipart - 16 > 0 ? w >> (ipart - 16) : w << (16 - ipart)) - 32768 - 16384;
+  fpart = (n * ((n * ((n * ((n * -1402 >> 15) + 2546) >> 15) - 5216) >> 15) + 15745) >> 15) - 6793;
+  return (ipart << 10) + (fpart >> 4);
+}
+
+/* analyze.c:1167-1234, one luma block: returns the activity, *sum = pixel sum */
+OCO_EXPORT unsigned oco_block_activity(const uint8_t *src, int ystride, int *sum) {
+  const uint8_t *s = src;
+  unsigned x = 0, x2 = 0, act;
+  int i, j;
+  for (i = 0; i < 8; i++) {
+    for (j = 0; j < 8; j++) { unsigned c = s[j]; x += c; x2 += c * c; }
+    s += ystride;
+  }
+  if (sum) *sum = (int)x;
+  act = (x2 << 6) - x * x;
+  if (act < 8u << 12) return act < (5u << 12) ? act : (5u << 12);
+  {
+    unsigned e1 = 0, e2 = 0, e3 = 0, e4 = 0, emax;
+    s = src - 1;
+    for (i = 0; i < 8; i++) {
+      const uint8_t *u = s - ystride, *d = s + ystride;
+      for (j = 0; j < 8; j++) {
+        e1 += (unsigned)abs(((s[j + 2] - s[j]) << 1) + u[j + 2] - u[j] + d[j + 2] - d[j]);
+        e2 += (unsigned)abs(((d[j + 1] - u[j + 1]) << 1) + d[j] - u[j] + d[j + 2] - u[j + 2]);
+        e3 += (unsigned)abs(((d[j + 2] - u[j]) << 1) + d[j + 1] - s[j] + s[j + 2] - u[j + 1]);
+        e4 += (unsigned)abs(((d[j] - u[j + 2]) << 1) + d[j + 1] - s[j + 2] + s[j] - u[j + 1]);
+      }
+      s += ystride;
+    }
+    emax = e1 > e2 ? e1 : e2;
+    if (e3 > emax) emax = e3;
+    if (e4 > emax) emax = e4;
+    if (5 * emax > 2 * (e1 + e2 + e3 + e4)) act = oco_bexp32_q10(0x394A + (7 * (oco_blog32_q10(act) - 0x394A + 5) / 10));
+  }
+  return act;
+}
+
 OCO_EXPORT void oco_enc_metrics_batch(int metric, const uint8_t *src_base, const uint8_t *ref_base, int ystride,
                                       const ocg_enc_frag *frags, int n, uint32_t *out_val, int32_t *out_dc) {
   int i;
@@ -636,6 +687,7 @@ OCO_EXPORT void oco_enc_metrics_batch(int metric, const uint8_t *src_base, const
         v = oco_frag_border_ssd(src, r0, ystride,
                                 (int64_t)(((uint64_t)(uint32_t)frags[i].aux << 32) | (uint32_t)frags[i].ref_off1));
         break;
+      case OCG_MET_ACTIVITY: v = oco_block_activity(src, ystride, &dc); break;
       default: break;
     }
     out_val[i] = v;

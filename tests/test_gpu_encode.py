@@ -51,7 +51,7 @@ def make_frags(rng, st, n, taps):
     return fr, base, ystride
 
 
-@pytest.mark.parametrize("metric,taps", [(0, 1), (0, 2), (1, 1), (1, 2), (2, 0), (3, 1), (4, 0)])
+@pytest.mark.parametrize("metric,taps", [(0, 1), (0, 2), (1, 1), (1, 2), (2, 0), (3, 1), (4, 0), (6, 0)])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_metrics_batch(metric, taps, mode):
     rng = np.random.default_rng(metric * 10 + taps * 3 + mode)
@@ -135,3 +135,31 @@ def test_fdct_quant_batch(taps, mode):
     assert np.array_equal(od.cpu().numpy(), want_d)
     assert np.array_equal(oq.cpu().numpy(), want_q)
     assert np.array_equal(onz.cpu().numpy(), want_nz)
+
+
+@pytest.mark.parametrize("kind", ["noise", "flat", "edges", "texture"])
+def test_activity_batch(kind):
+    """OCG_MET_ACTIVITY (oc_mb_activity per luma block, analyze.c:1167-1234) on every block of scenes that
+    reach the flat clamp, the plain variance and the edge (log/exp) branch."""
+    import test_oracle_activity as TA
+    rng = np.random.default_rng(len(kind) + 40)
+    a, st = TA.frames(rng, kind)
+    ystride = -st
+    base = (TA.PAD + TA.H - 1) * st + TA.PAD
+    fy, fx = np.divmod(np.arange((TA.W // 8) * (TA.H // 8)), TA.W // 8)
+    n = fy.size
+    fr = np.zeros(n, S.ENC_FRAG_DTYPE)
+    fr["src_off"] = fy * 8 * ystride + fx * 8
+    fr["ref_off0"] = fr["ref_off1"] = S.INT32_MIN
+    want_v, want_dc = np.zeros(n, np.uint32), np.zeros(n, np.int32)
+    S.oracle().oco_enc_metrics_batch(6, a.ctypes.data + base, None, ystride, fr.ctypes.data, n,
+                                     S.ptr(want_v, S.u32p), S.ptr(want_dc, S.i32p))
+    da = torch.from_numpy(a).cuda()
+    dfr = torch.from_numpy(fr.view(np.int32).reshape(n, 4)).cuda()
+    ov = torch.zeros(n, dtype=torch.int32, device="cuda")
+    odc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    abi.check(abi.lib().ocg_enc_metrics_batch(6, da.data_ptr() + base, None, ystride, dfr.data_ptr(), n,
+                                              ov.data_ptr(), odc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(ov.cpu().numpy().view(np.uint32), want_v)
+    assert np.array_equal(odc.cpu().numpy(), want_dc)

@@ -230,6 +230,71 @@ ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__re
   if (out_dc != nullptr) out_dc[fi] = dc;
 }
 
+/* ------------------------------------------------------------------------ */
+/* oc_mb_activity (analyze.c:1152-1237) per luma block, one lane per block:
+   pixel sum and sum of squares -> variance-like activity, and for non-flat
+   blocks the four directional edge energies over the 10x10 neighbourhood; an
+   "edge" block gets act_th*(act/act_th)^0.7 through the reference's Q10
+   log/exp polynomials (mathops.c:294-313). */
+__device__ __forceinline__ uint32_t bexp32_q10(int z) {
+  const int ipart = z >> 10;
+  unsigned n = (unsigned)(z & 1023) << 4;
+  n = (n * ((n * ((n * ((n * 3548u >> 15) + 6817u) >> 15) + 15823u) >> 15) + 22708u) >> 15) + 16384u;
+  return 14 - ipart > 0 ? (n + (1u << (13 - ipart))) >> (14 - ipart) : n << (ipart - 14);
+}
+__device__ __forceinline__ int blog32_q10(uint32_t w) {
+  if (w == 0) return -1;
+  const int ipart = 32 - __clz(w);
+  const int n = (int)(ipart - 16 > 0 ? w >> (ipart - 16) : w << (16 - ipart)) - 32768 - 16384;
+  const int fpart = (n * ((n * ((n * ((n * -1402 >> 15) + 2546) >> 15) - 5216) >> 15) + 15745) >> 15) - 6793;
+  return (ipart << 10) + (fpart >> 4);
+}
+
+/* ten pixels of a row starting one byte left of p */
+__device__ __forceinline__ void load_row10(const uint8_t *p, int (&o)[10]) {
+  const uint2 a = ld8u(p - 1), b = ld8u(p + 7);
+  int t[8];
+  unpack8(a, t);
+#pragma unroll
+  for (int i = 0; i < 8; i++) o[i] = t[i];
+  o[8] = (int)(b.x & 0xFFu);
+  o[9] = (int)((b.x >> 8) & 0xFFu);
+}
+
+__global__ void __launch_bounds__(128)
+ocg_enc_activity_kernel(const uint8_t *__restrict__ src_base, int ystride, const ocg_enc_frag *__restrict__ frags, int n,
+                        uint32_t *__restrict__ out_act, int32_t *__restrict__ out_sum) {
+  const int fi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (fi >= n) return;
+  const uint8_t *s = src_base + frags[fi].src_off;
+  int up[10], cur[10], dn[10];
+  load_row10(s - ystride, up);
+  load_row10(s, cur);
+  unsigned x = 0, x2 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    load_row10(s + (i + 1) * ystride, dn);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const unsigned c = (unsigned)cur[j + 1];
+      x += c;
+      x2 += c * c;
+      e1 += (unsigned)abs(((cur[j + 2] - cur[j]) << 1) + up[j + 2] - up[j] + dn[j + 2] - dn[j]);
+      e2 += (unsigned)abs(((dn[j + 1] - up[j + 1]) << 1) + dn[j] - up[j] + dn[j + 2] - up[j + 2]);
+      e3 += (unsigned)abs(((dn[j + 2] - up[j]) << 1) + dn[j + 1] - cur[j] + cur[j + 2] - up[j + 1]);
+      e4 += (unsigned)abs(((dn[j] - up[j + 2]) << 1) + dn[j + 1] - cur[j + 2] + cur[j] - up[j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 10; j++) { up[j] = cur[j]; cur[j] = dn[j]; }
+  }
+  unsigned act = (x2 << 6) - x * x;
+  if (act < (8u << 12)) act = min(act, 5u << 12);
+  else if (5u * max(max(e1, e2), max(e3, e4)) > 2u * (e1 + e2 + e3 + e4))
+    act = bexp32_q10(0x394A + (7 * (blog32_q10(act) - 0x394A + 5) / 10));
+  out_act[fi] = act;
+  if (out_sum != nullptr) out_sum[fi] = (int32_t)x;
+}
+
 /* fdct.c:28-120 */
 __device__ __forceinline__ int fd_exp(int t, int bias) { return ((27146 * t + bias) >> 16) + t + (t != 0); }
 
@@ -1222,11 +1287,12 @@ OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uin
                                   const ocg_enc_frag *frags, int n, uint32_t *out_val, int32_t *out_dc,
                                   void *stream) {
   if (src_base == nullptr || frags == nullptr || out_val == nullptr) return OCG_EFAULT;
-  if (metric < OCG_MET_SAD || metric > OCG_MET_BORDER_SSD || n < 0) return OCG_EINVAL;
+  if (metric < OCG_MET_SAD || metric > OCG_MET_ACTIVITY || n < 0) return OCG_EINVAL;
   if (n == 0) return OCG_OK;
   const unsigned grid = (unsigned)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   switch (metric) {
+    case OCG_MET_ACTIVITY: ocg_enc_activity_kernel<<<grid, 128, 0, st>>>(src_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_SAD: ocg_enc_metrics_kernel<OCG_MET_SAD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_SATD: ocg_enc_metrics_kernel<OCG_MET_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_INTRA_SATD: ocg_enc_metrics_kernel<OCG_MET_INTRA_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
