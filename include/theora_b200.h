@@ -116,6 +116,10 @@ typedef struct ocg_dec_frame {
   int32_t             ncoded;          /* coded fragments in recs (informational)  */
   int32_t             intra_frame;     /* 1: key frame, no record references PREV/GOLD */
   int32_t             ncoeff_rows;
+  int32_t             dc_residual;     /* 1: recs[].dc hold the DC-prediction RESIDUALS as decoded
+                                          (decode.c:1277-1316) and the device undoes the prediction
+                                          (oc_dec_dc_unpredict_mcu_plane, decode.c:1392-1500) before
+                                          reconstructing; 0: recs[].dc are final (host did it)      */
   const ocg_frag_rec *recs;            /* nfrags records, fragment-index order     */
   const int16_t      *coeff_rows;      /* ncoeff_rows x 8 int16                    */
 } ocg_dec_frame;
@@ -138,6 +142,10 @@ OCG_API int  ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device);
 OCG_API void ocg_ctx_destroy(ocg_ctx *ctx);
 OCG_API const ocg_geometry *ocg_ctx_geometry(const ocg_ctx *ctx);
 OCG_API int  ocg_ctx_sync(ocg_ctx *ctx);
+/* 1 if frames of this geometry may be submitted with dc_residual=1 (the DC
+   wave-front kernel runs one thread per fragment row of a plane, at most 1024
+   rows, reference types of a plane in shared memory), else 0. */
+OCG_API int  ocg_dc_unpredict_supported(const ocg_geometry *g);
 OCG_API void *ocg_ctx_stream(ocg_ctx *ctx);                 /* cudaStream_t */
 OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *ctx, int buf);  /* device address of buffer `buf` */
 /* Whole padded buffer, host <-> device (ref_frame_sz bytes). */

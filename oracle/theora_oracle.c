@@ -339,6 +339,60 @@ OCO_EXPORT void oco_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs)
   }
 }
 
+/* decode.c:1392-1500 (oc_dec_dc_unpredict_mcu_plane_c) over a whole plane:
+   refs[i] = reference type of fragment i (0..2) or OCG_FRAG_UNCODED, dc[i] in:
+   residual, out: value.  pred_last starts at 0 for every type (decode.c:1367). */
+OCO_EXPORT void oco_dc_unpredict_plane(int16_t *dc, const uint8_t *refs, int nhfrags, int nvfrags) {
+  int pred_last[3] = {0, 0, 0};
+  int fragx, fragy, fragi = 0;
+  for (fragy = 0; fragy < nvfrags; fragy++) {
+    if (fragy == 0) {
+      for (fragx = 0; fragx < nhfrags; fragx++, fragi++) {
+        if (refs[fragi] != OCG_FRAG_UNCODED) {
+          int refi = refs[fragi];
+          dc[fragi] = (int16_t)(dc[fragi] + pred_last[refi]);
+          pred_last[refi] = dc[fragi];
+        }
+      }
+    } else {
+      const int16_t *u_dc = dc - nhfrags;
+      const uint8_t *u_refs = refs - nhfrags;
+      int l_ref = -1, ul_ref = -1, u_ref = u_refs[fragi] == OCG_FRAG_UNCODED ? -1 : u_refs[fragi];
+      for (fragx = 0; fragx < nhfrags; fragx++, fragi++) {
+        int ur_ref;
+        if (fragx + 1 >= nhfrags) ur_ref = -1;
+        else ur_ref = u_refs[fragi + 1] == OCG_FRAG_UNCODED ? -1 : u_refs[fragi + 1];
+        if (refs[fragi] != OCG_FRAG_UNCODED) {
+          int pred, refi = refs[fragi];
+          switch ((l_ref == refi) | (ul_ref == refi) << 1 | (u_ref == refi) << 2 | (ur_ref == refi) << 3) {
+            default: pred = pred_last[refi]; break;
+            case 1: case 3: pred = dc[fragi - 1]; break;
+            case 2: pred = u_dc[fragi - 1]; break;
+            case 4: case 6: case 12: pred = u_dc[fragi]; break;
+            case 5: pred = (dc[fragi - 1] + u_dc[fragi]) / 2; break;
+            case 8: pred = u_dc[fragi + 1]; break;
+            case 9: case 11: case 13: pred = (75 * dc[fragi - 1] + 53 * u_dc[fragi + 1]) / 128; break;
+            case 10: pred = (u_dc[fragi - 1] + u_dc[fragi + 1]) / 2; break;
+            case 14: pred = (3 * (u_dc[fragi - 1] + u_dc[fragi + 1]) + 10 * u_dc[fragi]) / 16; break;
+            case 7: case 15: {
+              int p0 = dc[fragi - 1], p1 = u_dc[fragi - 1], p2 = u_dc[fragi];
+              pred = (29 * (p0 + p2) - 26 * p1) / 32;
+              if (abs(pred - p2) > 128) pred = p2;
+              else if (abs(pred - p0) > 128) pred = p0;
+              else if (abs(pred - p1) > 128) pred = p1;
+            } break;
+          }
+          dc[fragi] = (int16_t)(dc[fragi] + pred);
+          pred_last[refi] = dc[fragi];
+          l_ref = refi;
+        } else l_ref = -1;
+        ul_ref = u_ref;
+        u_ref = ur_ref;
+      }
+    }
+  }
+}
+
 /* The whole-frame sequence of decode.c:2858-2945 driven from the C-ABI frame
    description: recon of coded fragments (decode.c:1584 -> state.c:959), copy
    of uncoded ones (decode.c:1599), loop filter over all rows (2882), borders
@@ -348,10 +402,21 @@ OCO_EXPORT void oco_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs)
 OCO_EXPORT void oco_dec_frame(const ocg_geometry *g, uint8_t *frames, const ocg_dec_frame *f, int stage_mask) {
   uint8_t *base[3];
   uint8_t *coded = (uint8_t *)malloc((size_t)g->nfrags);
+  int16_t *dcv = NULL;
   int i, r, c, pli;
   for (i = 0; i < 3; i++)
     base[i] = f->ref_idx[i] >= 0 ? frames + (int64_t)f->ref_idx[i] * g->ref_frame_sz + g->base_off : NULL;
   for (i = 0; i < g->nfrags; i++) coded[i] = f->recs[i].refi != OCG_FRAG_UNCODED;
+  if (f->dc_residual && (stage_mask & 1)) {
+    /* the records carry DC residuals: undo the prediction first (decode.c:2876) */
+    uint8_t *refs = (uint8_t *)malloc((size_t)g->nfrags);
+    dcv = (int16_t *)malloc((size_t)g->nfrags * sizeof(int16_t));
+    for (i = 0; i < g->nfrags; i++) { refs[i] = f->recs[i].refi; dcv[i] = f->recs[i].dc; }
+    for (pli = 0; pli < 3; pli++)
+      oco_dc_unpredict_plane(dcv + g->planes[pli].froffset, refs + g->planes[pli].froffset, g->planes[pli].nhfrags,
+                             g->planes[pli].nvfrags);
+    free(refs);
+  }
   if (stage_mask & 1) {
     for (i = 0; i < g->nfrags; i++) {
       const ocg_frag_rec *rec = &f->recs[i];
@@ -367,7 +432,7 @@ OCO_EXPORT void oco_dec_frame(const ocg_geometry *g, uint8_t *frames, const ocg_
           for (c = 0; c < 8; c++) blk[r * 8 + c] = rows[c];
           rows += 8;
         }
-        blk[0] = rec->dc;
+        blk[0] = dcv ? dcv[i] : rec->dc;
         oco_state_frag_recon(base[OCG_FRAME_SELF], rec->refi == OCG_FRAME_SELF ? NULL : base[rec->refi],
                              rec->buf_off, g->planes[pl].ystride, pl, g->pixel_fmt,
                              rec->refi == OCG_FRAME_SELF, rec->mv, blk, rec->last_zzi, f->dc_quant[pl][qti]);
@@ -382,6 +447,7 @@ OCO_EXPORT void oco_dec_frame(const ocg_geometry *g, uint8_t *frames, const ocg_
     if (stage_mask & 4) oco_borders_fill_plane(pix, p->ystride, p->width, p->height, p->hpad, p->vpad);
   }
   free(coded);
+  free(dcv);
 }
 
 /* ---------------------------------------------------------------------- */

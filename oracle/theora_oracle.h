@@ -67,6 +67,7 @@ unsigned oco_frag_ssd(const uint8_t *src, const uint8_t *ref, int ystride);     
 unsigned oco_frag_border_ssd(const uint8_t *src, const uint8_t *ref, int ystride, int64_t mask); /* :352 */
 void     oco_frag_copy2(uint8_t *dst, const uint8_t *s1, const uint8_t *s2, int ystride);     /* :368 */
 
+void     oco_dc_unpredict_plane(int16_t *dc, const uint8_t *refs, int nhfrags, int nvfrags);   /* decode.c:1392-1500 */
 unsigned oco_block_activity(const uint8_t *src, int ystride, int *sum);                     /* analyze.c:1167-1234 */
 
 /* Batch forms matching the C-ABI encoder entry points. */

@@ -30,13 +30,14 @@ CASES = [
 ]
 
 
-def replay_and_compare(case):
+def replay_and_compare(case, dc_mode=streams.DC_HOST):
     w, h, n, q, kf, sp, ns = case[:7]
     fmt = case[7] if len(case) > 7 else 0
     R = S.ref("c")
     st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns, fmt=fmt)
     blob = st.to_bytes()
-    g, works, _ = streams.capture_stream_work(blob, streams.BACKEND_RECORD)
+    g, works, _ = streams.capture_stream_work(blob, streams.BACKEND_RECORD, dc_mode=dc_mode)
+    assert all(wk is None or wk.dc_residual == (dc_mode == streams.DC_DEVICE) for wk in works)
     dec = S.Decoder(R, st)
     frames = np.full(g.nrefs * g.ref_frame_sz, 0x80, np.uint8)
     assert len(works) == n
@@ -61,9 +62,12 @@ def replay_and_compare(case):
     return stats
 
 
+@pytest.mark.parametrize("dc_mode", [streams.DC_DEVICE, streams.DC_HOST])
 @pytest.mark.parametrize("case", CASES)
-def test_recorded_lists_replay_to_reference_frames(case):
-    stats = replay_and_compare(case)
+def test_recorded_lists_replay_to_reference_frames(case, dc_mode):
+    """dc_mode DC_DEVICE: the records carry DC residuals and the executor undoes the
+    prediction (oco_dc_unpredict_plane); DC_HOST: the reference's own routine ran in the hook."""
+    stats = replay_and_compare(case, dc_mode)
     assert stats["coded"] > 0
 
 

@@ -138,3 +138,55 @@ def test_batch_of_streams_matches_single_submits():
     for s in range(nstreams):
         got = np.concatenate([ctxs[s].download_frame(b) for b in range(3)])
         assert np.array_equal(wants[s], got), (s, first_diff(g, wants[s], got))
+
+
+DC_CASES = [
+    # fw, fh, fmt, density, intra_only
+    (64, 64, 0, 0.7, False),
+    (64, 64, 0, 1.0, True),      # every pattern is 15/7: the longest chains
+    (352, 288, 0, 0.15, False),  # sparse: pred_last reaches far back in raster order
+    (352, 288, 0, 0.6, False),
+    (176, 144, 2, 0.5, False),
+    (176, 144, 3, 0.9, False),
+    (16, 16, 0, 1.0, False),     # a single super block
+    (1920, 1088, 0, 0.4, False),
+    (32, 2048, 0, 0.5, False),   # tall: 256 fragment rows in one CTA
+    (3840, 2160, 0, 0.5, False), # luma DC values do not fit shared memory: global scratch variant
+]
+
+
+@pytest.mark.parametrize("case", DC_CASES)
+def test_dc_unprediction_on_device_matches_oracle(case):
+    """dc_residual=1: the device undoes the DC prediction (decode.c:1392-1500) before reconstructing;
+    the records' dc fields are treated as residuals by both sides."""
+    from theora_b200 import abi
+    fw, fh, fmt, density, intra = case
+    rng = np.random.default_rng(hash(case) & 0xFFFF)
+    g = S.make_geometry(fw, fh, fmt, 3)
+    assert abi.lib().ocg_dc_unpredict_supported(g) == 1
+    frames = W.random_frames(g, rng)
+    work = W.random_work(g, rng, density=density, intra_only=intra, lf_limit=0, ref_idx=(1, 2, 0))
+    # large residuals too, so the 16-bit wrap of frags[].dc is reached now and then
+    coded = work.recs["refi"] != 3
+    big = rng.random(len(work.recs)) < 0.02
+    work.recs["dc"][coded & big] = rng.integers(-32768, 32768, size=int((coded & big).sum()))
+    w2 = abi.FrameWork(work.ref_idx, work.lf_limit, work.dc_quant, work.recs, work.rows, dc_residual=1)
+    want = W.oracle_decode(g, frames, w2, 1)
+    got = run_gpu(g, frames, w2, 1)
+    assert np.array_equal(want, got), first_diff(g, want, got)
+    # and it is not a no-op: with the flag off the same records reconstruct differently
+    if density > 0.3:
+        assert not np.array_equal(want, W.oracle_decode(g, frames, work, 1))
+
+
+def test_dc_residual_frames_are_refused_in_resident_packs():
+    from theora_b200 import abi
+    rng = np.random.default_rng(3)
+    g = S.make_geometry(64, 64, 0, 3)
+    work = W.random_work(g, rng, density=0.5)
+    w2 = abi.FrameWork(work.ref_idx, work.lf_limit, work.dc_quant, work.recs, work.rows, dc_residual=1)
+    ctx = T.Context(g)
+    pack = T.Pack([w2], g.nfrags)
+    with pytest.raises(abi.OcgError):
+        T.run_batch([ctx], [pack], [0])
+    ctx.close()

@@ -23,12 +23,15 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("dc_mode", [streams.DC_DEVICE, streams.DC_HOST])
 @pytest.mark.parametrize("case", CASES)
-def test_public_api_decode_matches_reference(case):
+def test_public_api_decode_matches_reference(case, dc_mode):
+    """DC_DEVICE: DC un-prediction by the wave-front kernel; DC_HOST: by the reference's C routine."""
     w, h, n, q, kf, sp, ns = case
     R = S.ref("c")
     st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns)
-    g, works, outs = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_GPU)
+    g, works, outs = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_GPU, dc_mode=dc_mode)
+    assert all(wk is None or wk.dc_residual == (dc_mode == streams.DC_DEVICE) for wk in works)
     dec = S.Decoder(R, st)
     assert len(outs) == n
     for i in range(n):

@@ -36,7 +36,7 @@ class Geometry(C.Structure):
 class DecFrame(C.Structure):
     _fields_ = [("ref_idx", C.c_int32 * 3), ("lf_limit", C.c_int32), ("dc_quant", (C.c_uint16 * 2) * 3),
                 ("ncoded", C.c_int32), ("intra_frame", C.c_int32),
-                ("ncoeff_rows", C.c_int32), ("recs", C.c_void_p), ("coeff_rows", C.c_void_p)]
+                ("ncoeff_rows", C.c_int32), ("dc_residual", C.c_int32), ("recs", C.c_void_p), ("coeff_rows", C.c_void_p)]
 
 
 class Staging(C.Structure):
@@ -70,7 +70,8 @@ class FrameWork:
     """One frame of decoder block work held in numpy arrays (keeps them alive):
     `recs` has one record per fragment, in fragment-index order."""
 
-    def __init__(self, ref_idx, lf_limit, dc_quant, recs, rows):
+    def __init__(self, ref_idx, lf_limit, dc_quant, recs, rows, dc_residual=0):
+        self.dc_residual = int(dc_residual)
         self.ref_idx = tuple(int(x) for x in ref_idx)
         self.lf_limit = int(lf_limit)
         self.dc_quant = np.asarray(dc_quant, dtype=np.uint16).reshape(3, 2).copy()
@@ -87,6 +88,7 @@ class FrameWork:
         f.ncoded = self.ncoded
         f.intra_frame = int(bool(np.all(self.recs["refi"] == OCG_FRAME_SELF)))
         f.ncoeff_rows = len(self.rows)
+        f.dc_residual = self.dc_residual
         f.recs = self.recs.ctypes.data
         f.coeff_rows = self.rows.ctypes.data if len(self.rows) else None
         return f
@@ -113,7 +115,7 @@ class FrameWork:
         return self.recs.nbytes + self.rows.nbytes
 
     def with_refs(self, ref_idx):
-        return FrameWork(ref_idx, self.lf_limit, self.dc_quant, self.recs, self.rows)
+        return FrameWork(ref_idx, self.lf_limit, self.dc_quant, self.recs, self.rows, self.dc_residual)
 
     def to_dict(self, prefix):
         return {prefix + "ref_idx": np.array(self.ref_idx, np.int32), prefix + "lf": np.array([self.lf_limit], np.int32),
@@ -135,6 +137,7 @@ _PROTOS = {
     "ocg_ctx_destroy": (None, [C.c_void_p]),
     "ocg_ctx_geometry": (C.POINTER(Geometry), [C.c_void_p]),
     "ocg_ctx_sync": (C.c_int, [C.c_void_p]),
+    "ocg_dc_unpredict_supported": (C.c_int, [C.POINTER(Geometry)]),
     "ocg_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "ocg_ctx_frame_devptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ocg_ctx_upload_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

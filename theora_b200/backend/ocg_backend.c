@@ -50,6 +50,7 @@ typedef struct ocg_backend {
   ogg_uint16_t       dcq[3][2];
   unsigned char      dev_valid[6];
   int                pinned;
+  int                dc_device;   /* DC prediction is undone on the device (records carry residuals) */
   th_stripe_callback user_cb;
   struct ocg_backend *next;
 } ocg_backend;
@@ -57,6 +58,7 @@ typedef struct ocg_backend {
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static ocg_backend *g_list;
 static int g_mode = OCG_BACKEND_GPU;
+static int g_dc_mode = OCG_DC_HOST;
 static ocg_capture_fn g_capture;
 static void *g_capture_user;
 static int g_device; /* one process per GPU: process-wide */
@@ -66,6 +68,7 @@ static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 
 OCG_API void ocg_backend_set_mode(int mode) { g_mode = mode; }
 OCG_API void ocg_backend_set_device(int device) { g_device = device; }
+OCG_API void ocg_backend_set_dc_mode(int mode) { g_dc_mode = mode; }
 OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user) { g_capture = fn; g_capture_user = user; }
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset) {
   pthread_mutex_lock(&g_stats_lock);
@@ -135,6 +138,7 @@ static void backend_flush(ocg_backend *b) {
   f.ncoded = b->ncoded;
   f.intra_frame = st->frame_type == OC_INTRA_FRAME;
   f.ncoeff_rows = b->nrows;
+  f.dc_residual = b->dc_device;
   b->frame_open = 0;
   if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
   if (b->ctx == NULL) { stats_add(b, 0, 0, 0.0); return; } /* record mode */
@@ -173,7 +177,21 @@ static void backend_flush(ocg_backend *b) {
 /* ---- recorders ----------------------------------------------------------- */
 static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli) {
   ocg_backend *b = backend_of(_dec);
-  oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
+  if (b != NULL && b->dc_device) {
+    /* the device undoes the prediction (ocg_dc_unpredict_kernel); what is left of
+       this hook is its side effect, decode.c:1496-1499: the MCU's fragment counts */
+    const oc_fragment_plane *fplane = _dec->state.fplanes + _pli;
+    const oc_fragment *frags = _dec->state.frags;
+    const int fragy0 = _pipe->fragy0[_pli], fragy_end = _pipe->fragy_end[_pli];
+    ptrdiff_t fragi = fplane->froffset + fragy0 * (ptrdiff_t)fplane->nhfrags;
+    const ptrdiff_t end = fplane->froffset + fragy_end * (ptrdiff_t)fplane->nhfrags;
+    ptrdiff_t ncoded = 0;
+    for (; fragi < end; fragi++) ncoded += frags[fragi].coded;
+    _pipe->ncoded_fragis[_pli] = ncoded;
+    _pipe->nuncoded_fragis[_pli] = (fragy_end - fragy0) * (ptrdiff_t)fplane->nhfrags - ncoded;
+  } else {
+    oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
+  }
   if (b != NULL && !b->frame_open) backend_begin_frame(b);
 }
 
@@ -307,6 +325,7 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
     free(b);
     return;
   }
+  b->dc_device = g_dc_mode == OCG_DC_DEVICE && (b->mode != OCG_BACKEND_GPU || ocg_dc_unpredict_supported(&b->geom));
   if (b->mode == OCG_BACKEND_GPU) {
     if (ocg_ctx_create(&b->ctx, &b->geom, g_device) < 0) {
       fprintf(stderr, "theora_b200 back-end: %s\n", ocg_last_error());

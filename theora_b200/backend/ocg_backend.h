@@ -16,6 +16,24 @@ extern "C" {
 OCG_API void ocg_backend_set_mode(int mode);      /* applies to decoders allocated afterwards */
 OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders allocated afterwards (process-wide: one process per GPU) */
 
+/* Where the DC prediction is undone (oc_dec_dc_unpredict_mcu_plane, decode.c:1392):
+   OCG_DC_HOST (default): the reference's C routine runs in the hook and the
+   records carry final DC values (also what resident packs need).
+   OCG_DC_DEVICE: the hook only counts the coded fragments of the MCU (its other
+   duty, decode.c:1496-1499); the records carry the DC residuals and the device
+   runs the wave-front kernel before reconstructing (dc_residual=1); geometries
+   the kernel does not cover (ocg_dc_unpredict_supported) stay on the host.
+   Bit-exact either way.  Measured on B200 (1080p): a key frame costs +0.07 ms
+   of device time, but an inter frame with mixed reference types +0.5..1.1 ms,
+   because the "last value of the same reference type" predictor (decode.c:1452)
+   links rows end-to-start and the dependency chain grows to thousands of
+   fragments, ~0.25 us each on a GPU vs ~7 ns on a CPU core: through
+   th_decode_packetin the device variant is slower (6.8 k vs 10.6 k frames/s),
+   hence opt-in. */
+#define OCG_DC_DEVICE 0
+#define OCG_DC_HOST   1
+OCG_API void ocg_backend_set_dc_mode(int mode);   /* applies to decoders allocated afterwards */
+
 /* Called at every frame flush with the frame description (list pointers NULL)
    and the staged lists, before they are submitted. */
 typedef void (*ocg_capture_fn)(void *user, const ocg_dec_frame *frame, const ocg_staging *lists);

@@ -63,6 +63,7 @@ struct ocg_ctx {
   ocg_frag_rec *d_recs = nullptr;
   int16_t *d_rows = nullptr;
   uint8_t *d_map = nullptr;  /* coded map, produced by the recon kernel */
+  int16_t *d_dc_tmp = nullptr; /* DC wave-front scratch (planes too large for shared memory) */
   int32_t *d_xlist = nullptr; /* transform work list + 2 counters behind it */
   CUtensorMap *d_tmaps = nullptr; /* [nrefs][3] tiled views of the padded planes for the TMA loop filter */
   OcgJobDev *d_job = nullptr;
@@ -124,9 +125,20 @@ static void fill_job(OcgJobDev &j, const ocg_ctx *c, const ocg_dec_frame &f, con
   j.xlist = c->d_xlist;
   j.xcount = c->d_xlist + c->geom.nfrags;
   j.lf_limit = f.lf_limit;
+  j.dc_residual = f.dc_residual != 0;
+  j.dc_tmp = c->d_dc_tmp;
   j.lf_tmaps = c->d_tmaps ? c->d_tmaps + (size_t)f.ref_idx[OCG_FRAME_SELF] * 3 : nullptr;
   for (int p = 0; p < 3; p++)
     for (int q = 0; q < 2; q++) j.dcq[p][q] = f.dc_quant[p][q];
+}
+
+extern "C" OCG_API int ocg_dc_unpredict_supported(const ocg_geometry *g) {
+  if (g == nullptr) return 0;
+  for (int pli = 0; pli < 3; pli++) {
+    const size_t nv = (size_t)g->planes[pli].nvfrags, nfr = (size_t)g->planes[pli].nfrags;
+    if (nv > 1024 || 8 * nv * sizeof(int) + ((nfr + 15) & ~(size_t)15) > 227 * 1024) return 0;
+  }
+  return 1;
 }
 
 static int check_frame(const ocg_geometry &g, const ocg_dec_frame &f) {
@@ -136,6 +148,7 @@ static int check_frame(const ocg_geometry &g, const ocg_dec_frame &f) {
   for (int i = 0; i < 2; i++)
     if (f.ref_idx[i] >= g.nrefs) return fail(OCG_EINVAL, "bad reference buffer index");
   if (f.lf_limit < 0 || f.lf_limit > 127) return fail(OCG_EINVAL, "loop filter limit out of range");
+  if (f.dc_residual && !ocg_dc_unpredict_supported(&g)) return fail(OCG_EIMPL, "DC un-prediction on the device does not support this frame size");
   return OCG_OK;
 }
 
@@ -214,8 +227,9 @@ static void timed_stage(int stage, cudaStream_t st, F &&launch) {
 }
 
 static void launch_stages(const OcgGeomDev &gd, const OcgJobDev *jobs, int njobs, bool any_lf, bool use_tma,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool any_dc = false) {
   const int mask = g_stage_mask.load(std::memory_order_relaxed);
+  if (any_dc && (mask & 1)) ocg_launch_dc_unpredict(gd, jobs, njobs, st);
   if (mask & 1) timed_stage(0, st, [&] { ocg_launch_recon(gd, jobs, njobs, st); });
   else if ((mask & 2) && any_lf) ocg_launch_codedmap(gd, jobs, njobs, st);
   if ((mask & 2) && any_lf) timed_stage(1, st, [&] { ocg_launch_loop_filter(gd, jobs, njobs, use_tma, st); });
@@ -340,6 +354,7 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
   cudaFree(c->d_recs);
   cudaFree(c->d_rows);
   cudaFree(c->d_map);
+  cudaFree(c->d_dc_tmp);
   cudaFree(c->d_xlist);
   cudaFree(c->d_tmaps);
   cudaFree(c->d_job);
@@ -383,6 +398,7 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   CUX(cudaMalloc(&c->d_recs, nf * sizeof(ocg_frag_rec)));
   CUX(cudaMalloc(&c->d_rows, nf * 8 * 16));
   CUX(cudaMalloc(&c->d_map, nf));
+  CUX(cudaMalloc(&c->d_dc_tmp, nf * sizeof(int16_t)));
   CUX(cudaMalloc(&c->d_xlist, (nf + 2) * sizeof(int32_t)));
   CUX(cudaMemsetAsync(c->d_xlist, 0, (nf + 2) * sizeof(int32_t), c->stream));
   CUX(cudaMalloc(&c->d_job, sizeof(OcgJobDev)));
@@ -527,7 +543,7 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
   CU(cudaMemcpyAsync(c->d_job, s.job, sizeof(OcgJobDev), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(s.consumed, st));
   s.busy = true;
-  launch_stages(c->gdev, c->d_job, 1, f->lf_limit != 0, c->d_tmaps != nullptr && g_use_tma.load(), st);
+  launch_stages(c->gdev, c->d_job, 1, f->lf_limit != 0, c->d_tmaps != nullptr && g_use_tma.load(), st, f->dc_residual != 0);
   CU(cudaGetLastError());
   if (host_out != nullptr) {
     CU(cudaMemcpyAsync(host_out, c->frames + (size_t)f->ref_idx[OCG_FRAME_SELF] * c->geom.ref_frame_sz,
@@ -731,6 +747,8 @@ OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, cons
     const ocg_dec_frame &f = p->frames[(size_t)frame_idx[i]];
     int r = check_frame(c->geom, f);
     if (r < 0) return r;
+    /* a resident frame is replayed: its records must not be rewritten in place */
+    if (f.dc_residual) return fail(OCG_EINVAL, "resident packs hold final DC values (dc_residual frames go through ocg_dec_submit)");
     fill_job(bs.h[i], c, f, f.recs, f.coeff_rows);
     any_lf |= f.lf_limit != 0;
     all_tma = all_tma && c->d_tmaps != nullptr;

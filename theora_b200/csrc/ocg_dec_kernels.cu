@@ -23,6 +23,7 @@
  * All loads/stores are 64- or 128-bit.  There is no dense contraction here, so
  * tensor cores are not used.
  */
+#include <algorithm>
 #include "ocg_internal.h"
 
 namespace {
@@ -802,6 +803,141 @@ ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   }
 }
 
+/* ------------------------------------------------------------------------ */
+/* DC un-prediction (oc_dec_dc_unpredict_mcu_plane_c, decode.c:1392-1500) for a
+   whole plane.  The recurrence dc = residual + pred(left, up-left, up,
+   up-right | last value of the same reference type) is serial along a row and
+   skewed by two columns between rows, so one CTA per plane runs a wave-front
+   with ONE THREAD PER FRAGMENT ROW: in each step a row skips its uncoded
+   fragments and finishes at most one coded fragment, as soon as the row above
+   has passed column x+1; rows publish their progress through a double-buffered
+   shared array, one __syncthreads_or per step.  The "no neighbour of my
+   reference type" case (pred_last, decode.c:1452) points at the last coded
+   fragment of that type in raster order, which is known before any value is:
+   per-row last positions are tabulated first and the row simply waits until
+   that particular fragment is final.  Reference types and (where the plane
+   fits) the DC values live in shared memory; results go straight into the
+   records the reconstruction kernels read. */
+#define OCG_DC_MAX_ROWS 1024
+
+template <bool DC_IN_SMEM>
+__global__ void __launch_bounds__(OCG_DC_MAX_ROWS)
+ocg_dc_unpredict_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  const OcgJobDev &job = jobs[blockIdx.y];
+  if (!job.dc_residual) return;
+  const OcgPlaneDev &P = g.p[blockIdx.x];
+  const int nh = P.nhfrags, nv = P.nvfrags, nfr = nh * nv;
+  ocg_frag_rec *recs = const_cast<ocg_frag_rec *>(job.recs) + P.froffset;
+  extern __shared__ __align__(16) unsigned char smem[];
+  int *progress = (int *)smem;                 /* [2][nv] */
+  int *rowlast = progress + 2 * nv;            /* [3][nv] last coded x of each reference type in a row, or -1 */
+  int *prevrow = rowlast + 3 * nv;             /* [3][nv] nearest earlier row that has one, or -1 */
+  uint8_t *refs = (uint8_t *)(prevrow + 3 * nv); /* [nfr] 0..2 = reference type, 3 = not coded */
+  volatile int16_t *dcs = DC_IN_SMEM ? (volatile int16_t *)(refs + ((nfr + 15) & ~15))
+                                     : (volatile int16_t *)(job.dc_tmp + P.froffset);
+  const int y = (int)threadIdx.x;
+  for (int i = (int)threadIdx.x; i < nfr; i += (int)blockDim.x) {
+    const uint2 lo = *(const uint2 *)(recs + i); /* buf_off, mv|dc<<16 */
+    const uint32_t hi = ((const uint32_t *)(recs + i))[3]; /* rowmask, last_zzi, refi, pli_qti */
+    refs[i] = (uint8_t)((hi >> 16) & 0xFFu);
+    dcs[i] = (int16_t)(lo.y >> 16);
+  }
+  if (y < nv) { progress[y] = 0; progress[nv + y] = 0; }
+  __syncthreads();
+  if (y < nv) {
+    int l0 = -1, l1 = -1, l2 = -1;
+    const uint8_t *rr = refs + y * nh;
+    for (int x = 0; x < nh; x++) {
+      const int r = rr[x];
+      l0 = r == 0 ? x : l0;
+      l1 = r == 1 ? x : l1;
+      l2 = r == 2 ? x : l2;
+    }
+    rowlast[y] = l0;
+    rowlast[nv + y] = l1;
+    rowlast[2 * nv + y] = l2;
+  }
+  __syncthreads();
+  if (y < 3) {
+    int last = -1;
+    for (int r = 0; r < nv; r++) {
+      prevrow[y * nv + r] = last;
+      if (rowlast[y * nv + r] >= 0) last = r;
+    }
+  }
+  __syncthreads();
+  int x = 0, l_ref = -1, l_dc = 0, hasmask = 0, last0 = 0, last1 = 0, last2 = 0;
+  const bool active = y < nv;
+  const uint8_t *myref = refs + y * nh;
+  const uint8_t *upref = refs + (y - 1) * nh;
+  for (int it = 0;; it++) {
+    const int *pcur = progress + (it & 1) * nv;
+    int *pnext = progress + ((it & 1) ^ 1) * nv;
+    bool more = false;
+    if (active) {
+      while (x < nh && myref[x] == 3) { x++; l_ref = -1; }
+      if (x < nh) {
+        const int r = myref[x];
+        const int i = y * nh + x;
+        const int mine = r == 0 ? last0 : (r == 1 ? last1 : last2);
+        bool ready = true;
+        int pred = 0;
+        if (y == 0) pred = mine; /* decode.c:1415-1425 (0 until the first one) */
+        else {
+          ready = pcur[y - 1] >= min(x + 2, nh);
+          if (ready) {
+            const int ul = x > 0 ? upref[x - 1] : 255, u = upref[x], ur = x + 1 < nh ? upref[x + 1] : 255;
+            const int pat = (l_ref == r) | (ul == r) << 1 | (u == r) << 2 | (ur == r) << 3;
+            const int iu = i - nh;
+            switch (pat) {
+              case 0:
+                if (hasmask >> r & 1) pred = mine;
+                else {
+                  const int yp = prevrow[r * nv + y];
+                  if (yp >= 0) {
+                    const int xs = rowlast[r * nv + yp];
+                    if (pcur[yp] > xs) pred = dcs[yp * nh + xs];
+                    else ready = false;
+                  }
+                }
+                break;
+              case 1: case 3: pred = l_dc; break;
+              case 2: pred = dcs[iu - 1]; break;
+              case 4: case 6: case 12: pred = dcs[iu]; break;
+              case 5: pred = (l_dc + dcs[iu]) / 2; break;
+              case 8: pred = dcs[iu + 1]; break;
+              case 9: case 11: case 13: pred = (75 * l_dc + 53 * dcs[iu + 1]) / 128; break;
+              case 10: pred = (dcs[iu - 1] + dcs[iu + 1]) / 2; break;
+              case 14: pred = (3 * (dcs[iu - 1] + dcs[iu + 1]) + 10 * dcs[iu]) / 16; break;
+              default: { /* 7, 15 */
+                const int p0 = l_dc, p1 = dcs[iu - 1], p2 = dcs[iu];
+                pred = (29 * (p0 + p2) - 26 * p1) / 32;
+                if (abs(pred - p2) > 128) pred = p2;
+                else if (abs(pred - p0) > 128) pred = p0;
+                else if (abs(pred - p1) > 128) pred = p1;
+              } break;
+            }
+          }
+        }
+        if (ready) {
+          const int v = (int)(int16_t)(dcs[i] + pred); /* frags[].dc is a 16-bit field (state.h:320) */
+          dcs[i] = (int16_t)v;
+          recs[i].dc = (int16_t)v;
+          if (r == 0) last0 = v; else if (r == 1) last1 = v; else last2 = v;
+          hasmask |= 1 << r;
+          l_ref = r;
+          l_dc = v;
+          x++;
+          while (x < nh && myref[x] == 3) { x++; l_ref = -1; }
+        }
+      }
+      pnext[y] = x;
+      more = x < nh;
+    }
+    if (!__syncthreads_or(more)) break;
+  }
+}
+
 } /* namespace */
 
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
@@ -816,6 +952,38 @@ void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cud
   dim3 gb((unsigned)per_job, (unsigned)njobs);
   ocg_recon_xform_kernel<<<gb, OCG_RECON_THREADS, 0, st>>>(g, jobs);
   ocg_count_launch(2);
+}
+
+/* shared memory the DC kernel needs for a plane; dc_in_smem says whether the values fit too */
+static size_t dc_smem_bytes(const OcgPlaneDev &P, bool dc_in_smem) {
+  const size_t nv = (size_t)P.nvfrags, nfr = (size_t)P.nhfrags * P.nvfrags;
+  return 8 * nv * sizeof(int) + ((nfr + 15) & ~(size_t)15) + (dc_in_smem ? nfr * 2 : 0);
+}
+
+int ocg_launch_dc_unpredict(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return 0;
+  static const size_t kMaxSmem = 227 * 1024;
+  size_t need_all = 0, need_refs = 0;
+  int rows = 0;
+  for (int pli = 0; pli < 3; pli++) {
+    need_all = std::max(need_all, dc_smem_bytes(g.p[pli], true));
+    need_refs = std::max(need_refs, dc_smem_bytes(g.p[pli], false));
+    rows = std::max(rows, (int)g.p[pli].nvfrags);
+  }
+  if (rows > OCG_DC_MAX_ROWS || need_refs > kMaxSmem) return -1; /* frame too tall / plane too large for this kernel */
+  const unsigned threads = (unsigned)((rows + 31) & ~31);
+  dim3 grid(3, (unsigned)njobs);
+  if (need_all <= kMaxSmem) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(ocg_dc_unpredict_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem); attr = true; }
+    ocg_dc_unpredict_kernel<true><<<grid, threads, need_all, st>>>(g, jobs);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(ocg_dc_unpredict_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem); attr = true; }
+    ocg_dc_unpredict_kernel<false><<<grid, threads, need_refs, st>>>(g, jobs);
+  }
+  ocg_count_launch(1);
+  return 0;
 }
 
 void ocg_launch_xlist_reset(const OcgJobDev *jobs, int njobs, cudaStream_t st) {

@@ -34,6 +34,7 @@ class EncBackendStats(C.Structure):
 
 
 ENC_AUTO, ENC_HOST = 0, 1
+DC_DEVICE, DC_HOST = 0, 1
 
 _lib = None
 
@@ -53,6 +54,7 @@ def lib():
         L = C.CDLL(OCG_LIB)
         L.ocg_backend_set_mode.argtypes = [C.c_int]
         L.ocg_backend_set_device.argtypes = [C.c_int]
+        L.ocg_backend_set_dc_mode.argtypes = [C.c_int]
         L.ocg_backend_set_capture.argtypes = [CAPTURE_FN, C.c_void_p]
         L.ocg_backend_get_stats.argtypes = [C.POINTER(BackendStats), C.c_int]
         L.ocg_backend_set_enc_mode.argtypes = [C.c_int]
@@ -116,7 +118,8 @@ class Capture:
         recs = _copy(st.recs, self.nfrags * 16, REC_DTYPE)
         rows = _copy(st.coeff_rows, f.ncoeff_rows * 16, np.int16).reshape(-1, 8)
         dcq = [[f.dc_quant[i][j] for j in range(2)] for i in range(3)]
-        self.frames.append(FrameWork([f.ref_idx[i] for i in range(3)], f.lf_limit, dcq, recs, rows))
+        self.frames.append(FrameWork([f.ref_idx[i] for i in range(3)], f.lf_limit, dcq, recs, rows,
+                                     dc_residual=int(f.dc_residual)))
 
     def install(self):
         lib().ocg_backend_set_capture(self._cb, None)
@@ -126,12 +129,14 @@ class Capture:
         lib().ocg_backend_set_capture(C.cast(None, CAPTURE_FN), None)
 
 
-def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None):
+def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None, dc_mode=DC_HOST):
     """Decodes `stream_blob` (tools/th_harness.c serialisation) through the
     integrated library and returns (info, [FrameWork per decoded frame],
-    [decoded frame bytes per frame or None in record mode])."""
+    [decoded frame bytes per frame or None in record mode]).  dc_mode: DC_DEVICE
+    = the lists carry DC residuals (FrameWork.dc_residual), DC_HOST = final DCs."""
     L = lib()
     L.ocg_backend_set_mode(mode)
+    L.ocg_backend_set_dc_mode(dc_mode)
     buf = (C.c_uint8 * len(stream_blob)).from_buffer_copy(stream_blob)
     sh = L.refh_stream_from_blob(buf, len(stream_blob))
     assert sh, "bad stream blob"
@@ -173,4 +178,5 @@ def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None):
         L.refh_dec_close(d)
         L.refh_stream_free(sh)
         L.ocg_backend_set_mode(BACKEND_GPU)
+        L.ocg_backend_set_dc_mode(DC_HOST)
     return g, cap.frames, outs
