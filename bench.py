@@ -440,7 +440,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=32, help="independent resident streams per GPU")
+    ap.add_argument("--streams", type=int, default=64, help="independent resident streams per GPU")
+    ap.add_argument("--stream-groups", type=int, default=4, help="CUDA streams the resident decoder streams are spread over")
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
@@ -544,9 +545,32 @@ def main():
     stream = torch.cuda.ExternalStream(ctxs[0].stream, device=dev)
     L = abi.lib()
 
+    # `groups` CUDA streams, S/groups decoder streams each: one group's ALU-bound loop filter overlaps
+    # another group's memory-bound reconstruction
+    G = max(1, min(args.stream_groups, S))
+    bounds = [S * k // G for k in range(G + 1)]
+    gstreams = [ctxs[bounds[k]].stream for k in range(G)]
+    fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in range(G)]
+
     def step():
         for f in range(nframes):
-            T.run_batch(ctxs, packs, [f] * S, ctxs[0].stream)
+            for k in range(G):
+                T.run_batch(ctxs[bounds[k]:bounds[k + 1]], packs[bounds[k]:bounds[k + 1]],
+                            [f] * (bounds[k + 1] - bounds[k]), gstreams[k])
+
+    def fork_groups():  # the other groups' streams start after everything queued on group 0's stream so far
+        if G > 1:
+            with torch.cuda.stream(stream):
+                fork.record()
+            for k in range(1, G):
+                torch.cuda.ExternalStream(gstreams[k], device=dev).wait_event(fork)
+
+    def join_groups():  # group 0's stream (where the timing events live) waits for the other groups
+        for k in range(1, G):
+            es = torch.cuda.ExternalStream(gstreams[k], device=dev)
+            with torch.cuda.stream(es):
+                joins[k].record()
+            stream.wait_event(joins[k])
 
     sampler = ClockSampler(LOCAL_RANK)  # samples through warm-up + timed region (both under the same load)
     sampler.start()
@@ -559,8 +583,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record()
-        for _ in range(args.steps):
-            step()
+    fork_groups()
+    for _ in range(args.steps):
+        step()
+    join_groups()
+    with torch.cuda.stream(stream):
         e1.record()
     e1.synchronize()
     torch.cuda.synchronize()
@@ -571,8 +598,11 @@ def main():
     value = WORLD * S * nframes * args.steps / (ms_total * 1e-3)
 
     # per-kernel device time (CUDA events on the launching stream) for the roofline
+    # (all S streams in one launch set on one CUDA stream, so the event pairs bracket one kernel each)
+    torch.cuda.synchronize()
     L.ocg_profile_enable(1)
-    step()
+    for f in range(nframes):
+        T.run_batch(ctxs, packs, [f] * S, ctxs[0].stream)
     ms3, n3 = (C.c_double * 3)(), (C.c_long * 3)()
     abi.check(L.ocg_profile_collect(ms3, n3))
     L.ocg_profile_enable(0)
@@ -696,7 +726,7 @@ def main():
                 "config": {"workload": workload, "streams_per_gpu": S, "frames_per_stream": nframes,
                            "frame_units_per_step": S * nframes, "l2": "working set of a launch (%d streams x 3 x %.1f MB "
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
-                           "parallelism": "independent streams, %d per GPU" % S},
+                           "parallelism": "independent streams, %d per GPU on %d CUDA stream(s)" % (S, G)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
                 "encode_intra": enc_intra, "motion_analysis": me_frame,
                 "gpu_launches": int(launches),

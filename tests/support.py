@@ -123,6 +123,7 @@ def _bind_harness(L):
     L.refh_dec_copy_frame.restype = C.c_long
     L.refh_dec_ctx.argtypes = [C.c_void_p]
     L.refh_dec_ctx.restype = C.c_void_p
+    L.refh_dec_set_pplevel.argtypes = [C.c_void_p, C.c_int]
     L.refh_decode_time.restype = C.c_double
     L.refh_decode_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.refh_encode_time.restype = C.c_double
@@ -206,6 +207,9 @@ class Decoder:
 
     def next(self):
         return self.lib.refh_dec_next(self.d)
+
+    def set_pplevel(self, level):
+        return self.lib.refh_dec_set_pplevel(self.d, level)
 
     def hashes(self):
         h = (C.c_uint64 * 3)()

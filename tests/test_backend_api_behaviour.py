@@ -29,7 +29,9 @@ def open_decoder(blob, mode):
     return L, sh, d, buf
 
 
-def test_postprocessing_is_refused_with_th_eimpl():
+def test_postprocessing_levels_are_accepted_like_the_reference():
+    """TH_DECCTL_SET_PPLEVEL / GET_PPLEVEL_MAX behave as in decode.c:1980-2000 (the filters themselves run
+    on the host after the flush: tests/test_gpu_postproc.py)."""
     L, sh, d, _ = open_decoder(G["s64_q48_blob"].tobytes(), streams.BACKEND_RECORD)
     assert d
     L.refh_dec_ctx.restype = C.c_void_p
@@ -37,11 +39,13 @@ def test_postprocessing_is_refused_with_th_eimpl():
     L.th_decode_ctl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     ctx = L.refh_dec_ctx(d)
     v = C.c_int(-1)
-    assert L.th_decode_ctl(ctx, TH_DECCTL_GET_PPLEVEL_MAX, C.byref(v), C.sizeof(v)) == 0 and v.value == 0
-    v = C.c_int(2)
-    assert L.th_decode_ctl(ctx, TH_DECCTL_SET_PPLEVEL, C.byref(v), C.sizeof(v)) == TH_EIMPL
+    assert L.th_decode_ctl(ctx, TH_DECCTL_GET_PPLEVEL_MAX, C.byref(v), C.sizeof(v)) == 0 and v.value == 7
+    for lvl in (2, 7, 0):
+        v = C.c_int(lvl)
+        assert L.th_decode_ctl(ctx, TH_DECCTL_SET_PPLEVEL, C.byref(v), C.sizeof(v)) == 0
+    v = C.c_int(8)
+    assert L.th_decode_ctl(ctx, TH_DECCTL_SET_PPLEVEL, C.byref(v), C.sizeof(v)) == -10  # TH_EINVAL: out of range
     v = C.c_int(0)
-    assert L.th_decode_ctl(ctx, TH_DECCTL_SET_PPLEVEL, C.byref(v), C.sizeof(v)) == 0
     assert L.th_decode_ctl(ctx, TH_DECCTL_SET_PPLEVEL, C.byref(v), 1) == -10  # TH_EINVAL, as decode.c:1985
     L.refh_dec_close(d)
     L.refh_stream_free(sh)

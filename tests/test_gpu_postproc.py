@@ -1,0 +1,49 @@
+"""TH_DECCTL_SET_PPLEVEL through the B200 back-end: the reconstruction runs on the
+device, the (non-normative) de-blocking / de-ringing filters of decode.c:1609-1957
+run on the host over the whole frame after the flush (ocg_pp_host.c).  Output
+must equal the unmodified reference decoder's at the same level, every frame."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import support as S
+from theora_b200 import streams
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (S.ref_available("c") and streams.available()),
+                                 reason="needs oracle/_ref and the integrated build")]
+
+
+def decode_all(lib, st_blob, level, nframes):
+    buf = (C.c_uint8 * len(st_blob)).from_buffer_copy(st_blob)
+    sh = lib.refh_stream_from_blob(buf, len(st_blob))
+    stream = S.Stream(lib, sh)
+    dec = S.Decoder(lib, stream)
+    assert dec.set_pplevel(level) == 0
+    out = []
+    for _ in range(nframes):
+        assert dec.next() >= 0
+        out.append(dec.frame())
+    dec.close()
+    stream.free()
+    return out
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("case", [(176, 144, 6, 10, 4, 28), (352, 288, 5, 24, 64, 30), (208, 112, 5, 5, 3, 26)])
+def test_postprocessed_output_matches_reference(case, level):
+    w, h, n, q, kf, ns = case
+    R = S.ref("c")
+    st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=1, noise_shift=ns)
+    blob = st.to_bytes()
+    st.free()
+    want = decode_all(R, blob, level, n)
+    G = streams.lib()
+    G.ocg_backend_set_mode(streams.BACKEND_GPU)
+    got = decode_all(G, blob, level, n)
+    for i in range(n):
+        assert np.array_equal(got[i], want[i]), "pp level %d: frame %d differs" % (level, i)
+    if level >= 2:
+        plain = decode_all(R, blob, 0, n)
+        assert any(not np.array_equal(plain[i], want[i]) for i in range(n)), "the filters changed nothing"

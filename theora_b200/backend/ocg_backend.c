@@ -34,6 +34,7 @@
 th_dec_ctx *oc_refimpl_decode_alloc(const th_info *_info, const th_setup_info *_setup);
 void oc_refimpl_decode_free(th_dec_ctx *_dec);
 int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
+void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_pp_host.c */
 
 typedef struct ocg_backend {
   th_dec_ctx        *dec;
@@ -164,6 +165,10 @@ static void backend_flush(ocg_backend *b) {
     stats_add(b, extra_h2d + (long)b->geom.nfrags * 16 + (long)b->nrows * 16, (long)b->geom.ref_frame_sz,
               now_s() - t0);
   }
+  /* Out-of-loop post-processing (non-normative, decode.c:2899-2914) ran inside the MCU loop on a host
+     frame that was not there yet; now that it is, run it again over the whole frame. */
+  if (b->ctx != NULL && b->dec->pipe.pp_level > 0 /* OC_PP_LEVEL_DISABLED */)
+    ocg_pp_host_whole_frame(b->dec, f.ref_idx[OCG_FRAME_SELF]);
   /* the stripe callback, once, with the whole (now final) frame:
      decode.c:2936-2940 flips the row range, the telemetry path at 2975 already
      calls it with the full range. */
@@ -384,19 +389,6 @@ void th_decode_free(th_dec_ctx *_dec) {
 int th_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz) {
   ocg_backend *b = _dec != NULL ? backend_of(_dec) : NULL;
   if (b != NULL) {
-    if (_req == TH_DECCTL_SET_PPLEVEL) {
-      if (_buf == NULL) return TH_EFAULT;
-      if (_buf_sz != sizeof(int)) return TH_EINVAL;
-      /* post-processing filters read the reconstructed frame on the host inside
-         the MCU loop (decode.c:2899-2907): not available with record-and-flush */
-      if (*(int *)_buf != 0) return TH_EIMPL;
-    }
-    if (_req == TH_DECCTL_GET_PPLEVEL_MAX) {
-      if (_buf == NULL) return TH_EFAULT;
-      if (_buf_sz != sizeof(int)) return TH_EINVAL;
-      *(int *)_buf = 0;
-      return 0;
-    }
     if (_req == TH_DECCTL_SET_STRIPE_CB) {
       if (_buf == NULL) return TH_EFAULT;
       if (_buf_sz != sizeof(th_stripe_callback)) return TH_EINVAL;

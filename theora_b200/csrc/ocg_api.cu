@@ -711,7 +711,7 @@ struct BatchScratch {
   cudaEvent_t done = nullptr;
   bool pending = false;
 };
-static thread_local BatchScratch g_bs[2];
+static thread_local BatchScratch g_bs[8]; /* job tables in flight: the host may run this many batches ahead */
 static thread_local int g_bs_i = 0;
 
 OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, const int32_t *frame_idx, int n,
@@ -722,7 +722,7 @@ OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, cons
   if (c0 == nullptr) return fail(OCG_EFAULT, "NULL context");
   CU(cudaSetDevice(c0->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c0->stream;
-  g_bs_i ^= 1;
+  g_bs_i = (g_bs_i + 1) & 7;
   BatchScratch &bs = g_bs[g_bs_i];
   if (bs.pending) { CU(cudaEventSynchronize(bs.done)); bs.pending = false; }
   if (bs.cap < n || bs.device != c0->device) {

@@ -365,6 +365,12 @@ __constant__ uint8_t c_izig[64] = {
     41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
     46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 
+/* (A one-lane-per-block variant -- whole 8x8 block in registers, static zig-zag,
+   tables in shared memory, coalesced stores through a padded tile -- was
+   measured on B200 at 4.9 G blocks/s vs 5.8 G for this 8-lanes-per-block form:
+   ~4300 instructions per block at 128 registers per lane and 25 % occupancy.
+   The transform + quantiser are instruction-bound either way: 16 one-dimensional
+   transforms and 64 quantiser evaluations per block.) */
 __global__ void __launch_bounds__(256)
 ocg_enc_fdct_quant_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__restrict__ ref_base, int ystride,
                           const ocg_enc_frag *__restrict__ frags, int n, const uint16_t *__restrict__ dequant,

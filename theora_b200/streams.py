@@ -90,6 +90,7 @@ def _bind_harness(L):
     L.refh_dec_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.refh_dec_next.argtypes = [C.c_void_p]
     L.refh_dec_rewind.argtypes = [C.c_void_p]
+    L.refh_dec_set_pplevel.argtypes = [C.c_void_p, C.c_int]
     L.refh_dec_hash.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.refh_dec_copy_frame.argtypes = [C.c_void_p, C.c_void_p]
     L.refh_dec_copy_frame.restype = C.c_long

@@ -395,6 +395,11 @@ REFH_API long refh_dec_copy_frame(const refh_dec *d, unsigned char *dst) {
 
 REFH_API th_dec_ctx *refh_dec_ctx(refh_dec *d) { return d->td; }
 
+/* TH_DECCTL_SET_PPLEVEL (theoradec.h); returns th_decode_ctl's code. */
+REFH_API int refh_dec_set_pplevel(refh_dec *d, int level) {
+  return th_decode_ctl(d->td, TH_DECCTL_SET_PPLEVEL, &level, sizeof(level));
+}
+
 /* ---------------------------------------------------------------------- */
 /* Decode timing: `nthreads` independent decoders each decode the whole stream
    `passes` times (the library is single-threaded; streams share nothing).
