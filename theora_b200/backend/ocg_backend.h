@@ -75,6 +75,27 @@ typedef struct ocg_enc_backend_stats {
   double flush_seconds;     /* host wall time inside the reconstruction flush */
 } ocg_enc_backend_stats;
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset);
+/* Test instrumentation: a snapshot at the start of every analysis pass of an encoder that runs on the
+   host (enquant_table_fixup, analyze.c:564: input frame in place, references rotated, the pass's own
+   motion search not yet started): the frame buffers by role and the per-macro-block analysis state
+   (oc_mb_enc_info, encint.h:346-382) converted to the layout of ocg_me_mb, i.e. the state the previous
+   pass left behind.  Lets a test replay the reference encoder's own motion analysis on the device. */
+typedef struct ocg_enc_spy_frame {
+  int32_t frame_type;              /* OC_INTRA_FRAME 0 / OC_INTER_FRAME 1 of the pass that is starting */
+  int32_t prevframe_dropped;
+  int32_t sp_level;
+  int32_t keyframe_frequency_force;
+  int32_t nmbs;
+  int32_t reserved;
+  int64_t curframe_num;
+  int64_t ref_frame_sz;
+  const unsigned char *frames[5];  /* whole buffers: IO, PREV_ORIG, GOLD_ORIG, PREV, GOLD (NULL: none yet) */
+  const ocg_me_mb *state;          /* nmbs entries; block_satd and ref_block_satd both hold embs.block_satd */
+  const unsigned char *refined;    /* oc_mb_enc_info.refined per macro block */
+} ocg_enc_spy_frame;
+typedef void (*ocg_enc_spy_fn)(void *user, const ocg_enc_spy_frame *frame);
+OCG_API void ocg_backend_set_enc_spy(ocg_enc_spy_fn fn, void *user); /* applies to encoders allocated afterwards */
+
 /* Test accessor: copies the encoder's current reconstruction (three top-down
    planes, frame_width x frame_height, packed); returns the byte count. */
 struct th_enc_ctx;

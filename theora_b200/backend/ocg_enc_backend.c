@@ -74,6 +74,8 @@ typedef struct ocg_enc_backend {
 static pthread_mutex_t g_elock = PTHREAD_MUTEX_INITIALIZER;
 static ocg_enc_backend *g_elist;
 static int g_enc_mode = OCG_ENC_AUTO;
+static ocg_enc_spy_fn g_enc_spy;
+static void *g_enc_spy_user;
 static __thread ocg_enc_backend *t_enc;
 static __thread int t_enc_init_failed;
 static __thread ocg_enc_backend *t_enc_created; /* made by the th_encode_alloc in progress */
@@ -81,6 +83,7 @@ static ocg_enc_backend_stats g_estats;
 static pthread_mutex_t g_estats_lock = PTHREAD_MUTEX_INITIALIZER;
 
 OCG_API void ocg_backend_set_enc_mode(int mode) { g_enc_mode = mode; }
+OCG_API void ocg_backend_set_enc_spy(ocg_enc_spy_fn fn, void *user) { g_enc_spy = fn; g_enc_spy_user = user; }
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset) {
   pthread_mutex_lock(&g_estats_lock);
   if (out) *out = g_estats;
@@ -349,6 +352,55 @@ static void ocge_no_copy_list(unsigned char *d, const unsigned char *s, int y, c
   if (n > 0) enc_fatal("frag_copy_list: inter-frame hook in the intra-only device encoder");
 }
 
+
+/* ---- test instrumentation: analysis-pass snapshots of a host encoder ------- */
+static void ocge_spy_fixup(void *_enquant[3][3][2], int _nqis) {
+  static const int ROLE[5] = {OC_FRAME_IO, OC_FRAME_PREV_ORIG, OC_FRAME_GOLD_ORIG, OC_FRAME_PREV, OC_FRAME_GOLD};
+  oc_enc_ctx *enc = (oc_enc_ctx *)((char *)_enquant - offsetof(oc_enc_ctx, enquant));
+  oc_theora_state *st = &enc->state;
+  ocg_enc_spy_frame f;
+  ocg_me_mb *mb;
+  unsigned char *refined;
+  size_t fsz, mbi;
+  int i, k;
+  oc_enc_enquant_table_fixup_c(_enquant, _nqis);
+  if (g_enc_spy == NULL) return;
+  memset(&f, 0, sizeof(f));
+  fsz = (size_t)(st->ref_frame_bufs[1][0].data - st->ref_frame_bufs[0][0].data);
+  mb = (ocg_me_mb *)calloc(st->nmbs, sizeof(*mb));
+  refined = (unsigned char *)calloc(st->nmbs, 1);
+  if (mb == NULL || refined == NULL) { free(mb); free(refined); return; }
+  for (mbi = 0; mbi < st->nmbs; mbi++) {
+    const oc_mb_enc_info *e = enc->mb_info + mbi;
+    for (i = 0; i < 3; i++) for (k = 0; k < 2; k++) mb[mbi].analysis_mv[i][k] = e->analysis_mv[i][k];
+    for (k = 0; k < 2; k++) {
+      mb[mbi].error[k] = e->error[k];
+      mb[mbi].satd[k] = e->satd[k];
+      mb[mbi].unref_mv[k] = e->unref_mv[k];
+    }
+    for (k = 0; k < 4; k++) {
+      mb[mbi].block_mv[k] = e->block_mv[k];
+      mb[mbi].ref_mv[k] = e->ref_mv[k];
+      mb[mbi].block_satd[k] = mb[mbi].ref_block_satd[k] = e->block_satd[k];
+    }
+    refined[mbi] = e->refined;
+  }
+  f.frame_type = st->frame_type;
+  f.prevframe_dropped = enc->prevframe_dropped;
+  f.sp_level = enc->sp_level;
+  f.keyframe_frequency_force = (int)enc->keyframe_frequency_force;
+  f.nmbs = (int)st->nmbs;
+  f.curframe_num = st->curframe_num;
+  f.ref_frame_sz = (ogg_int64_t)fsz;
+  for (i = 0; i < 5; i++)
+    f.frames[i] = st->ref_frame_idx[ROLE[i]] >= 0 ? st->ref_frame_handle + (size_t)st->ref_frame_idx[ROLE[i]] * fsz : NULL;
+  f.state = mb;
+  f.refined = refined;
+  (*g_enc_spy)(g_enc_spy_user, &f);
+  free(mb);
+  free(refined);
+}
+
 /* ---- set-up / tear-down --------------------------------------------------- */
 static void enc_backend_destroy(ocg_enc_backend *b) {
   ocg_enc_backend **pp;
@@ -374,7 +426,10 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   oc_enc_accel_init_c(_enc);
   t_enc_init_failed = 0;
   /* only an encoder that cannot emit inter frames takes the device path */
-  if (g_enc_mode == OCG_ENC_HOST || st->info.keyframe_granule_shift != 0) return;
+  if (g_enc_mode == OCG_ENC_HOST || st->info.keyframe_granule_shift != 0) {
+    if (g_enc_spy != NULL) _enc->opt_vtable.enquant_table_fixup = ocge_spy_fixup;
+    return;
+  }
   t_enc_init_failed = 1;
   b = (ocg_enc_backend *)calloc(1, sizeof(*b));
   if (b == NULL) return;
