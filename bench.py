@@ -619,12 +619,15 @@ def main():
     dom = max(range(3), key=lambda i: ms3[i])
     achieved = stage_bytes[dom] / (ms3[dom] / n3[dom] * 1e-3) / 1e9 if n3[dom] and stage_bytes[dom] else 0.0
     traffic = None
-    try:  # measured DRAM bytes per launch from the committed ncu capture (same streams-per-launch only)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
-        if int(tj["streams_per_launch"]) == S:
-            traffic = tj["dram_bytes_per_launch"].get(stage_names[dom])
-    except Exception:
-        traffic = None
+    for name in ("r1b_traffic.json", "r1_final_traffic.json"):
+        # measured DRAM bytes per launch from the committed ncu captures (same streams-per-launch only)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if int(tj["streams_per_launch"]) == S:
+                traffic = tj["dram_bytes_per_launch"].get(stage_names[dom])
+                break
+        except Exception:
+            continue
     roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                 "alg_bytes_per_launch": stage_bytes[dom], "kernels": kern}
