@@ -32,6 +32,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one CUDA stream per decoder/encoder thread: ask the driver for its maximum of hardware work queues before
+# anything initialises CUDA (the library's constructor does the same for C callers; see ocg_api.cu)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
@@ -158,20 +161,23 @@ def bench_encode_intra(Lo, threads, width, height, quality, frames=13):
     out = {"workload": "%dx%d 4:2:0 intra-only encode (keyframe every frame), q=%d, speed 1, %d timed frames x %d threads"
            % (width, height, quality, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
 
-    def run(L):
-        best = None
-        for _ in range(3):
-            h, b = C.c_uint64(), C.c_long()
-            secs = L.refh_encode_time_mt(width, height, frames, quality, 1, 1, 30, 12345, threads, C.byref(h), C.byref(b))
-            assert secs > 0, "encode failed"
-            if best is None or secs < best[0]:
-                best = (secs, h.value, b.value)
-        return best
+    def one(L):
+        h, b = C.c_uint64(), C.c_long()
+        secs = L.refh_encode_time_mt(width, height, frames, quality, 1, 1, 30, 12345, threads, C.byref(h), C.byref(b))
+        assert secs > 0, "encode failed"
+        return secs, h.value, b.value
+    R, kind = reference_lib()
     st = streams.EncBackendStats()
     Lo.ocg_backend_set_enc_mode(streams.ENC_AUTO)
+    one(Lo)  # warm-up: contexts, pinned pools
     Lo.ocg_backend_get_enc_stats(None, 1)
-    secs, hsh, nbytes = run(Lo)
+    ours, refs = [], []
+    for _ in range(3):  # interleaved, so that drifts of the host's speed hit both sides alike
+        ours.append(one(Lo))
+        refs.append(one(R))
     Lo.ocg_backend_get_enc_stats(C.byref(st), 0)
+    secs, hsh, nbytes = sorted(ours)[1]
+    rsecs, rhsh, rbytes = sorted(refs)[1]
     out["value"] = (frames - 1) * threads / secs
     out["api"] = "th_encode_ycbcr_in + th_encode_packetout (reference host code, B200 back-end)"
     out["device_frames"] = int(st.frames)
@@ -179,11 +185,10 @@ def bench_encode_intra(Lo, threads, width, height, quality, frames=13):
     out["flush_ms_per_frame"] = 1e3 * st.flush_seconds / max(st.frames, 1)
     out["h2d_bytes_per_frame"] = int(st.h2d_bytes / max(st.prepass_frames, 1))
     out["d2h_bytes_per_frame"] = int(st.d2h_bytes / max(st.prepass_frames, 1))
-    R, kind = reference_lib()
-    rsecs, rhsh, rbytes = run(R)
     out["cpu_baseline"] = {"value": (frames - 1) * threads / rsecs, "cores": threads,
                            "kind": "reference" if kind == "asm" else "reference (C path)"}
-    out["packets_identical_to_reference"] = bool((hsh, nbytes) == (rhsh, rbytes))
+    out["timing"] = "median of 3 passes each, ours and the reference interleaved"
+    out["packets_identical_to_reference"] = bool(all((o[1], o[2]) == (rhsh, rbytes) for o in ours))
     return out
 
 
@@ -690,15 +695,31 @@ def main():
 
     cpu = None
     if RANK == 0 and WORLD == 1 and not args.no_cpu:
-        fps, secs, kind, ref_hash = time_reference(blob, ncores, 1)
-        more = [time_reference(blob, ncores, 1) for _ in range(2)]
-        fps, secs = sorted([(fps, secs)] + [(m[0], m[1]) for m in more])[1]
+        # reference passes interleaved with further passes of ours: the host's speed drifts by +-10-20 % over a
+        # run on these boxes, and the e2e figure is host-bound, so both sides are sampled side by side
+        pairs = []
+        h2 = stream_handle(Lo, blob) if e2e is not None else None
+        for _ in range(3):
+            fps, secs, kind, ref_hash = time_reference(blob, ncores, 1)
+            o = None
+            if h2 is not None:
+                Lo.ocg_backend_set_dc_mode(streams.DC_HOST)
+                so = Lo.refh_decode_time(h2, ncores, 1, None)
+                o = ncores * nframes / so if so > 0 else None
+            pairs.append((fps, secs, o))
+        if h2 is not None:
+            Lo.refh_stream_free(h2)
+        fps, secs = sorted((p[0], p[1]) for p in pairs)[1]
         cpu = {"value": fps, "unit": "frames/s", "cores": ncores,
                "kind": "reference" if kind == "asm" else "reference (C path)",
-               "sample": "%d streams x %d frames via th_decode_packetin, %.1fs" % (ncores, nframes, secs),
+               "sample": "%d streams x %d frames via th_decode_packetin, %.1fs; median of 3" % (ncores, nframes, secs),
                "final_frame_hash": ref_hash}
         if e2e is not None:
             e2e["parity_with_cpu_baseline"] = bool(e2e["final_frame_hash"] == ref_hash)
+            side = sorted(p[2] for p in pairs if p[2])
+            if side:
+                cpu["e2e_interleaved"] = {"ours_frames_per_s": side[len(side) // 2], "reference_frames_per_s": fps,
+                                          "note": "three (reference, ours) pass pairs back to back; medians"}
 
     enc = None
     if RANK == 0 and not args.no_encode_kernels:
