@@ -156,40 +156,18 @@ def bench_encode_intra(Lo, threads, width, height, quality, frames=13):
     back-end -- device pre-pass look-ups + recorded reconstruction -- next to the
     reference x86 SIMD build on the same threads and the same frames; the first
     frame of every encoder is outside the timed region.  Packets must be
-    byte-identical (hash + size of thread 0's packets)."""
-    from theora_b200 import streams
-    out = {"workload": "%dx%d 4:2:0 intra-only encode (keyframe every frame), q=%d, speed 1, %d timed frames x %d threads"
-           % (width, height, quality, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
-
-    def one(L):
-        h, b = C.c_uint64(), C.c_long()
-        secs = L.refh_encode_time_mt(width, height, frames, quality, 1, 1, 30, 12345, threads, C.byref(h), C.byref(b))
-        assert secs > 0, "encode failed"
-        return secs, h.value, b.value
-    R, kind = reference_lib()
-    st = streams.EncBackendStats()
-    Lo.ocg_backend_set_enc_mode(streams.ENC_AUTO)
-    one(Lo)  # warm-up: contexts, pinned pools
-    Lo.ocg_backend_get_enc_stats(None, 1)
-    ours, refs = [], []
-    for _ in range(3):  # interleaved, so that drifts of the host's speed hit both sides alike
-        ours.append(one(Lo))
-        refs.append(one(R))
-    Lo.ocg_backend_get_enc_stats(C.byref(st), 0)
-    secs, hsh, nbytes = sorted(ours)[1]
-    rsecs, rhsh, rbytes = sorted(refs)[1]
-    out["value"] = (frames - 1) * threads / secs
-    out["api"] = "th_encode_ycbcr_in + th_encode_packetout (reference host code, B200 back-end)"
-    out["device_frames"] = int(st.frames)
-    out["prepass_ms_per_frame"] = 1e3 * st.prepass_seconds / max(st.prepass_frames, 1)
-    out["flush_ms_per_frame"] = 1e3 * st.flush_seconds / max(st.frames, 1)
-    out["h2d_bytes_per_frame"] = int(st.h2d_bytes / max(st.prepass_frames, 1))
-    out["d2h_bytes_per_frame"] = int(st.d2h_bytes / max(st.prepass_frames, 1))
-    out["cpu_baseline"] = {"value": (frames - 1) * threads / rsecs, "cores": threads,
-                           "kind": "reference" if kind == "asm" else "reference (C path)"}
-    out["timing"] = "median of 3 passes each, ours and the reference interleaved"
-    out["packets_identical_to_reference"] = bool(all((o[1], o[2]) == (rhsh, rbytes) for o in ours))
-    return out
+    byte-identical.  Runs in a process of its own (tools/enc_intra_bench.py: ctypes
+    only), the way a C program would use the library: inside this process torch's
+    CUDA client and thread pools share the driver and the cores with the 16 encoder
+    threads, which costs the device path ~25 %."""
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = env.get("CUDA_VISIBLE_DEVICES", "").split(",")[LOCAL_RANK] if env.get(
+        "CUDA_VISIBLE_DEVICES") else str(LOCAL_RANK)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "enc_intra_bench.py"), str(width), str(height),
+                        str(quality), str(threads), str(frames)], capture_output=True, text=True, env=env, timeout=900)
+    if p.returncode != 0:
+        raise RuntimeError("enc_intra_bench failed: " + p.stderr[-400:])
+    return json.loads(p.stdout.strip().splitlines()[-1])
 
 
 def bench_encode_kernels(torch, dev, peak, nframes=40):
@@ -641,85 +619,68 @@ def main():
     for p in packs:
         p.close()
 
-    # e2e through the public API: T host threads, packets in RAM -> frames in RAM
+    # e2e through the public API: T host threads, packets in RAM -> frames in RAM.  Measured by
+    # tools/dec_e2e_bench.py in a process of its own per rank (ctypes only, the way a C program uses the
+    # library; inside this process torch's CUDA client and thread pools share the driver and the cores with
+    # the stream threads), ours and -- on a single GPU -- the reference interleaved pass by pass.
     e2e = None
+    cpu = None
     if not args.no_e2e:
-        h = stream_handle(Lo, blob)
-        Lo.ocg_backend_set_mode(streams.BACKEND_GPU)
-        st = streams.BackendStats()
-        Lo.refh_decode_time(h, min(ncores, 2), 1, None)  # warm-up (contexts, pinned pools)
-        Lo.ocg_backend_get_stats(C.byref(st), 1)
-        barrier()
-        hsh = C.c_uint64(0)
+        blob_path = os.path.join("/tmp", "theora_b200_bench_rank%d.ogs" % RANK)
+        with open(blob_path, "wb") as f:
+            f.write(blob)
+        env = dict(os.environ)
+        vis = env.get("CUDA_VISIBLE_DEVICES", "")
+        env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[LOCAL_RANK] if vis else str(LOCAL_RANK)
+        with_ref = int(RANK == 0 and WORLD == 1 and not args.no_cpu)
 
-        def e2e_pass(nthreads, blocking, dc_mode):
-            """median of three passes: T host threads + PCIe make single passes noisy"""
-            L.ocg_set_blocking_sync(1 if blocking else 0)
-            Lo.ocg_backend_set_dc_mode(dc_mode)
-            runs = []
-            for _ in range(3):
-                Lo.ocg_backend_get_stats(C.byref(st), 1)  # reset
-                secs_i = Lo.refh_decode_time(h, nthreads, 1, C.byref(hsh))
-                st_i = streams.BackendStats()
-                Lo.ocg_backend_get_stats(C.byref(st_i), 1)
-                runs.append((secs_i, st_i, int(hsh.value)))
-            L.ocg_set_blocking_sync(0)
-            Lo.ocg_backend_set_dc_mode(streams.DC_HOST)
-            runs.sort(key=lambda r: r[0])
-            secs, st_m, hv = runs[1]
-            assert secs > 0, "e2e decode failed"
-            secs = sharding.max_over_ranks(secs, dev)
-            return {"value": WORLD * nthreads * nframes / secs, "unit": "frames/s",
-                    "h2d_bytes_per_step": int(st_m.h2d_bytes), "d2h_bytes_per_step": int(st_m.d2h_bytes),
-                    "host_threads": nthreads, "host_cores": ncores,
-                    "sync": "blocking event (thread sleeps during a flush)" if blocking else "spin",
-                    "dc_unprediction": "device (wave-front kernel)" if dc_mode == streams.DC_DEVICE else "host (reference C routine in the hook)",
-                    "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
-                    "flush_ms_per_frame": 1e3 * st_m.flush_seconds / max(st_m.frames, 1),
-                    "final_frame_hash": hv}
-        # one stream thread per core; DC un-prediction in the hook on the host (default) or by the device
-        # wave-front kernel (opt-in, measured slower).  Optional third pass: several threads per core with
-        # sleeping waits (also measured slower on this box).
-        cands = [e2e_pass(ncores, False, streams.DC_HOST)]
+        def e2e_pass(nthreads, blocking, dc_mode, ref):
+            barrier()
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dec_e2e_bench.py"), blob_path, str(nthreads),
+                                str(int(ref)), str(dc_mode), str(int(blocking))], capture_output=True, text=True, env=env,
+                               timeout=1200)
+            if p.returncode != 0:
+                raise RuntimeError("dec_e2e_bench failed: " + p.stderr[-400:])
+            d = json.loads(p.stdout.strip().splitlines()[-1])
+            secs = sharding.max_over_ranks(d["secs"], dev)
+            r = {"value": WORLD * nthreads * nframes / secs, "unit": "frames/s",
+                 "h2d_bytes_per_step": int(d["h2d_bytes"]), "d2h_bytes_per_step": int(d["d2h_bytes"]),
+                 "host_threads": nthreads, "host_cores": ncores,
+                 "sync": "blocking event (thread sleeps during a flush)" if blocking else "spin",
+                 "dc_unprediction": "device (wave-front kernel)" if dc_mode == streams.DC_DEVICE else "host (reference C routine in the hook)",
+                 "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
+                 "flush_ms_per_frame": d["flush_ms_per_frame"], "final_frame_hash": d["hash"],
+                 "timing": "median of 3 passes, in a process of its own per rank"}
+            return r, d
+        main_pass, raw = e2e_pass(ncores, False, streams.DC_HOST, with_ref)
+        cands = [main_pass]
         if args.e2e_variants:
-            cands.append(e2e_pass(ncores, False, streams.DC_DEVICE))
+            cands.append(e2e_pass(ncores, False, streams.DC_DEVICE, 0)[0])
         if args.e2e_oversub > 1:
-            cands.append(e2e_pass(ncores * args.e2e_oversub, True, streams.DC_DEVICE))
+            cands.append(e2e_pass(ncores * args.e2e_oversub, True, streams.DC_HOST, 0)[0])
         hashes = {c["final_frame_hash"] for c in cands}
         cands.sort(key=lambda r: -r["value"])
         e2e = cands[0]
         e2e["alternatives"] = [{k: c[k] for k in ("value", "host_threads", "sync", "dc_unprediction", "flush_ms_per_frame")}
                                for c in cands[1:]]
         e2e["all_variants_same_output"] = len(hashes) == 1
-        Lo.refh_stream_free(h)
-
-    cpu = None
-    if RANK == 0 and WORLD == 1 and not args.no_cpu:
-        # reference passes interleaved with further passes of ours: the host's speed drifts by +-10-20 % over a
-        # run on these boxes, and the e2e figure is host-bound, so both sides are sampled side by side
-        pairs = []
-        h2 = stream_handle(Lo, blob) if e2e is not None else None
-        for _ in range(3):
-            fps, secs, kind, ref_hash = time_reference(blob, ncores, 1)
-            o = None
-            if h2 is not None:
-                Lo.ocg_backend_set_dc_mode(streams.DC_HOST)
-                so = Lo.refh_decode_time(h2, ncores, 1, None)
-                o = ncores * nframes / so if so > 0 else None
-            pairs.append((fps, secs, o))
-        if h2 is not None:
-            Lo.refh_stream_free(h2)
-        fps, secs = sorted((p[0], p[1]) for p in pairs)[1]
+        if "ref_secs" in raw:
+            rfps = ncores * nframes / raw["ref_secs"]
+            cpu = {"value": rfps, "unit": "frames/s", "cores": ncores,
+                   "kind": "reference" if raw["ref_kind"] == "asm" else "reference (C path)",
+                   "sample": "%d streams x %d frames via th_decode_packetin, %.1fs; median of 3 passes interleaved with ours"
+                   % (ncores, nframes, raw["ref_secs"]), "final_frame_hash": raw["ref_hash"]}
+            e2e["parity_with_cpu_baseline"] = bool(main_pass["final_frame_hash"] == raw["ref_hash"])
+        try:
+            os.remove(blob_path)
+        except OSError:
+            pass
+    if cpu is None and RANK == 0 and WORLD == 1 and not args.no_cpu:
+        fps, secs, kind, ref_hash = sorted(time_reference(blob, ncores, 1) for _ in range(3))[1]
         cpu = {"value": fps, "unit": "frames/s", "cores": ncores,
                "kind": "reference" if kind == "asm" else "reference (C path)",
                "sample": "%d streams x %d frames via th_decode_packetin, %.1fs; median of 3" % (ncores, nframes, secs),
                "final_frame_hash": ref_hash}
-        if e2e is not None:
-            e2e["parity_with_cpu_baseline"] = bool(e2e["final_frame_hash"] == ref_hash)
-            side = sorted(p[2] for p in pairs if p[2])
-            if side:
-                cpu["e2e_interleaved"] = {"ours_frames_per_s": side[len(side) // 2], "reference_frames_per_s": fps,
-                                          "note": "three (reference, ours) pass pairs back to back; medians"}
 
     enc = None
     if RANK == 0 and not args.no_encode_kernels:

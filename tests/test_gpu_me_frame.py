@@ -107,3 +107,33 @@ def test_batch_of_streams_matches_single_calls():
         L.ocg_me_destroy(m)
     for c in ctxs:
         c.close()
+
+
+def test_me_api_rejects_bad_arguments():
+    """Error behaviour of the ocg_me_* entry points: negative codes, never a crash."""
+    L = abi.lib()
+    g3 = S.make_geometry(64, 64, 0, 3)
+    g6 = S.make_geometry(64, 64, 0, 6)
+    me = C.c_void_p()
+    assert L.ocg_me_create(C.byref(me), None, None) == -1            # OCG_EFAULT
+    ctx3 = T.Context(g3, 0)
+    assert L.ocg_me_create(C.byref(me), ctx3.h, None) == -10         # needs IO + 2 originals + 2 reconstructions
+    ctx3.close()
+    ctx = T.Context(g6, 0)
+    n = L.ocg_me_nmbs(C.byref(g6))
+    topo = np.zeros(n, abi.ME_TOPO_DTYPE)
+    assert L.ocg_me_topology(C.byref(g6), topo.ctypes.data) == 0
+    bad = topo.copy()
+    last = int(np.nonzero(bad["valid"])[0][-1])
+    first = int(np.nonzero(bad["valid"])[0][0])
+    bad["cn"][first][0] = last                                       # a neighbour that comes LATER in coding order
+    bad["ncn"][first] = 1
+    assert L.ocg_me_create(C.byref(me), ctx.h, bad.ctypes.data) == -10
+    abi.check(L.ocg_me_create(C.byref(me), ctx.h, topo.ctypes.data), "ocg_me_create")
+    assert L.ocg_me_frame(me, None, 0, None) == -1
+    assert L.ocg_me_frame(me, (C.c_int * 5)(0, 1, 2, 3, 4), 1 << 9, None) == -10   # unknown flag
+    assert L.ocg_me_frame(me, (C.c_int * 5)(0, 1, 2, 3, 9), 0, None) == -10        # buffer index out of range
+    assert L.ocg_me_read(me, None) == -1
+    L.ocg_me_destroy(me)
+    L.ocg_me_destroy(None)
+    ctx.close()

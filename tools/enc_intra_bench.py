@@ -1,0 +1,56 @@
+"""BASELINE configs[2] through th_encode_ycbcr_in / th_encode_packetout, measured in a plain process
+(ctypes only: no torch, no second CUDA client in the process), ours and the reference interleaved.
+Prints one JSON object; bench.py embeds it as `encode_intra`."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
+def main():
+    width, height, quality, threads, frames = (int(a) for a in sys.argv[1:6])
+    import support as S
+    from theora_b200 import streams
+    Lo = streams.lib()
+    kind = "asm" if S.ref_available("asm") else "c"
+    R = S.ref(kind)
+    out = {"workload": "%dx%d 4:2:0 intra-only encode (keyframe every frame), q=%d, speed 1, %d timed frames x %d threads"
+           % (width, height, quality, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
+
+    def one(L):
+        h, b = C.c_uint64(), C.c_long()
+        secs = L.refh_encode_time_mt(width, height, frames, quality, 1, 1, 30, 12345, threads, C.byref(h), C.byref(b))
+        assert secs > 0, "encode failed"
+        return secs, h.value, b.value
+    st = streams.EncBackendStats()
+    Lo.ocg_backend_set_enc_mode(streams.ENC_AUTO)
+    one(Lo)  # warm-up: contexts, pinned pools
+    Lo.ocg_backend_get_enc_stats(None, 1)
+    ours, refs = [], []
+    for _ in range(3):  # interleaved, so that drifts of the host's speed hit both sides alike
+        ours.append(one(Lo))
+        refs.append(one(R))
+    Lo.ocg_backend_get_enc_stats(C.byref(st), 0)
+    secs, hsh, nbytes = sorted(ours)[1]
+    rsecs, rhsh, rbytes = sorted(refs)[1]
+    out["value"] = (frames - 1) * threads / secs
+    out["api"] = "th_encode_ycbcr_in + th_encode_packetout (reference host code, B200 back-end)"
+    out["device_frames"] = int(st.frames)
+    out["prepass_ms_per_frame"] = 1e3 * st.prepass_seconds / max(st.prepass_frames, 1)
+    out["flush_ms_per_frame"] = 1e3 * st.flush_seconds / max(st.frames, 1)
+    out["h2d_bytes_per_frame"] = int(st.h2d_bytes / max(st.prepass_frames, 1))
+    out["d2h_bytes_per_frame"] = int(st.d2h_bytes / max(st.prepass_frames, 1))
+    out["cpu_baseline"] = {"value": (frames - 1) * threads / rsecs, "cores": threads,
+                           "kind": "reference" if kind == "asm" else "reference (C path)"}
+    out["timing"] = "median of 3 passes each, ours and the reference interleaved, in a process of its own"
+    out["packets_identical_to_reference"] = bool(all((o[1], o[2]) == (rhsh, rbytes) for o in ours))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
