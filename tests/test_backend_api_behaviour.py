@@ -1,5 +1,5 @@
 """API behaviour of the integrated library that differs from / must match the
-reference: post-processing is refused, the stripe
+reference: post-processing levels are accepted, the stripe
 callback is delivered once per frame, dropped (0-byte) packets are
 TH_DUPFRAME, a missing device fails th_decode_alloc.  CPU-only parts use the
 recorder mode; the GPU parts are marked."""

@@ -17,9 +17,11 @@
  *                           reference buffer th_decode_ycbcr_out hands out.
  * th_decode_alloc / th_decode_free / th_decode_ctl are thin wrappers around
  * the reference's own functions (renamed at compile time) so device state
- * follows the decoder's life time, post-processing (which would read stale
- * host pixels inside the MCU loop, decode.c:2899-2907) is refused with
- * TH_EIMPL, and the stripe callback is delivered once per frame after flush.
+ * follows the decoder's life time and the stripe callback is delivered once per
+ * frame after the flush.  Post-processing (TH_DECCTL_SET_PPLEVEL > 0), which the
+ * reference runs inside the MCU loop on host pixels that are not there yet
+ * (decode.c:2899-2914), is re-run over the whole frame after the flush by the
+ * reference's own filters (ocg_pp_host.c).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -278,9 +280,8 @@ static void ocg_restore_fpu(void) {
 
 /* ---- init functions named by ocg_hooks.h --------------------------------- */
 void oc_state_accel_init_ocg(oc_theora_state *_state) {
-  /* shared encoder/decoder table: plain C entries; the decoder init below
-     overrides the ones it offloads (the encoder keeps the C block kernels
-     until its batched analysis front-end lands). */
+  /* shared encoder/decoder table: plain C entries; the decoder and encoder inits
+     override the ones they offload (ocg_enc_backend.c for intra-only encoders). */
   oc_state_accel_init_c(_state);
 }
 
