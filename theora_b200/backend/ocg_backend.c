@@ -36,7 +36,10 @@
 th_dec_ctx *oc_refimpl_decode_alloc(const th_info *_info, const th_setup_info *_setup);
 void oc_refimpl_decode_free(th_dec_ctx *_dec);
 int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
-void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_pp_host.c */
+void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_dec_host.c */
+int ocg_host_expand_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli, ptrdiff_t _ncoded,
+                              ptrdiff_t _nuncoded, ocg_frag_rec *_recs, ogg_int16_t *_rows, int _nrows0,
+                              ogg_uint16_t _dcq_out[2], unsigned *_stray); /* ocg_dec_host.c */
 
 typedef struct ocg_backend {
   th_dec_ctx        *dec;
@@ -54,6 +57,8 @@ typedef struct ocg_backend {
   unsigned char      dev_valid[6];
   int                pinned;
   int                dc_device;   /* DC prediction is undone on the device (records carry residuals) */
+  int                expand;      /* the back-end expands the tokens itself (ocg_host_expand_mcu_plane) */
+  unsigned           stray;       /* see ocg_host_expand_mcu_plane */
   th_stripe_callback user_cb;
   struct ocg_backend *next;
 } ocg_backend;
@@ -62,6 +67,7 @@ static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static ocg_backend *g_list;
 static int g_mode = OCG_BACKEND_GPU;
 static int g_dc_mode = OCG_DC_HOST;
+static int g_expand_mode = OCG_EXPAND_BACKEND;
 static ocg_capture_fn g_capture;
 static void *g_capture_user;
 static int g_device; /* one process per GPU: process-wide */
@@ -72,6 +78,7 @@ static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 OCG_API void ocg_backend_set_mode(int mode) { g_mode = mode; }
 OCG_API void ocg_backend_set_device(int device) { g_device = device; }
 OCG_API void ocg_backend_set_dc_mode(int mode) { g_dc_mode = mode; }
+OCG_API void ocg_backend_set_expand_mode(int mode) { g_expand_mode = mode; }
 OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user) { g_capture = fn; g_capture_user = user; }
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset) {
   pthread_mutex_lock(&g_stats_lock);
@@ -122,6 +129,7 @@ static void backend_begin_frame(ocg_backend *b) {
      (decode.c:1584,1601), which refresh the rest */
   if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
   b->ncoded = b->nrows = 0;
+  b->stray = 0;
   /* decode.c:2790-2794 has already picked SELF; GOLD/PREV are still the
      references this frame predicts from (they rotate at 2947-2962). */
   for (i = 0; i < 3; i++) b->ref_idx[i] = st->ref_frame_idx[i];
@@ -200,6 +208,18 @@ static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *
     oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
   }
   if (b != NULL && !b->frame_open) backend_begin_frame(b);
+  if (b != NULL && b->expand) {
+    /* claim the MCU's fragments: expand their tokens straight into the flush lists and leave
+       oc_dec_frags_recon_mcu_plane (decode.c:1511) an empty range */
+    const ptrdiff_t ncoded = _pipe->ncoded_fragis[_pli], nuncoded = _pipe->nuncoded_fragis[_pli];
+    ogg_uint16_t dcq[2];
+    b->nrows += ocg_host_expand_mcu_plane(_dec, _pipe, _pli, ncoded, nuncoded, b->st.recs, b->st.coeff_rows, b->nrows,
+                                          dcq, &b->stray);
+    if (ncoded > 0) { b->dcq[_pli][0] = dcq[0]; b->dcq[_pli][1] = dcq[1]; }
+    b->ncoded += (int)ncoded;
+    _pipe->ncoded_fragis[_pli] = 0;
+    _pipe->nuncoded_fragis[_pli] = 0;
+  }
 }
 
 static inline int row_nonzero(const ogg_int16_t *row) {
@@ -331,6 +351,7 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
     free(b);
     return;
   }
+  b->expand = g_expand_mode == OCG_EXPAND_BACKEND;
   b->dc_device = g_dc_mode == OCG_DC_DEVICE && (b->mode != OCG_BACKEND_GPU || ocg_dc_unpredict_supported(&b->geom));
   if (b->mode == OCG_BACKEND_GPU) {
     if (ocg_ctx_create(&b->ctx, &b->geom, g_device) < 0) {

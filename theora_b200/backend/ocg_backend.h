@@ -34,6 +34,15 @@ OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders al
 #define OCG_DC_HOST   1
 OCG_API void ocg_backend_set_dc_mode(int mode);   /* applies to decoders allocated afterwards */
 
+/* Who expands a coded fragment's tokens into coefficients (decode.c:1531-1586):
+   OCG_EXPAND_BACKEND (default): the back-end, inside the dc_unpredict_mcu_plane hook, straight into the
+   pinned flush lists (ocg_host_expand_mcu_plane); oc_dec_frags_recon_mcu_plane is left an empty range.
+   OCG_EXPAND_REFERENCE: the reference's loop, one state_frag_recon hook call per fragment (the recorder
+   then re-finds, copies and clears the non-zero rows).  Identical lists either way. */
+#define OCG_EXPAND_BACKEND   0
+#define OCG_EXPAND_REFERENCE 1
+OCG_API void ocg_backend_set_expand_mode(int mode);   /* applies to decoders allocated afterwards */
+
 /* Called at every frame flush with the frame description (list pointers NULL)
    and the staged lists, before they are submitted. */
 typedef void (*ocg_capture_fn)(void *user, const ocg_dec_frame *frame, const ocg_staging *lists);

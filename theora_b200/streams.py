@@ -35,6 +35,7 @@ class EncBackendStats(C.Structure):
 
 ENC_AUTO, ENC_HOST = 0, 1
 DC_DEVICE, DC_HOST = 0, 1
+EXPAND_BACKEND, EXPAND_REFERENCE = 0, 1
 
 _lib = None
 
@@ -55,6 +56,7 @@ def lib():
         L.ocg_backend_set_mode.argtypes = [C.c_int]
         L.ocg_backend_set_device.argtypes = [C.c_int]
         L.ocg_backend_set_dc_mode.argtypes = [C.c_int]
+        L.ocg_backend_set_expand_mode.argtypes = [C.c_int]
         L.ocg_backend_set_capture.argtypes = [CAPTURE_FN, C.c_void_p]
         L.ocg_backend_get_stats.argtypes = [C.POINTER(BackendStats), C.c_int]
         L.ocg_backend_set_enc_mode.argtypes = [C.c_int]

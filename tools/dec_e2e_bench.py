@@ -16,6 +16,7 @@ def main():
     path, threads, with_ref = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     dc_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1   # streams.DC_HOST
     blocking = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    expand = int(sys.argv[6]) if len(sys.argv) > 6 else 0     # OCG_EXPAND_BACKEND
     import support as S
     from theora_b200 import streams
     blob = open(path, "rb").read()
@@ -25,6 +26,7 @@ def main():
     nframes = Lo.refh_stream_npackets(h) - 3
     Lo.ocg_backend_set_mode(streams.BACKEND_GPU)
     Lo.ocg_backend_set_dc_mode(dc_mode)
+    Lo.ocg_backend_set_expand_mode(expand)
     from theora_b200 import abi
     abi.lib().ocg_set_blocking_sync(blocking)
     Lo.refh_decode_time(h, min(threads, 2), 1, None)  # warm-up
