@@ -116,10 +116,12 @@ typedef struct ocg_dec_frame {
   int32_t             ncoded;          /* coded fragments in recs (informational)  */
   int32_t             intra_frame;     /* 1: key frame, no record references PREV/GOLD */
   int32_t             ncoeff_rows;
-  int32_t             dc_residual;     /* 1: recs[].dc hold the DC-prediction RESIDUALS as decoded
-                                          (decode.c:1277-1316) and the device undoes the prediction
+  int32_t             dc_residual;     /* 0: recs[].dc are final (the host undid the DC prediction).
+                                          1: recs[].dc hold the DC-prediction RESIDUALS as decoded
+                                          (decode.c:1277-1316); the device undoes the prediction
                                           (oc_dec_dc_unpredict_mcu_plane, decode.c:1392-1500) before
-                                          reconstructing; 0: recs[].dc are final (host did it)      */
+                                          reconstructing.  2: the final values were computed ahead of
+                                          the lists by ocg_dec_dc_begin and replace recs[].dc       */
   const ocg_frag_rec *recs;            /* nfrags records, fragment-index order     */
   const int16_t      *coeff_rows;      /* ncoeff_rows x 8 int16                    */
 } ocg_dec_frame;
@@ -146,6 +148,13 @@ OCG_API int  ocg_ctx_sync(ocg_ctx *ctx);
    wave-front kernel runs one thread per fragment row of a plane, at most 1024
    rows, reference types of a plane in shared memory), else 0. */
 OCG_API int  ocg_dc_unpredict_supported(const ocg_geometry *g);
+/* Starts the DC un-prediction of the frame that is being assembled, ahead of its lists: everything the
+   recurrence needs (coded flag, reference type, DC residual of every fragment) is known as soon as the
+   packet's tokens are unpacked, i.e. before the host expands a single coefficient, so the wave-front
+   kernel can run on the device WHILE the host builds the lists.  frag_words: the decoder's oc_fragment
+   array (state.h:297-322) viewed as 32-bit words (bit 0 coded, bits 6-7 refi, bits 16-31 dc residual);
+   copied before the call returns.  Submit the frame with dc_residual = 2. */
+OCG_API int  ocg_dec_dc_begin(ocg_ctx *ctx, const uint32_t *frag_words);
 OCG_API void *ocg_ctx_stream(ocg_ctx *ctx);                 /* cudaStream_t */
 OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *ctx, int buf);  /* device address of buffer `buf` */
 /* Whole padded buffer, host <-> device (ref_frame_sz bytes). */

@@ -138,6 +138,7 @@ _PROTOS = {
     "ocg_ctx_geometry": (C.POINTER(Geometry), [C.c_void_p]),
     "ocg_ctx_sync": (C.c_int, [C.c_void_p]),
     "ocg_dc_unpredict_supported": (C.c_int, [C.POINTER(Geometry)]),
+    "ocg_dec_dc_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ocg_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "ocg_ctx_frame_devptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ocg_ctx_upload_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

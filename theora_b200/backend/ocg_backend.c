@@ -59,6 +59,7 @@ typedef struct ocg_backend {
   int                dc_device;   /* DC prediction is undone on the device (records carry residuals) */
   int                expand;      /* the back-end expands the tokens itself (ocg_host_expand_mcu_plane) */
   unsigned           stray;       /* see ocg_host_expand_mcu_plane */
+  int                dc_ahead;    /* ocg_dec_dc_begin was called for the frame being assembled */
   th_stripe_callback user_cb;
   struct ocg_backend *next;
 } ocg_backend;
@@ -135,6 +136,14 @@ static void backend_begin_frame(ocg_backend *b) {
   for (i = 0; i < 3; i++) b->ref_idx[i] = st->ref_frame_idx[i];
   memset(b->dcq, 0, sizeof(b->dcq));
   b->frame_open = 1;
+  b->dc_ahead = 0;
+  if (b->dc_device && b->ctx != NULL) {
+    /* Every input of the DC recurrence (coded flags, reference types, residuals) is in frags[] once the
+       tokens are unpacked (decode.c:2822), i.e. now: the device starts on it while the host expands
+       the coefficients of the whole frame. */
+    if (ocg_dec_dc_begin(b->ctx, (const ogg_uint32_t *)st->frags) < 0) backend_fatal("ocg_dec_dc_begin failed");
+    b->dc_ahead = 1;
+  }
 }
 
 static void backend_flush(ocg_backend *b) {
@@ -149,7 +158,8 @@ static void backend_flush(ocg_backend *b) {
   f.ncoded = b->ncoded;
   f.intra_frame = st->frame_type == OC_INTRA_FRAME;
   f.ncoeff_rows = b->nrows;
-  f.dc_residual = b->dc_device;
+  f.dc_residual = b->dc_device ? (b->dc_ahead ? 2 : 1) : 0;
+  b->dc_ahead = 0;
   b->frame_open = 0;
   if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
   if (b->ctx == NULL) { stats_add(b, 0, 0, 0.0); return; } /* record mode */
@@ -353,6 +363,16 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
   }
   b->expand = g_expand_mode == OCG_EXPAND_BACKEND;
   b->dc_device = g_dc_mode == OCG_DC_DEVICE && (b->mode != OCG_BACKEND_GPU || ocg_dc_unpredict_supported(&b->geom));
+  if (b->dc_device && b->mode == OCG_BACKEND_GPU) {
+    /* the device reads oc_fragment as a 32-bit word: bit 0 coded, bits 6-7 refi, bits 16-31 dc (state.h:297-322
+       as this compiler lays the bit-fields out); verify instead of assuming */
+    oc_fragment t;
+    ogg_uint32_t w;
+    memset(&t, 0, sizeof(t));
+    t.coded = 1; t.refi = 2; t.dc = -3;
+    memcpy(&w, &t, sizeof(w));
+    if (sizeof(t) != 4 || w != (1u | 2u << 6 | 0xFFFDu << 16)) b->dc_device = 0;
+  }
   if (b->mode == OCG_BACKEND_GPU) {
     if (ocg_ctx_create(&b->ctx, &b->geom, g_device) < 0) {
       fprintf(stderr, "theora_b200 back-end: %s\n", ocg_last_error());

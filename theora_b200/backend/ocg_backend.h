@@ -17,19 +17,20 @@ OCG_API void ocg_backend_set_mode(int mode);      /* applies to decoders allocat
 OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders allocated afterwards (process-wide: one process per GPU) */
 
 /* Where the DC prediction is undone (oc_dec_dc_unpredict_mcu_plane, decode.c:1392):
-   OCG_DC_HOST (default): the reference's C routine runs in the hook and the
-   records carry final DC values (also what resident packs need).
-   OCG_DC_DEVICE: the hook only counts the coded fragments of the MCU (its other
-   duty, decode.c:1496-1499); the records carry the DC residuals and the device
-   runs the wave-front kernel before reconstructing (dc_residual=1); geometries
-   the kernel does not cover (ocg_dc_unpredict_supported) stay on the host.
-   Bit-exact either way.  Measured on B200 (1080p): a key frame costs +0.07 ms
-   of device time, but an inter frame with mixed reference types +0.5..1.1 ms,
-   because the "last value of the same reference type" predictor (decode.c:1452)
-   links rows end-to-start and the dependency chain grows to thousands of
-   fragments, ~0.25 us each on a GPU vs ~7 ns on a CPU core: through
-   th_decode_packetin the device variant is slower (6.8 k vs 10.6 k frames/s),
-   hence opt-in. */
+   OCG_DC_HOST: the reference's C routine runs in the hook and the records carry final DC values (also
+   what resident packs need).
+   OCG_DC_DEVICE: the hook only counts the coded fragments of the MCU (its other duty,
+   decode.c:1496-1499).  On the device path the recurrence is started at the first hook of the frame
+   (ocg_dec_dc_begin: its inputs are all in frags[] by then) and runs WHILE the host expands the frame's
+   coefficients; the flush patches the final values into the records (dc_residual=2).  In record mode the
+   records simply carry the residuals (dc_residual=1).  Geometries the kernel does not cover
+   (ocg_dc_unpredict_supported) stay on the host.  Bit-exact either way.
+   The kernel alone is slow on inter frames (the "last value of the same reference type" predictor,
+   decode.c:1452, links rows end-to-start: chains of thousands of fragments at ~0.25 us each vs ~7 ns on a
+   CPU core; +0.5..1.1 ms per 1080p inter frame).  Started ahead of the lists it overlaps the host's
+   ~0.55 ms of coefficient expansion, which is not enough to hide it: measured through
+   th_decode_packetin 8.5 k vs 11.5 k frames/s for OCG_DC_HOST (6.8 k when the kernel sits in the flush),
+   so the host routine stays the default. */
 #define OCG_DC_DEVICE 0
 #define OCG_DC_HOST   1
 OCG_API void ocg_backend_set_dc_mode(int mode);   /* applies to decoders allocated afterwards */

@@ -64,6 +64,9 @@ struct ocg_ctx {
   int16_t *d_rows = nullptr;
   uint8_t *d_map = nullptr;  /* coded map, produced by the recon kernel */
   int16_t *d_dc_tmp = nullptr; /* DC wave-front scratch (planes too large for shared memory) */
+  uint32_t *d_dc_words = nullptr; /* ocg_dec_dc_begin: the decoder's packed fragment words */
+  int16_t *d_dc_final = nullptr;  /* ... and the final DC values computed from them */
+  bool dc_ahead = false;          /* ocg_dec_dc_begin ran for the frame being assembled */
   int32_t *d_xlist = nullptr; /* transform work list + 2 counters behind it */
   CUtensorMap *d_tmaps = nullptr; /* [nrefs][3] tiled views of the padded planes for the TMA loop filter */
   OcgJobDev *d_job = nullptr;
@@ -125,7 +128,7 @@ static void fill_job(OcgJobDev &j, const ocg_ctx *c, const ocg_dec_frame &f, con
   j.xlist = c->d_xlist;
   j.xcount = c->d_xlist + c->geom.nfrags;
   j.lf_limit = f.lf_limit;
-  j.dc_residual = f.dc_residual != 0;
+  j.dc_residual = f.dc_residual == 1;
   j.dc_tmp = c->d_dc_tmp;
   j.lf_tmaps = c->d_tmaps ? c->d_tmaps + (size_t)f.ref_idx[OCG_FRAME_SELF] * 3 : nullptr;
   for (int p = 0; p < 3; p++)
@@ -361,6 +364,8 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
   cudaFree(c->d_rows);
   cudaFree(c->d_map);
   cudaFree(c->d_dc_tmp);
+  cudaFree(c->d_dc_words);
+  cudaFree(c->d_dc_final);
   cudaFree(c->d_xlist);
   cudaFree(c->d_tmaps);
   cudaFree(c->d_job);
@@ -405,6 +410,8 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   CUX(cudaMalloc(&c->d_rows, nf * 8 * 16));
   CUX(cudaMalloc(&c->d_map, nf));
   CUX(cudaMalloc(&c->d_dc_tmp, nf * sizeof(int16_t)));
+  CUX(cudaMalloc(&c->d_dc_words, nf * sizeof(uint32_t)));
+  CUX(cudaMalloc(&c->d_dc_final, nf * sizeof(int16_t)));
   CUX(cudaMalloc(&c->d_xlist, (nf + 2) * sizeof(int32_t)));
   CUX(cudaMemsetAsync(c->d_xlist, 0, (nf + 2) * sizeof(int32_t), c->stream));
   CUX(cudaMalloc(&c->d_job, sizeof(OcgJobDev)));
@@ -549,12 +556,29 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
   CU(cudaMemcpyAsync(c->d_job, s.job, sizeof(OcgJobDev), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(s.consumed, st));
   s.busy = true;
-  launch_stages(c->gdev, c->d_job, 1, f->lf_limit != 0, c->d_tmaps != nullptr && g_use_tma.load(), st, f->dc_residual != 0);
+  if (f->dc_residual == 2) {
+    if (!c->dc_ahead) return fail(OCG_EINVAL, "dc_residual=2 without a preceding ocg_dec_dc_begin");
+    ocg_launch_dc_patch(c->d_recs, c->d_dc_final, c->geom.nfrags, st);
+  }
+  c->dc_ahead = false;
+  launch_stages(c->gdev, c->d_job, 1, f->lf_limit != 0, c->d_tmaps != nullptr && g_use_tma.load(), st, f->dc_residual == 1);
   CU(cudaGetLastError());
   if (host_out != nullptr) {
     CU(cudaMemcpyAsync(host_out, c->frames + (size_t)f->ref_idx[OCG_FRAME_SELF] * c->geom.ref_frame_sz,
                        (size_t)c->geom.ref_frame_sz, cudaMemcpyDeviceToHost, st));
   }
+  return OCG_OK;
+}
+
+OCG_API int ocg_dec_dc_begin(ocg_ctx *c, const uint32_t *frag_words) {
+  if (c == nullptr || frag_words == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  if (!ocg_dc_unpredict_supported(&c->geom)) return fail(OCG_EIMPL, "DC un-prediction on the device does not support this frame size");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->d_dc_words, frag_words, (size_t)c->geom.nfrags * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (ocg_launch_dc_unpredict_words(c->gdev, c->d_dc_words, c->d_dc_final, c->d_dc_tmp, c->stream) < 0)
+    return fail(OCG_EIMPL, "DC un-prediction launch failed");
+  CU(cudaGetLastError());
+  c->dc_ahead = true;
   return OCG_OK;
 }
 
@@ -754,7 +778,7 @@ OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, cons
     int r = check_frame(c->geom, f);
     if (r < 0) return r;
     /* a resident frame is replayed: its records must not be rewritten in place */
-    if (f.dc_residual) return fail(OCG_EINVAL, "resident packs hold final DC values (dc_residual frames go through ocg_dec_submit)");
+    if (f.dc_residual != 0) return fail(OCG_EINVAL, "resident packs hold final DC values (dc_residual frames go through ocg_dec_submit)");
     fill_job(bs.h[i], c, f, f.recs, f.coeff_rows);
     any_lf |= f.lf_limit != 0;
     all_tma = all_tma && c->d_tmaps != nullptr;

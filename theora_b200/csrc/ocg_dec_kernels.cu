@@ -820,27 +820,52 @@ ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
    records the reconstruction kernels read. */
 #define OCG_DC_MAX_ROWS 1024
 
+/* Inputs/outputs of one DC job: either the fragment records (dc rewritten in place), or -- when the kernel
+   runs ahead of the frame's lists -- the decoder's packed fragment words (oc_fragment, state.h:297-322:
+   bit 0 coded, bits 6-7 refi, bits 16-31 dc) and a separate array of final values. */
+struct OcgDcArgs {
+  ocg_frag_rec *recs;
+  const uint32_t *words;
+  int16_t *dc_final;
+  int16_t *dc_tmp;
+};
+
 template <bool DC_IN_SMEM>
 __global__ void __launch_bounds__(OCG_DC_MAX_ROWS)
-ocg_dc_unpredict_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  const OcgJobDev &job = jobs[blockIdx.y];
-  if (!job.dc_residual) return;
+ocg_dc_unpredict_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs, const OcgDcArgs single) {
+  OcgDcArgs A = single;
+  if (jobs != nullptr) {
+    const OcgJobDev &job = jobs[blockIdx.y];
+    if (job.dc_residual != 1) return;
+    A.recs = const_cast<ocg_frag_rec *>(job.recs);
+    A.words = nullptr;
+    A.dc_final = nullptr;
+    A.dc_tmp = job.dc_tmp;
+  }
   const OcgPlaneDev &P = g.p[blockIdx.x];
   const int nh = P.nhfrags, nv = P.nvfrags, nfr = nh * nv;
-  ocg_frag_rec *recs = const_cast<ocg_frag_rec *>(job.recs) + P.froffset;
+  ocg_frag_rec *recs = A.recs != nullptr ? A.recs + P.froffset : nullptr;
+  const uint32_t *words = A.words != nullptr ? A.words + P.froffset : nullptr;
+  int16_t *dc_final = A.dc_final != nullptr ? A.dc_final + P.froffset : nullptr;
   extern __shared__ __align__(16) unsigned char smem[];
   int *progress = (int *)smem;                 /* [2][nv] */
   int *rowlast = progress + 2 * nv;            /* [3][nv] last coded x of each reference type in a row, or -1 */
   int *prevrow = rowlast + 3 * nv;             /* [3][nv] nearest earlier row that has one, or -1 */
   uint8_t *refs = (uint8_t *)(prevrow + 3 * nv); /* [nfr] 0..2 = reference type, 3 = not coded */
   volatile int16_t *dcs = DC_IN_SMEM ? (volatile int16_t *)(refs + ((nfr + 15) & ~15))
-                                     : (volatile int16_t *)(job.dc_tmp + P.froffset);
+                                     : (volatile int16_t *)(A.dc_tmp + P.froffset);
   const int y = (int)threadIdx.x;
   for (int i = (int)threadIdx.x; i < nfr; i += (int)blockDim.x) {
-    const uint2 lo = *(const uint2 *)(recs + i); /* buf_off, mv|dc<<16 */
-    const uint32_t hi = ((const uint32_t *)(recs + i))[3]; /* rowmask, last_zzi, refi, pli_qti */
-    refs[i] = (uint8_t)((hi >> 16) & 0xFFu);
-    dcs[i] = (int16_t)(lo.y >> 16);
+    if (words != nullptr) {
+      const uint32_t w = words[i];
+      refs[i] = (uint8_t)((w & 1u) ? ((w >> 6) & 3u) : 3u);
+      dcs[i] = (int16_t)(w >> 16);
+    } else {
+      const uint2 lo = *(const uint2 *)(recs + i); /* buf_off, mv|dc<<16 */
+      const uint32_t hi = ((const uint32_t *)(recs + i))[3]; /* rowmask, last_zzi, refi, pli_qti */
+      refs[i] = (uint8_t)((hi >> 16) & 0xFFu);
+      dcs[i] = (int16_t)(lo.y >> 16);
+    }
   }
   if (y < nv) { progress[y] = 0; progress[nv + y] = 0; }
   __syncthreads();
@@ -922,7 +947,8 @@ ocg_dc_unpredict_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) 
         if (ready) {
           const int v = (int)(int16_t)(dcs[i] + pred); /* frags[].dc is a 16-bit field (state.h:320) */
           dcs[i] = (int16_t)v;
-          recs[i].dc = (int16_t)v;
+          if (dc_final != nullptr) dc_final[i] = (int16_t)v;
+          else recs[i].dc = (int16_t)v;
           if (r == 0) last0 = v; else if (r == 1) last1 = v; else last2 = v;
           hasmask |= 1 << r;
           l_ref = r;
@@ -936,6 +962,13 @@ ocg_dc_unpredict_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) 
     }
     if (!__syncthreads_or(more)) break;
   }
+}
+
+/* final DC values computed ahead of the lists (ocg_dec_dc_begin) -> the records of coded fragments */
+__global__ void __launch_bounds__(256)
+ocg_dc_patch_kernel(ocg_frag_rec *__restrict__ recs, const int16_t *__restrict__ dc_final, int nfrags) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i < nfrags && recs[i].refi != OCG_FRAG_UNCODED) recs[i].dc = dc_final[i];
 }
 
 } /* namespace */
@@ -960,8 +993,7 @@ static size_t dc_smem_bytes(const OcgPlaneDev &P, bool dc_in_smem) {
   return 8 * nv * sizeof(int) + ((nfr + 15) & ~(size_t)15) + (dc_in_smem ? nfr * 2 : 0);
 }
 
-int ocg_launch_dc_unpredict(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
-  if (njobs <= 0) return 0;
+static int dc_launch(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, const OcgDcArgs &single, cudaStream_t st) {
   static const size_t kMaxSmem = 227 * 1024;
   size_t need_all = 0, need_refs = 0;
   int rows = 0;
@@ -976,14 +1008,29 @@ int ocg_launch_dc_unpredict(const OcgGeomDev &g, const OcgJobDev *jobs, int njob
   if (need_all <= kMaxSmem) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(ocg_dc_unpredict_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem); attr = true; }
-    ocg_dc_unpredict_kernel<true><<<grid, threads, need_all, st>>>(g, jobs);
+    ocg_dc_unpredict_kernel<true><<<grid, threads, need_all, st>>>(g, jobs, single);
   } else {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(ocg_dc_unpredict_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem); attr = true; }
-    ocg_dc_unpredict_kernel<false><<<grid, threads, need_refs, st>>>(g, jobs);
+    ocg_dc_unpredict_kernel<false><<<grid, threads, need_refs, st>>>(g, jobs, single);
   }
   ocg_count_launch(1);
   return 0;
+}
+
+int ocg_launch_dc_unpredict(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return 0;
+  return dc_launch(g, jobs, njobs, OcgDcArgs{nullptr, nullptr, nullptr, nullptr}, st);
+}
+
+int ocg_launch_dc_unpredict_words(const OcgGeomDev &g, const uint32_t *words, int16_t *dc_final, int16_t *dc_tmp,
+                                  cudaStream_t st) {
+  return dc_launch(g, nullptr, 1, OcgDcArgs{nullptr, words, dc_final, dc_tmp}, st);
+}
+
+void ocg_launch_dc_patch(ocg_frag_rec *recs, const int16_t *dc_final, int nfrags, cudaStream_t st) {
+  ocg_dc_patch_kernel<<<(unsigned)((nfrags + 255) / 256), 256, 0, st>>>(recs, dc_final, nfrags);
+  ocg_count_launch(1);
 }
 
 void ocg_launch_xlist_reset(const OcgJobDev *jobs, int njobs, cudaStream_t st) {

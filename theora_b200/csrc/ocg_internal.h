@@ -35,7 +35,7 @@ struct OcgJobDev {
   int32_t            *xcount;    /* [0] list length; 0 between frames (cleared by the border kernel) */
   int32_t             lf_limit;
   uint16_t            dcq[3][2];
-  int32_t             dc_residual; /* recs[].dc are DC-prediction residuals: run ocg_dc_unpredict_kernel first */
+  int32_t             dc_residual; /* 1: recs[].dc are DC-prediction residuals: run ocg_dc_unpredict_kernel first */
   int16_t            *dc_tmp;     /* nfrags scratch for planes whose DC values do not fit shared memory */
   const CUtensorMap  *lf_tmaps;  /* 3 tensor maps (one per plane) of the SELF buffer, or NULL: no TMA path */
 };
@@ -45,6 +45,10 @@ struct OcgJobDev {
 
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 int  ocg_launch_dc_unpredict(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st); /* <0: unsupported size */
+/* the same recurrence ahead of the frame's lists: packed oc_fragment words in, final DC array out */
+int  ocg_launch_dc_unpredict_words(const OcgGeomDev &g, const uint32_t *words, int16_t *dc_final, int16_t *dc_tmp,
+                                   cudaStream_t st);
+void ocg_launch_dc_patch(ocg_frag_rec *recs, const int16_t *dc_final, int nfrags, cudaStream_t st);
 void ocg_launch_xlist_reset(const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st);
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, bool use_tma, cudaStream_t st);
