@@ -648,6 +648,7 @@ def main():
                  "host_threads": nthreads, "host_cores": ncores,
                  "sync": "blocking event (thread sleeps during a flush)" if blocking else "spin",
                  "dc_unprediction": "device (wave-front kernel)" if dc_mode == streams.DC_DEVICE else "host (reference C routine in the hook)",
+                 "token_expansion": "back-end, inside the dc_unpredict_mcu_plane hook (ocg_host_expand_mcu_plane)",
                  "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
                  "flush_ms_per_frame": d["flush_ms_per_frame"], "final_frame_hash": d["hash"],
                  "timing": "median of 3 passes, in a process of its own per rank"}
