@@ -1040,3 +1040,142 @@ OCO_EXPORT void oco_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *r
     }
   }
 }
+
+/* ---------------------------------------------------------------------- */
+/* Whole-frame motion analysis: oc_mcenc_search (mcenc.c:517-548) for every
+   macro block in coding order, with the candidate sets of
+   oc_mcenc_find_candidates_a/_b (mcenc.c:90-164) built from the neighbours'
+   current vectors, and the refinements where oc_enc_analyze_inter runs them
+   (analyze.c:2469-2489).  State layout = ocg_me_mb (oc_mb_enc_info fields). */
+static int oco_mv_x(int mv) { return (int)(signed char)(mv & 0xFF); }
+static int oco_mv_y(int mv) { return (int)(int16_t)mv >> 8; }
+static int oco_mv(int x, int y) { return (int)(int16_t)((x & 0xFF) | (y * 256)); }
+static int oco_clamp31(int v) { return v < -31 ? -31 : (v > 31 ? 31 : v); }
+static void oco_sort2(int *a, int *b) { if (*a > *b) { int t = *a; *a = *b; *b = t; } }
+
+static void oco_me_search_one(const uint8_t *src, const uint8_t *ref_full, const uint8_t *ref_satd, int ystride,
+                              const ocg_me_topo *topo, ocg_me_mb *mb, int mbi, int f, int flags,
+                              const uint8_t *gold_refine) {
+  const ocg_me_topo *t = &topo[mbi];
+  ocg_me_mb *m = &mb[mbi];
+  ocg_mb_search_in in;
+  ocg_mb_search_out out;
+  int mv0 = m->analysis_mv[0][f], mv1 = m->analysis_mv[1][f], mv2 = m->analysis_mv[2][f];
+  int accum, ax, ay, nc = 1, i, a[3][2], h1, h2, refine;
+  unsigned t2;
+  /* mcenc.c:523-531 / 540-541 */
+  if (f == 1) {
+    int old2 = mv2;
+    accum = (flags & OCG_ME_DROPPED) ? mv0 : 0;
+    mv2 = mv1;
+    mv1 = oco_mv(oco_mv_x(mv0) - oco_mv_x(old2), oco_mv_y(mv0) - oco_mv_y(old2));
+  } else {
+    accum = mv2;
+    mv2 = mv1;
+    mv1 = mv0;
+    mv1 = oco_mv(oco_mv_x(mv1) - oco_mv_x(mv2), oco_mv_y(mv1) - oco_mv_y(mv2));
+    mv2 = oco_mv(oco_mv_x(mv2) - oco_mv_x(accum), oco_mv_y(mv2) - oco_mv_y(accum));
+  }
+  ax = oco_mv_x(accum);
+  ay = oco_mv_y(accum);
+  memset(&in, 0, sizeof(in));
+  for (i = 0; i < 4; i++) in.frag_off[i] = t->frag_off[i];
+  /* set A, mcenc.c:101-127 */
+  for (i = 0; i < t->ncn; i++) {
+    in.cand[nc][0] = (int8_t)oco_mv_x(mb[t->cn[i]].analysis_mv[0][f]);
+    in.cand[nc][1] = (int8_t)oco_mv_y(mb[t->cn[i]].analysis_mv[0][f]);
+    nc++;
+  }
+  in.cand[nc][0] = (int8_t)ax; in.cand[nc][1] = (int8_t)ay; nc++;
+  in.cand[nc][0] = (int8_t)oco_clamp31(oco_mv_x(mv1) + ax);
+  in.cand[nc][1] = (int8_t)oco_clamp31(oco_mv_y(mv1) + ay);
+  nc++;
+  in.cand[nc][0] = in.cand[nc][1] = 0; nc++;
+  /* median of the first three, mcenc.c:130-138 */
+  for (i = 0; i < 3; i++) { a[i][0] = in.cand[1 + i][0]; a[i][1] = in.cand[1 + i][1]; }
+  oco_sort2(&a[0][0], &a[1][0]); oco_sort2(&a[0][1], &a[1][1]);
+  oco_sort2(&a[1][0], &a[2][0]); oco_sort2(&a[1][1], &a[2][1]);
+  oco_sort2(&a[0][0], &a[1][0]); oco_sort2(&a[0][1], &a[1][1]);
+  in.cand[0][0] = (int8_t)a[1][0];
+  in.cand[0][1] = (int8_t)a[1][1];
+  in.setb0 = (uint8_t)nc;
+  /* set B, mcenc.c:156-163 */
+  in.cand[nc][0] = (int8_t)oco_clamp31(2 * oco_mv_x(mv1) - oco_mv_x(mv2) + ax);
+  in.cand[nc][1] = (int8_t)oco_clamp31(2 * oco_mv_y(mv1) - oco_mv_y(mv2) + ay);
+  nc++;
+  in.ncand = (uint8_t)nc;
+  /* mcenc.c:337-341 */
+  t2 = m->error[f];
+  for (i = 0; i < (t->ncn < 3 ? t->ncn : 3); i++)
+    if (mb[t->cn[i]].error[f] > t2) t2 = mb[t->cn[i]].error[f];
+  in.t2_base = (uint16_t)t2;
+  in.is_prev = (uint8_t)(f == 1);
+  oco_mcenc_search_batch(src, ref_full, ref_satd, ystride, &in, &out, 1);
+  if (flags & OCG_ME_NOSATD) { /* mcenc.c:238-241: SAD instead of SATD for the final score */
+    unsigned s = 0;
+    for (i = 0; i < 4; i++)
+      s += oco_frag_sad(src + t->frag_off[i], ref_satd + t->frag_off[i] + out.best_vec[0] + out.best_vec[1] * ystride, ystride);
+    out.satd = s;
+  }
+  /* mcenc.c:534, 546-547 */
+  if (f == 1) { h2 = accum; h1 = mv1; }
+  else {
+    h2 = oco_mv(oco_mv_x(mv2) + ax, oco_mv_y(mv2) + ay);
+    h1 = oco_mv(oco_mv_x(mv1) + oco_mv_x(h2), oco_mv_y(mv1) + oco_mv_y(h2));
+  }
+  m->analysis_mv[1][f] = (int16_t)h1;
+  m->analysis_mv[2][f] = (int16_t)h2;
+  m->error[f] = out.error;
+  m->analysis_mv[0][f] = m->unref_mv[f] = (int16_t)oco_mv(out.best_vec[0] * 2, out.best_vec[1] * 2);
+  m->satd[f] = m->unref_satd[f] = out.satd;
+  if (f == 1 && !(flags & OCG_ME_FAST)) {
+    for (i = 0; i < 4; i++) {
+      m->block_mv[i] = (int16_t)oco_mv(out.block_vec[i][0] * 2, out.block_vec[i][1] * 2);
+      m->block_satd[i] = out.block_satd[i];
+    }
+  }
+  refine = f == 1 ? (flags & OCG_ME_REFINE_PREV) != 0 : (gold_refine != NULL && gold_refine[mbi] != 0);
+  if (refine) { /* analyze.c:2476-2489 -> mcenc.c:666-675 */
+    ocg_mb_refine_in rin;
+    ocg_mb_refine_out rout;
+    memset(&rin, 0, sizeof(rin));
+    for (i = 0; i < 4; i++) rin.frag_off[i] = t->frag_off[i];
+    rin.vec[0] = out.best_vec[0];
+    rin.vec[1] = out.best_vec[1];
+    rin.satd = out.satd;
+    oco_mcenc_refine_batch(src, ref_satd, ystride, &rin, &rout, 1,
+                           OCG_REFINE_1MV | ((flags & OCG_ME_NOSATD) ? OCG_REFINE_SAD : 0));
+    m->analysis_mv[0][f] = (int16_t)oco_mv(rout.mv[0], rout.mv[1]);
+    m->satd[f] = rout.satd;
+  }
+}
+
+OCO_EXPORT void oco_me_frame(const uint8_t *src, const uint8_t *ref_full_gold, const uint8_t *ref_full_prev,
+                             const uint8_t *ref_satd_gold, const uint8_t *ref_satd_prev, int ystride,
+                             const ocg_me_topo *topo, ocg_me_mb *mb, int nmbs, int flags, const uint8_t *gold_refine) {
+  int mbi, i;
+  for (mbi = 0; mbi < nmbs; mbi++) {
+    if (!topo[mbi].valid) continue;
+    oco_me_search_one(src, ref_full_prev, ref_satd_prev, ystride, topo, mb, mbi, 1, flags, gold_refine);
+    oco_me_search_one(src, ref_full_gold, ref_satd_gold, ystride, topo, mb, mbi, 0, flags, gold_refine);
+  }
+  if ((flags & OCG_ME_REFINE_4MV) && !(flags & OCG_ME_FAST)) {
+    for (mbi = 0; mbi < nmbs; mbi++) { /* mcenc.c:763-791 */
+      ocg_mb_refine_in rin;
+      ocg_mb_refine_out rout;
+      if (!topo[mbi].valid) continue;
+      memset(&rin, 0, sizeof(rin));
+      for (i = 0; i < 4; i++) {
+        rin.frag_off[i] = topo[mbi].frag_off[i];
+        rin.block_vec[i][0] = (int8_t)(oco_mv_x(mb[mbi].block_mv[i]) / 2);
+        rin.block_vec[i][1] = (int8_t)(oco_mv_y(mb[mbi].block_mv[i]) / 2);
+        rin.block_satd[i] = mb[mbi].block_satd[i];
+      }
+      oco_mcenc_refine_batch(src, ref_satd_prev, ystride, &rin, &rout, 1, OCG_REFINE_4MV);
+      for (i = 0; i < 4; i++) {
+        mb[mbi].ref_mv[i] = (int16_t)oco_mv(rout.ref_mv[i][0], rout.ref_mv[i][1]);
+        mb[mbi].ref_block_satd[i] = rout.block_satd[i];
+      }
+    }
+  }
+}

@@ -82,6 +82,11 @@ void oco_mcenc_search_batch(const uint8_t *src_base, const uint8_t *ref_full_bas
 void oco_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,
                             const ocg_mb_refine_in *in, ocg_mb_refine_out *out, int n, int flags); /* mcenc.c:606-791 */
 
+/* whole-frame motion analysis, state in/out in mb[] (mcenc.c:90-164, 517-548; analyze.c:2469-2489) */
+void oco_me_frame(const uint8_t *src, const uint8_t *ref_full_gold, const uint8_t *ref_full_prev,
+                  const uint8_t *ref_satd_gold, const uint8_t *ref_satd_prev, int ystride,
+                  const ocg_me_topo *topo, ocg_me_mb *mb, int nmbs, int flags, const uint8_t *gold_refine);
+
 #ifdef __cplusplus
 }
 #endif

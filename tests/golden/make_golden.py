@@ -141,6 +141,21 @@ def streams():
     print("streams.npz:", {k: v.shape for k, v in out.items()})
 
 
+def me_frame():
+    """Whole-frame motion analysis by the reference (oc_mcenc_search + refinements over every macro block,
+    oracle/ref_internal_harness.c refh_me_frame) on the deterministic scene of tests/test_oracle_me_frame.py;
+    also oc_mb_activity on one of its frames through oracle/_ref/libth_c_analyze.so."""
+    import megen
+    import test_oracle_me_frame as T
+    R = megen.bind_ref_me(S.ref("c"))
+    out = {}
+    for t, fl, topo, got, want in T.run_sequence(**T.GOLDEN_CASE, ref=R):
+        out["frame%d" % t] = want.view(np.uint8).copy()
+    np.savez_compressed(os.path.join(HERE, "me_frame.npz"), **out)
+    print("me_frame.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     units()
     streams()
+    me_frame()

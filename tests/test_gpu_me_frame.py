@@ -137,3 +137,37 @@ def test_me_api_rejects_bad_arguments():
     L.ocg_me_destroy(me)
     L.ocg_me_destroy(None)
     ctx.close()
+
+
+def test_device_matches_oracle_and_golden():
+    """Same sequence as tests/golden/me_frame.npz (made by the reference): device == CPU oracle == golden,
+    so the check also holds on a box without oracle/_ref."""
+    import test_oracle_me_frame as TO
+    G = np.load(TO.GOLDEN)
+    c = TO.GOLDEN_CASE
+    g = S.make_geometry(c["fw"], c["fh"], 0, 6)
+    L = abi.lib()
+    ctx = T.Context(g, 0)
+    me = C.c_void_p()
+    abi.check(L.ocg_me_create(C.byref(me), ctx.h, None), "ocg_me_create")
+    n = L.ocg_me_nmbs(C.byref(g))
+    got = np.zeros(n, abi.ME_MB_DTYPE)
+    # regenerate the inputs exactly as run_sequence does
+    rng = np.random.default_rng(c["seed"])
+    orig, recon = megen.scene_buffers(g, rng, c["nframes"] + 1, motion=c["motion"])
+    seq = TO.run_sequence(**c)
+    try:
+        for t, fl, topo, oracle_state, _ in seq:
+            gold_t = 0 if t < 3 else 1
+            frames = [orig[t], orig[t - 1], orig[gold_t], recon[t - 1], recon[gold_t]]
+            mask = (rng.random(n) < c["density"]).astype(np.uint8)
+            for i, f in enumerate(frames):
+                ctx.upload_frame(i, f)
+            abi.check(L.ocg_me_frame(me, (C.c_int * 5)(0, 1, 2, 3, 4), fl, mask.ctypes.data), "ocg_me_frame")
+            abi.check(L.ocg_me_read(me, got.ctypes.data), "ocg_me_read")
+            megen.assert_me_equal(got, oracle_state, topo["valid"], fl, "vs oracle, frame %d" % t)
+            megen.assert_me_equal(got, G["frame%d" % t].view(abi.ME_MB_DTYPE).reshape(-1), topo["valid"], fl,
+                                  "vs golden, frame %d" % t)
+    finally:
+        L.ocg_me_destroy(me)
+        ctx.close()
