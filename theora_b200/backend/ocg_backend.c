@@ -37,6 +37,7 @@ th_dec_ctx *oc_refimpl_decode_alloc(const th_info *_info, const th_setup_info *_
 void oc_refimpl_decode_free(th_dec_ctx *_dec);
 int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
 void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_dec_host.c */
+void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli); /* ocg_dec_host.c */
 int ocg_host_expand_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli, ptrdiff_t _ncoded,
                               ptrdiff_t _nuncoded, ocg_frag_rec *_recs, ogg_int16_t *_rows, int _nrows0,
                               ogg_uint16_t _dcq_out[2], unsigned *_stray); /* ocg_dec_host.c */
@@ -214,6 +215,8 @@ static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *
     for (; fragi < end; fragi++) ncoded += frags[fragi].coded;
     _pipe->ncoded_fragis[_pli] = ncoded;
     _pipe->nuncoded_fragis[_pli] = (fragy_end - fragy0) * (ptrdiff_t)fplane->nhfrags - ncoded;
+  } else if (b != NULL && b->expand) {
+    ocg_host_dc_unpredict_mcu_plane(_dec, _pipe, _pli); /* same contract, restated for speed */
   } else {
     oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
   }

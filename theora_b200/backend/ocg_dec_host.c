@@ -147,3 +147,136 @@ int ocg_host_expand_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, in
   }
   return nrows - _nrows0;
 }
+
+/* (3) DC un-prediction in the hook, restated for speed.
+ *
+ * Same contract as oc_dec_dc_unpredict_mcu_plane_c (decode.c:1392-1500): undoes
+ * the DC prediction of fragment rows [fragy0,fragy_end) of one plane in place
+ * (frags[].dc), carries pipe->pred_last across calls, and counts the coded /
+ * uncoded fragments of the MCU.  The reference dispatches every coded fragment
+ * through a 16-way switch on which of its four causal neighbours share its
+ * reference type; on frames that mix reference types that switch mispredicts.
+ * Here the neighbour test yields a 4-bit pattern that indexes a small table of
+ * weights and shifts (the same integer formulas: x/2^k with truncation towards
+ * zero == (x + ((x>>31) & (2^k-1))) >> k), so only the two special cases stay
+ * as branches: "no neighbour" (pred_last) and the three-neighbour gradient
+ * predictor with its outlier clamps (cases 7 and 15). */
+typedef struct ocg_dc_rule {
+  short wl, wul, wu, wur; /* weights of left, up-left, up, up-right */
+  short shift;            /* divisor 2^shift */
+  short special;          /* 0 table, 1 pred_last, 2 gradient predictor with clamps */
+} ocg_dc_rule;
+
+/* index: (l==ref) | (ul==ref)<<1 | (u==ref)<<2 | (ur==ref)<<3, decode.c:1450-1484 */
+static const ocg_dc_rule OCG_DC_RULES[16] = {
+  {0, 0, 0, 0, 0, 1},     /*  0: pred_last                      */
+  {1, 0, 0, 0, 0, 0},     /*  1: l                              */
+  {0, 1, 0, 0, 0, 0},     /*  2: ul                             */
+  {1, 0, 0, 0, 0, 0},     /*  3: l                              */
+  {0, 0, 1, 0, 0, 0},     /*  4: u                              */
+  {1, 0, 1, 0, 1, 0},     /*  5: (l+u)/2                        */
+  {0, 0, 1, 0, 0, 0},     /*  6: u                              */
+  {29, -26, 29, 0, 5, 2}, /*  7: (29*(l+u)-26*ul)/32 + clamps   */
+  {0, 0, 0, 1, 0, 0},     /*  8: ur                             */
+  {75, 0, 0, 53, 7, 0},   /*  9: (75*l+53*ur)/128               */
+  {0, 1, 0, 1, 1, 0},     /* 10: (ul+ur)/2                      */
+  {75, 0, 0, 53, 7, 0},   /* 11                                 */
+  {0, 0, 1, 0, 0, 0},     /* 12: u                              */
+  {75, 0, 0, 53, 7, 0},   /* 13                                 */
+  {0, 3, 10, 3, 4, 0},    /* 14: (3*(ul+ur)+10*u)/16            */
+  {29, -26, 29, 0, 5, 2}  /* 15                                 */
+};
+
+void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli) {
+  const oc_fragment_plane *fplane = _dec->state.fplanes + _pli;
+  oc_fragment *frags = _dec->state.frags;
+  int *pred_last = _pipe->pred_last[_pli];
+  const int fragy0 = _pipe->fragy0[_pli], fragy_end = _pipe->fragy_end[_pli], nhfrags = fplane->nhfrags;
+  ptrdiff_t ncoded = 0, fragi = fplane->froffset + fragy0 * (ptrdiff_t)nhfrags;
+  int fragx, fragy;
+  for (fragy = fragy0; fragy < fragy_end; fragy++) {
+    if (fragy == 0) {
+      for (fragx = 0; fragx < nhfrags; fragx++, fragi++) {
+        if (frags[fragi].coded) {
+          int refi = frags[fragi].refi;
+          pred_last[refi] = frags[fragi].dc += pred_last[refi];
+          ncoded++;
+        }
+      }
+    } else {
+      const oc_fragment *u_frags = frags - nhfrags;
+      /* like the reference, the rows above are judged by refi alone: an uncoded fragment carries
+         OC_FRAME_NONE there (decode.c:658) */
+      int l_ref = -1, ul_ref = -1, u_ref = u_frags[fragi].refi;
+      int l_dc = 0, ul_dc = 0, u_dc = u_frags[fragi].dc;
+      for (fragx = 0; fragx < nhfrags; fragx++, fragi++) {
+        int ur_ref = -1, ur_dc = 0;
+        if (fragx + 1 < nhfrags) {
+          ur_ref = u_frags[fragi + 1].refi;
+          ur_dc = u_frags[fragi + 1].dc;
+        }
+        if (frags[fragi].coded) {
+          const int refi = frags[fragi].refi;
+          const ocg_dc_rule *r = OCG_DC_RULES + ((l_ref == refi) | (ul_ref == refi) << 1 | (u_ref == refi) << 2 |
+                                                 (ur_ref == refi) << 3);
+          int pred;
+          if (r->special == 1) pred = pred_last[refi];
+          else {
+            int sum = r->wl * l_dc + r->wul * ul_dc + r->wu * u_dc + r->wur * ur_dc;
+            pred = (sum + ((sum >> 31) & ((1 << r->shift) - 1))) >> r->shift;
+            if (r->special == 2) {
+              if (abs(pred - u_dc) > 128) pred = u_dc;
+              else if (abs(pred - l_dc) > 128) pred = l_dc;
+              else if (abs(pred - ul_dc) > 128) pred = ul_dc;
+            }
+          }
+          pred_last[refi] = frags[fragi].dc += pred;
+          ncoded++;
+          l_ref = refi;
+          l_dc = frags[fragi].dc;
+        } else l_ref = -1;
+        ul_ref = u_ref;
+        ul_dc = u_dc;
+        u_ref = ur_ref;
+        u_dc = ur_dc;
+      }
+    }
+  }
+  _pipe->ncoded_fragis[_pli] = ncoded;
+  _pipe->nuncoded_fragis[_pli] = (fragy_end - fragy0) * (ptrdiff_t)nhfrags - ncoded;
+}
+
+/* Test hook: both implementations on the same random plane (fake decoder context); returns the number of
+   fragments whose DC differs, or -1 if the counts differ. */
+OCG_API long ocg_host_dc_selftest(int nhfrags, int nvfrags, int mcu_rows, unsigned seed, int coded_pct, int mixed) {
+  oc_dec_ctx *da = (oc_dec_ctx *)calloc(1, sizeof(*da)), *db = (oc_dec_ctx *)calloc(1, sizeof(*db));
+  oc_dec_pipeline_state *pa = &da->pipe, *pb = &db->pipe;
+  size_t n = (size_t)nhfrags * nvfrags, i;
+  oc_fragment *fa = (oc_fragment *)calloc(n, sizeof(*fa)), *fb = (oc_fragment *)calloc(n, sizeof(*fb));
+  long bad = 0;
+  int y0;
+  unsigned s = seed * 2654435761u + 12345u;
+  for (i = 0; i < n; i++) {
+    s = s * 1664525u + 1013904223u;
+    fa[i].coded = (s >> 8) % 100 < (unsigned)coded_pct;
+    fa[i].refi = mixed ? (s >> 16) % 3 : 1;
+    s = s * 1664525u + 1013904223u;
+    fa[i].dc = (int)((s >> 12) % 1201) - 600;
+    if (((s >> 28) & 15) == 0) fa[i].dc = (int)(s >> 16) - 32768; /* the odd huge value: 16-bit wrap */
+    fb[i] = fa[i];
+  }
+  da->state.frags = fa; db->state.frags = fb;
+  da->state.fplanes[0].nhfrags = db->state.fplanes[0].nhfrags = nhfrags;
+  da->state.fplanes[0].nvfrags = db->state.fplanes[0].nvfrags = nvfrags;
+  for (y0 = 0; y0 < nvfrags; y0 += mcu_rows) {
+    pa->fragy0[0] = pb->fragy0[0] = y0;
+    pa->fragy_end[0] = pb->fragy_end[0] = y0 + mcu_rows < nvfrags ? y0 + mcu_rows : nvfrags;
+    oc_dec_dc_unpredict_mcu_plane_c(da, pa, 0);
+    ocg_host_dc_unpredict_mcu_plane(db, pb, 0);
+    if (pa->ncoded_fragis[0] != pb->ncoded_fragis[0] || pa->nuncoded_fragis[0] != pb->nuncoded_fragis[0]) bad = -1;
+  }
+  if (bad == 0)
+    for (i = 0; i < n; i++) bad += fa[i].dc != fb[i].dc;
+  free(fa); free(fb); free(da); free(db);
+  return bad;
+}
