@@ -634,7 +634,12 @@ def main():
         env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[LOCAL_RANK] if vis else str(LOCAL_RANK)
         with_ref = int(RANK == 0 and WORLD == 1 and not args.no_cpu)
 
+        npass = [0]
+
         def e2e_pass(nthreads, blocking, dc_mode, ref):
+            # ranks start together and finished ranks SLEEP until the last one is done (a NCCL barrier would
+            # spin a host core per waiting rank and slow the ranks that are still measuring)
+            npass[0] += 1
             barrier()
             p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dec_e2e_bench.py"), blob_path, str(nthreads),
                                 str(int(ref)), str(dc_mode), str(int(blocking))], capture_output=True, text=True, env=env,
@@ -642,6 +647,7 @@ def main():
             if p.returncode != 0:
                 raise RuntimeError("dec_e2e_bench failed: " + p.stderr[-400:])
             d = json.loads(p.stdout.strip().splitlines()[-1])
+            sharding.quiet_barrier("e2e_pass_%d" % npass[0])
             secs = sharding.max_over_ranks(d["secs"], dev)
             r = {"value": WORLD * nthreads * nframes / secs, "unit": "frames/s",
                  "h2d_bytes_per_step": int(d["h2d_bytes"]), "d2h_bytes_per_step": int(d["d2h_bytes"]),

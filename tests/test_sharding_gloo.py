@@ -39,6 +39,7 @@ def _worker(rank, world, port, blob, q):
                 frames += len(works)
         else:
             frames = 6 * len(mine)
+        sharding.quiet_barrier("after_parse")  # store-based rendezvous (no spinning), as bench.py uses around e2e
         total = sharding.sum_over_ranks(frames)
         worst = sharding.max_over_ranks(1.0 + rank)
         q.put((rank, got == blob, mine, frames, total, worst))

@@ -42,3 +42,19 @@ def sum_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def quiet_barrier(tag):
+    """Rendezvous that SLEEPS while it waits (key/value store of the process group, blocking socket wait).
+    A NCCL barrier or all-reduce spins a host core per waiting rank; around a host-bound measurement (the
+    e2e decode runs T threads per rank on shared cores) the early finishers would steal cores from the
+    ranks still measuring.  Falls back to dist.barrier() if the store is not reachable."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    try:
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        store.set("%s_%d" % (tag, dist.get_rank()), "1")
+        store.wait(["%s_%d" % (tag, r) for r in range(dist.get_world_size())], datetime.timedelta(seconds=1800))
+    except Exception:
+        dist.barrier()
