@@ -24,6 +24,8 @@ def main():
         for fi, wk in enumerate(works):
             if wk is None:
                 continue
+            if wk.dc_residual:
+                wk.dc_residual = 1  # stand-alone submit: the wave-front kernel runs inside the flush
             ts = []
             for rep in range(6):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
