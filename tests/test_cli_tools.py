@@ -205,3 +205,36 @@ def test_gpu_tools_write_identical_files(case, tmp_path):
         run(os.path.join(BIN, "ref_encoder_example"), "-o", a, "-v", str(q), "-k", "1", y4m)
         run(os.path.join(BIN, "ocg_encoder_example"), "-o", b, "-v", str(q), "-k", "1", y4m)
         assert open(a, "rb").read() == open(b, "rb").read(), "intra-only .ogv differs from the reference encoder's"
+
+
+@pytest.mark.skipif(not have("ref_encoder_example", "ref_dump_video"), reason="tools/cli not built (needs the reference)")
+def test_large_packets_span_pages_and_damage_is_survived(tmp_path):
+    """A key frame larger than one page's 255 x 255 bytes must continue on the following pages (RFC 3533
+    section 5: continued-packet flag, granule position -1 on pages where no packet ends); and the reader
+    must drop a page with a bad CRC, resynchronise, and carry on with the packets it can still complete."""
+    w, h, n = 640, 480, 4
+    y4m, ogv, out = str(tmp_path / "in.y4m"), str(tmp_path / "a.ogv"), str(tmp_path / "out.y4m")
+    rng = np.random.default_rng(9)
+    with open(y4m, "wb") as f:
+        f.write(("YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420jpeg\n" % (w, h)).encode())
+        for t in range(n):
+            f.write(b"FRAME\n" + rng.integers(0, 256, size=w * h * 3 // 2, dtype=np.uint8).tobytes())  # incompressible
+    run(os.path.join(BIN, "ref_encoder_example"), "-o", ogv, "-v", "10", "-k", "2", y4m)
+    blob = open(ogv, "rb").read()
+    packets, pages = parse_ogg(blob)
+    assert len(packets) == 3 + n
+    assert max(len(p) for p in packets) > 255 * 255, "the test needs a packet that cannot fit one page"
+    assert any(pg["flags"] & 1 for pg in pages) and any(pg["granulepos"] == -1 for pg in pages)
+    run(os.path.join(BIN, "ref_dump_video"), "-o", out, ogv)
+    _, _, frames = read_y4m(out)
+    assert len(frames) == n
+    # flip one byte in the middle of the LAST data packet's pages: that frame is lost, the rest decodes
+    bad = bytearray(blob)
+    bad[len(bad) - 2000] ^= 0x55
+    open(ogv, "wb").write(bytes(bad))
+    log = run(os.path.join(BIN, "ref_dump_video"), "-o", out, ogv)
+    assert "1 bad CRC" in log
+    _, _, frames2 = read_y4m(out)
+    assert 1 <= len(frames2) < n
+    for a, b in zip(frames2, frames):
+        assert np.array_equal(a, b)

@@ -15,6 +15,7 @@
  */
 #include <climits>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 #include "ocg_internal.h"
@@ -1056,7 +1057,8 @@ struct ocg_me {
   uint32_t seq = 0;
 };
 
-/* batch scratch (one launch set for many streams), process-wide like the decoder's */
+/* batch scratch (one launch set for many streams), process-wide; calls are serialised by g_me_batch_lock */
+static std::mutex g_me_batch_lock;
 static struct {
   OcgMeJob *d = nullptr, *h = nullptr;
   int cap = 0;
@@ -1236,6 +1238,7 @@ OCG_API int ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int f
   if (mes == nullptr || bufs == nullptr) return OCG_EFAULT;
   if (n <= 0 || (flags & ~31)) return OCG_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lk(g_me_batch_lock);
   if (g_me_batch.busy) {
     if (cudaEventSynchronize(g_me_batch.used) != cudaSuccess) return OCG_ECUDA;
     g_me_batch.busy = false;
