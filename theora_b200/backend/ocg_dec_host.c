@@ -187,39 +187,68 @@ static const ocg_dc_rule OCG_DC_RULES[16] = {
   {29, -26, 29, 0, 5, 2}  /* 15                                 */
 };
 
+/* oc_fragment as one 32-bit word (state.h:297-322 as GCC lays the bit-fields out on little-endian targets;
+   ocg_dc_words_ok() verifies it once): bit 0 coded, bits 6-7 refi, bits 16-31 dc. */
+#define OCG_W_CODED(w) ((w) & 1u)
+#define OCG_W_REFI(w)  ((int)((w) >> 6 & 3u))
+#define OCG_W_DC(w)    ((int)(ogg_int16_t)((w) >> 16))
+
+static int ocg_dc_words_ok(void) {
+  static int ok = -1;
+  if (ok < 0) {
+    oc_fragment t;
+    ogg_uint32_t w = 0;
+    memset(&t, 0, sizeof(t));
+    t.coded = 1; t.refi = 2; t.dc = -3;
+    if (sizeof(t) == 4) memcpy(&w, &t, 4);
+    ok = sizeof(t) == 4 && w == (1u | 2u << 6 | 0xFFFDu << 16);
+  }
+  return ok;
+}
+
 void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli) {
   const oc_fragment_plane *fplane = _dec->state.fplanes + _pli;
-  oc_fragment *frags = _dec->state.frags;
+  ogg_uint32_t *words = (ogg_uint32_t *)_dec->state.frags;
   int *pred_last = _pipe->pred_last[_pli];
   const int fragy0 = _pipe->fragy0[_pli], fragy_end = _pipe->fragy_end[_pli], nhfrags = fplane->nhfrags;
   ptrdiff_t ncoded = 0, fragi = fplane->froffset + fragy0 * (ptrdiff_t)nhfrags;
   int fragx, fragy;
+  if (!ocg_dc_words_ok()) { /* unexpected bit-field layout: the reference routine knows its own */
+    oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
+    return;
+  }
   for (fragy = fragy0; fragy < fragy_end; fragy++) {
     if (fragy == 0) {
       for (fragx = 0; fragx < nhfrags; fragx++, fragi++) {
-        if (frags[fragi].coded) {
-          int refi = frags[fragi].refi;
-          pred_last[refi] = frags[fragi].dc += pred_last[refi];
+        const ogg_uint32_t w = words[fragi];
+        if (OCG_W_CODED(w)) {
+          const int refi = OCG_W_REFI(w);
+          const int dc = (ogg_int16_t)(OCG_W_DC(w) + pred_last[refi]);
+          words[fragi] = (w & 0xFFFFu) | (ogg_uint32_t)dc << 16;
+          pred_last[refi] = dc;
           ncoded++;
         }
       }
     } else {
-      const oc_fragment *u_frags = frags - nhfrags;
+      const ogg_uint32_t *u_words = words - nhfrags;
       /* like the reference, the rows above are judged by refi alone: an uncoded fragment carries
          OC_FRAME_NONE there (decode.c:658) */
-      int l_ref = -1, ul_ref = -1, u_ref = u_frags[fragi].refi;
-      int l_dc = 0, ul_dc = 0, u_dc = u_frags[fragi].dc;
+      ogg_uint32_t uw = u_words[fragi];
+      int l_ref = -1, ul_ref = -1, u_ref = OCG_W_REFI(uw);
+      int l_dc = 0, ul_dc = 0, u_dc = OCG_W_DC(uw);
       for (fragx = 0; fragx < nhfrags; fragx++, fragi++) {
+        const ogg_uint32_t w = words[fragi];
         int ur_ref = -1, ur_dc = 0;
         if (fragx + 1 < nhfrags) {
-          ur_ref = u_frags[fragi + 1].refi;
-          ur_dc = u_frags[fragi + 1].dc;
+          const ogg_uint32_t urw = u_words[fragi + 1];
+          ur_ref = OCG_W_REFI(urw);
+          ur_dc = OCG_W_DC(urw);
         }
-        if (frags[fragi].coded) {
-          const int refi = frags[fragi].refi;
+        if (OCG_W_CODED(w)) {
+          const int refi = OCG_W_REFI(w);
           const ocg_dc_rule *r = OCG_DC_RULES + ((l_ref == refi) | (ul_ref == refi) << 1 | (u_ref == refi) << 2 |
                                                  (ur_ref == refi) << 3);
-          int pred;
+          int pred, dc;
           if (r->special == 1) pred = pred_last[refi];
           else {
             int sum = r->wl * l_dc + r->wul * ul_dc + r->wu * u_dc + r->wur * ur_dc;
@@ -230,10 +259,12 @@ void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_p
               else if (abs(pred - ul_dc) > 128) pred = ul_dc;
             }
           }
-          pred_last[refi] = frags[fragi].dc += pred;
+          dc = (ogg_int16_t)(OCG_W_DC(w) + pred); /* frags[].dc is a 16-bit field */
+          words[fragi] = (w & 0xFFFFu) | (ogg_uint32_t)dc << 16;
+          pred_last[refi] = dc;
           ncoded++;
           l_ref = refi;
-          l_dc = frags[fragi].dc;
+          l_dc = dc;
         } else l_ref = -1;
         ul_ref = u_ref;
         ul_dc = u_dc;
