@@ -1,6 +1,6 @@
 """TH_DECCTL_SET_PPLEVEL through the B200 back-end: the reconstruction runs on the
 device, the (non-normative) de-blocking / de-ringing filters of decode.c:1609-1957
-run on the host over the whole frame after the flush (ocg_pp_host.c).  Output
+run on the host over the whole frame after the flush (ocg_dec_host.c).  Output
 must equal the unmodified reference decoder's at the same level, every frame."""
 import ctypes as C
 

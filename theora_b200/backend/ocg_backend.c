@@ -21,7 +21,7 @@
  * frame after the flush.  Post-processing (TH_DECCTL_SET_PPLEVEL > 0), which the
  * reference runs inside the MCU loop on host pixels that are not there yet
  * (decode.c:2899-2914), is re-run over the whole frame after the flush by the
- * reference's own filters (ocg_pp_host.c).
+ * reference's own filters (ocg_dec_host.c).
  */
 #include <stdio.h>
 #include <stdlib.h>
