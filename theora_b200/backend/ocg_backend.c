@@ -37,6 +37,7 @@ th_dec_ctx *oc_refimpl_decode_alloc(const th_info *_info, const th_setup_info *_
 void oc_refimpl_decode_free(th_dec_ctx *_dec);
 int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
 void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_dec_host.c */
+void oc_state_accel_init_ocg(oc_theora_state *_state);
 void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli); /* ocg_dec_host.c */
 int ocg_host_expand_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli, ptrdiff_t _ncoded,
                               ptrdiff_t _nuncoded, ocg_frag_rec *_recs, ogg_int16_t *_rows, int _nrows0,
@@ -312,6 +313,13 @@ static void ocg_restore_fpu(void) {
 }
 
 /* ---- init functions named by ocg_hooks.h --------------------------------- */
+#if defined(OC_X86_ASM)
+/* x86int.h names oc_state_accel_init_x86 as the init function of every unit built with OC_X86_ASM: that is
+   this function here (theora_b200/backend/Makefile); the reference's own body is oc_refimpl_state_accel_init_x86
+   and is used for encoders that keep their block kernels on the host (ocg_enc_backend.c). */
+void oc_state_accel_init_x86(oc_theora_state *_state) { oc_state_accel_init_ocg(_state); }
+#endif
+
 void oc_state_accel_init_ocg(oc_theora_state *_state) {
   /* shared encoder/decoder table: plain C entries; the decoder and encoder inits
      override the ones they offload (ocg_enc_backend.c for intra-only encoders). */

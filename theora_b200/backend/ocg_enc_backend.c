@@ -419,6 +419,14 @@ static void enc_backend_destroy(ocg_enc_backend *b) {
   free(b);
 }
 
+#if defined(OC_X86_ASM)
+void oc_refimpl_state_accel_init_x86(oc_theora_state *_state); /* lib/x86/x86state.c, renamed */
+void oc_refimpl_enc_accel_init_x86(oc_enc_ctx *_enc);          /* lib/x86/x86enc.c, renamed */
+void oc_enc_accel_init_ocg(oc_enc_ctx *_enc);
+/* x86enc.h names oc_enc_accel_init_x86 as the encoder's init function (see ocg_backend.c) */
+void oc_enc_accel_init_x86(oc_enc_ctx *_enc) { oc_enc_accel_init_ocg(_enc); }
+#endif
+
 void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   oc_theora_state *st = &_enc->state;
   ocg_enc_backend *b;
@@ -427,7 +435,17 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   t_enc_init_failed = 0;
   /* only an encoder that cannot emit inter frames takes the device path */
   if (g_enc_mode == OCG_ENC_HOST || st->info.keyframe_granule_shift != 0) {
-    if (g_enc_spy != NULL) _enc->opt_vtable.enquant_table_fixup = ocge_spy_fixup;
+#if defined(OC_X86_ASM)
+    /* everything stays on the host: with the reference's SIMD kernels, exactly as its own x86 build
+       would set this context up (x86state.c:66-95, x86enc.c:21-62; oc_enc_init sizes the quantiser
+       tables after this call, encode.c:1160-1190) */
+    if (g_enc_mode != OCG_ENC_HOST) {
+      oc_refimpl_state_accel_init_x86(st);
+      oc_refimpl_enc_accel_init_x86(_enc);
+    }
+#endif
+    /* the spy wraps the C fix-up: host (C kernel) mode only */
+    if (g_enc_spy != NULL && g_enc_mode == OCG_ENC_HOST) _enc->opt_vtable.enquant_table_fixup = ocge_spy_fixup;
     return;
   }
   t_enc_init_failed = 1;
