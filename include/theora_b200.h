@@ -160,6 +160,11 @@ OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *ctx, int buf);  /* device address of
 /* Whole padded buffer, host <-> device (ref_frame_sz bytes). */
 OCG_API int  ocg_ctx_upload_frame(ocg_ctx *ctx, int buf, const uint8_t *host_buf);
 OCG_API int  ocg_ctx_download_frame(ocg_ctx *ctx, int buf, uint8_t *host_buf);
+/* Only the coded-frame area of the three planes (what th_decode_ycbcr_out exposes, decode.c:2988-2992),
+   device -> the same positions of a host buffer laid out like the reference's; asynchronous on the
+   context's stream.  ocg_picture_bytes: the bytes that moves. */
+OCG_API int  ocg_ctx_download_picture(ocg_ctx *ctx, int buf, uint8_t *host_buf);
+OCG_API long ocg_picture_bytes(const ocg_geometry *g);
 OCG_API int  ocg_ctx_fill_frame(ocg_ctx *ctx, int buf, int value);  /* oc_dec_init_dummy_frame, decode.c:2053 */
 /* Page-locks caller-owned host memory (the reference's ref_frame_handle) so the
    per-frame D2H runs at full PCIe rate and asynchronously. */
@@ -185,6 +190,17 @@ OCG_API int  ocg_dec_staging(ocg_ctx *ctx, ocg_staging *out);
    the finished SELF buffer is also copied back (ref_frame_sz bytes) on the same
    stream; call ocg_ctx_sync before reading it. */
 OCG_API int  ocg_dec_submit(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_out);
+
+/* The same frame flush as ONE driver call: lists H2D, [DC un-prediction], reconstruction, loop filter,
+   borders, copy-back and a completion flag in host memory are a CUDA graph that is instantiated once per
+   (staging slot, SELF buffer, destination) and replayed; ocg_dec_wait polls the flag without entering
+   the driver.  host_out must be page-locked (ocg_host_register) and laid out like the reference's buffer;
+   out_mode selects what is copied back.  dc_residual 0 or 1. */
+#define OCG_OUT_PICTURE 0   /* the coded-frame area of the three planes (what th_decode_ycbcr_out exposes) */
+#define OCG_OUT_PADDED  1   /* the whole padded buffer, aprons included */
+#define OCG_OUT_NONE    2   /* nothing: the frame stays on the device */
+OCG_API int  ocg_dec_flush(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_out, int out_mode);
+OCG_API int  ocg_dec_wait(ocg_ctx *ctx);   /* until the last ocg_dec_flush has completed */
 
 /* ---- decode: device-resident frames, batched over independent streams ---- */
 OCG_API int  ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int nfrags,
@@ -356,7 +372,10 @@ typedef struct ocg_me_mb {
   int16_t  ref_mv[4];         /* oc_mcenc_refine4mv result (valid after OCG_ME_REFINE_4MV)  */
   uint32_t block_satd[4];     /* block_satd[bi] as the full-pel search left it              */
   uint32_t ref_block_satd[4]; /* block_satd[bi] after oc_mcenc_refine4mv                    */
-  uint8_t  pad[12];
+  int16_t  gold_ref_mv;       /* OCG_ME_SPEC_GOLD: what oc_mcenc_refine1mv(OC_FRAME_GOLD) would */
+  uint16_t pad0;              /*   make of analysis_mv[0][GOLD] / satd[GOLD] (macro blocks whose */
+  uint32_t gold_ref_satd;     /*   GOLD vector was not refined inside the chain)                */
+  uint8_t  pad[4];
 } ocg_me_mb;                  /* 96 bytes */
 
 #define OCG_ME_REFINE_PREV 1   /* inter frame: oc_mcenc_refine1mv(OC_FRAME_PREV) for every MB   */
@@ -364,6 +383,7 @@ typedef struct ocg_me_mb {
 #define OCG_ME_NOSATD      4   /* sp_level>=OC_SP_LEVEL_NOSATD: SAD instead of SATD (mcenc.c:233,648) */
 #define OCG_ME_FAST        8   /* sp_level>=OC_SP_LEVEL_FAST_ANALYSIS: no block_mv/block_satd (mcenc.c:506) */
 #define OCG_ME_DROPPED    16   /* _enc->prevframe_dropped (mcenc.c:523)                          */
+#define OCG_ME_SPEC_GOLD  32   /* also compute gold_ref_mv / gold_ref_satd for every macro block */
 
 typedef struct ocg_me ocg_me;
 /* Macro blocks of the frame in the reference's numbering (4 per luma super
@@ -387,6 +407,17 @@ OCG_API int  ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int 
 /* Copy the state out (after the queued work has finished) / seed it. */
 OCG_API int  ocg_me_read(ocg_me *me, ocg_me_mb *out);
 OCG_API int  ocg_me_write(ocg_me *me, const ocg_me_mb *in);
+/* The same without the stream synchronisation (page-locked arrays; the caller orders them, e.g. with
+   ocg_ctx_sync). */
+OCG_API int  ocg_me_read_async(ocg_me *me, ocg_me_mb *out);
+OCG_API int  ocg_me_write_async(ocg_me *me, const ocg_me_mb *in);
+/* One macro block again, against reference frame `frame` (0 GOLD, 1 PREV) of the last ocg_me_frame call,
+   with the caller's candidate set; refine != 0 adds oc_mcenc_refine1mv of the result.  Synchronous.  For
+   callers that run the GOLD chain without refinements (their decision, analyze.c:2476-2485) and must
+   redo the macro blocks whose candidates a later refinement changed (mcenc.c:104-110). */
+OCG_API int  ocg_me_repair(ocg_me *me, int frame, const ocg_mb_search_in *in, int refine, ocg_mb_search_out *out,
+                           ocg_mb_refine_out *rout);
+OCG_API int  ocg_ctx_device(const ocg_ctx *ctx);
 
 /* Intra-frame analysis pre-pass (BASELINE config "intra-only encode").  The
    per-block encoder hooks return their result synchronously to serial host

@@ -94,22 +94,6 @@ def test_intra_only_encode_422_444(fmt):
     got.free()
 
 
-def test_inter_capable_encoder_keeps_host_kernels():
-    """keyframe_granule_shift > 0: not served by the device encoder; the stream
-    is still the reference's and the device statistics stay at zero."""
-    R = S.ref("c")
-    G = streams.lib()
-    G.ocg_backend_get_enc_stats(None, 1)
-    want = S.Stream.encode(R, 96, 80, 4, quality=32, kf=4, speed=1, noise_shift=28)
-    got = S.Stream.encode(G, 96, 80, 4, quality=32, kf=4, speed=1, noise_shift=28)
-    st = streams.EncBackendStats()
-    G.ocg_backend_get_enc_stats(C.byref(st), 0)
-    assert st.frames == 0
-    assert got.to_bytes() == want.to_bytes()
-    want.free()
-    got.free()
-
-
 def test_multithreaded_encoders_agree_with_the_reference():
     R = S.ref("c")
     G = streams.lib()

@@ -23,16 +23,17 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("dc_mode", [streams.DC_DEVICE, streams.DC_HOST])
+@pytest.mark.parametrize("dc_mode", [streams.DC_DEVICE, streams.DC_HOST, streams.DC_DEVICE_AHEAD])
 @pytest.mark.parametrize("case", CASES)
 def test_public_api_decode_matches_reference(case, dc_mode):
-    """DC_DEVICE: DC un-prediction by the wave-front kernel; DC_HOST: by the reference's C routine."""
+    """DC_DEVICE: DC un-prediction by the wave-front kernel inside the flush graph; DC_DEVICE_AHEAD: the same
+    kernel started ahead of the lists; DC_HOST: on the host, in the hook."""
     w, h, n, q, kf, sp, ns = case
     R = S.ref("c")
     st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns)
     g, works, outs = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_GPU, dc_mode=dc_mode)
-    # DC_DEVICE on the device path: the recurrence is started ahead of the lists (dc_residual == 2)
-    assert all(wk is None or wk.dc_residual == (2 if dc_mode == streams.DC_DEVICE else 0) for wk in works)
+    want = {streams.DC_DEVICE: 1, streams.DC_HOST: 0, streams.DC_DEVICE_AHEAD: 2}[dc_mode]
+    assert all(wk is None or wk.dc_residual == want for wk in works)
     dec = S.Decoder(R, st)
     assert len(outs) == n
     for i in range(n):

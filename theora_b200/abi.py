@@ -52,9 +52,9 @@ ME_TOPO_DTYPE = np.dtype([("frag_off", "<i4", (4,)), ("cn", "<i4", (4,)), ("ncn"
 ME_MB_DTYPE = np.dtype([("analysis_mv", "<i2", (3, 2)), ("error", "<u2", (2,)), ("satd", "<u4", (2,)),
                         ("unref_mv", "<i2", (2,)), ("unref_satd", "<u4", (2,)), ("block_mv", "<i2", (4,)),
                         ("ref_mv", "<i2", (4,)), ("block_satd", "<u4", (4,)), ("ref_block_satd", "<u4", (4,)),
-                        ("pad", "u1", (12,))])
+                        ("gold_ref_mv", "<i2"), ("pad0", "<u2"), ("gold_ref_satd", "<u4"), ("pad", "u1", (4,))])
 assert ME_TOPO_DTYPE.itemsize == 40 and ME_MB_DTYPE.itemsize == 96
-OCG_ME_REFINE_PREV, OCG_ME_REFINE_4MV, OCG_ME_NOSATD, OCG_ME_FAST, OCG_ME_DROPPED = 1, 2, 4, 8, 16
+OCG_ME_REFINE_PREV, OCG_ME_REFINE_4MV, OCG_ME_NOSATD, OCG_ME_FAST, OCG_ME_DROPPED, OCG_ME_SPEC_GOLD = 1, 2, 4, 8, 16, 32
 
 
 def cls_of_last_zzi(last_zzi):
@@ -143,11 +143,15 @@ _PROTOS = {
     "ocg_ctx_frame_devptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ocg_ctx_upload_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ocg_ctx_download_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ocg_ctx_download_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ocg_picture_bytes": (C.c_long, [C.POINTER(Geometry)]),
     "ocg_ctx_fill_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ocg_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "ocg_host_unregister": (C.c_int, [C.c_void_p]),
     "ocg_dec_staging": (C.c_int, [C.c_void_p, C.POINTER(Staging)]),
     "ocg_dec_submit": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p]),
+    "ocg_dec_flush": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p, C.c_int]),
+    "ocg_dec_wait": (C.c_int, [C.c_void_p]),
     "ocg_pack_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecFrame), C.c_int, C.c_int, C.c_int]),
     "ocg_pack_destroy": (None, [C.c_void_p]),
     "ocg_pack_nframes": (C.c_int, [C.c_void_p]),
@@ -165,6 +169,10 @@ _PROTOS = {
     "ocg_me_frame_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p]),
     "ocg_me_read": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ocg_me_write": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocg_me_read_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocg_me_write_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocg_me_repair": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ocg_ctx_device": (C.c_int, [C.c_void_p]),
     "ocg_profile_enable": (None, [C.c_int]),
     "ocg_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "ocg_enc_metrics_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

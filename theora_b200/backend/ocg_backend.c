@@ -36,6 +36,8 @@
 th_dec_ctx *oc_refimpl_decode_alloc(const th_info *_info, const th_setup_info *_setup);
 void oc_refimpl_decode_free(th_dec_ctx *_dec);
 int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
+int oc_refimpl_decode_packetin(th_dec_ctx *_dec, const ogg_packet *_op, ogg_int64_t *_granpos);
+int oc_refimpl_decode_ycbcr_out(th_dec_ctx *_dec, th_ycbcr_buffer _ycbcr);
 void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_dec_host.c */
 void oc_state_accel_init_ocg(oc_theora_state *_state);
 void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli); /* ocg_dec_host.c */
@@ -62,6 +64,10 @@ typedef struct ocg_backend {
   int                expand;      /* the back-end expands the tokens itself (ocg_host_expand_mcu_plane) */
   unsigned           stray;       /* see ocg_host_expand_mcu_plane */
   int                dc_ahead;    /* ocg_dec_dc_begin was called for the frame being assembled */
+  int                dc_ahead_used;
+  int                pending;     /* a flushed frame's kernels / copy-back may still be running */
+  int                failed;      /* a device call failed: the decoder is unusable, the API returns TH_EFAULT */
+  int                out_mode;
   th_stripe_callback user_cb;
   struct ocg_backend *next;
 } ocg_backend;
@@ -71,6 +77,7 @@ static ocg_backend *g_list;
 static int g_mode = OCG_BACKEND_GPU;
 static int g_dc_mode = OCG_DC_HOST;
 static int g_expand_mode = OCG_EXPAND_BACKEND;
+static int g_out_mode = OCG_OUT_PICTURE;
 static ocg_capture_fn g_capture;
 static void *g_capture_user;
 static int g_device; /* one process per GPU: process-wide */
@@ -82,6 +89,7 @@ OCG_API void ocg_backend_set_mode(int mode) { g_mode = mode; }
 OCG_API void ocg_backend_set_device(int device) { g_device = device; }
 OCG_API void ocg_backend_set_dc_mode(int mode) { g_dc_mode = mode; }
 OCG_API void ocg_backend_set_expand_mode(int mode) { g_expand_mode = mode; }
+OCG_API void ocg_backend_set_output_mode(int mode) { g_out_mode = mode; }
 OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user) { g_capture = fn; g_capture_user = user; }
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset) {
   pthread_mutex_lock(&g_stats_lock);
@@ -106,9 +114,32 @@ static ocg_backend *backend_of(const void *dec) {
   return b;
 }
 
-static void backend_fatal(const char *what) {
-  fprintf(stderr, "theora_b200 back-end: %s (%s)\n", what, ocg_last_error());
+/* The hooks cannot report errors (state.h:352-370: all void).  A failed device call is latched: the rest
+   of the frame's hooks become no-ops and the th_decode_* wrappers below return TH_EFAULT from then on
+   (the decoder's reference frames are no longer valid).  OCG_BACKEND_ABORT_ON_ERROR keeps the old
+   behaviour for debugging. */
+static void backend_fail(ocg_backend *b, const char *what) {
+  if (b == NULL || !b->failed) fprintf(stderr, "theora_b200 back-end: %s (%s)\n", what, ocg_last_error());
+#if defined(OCG_BACKEND_ABORT_ON_ERROR)
   abort();
+#endif
+  if (b != NULL) {
+    b->failed = 1;
+    b->frame_open = 0;
+    b->pending = 0;
+  }
+}
+
+/* Waits for the last flushed frame (kernels + copy-back). */
+static void backend_wait(ocg_backend *b) {
+  if (b->pending && b->ctx != NULL) {
+    double t0 = now_s();
+    b->pending = 0;
+    if ((b->dc_ahead_used ? ocg_ctx_sync(b->ctx) : ocg_dec_wait(b->ctx)) < 0) { backend_fail(b, "waiting for the frame failed"); return; }
+    pthread_mutex_lock(&g_stats_lock);
+    g_stats.wait_seconds += now_s() - t0;
+    pthread_mutex_unlock(&g_stats_lock);
+  }
 }
 
 static void stats_add(const ocg_backend *b, long h2d, long d2h, double secs) {
@@ -130,7 +161,7 @@ static void backend_begin_frame(ocg_backend *b) {
   /* staging records keep buf_off/plane from context creation; every fragment
      is visited once per frame by exactly one of the recon and copy-list hooks
      (decode.c:1584,1601), which refresh the rest */
-  if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) backend_fatal("ocg_dec_staging failed");
+  if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) { backend_fail(b, "ocg_dec_staging failed"); return; }
   b->ncoded = b->nrows = 0;
   b->stray = 0;
   /* decode.c:2790-2794 has already picked SELF; GOLD/PREV are still the
@@ -139,11 +170,11 @@ static void backend_begin_frame(ocg_backend *b) {
   memset(b->dcq, 0, sizeof(b->dcq));
   b->frame_open = 1;
   b->dc_ahead = 0;
-  if (b->dc_device && b->ctx != NULL) {
+  if (b->dc_device == 2 && b->ctx != NULL) {
     /* Every input of the DC recurrence (coded flags, reference types, residuals) is in frags[] once the
        tokens are unpacked (decode.c:2822), i.e. now: the device starts on it while the host expands
        the coefficients of the whole frame. */
-    if (ocg_dec_dc_begin(b->ctx, (const ogg_uint32_t *)st->frags) < 0) backend_fatal("ocg_dec_dc_begin failed");
+    if (ocg_dec_dc_begin(b->ctx, (const ogg_uint32_t *)st->frags) < 0) { backend_fail(b, "ocg_dec_dc_begin failed"); return; }
     b->dc_ahead = 1;
   }
 }
@@ -161,41 +192,61 @@ static void backend_flush(ocg_backend *b) {
   f.intra_frame = st->frame_type == OC_INTRA_FRAME;
   f.ncoeff_rows = b->nrows;
   f.dc_residual = b->dc_device ? (b->dc_ahead ? 2 : 1) : 0;
+  b->dc_ahead_used = b->dc_ahead;
   b->dc_ahead = 0;
   b->frame_open = 0;
   if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
   if (b->ctx == NULL) { stats_add(b, 0, 0, 0.0); return; } /* record mode */
   {
-    unsigned char *host_self = st->ref_frame_handle + (size_t)f.ref_idx[OCG_FRAME_SELF] * (size_t)b->geom.ref_frame_sz;
-    long extra_h2d = 0;
+    const int self = f.ref_idx[OCG_FRAME_SELF];
+    unsigned char *host_self = st->ref_frame_handle + (size_t)self * (size_t)b->geom.ref_frame_sz;
+    long extra_h2d = 0, d2h;
+    int r;
     /* A reference the device has never produced (stream starting on an inter
        frame: oc_dec_init_dummy_frame, decode.c:2053) is taken from the host. */
     if (st->frame_type != OC_INTRA_FRAME) {
       for (i = 0; i < 2; i++) {
         int ri = f.ref_idx[i];
         if (ri >= 0 && !b->dev_valid[ri]) {
-          if (ocg_ctx_upload_frame(b->ctx, ri, st->ref_frame_handle + (size_t)ri * (size_t)b->geom.ref_frame_sz) < 0)
-            backend_fatal("reference upload failed");
+          if (ocg_ctx_upload_frame(b->ctx, ri, st->ref_frame_handle + (size_t)ri * (size_t)b->geom.ref_frame_sz) < 0) {
+            backend_fail(b, "reference upload failed");
+            return;
+          }
           b->dev_valid[ri] = 1;
           extra_h2d += (long)b->geom.ref_frame_sz;
         }
       }
     }
-    if (ocg_dec_submit(b->ctx, &f, host_self) < 0) backend_fatal("ocg_dec_submit failed");
-    if (ocg_ctx_sync(b->ctx) < 0) backend_fatal("ocg_ctx_sync failed");
-    b->dev_valid[f.ref_idx[OCG_FRAME_SELF]] = 1;
-    stats_add(b, extra_h2d + (long)b->geom.nfrags * 16 + (long)b->nrows * 16, (long)b->geom.ref_frame_sz,
-              now_s() - t0);
+    /* Everything below is queued on the context's stream and NOT waited for here: the frame is only
+       needed in host memory when the application asks for it (th_decode_ycbcr_out), a stripe callback
+       is due, or post-processing reads it; meanwhile this thread is free (the next packet's entropy
+       decode touches none of it) and other stream threads get the core. */
+    if (b->dc_ahead_used) {
+      /* the opt-in "DC ahead of the lists" variant keeps the call-by-call path */
+      if (ocg_dec_submit(b->ctx, &f, NULL) < 0) { backend_fail(b, "ocg_dec_submit failed"); return; }
+      r = b->out_mode == OCG_OUT_PADDED ? ocg_ctx_download_frame(b->ctx, self, host_self)
+                                        : ocg_ctx_download_picture(b->ctx, self, host_self);
+      if (r < 0) { backend_fail(b, "frame copy-back failed"); return; }
+    } else if (ocg_dec_flush(b->ctx, &f, host_self, b->out_mode) < 0) { backend_fail(b, "ocg_dec_flush failed"); return; }
+    d2h = b->out_mode == OCG_OUT_PADDED ? (long)b->geom.ref_frame_sz : ocg_picture_bytes(&b->geom);
+    b->pending = 1;
+    b->dev_valid[self] = 1;
+    stats_add(b, extra_h2d + (long)b->geom.nfrags * 16 + (long)b->nrows * 16, d2h, now_s() - t0);
   }
   /* Out-of-loop post-processing (non-normative, decode.c:2899-2914) ran inside the MCU loop on a host
      frame that was not there yet; now that it is, run it again over the whole frame. */
-  if (b->ctx != NULL && b->dec->pipe.pp_level > 0 /* OC_PP_LEVEL_DISABLED */)
+  if (b->ctx != NULL && b->dec->pipe.pp_level > 0 /* OC_PP_LEVEL_DISABLED */) {
+    backend_wait(b);
+    if (b->failed) return;
     ocg_pp_host_whole_frame(b->dec, f.ref_idx[OCG_FRAME_SELF]);
+  }
   /* the stripe callback, once, with the whole (now final) frame:
      decode.c:2936-2940 flips the row range, the telemetry path at 2975 already
      calls it with the full range. */
   if (b->user_cb.stripe_decoded != NULL) {
     th_ycbcr_buffer stripe;
+    backend_wait(b);
+    if (b->failed) return;
     oc_ycbcr_buffer_flip(stripe, b->dec->pp_frame_buf);
     (*b->user_cb.stripe_decoded)(b->user_cb.ctx, stripe, 0, st->fplanes[0].nvfrags);
   }
@@ -204,6 +255,7 @@ static void backend_flush(ocg_backend *b) {
 /* ---- recorders ----------------------------------------------------------- */
 static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli) {
   ocg_backend *b = backend_of(_dec);
+  if (b != NULL && b->failed) b = NULL; /* latched error: behave like the plain C table until the API reports it */
   if (b != NULL && b->dc_device) {
     /* the device undoes the prediction (ocg_dc_unpredict_kernel); what is left of
        this hook is its side effect, decode.c:1496-1499: the MCU's fragment counts */
@@ -222,6 +274,7 @@ static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *
     oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
   }
   if (b != NULL && !b->frame_open) backend_begin_frame(b);
+  if (b != NULL && b->failed) return;
   if (b != NULL && b->expand) {
     /* claim the MCU's fragments: expand their tokens straight into the flush lists and leave
        oc_dec_frags_recon_mcu_plane (decode.c:1511) an empty range */
@@ -252,7 +305,8 @@ static void ocg_state_frag_recon(const oc_theora_state *_state, ptrdiff_t _fragi
   int nr, r, qti, mask = 0;
   ogg_int16_t dc = _dct_coeffs[0];
   if (__builtin_expect(b == NULL || (const void *)b->dec != (const void *)_state, 0)) b = backend_of(_state);
-  if (b == NULL || !b->frame_open) backend_fatal("state_frag_recon outside a frame");
+  if (b == NULL || b->failed) return;
+  if (!b->frame_open) { backend_fail(b, "state_frag_recon outside a frame"); return; }
   /* footprint of the transform the reference would run (state.c:967,
      idct.c:327-329): 0, 2, 4 or 8 leading rows */
   nr = _last_zzi < 2 ? 0 : (_last_zzi <= 3 ? 2 : (_last_zzi <= 10 ? 4 : 8));
@@ -296,7 +350,8 @@ static void ocg_frag_copy_list(unsigned char *_dst_frame, const unsigned char *_
   ocg_frag_rec *recs;
   ptrdiff_t i;
   (void)_dst_frame; (void)_src_frame; (void)_ystride; (void)_frag_buf_offs;
-  if (b == NULL || !b->frame_open) backend_fatal("frag_copy_list outside a frame");
+  if (b == NULL || b->failed) return;
+  if (!b->frame_open) { backend_fail(b, "frag_copy_list outside a frame"); return; }
   recs = b->st.recs;
   for (i = 0; i < _nfragis; i++) recs[_fragis[i]].refi = OCG_FRAG_UNCODED;
 }
@@ -309,7 +364,7 @@ static void ocg_state_loop_filter_frag_rows(const oc_theora_state *_state, signe
 
 static void ocg_restore_fpu(void) {
   ocg_backend *b = t_cur;
-  if (b != NULL && b->frame_open) backend_flush(b);
+  if (b != NULL && b->frame_open && !b->failed) backend_flush(b);
 }
 
 /* ---- init functions named by ocg_hooks.h --------------------------------- */
@@ -373,7 +428,10 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
     return;
   }
   b->expand = g_expand_mode == OCG_EXPAND_BACKEND;
-  b->dc_device = g_dc_mode == OCG_DC_DEVICE && (b->mode != OCG_BACKEND_GPU || ocg_dc_unpredict_supported(&b->geom));
+  b->out_mode = g_out_mode;
+  b->dc_device = (g_dc_mode == OCG_DC_DEVICE || g_dc_mode == OCG_DC_DEVICE_AHEAD) &&
+                 (b->mode != OCG_BACKEND_GPU || ocg_dc_unpredict_supported(&b->geom));
+  if (b->dc_device && g_dc_mode == OCG_DC_DEVICE_AHEAD) b->dc_device = 2;
   if (b->dc_device && b->mode == OCG_BACKEND_GPU) {
     /* the device reads oc_fragment as a 32-bit word: bit 0 coded, bits 6-7 refi, bits 16-31 dc (state.h:297-322
        as this compiler lays the bit-fields out); verify instead of assuming */
@@ -432,6 +490,26 @@ th_dec_ctx *th_decode_alloc(const th_info *_info, const th_setup_info *_setup) {
     return NULL;
   }
   return dec;
+}
+
+/* The flush at the end of th_decode_packetin (decode.c:2965) is asynchronous; the frame must be in host
+   memory when the application looks at it. */
+int th_decode_packetin(th_dec_ctx *_dec, const ogg_packet *_op, ogg_int64_t *_granpos) {
+  ocg_backend *b = _dec != NULL ? backend_of(_dec) : NULL;
+  int ret;
+  if (b != NULL && b->failed) return TH_EFAULT;
+  ret = oc_refimpl_decode_packetin(_dec, _op, _granpos);
+  if (b != NULL && b->failed) return TH_EFAULT;
+  return ret;
+}
+
+int th_decode_ycbcr_out(th_dec_ctx *_dec, th_ycbcr_buffer _ycbcr) {
+  ocg_backend *b = _dec != NULL ? backend_of(_dec) : NULL;
+  if (b != NULL) {
+    backend_wait(b);
+    if (b->failed) return TH_EFAULT;
+  }
+  return oc_refimpl_decode_ycbcr_out(_dec, _ycbcr);
 }
 
 void th_decode_free(th_dec_ctx *_dec) {

@@ -31,8 +31,9 @@ OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders al
    ~0.55 ms of coefficient expansion, which is not enough to hide it: measured through
    th_decode_packetin 8.5 k vs 11.5 k frames/s for OCG_DC_HOST (6.8 k when the kernel sits in the flush),
    so the host routine stays the default. */
-#define OCG_DC_DEVICE 0
+#define OCG_DC_DEVICE 0        /* inside the flush graph (dc_residual=1) */
 #define OCG_DC_HOST   1
+#define OCG_DC_DEVICE_AHEAD 2  /* started at the first hook of the frame (ocg_dec_dc_begin, dc_residual=2) */
 OCG_API void ocg_backend_set_dc_mode(int mode);   /* applies to decoders allocated afterwards */
 
 /* Who expands a coded fragment's tokens into coefficients (decode.c:1531-1586):
@@ -43,6 +44,11 @@ OCG_API void ocg_backend_set_dc_mode(int mode);   /* applies to decoders allocat
 #define OCG_EXPAND_BACKEND   0
 #define OCG_EXPAND_REFERENCE 1
 OCG_API void ocg_backend_set_expand_mode(int mode);   /* applies to decoders allocated afterwards */
+
+/* What the flush copies back into the decoder's host reference buffer (the memory th_decode_ycbcr_out
+   hands out): OCG_OUT_PICTURE (default) = the coded-frame area of the three planes, which is all the API
+   exposes; OCG_OUT_PADDED = the whole padded buffer including the aprons (diagnostics). */
+OCG_API void ocg_backend_set_output_mode(int mode);   /* applies to decoders allocated afterwards */
 
 /* Called at every frame flush with the frame description (list pointers NULL)
    and the staged lists, before they are submitted. */
@@ -57,7 +63,8 @@ typedef struct ocg_backend_stats {
   long   coeff_rows;
   long   h2d_bytes;
   long   d2h_bytes;
-  double flush_seconds;   /* host wall time inside flush (submit + sync) */
+  double flush_seconds;   /* host wall time inside the flush (queueing copies and kernels) */
+  double wait_seconds;    /* host wall time waiting for a flushed frame (th_decode_ycbcr_out, stripe callback) */
 } ocg_backend_stats;
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset);
 
@@ -83,6 +90,9 @@ typedef struct ocg_enc_backend_stats {
   long   d2h_bytes;
   double prepass_seconds;   /* host wall time inside the pre-pass call        */
   double flush_seconds;     /* host wall time inside the reconstruction flush */
+  long   me_frames;         /* analysis passes whose motion analysis ran on the device          */
+  long   me_gold_refines;   /* oc_mcenc_refine1mv(OC_FRAME_GOLD) decisions of the host loop      */
+  long   me_repairs;        /* GOLD searches redone because a neighbour's refinement changed their candidates */
 } ocg_enc_backend_stats;
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset);
 /* Test instrumentation: a snapshot at the start of every analysis pass of an encoder that runs on the

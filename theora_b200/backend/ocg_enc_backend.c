@@ -1,31 +1,30 @@
-/* ocg_enc_backend.c -- encoder half of the vtable back-end: INTRA frames of an
- * unmodified th_encode_* run their block pipeline on the B200.
+/* ocg_enc_backend.c -- encoder half of the vtable back-end.
  *
  * Every encoder hook (encint.h:292-325) returns its result synchronously to
  * serial host code (mode decision, R-D tokeniser), so none of them can launch
- * a kernel per call.  For an intra frame, however,
- *   frag_intra_satd(src)                      analyze.c:1385-1534
- *   frag_sub_128(src) -> fdct8x8 -> quantize  analyze.c:725-782
- * are functions of the input frame and the frame's quantiser tables only.
- * The first hook of a frame, enquant_table_fixup (analyze.c:564, after the
- * input has been copied into OC_FRAME_IO and the tables have been condensed),
- * therefore runs ONE batched device pre-pass over all fragments
- * (ocg_enc_intra_prepass) and the per-block hooks become table look-ups keyed
- * by the block's source pointer.  What happens after the tokeniser --
- * idct8x8 + frag_recon_intra (analyze.c:803-822), the loop filter and the
- * border fill -- is never read back by intra analysis (the SSD check at
- * analyze.c:825 is inter-only, _fr!=NULL), so it is RECORDED exactly like the
- * decoder's state_frag_recon and flushed through ocg_dec_submit at the
- * restore_fpu that opens oc_enc_frame_pack (encode.c:911); the reconstructed
- * frame is copied back into the host SELF buffer for whoever predicts from it.
+ * a kernel per call.  What the device does instead:
  *
- * Inter frames need their reconstruction inside the analysis loop (skip
- * decision, analyze.c:825-862) and their candidates from already-analysed
- * neighbours (mcenc.c:90-164): that needs a restructured caller and is not
- * served by this back-end.  An encoder that can emit inter frames
- * (keyframe_granule_shift > 0) keeps the reference's C kernels on the host; an
- * intra-only encoder (keyframe_granule_shift == 0) takes the device path and
- * fails to allocate without a device -- there is no silent CPU fallback for it.
+ * INTRA frames.  frag_intra_satd(src) (analyze.c:1385-1534) and
+ * frag_sub_128(src) -> fdct8x8 -> quantize (analyze.c:725-782) are functions
+ * of the input frame and the frame's quantiser tables only.  The first hook of
+ * an analysis pass, enquant_table_fixup (analyze.c:564), runs ONE batched
+ * device pre-pass over all fragments (ocg_enc_intra_prepass) and the per-block
+ * hooks become table look-ups keyed by the block's source pointer.
+ *
+ * EVERY frame.  What happens after the tokeniser -- idct8x8 + frag_recon_*
+ * (analyze.c:803-822), the uncoded-fragment copy, the loop filter and the
+ * border fill -- is RECORDED like the decoder's state_frag_recon and flushed as
+ * one CUDA graph (ocg_dec_flush) at the restore_fpu that opens
+ * oc_enc_frame_pack (encode.c:911): the reconstructed reference frames live on
+ * the device; for an encoder that can emit inter frames the finished frame is
+ * also copied back into the host's buffer.
+ *
+ * INTER frames (encoders with keyframe_granule_shift > 0).  The analysis loop
+ * compares the SSD of the block it has just reconstructed (analyze.c:825-868)
+ * and its mode costs depend on the running entropy state, so the loop stays on
+ * the host; see DESIGN.md section 1 for what the device serves to it and what
+ * the loop still computes itself (with the reference's plain C kernels: no
+ * lib/x86 code is linked).
  */
 #include <stddef.h>
 #include <stdio.h>
@@ -36,9 +35,13 @@
 #include "encint.h"
 #include "ocg_backend.h"
 
-/* the reference's own entry points, renamed on encode.c's command line */
+/* the reference's own entry points, renamed on encode.c's / mcenc.c's command line */
 th_enc_ctx *oc_refimpl_encode_alloc(const th_info *_info);
 void oc_refimpl_encode_free(th_enc_ctx *_enc);
+int oc_refimpl_encode_ycbcr_in(th_enc_ctx *_enc, th_ycbcr_buffer _img);
+void oc_refimpl_mcenc_search(oc_enc_ctx *_enc, int _mbi);
+void oc_refimpl_mcenc_refine1mv(oc_enc_ctx *_enc, int _mbi, int _frame);
+void oc_refimpl_mcenc_refine4mv(oc_enc_ctx *_enc, int _mbi);
 
 int ocg_backend_device_(void); /* ocg_backend.c */
 
@@ -49,7 +52,12 @@ typedef struct ocg_enc_backend {
   ocg_staging          st;
   ocg_enc_intra_tables tab;
   int                  nqis;
-  int                  frame_open;
+  int                  frame_open;     /* an analysis pass is being recorded */
+  int                  tables;         /* the intra pre-pass tables serve this pass */
+  int                  inter_capable;  /* keyframe_granule_shift > 0: inter frames possible, host frames kept current */
+  int                  inter_frame;    /* the pass in progress analyses an inter frame */
+  int                  pending;        /* a flushed frame may still be running / copying back */
+  int                  failed;         /* latched: hooks fall through to the C kernels, the API returns TH_EFAULT */
   int                  ncoded;
   int                  nrows;
   int                  pinned;
@@ -58,13 +66,23 @@ typedef struct ocg_enc_backend {
   ogg_int32_t         *off2frag;
   ptrdiff_t            off_min;
   size_t               noff;
-  /* block in flight: sub_128 -> fdct8x8 -> quantize -> [idct8x8] -> recon_intra */
+  /* block in flight: sub_128 -> fdct8x8 -> quantize -> [idct8x8] -> recon */
   ptrdiff_t            cur_fragi;
   int                  idct_pending;
   int                  pend_last_zzi;
   ogg_uint32_t         pend_row0;
   int                  pend_mask;
   ogg_int16_t          pend_dc;
+  /* whole-frame motion analysis on the device (oc_mcenc_search / refine*, served as look-ups) */
+  ocg_me              *me;
+  ocg_me_mb           *me_tab;         /* page-locked: state upload, then the device's results for this frame */
+  int                  me_valid;       /* me_tab holds the results of the frame being analysed */
+  int                  me_flags;
+  int                  me_seen_frame;  /* a pass for me_frame_num has run */
+  ogg_int64_t          me_frame_num;
+  unsigned char       *gold_dirty;     /* [nmbs] the macro block's final GOLD vector/error differ from the speculation */
+  unsigned char       *gold_fixed;     /* [nmbs] its GOLD search was redone (gold_fix holds the refinement) */
+  struct { ogg_int16_t mv; ogg_uint32_t satd; } *gold_fix;
   /* quantiser tables in the layout of ocg_enc_fdct_quant_batch */
   ogg_uint16_t         dequant[3][2][3][64];
   ogg_int16_t          enquant[3][2][3][64][2];
@@ -97,9 +115,21 @@ static double enc_now_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static void enc_fatal(const char *what) {
-  fprintf(stderr, "theora_b200 encoder back-end: %s (%s)\n", what, ocg_last_error());
+/* The hooks cannot report errors (encint.h:292-325: they return data).  A failed device call or a violated
+   assumption is latched: from then on every hook falls through to the reference's C kernel, so the host
+   code above keeps running on defined data, nothing touches the device any more, and th_encode_ycbcr_in
+   returns TH_EFAULT (the encoder's reference frames are no longer trustworthy). */
+static void enc_fail(ocg_enc_backend *b, const char *what) {
+  if (b == NULL || !b->failed) fprintf(stderr, "theora_b200 encoder back-end: %s (%s)\n", what, ocg_last_error());
+#if defined(OCG_BACKEND_ABORT_ON_ERROR)
   abort();
+#endif
+  if (b != NULL) {
+    b->failed = 1;
+    b->frame_open = 0;
+    b->tables = 0;
+    b->pending = 0;
+  }
 }
 
 static ocg_enc_backend *enc_backend_of(const oc_enc_ctx *enc) {
@@ -111,82 +141,202 @@ static ocg_enc_backend *enc_backend_of(const oc_enc_ctx *enc) {
   return b;
 }
 
+/* Fragment whose row 0 is at p inside the buffer playing role `frame`, or -1. */
 static inline ptrdiff_t enc_fragi_of(const ocg_enc_backend *b, const unsigned char *p, int frame) {
   const unsigned char *base = b->enc->state.ref_frame_data[frame];
   size_t k = (size_t)((p - base) - b->off_min);
-  ogg_int32_t fragi;
-  if ((k & 7) != 0 || (k >> 3) >= b->noff || (fragi = b->off2frag[k >> 3]) < 0)
-    enc_fatal("block pointer does not address a fragment of the expected frame");
-  return fragi;
+  if ((k & 7) != 0 || (k >> 3) >= b->noff) return -1;
+  return b->off2frag[k >> 3];
+}
+
+static void enc_wait(ocg_enc_backend *b) {
+  if (b->pending) {
+    b->pending = 0;
+    if (ocg_dec_wait(b->ctx) < 0) enc_fail(b, "ocg_dec_wait failed");
+  }
+}
+
+/* ---- motion analysis pre-pass ---------------------------------------------
+   oc_mcenc_search for macro block m reads the vectors and errors of m's already-analysed neighbours
+   (mcenc.c:90-164, 331-337) AFTER their half-pel refinement.  Against OC_FRAME_PREV that refinement always
+   runs (analyze.c:2486-2489), so the whole PREV chain is a function of the frames alone and the device's
+   wave-front reproduces it exactly.  Against OC_FRAME_GOLD it runs only where the serial mode decision
+   asks for it (analyze.c:2476-2485), which is not known here: the device runs the GOLD chain WITHOUT
+   refinements and also reports what each refinement would give; the look-ups below check, per macro
+   block, whether the neighbours' final GOLD vectors/errors still produce the candidate set the device
+   used, and redo the one search on the device where they do not (ocg_me_repair). */
+static int enc_me_prepass(ocg_enc_backend *b) {
+  oc_enc_ctx *enc = b->enc;
+  oc_theora_state *st = &enc->state;
+  static const int ROLE[5] = {OC_FRAME_IO, OC_FRAME_PREV_ORIG, OC_FRAME_GOLD_ORIG, OC_FRAME_PREV, OC_FRAME_GOLD};
+  const int first_pass = !(b->me_seen_frame && b->me_frame_num == st->curframe_num);
+  int bufs[5], i, k, flags, wanted;
+  size_t mbi;
+  if (!first_pass) return 0; /* a re-analysis of the same frame keeps the first pass's vectors (_recode, analyze.c:2402) */
+  b->me_seen_frame = 1;
+  b->me_frame_num = st->curframe_num;
+  b->me_valid = 0;
+  /* the input frame joins the device's frame pool (an intra frame's pre-pass uploads it itself) */
+  if (b->inter_frame &&
+      ocg_ctx_upload_frame(b->ctx, st->ref_frame_idx[OC_FRAME_IO],
+                           st->ref_frame_handle + (size_t)st->ref_frame_idx[OC_FRAME_IO] * (size_t)b->geom.ref_frame_sz) < 0) {
+    enc_fail(b, "input frame upload failed");
+    return -1;
+  }
+  /* who will call oc_mcenc_search in this pass: analyze.c:1723-1726 (key frames), 2402 (inter frames) */
+  wanted = enc->sp_level < OC_SP_LEVEL_NOSATD &&
+           (b->inter_frame ? 1 : st->curframe_num > 0 && enc->keyframe_frequency_force > 1);
+  for (i = 0; i < 5; i++) {
+    bufs[i] = st->ref_frame_idx[ROLE[i]];
+    if (bufs[i] < 0) wanted = 0;
+  }
+  if (!wanted) return 0;
+  if (b->me == NULL) {
+    /* the reference's own tables: mb_maps (state.c:300-330), cneighbors (encode.c:967-1048) */
+    ocg_me_topo *topo = (ocg_me_topo *)calloc(st->nmbs, sizeof(*topo));
+    if (topo == NULL) { enc_fail(b, "out of memory"); return -1; }
+    for (mbi = 0; mbi < st->nmbs; mbi++) {
+      const oc_mb_enc_info *e = enc->mb_info + mbi;
+      if (st->mb_modes[mbi] == OC_MODE_INVALID) continue;
+      topo[mbi].valid = 1;
+      topo[mbi].ncn = e->ncneighbors;
+      for (k = 0; k < e->ncneighbors; k++) topo[mbi].cn[k] = (ogg_int32_t)e->cneighbors[k];
+      for (k = 0; k < 4; k++) topo[mbi].frag_off[k] = (ogg_int32_t)st->frag_buf_offs[st->mb_maps[mbi][0][k]];
+    }
+    i = ocg_me_create(&b->me, b->ctx, topo);
+    free(topo);
+    b->me_tab = (ocg_me_mb *)calloc(st->nmbs, sizeof(*b->me_tab));
+    b->gold_dirty = (unsigned char *)calloc(st->nmbs, 1);
+    b->gold_fixed = (unsigned char *)calloc(st->nmbs, 1);
+    b->gold_fix = calloc(st->nmbs, sizeof(*b->gold_fix));
+    if (i < 0 || b->me_tab == NULL || b->gold_dirty == NULL || b->gold_fixed == NULL || b->gold_fix == NULL ||
+        ocg_host_register(b->me_tab, st->nmbs * sizeof(*b->me_tab)) < 0) {
+      enc_fail(b, "motion analysis set-up failed");
+      return -1;
+    }
+  }
+  for (mbi = 0; mbi < st->nmbs; mbi++) {
+    const oc_mb_enc_info *e = enc->mb_info + mbi;
+    ocg_me_mb *m = b->me_tab + mbi;
+    for (i = 0; i < 3; i++) for (k = 0; k < 2; k++) m->analysis_mv[i][k] = e->analysis_mv[i][k];
+    for (k = 0; k < 2; k++) { m->error[k] = e->error[k]; m->satd[k] = e->satd[k]; }
+    for (k = 0; k < 4; k++) { m->block_mv[k] = e->block_mv[k]; m->block_satd[k] = e->block_satd[k]; }
+  }
+  flags = OCG_ME_SPEC_GOLD;
+  if (b->inter_frame) flags |= OCG_ME_REFINE_PREV;
+  if (enc->sp_level >= OC_SP_LEVEL_FAST_ANALYSIS) flags |= OCG_ME_FAST;
+  else if (b->inter_frame) flags |= OCG_ME_REFINE_4MV;
+  if (enc->prevframe_dropped) flags |= OCG_ME_DROPPED;
+  if (ocg_me_write_async(b->me, b->me_tab) < 0 || ocg_me_frame(b->me, bufs, flags, NULL) < 0 ||
+      ocg_me_read_async(b->me, b->me_tab) < 0 || ocg_ctx_sync(b->ctx) < 0) {
+    enc_fail(b, "motion analysis on the device failed");
+    return -1;
+  }
+  memset(b->gold_dirty, 0, st->nmbs);
+  memset(b->gold_fixed, 0, st->nmbs);
+  b->me_flags = flags;
+  b->me_valid = 1;
+  pthread_mutex_lock(&g_estats_lock);
+  g_estats.me_frames++;
+  g_estats.h2d_bytes += (long)(b->inter_frame ? b->geom.ref_frame_sz : 0) + (long)(st->nmbs * sizeof(ocg_me_mb));
+  g_estats.d2h_bytes += (long)(st->nmbs * sizeof(ocg_me_mb));
+  pthread_mutex_unlock(&g_estats_lock);
+  return 0;
 }
 
 /* ---- frame life cycle ---------------------------------------------------- */
-static void enc_begin_frame(ocg_enc_backend *b, int nqis) {
+/* enquant_table_fixup, analyze.c:564: the first hook of every analysis pass (oc_enc_pipeline_init); the
+   input frame is in OC_FRAME_IO, the references are rotated, state.frame_type says which analysis runs. */
+static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
   oc_enc_ctx *enc = b->enc;
   oc_theora_state *st = &enc->state;
   const unsigned char *host_io;
   double t0 = enc_now_s();
   int pli, qii, zzi;
-  if (st->frame_type != OC_INTRA_FRAME)
-    enc_fatal("inter frame reached the intra-only device encoder (keyframe_granule_shift==0 expected)");
-  if (nqis < 1 || nqis > 3) enc_fatal("unexpected quantiser count");
-  /* a frame that was analysed but never packed (re-analysis) is simply dropped */
-  if (ocg_dec_staging(b->ctx, &b->st) < 0) enc_fatal("ocg_dec_staging failed");
+  b->frame_open = 0;
+  b->tables = 0;
+  if (b->failed) return;
+  /* the previous frame's reconstruction must have reached the host buffers the C kernels of an inter
+     analysis read (and its staging slots are free again) */
+  enc_wait(b);
+  if (b->failed) return;
+  if (nqis < 1 || nqis > 3) { enc_fail(b, "unexpected quantiser count"); return; }
+  b->inter_frame = st->frame_type != OC_INTRA_FRAME;
+  if (b->inter_frame && !b->inter_capable) { enc_fail(b, "inter frame in an encoder that was set up as intra-only"); return; }
+  /* a pass that was analysed but never packed (dry run, re-analysis as a key frame) is simply dropped */
+  if (ocg_dec_staging(b->ctx, &b->st) < 0) { enc_fail(b, "ocg_dec_staging failed"); return; }
   b->ncoded = b->nrows = 0;
   b->cur_fragi = -1;
   b->idct_pending = 0;
   b->nqis = nqis;
-  /* analyze.c:544-564 has just condensed the tables for this frame */
-  for (pli = 0; pli < 3; pli++)
-    for (qii = 0; qii < nqis; qii++) {
-      const oc_iquant *iq = (const oc_iquant *)enc->enquant[pli][qii][0];
-      memcpy(b->dequant[pli][0][qii], enc->dequant[pli][qii][0], 64 * sizeof(ogg_uint16_t));
-      for (zzi = 0; zzi < 64; zzi++) {
-        b->enquant[pli][0][qii][zzi][0] = iq[zzi].m;
-        b->enquant[pli][0][qii][zzi][1] = iq[zzi].l;
+  if (b->inter_capable && enc_me_prepass(b) < 0) return;
+  if (!b->inter_frame) {
+    /* analyze.c:544-564 has just condensed the tables for this frame */
+    for (pli = 0; pli < 3; pli++)
+      for (qii = 0; qii < nqis; qii++) {
+        const oc_iquant *iq = (const oc_iquant *)enc->enquant[pli][qii][0];
+        memcpy(b->dequant[pli][0][qii], enc->dequant[pli][qii][0], 64 * sizeof(ogg_uint16_t));
+        for (zzi = 0; zzi < 64; zzi++) {
+          b->enquant[pli][0][qii][zzi][0] = iq[zzi].m;
+          b->enquant[pli][0][qii][zzi][1] = iq[zzi].l;
+        }
       }
+    host_io = st->ref_frame_handle + (size_t)st->ref_frame_idx[OC_FRAME_IO] * (size_t)b->geom.ref_frame_sz;
+    if (ocg_enc_intra_prepass(b->ctx, st->ref_frame_idx[OC_FRAME_IO], host_io, &b->dequant[0][0][0][0],
+                              &b->enquant[0][0][0][0][0], nqis, &b->tab) < 0) {
+      enc_fail(b, "ocg_enc_intra_prepass failed");
+      return;
     }
-  host_io = st->ref_frame_handle + (size_t)st->ref_frame_idx[OC_FRAME_IO] * (size_t)b->geom.ref_frame_sz;
-  if (ocg_enc_intra_prepass(b->ctx, st->ref_frame_idx[OC_FRAME_IO], host_io, &b->dequant[0][0][0][0],
-                            &b->enquant[0][0][0][0][0], nqis, &b->tab) < 0)
-    enc_fatal("ocg_enc_intra_prepass failed");
+    b->tables = 1;
+    pthread_mutex_lock(&g_estats_lock);
+    g_estats.h2d_bytes += (long)b->geom.ref_frame_sz;
+    g_estats.d2h_bytes += (long)b->geom.nfrags * (8 + 4 * nqis + 128 + 128 * nqis);
+    pthread_mutex_unlock(&g_estats_lock);
+  }
   b->frame_open = 1;
   pthread_mutex_lock(&g_estats_lock);
   g_estats.prepass_frames++;
   g_estats.prepass_seconds += enc_now_s() - t0;
-  g_estats.h2d_bytes += (long)b->geom.ref_frame_sz;
-  g_estats.d2h_bytes += (long)b->geom.nfrags * (8 + 4 * nqis + 128 + 128 * nqis);
   pthread_mutex_unlock(&g_estats_lock);
 }
 
+/* restore_fpu at encode.c:911 (oc_enc_frame_pack): the analysis pass that will be packed is complete. */
 static void enc_flush(ocg_enc_backend *b) {
   oc_theora_state *st = &b->enc->state;
   ocg_dec_frame f;
   double t0 = enc_now_s();
-  int pli;
+  int pli, self = st->ref_frame_idx[OC_FRAME_SELF];
   b->frame_open = 0;
-  if (b->ncoded != b->geom.nfrags) enc_fatal("intra frame did not reconstruct every fragment");
+  b->tables = 0;
+  if (!b->inter_frame && b->ncoded != b->geom.nfrags) { enc_fail(b, "intra frame did not reconstruct every fragment"); return; }
   memset(&f, 0, sizeof(f));
-  f.ref_idx[OCG_FRAME_GOLD] = f.ref_idx[OCG_FRAME_PREV] = -1;
-  f.ref_idx[OCG_FRAME_SELF] = st->ref_frame_idx[OC_FRAME_SELF];
+  f.ref_idx[OCG_FRAME_GOLD] = b->inter_frame ? st->ref_frame_idx[OC_FRAME_GOLD] : -1;
+  f.ref_idx[OCG_FRAME_PREV] = b->inter_frame ? st->ref_frame_idx[OC_FRAME_PREV] : -1;
+  f.ref_idx[OCG_FRAME_SELF] = self;
   f.lf_limit = st->loop_filter_limits[st->qis[0]];
   /* the records carry already-scaled DC terms: slot 0 = dequantised DC of a
      transformed block (analyze.c:803), slot 1 = the flat residual p of a
      DC-only block (analyze.c:790-794) as (32p+15)>>5 == p */
   for (pli = 0; pli < 3; pli++) { f.dc_quant[pli][0] = 1; f.dc_quant[pli][1] = 32; }
   f.ncoded = b->ncoded;
-  f.intra_frame = 1;
+  f.intra_frame = !b->inter_frame;
   f.ncoeff_rows = b->nrows;
-  /* An intra-only encoder never predicts from SELF, so the reconstruction stays
-     on the device (ocg_backend_enc_copy_recon fetches it on demand) and the
-     flush is asynchronous: the staging slots are double-buffered and the next
-     frame's pre-pass queues behind these kernels on the same stream. */
-  if (ocg_dec_submit(b->ctx, &f, NULL) < 0) enc_fatal("ocg_dec_submit failed");
-  b->self_on_device = f.ref_idx[OCG_FRAME_SELF];
+  /* One graph launch; nothing is waited for here.  An intra-only encoder never predicts from SELF, so
+     its reconstruction stays on the device (ocg_backend_enc_copy_recon fetches it on demand).  An
+     encoder that can emit inter frames gets the finished, padded frame back into its own buffer: the
+     next frame's analysis reads it there wherever the loop still runs a C kernel. */
+  if (ocg_dec_flush(b->ctx, &f, b->inter_capable ? st->ref_frame_handle + (size_t)self * (size_t)b->geom.ref_frame_sz : NULL,
+                    b->inter_capable ? OCG_OUT_PADDED : OCG_OUT_NONE) < 0) {
+    enc_fail(b, "ocg_dec_flush failed");
+    return;
+  }
+  b->pending = 1;
+  b->self_on_device = b->inter_capable ? -1 : self;
   pthread_mutex_lock(&g_estats_lock);
   g_estats.frames++;
   g_estats.coeff_rows += b->nrows;
   g_estats.h2d_bytes += (long)b->geom.nfrags * 16 + (long)b->nrows * 16;
+  if (b->inter_capable) g_estats.d2h_bytes += (long)b->geom.ref_frame_sz;
   g_estats.flush_seconds += enc_now_s() - t0;
   pthread_mutex_unlock(&g_estats_lock);
 }
@@ -197,54 +347,74 @@ static void ocge_enquant_table_fixup(void *_enquant[3][3][2], int _nqis) {
   oc_enc_ctx *enc = (oc_enc_ctx *)((char *)_enquant - offsetof(oc_enc_ctx, enquant));
   ocg_enc_backend *b = enc_backend_of(enc);
   oc_enc_enquant_table_fixup_c(_enquant, _nqis);
-  if (b == NULL) enc_fatal("enquant_table_fixup from an unknown encoder");
   t_enc = b;
-  enc_begin_frame(b, _nqis);
+  if (b != NULL) enc_begin_pass(b, _nqis);
 }
 
-static ocg_enc_backend *enc_cur(void) {
+/* the back-end of the pass in progress, if its tables / recorder are live */
+static inline ocg_enc_backend *enc_live(void) {
   ocg_enc_backend *b = t_enc;
-  if (b == NULL || !b->frame_open) enc_fatal("block hook outside an intra frame");
-  return b;
+  return b != NULL && b->frame_open && !b->failed ? b : NULL;
 }
 
 static unsigned ocge_frag_intra_satd(int *_dc, const unsigned char *_src, int _ystride) {
-  ocg_enc_backend *b = enc_cur();
-  ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
-  (void)_ystride;
-  *_dc = b->tab.satd_dc[fragi];
-  return b->tab.satd[fragi];
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL && b->tables) {
+    ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+    if (fragi >= 0) {
+      *_dc = b->tab.satd_dc[fragi];
+      return b->tab.satd[fragi];
+    }
+    enc_fail(b, "frag_intra_satd: not a fragment of the input frame");
+  }
+  return oc_enc_frag_intra_satd_c(_dc, _src, _ystride);
 }
 
 static void ocge_frag_sub_128(ogg_int16_t _diff[64], const unsigned char *_src, int _ystride) {
-  /* the residual itself stays on the device; its only consumer is fdct8x8 */
-  ocg_enc_backend *b = enc_cur();
-  (void)_diff; (void)_ystride;
-  b->cur_fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
-  b->idct_pending = 0;
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL) {
+    b->idct_pending = 0;
+    b->cur_fragi = -1;
+    if (b->tables) {
+      /* the residual itself stays on the device; its only consumer is fdct8x8 */
+      b->cur_fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+      if (b->cur_fragi >= 0) return;
+      enc_fail(b, "frag_sub_128: not a fragment of the input frame");
+    }
+  }
+  oc_enc_frag_sub_128_c(_diff, _src, _ystride);
+}
+
+static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, const unsigned char *_ref, int _ystride) {
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL) { b->idct_pending = 0; b->cur_fragi = -1; }
+  oc_enc_frag_sub_c(_diff, _src, _ref, _ystride);
 }
 
 static void ocge_fdct8x8(ogg_int16_t _y[64], const ogg_int16_t _x[64]) {
-  ocg_enc_backend *b = enc_cur();
-  (void)_x;
-  if (b->cur_fragi < 0) enc_fatal("fdct8x8 without a preceding frag_sub_128");
-  memcpy(_y, b->tab.dct + (size_t)b->cur_fragi * 64, 64 * sizeof(ogg_int16_t));
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL && b->tables && b->cur_fragi >= 0) {
+    memcpy(_y, b->tab.dct + (size_t)b->cur_fragi * 64, 64 * sizeof(ogg_int16_t));
+    return;
+  }
+  oc_enc_fdct8x8_c(_y, _x);
 }
 
 static int ocge_quantize(ogg_int16_t _qdct[64], const ogg_int16_t _dct[64], const ogg_uint16_t _dequant[64],
                          const void *_enquant) {
-  ocg_enc_backend *b = enc_cur();
-  oc_enc_ctx *enc = b->enc;
-  int pli, qii;
-  size_t at;
-  (void)_dct; (void)_dequant;
-  if (b->cur_fragi < 0) enc_fatal("quantize without a preceding frag_sub_128");
-  pli = b->st.recs[b->cur_fragi].pli_qti & 3;
-  for (qii = 0; qii < b->nqis && enc->enquant[pli][qii][0] != _enquant; qii++) {}
-  if (qii >= b->nqis) enc_fatal("quantize with a table that is not one of the frame's intra tables");
-  at = (size_t)qii * (size_t)b->geom.nfrags + (size_t)b->cur_fragi;
-  memcpy(_qdct, b->tab.qdct + at * 64, 64 * sizeof(ogg_int16_t));
-  return b->tab.nonzero[at];
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL && b->tables && b->cur_fragi >= 0) {
+    oc_enc_ctx *enc = b->enc;
+    int pli = b->st.recs[b->cur_fragi].pli_qti & 3, qii;
+    for (qii = 0; qii < b->nqis && enc->enquant[pli][qii][0] != _enquant; qii++) {}
+    if (qii < b->nqis) {
+      size_t at = (size_t)qii * (size_t)b->geom.nfrags + (size_t)b->cur_fragi;
+      memcpy(_qdct, b->tab.qdct + at * 64, 64 * sizeof(ogg_int16_t));
+      return b->tab.nonzero[at];
+    }
+    /* _dct came from the table, so the C quantiser below is still exact */
+  }
+  return oc_enc_quantize_c(_qdct, _dct, _dequant, _enquant);
 }
 
 static inline int enc_row_nonzero(const ogg_int16_t *row) {
@@ -254,22 +424,24 @@ static inline int enc_row_nonzero(const ogg_int16_t *row) {
   return (a | c) != 0;
 }
 
-/* oc_idct8x8 (state.h:98, called at analyze.c:806 with the dequantised
-   coefficients the tokeniser left in _x): take the rows the transform of this
-   footprint reads (idct.c:327-329) and leave _x zeroed (idct.c:245,276,295). */
+/* oc_idct8x8 (state.h:98, called at analyze.c:806 with the dequantised coefficients the tokeniser left
+   in _x): take the rows the transform of this footprint reads (idct.c:327-329) for the device, and
+   leave _x zeroed (idct.c:245,276,295).  In an inter frame the analysis loop goes on to measure the
+   reconstructed block (analyze.c:825-868), so the residual is also produced here, by the reference's C
+   transform. */
 static void ocge_idct8x8(ogg_int16_t _y[64], ogg_int16_t _x[64], int _last_zzi) {
-  ocg_enc_backend *b = enc_cur();
+  ocg_enc_backend *b = enc_live();
   int nr = _last_zzi <= 3 ? 2 : (_last_zzi <= 10 ? 4 : 8);
   int r, mask = 0;
-  (void)_y;
+  if (b == NULL) { oc_idct8x8_c(_y, _x, _last_zzi); return; }
   b->pend_dc = _x[0];
-  _x[0] = 0; /* DC travels in the record */
   b->pend_row0 = (ogg_uint32_t)b->nrows;
   for (r = 0; r < nr; r++) {
-    ogg_int16_t *row = _x + r * 8;
+    const ogg_int16_t *row = _x + r * 8;
     if (enc_row_nonzero(row)) {
-      memcpy(b->st.coeff_rows + (size_t)b->nrows * 8, row, 16);
-      memset(row, 0, 16);
+      ogg_int16_t *out = b->st.coeff_rows + (size_t)b->nrows * 8;
+      memcpy(out, row, 16);
+      if (r == 0) out[0] = 0; /* DC travels in the record */
       b->nrows++;
       mask |= 1 << r;
     }
@@ -278,16 +450,16 @@ static void ocge_idct8x8(ogg_int16_t _y[64], ogg_int16_t _x[64], int _last_zzi) 
   /* never the DC-only shortcut of state.c:967: analyze.c:806 always transforms */
   b->pend_last_zzi = _last_zzi < 2 ? 2 : _last_zzi;
   b->idct_pending = 1;
+  if (b->inter_frame) oc_idct8x8_c(_y, _x, _last_zzi);
+  else memset(_x, 0, (size_t)nr * 16);
 }
 
-static void ocge_frag_recon_intra(unsigned char *_dst, int _ystride, const ogg_int16_t _residue[64]) {
-  ocg_enc_backend *b = enc_cur();
-  ptrdiff_t fragi = enc_fragi_of(b, _dst, OC_FRAME_SELF);
+/* Shared by frag_recon_intra / frag_recon_inter: the fragment's record for the device. */
+static void enc_record(ocg_enc_backend *b, ptrdiff_t fragi, int refi, int mv, const ogg_int16_t _residue[64]) {
   ocg_frag_rec *rec = b->st.recs + fragi;
   int pli = rec->pli_qti & 3;
-  (void)_ystride;
-  rec->mv = 0;
-  rec->refi = OC_FRAME_SELF;
+  rec->mv = (ogg_int16_t)mv;
+  rec->refi = (unsigned char)refi;
   if (b->idct_pending) {
     rec->coeff_row = b->pend_row0;
     rec->dc = b->pend_dc;
@@ -307,51 +479,226 @@ static void ocge_frag_recon_intra(unsigned char *_dst, int _ystride, const ogg_i
   b->ncoded++;
 }
 
+static void ocge_frag_recon_intra(unsigned char *_dst, int _ystride, const ogg_int16_t _residue[64]) {
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL) {
+    ptrdiff_t fragi = enc_fragi_of(b, _dst, OC_FRAME_SELF);
+    if (fragi >= 0) enc_record(b, fragi, OC_FRAME_SELF, 0, _residue);
+    else enc_fail(b, "frag_recon_intra: not a fragment of the frame being reconstructed");
+    if (b->frame_open && !b->inter_frame) return; /* nobody reads an intra frame's pixels on the host */
+  }
+  oc_frag_recon_intra_c(_dst, _ystride, _residue);
+}
+
+static void ocge_frag_recon_inter(unsigned char *_dst, const unsigned char *_src, int _ystride,
+                                  const ogg_int16_t _residue[64]) {
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL) {
+    ptrdiff_t fragi = enc_fragi_of(b, _dst, OC_FRAME_SELF);
+    if (fragi >= 0) {
+      /* the predictor is a function of the reference frame and the vector (oc_state_get_mv_offsets,
+         state.c:846-957, restated on the device): analyze.c:710-746 */
+      const oc_fragment *frag = b->enc->state.frags + fragi;
+      int mode = frag->mb_mode;
+      int mv = mode == OC_MODE_INTER_NOMV || mode == OC_MODE_GOLDEN_NOMV ? 0 : b->enc->state.frag_mvs[fragi];
+      enc_record(b, fragi, frag->refi, mv, _residue);
+    } else enc_fail(b, "frag_recon_inter: not a fragment of the frame being reconstructed");
+  }
+  /* analyze.c:829-835 measures this block next */
+  oc_frag_recon_inter_c(_dst, _src, _ystride, _residue);
+}
+
+static void ocge_frag_copy_list(unsigned char *_dst_frame, const unsigned char *_src_frame, int _ystride,
+                                const ptrdiff_t *_fragis, ptrdiff_t _nfragis, const ptrdiff_t *_frag_buf_offs) {
+  /* analyze.c:610-622: the MCU's uncoded fragments; the device copies them PREV -> SELF at the flush */
+  ocg_enc_backend *b = enc_live();
+  ptrdiff_t i;
+  if (b == NULL) { oc_frag_copy_list_c(_dst_frame, _src_frame, _ystride, _fragis, _nfragis, _frag_buf_offs); return; }
+  for (i = 0; i < _nfragis; i++) b->st.recs[_fragis[i]].refi = OCG_FRAG_UNCODED;
+}
+
 static void ocge_state_loop_filter_frag_rows(const oc_theora_state *_state, signed char _bv[256], int _refi, int _pli,
                                              int _fragy0, int _fragy_end) {
   /* filtered on the device over the whole frame at flush */
-  (void)_state; (void)_bv; (void)_refi; (void)_pli; (void)_fragy0; (void)_fragy_end;
+  ocg_enc_backend *b = t_enc;
+  if (b != NULL && !b->failed) return;
+  oc_state_loop_filter_frag_rows_c(_state, _bv, _refi, _pli, _fragy0, _fragy_end);
 }
 
 static void ocge_restore_fpu(void) {
   ocg_enc_backend *b = t_enc;
-  if (b != NULL && b->frame_open) enc_flush(b);
+  if (b != NULL && b->frame_open && !b->failed) enc_flush(b);
 }
 
-/* hooks that only inter frames use: reaching one is a configuration error */
-static void ocge_no_sub(ogg_int16_t d[64], const unsigned char *s, const unsigned char *r, int y) {
-  (void)d; (void)s; (void)r; (void)y; enc_fatal("frag_sub: inter-frame hook in the intra-only device encoder");
-}
-static unsigned ocge_no_sad(const unsigned char *s, const unsigned char *r, int y) {
-  (void)s; (void)r; (void)y; enc_fatal("frag_sad/ssd: inter-frame hook in the intra-only device encoder"); return 0;
-}
-static unsigned ocge_no_sad_thresh(const unsigned char *s, const unsigned char *r, int y, unsigned t) {
-  (void)s; (void)r; (void)y; (void)t; enc_fatal("frag_sad_thresh: inter-frame hook in the intra-only device encoder"); return 0;
-}
-static unsigned ocge_no_sad2_thresh(const unsigned char *s, const unsigned char *r1, const unsigned char *r2, int y, unsigned t) {
-  (void)s; (void)r1; (void)r2; (void)y; (void)t; enc_fatal("frag_sad2_thresh: inter-frame hook in the intra-only device encoder"); return 0;
-}
-static unsigned ocge_no_satd(int *dc, const unsigned char *s, const unsigned char *r, int y) {
-  (void)dc; (void)s; (void)r; (void)y; enc_fatal("frag_satd: inter-frame hook in the intra-only device encoder"); return 0;
-}
-static unsigned ocge_no_satd2(int *dc, const unsigned char *s, const unsigned char *r1, const unsigned char *r2, int y) {
-  (void)dc; (void)s; (void)r1; (void)r2; (void)y; enc_fatal("frag_satd2: inter-frame hook in the intra-only device encoder"); return 0;
-}
-static unsigned ocge_no_border_ssd(const unsigned char *s, const unsigned char *r, int y, ogg_int64_t m) {
-  (void)s; (void)r; (void)y; (void)m; enc_fatal("frag_border_ssd: inter-frame hook in the intra-only device encoder"); return 0;
-}
-static void ocge_no_copy2(unsigned char *d, const unsigned char *a, const unsigned char *c, int y) {
-  (void)d; (void)a; (void)c; (void)y; enc_fatal("frag_copy2: inter-frame hook in the intra-only device encoder");
-}
-static void ocge_no_recon_inter(unsigned char *d, const unsigned char *s, int y, const ogg_int16_t r[64]) {
-  (void)d; (void)s; (void)y; (void)r; enc_fatal("frag_recon_inter: inter-frame hook in the intra-only device encoder");
-}
-static void ocge_no_copy_list(unsigned char *d, const unsigned char *s, int y, const ptrdiff_t *f, ptrdiff_t n,
-                              const ptrdiff_t *o) {
-  (void)d; (void)s; (void)y; (void)f; (void)o;
-  if (n > 0) enc_fatal("frag_copy_list: inter-frame hook in the intra-only device encoder");
+/* ---- motion analysis (mcenc.c:517-548, 666-672, 763-791) -------------------
+   Not vtable entries in the reference: analyze.c calls them by name, so the integrated build renames
+   the reference's definitions (theora_b200/backend/Makefile) and these take their place.  They hand out
+   the device's results of enc_me_prepass; an encoder without them (tooling mode, speed levels the
+   device analysis does not cover) runs the reference's own functions. */
+static inline int ocge_div2(int v) { return v / 2; } /* OC_DIV2: towards zero */
+static inline int ocge_clamp31(int v) { return v < -31 ? -31 : (v > 31 ? 31 : v); }
+static inline int ocge_mv_x(int mv) { return (signed char)mv; }
+static inline int ocge_mv_y(int mv) { return (ogg_int16_t)mv >> 8; }
+static inline int ocge_mv(int x, int y) { return (ogg_int16_t)((x & 0xFF) | y * 256); }
+static inline int ocge_mv_sub(int a, int c) { return ocge_mv(ocge_mv_x(a) - ocge_mv_x(c), ocge_mv_y(a) - ocge_mv_y(c)); }
+static inline int ocge_med3(int a, int c, int d) {
+  int lo = a < c ? a : c, hi = a < c ? c : a;
+  return d < lo ? lo : (d > hi ? hi : d);
 }
 
+/* The candidate set of a GOLD search (mcenc.c:90-164) and its threshold base (331-337), given the
+   neighbours' vectors/errors: half-pel entries as ocg_mb_search_in wants them, [0] = median of [1..3]. */
+static void ocge_gold_cands(ocg_mb_search_in *in, int ncn, const int nb_mv[4], const unsigned nb_err[4], int accum,
+                            int m1, int m2, unsigned own_err) {
+  int n = 1, i;
+  unsigned t2 = own_err;
+  for (i = 0; i < ncn; i++, n++) {
+    in->cand[n][0] = (signed char)ocge_mv_x(nb_mv[i]);
+    in->cand[n][1] = (signed char)ocge_mv_y(nb_mv[i]);
+  }
+  in->cand[n][0] = (signed char)ocge_mv_x(accum);
+  in->cand[n][1] = (signed char)ocge_mv_y(accum);
+  n++;
+  in->cand[n][0] = (signed char)ocge_clamp31(ocge_mv_x(m1) + ocge_mv_x(accum));
+  in->cand[n][1] = (signed char)ocge_clamp31(ocge_mv_y(m1) + ocge_mv_y(accum));
+  n++;
+  in->cand[n][0] = in->cand[n][1] = 0;
+  n++;
+  in->cand[0][0] = (signed char)ocge_med3(in->cand[1][0], in->cand[2][0], in->cand[3][0]);
+  in->cand[0][1] = (signed char)ocge_med3(in->cand[1][1], in->cand[2][1], in->cand[3][1]);
+  in->setb0 = (unsigned char)n;
+  in->cand[n][0] = (signed char)ocge_clamp31(2 * ocge_mv_x(m1) - ocge_mv_x(m2) + ocge_mv_x(accum));
+  in->cand[n][1] = (signed char)ocge_clamp31(2 * ocge_mv_y(m1) - ocge_mv_y(m2) + ocge_mv_y(accum));
+  n++;
+  in->ncand = (unsigned char)n;
+  for (i = 0; i < (ncn < 3 ? ncn : 3); i++) if (nb_err[i] > t2) t2 = nb_err[i];
+  in->t2_base = (ogg_uint16_t)t2;
+  in->is_prev = 0;
+}
+
+static ocg_enc_backend *enc_me_live(oc_enc_ctx *_enc) {
+  ocg_enc_backend *b = t_enc;
+  if (b == NULL || b->enc != _enc) b = enc_backend_of(_enc);
+  return b != NULL && b->me_valid && !b->failed ? b : NULL;
+}
+
+void oc_mcenc_search(oc_enc_ctx *_enc, int _mbi) {
+  ocg_enc_backend *b = enc_me_live(_enc);
+  oc_mb_enc_info *e;
+  const ocg_me_mb *m;
+  int k, ncn, stale = 0;
+  int gold_mv, gold_satd;
+  unsigned gold_err;
+  if (b == NULL) { oc_refimpl_mcenc_search(_enc, _mbi); return; }
+  e = _enc->mb_info + _mbi;
+  m = b->me_tab + _mbi;
+  ncn = e->ncneighbors;
+  gold_mv = m->unref_mv[OC_FRAME_GOLD];
+  gold_err = m->error[OC_FRAME_GOLD];
+  gold_satd = (int)m->unref_satd[OC_FRAME_GOLD];
+  for (k = 0; k < ncn; k++) stale |= b->gold_dirty[e->cneighbors[k]];
+  if (stale) {
+    /* did the speculation feed this search what the reference would? compare what the search consumes:
+       the full-pel candidate list and the threshold base */
+    ocg_mb_search_in spec, real;
+    int nb_spec[4], nb_real[4], same;
+    unsigned err_spec[4], err_real[4];
+    /* this macro block's own history as oc_mcenc_search rotates it before the GOLD search (mcenc.c:526-541) */
+    const int old0 = e->analysis_mv[0][OC_FRAME_GOLD], old1 = e->analysis_mv[1][OC_FRAME_GOLD];
+    const int accum = e->analysis_mv[2][OC_FRAME_GOLD];
+    const int m2 = ocge_mv_sub(old1, accum), m1 = ocge_mv_sub(old0, old1);
+    for (k = 0; k < ncn; k++) {
+      const unsigned n = e->cneighbors[k];
+      nb_spec[k] = b->me_tab[n].analysis_mv[0][OC_FRAME_GOLD];
+      err_spec[k] = b->me_tab[n].error[OC_FRAME_GOLD];
+      nb_real[k] = _enc->mb_info[n].analysis_mv[0][OC_FRAME_GOLD];
+      err_real[k] = _enc->mb_info[n].error[OC_FRAME_GOLD];
+    }
+    memset(&spec, 0, sizeof(spec));
+    memset(&real, 0, sizeof(real));
+    ocge_gold_cands(&spec, ncn, nb_spec, err_spec, accum, m1, m2, e->error[OC_FRAME_GOLD]);
+    ocge_gold_cands(&real, ncn, nb_real, err_real, accum, m1, m2, e->error[OC_FRAME_GOLD]);
+    same = spec.t2_base == real.t2_base;
+    for (k = 0; k < spec.ncand && same; k++)
+      same = ocge_div2(spec.cand[k][0]) == ocge_div2(real.cand[k][0]) && ocge_div2(spec.cand[k][1]) == ocge_div2(real.cand[k][1]);
+    if (!same) {
+      ocg_mb_search_out so;
+      ocg_mb_refine_out ro;
+      for (k = 0; k < 4; k++) real.frag_off[k] = (ogg_int32_t)_enc->state.frag_buf_offs[_enc->state.mb_maps[_mbi][0][k]];
+      if (ocg_me_repair(b->me, OC_FRAME_GOLD, &real, 1, &so, &ro) < 0) {
+        enc_fail(b, "ocg_me_repair failed");
+        oc_refimpl_mcenc_search(_enc, _mbi);
+        return;
+      }
+      gold_mv = ocge_mv(so.best_vec[0] * 2, so.best_vec[1] * 2);
+      gold_err = so.error;
+      gold_satd = (int)so.satd;
+      b->gold_fixed[_mbi] = 1;
+      b->gold_fix[_mbi].mv = (ogg_int16_t)ocge_mv(ro.mv[0], ro.mv[1]);
+      b->gold_fix[_mbi].satd = ro.satd;
+      /* later macro blocks were fed the speculative values of this one */
+      if (gold_mv != m->analysis_mv[0][OC_FRAME_GOLD] || gold_err != m->error[OC_FRAME_GOLD]) b->gold_dirty[_mbi] = 1;
+      pthread_mutex_lock(&g_estats_lock);
+      g_estats.me_repairs++;
+      pthread_mutex_unlock(&g_estats_lock);
+    }
+  }
+  /* history as the reference leaves it (mcenc.c:534, 546-547): a function of this macro block alone */
+  for (k = 0; k < 2; k++) {
+    e->analysis_mv[1][k] = m->analysis_mv[1][k];
+    e->analysis_mv[2][k] = m->analysis_mv[2][k];
+  }
+  e->analysis_mv[0][OC_FRAME_PREV] = m->unref_mv[OC_FRAME_PREV];
+  e->error[OC_FRAME_PREV] = m->error[OC_FRAME_PREV];
+  e->satd[OC_FRAME_PREV] = m->unref_satd[OC_FRAME_PREV];
+  if (!(b->me_flags & OCG_ME_FAST)) {
+    for (k = 0; k < 4; k++) { e->block_mv[k] = m->block_mv[k]; e->block_satd[k] = m->block_satd[k]; }
+  }
+  e->analysis_mv[0][OC_FRAME_GOLD] = (oc_mv)gold_mv;
+  e->error[OC_FRAME_GOLD] = (ogg_uint16_t)gold_err;
+  e->satd[OC_FRAME_GOLD] = (unsigned)gold_satd;
+}
+
+void oc_mcenc_refine1mv(oc_enc_ctx *_enc, int _mbi, int _frame) {
+  ocg_enc_backend *b = enc_me_live(_enc);
+  oc_mb_enc_info *e;
+  const ocg_me_mb *m;
+  if (b == NULL || !(b->me_flags & OCG_ME_REFINE_PREV)) { oc_refimpl_mcenc_refine1mv(_enc, _mbi, _frame); return; }
+  e = _enc->mb_info + _mbi;
+  m = b->me_tab + _mbi;
+  if (_frame == OC_FRAME_PREV) {
+    e->analysis_mv[0][OC_FRAME_PREV] = m->analysis_mv[0][OC_FRAME_PREV];
+    e->satd[OC_FRAME_PREV] = m->satd[OC_FRAME_PREV];
+  } else {
+    const int before = e->analysis_mv[0][OC_FRAME_GOLD];
+    if (b->gold_fixed[_mbi]) {
+      e->analysis_mv[0][OC_FRAME_GOLD] = b->gold_fix[_mbi].mv;
+      e->satd[OC_FRAME_GOLD] = b->gold_fix[_mbi].satd;
+    } else {
+      e->analysis_mv[0][OC_FRAME_GOLD] = m->gold_ref_mv;
+      e->satd[OC_FRAME_GOLD] = m->gold_ref_satd;
+    }
+    /* the device's chain handed the unrefined vector to this macro block's later neighbours */
+    if (e->analysis_mv[0][OC_FRAME_GOLD] != before) b->gold_dirty[_mbi] = 1;
+    pthread_mutex_lock(&g_estats_lock);
+    g_estats.me_gold_refines++;
+    pthread_mutex_unlock(&g_estats_lock);
+  }
+}
+
+void oc_mcenc_refine4mv(oc_enc_ctx *_enc, int _mbi) {
+  ocg_enc_backend *b = enc_me_live(_enc);
+  oc_mb_enc_info *e;
+  const ocg_me_mb *m;
+  int k;
+  if (b == NULL || !(b->me_flags & OCG_ME_REFINE_4MV)) { oc_refimpl_mcenc_refine4mv(_enc, _mbi); return; }
+  e = _enc->mb_info + _mbi;
+  m = b->me_tab + _mbi;
+  for (k = 0; k < 4; k++) {
+    e->ref_mv[k] = m->ref_mv[k];
+    e->block_satd[k] = m->ref_block_satd[k];
+  }
+}
 
 /* ---- test instrumentation: analysis-pass snapshots of a host encoder ------- */
 static void ocge_spy_fixup(void *_enquant[3][3][2], int _nqis) {
@@ -412,20 +759,18 @@ static void enc_backend_destroy(ocg_enc_backend *b) {
   if (t_enc == b) t_enc = NULL;
   if (b->ctx != NULL) {
     ocg_ctx_sync(b->ctx);
+    if (b->me != NULL) ocg_me_destroy(b->me);
+    if (b->me_tab != NULL) ocg_host_unregister(b->me_tab);
     if (b->pinned) ocg_host_unregister(b->enc->state.ref_frame_handle);
     ocg_ctx_destroy(b->ctx);
   }
+  free(b->me_tab);
+  free(b->gold_dirty);
+  free(b->gold_fixed);
+  free(b->gold_fix);
   free(b->off2frag);
   free(b);
 }
-
-#if defined(OC_X86_ASM)
-void oc_refimpl_state_accel_init_x86(oc_theora_state *_state); /* lib/x86/x86state.c, renamed */
-void oc_refimpl_enc_accel_init_x86(oc_enc_ctx *_enc);          /* lib/x86/x86enc.c, renamed */
-void oc_enc_accel_init_ocg(oc_enc_ctx *_enc);
-/* x86enc.h names oc_enc_accel_init_x86 as the encoder's init function (see ocg_backend.c) */
-void oc_enc_accel_init_x86(oc_enc_ctx *_enc) { oc_enc_accel_init_ocg(_enc); }
-#endif
 
 void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   oc_theora_state *st = &_enc->state;
@@ -433,19 +778,9 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   ptrdiff_t fragi, omin, omax;
   oc_enc_accel_init_c(_enc);
   t_enc_init_failed = 0;
-  /* only an encoder that cannot emit inter frames takes the device path */
-  if (g_enc_mode == OCG_ENC_HOST || st->info.keyframe_granule_shift != 0) {
-#if defined(OC_X86_ASM)
-    /* everything stays on the host: with the reference's SIMD kernels, exactly as its own x86 build
-       would set this context up (x86state.c:66-95, x86enc.c:21-62; oc_enc_init sizes the quantiser
-       tables after this call, encode.c:1160-1190) */
-    if (g_enc_mode != OCG_ENC_HOST) {
-      oc_refimpl_state_accel_init_x86(st);
-      oc_refimpl_enc_accel_init_x86(_enc);
-    }
-#endif
-    /* the spy wraps the C fix-up: host (C kernel) mode only */
-    if (g_enc_spy != NULL && g_enc_mode == OCG_ENC_HOST) _enc->opt_vtable.enquant_table_fixup = ocge_spy_fixup;
+  if (g_enc_mode == OCG_ENC_HOST) {
+    /* tooling mode: the reference's C kernels for everything; the spy wraps the C fix-up */
+    if (g_enc_spy != NULL) _enc->opt_vtable.enquant_table_fixup = ocge_spy_fixup;
     return;
   }
   t_enc_init_failed = 1;
@@ -453,6 +788,7 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   if (b == NULL) return;
   b->enc = _enc;
   b->self_on_device = -1;
+  b->inter_capable = st->info.keyframe_granule_shift != 0;
   if (ocg_geometry_init(&b->geom, (int)st->info.frame_width, (int)st->info.frame_height, (int)st->info.pixel_fmt, 6) < 0) {
     fprintf(stderr, "theora_b200 encoder back-end: %s\n", ocg_last_error());
     free(b);
@@ -492,32 +828,31 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
     fprintf(stderr, "theora_b200 encoder back-end: %s\n", ocg_last_error());
     free(b->off2frag);
     free(b);
-    return; /* th_encode_alloc (below) reports the failure; no CPU fallback for an intra-only encoder */
+    return; /* th_encode_alloc (below) reports the failure: there is no CPU fallback encoder */
   }
   b->pinned = ocg_host_register(st->ref_frame_handle, (size_t)b->geom.ref_frame_sz * 6) == 0;
-  /* pre-pass look-ups */
+  if (b->inter_capable && !b->pinned) {
+    /* the flush graph copies the finished frame straight into the encoder's own buffer */
+    fprintf(stderr, "theora_b200 encoder back-end: cannot page-lock the frame buffers (%s)\n", ocg_last_error());
+    ocg_ctx_destroy(b->ctx);
+    free(b->off2frag);
+    free(b);
+    return;
+  }
+  /* pre-pass look-ups (intra frames) */
   _enc->opt_vtable.enquant_table_fixup = ocge_enquant_table_fixup;
   _enc->opt_vtable.frag_intra_satd = ocge_frag_intra_satd;
   _enc->opt_vtable.frag_sub_128 = ocge_frag_sub_128;
+  _enc->opt_vtable.frag_sub = ocge_frag_sub;
   _enc->opt_vtable.fdct8x8 = ocge_fdct8x8;
   _enc->opt_vtable.quantize = ocge_quantize;
-  /* recorded reconstruction */
+  /* recorded reconstruction (every frame) */
   _enc->opt_vtable.frag_recon_intra = ocge_frag_recon_intra;
+  _enc->opt_vtable.frag_recon_inter = ocge_frag_recon_inter;
   st->opt_vtable.idct8x8 = ocge_idct8x8;
+  st->opt_vtable.frag_copy_list = ocge_frag_copy_list;
   st->opt_vtable.state_loop_filter_frag_rows = ocge_state_loop_filter_frag_rows;
   st->opt_vtable.restore_fpu = ocge_restore_fpu;
-  /* inter-only hooks */
-  _enc->opt_vtable.frag_sub = ocge_no_sub;
-  _enc->opt_vtable.frag_sad = ocge_no_sad;
-  _enc->opt_vtable.frag_sad_thresh = ocge_no_sad_thresh;
-  _enc->opt_vtable.frag_sad2_thresh = ocge_no_sad2_thresh;
-  _enc->opt_vtable.frag_satd = ocge_no_satd;
-  _enc->opt_vtable.frag_satd2 = ocge_no_satd2;
-  _enc->opt_vtable.frag_ssd = ocge_no_sad;
-  _enc->opt_vtable.frag_border_ssd = ocge_no_border_ssd;
-  _enc->opt_vtable.frag_copy2 = ocge_no_copy2;
-  _enc->opt_vtable.frag_recon_inter = ocge_no_recon_inter;
-  st->opt_vtable.frag_copy_list = ocge_no_copy_list;
   pthread_mutex_lock(&g_elock);
   b->next = g_elist;
   g_elist = b;
@@ -536,7 +871,7 @@ th_enc_ctx *th_encode_alloc(const th_info *_info) {
   if (enc == NULL && t_enc_created != NULL) enc_backend_destroy(t_enc_created); /* oc_enc_init failed later */
   t_enc_created = NULL;
   if (enc != NULL && t_enc_init_failed) {
-    /* an intra-only encoder without a usable device: fail the allocation */
+    /* no usable device: fail the allocation rather than encode on the CPU */
     oc_refimpl_encode_free(enc);
     return NULL;
   }
@@ -546,6 +881,15 @@ th_enc_ctx *th_encode_alloc(const th_info *_info) {
 void th_encode_free(th_enc_ctx *_enc) {
   if (_enc != NULL) enc_backend_destroy(enc_backend_of(_enc));
   oc_refimpl_encode_free(_enc);
+}
+
+int th_encode_ycbcr_in(th_enc_ctx *_enc, th_ycbcr_buffer _img) {
+  ocg_enc_backend *b = _enc != NULL ? enc_backend_of(_enc) : NULL;
+  int ret;
+  if (b != NULL && b->failed) return TH_EFAULT;
+  ret = oc_refimpl_encode_ycbcr_in(_enc, _img);
+  if (b != NULL && b->failed) return TH_EFAULT;
+  return ret;
 }
 
 /* Test accessor: the encoder's current reconstruction (OC_FRAME_SELF of the
@@ -561,6 +905,8 @@ OCG_API long ocg_backend_enc_copy_recon(th_enc_ctx *_enc, unsigned char *_dst) {
   if (idx < 0) return TH_EINVAL;
   {
     ocg_enc_backend *b = enc_backend_of(_enc);
+    if (b != NULL) enc_wait(b);
+    if (b != NULL && b->failed) return TH_EFAULT;
     if (b != NULL && b->self_on_device == idx) {
       if (ocg_ctx_download_frame(b->ctx, idx, (unsigned char *)st->ref_frame_handle + (size_t)idx * (size_t)b->geom.ref_frame_sz) < 0 ||
           ocg_ctx_sync(b->ctx) < 0)

@@ -7,6 +7,9 @@
 #include <mutex>
 #include <new>
 #include <vector>
+#include <stdint.h>
+#include <sched.h>
+#include <time.h>
 #include "ocg_internal.h"
 
 namespace {
@@ -37,6 +40,16 @@ struct Slot {
   OcgJobDev *job = nullptr;     /* pinned */
   cudaEvent_t consumed = nullptr;
   bool busy = false;
+  uint32_t flush_seq = 0;       /* ocg_dec_flush: the slot is free once the context's done flag reaches this */
+  bool flush_busy = false;
+};
+
+/* One instantiated CUDA graph of a whole frame flush (ocg_dec_flush). */
+struct FlushGraph {
+  int slot, self, out_mode, dc, lf;
+  uint8_t *host_out;
+  cudaGraphExec_t exec;
+  int kernels;
 };
 
 } /* namespace */
@@ -75,6 +88,12 @@ struct ocg_ctx {
   cudaEvent_t done = nullptr; /* cudaEventBlockingSync: ocg_ctx_sync can sleep instead of spinning */
   int cur_slot = 0;      /* slot handed out by the last ocg_dec_staging */
   bool staged = false;
+  /* ocg_dec_flush / ocg_dec_wait */
+  std::vector<FlushGraph> graphs;
+  volatile uint32_t *h_done = nullptr; /* pinned + mapped: sequence number of the last finished flush */
+  uint32_t *d_done = nullptr;          /* the device's address of the same word */
+  uint32_t *d_out_counter = nullptr;   /* copy-out kernel: CTAs finished */
+  uint32_t flush_seq = 0;
 };
 
 struct ocg_pack {
@@ -359,6 +378,9 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
     delete c->enc;
   }
   if (c->done) cudaEventDestroy(c->done);
+  for (FlushGraph &fg : c->graphs) cudaGraphExecDestroy(fg.exec);
+  if (c->h_done) cudaFreeHost((void *)c->h_done);
+  cudaFree(c->d_out_counter);
   cudaFree(c->frames);
   cudaFree(c->d_recs);
   cudaFree(c->d_rows);
@@ -415,10 +437,16 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   CUX(cudaMalloc(&c->d_xlist, (nf + 2) * sizeof(int32_t)));
   CUX(cudaMemsetAsync(c->d_xlist, 0, (nf + 2) * sizeof(int32_t), c->stream));
   CUX(cudaMalloc(&c->d_job, sizeof(OcgJobDev)));
+  CUX(cudaHostAlloc((void **)&c->h_done, 64, cudaHostAllocMapped));
+  *c->h_done = 0;
+  CUX(cudaHostGetDevicePointer((void **)&c->d_done, (void *)c->h_done, 0));
+  CUX(cudaMalloc(&c->d_out_counter, sizeof(uint32_t)));
+  CUX(cudaMemsetAsync(c->d_out_counter, 0, sizeof(uint32_t), c->stream));
   for (Slot &s : c->slots) {
-    CUX(cudaHostAlloc(&s.recs, nf * sizeof(ocg_frag_rec), cudaHostAllocDefault));
-    CUX(cudaHostAlloc(&s.rows, nf * 8 * 16, cudaHostAllocDefault));
-    CUX(cudaHostAlloc(&s.job, sizeof(OcgJobDev), cudaHostAllocDefault));
+    /* mapped: ocg_dec_flush's stage-in kernel reads them in place */
+    CUX(cudaHostAlloc(&s.recs, nf * sizeof(ocg_frag_rec), cudaHostAllocMapped));
+    CUX(cudaHostAlloc(&s.rows, nf * 8 * 16, cudaHostAllocMapped));
+    CUX(cudaHostAlloc(&s.job, sizeof(OcgJobDev), cudaHostAllocMapped));
     CUX(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
   }
   /* record template: every fragment uncoded, offsets and planes filled in */
@@ -447,6 +475,7 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
 
 OCG_API const ocg_geometry *ocg_ctx_geometry(const ocg_ctx *c) { return c ? &c->geom : nullptr; }
 OCG_API void *ocg_ctx_stream(ocg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+OCG_API int ocg_ctx_device(const ocg_ctx *c) { return c ? c->device : -1; }
 
 OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *c, int buf) {
   if (c == nullptr || buf < 0 || buf >= c->geom.nrefs) return nullptr;
@@ -486,6 +515,33 @@ OCG_API int ocg_ctx_download_frame(ocg_ctx *c, int buf, uint8_t *host) {
   return OCG_OK;
 }
 
+/* The coded-frame area only (frame_width x frame_height of every plane; what th_decode_ycbcr_out exposes):
+   three strided copies into the same positions of a host buffer that has the reference's layout.  The
+   aprons are device-only state (motion compensation reads them there), so they need not cross PCIe:
+   3 133 440 instead of 3 279 360 bytes per 1080p frame. */
+OCG_API int ocg_ctx_download_picture(ocg_ctx *c, int buf, uint8_t *host) {
+  if (c == nullptr || host == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
+  CU(cudaSetDevice(c->device));
+  const uint8_t *dev = c->frames + (size_t)buf * c->geom.ref_frame_sz;
+  for (int pli = 0; pli < 3; pli++) {
+    const ocg_plane_geom &p = c->geom.planes[pli];
+    const size_t pitch = (size_t)(-(int64_t)p.ystride);
+    /* top-left pixel of the plane = lowest address (rows are addressed bottom-up) */
+    const int64_t top = c->geom.base_off + p.plane_off + (int64_t)(p.height - 1) * p.ystride;
+    CU(cudaMemcpy2DAsync(host + top, pitch, dev + top, pitch, (size_t)p.width, (size_t)p.height, cudaMemcpyDeviceToHost,
+                         c->stream));
+  }
+  return OCG_OK;
+}
+
+OCG_API long ocg_picture_bytes(const ocg_geometry *g) {
+  long n = 0;
+  if (g == nullptr) return 0;
+  for (int pli = 0; pli < 3; pli++) n += (long)g->planes[pli].width * g->planes[pli].height;
+  return n;
+}
+
 OCG_API int ocg_ctx_fill_frame(ocg_ctx *c, int buf, int value) {
   if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
   if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
@@ -496,7 +552,7 @@ OCG_API int ocg_ctx_fill_frame(ocg_ctx *c, int buf, int value) {
 
 OCG_API int ocg_host_register(void *p, size_t bytes) {
   if (p == nullptr) return fail(OCG_EFAULT, "NULL argument");
-  CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   return OCG_OK;
 }
 
@@ -507,6 +563,34 @@ OCG_API int ocg_host_unregister(void *p) {
 }
 
 /* ---- single-frame decode ------------------------------------------------ */
+/* Waits until the context's done flag (written by the last node of a flush graph into mapped host
+   memory) has reached `seq`: no driver call on the way, so stream threads do not meet in the driver's
+   locks.  Wait policy as for ocg_ctx_sync: spin, or -- ocg_set_blocking_sync(1) -- give the core away
+   between looks so that a host running more stream threads than cores keeps them busy. */
+static int wait_done(ocg_ctx *c, uint32_t seq) {
+  const bool yield = g_blocking_sync.load() != 0;
+  struct timespec t0;
+  long spins = 0;
+  bool timed = false;
+  while ((int32_t)(*c->h_done - seq) < 0) {
+    if (yield) sched_yield();
+    else __builtin_ia32_pause();
+    if ((++spins & 0xFFF) == 0) {
+      /* a faulted kernel never writes the flag: look at the stream now and then */
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if (!timed) { t0 = t1; timed = true; }
+      else if (t1.tv_sec - t0.tv_sec >= 1) {
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return fail(OCG_ECUDA, "flush failed on the device", e);
+        if (e == cudaSuccess && (int32_t)(*c->h_done - seq) < 0) return fail(OCG_ECUDA, "flush finished without its completion flag");
+        t0 = t1;
+      }
+    }
+  }
+  return OCG_OK;
+}
+
 static int acquire_slot(ocg_ctx *c) {
   const int si = (c->cur_slot + 1) % kSlots;
   Slot &s = c->slots[si];
@@ -514,6 +598,11 @@ static int acquire_slot(ocg_ctx *c) {
     cudaError_t e = cudaEventSynchronize(s.consumed);
     if (e != cudaSuccess) return fail(OCG_ECUDA, "cudaEventSynchronize", e);
     s.busy = false;
+  }
+  if (s.flush_busy) {
+    int r = wait_done(c, s.flush_seq);
+    if (r < 0) return r;
+    s.flush_busy = false;
   }
   c->cur_slot = si;
   return OCG_OK;
@@ -567,6 +656,98 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
     CU(cudaMemcpyAsync(host_out, c->frames + (size_t)f->ref_idx[OCG_FRAME_SELF] * c->geom.ref_frame_sz,
                        (size_t)c->geom.ref_frame_sz, cudaMemcpyDeviceToHost, st));
   }
+  return OCG_OK;
+}
+
+/* One frame = one driver call.  The whole flush -- records and job header H2D, [DC un-prediction],
+   recon pass A/B, loop filter, borders, copy-back of the picture (or the padded buffer) into host_out,
+   completion flag -- is a CUDA graph, instantiated once per (staging slot, SELF buffer, destination,
+   variant) and replayed; the coefficient rows are read in place from the mapped staging memory.  With
+   one stream thread per decoder the eleven driver calls of ocg_dec_submit + copy-back + sync serialise
+   on the driver's locks (measured: 0.25 ms of host time per frame at 16 threads); a graph launch plus a
+   flag in host memory needs one. */
+OCG_API int ocg_dec_flush(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out, int out_mode) {
+  if (c == nullptr || f == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  int r = check_frame(c->geom, *f);
+  if (r < 0) return r;
+  if (f->dc_residual == 2) return fail(OCG_EINVAL, "ocg_dec_flush takes dc_residual 0 or 1");
+  if (out_mode != OCG_OUT_NONE && host_out == nullptr) return fail(OCG_EFAULT, "NULL output buffer");
+  CU(cudaSetDevice(c->device));
+  const bool from_staging = c->staged && f->recs == nullptr && f->coeff_rows == nullptr;
+  if (!from_staging) {
+    if (!f->recs || (f->ncoeff_rows && !f->coeff_rows)) return fail(OCG_EFAULT, "NULL list pointer (and no staged lists)");
+    r = acquire_slot(c);
+    if (r < 0) return r;
+  }
+  const int si = c->cur_slot;
+  Slot &s = c->slots[si];
+  c->staged = false;
+  cudaStream_t st = c->stream;
+  const size_t nf = (size_t)c->geom.nfrags;
+  if (!from_staging) {
+    memcpy(s.recs, f->recs, nf * sizeof(ocg_frag_rec));
+    if (f->ncoeff_rows) memcpy(s.rows, f->coeff_rows, (size_t)f->ncoeff_rows * 16);
+  }
+  int16_t *d_rows_mapped = nullptr;
+  ocg_frag_rec *d_recs_mapped = nullptr;
+  OcgJobDev *d_job_mapped = nullptr;
+  uint8_t *d_out_mapped = nullptr;
+  CU(cudaHostGetDevicePointer((void **)&d_rows_mapped, s.rows, 0));
+  CU(cudaHostGetDevicePointer((void **)&d_recs_mapped, s.recs, 0));
+  CU(cudaHostGetDevicePointer((void **)&d_job_mapped, s.job, 0));
+  if (out_mode != OCG_OUT_NONE) {
+    if (((uintptr_t)host_out & 15) != 0) return fail(OCG_EINVAL, "output buffer must be 16-byte aligned");
+    if (cudaHostGetDevicePointer((void **)&d_out_mapped, host_out, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(OCG_EINVAL, "output buffer is not page-locked (ocg_host_register)");
+    }
+  }
+  fill_job(*s.job, c, *f, c->d_recs, c->d_rows);
+  s.job->ncoeff_rows = f->ncoeff_rows;
+  const int self = f->ref_idx[OCG_FRAME_SELF], dc = f->dc_residual == 1, lf = f->lf_limit != 0;
+  const bool tma = c->d_tmaps != nullptr && g_use_tma.load();
+  FlushGraph *fg = nullptr;
+  for (FlushGraph &g : c->graphs)
+    if (g.slot == si && g.self == self && g.out_mode == out_mode && g.dc == dc && g.lf == lf && g.host_out == host_out) fg = &g;
+  if (fg == nullptr) {
+    /* the capture must not see other threads' work, and nothing else may be queued on this stream meanwhile */
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    ocg_launch_stage_in(d_job_mapped, c->d_job, d_recs_mapped, c->d_recs, c->geom.nfrags, d_rows_mapped, c->d_rows, st);
+    if (dc) ocg_launch_dc_unpredict(c->gdev, c->d_job, 1, st);
+    ocg_launch_recon(c->gdev, c->d_job, 1, st);
+    if (lf) ocg_launch_loop_filter(c->gdev, c->d_job, 1, tma, st);
+    ocg_launch_borders(c->gdev, c->d_job, 1, st);
+    ocg_launch_copy_out(c->geom, out_mode, c->frames + (size_t)self * c->geom.ref_frame_sz, d_out_mapped, c->d_job,
+                        c->d_out_counter, c->d_done, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (e != cudaSuccess || graph == nullptr) { cudaGetLastError(); return fail(OCG_ECUDA, "flush graph capture failed", e); }
+    size_t nnodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nnodes); /* all of them kernels */
+    const int kernels = (int)nnodes;
+    g_launches.fetch_sub(kernels); /* the capture counted them once; they are counted per replay below */
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(OCG_ECUDA, "cudaGraphInstantiate", e);
+    c->graphs.push_back(FlushGraph{si, self, out_mode, dc, lf, host_out, exec, kernels});
+    fg = &c->graphs.back();
+  }
+  /* the stage-in kernel reads the staging memory when it runs: everything it reads is final now */
+  c->flush_seq++;
+  s.job->seq = c->flush_seq;
+  s.flush_seq = c->flush_seq;
+  s.flush_busy = true;
+  CU(cudaGraphLaunch(fg->exec, st));
+  g_launches.fetch_add(fg->kernels, std::memory_order_relaxed);
+  return OCG_OK;
+}
+
+OCG_API int ocg_dec_wait(ocg_ctx *c) {
+  if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
+  int r = wait_done(c, c->flush_seq);
+  if (r < 0) return r;
+  for (Slot &s : c->slots) s.flush_busy = false;
   return OCG_OK;
 }
 

@@ -1046,6 +1046,133 @@ void ocg_launch_codedmap(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, 
   ocg_count_launch(1);
 }
 
+/* ---- flush graph: stage-in and copy-out without the copy engines -----------
+   A graph made of kernels only is one cheap submission; every memcpy node in it is a separate one, and
+   with a stream thread per decoder the driver's submission rate (not the GPU, not PCIe) was what capped
+   the end-to-end frame rate.  So the lists come in and the picture goes out through mapped host memory. */
+__device__ __forceinline__ uint4 ld_host16(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+/* records (nfrags x 16 B), the frame's coefficient rows and the job header: mapped host memory -> device */
+__global__ void __launch_bounds__(256)
+ocg_stage_in_kernel(const OcgJobDev *__restrict__ h_job, OcgJobDev *__restrict__ d_job, const uint4 *__restrict__ h_recs,
+                    uint4 *__restrict__ d_recs, int nfrags, const uint4 *__restrict__ h_rows, uint4 *__restrict__ d_rows) {
+  const int nrows = h_job->ncoeff_rows;
+  const int total = nfrags + nrows;
+  const int stride = (int)(gridDim.x * blockDim.x);
+  int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  /* four independent 16-byte reads in flight per thread: PCIe latency is ~1-2 us */
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int j = i + k * stride;
+      v[k] = j < nfrags ? ld_host16(h_recs + j) : ld_host16(h_rows + (j - nfrags));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int j = i + k * stride;
+      if (j < nfrags) d_recs[j] = v[k];
+      else d_rows[j - nfrags] = v[k];
+    }
+  }
+  for (; i < total; i += stride) {
+    if (i < nfrags) d_recs[i] = ld_host16(h_recs + i);
+    else d_rows[i - nfrags] = ld_host16(h_rows + (i - nfrags));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < sizeof(OcgJobDev) / 8) {
+    static_assert(sizeof(OcgJobDev) % 8 == 0, "job header is copied in 8-byte words");
+    ((uint64_t *)d_job)[threadIdx.x] = ((const uint64_t *)h_job)[threadIdx.x];
+  }
+}
+
+void ocg_launch_stage_in(const OcgJobDev *h_job, OcgJobDev *d_job, const ocg_frag_rec *h_recs, ocg_frag_rec *d_recs,
+                         int nfrags, const int16_t *h_rows, int16_t *d_rows, cudaStream_t st) {
+  static_assert(sizeof(OcgJobDev) / 8 <= 256, "job header larger than one CTA copies");
+  ocg_stage_in_kernel<<<64, 256, 0, st>>>(h_job, d_job, (const uint4 *)h_recs, (uint4 *)d_recs, nfrags,
+                                          (const uint4 *)h_rows, (uint4 *)d_rows);
+  ocg_count_launch(1);
+}
+
+/* The finished frame -> mapped host memory (same layout on both sides), then the frame's sequence number
+   into the host flag: every CTA fences its stores system-wide, the last one to finish publishes. */
+struct OcgOutRect { int64_t off; int32_t pitch, width, height; }; /* width in bytes, multiple of 8 */
+struct OcgOutPlan { OcgOutRect r[3]; int32_t nrect; };
+
+template <typename V>
+__device__ __forceinline__ void copy_rect(const uint8_t *src, uint8_t *dst, const OcgOutRect &r, int tid, int nthreads) {
+  const int per_row = r.width / (int)sizeof(V);
+  const int total = per_row * r.height;
+  int i = tid;
+  for (; i + 3 * nthreads < total; i += 4 * nthreads) {
+    V v[4];
+    int64_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int j = i + k * nthreads;
+      const int y = j / per_row, x = j - y * per_row;
+      o[k] = r.off + (int64_t)y * r.pitch + (int64_t)x * (int)sizeof(V);
+      v[k] = *(const V *)(src + o[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) *(V *)(dst + o[k]) = v[k];
+  }
+  for (; i < total; i += nthreads) {
+    const int y = i / per_row, x = i - y * per_row;
+    const int64_t o = r.off + (int64_t)y * r.pitch + (int64_t)x * (int)sizeof(V);
+    *(V *)(dst + o) = *(const V *)(src + o);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ocg_copy_out_kernel(const OcgOutPlan plan, const uint8_t *__restrict__ src, uint8_t *__restrict__ host_dst,
+                    const OcgJobDev *__restrict__ job, uint32_t *counter, uint32_t *host_flag) {
+  const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), nthreads = (int)(gridDim.x * blockDim.x);
+  for (int k = 0; k < plan.nrect; k++) {
+    if ((plan.r[k].width & 15) == 0) copy_rect<uint4>(src, host_dst, plan.r[k], tid, nthreads);
+    else copy_rect<uint2>(src, host_dst, plan.r[k], tid, nthreads);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(counter, 1u) + 1u == gridDim.x) {
+      *counter = 0;
+      __threadfence_system();
+      *(volatile uint32_t *)host_flag = job->seq;
+      __threadfence_system();
+    }
+  }
+}
+
+/* out_mode: OCG_OUT_PICTURE / OCG_OUT_PADDED / OCG_OUT_NONE (flag only); src / host_dst = the buffer's first byte */
+void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const uint8_t *src, uint8_t *host_dst, const OcgJobDev *job,
+                         uint32_t *counter, uint32_t *host_flag, cudaStream_t st) {
+  OcgOutPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  if (out_mode == OCG_OUT_PADDED) {
+    plan.nrect = 1;
+    plan.r[0].off = 0;
+    plan.r[0].pitch = 0;
+    plan.r[0].width = (int32_t)g.ref_frame_sz; /* multiple of 16 (state.c:582) */
+    plan.r[0].height = 1;
+  } else if (out_mode == OCG_OUT_PICTURE) {
+    plan.nrect = 3;
+    for (int pli = 0; pli < 3; pli++) {
+      const ocg_plane_geom &p = g.planes[pli];
+      plan.r[pli].off = g.base_off + p.plane_off + (int64_t)(p.height - 1) * p.ystride; /* top-left pixel */
+      plan.r[pli].pitch = -p.ystride;
+      plan.r[pli].width = p.width;
+      plan.r[pli].height = p.height;
+    }
+  }
+  const unsigned grid = out_mode == OCG_OUT_NONE ? 1u : 96u;
+  ocg_copy_out_kernel<<<grid, 256, 0, st>>>(plan, src, host_dst, job, counter, host_flag);
+  ocg_count_launch(1);
+}
+
 void ocg_init_device_tables(cudaStream_t st) {
   ocg_lf_table_kernel<<<128, 128, 0, st>>>();
 }

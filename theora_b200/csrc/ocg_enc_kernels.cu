@@ -746,6 +746,7 @@ struct OcgMeJob {
   ocg_me_mb *mb;
   uint32_t *done;              /* [nmbs][2]: == seq once the MB's analysis against that frame is final */
   const uint8_t *gold_refine;  /* nmbs flags or NULL */
+  uint32_t *ticket;            /* [frame][2]: super-block rows claimed / finished in this launch */
   int32_t ystride, nhsbs, nvsbs, nmbs, flags;
   uint32_t seq;
 };
@@ -800,7 +801,13 @@ ocg_me_wavefront_kernel(const OcgMeJob *__restrict__ jobs) {
   const bool is_prev = f == 1;
   const bool nosatd = (J.flags & OCG_ME_NOSATD) != 0;
   const bool want_blocks = is_prev && (J.flags & OCG_ME_FAST) == 0;
-  const int mbi0 = (int)blockIdx.x * J.nhsbs * 4;
+  /* Rows are CLAIMED in order through a ticket, not taken from blockIdx: a CTA only ever waits on rows
+     with smaller tickets, and those were claimed by CTAs that are already running, so the wave-front makes
+     progress whatever order the hardware dispatches the grid in and however many CTAs are resident. */
+  int row_claim = 0;
+  if (lane == 0) row_claim = (int)atomicAdd(J.ticket + f * 2, 1u);
+  row_claim = __shfl_sync(0xFFFFFFFFu, row_claim, 0);
+  const int mbi0 = row_claim * J.nhsbs * 4;
   for (int k = 0; k < J.nhsbs * 4; k++) {
     const int mbi = mbi0 + k;
     const ocg_me_topo *T = J.topo + mbi;
@@ -1000,6 +1007,25 @@ ocg_me_wavefront_kernel(const OcgMeJob *__restrict__ jobs) {
     __threadfence();
     __syncwarp();
     if (lane == 0) st_release_u32(J.done + (size_t)mbi * 2 + f, J.seq);
+    /* Speculative oc_mcenc_refine1mv(OC_FRAME_GOLD): what the refinement WOULD give, kept beside the
+       state (the host decides per macro block whether it happens, analyze.c:2476-2485); off the chain */
+    if (!is_prev && !refine && (J.flags & OCG_ME_SPEC_GOLD)) {
+      int rx, ry;
+      uint32_t rscore;
+      me_refine1(J.src, J.ref_satd[f], ystride, off_refine, lane, bx, by, tot, nosatd, rx, ry, rscore);
+      if (lane == 0) {
+        m->gold_ref_mv = (int16_t)mv_make(rx, ry);
+        m->gold_ref_satd = rscore;
+      }
+    }
+  }
+  /* the last row to finish re-arms the tickets for the next launch */
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(J.ticket + f * 2 + 1, 1u) + 1u == (unsigned)J.nvsbs) {
+      J.ticket[f * 2] = 0;
+      J.ticket[f * 2 + 1] = 0;
+    }
   }
 }
 
@@ -1037,6 +1063,16 @@ ocg_me_refine4_kernel(const OcgMeJob *__restrict__ jobs) {
   }
 }
 
+/* ocg_me_repair: the refinement's input is the search's output */
+__global__ void ocg_me_repair_chain_kernel(const ocg_mb_search_in *in, const ocg_mb_search_out *so, ocg_mb_refine_in *ri) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; i++) { ri->frag_off[i] = in->frag_off[i]; ri->block_vec[i][0] = ri->block_vec[i][1] = 0; ri->block_satd[i] = 0; }
+    ri->vec[0] = so->best_vec[0];
+    ri->vec[1] = so->best_vec[1];
+    ri->satd = so->satd;
+  }
+}
+
 } /* namespace */
 
 extern "C" {
@@ -1055,16 +1091,24 @@ struct ocg_me {
   cudaEvent_t job_used = nullptr;
   bool job_busy = false;
   uint32_t seq = 0;
+  uint32_t *d_ticket = nullptr; /* 4 words, zero between launches */
+  int device = 0;
+  int last_bufs[5] = {-1, -1, -1, -1, -1};
+  int last_flags = 0;
+  /* ocg_me_repair scratch: one macro block */
+  uint8_t *h_rep = nullptr;     /* pinned: search_in | refine_in | search_out | refine_out */
+  uint8_t *d_rep = nullptr;
 };
 
-/* batch scratch (one launch set for many streams), process-wide; calls are serialised by g_me_batch_lock */
+/* batch scratch (one launch set for many streams), one per device; calls are serialised by g_me_batch_lock */
 static std::mutex g_me_batch_lock;
-static struct {
+struct MeBatch {
   OcgMeJob *d = nullptr, *h = nullptr;
   int cap = 0;
   cudaEvent_t used = nullptr;
   bool busy = false;
-} g_me_batch;
+};
+static MeBatch g_me_batches[16];
 
 OCG_API int ocg_me_nmbs(const ocg_geometry *g) {
   if (g == nullptr) return OCG_EFAULT;
@@ -1114,7 +1158,11 @@ OCG_API int ocg_me_topology(const ocg_geometry *g, ocg_me_topo *topo) {
 
 OCG_API void ocg_me_destroy(ocg_me *me) {
   if (me == nullptr) return;
+  cudaSetDevice(me->device);
   if (me->ctx != nullptr) ocg_ctx_sync(me->ctx);
+  cudaFree(me->d_ticket);
+  cudaFree(me->d_rep);
+  if (me->h_rep) cudaFreeHost(me->h_rep);
   cudaFree(me->d_topo);
   cudaFree(me->d_mb);
   cudaFree(me->d_done);
@@ -1140,9 +1188,11 @@ OCG_API int ocg_me_create(ocg_me **out, ocg_ctx *ctx, const ocg_me_topo *topo) {
   *out = nullptr;
   const ocg_geometry *g = ocg_ctx_geometry(ctx);
   if (g->nrefs < 5) return OCG_EINVAL; /* IO + two originals + two reconstructions */
+  if (cudaSetDevice(ocg_ctx_device(ctx)) != cudaSuccess) return OCG_ECUDA;
   ocg_me *me = new (std::nothrow) ocg_me();
   if (me == nullptr) return OCG_ENOMEM;
   me->ctx = ctx;
+  me->device = ocg_ctx_device(ctx);
   me->nhsbs = (g->planes[0].nhfrags + 3) >> 2;
   me->nvsbs = (g->planes[0].nvfrags + 3) >> 2;
   me->nmbs = me->nhsbs * me->nvsbs * 4;
@@ -1169,6 +1219,10 @@ OCG_API int ocg_me_create(ocg_me **out, ocg_ctx *ctx, const ocg_me_topo *topo) {
   ME_CU(cudaHostAlloc(&me->h_gold, n, cudaHostAllocDefault));
   ME_CU(cudaHostAlloc(&me->h_job, sizeof(OcgMeJob), cudaHostAllocDefault));
   ME_CU(cudaEventCreateWithFlags(&me->job_used, cudaEventDisableTiming));
+  ME_CU(cudaMalloc(&me->d_ticket, 4 * sizeof(uint32_t)));
+  ME_CU(cudaMemsetAsync(me->d_ticket, 0, 4 * sizeof(uint32_t), st));
+  ME_CU(cudaMalloc(&me->d_rep, 256));
+  ME_CU(cudaHostAlloc(&me->h_rep, 256, cudaHostAllocDefault));
   ME_CU(cudaMemcpyAsync(me->d_topo, topo, n * sizeof(ocg_me_topo), cudaMemcpyHostToDevice, st));
   ME_CU(cudaMemsetAsync(me->d_mb, 0, n * sizeof(ocg_me_mb), st));
   ME_CU(cudaMemsetAsync(me->d_done, 0, n * 2 * sizeof(uint32_t), st));
@@ -1195,12 +1249,15 @@ static int me_fill_job(ocg_me *me, const int bufs[5], int flags, bool gold, OcgM
   j->mb = me->d_mb;
   j->done = me->d_done;
   j->gold_refine = gold ? me->d_gold : nullptr;
+  j->ticket = me->d_ticket;
   j->ystride = g->planes[0].ystride;
   j->nhsbs = me->nhsbs;
   j->nvsbs = me->nvsbs;
   j->nmbs = me->nmbs;
   j->flags = flags;
   j->seq = ++me->seq;
+  for (int i = 0; i < 5; i++) me->last_bufs[i] = bufs[i];
+  me->last_flags = flags;
   return OCG_OK;
 }
 
@@ -1216,7 +1273,8 @@ static int me_launch(const OcgMeJob *d_jobs, int n, int nvsbs, int nmbs, int fla
 
 OCG_API int ocg_me_frame(ocg_me *me, const int bufs[5], int flags, const uint8_t *gold_refine) {
   if (me == nullptr || bufs == nullptr) return OCG_EFAULT;
-  if (flags & ~31) return OCG_EINVAL;
+  if (flags & ~63) return OCG_EINVAL;
+  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   if (me->job_busy) {
     if (cudaEventSynchronize(me->job_used) != cudaSuccess) return OCG_ECUDA;
@@ -1235,10 +1293,16 @@ OCG_API int ocg_me_frame(ocg_me *me, const int bufs[5], int flags, const uint8_t
 }
 
 OCG_API int ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int flags, void *stream) {
-  if (mes == nullptr || bufs == nullptr) return OCG_EFAULT;
-  if (n <= 0 || (flags & ~31)) return OCG_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (mes == nullptr || bufs == nullptr || mes[0] == nullptr) return OCG_EFAULT;
+  if (n <= 0 || (flags & ~63)) return OCG_EINVAL;
+  const int device = mes[0]->device;
+  if (device < 0 || device >= 16) return OCG_EINVAL;
+  for (int i = 0; i < n; i++)
+    if (mes[i] == nullptr || mes[i]->device != device) return OCG_EINVAL; /* one launch set = one device */
+  if (cudaSetDevice(device) != cudaSuccess) return OCG_ECUDA;
+  cudaStream_t st = stream != nullptr ? (cudaStream_t)stream : (cudaStream_t)ocg_ctx_stream(mes[0]->ctx);
   std::lock_guard<std::mutex> lk(g_me_batch_lock);
+  MeBatch &g_me_batch = g_me_batches[device];
   if (g_me_batch.busy) {
     if (cudaEventSynchronize(g_me_batch.used) != cudaSuccess) return OCG_ECUDA;
     g_me_batch.busy = false;
@@ -1268,6 +1332,7 @@ OCG_API int ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int f
 
 OCG_API int ocg_me_read(ocg_me *me, ocg_me_mb *out) {
   if (me == nullptr || out == nullptr) return OCG_EFAULT;
+  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   if (cudaMemcpyAsync(out, me->d_mb, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
   return cudaStreamSynchronize(st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
@@ -1275,9 +1340,61 @@ OCG_API int ocg_me_read(ocg_me *me, ocg_me_mb *out) {
 
 OCG_API int ocg_me_write(ocg_me *me, const ocg_me_mb *in) {
   if (me == nullptr || in == nullptr) return OCG_EFAULT;
+  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   if (cudaMemcpyAsync(me->d_mb, in, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyHostToDevice, st) != cudaSuccess) return OCG_ECUDA;
   return cudaStreamSynchronize(st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+/* Asynchronous forms for a caller that brackets them with its own synchronisation (pinned `in`/`out`). */
+OCG_API int ocg_me_write_async(ocg_me *me, const ocg_me_mb *in) {
+  if (me == nullptr || in == nullptr) return OCG_EFAULT;
+  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
+  return cudaMemcpyAsync(me->d_mb, in, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyHostToDevice, st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+OCG_API int ocg_me_read_async(ocg_me *me, ocg_me_mb *out) {
+  if (me == nullptr || out == nullptr) return OCG_EFAULT;
+  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
+  return cudaMemcpyAsync(out, me->d_mb, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyDeviceToHost, st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
+}
+
+/* One macro block's search against one reference frame of the last ocg_me_frame call, with the candidate
+   set given by the caller, then (refine != 0) the half-pel refinement of the result.  Synchronous.  This
+   is the repair step of a caller that ran the GOLD chain speculatively (no refinements) and later learns
+   that a neighbour's vector was refined after all (analyze.c:2476-2485 -> mcenc.c:104-110). */
+OCG_API int ocg_me_repair(ocg_me *me, int frame, const ocg_mb_search_in *in, int refine, ocg_mb_search_out *out,
+                          ocg_mb_refine_out *rout) {
+  if (me == nullptr || in == nullptr || out == nullptr || (refine && rout == nullptr)) return OCG_EFAULT;
+  if (frame < 0 || frame > 1 || me->last_bufs[0] < 0) return OCG_EINVAL;
+  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  const ocg_geometry *g = ocg_ctx_geometry(me->ctx);
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
+  const uint8_t *b[5];
+  for (int i = 0; i < 5; i++) b[i] = (const uint8_t *)ocg_ctx_frame_devptr(me->ctx, me->last_bufs[i]) + g->base_off;
+  const uint8_t *ref_full = frame == 1 ? b[1] : b[2], *ref_satd = frame == 1 ? b[3] : b[4];
+  ocg_mb_search_in *h_in = (ocg_mb_search_in *)me->h_rep, *d_in = (ocg_mb_search_in *)me->d_rep;
+  ocg_mb_refine_in *d_rin = (ocg_mb_refine_in *)(me->d_rep + 48);
+  ocg_mb_search_out *h_out = (ocg_mb_search_out *)(me->h_rep + 96), *d_out = (ocg_mb_search_out *)(me->d_rep + 96);
+  ocg_mb_refine_out *h_rout = (ocg_mb_refine_out *)(me->h_rep + 128), *d_rout = (ocg_mb_refine_out *)(me->d_rep + 128);
+  *h_in = *in;
+  if (cudaMemcpyAsync(d_in, h_in, sizeof(*h_in), cudaMemcpyHostToDevice, st) != cudaSuccess) return OCG_ECUDA;
+  const int ystride = g->planes[0].ystride;
+  const bool nosatd = (me->last_flags & OCG_ME_NOSATD) != 0;
+  ocg_mcenc_search_kernel<<<1, 128, 0, st>>>(b[0], ref_full, ref_satd, ystride, d_in, d_out, 1);
+  ocg_count_launch(1);
+  if (refine) {
+    ocg_me_repair_chain_kernel<<<1, 32, 0, st>>>(d_in, d_out, d_rin);
+    ocg_mcenc_refine_kernel<<<1, 128, 0, st>>>(b[0], ref_satd, ystride, d_rin, d_rout, 1,
+                                               OCG_REFINE_1MV | (nosatd ? OCG_REFINE_SAD : 0));
+    ocg_count_launch(2);
+  }
+  if (cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return OCG_ECUDA;
+  *out = *h_out;
+  if (refine) *rout = *h_rout;
+  return OCG_OK;
 }
 
 OCG_API int ocg_mcenc_refine_batch(const uint8_t *src_base, const uint8_t *ref_base, int ystride,

@@ -23,18 +23,19 @@ CAPTURE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(DecFrame), C.POINTER(Stagin
 class BackendStats(C.Structure):
     _fields_ = [("frames", C.c_long), ("coded_frags", C.c_long), ("uncoded_frags", C.c_long),
                 ("coeff_rows", C.c_long), ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long),
-                ("flush_seconds", C.c_double)]
+                ("flush_seconds", C.c_double), ("wait_seconds", C.c_double)]
 
 
 class EncBackendStats(C.Structure):
     """ocg_enc_backend_stats (theora_b200/backend/ocg_backend.h)."""
     _fields_ = [("frames", C.c_long), ("prepass_frames", C.c_long), ("coeff_rows", C.c_long),
                 ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long), ("prepass_seconds", C.c_double),
-                ("flush_seconds", C.c_double)]
+                ("flush_seconds", C.c_double), ("me_frames", C.c_long), ("me_gold_refines", C.c_long),
+                ("me_repairs", C.c_long)]
 
 
 ENC_AUTO, ENC_HOST = 0, 1
-DC_DEVICE, DC_HOST = 0, 1
+DC_DEVICE, DC_HOST, DC_DEVICE_AHEAD = 0, 1, 2
 EXPAND_BACKEND, EXPAND_REFERENCE = 0, 1
 
 _lib = None

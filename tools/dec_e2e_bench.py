@@ -45,15 +45,16 @@ def main():
         s2 = streams.BackendStats()
         Lo.ocg_backend_get_stats(C.byref(s2), 1)
         assert secs > 0
-        ours.append((secs, s2.h2d_bytes, s2.d2h_bytes, s2.flush_seconds / max(s2.frames, 1)))
+        ours.append((secs, s2.h2d_bytes, s2.d2h_bytes, s2.flush_seconds / max(s2.frames, 1),
+                     s2.wait_seconds / max(s2.frames, 1)))
         if R is not None:
             rs = R.refh_decode_time(hr, threads, 1, C.byref(rh))
             assert rs > 0
             refs.append(rs)
     ours.sort()
-    secs, h2d, d2h, flush = ours[1]
+    secs, h2d, d2h, flush, wait = ours[1]
     out = {"secs": secs, "frames": threads * nframes, "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
-           "flush_ms_per_frame": 1e3 * flush, "hash": int(hsh.value), "threads": threads}
+           "flush_ms_per_frame": 1e3 * flush, "wait_ms_per_frame": 1e3 * wait, "hash": int(hsh.value), "threads": threads}
     if refs:
         out["ref_secs"] = sorted(refs)[1]
         out["ref_hash"] = int(rh.value)
