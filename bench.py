@@ -150,23 +150,24 @@ def time_reference(blob, threads, passes):
     return threads * passes * nframes / secs, secs, kind, int(hsh.value)
 
 
-def bench_encode_intra(Lo, threads, width, height, quality, frames=13):
+def bench_encode_api(Lo, threads, width, height, quality, frames=13, kf=1, speed=1):
     """BASELINE configs[2]: intra-only encode through th_encode_ycbcr_in/packetout.
     `threads` independent encoders (unmodified reference host code) on the B200
     back-end -- device pre-pass look-ups + recorded reconstruction -- next to the
     reference x86 SIMD build on the same threads and the same frames; the first
     frame of every encoder is outside the timed region.  Packets must be
-    byte-identical.  Runs in a process of its own (tools/enc_intra_bench.py: ctypes
+    byte-identical.  Runs in a process of its own (tools/enc_bench.py: ctypes
     only), the way a C program would use the library: inside this process torch's
     CUDA client and thread pools share the driver and the cores with the 16 encoder
     threads, which costs the device path ~25 %."""
     env = dict(os.environ)
     env["CUDA_VISIBLE_DEVICES"] = env.get("CUDA_VISIBLE_DEVICES", "").split(",")[LOCAL_RANK] if env.get(
         "CUDA_VISIBLE_DEVICES") else str(LOCAL_RANK)
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "enc_intra_bench.py"), str(width), str(height),
-                        str(quality), str(threads), str(frames)], capture_output=True, text=True, env=env, timeout=900)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "enc_bench.py"), str(width), str(height),
+                        str(quality), str(threads), str(frames), str(kf), str(speed)], capture_output=True, text=True,
+                       env=env, timeout=900)
     if p.returncode != 0:
-        raise RuntimeError("enc_intra_bench failed: " + p.stderr[-400:])
+        raise RuntimeError("enc_bench failed: " + p.stderr[-400:])
     return json.loads(p.stdout.strip().splitlines()[-1])
 
 
@@ -703,12 +704,17 @@ def main():
         except Exception as e:
             me_frame = {"error": repr(e)}
 
-    enc_intra = None
+    enc_intra = enc_inter = None
     if RANK == 0 and WORLD == 1 and not args.no_e2e and not args.no_cpu:
         try:
-            enc_intra = bench_encode_intra(Lo, ncores, args.width, args.height, args.quality)
+            enc_intra = bench_encode_api(Lo, ncores, args.width, args.height, args.quality)
         except Exception as e:
             enc_intra = {"error": repr(e)}
+        try:
+            # BASELINE configs[3]: key frame + inter frames with the motion search, speed level 1
+            enc_inter = bench_encode_api(Lo, ncores, args.width, args.height, args.quality, frames=9, kf=64, speed=1)
+        except Exception as e:
+            enc_inter = {"error": repr(e)}
 
     if RANK == 0:
         line = {"metric": "1080p decode frames/sec", "value": value, "unit": "frames/s", "n_gpus": WORLD,
@@ -720,7 +726,7 @@ def main():
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
                            "parallelism": "independent streams, %d per GPU on %d CUDA stream(s)" % (S, G)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
-                "encode_intra": enc_intra, "motion_analysis": me_frame,
+                "encode_intra": enc_intra, "encode_inter": enc_inter, "motion_analysis": me_frame,
                 "gpu_launches": int(launches),
                 "clocks": clocks}
         emit(line)

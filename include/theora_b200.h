@@ -201,6 +201,9 @@ OCG_API int  ocg_dec_submit(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_
 #define OCG_OUT_NONE    2   /* nothing: the frame stays on the device */
 OCG_API int  ocg_dec_flush(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_out, int out_mode);
 OCG_API int  ocg_dec_wait(ocg_ctx *ctx);   /* until the last ocg_dec_flush has completed */
+/* Host time spent inside ocg_dec_flush since the last reset, process-wide: before the graph launch
+   (seconds), inside cudaGraphLaunch (seconds), number of flushes. */
+OCG_API void ocg_flush_profile(double *prepare_s, double *launch_s, long *n, int reset);
 
 /* ---- decode: device-resident frames, batched over independent streams ---- */
 OCG_API int  ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int nfrags,
@@ -418,6 +421,45 @@ OCG_API int  ocg_me_write_async(ocg_me *me, const ocg_me_mb *in);
 OCG_API int  ocg_me_repair(ocg_me *me, int frame, const ocg_mb_search_in *in, int refine, ocg_mb_search_out *out,
                            ocg_mb_refine_out *rout);
 OCG_API int  ocg_ctx_device(const ocg_ctx *ctx);
+
+/* Inter-frame analysis tables (BASELINE configs[3]): everything the reference's analysis loop asks of the
+   block kernels that depends only on the input frame, the reference frames and the frame's motion analysis,
+   computed for the whole frame behind ocg_me_frame on the same stream:
+     oc_enc_frag_intra_satd of every fragment                  (oc_mb_intra_satd, analyze.c:1360-1400)
+     oc_enc_frag_ssd / _border_ssd vs the co-located PREV block (oc_skip_cost,     analyze.c:1968-2040)
+     oc_enc_frag_satd / _satd2 for OCG_ENC_NCAND candidate predictors per fragment (oc_cost_inter*,
+       analyze.c:2062-2286): NOMV, GOLDEN_NOMV, the unrefined and refined PREV and GOLD vectors, the
+       unrefined and refined 4MV block vectors.
+   A candidate is identified by what the hook is called with -- the predictor's tap offsets relative to the
+   frame pool (buffer 0's bottom-left luma pixel, i.e. ocg_ctx_frame_devptr(ctx,0)+base_off on the device,
+   ref_frame_handle+base_off in the reference) -- so a hit is exact whichever mode asks.  Asynchronous;
+   the tables are complete after ocg_ctx_sync. */
+#define OCG_ENC_NCAND 8
+typedef struct ocg_enc_inter ocg_enc_inter;
+typedef struct ocg_enc_inter_tables {
+  const uint32_t *intra_satd;   /* [nfrags]                                                     */
+  const int32_t  *intra_dc;     /* [nfrags]                                                     */
+  const uint32_t *skip_ssd;     /* [nfrags] plain SSD vs PREV                                   */
+  const uint32_t *border_ssd;   /* [nborder] masked SSD vs PREV, indexed by ocg_enc_inter_border_slot */
+  int32_t         ncand;        /* OCG_ENC_NCAND, or 0 when the candidates were not requested   */
+  int32_t         nluma, nfrags;
+  const ocg_enc_frag *cand;     /* candidate k of fragment f at ocg_enc_cand_index(t,k,f): ref_off0 / ref_off1 (INT32_MIN: one tap) */
+  const uint32_t *cand_satd;    /* same indexing                                                */
+  const int32_t  *cand_dc;
+  long            d2h_bytes;
+} ocg_enc_inter_tables;
+static inline size_t ocg_enc_cand_index(const ocg_enc_inter_tables *t, int k, int fragi) {
+  return fragi < t->nluma ? (size_t)k * (size_t)t->nluma + (size_t)fragi
+                          : (size_t)t->ncand * (size_t)t->nluma + (size_t)k * (size_t)(t->nfrags - t->nluma) + (size_t)(fragi - t->nluma);
+}
+/* mbfrags: [ocg_me_nmbs][12] = state.mb_maps[mbi][pli][bi] (-1: absent); border_fragi/border_mask: the
+   fragments with a border mask (state.borders[frags[i].borderi].mask). */
+OCG_API int  ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, const int32_t *mbfrags,
+                                  const int32_t *border_fragi, const int64_t *border_mask, int nborder);
+OCG_API void ocg_enc_inter_destroy(ocg_enc_inter *ei);
+OCG_API int  ocg_enc_inter_border_slot(const ocg_enc_inter *ei, int fragi);
+OCG_API int  ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, int gold_buf, int with_cands,
+                                   ocg_enc_inter_tables *out);
 
 /* Intra-frame analysis pre-pass (BASELINE config "intra-only encode").  The
    per-block encoder hooks return their result synchronously to serial host

@@ -152,6 +152,7 @@ _PROTOS = {
     "ocg_dec_submit": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p]),
     "ocg_dec_flush": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p, C.c_int]),
     "ocg_dec_wait": (C.c_int, [C.c_void_p]),
+    "ocg_flush_profile": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),
     "ocg_pack_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecFrame), C.c_int, C.c_int, C.c_int]),
     "ocg_pack_destroy": (None, [C.c_void_p]),
     "ocg_pack_nframes": (C.c_int, [C.c_void_p]),
@@ -183,6 +184,11 @@ _PROTOS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ocg_mcenc_refine_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p]),
+    "ocg_enc_inter_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int]),
+    "ocg_enc_inter_destroy": (None, [C.c_void_p]),
+    "ocg_enc_inter_border_slot": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocg_enc_inter_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ocg_enc_intra_reserve": (C.c_int, [C.c_void_p]),
     "ocg_enc_intra_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p]),

@@ -93,6 +93,12 @@ typedef struct ocg_enc_backend_stats {
   long   me_frames;         /* analysis passes whose motion analysis ran on the device          */
   long   me_gold_refines;   /* oc_mcenc_refine1mv(OC_FRAME_GOLD) decisions of the host loop      */
   long   me_repairs;        /* GOLD searches redone because a neighbour's refinement changed their candidates */
+  /* inter frames that were packed: how the analysis loop's block-metric calls were served */
+  long   satd_lookups;      /* frag_satd / frag_satd2 answered from the device's candidate tables          */
+  long   satd_host;         /* ... computed by the reference's C kernel (no candidate with that predictor) */
+  long   ssd_lookups;       /* frag_ssd / frag_border_ssd of oc_skip_cost answered from the device table   */
+  long   ssd_host;          /* ... of the block just reconstructed (analyze.c:829-835): host               */
+  long   intra_satd_lookups;
 } ocg_enc_backend_stats;
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset);
 /* Test instrumentation: a snapshot at the start of every analysis pass of an encoder that runs on the

@@ -83,6 +83,14 @@ typedef struct ocg_enc_backend {
   unsigned char       *gold_dirty;     /* [nmbs] the macro block's final GOLD vector/error differ from the speculation */
   unsigned char       *gold_fixed;     /* [nmbs] its GOLD search was redone (gold_fix holds the refinement) */
   struct { ogg_int16_t mv; ogg_uint32_t satd; } *gold_fix;
+  /* inter-frame analysis tables (intra SATD, skip SSD, SATD of the candidate predictors) */
+  ocg_enc_inter       *ei;
+  ocg_enc_inter_tables itab;
+  int                  itab_valid;     /* itab holds the tables of the frame being analysed */
+  ogg_int32_t         *border_slot;    /* [nfrags] index into itab.border_ssd, or -1 */
+  ogg_int64_t         *border_mask;    /* [nfrags] the mask that slot was computed with */
+  const unsigned char *pool0;          /* ref_frame_handle + base_off: what the candidates' tap offsets are relative to */
+  long                 n_satd_hit, n_satd_miss, n_ssd_hit, n_ssd_host, n_isatd_hit; /* per pass, folded into the stats at the flush */
   /* quantiser tables in the layout of ocg_enc_fdct_quant_batch */
   ogg_uint16_t         dequant[3][2][3][64];
   ogg_int16_t          enquant[3][2][3][64][2];
@@ -165,6 +173,44 @@ static void enc_wait(ocg_enc_backend *b) {
    refinements and also reports what each refinement would give; the look-ups below check, per macro
    block, whether the neighbours' final GOLD vectors/errors still produce the candidate set the device
    used, and redo the one search on the device where they do not (ocg_me_repair). */
+/* Static inputs of the inter-frame tables: which fragments make up each macro block (state.mb_maps) and
+   which fragments straddle the picture border, with their pixel masks (state.c:473-543). */
+static int enc_inter_setup(ocg_enc_backend *b) {
+  oc_theora_state *st = &b->enc->state;
+  ogg_int32_t *mbfrags = (ogg_int32_t *)malloc(st->nmbs * 12 * sizeof(*mbfrags));
+  ogg_int32_t *bfragi = (ogg_int32_t *)malloc((size_t)st->nfrags * sizeof(*bfragi));
+  ogg_int64_t *bmask = (ogg_int64_t *)malloc((size_t)st->nfrags * sizeof(*bmask));
+  ptrdiff_t fragi;
+  size_t mbi;
+  int pli, bi, nb = 0, r = -1;
+  b->border_slot = (ogg_int32_t *)malloc((size_t)st->nfrags * sizeof(*b->border_slot));
+  b->border_mask = (ogg_int64_t *)calloc((size_t)st->nfrags, sizeof(*b->border_mask));
+  if (mbfrags != NULL && bfragi != NULL && bmask != NULL && b->border_slot != NULL && b->border_mask != NULL) {
+    for (mbi = 0; mbi < st->nmbs; mbi++)
+      for (pli = 0; pli < 3; pli++)
+        for (bi = 0; bi < 4; bi++)
+          mbfrags[mbi * 12 + pli * 4 + bi] = st->mb_modes[mbi] == OC_MODE_INVALID ? -1 : (ogg_int32_t)st->mb_maps[mbi][pli][bi];
+    for (fragi = 0; fragi < st->nfrags; fragi++) {
+      if (st->frags[fragi].borderi >= 0) {
+        bfragi[nb] = (ogg_int32_t)fragi;
+        bmask[nb] = st->borders[st->frags[fragi].borderi].mask;
+        b->border_mask[fragi] = bmask[nb];
+        nb++;
+      }
+    }
+    if (ocg_enc_inter_create(&b->ei, b->ctx, b->me, mbfrags, bfragi, bmask, nb) == 0) {
+      for (fragi = 0; fragi < st->nfrags; fragi++) b->border_slot[fragi] = ocg_enc_inter_border_slot(b->ei, (int)fragi);
+      b->pool0 = st->ref_frame_handle + b->geom.base_off;
+      r = 0;
+    }
+  }
+  free(mbfrags);
+  free(bfragi);
+  free(bmask);
+  if (r < 0) enc_fail(b, "inter-frame table set-up failed");
+  return r;
+}
+
 static int enc_me_prepass(ocg_enc_backend *b) {
   oc_enc_ctx *enc = b->enc;
   oc_theora_state *st = &enc->state;
@@ -172,10 +218,11 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   const int first_pass = !(b->me_seen_frame && b->me_frame_num == st->curframe_num);
   int bufs[5], i, k, flags, wanted;
   size_t mbi;
-  if (!first_pass) return 0; /* a re-analysis of the same frame keeps the first pass's vectors (_recode, analyze.c:2402) */
+  if (!first_pass) return 0; /* itab too: functions of the frames and the first pass's vectors */
   b->me_seen_frame = 1;
   b->me_frame_num = st->curframe_num;
   b->me_valid = 0;
+  b->itab_valid = 0;
   /* the input frame joins the device's frame pool (an intra frame's pre-pass uploads it itself) */
   if (b->inter_frame &&
       ocg_ctx_upload_frame(b->ctx, st->ref_frame_idx[OC_FRAME_IO],
@@ -214,6 +261,7 @@ static int enc_me_prepass(ocg_enc_backend *b) {
       enc_fail(b, "motion analysis set-up failed");
       return -1;
     }
+    if (enc_inter_setup(b) < 0) return -1;
   }
   for (mbi = 0; mbi < st->nmbs; mbi++) {
     const oc_mb_enc_info *e = enc->mb_info + mbi;
@@ -227,11 +275,15 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   if (enc->sp_level >= OC_SP_LEVEL_FAST_ANALYSIS) flags |= OCG_ME_FAST;
   else if (b->inter_frame) flags |= OCG_ME_REFINE_4MV;
   if (enc->prevframe_dropped) flags |= OCG_ME_DROPPED;
+  b->itab_valid = 0;
   if (ocg_me_write_async(b->me, b->me_tab) < 0 || ocg_me_frame(b->me, bufs, flags, NULL) < 0 ||
-      ocg_me_read_async(b->me, b->me_tab) < 0 || ocg_ctx_sync(b->ctx) < 0) {
+      ocg_me_read_async(b->me, b->me_tab) < 0 ||
+      (b->inter_frame && ocg_enc_inter_prepass(b->ei, bufs[0], bufs[3], bufs[4], 1, &b->itab) < 0) ||
+      ocg_ctx_sync(b->ctx) < 0) {
     enc_fail(b, "motion analysis on the device failed");
     return -1;
   }
+  b->itab_valid = b->inter_frame;
   memset(b->gold_dirty, 0, st->nmbs);
   memset(b->gold_fixed, 0, st->nmbs);
   b->me_flags = flags;
@@ -239,7 +291,7 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   pthread_mutex_lock(&g_estats_lock);
   g_estats.me_frames++;
   g_estats.h2d_bytes += (long)(b->inter_frame ? b->geom.ref_frame_sz : 0) + (long)(st->nmbs * sizeof(ocg_me_mb));
-  g_estats.d2h_bytes += (long)(st->nmbs * sizeof(ocg_me_mb));
+  g_estats.d2h_bytes += (long)(st->nmbs * sizeof(ocg_me_mb)) + (b->inter_frame ? b->itab.d2h_bytes : 0);
   pthread_mutex_unlock(&g_estats_lock);
   return 0;
 }
@@ -269,6 +321,7 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
   b->cur_fragi = -1;
   b->idct_pending = 0;
   b->nqis = nqis;
+  b->n_satd_hit = b->n_satd_miss = b->n_ssd_hit = b->n_ssd_host = b->n_isatd_hit = 0;
   if (b->inter_capable && enc_me_prepass(b) < 0) return;
   if (!b->inter_frame) {
     /* analyze.c:544-564 has just condensed the tables for this frame */
@@ -334,6 +387,11 @@ static void enc_flush(ocg_enc_backend *b) {
   b->self_on_device = b->inter_capable ? -1 : self;
   pthread_mutex_lock(&g_estats_lock);
   g_estats.frames++;
+  g_estats.satd_lookups += b->n_satd_hit;
+  g_estats.satd_host += b->n_satd_miss;
+  g_estats.ssd_lookups += b->n_ssd_hit;
+  g_estats.ssd_host += b->n_ssd_host;
+  g_estats.intra_satd_lookups += b->n_isatd_hit;
   g_estats.coeff_rows += b->nrows;
   g_estats.h2d_bytes += (long)b->geom.nfrags * 16 + (long)b->nrows * 16;
   if (b->inter_capable) g_estats.d2h_bytes += (long)b->geom.ref_frame_sz;
@@ -366,8 +424,101 @@ static unsigned ocge_frag_intra_satd(int *_dc, const unsigned char *_src, int _y
       return b->tab.satd[fragi];
     }
     enc_fail(b, "frag_intra_satd: not a fragment of the input frame");
+  } else if (b != NULL && b->inter_frame && b->itab_valid) {
+    ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+    if (fragi >= 0) {
+      b->n_isatd_hit++;
+      *_dc = b->itab.intra_dc[fragi];
+      return b->itab.intra_satd[fragi];
+    }
   }
   return oc_enc_frag_intra_satd_c(_dc, _src, _ystride);
+}
+
+/* ---- inter-frame look-ups (tables of ocg_enc_inter_prepass) ----------------
+   A call is served from the tables iff its source block is a fragment of the input frame and its
+   predictor address(es) are the ones a table entry was computed with; anything else -- LAST/LAST2 vectors
+   that coincide with no listed candidate, chroma vectors of a 4MV macro block with skipped luma blocks,
+   the SSD of the block just reconstructed (analyze.c:829-835) -- runs the reference's C kernel on the host
+   frames, which are kept current for exactly that. */
+static inline ocg_enc_backend *enc_tables(void) {
+  ocg_enc_backend *b = t_enc;
+  return b != NULL && b->frame_open && !b->failed && b->inter_frame && b->itab_valid ? b : NULL;
+}
+
+static unsigned ocge_frag_satd(int *_dc, const unsigned char *_src, const unsigned char *_ref, int _ystride) {
+  ocg_enc_backend *b = enc_tables();
+  if (b != NULL) {
+    ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+    const ptrdiff_t roff = _ref - b->pool0;
+    if (fragi >= 0) {
+      int k;
+      for (k = 0; k < b->itab.ncand; k++) {
+        const size_t at = ocg_enc_cand_index(&b->itab, k, (int)fragi);
+        if (b->itab.cand[at].ref_off0 == roff && b->itab.cand[at].ref_off1 == INT32_MIN) {
+          b->n_satd_hit++;
+          *_dc = b->itab.cand_dc[at];
+          return b->itab.cand_satd[at];
+        }
+      }
+    }
+    b->n_satd_miss++;
+  }
+  return oc_enc_frag_satd_c(_dc, _src, _ref, _ystride);
+}
+
+static unsigned ocge_frag_satd2(int *_dc, const unsigned char *_src, const unsigned char *_ref1, const unsigned char *_ref2,
+                                int _ystride) {
+  ocg_enc_backend *b = enc_tables();
+  if (b != NULL) {
+    ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+    const ptrdiff_t r1 = _ref1 - b->pool0, r2 = _ref2 - b->pool0;
+    if (fragi >= 0) {
+      int k;
+      for (k = 0; k < b->itab.ncand; k++) {
+        const size_t at = ocg_enc_cand_index(&b->itab, k, (int)fragi);
+        const ocg_enc_frag *c = b->itab.cand + at;
+        /* the two-tap average is symmetric in its taps */
+        if ((c->ref_off0 == r1 && c->ref_off1 == r2) || (c->ref_off0 == r2 && c->ref_off1 == r1)) {
+          b->n_satd_hit++;
+          *_dc = b->itab.cand_dc[at];
+          return b->itab.cand_satd[at];
+        }
+      }
+    }
+    b->n_satd_miss++;
+  }
+  return oc_enc_frag_satd2_c(_dc, _src, _ref1, _ref2, _ystride);
+}
+
+static unsigned ocge_frag_ssd(const unsigned char *_src, const unsigned char *_ref, int _ystride) {
+  ocg_enc_backend *b = enc_tables();
+  if (b != NULL) {
+    /* oc_skip_cost (analyze.c:1996-2000, 2020-2024): the co-located block of the previous reconstruction */
+    const unsigned char *io = b->enc->state.ref_frame_data[OC_FRAME_IO];
+    if (_ref - b->enc->state.ref_frame_data[OC_FRAME_PREV] == _src - io) {
+      ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+      if (fragi >= 0) { b->n_ssd_hit++; return b->itab.skip_ssd[fragi]; }
+    }
+    b->n_ssd_host++;
+  }
+  return oc_enc_frag_ssd_c(_src, _ref, _ystride);
+}
+
+static unsigned ocge_frag_border_ssd(const unsigned char *_src, const unsigned char *_ref, int _ystride, ogg_int64_t _mask) {
+  ocg_enc_backend *b = enc_tables();
+  if (b != NULL) {
+    const unsigned char *io = b->enc->state.ref_frame_data[OC_FRAME_IO];
+    if (_ref - b->enc->state.ref_frame_data[OC_FRAME_PREV] == _src - io) {
+      ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+      if (fragi >= 0 && b->border_slot[fragi] >= 0 && b->border_mask[fragi] == _mask) {
+        b->n_ssd_hit++;
+        return b->itab.border_ssd[b->border_slot[fragi]];
+      }
+    }
+    b->n_ssd_host++;
+  }
+  return oc_enc_frag_border_ssd_c(_src, _ref, _ystride, _mask);
 }
 
 static void ocge_frag_sub_128(ogg_int16_t _diff[64], const unsigned char *_src, int _ystride) {
@@ -759,6 +910,7 @@ static void enc_backend_destroy(ocg_enc_backend *b) {
   if (t_enc == b) t_enc = NULL;
   if (b->ctx != NULL) {
     ocg_ctx_sync(b->ctx);
+    if (b->ei != NULL) ocg_enc_inter_destroy(b->ei);
     if (b->me != NULL) ocg_me_destroy(b->me);
     if (b->me_tab != NULL) ocg_host_unregister(b->me_tab);
     if (b->pinned) ocg_host_unregister(b->enc->state.ref_frame_handle);
@@ -768,6 +920,8 @@ static void enc_backend_destroy(ocg_enc_backend *b) {
   free(b->gold_dirty);
   free(b->gold_fixed);
   free(b->gold_fix);
+  free(b->border_slot);
+  free(b->border_mask);
   free(b->off2frag);
   free(b);
 }
@@ -844,6 +998,13 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
   _enc->opt_vtable.frag_intra_satd = ocge_frag_intra_satd;
   _enc->opt_vtable.frag_sub_128 = ocge_frag_sub_128;
   _enc->opt_vtable.frag_sub = ocge_frag_sub;
+  if (b->inter_capable) {
+    /* inter-frame look-ups */
+    _enc->opt_vtable.frag_satd = ocge_frag_satd;
+    _enc->opt_vtable.frag_satd2 = ocge_frag_satd2;
+    _enc->opt_vtable.frag_ssd = ocge_frag_ssd;
+    _enc->opt_vtable.frag_border_ssd = ocge_frag_border_ssd;
+  }
   _enc->opt_vtable.fdct8x8 = ocge_fdct8x8;
   _enc->opt_vtable.quantize = ocge_quantize;
   /* recorded reconstruction (every frame) */

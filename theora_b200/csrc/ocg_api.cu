@@ -34,6 +34,17 @@ int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
 
 constexpr int kSlots = 2;
 
+} /* namespace */
+
+/* cudaSetDevice is not free even when nothing changes; cudaGetDevice only reads the runtime's thread state */
+cudaError_t ocg_set_device(int device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return cudaSuccess;
+  return cudaSetDevice(device);
+}
+
+namespace {
+
 struct Slot {
   ocg_frag_rec *recs = nullptr; /* pinned, nfrags */
   int16_t *rows = nullptr;      /* pinned, nfrags*8 rows */
@@ -42,15 +53,19 @@ struct Slot {
   bool busy = false;
   uint32_t flush_seq = 0;       /* ocg_dec_flush: the slot is free once the context's done flag reaches this */
   bool flush_busy = false;
+  /* the device's addresses of the three pinned regions above (mapped) */
+  ocg_frag_rec *m_recs = nullptr;
+  int16_t *m_rows = nullptr;
+  OcgJobDev *m_job = nullptr;
 };
 
 /* One instantiated CUDA graph of a whole frame flush (ocg_dec_flush). */
 struct FlushGraph {
-  int slot, self, out_mode, dc, lf;
-  uint8_t *host_out;
+  int slot, out_mode, dc, lf;
   cudaGraphExec_t exec;
   int kernels;
 };
+struct MappedOut { uint8_t *host, *dev; }; /* page-locked destination buffers seen so far */
 
 } /* namespace */
 
@@ -90,6 +105,7 @@ struct ocg_ctx {
   bool staged = false;
   /* ocg_dec_flush / ocg_dec_wait */
   std::vector<FlushGraph> graphs;
+  std::vector<MappedOut> outs;
   volatile uint32_t *h_done = nullptr; /* pinned + mapped: sequence number of the last finished flush */
   uint32_t *d_done = nullptr;          /* the device's address of the same word */
   uint32_t *d_out_counter = nullptr;   /* copy-out kernel: CTAs finished */
@@ -360,7 +376,7 @@ OCG_API void ocg_geometry_frag_buf_offs(const ocg_geometry *g, int32_t *offs) {
 /* ---- context ------------------------------------------------------------ */
 OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
   if (c == nullptr) return;
-  cudaSetDevice(c->device);
+  ocg_set_device(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (Slot &s : c->slots) {
     if (s.recs) cudaFreeHost(s.recs);
@@ -407,7 +423,7 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   int r = ocg_geometry_init(&chk, g->frame_width, g->frame_height, g->pixel_fmt, g->nrefs);
   if (r < 0) return r;
   if (memcmp(&chk, g, sizeof(chk)) != 0) return fail(OCG_EINVAL, "geometry was not produced by ocg_geometry_init");
-  CU(cudaSetDevice(device));
+  CU(ocg_set_device(device));
   ocg_ctx *c = new (std::nothrow) ocg_ctx();
   if (c == nullptr) return fail(OCG_ENOMEM, "out of memory");
   c->geom = *g;
@@ -448,6 +464,9 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
     CUX(cudaHostAlloc(&s.rows, nf * 8 * 16, cudaHostAllocMapped));
     CUX(cudaHostAlloc(&s.job, sizeof(OcgJobDev), cudaHostAllocMapped));
     CUX(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    CUX(cudaHostGetDevicePointer((void **)&s.m_recs, s.recs, 0));
+    CUX(cudaHostGetDevicePointer((void **)&s.m_rows, s.rows, 0));
+    CUX(cudaHostGetDevicePointer((void **)&s.m_job, s.job, 0));
   }
   /* record template: every fragment uncoded, offsets and planes filled in */
   c->tmpl = (ocg_frag_rec *)calloc(nf, sizeof(ocg_frag_rec));
@@ -484,7 +503,7 @@ OCG_API void *ocg_ctx_frame_devptr(ocg_ctx *c, int buf) {
 
 OCG_API int ocg_ctx_sync(ocg_ctx *c) {
   if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   if (g_blocking_sync.load()) {
     /* the calling thread sleeps until the stream drains: with more stream threads than
        cores the core runs another stream's entropy decode meanwhile */
@@ -500,7 +519,7 @@ OCG_API int ocg_ctx_sync(ocg_ctx *c) {
 OCG_API int ocg_ctx_upload_frame(ocg_ctx *c, int buf, const uint8_t *host) {
   if (c == nullptr || host == nullptr) return fail(OCG_EFAULT, "NULL argument");
   if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   CU(cudaMemcpyAsync(c->frames + (size_t)buf * c->geom.ref_frame_sz, host, (size_t)c->geom.ref_frame_sz,
                      cudaMemcpyHostToDevice, c->stream));
   return OCG_OK;
@@ -509,7 +528,7 @@ OCG_API int ocg_ctx_upload_frame(ocg_ctx *c, int buf, const uint8_t *host) {
 OCG_API int ocg_ctx_download_frame(ocg_ctx *c, int buf, uint8_t *host) {
   if (c == nullptr || host == nullptr) return fail(OCG_EFAULT, "NULL argument");
   if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   CU(cudaMemcpyAsync(host, c->frames + (size_t)buf * c->geom.ref_frame_sz, (size_t)c->geom.ref_frame_sz,
                      cudaMemcpyDeviceToHost, c->stream));
   return OCG_OK;
@@ -522,7 +541,7 @@ OCG_API int ocg_ctx_download_frame(ocg_ctx *c, int buf, uint8_t *host) {
 OCG_API int ocg_ctx_download_picture(ocg_ctx *c, int buf, uint8_t *host) {
   if (c == nullptr || host == nullptr) return fail(OCG_EFAULT, "NULL argument");
   if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   const uint8_t *dev = c->frames + (size_t)buf * c->geom.ref_frame_sz;
   for (int pli = 0; pli < 3; pli++) {
     const ocg_plane_geom &p = c->geom.planes[pli];
@@ -545,7 +564,7 @@ OCG_API long ocg_picture_bytes(const ocg_geometry *g) {
 OCG_API int ocg_ctx_fill_frame(ocg_ctx *c, int buf, int value) {
   if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
   if (buf < 0 || buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   CU(cudaMemsetAsync(c->frames + (size_t)buf * c->geom.ref_frame_sz, value, (size_t)c->geom.ref_frame_sz, c->stream));
   return OCG_OK;
 }
@@ -610,7 +629,7 @@ static int acquire_slot(ocg_ctx *c) {
 
 OCG_API int ocg_dec_staging(ocg_ctx *c, ocg_staging *out) {
   if (c == nullptr || out == nullptr) return fail(OCG_EFAULT, "NULL argument");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   int r = acquire_slot(c);
   if (r < 0) return r;
   Slot &s = c->slots[c->cur_slot];
@@ -624,7 +643,7 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
   if (c == nullptr || f == nullptr) return fail(OCG_EFAULT, "NULL argument");
   int r = check_frame(c->geom, *f);
   if (r < 0) return r;
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   const bool from_staging = c->staged && f->recs == nullptr && f->coeff_rows == nullptr;
   if (!from_staging) {
     if (!f->recs || (f->ncoeff_rows && !f->coeff_rows)) return fail(OCG_EFAULT, "NULL list pointer (and no staged lists)");
@@ -659,6 +678,40 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
   return OCG_OK;
 }
 
+/* Captures and instantiates the flush of one staging slot: kernels only (see ocg_dec_flush). */
+static int build_flush_graph(ocg_ctx *c, int si, int out_mode, int dc, int lf, bool tma) {
+  Slot &s = c->slots[si];
+  cudaStream_t st = c->stream;
+  cudaGraph_t graph = nullptr;
+  /* thread-local capture: other threads' contexts keep working meanwhile */
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  ocg_launch_stage_in(s.m_job, c->d_job, s.m_recs, c->d_recs, c->geom.nfrags, s.m_rows, c->d_rows, st);
+  if (dc) ocg_launch_dc_unpredict(c->gdev, c->d_job, 1, st);
+  ocg_launch_recon(c->gdev, c->d_job, 1, st);
+  if (lf) ocg_launch_loop_filter(c->gdev, c->d_job, 1, tma, st);
+  ocg_launch_borders(c->gdev, c->d_job, 1, st);
+  ocg_launch_copy_out(c->geom, out_mode, c->d_job, c->d_out_counter, c->d_done, st);
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (e != cudaSuccess || graph == nullptr) { cudaGetLastError(); return fail(OCG_ECUDA, "flush graph capture failed", e); }
+  size_t nnodes = 0;
+  cudaGraphGetNodes(graph, nullptr, &nnodes); /* all of them kernels */
+  const int kernels = (int)nnodes;
+  g_launches.fetch_sub(kernels); /* the capture counted them once; they are counted per replay */
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(OCG_ECUDA, "cudaGraphInstantiate", e);
+  c->graphs.push_back(FlushGraph{si, out_mode, dc, lf, exec, kernels});
+  return OCG_OK;
+}
+
+static std::atomic<long> g_flush_prep_ns{0}, g_flush_launch_ns{0}, g_flush_n{0};
+static inline long now_ns() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long)ts.tv_sec * 1000000000L + ts.tv_nsec;
+}
+
 /* One frame = one driver call.  The whole flush -- records and job header H2D, [DC un-prediction],
    recon pass A/B, loop filter, borders, copy-back of the picture (or the padded buffer) into host_out,
    completion flag -- is a CUDA graph, instantiated once per (staging slot, SELF buffer, destination,
@@ -672,7 +725,8 @@ OCG_API int ocg_dec_flush(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out,
   if (r < 0) return r;
   if (f->dc_residual == 2) return fail(OCG_EINVAL, "ocg_dec_flush takes dc_residual 0 or 1");
   if (out_mode != OCG_OUT_NONE && host_out == nullptr) return fail(OCG_EFAULT, "NULL output buffer");
-  CU(cudaSetDevice(c->device));
+  const long t_in = now_ns();
+  CU(ocg_set_device(c->device));
   const bool from_staging = c->staged && f->recs == nullptr && f->coeff_rows == nullptr;
   if (!from_staging) {
     if (!f->recs || (f->ncoeff_rows && !f->coeff_rows)) return fail(OCG_EFAULT, "NULL list pointer (and no staged lists)");
@@ -688,59 +742,59 @@ OCG_API int ocg_dec_flush(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out,
     memcpy(s.recs, f->recs, nf * sizeof(ocg_frag_rec));
     if (f->ncoeff_rows) memcpy(s.rows, f->coeff_rows, (size_t)f->ncoeff_rows * 16);
   }
-  int16_t *d_rows_mapped = nullptr;
-  ocg_frag_rec *d_recs_mapped = nullptr;
-  OcgJobDev *d_job_mapped = nullptr;
-  uint8_t *d_out_mapped = nullptr;
-  CU(cudaHostGetDevicePointer((void **)&d_rows_mapped, s.rows, 0));
-  CU(cudaHostGetDevicePointer((void **)&d_recs_mapped, s.recs, 0));
-  CU(cudaHostGetDevicePointer((void **)&d_job_mapped, s.job, 0));
-  if (out_mode != OCG_OUT_NONE) {
-    if (((uintptr_t)host_out & 15) != 0) return fail(OCG_EINVAL, "output buffer must be 16-byte aligned");
-    if (cudaHostGetDevicePointer((void **)&d_out_mapped, host_out, 0) != cudaSuccess) {
-      cudaGetLastError();
-      return fail(OCG_EINVAL, "output buffer is not page-locked (ocg_host_register)");
-    }
-  }
   fill_job(*s.job, c, *f, c->d_recs, c->d_rows);
   s.job->ncoeff_rows = f->ncoeff_rows;
-  const int self = f->ref_idx[OCG_FRAME_SELF], dc = f->dc_residual == 1, lf = f->lf_limit != 0;
+  const int dc = f->dc_residual == 1, lf = f->lf_limit != 0;
   const bool tma = c->d_tmaps != nullptr && g_use_tma.load();
-  FlushGraph *fg = nullptr;
-  for (FlushGraph &g : c->graphs)
-    if (g.slot == si && g.self == self && g.out_mode == out_mode && g.dc == dc && g.lf == lf && g.host_out == host_out) fg = &g;
-  if (fg == nullptr) {
-    /* the capture must not see other threads' work, and nothing else may be queued on this stream meanwhile */
-    cudaGraph_t graph = nullptr;
-    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    ocg_launch_stage_in(d_job_mapped, c->d_job, d_recs_mapped, c->d_recs, c->geom.nfrags, d_rows_mapped, c->d_rows, st);
-    if (dc) ocg_launch_dc_unpredict(c->gdev, c->d_job, 1, st);
-    ocg_launch_recon(c->gdev, c->d_job, 1, st);
-    if (lf) ocg_launch_loop_filter(c->gdev, c->d_job, 1, tma, st);
-    ocg_launch_borders(c->gdev, c->d_job, 1, st);
-    ocg_launch_copy_out(c->geom, out_mode, c->frames + (size_t)self * c->geom.ref_frame_sz, d_out_mapped, c->d_job,
-                        c->d_out_counter, c->d_done, st);
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
-    if (e != cudaSuccess || graph == nullptr) { cudaGetLastError(); return fail(OCG_ECUDA, "flush graph capture failed", e); }
-    size_t nnodes = 0;
-    cudaGraphGetNodes(graph, nullptr, &nnodes); /* all of them kernels */
-    const int kernels = (int)nnodes;
-    g_launches.fetch_sub(kernels); /* the capture counted them once; they are counted per replay below */
-    cudaGraphExec_t exec = nullptr;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(OCG_ECUDA, "cudaGraphInstantiate", e);
-    c->graphs.push_back(FlushGraph{si, self, out_mode, dc, lf, host_out, exec, kernels});
-    fg = &c->graphs.back();
+  /* the destination's device address (one driver call per distinct buffer, then remembered) */
+  uint8_t *d_out_mapped = nullptr;
+  if (out_mode != OCG_OUT_NONE) {
+    for (const MappedOut &m : c->outs) if (m.host == host_out) d_out_mapped = m.dev;
+    if (d_out_mapped == nullptr) {
+      if (((uintptr_t)host_out & 15) != 0) return fail(OCG_EINVAL, "output buffer must be 16-byte aligned");
+      if (cudaHostGetDevicePointer((void **)&d_out_mapped, host_out, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCG_EINVAL, "output buffer is not page-locked (ocg_host_register)");
+      }
+      if (c->outs.size() >= 16) c->outs.clear();
+      c->outs.push_back(MappedOut{host_out, d_out_mapped});
+    }
   }
+  s.job->host_out = d_out_mapped;
+  /* both staging slots' graphs are made the first time a variant is seen (a stream alternates between
+     them from its second frame on) */
+  FlushGraph *fg = nullptr;
+  for (int pass = 0; pass < 2 && fg == nullptr; pass++) {
+    for (FlushGraph &g : c->graphs)
+      if (g.slot == si && g.out_mode == out_mode && g.dc == dc && g.lf == lf) fg = &g;
+    if (fg == nullptr) {
+      for (int k = 0; k < kSlots; k++) {
+        r = build_flush_graph(c, k, out_mode, dc, lf, tma);
+        if (r < 0) return r;
+      }
+    }
+  }
+  if (fg == nullptr) return fail(OCG_ECUDA, "flush graph missing");
   /* the stage-in kernel reads the staging memory when it runs: everything it reads is final now */
   c->flush_seq++;
   s.job->seq = c->flush_seq;
   s.flush_seq = c->flush_seq;
   s.flush_busy = true;
+  const long t_launch = now_ns();
   CU(cudaGraphLaunch(fg->exec, st));
+  const long t_out = now_ns();
+  g_flush_prep_ns.fetch_add(t_launch - t_in, std::memory_order_relaxed);
+  g_flush_launch_ns.fetch_add(t_out - t_launch, std::memory_order_relaxed);
+  g_flush_n.fetch_add(1, std::memory_order_relaxed);
   g_launches.fetch_add(fg->kernels, std::memory_order_relaxed);
   return OCG_OK;
+}
+
+OCG_API void ocg_flush_profile(double *prepare_s, double *launch_s, long *n, int reset) {
+  if (prepare_s) *prepare_s = 1e-9 * (double)g_flush_prep_ns.load();
+  if (launch_s) *launch_s = 1e-9 * (double)g_flush_launch_ns.load();
+  if (n) *n = g_flush_n.load();
+  if (reset) { g_flush_prep_ns.store(0); g_flush_launch_ns.store(0); g_flush_n.store(0); }
 }
 
 OCG_API int ocg_dec_wait(ocg_ctx *c) {
@@ -754,7 +808,7 @@ OCG_API int ocg_dec_wait(ocg_ctx *c) {
 OCG_API int ocg_dec_dc_begin(ocg_ctx *c, const uint32_t *frag_words) {
   if (c == nullptr || frag_words == nullptr) return fail(OCG_EFAULT, "NULL argument");
   if (!ocg_dc_unpredict_supported(&c->geom)) return fail(OCG_EIMPL, "DC un-prediction on the device does not support this frame size");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   CU(cudaMemcpyAsync(c->d_dc_words, frag_words, (size_t)c->geom.nfrags * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   if (ocg_launch_dc_unpredict_words(c->gdev, c->d_dc_words, c->d_dc_final, c->d_dc_tmp, c->stream) < 0)
     return fail(OCG_EIMPL, "DC un-prediction launch failed");
@@ -803,7 +857,7 @@ static int enc_pre_init(ocg_ctx *c) {
 
 OCG_API int ocg_enc_intra_reserve(ocg_ctx *c) {
   if (c == nullptr) return fail(OCG_EFAULT, "NULL context");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   return c->enc != nullptr ? OCG_OK : enc_pre_init(c);
 }
 
@@ -813,7 +867,7 @@ OCG_API int ocg_enc_intra_prepass(ocg_ctx *c, int io_buf, const uint8_t *host_fr
     return fail(OCG_EFAULT, "NULL argument");
   if (io_buf < 0 || io_buf >= c->geom.nrefs) return fail(OCG_EINVAL, "bad buffer index");
   if (nqis < 1 || nqis > 3) return fail(OCG_EINVAL, "nqis must be 1..3");
-  CU(cudaSetDevice(c->device));
+  CU(ocg_set_device(c->device));
   if (c->enc == nullptr) {
     int r = enc_pre_init(c);
     if (r < 0) return r;
@@ -866,7 +920,7 @@ OCG_API int ocg_enc_intra_prepass(ocg_ctx *c, int io_buf, const uint8_t *host_fr
 /* ---- device-resident packs ---------------------------------------------- */
 OCG_API void ocg_pack_destroy(ocg_pack *p) {
   if (p == nullptr) return;
-  cudaSetDevice(p->device);
+  ocg_set_device(p->device);
   cudaFree(p->blob);
   delete p;
 }
@@ -879,7 +933,7 @@ OCG_API int ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nfr
   if (out == nullptr || frames == nullptr) return fail(OCG_EFAULT, "NULL argument");
   *out = nullptr;
   if (nframes <= 0 || nfrags <= 0) return fail(OCG_EINVAL, "empty pack");
-  CU(cudaSetDevice(device));
+  CU(ocg_set_device(device));
   size_t total = 0;
   for (int i = 0; i < nframes; i++)
     total += align256((size_t)nfrags * sizeof(ocg_frag_rec)) + align256((size_t)frames[i].ncoeff_rows * 16);
@@ -931,7 +985,7 @@ OCG_API int ocg_dec_run_batch(ocg_ctx *const *ctxs, ocg_pack *const *packs, cons
   if (n <= 0) return fail(OCG_EINVAL, "empty batch");
   ocg_ctx *c0 = ctxs[0];
   if (c0 == nullptr) return fail(OCG_EFAULT, "NULL context");
-  CU(cudaSetDevice(c0->device));
+  CU(ocg_set_device(c0->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c0->stream;
   g_bs_i = (g_bs_i + 1) & 7;
   BatchScratch &bs = g_bs[g_bs_i];

@@ -1100,7 +1100,7 @@ void ocg_launch_stage_in(const OcgJobDev *h_job, OcgJobDev *d_job, const ocg_fra
 /* The finished frame -> mapped host memory (same layout on both sides), then the frame's sequence number
    into the host flag: every CTA fences its stores system-wide, the last one to finish publishes. */
 struct OcgOutRect { int64_t off; int32_t pitch, width, height; }; /* width in bytes, multiple of 8 */
-struct OcgOutPlan { OcgOutRect r[3]; int32_t nrect; };
+struct OcgOutPlan { OcgOutRect r[3]; int32_t nrect; int64_t base_off; };
 
 template <typename V>
 __device__ __forceinline__ void copy_rect(const uint8_t *src, uint8_t *dst, const OcgOutRect &r, int tid, int nthreads) {
@@ -1128,8 +1128,10 @@ __device__ __forceinline__ void copy_rect(const uint8_t *src, uint8_t *dst, cons
 }
 
 __global__ void __launch_bounds__(256)
-ocg_copy_out_kernel(const OcgOutPlan plan, const uint8_t *__restrict__ src, uint8_t *__restrict__ host_dst,
-                    const OcgJobDev *__restrict__ job, uint32_t *counter, uint32_t *host_flag) {
+ocg_copy_out_kernel(const OcgOutPlan plan, const OcgJobDev *__restrict__ job, uint32_t *counter, uint32_t *host_flag) {
+  /* source and destination travel in the job header, so one graph serves every SELF buffer */
+  const uint8_t *__restrict__ src = job->base[OCG_FRAME_SELF] - plan.base_off;
+  uint8_t *__restrict__ host_dst = job->host_out;
   const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), nthreads = (int)(gridDim.x * blockDim.x);
   for (int k = 0; k < plan.nrect; k++) {
     if ((plan.r[k].width & 15) == 0) copy_rect<uint4>(src, host_dst, plan.r[k], tid, nthreads);
@@ -1147,11 +1149,12 @@ ocg_copy_out_kernel(const OcgOutPlan plan, const uint8_t *__restrict__ src, uint
   }
 }
 
-/* out_mode: OCG_OUT_PICTURE / OCG_OUT_PADDED / OCG_OUT_NONE (flag only); src / host_dst = the buffer's first byte */
-void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const uint8_t *src, uint8_t *host_dst, const OcgJobDev *job,
-                         uint32_t *counter, uint32_t *host_flag, cudaStream_t st) {
+/* out_mode: OCG_OUT_PICTURE / OCG_OUT_PADDED / OCG_OUT_NONE (flag only) */
+void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const OcgJobDev *job, uint32_t *counter, uint32_t *host_flag,
+                         cudaStream_t st) {
   OcgOutPlan plan;
   memset(&plan, 0, sizeof(plan));
+  plan.base_off = g.base_off;
   if (out_mode == OCG_OUT_PADDED) {
     plan.nrect = 1;
     plan.r[0].off = 0;
@@ -1169,7 +1172,7 @@ void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const uint8_t *src
     }
   }
   const unsigned grid = out_mode == OCG_OUT_NONE ? 1u : 96u;
-  ocg_copy_out_kernel<<<grid, 256, 0, st>>>(plan, src, host_dst, job, counter, host_flag);
+  ocg_copy_out_kernel<<<grid, 256, 0, st>>>(plan, job, counter, host_flag);
   ocg_count_launch(1);
 }
 

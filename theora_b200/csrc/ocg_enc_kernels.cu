@@ -231,6 +231,105 @@ ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__re
   if (out_dc != nullptr) out_dc[fi] = dc;
 }
 
+
+/* oc_mv (state.h:225-240): x in the low byte, y above it, half-pel units */
+__device__ __forceinline__ int mv_x(int mv) { return (int)(signed char)(mv & 0xFF); }
+__device__ __forceinline__ int mv_y(int mv) { return (int)(short)mv >> 8; }
+__device__ __forceinline__ int mv_make(int x, int y) { return (int)(short)((x & 0xFF) | (y * 256)); }
+
+/* ---- inter-frame analysis tables (BASELINE configs[3]) ---------------------
+   oc_cost_inter* (analyze.c:2062-2286) score a macro block's 4 luma + 2..8 chroma blocks against a
+   predictor that is a function of (reference frame, vector).  Once the motion analysis of the frame is
+   known, the vectors of every mode but LAST/LAST2 are known too, so the predictors can be listed per
+   fragment and scored in one batch.  Candidate k of a macro block:
+     0 PREV (0,0)   OC_MODE_INTER_NOMV        4 GOLD unrefined      OC_MODE_GOLDEN_MV, first cost
+     1 GOLD (0,0)   OC_MODE_GOLDEN_NOMV       5 GOLD refined        ... after oc_mcenc_refine1mv (speculative)
+     2 PREV unrefined  OC_MODE_INTER_MV, first cost (analyze.c:2437)
+     3 PREV refined    ... after oc_mcenc_refine1mv (2490)
+     6 4MV unrefined block vectors, chroma vectors from all four (oc_set_chroma_mvs*, state.c:33-97)
+     7 4MV refined block vectors
+   The entries are keyed by what the hook will be called with: predictor tap offsets relative to the frame
+   pool, so a look-up is exact whoever asks (LAST/LAST2 hit whenever their vector coincides with one above). */
+__device__ __forceinline__ void enc_mv_taps(int mv, int qx, int qy, int ystride, int &off0, int &fx, int &fy) {
+  /* state.c:846-957 in closed form: first tap truncates towards zero, the second one (present iff a
+     component has a fractional part) lies one step further from zero */
+  const int dx = mv_x(mv), dy = mv_y(mv);
+  const int ax = abs(dx), ay = abs(dy);
+  const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+  fx = (ax & (qx ? 3 : 1)) ? sx : 0;
+  fy = (ay & (qy ? 3 : 1)) ? sy : 0;
+  off0 = sy * (ay >> (1 + qy)) * ystride + sx * (ax >> (1 + qx));
+}
+__device__ __forceinline__ int div_round_pow2(int v, int shift, int rval) { return (v + (v < 0 ? -1 : 0) + rval) >> shift; }
+
+struct OcgCandJob {
+  const ocg_me_mb *mb;
+  const int32_t *mbfrags;   /* [nmbs][12]: state.mb_maps[mbi][pli][bi], -1 = absent */
+  const int32_t *frag_off;  /* [nfrags] frag_buf_offs */
+  ocg_enc_frag *out;        /* luma block [K][nluma], then chroma block [K][nchroma] */
+  int32_t nmbs, nfrags, nluma;
+  int32_t ystride_y, ystride_c, qx, qy, fmt;
+  int32_t io_off, prev_off, gold_off; /* buffer index * ref_frame_sz */
+};
+
+__global__ void __launch_bounds__(128)
+ocg_enc_cand_kernel(const OcgCandJob J) {
+  const int mbi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (mbi >= J.nmbs) return;
+  const int32_t *mf = J.mbfrags + (size_t)mbi * 12;
+  if (mf[0] < 0) return; /* macro block outside the coded frame */
+  const ocg_me_mb m = J.mb[mbi];
+  const int nchroma = J.nfrags - J.nluma;
+  for (int k = 0; k < OCG_ENC_NCAND; k++) {
+    const bool gold = k == 1 || k == 4 || k == 5;
+    const int frame_off = gold ? J.gold_off : J.prev_off;
+    int lb[4], cb[4], one = 0;
+    bool four = false;
+    switch (k) {
+      case 2: one = m.unref_mv[1]; break;
+      case 3: one = m.analysis_mv[0][1]; break;
+      case 4: one = m.unref_mv[0]; break;
+      case 5: one = m.gold_ref_mv; break;
+      case 6: four = true; for (int b = 0; b < 4; b++) lb[b] = m.block_mv[b]; break;
+      case 7: four = true; for (int b = 0; b < 4; b++) lb[b] = m.ref_mv[b]; break;
+      default: break;
+    }
+    if (four) {
+      /* state.c:33-87 by pixel format: 0 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (1 is reserved: chroma decimated in y only) */
+      for (int b = 0; b < 4; b++) cb[b] = lb[b];
+      if (J.fmt == 0) {
+        const int dx = mv_x(lb[0]) + mv_x(lb[1]) + mv_x(lb[2]) + mv_x(lb[3]);
+        const int dy = mv_y(lb[0]) + mv_y(lb[1]) + mv_y(lb[2]) + mv_y(lb[3]);
+        cb[0] = mv_make(div_round_pow2(dx, 2, 2), div_round_pow2(dy, 2, 2));
+      } else if (J.fmt == 1) {
+        cb[0] = mv_make(div_round_pow2(mv_x(lb[0]) + mv_x(lb[2]), 1, 1), div_round_pow2(mv_y(lb[0]) + mv_y(lb[2]), 1, 1));
+        cb[1] = mv_make(div_round_pow2(mv_x(lb[1]) + mv_x(lb[3]), 1, 1), div_round_pow2(mv_y(lb[1]) + mv_y(lb[3]), 1, 1));
+      } else if (J.fmt == 2) {
+        cb[0] = mv_make(div_round_pow2(mv_x(lb[0]) + mv_x(lb[1]), 1, 1), div_round_pow2(mv_y(lb[0]) + mv_y(lb[1]), 1, 1));
+        cb[2] = mv_make(div_round_pow2(mv_x(lb[2]) + mv_x(lb[3]), 1, 1), div_round_pow2(mv_y(lb[2]) + mv_y(lb[3]), 1, 1));
+      }
+    }
+    for (int idx = 0; idx < 12; idx++) {
+      const int fragi = mf[idx];
+      if (fragi < 0) continue;
+      const int pli = idx >> 2, bi = idx & 3;
+      const int mv = four ? (pli ? cb[bi] : lb[bi]) : one;
+      const int ystride = pli ? J.ystride_c : J.ystride_y;
+      int off0, fx, fy;
+      enc_mv_taps(mv, pli ? J.qx : 0, pli ? J.qy : 0, ystride, off0, fx, fy);
+      const int foff = J.frag_off[fragi];
+      ocg_enc_frag e;
+      e.src_off = J.io_off + foff;
+      e.ref_off0 = frame_off + foff + off0;
+      e.ref_off1 = (fx | fy) ? e.ref_off0 + fy * ystride + fx : INT_MIN;
+      e.aux = 0;
+      const size_t at = fragi < J.nluma ? (size_t)k * J.nluma + fragi
+                                        : (size_t)OCG_ENC_NCAND * J.nluma + (size_t)k * nchroma + (fragi - J.nluma);
+      J.out[at] = e;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* oc_mb_activity (analyze.c:1152-1237) per luma block, one lane per block:
    pixel sum and sum of squares -> variance-like activity, and for non-flat
@@ -751,9 +850,6 @@ struct OcgMeJob {
   uint32_t seq;
 };
 
-__device__ __forceinline__ int mv_x(int mv) { return (int)(signed char)(mv & 0xFF); }
-__device__ __forceinline__ int mv_y(int mv) { return (int)(short)mv >> 8; }
-__device__ __forceinline__ int mv_make(int x, int y) { return (int)(short)((x & 0xFF) | (y * 256)); }
 __device__ __forceinline__ int mv_add(int a, int b) { return mv_make(mv_x(a) + mv_x(b), mv_y(a) + mv_y(b)); }
 __device__ __forceinline__ int mv_sub(int a, int b) { return mv_make(mv_x(a) - mv_x(b), mv_y(a) - mv_y(b)); }
 __device__ __forceinline__ int clamp31(int v) { return max(-31, min(31, v)); }
@@ -1158,7 +1254,7 @@ OCG_API int ocg_me_topology(const ocg_geometry *g, ocg_me_topo *topo) {
 
 OCG_API void ocg_me_destroy(ocg_me *me) {
   if (me == nullptr) return;
-  cudaSetDevice(me->device);
+  ocg_set_device(me->device);
   if (me->ctx != nullptr) ocg_ctx_sync(me->ctx);
   cudaFree(me->d_ticket);
   cudaFree(me->d_rep);
@@ -1188,7 +1284,7 @@ OCG_API int ocg_me_create(ocg_me **out, ocg_ctx *ctx, const ocg_me_topo *topo) {
   *out = nullptr;
   const ocg_geometry *g = ocg_ctx_geometry(ctx);
   if (g->nrefs < 5) return OCG_EINVAL; /* IO + two originals + two reconstructions */
-  if (cudaSetDevice(ocg_ctx_device(ctx)) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(ocg_ctx_device(ctx)) != cudaSuccess) return OCG_ECUDA;
   ocg_me *me = new (std::nothrow) ocg_me();
   if (me == nullptr) return OCG_ENOMEM;
   me->ctx = ctx;
@@ -1274,7 +1370,7 @@ static int me_launch(const OcgMeJob *d_jobs, int n, int nvsbs, int nmbs, int fla
 OCG_API int ocg_me_frame(ocg_me *me, const int bufs[5], int flags, const uint8_t *gold_refine) {
   if (me == nullptr || bufs == nullptr) return OCG_EFAULT;
   if (flags & ~63) return OCG_EINVAL;
-  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   if (me->job_busy) {
     if (cudaEventSynchronize(me->job_used) != cudaSuccess) return OCG_ECUDA;
@@ -1299,7 +1395,7 @@ OCG_API int ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int f
   if (device < 0 || device >= 16) return OCG_EINVAL;
   for (int i = 0; i < n; i++)
     if (mes[i] == nullptr || mes[i]->device != device) return OCG_EINVAL; /* one launch set = one device */
-  if (cudaSetDevice(device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = stream != nullptr ? (cudaStream_t)stream : (cudaStream_t)ocg_ctx_stream(mes[0]->ctx);
   std::lock_guard<std::mutex> lk(g_me_batch_lock);
   MeBatch &g_me_batch = g_me_batches[device];
@@ -1332,7 +1428,7 @@ OCG_API int ocg_me_frame_batch(ocg_me *const *mes, const int *bufs, int n, int f
 
 OCG_API int ocg_me_read(ocg_me *me, ocg_me_mb *out) {
   if (me == nullptr || out == nullptr) return OCG_EFAULT;
-  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   if (cudaMemcpyAsync(out, me->d_mb, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
   return cudaStreamSynchronize(st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
@@ -1340,7 +1436,7 @@ OCG_API int ocg_me_read(ocg_me *me, ocg_me_mb *out) {
 
 OCG_API int ocg_me_write(ocg_me *me, const ocg_me_mb *in) {
   if (me == nullptr || in == nullptr) return OCG_EFAULT;
-  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   if (cudaMemcpyAsync(me->d_mb, in, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyHostToDevice, st) != cudaSuccess) return OCG_ECUDA;
   return cudaStreamSynchronize(st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
@@ -1349,13 +1445,13 @@ OCG_API int ocg_me_write(ocg_me *me, const ocg_me_mb *in) {
 /* Asynchronous forms for a caller that brackets them with its own synchronisation (pinned `in`/`out`). */
 OCG_API int ocg_me_write_async(ocg_me *me, const ocg_me_mb *in) {
   if (me == nullptr || in == nullptr) return OCG_EFAULT;
-  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   return cudaMemcpyAsync(me->d_mb, in, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyHostToDevice, st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
 }
 OCG_API int ocg_me_read_async(ocg_me *me, ocg_me_mb *out) {
   if (me == nullptr || out == nullptr) return OCG_EFAULT;
-  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(me->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   return cudaMemcpyAsync(out, me->d_mb, (size_t)me->nmbs * sizeof(ocg_me_mb), cudaMemcpyDeviceToHost, st) == cudaSuccess ? OCG_OK : OCG_ECUDA;
 }
@@ -1368,7 +1464,7 @@ OCG_API int ocg_me_repair(ocg_me *me, int frame, const ocg_mb_search_in *in, int
                           ocg_mb_refine_out *rout) {
   if (me == nullptr || in == nullptr || out == nullptr || (refine && rout == nullptr)) return OCG_EFAULT;
   if (frame < 0 || frame > 1 || me->last_bufs[0] < 0) return OCG_EINVAL;
-  if (cudaSetDevice(me->device) != cudaSuccess) return OCG_ECUDA;
+  if (ocg_set_device(me->device) != cudaSuccess) return OCG_ECUDA;
   const ocg_geometry *g = ocg_ctx_geometry(me->ctx);
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(me->ctx);
   const uint8_t *b[5];
@@ -1394,6 +1490,176 @@ OCG_API int ocg_me_repair(ocg_me *me, int frame, const ocg_mb_search_in *in, int
   if (cudaStreamSynchronize(st) != cudaSuccess) return OCG_ECUDA;
   *out = *h_out;
   if (refine) *rout = *h_rout;
+  return OCG_OK;
+}
+
+
+/* ---- inter-frame analysis tables ------------------------------------------- */
+struct ocg_enc_inter {
+  ocg_ctx *ctx = nullptr;
+  ocg_me *me = nullptr;
+  int device = 0;
+  int nfrags = 0, nluma = 0, nmbs = 0, nborder_y = 0, nborder_c = 0;
+  int32_t *d_mbfrags = nullptr, *d_frag_off = nullptr;
+  ocg_enc_frag *d_all = nullptr;     /* [nfrags] {foff, foff} */
+  ocg_enc_frag *d_border = nullptr;  /* luma border fragments, then chroma ones: {foff, foff, mask lo, mask hi} */
+  ocg_enc_frag *d_cand = nullptr;    /* [K][nfrags] in the two-block layout of ocg_enc_cand_kernel */
+  uint8_t *d_out = nullptr, *h_out = nullptr;
+  size_t off_isatd = 0, off_idc = 0, off_skip = 0, off_border = 0, off_key = 0, off_csatd = 0, off_cdc = 0, out_sz = 0;
+  int32_t *h_border_slot = nullptr; /* [nfrags] index into border_ssd or -1 */
+};
+
+OCG_API void ocg_enc_inter_destroy(ocg_enc_inter *ei) {
+  if (ei == nullptr) return;
+  ocg_set_device(ei->device);
+  if (ei->ctx != nullptr) ocg_ctx_sync(ei->ctx);
+  cudaFree(ei->d_mbfrags);
+  cudaFree(ei->d_frag_off);
+  cudaFree(ei->d_all);
+  cudaFree(ei->d_border);
+  cudaFree(ei->d_cand);
+  cudaFree(ei->d_out);
+  if (ei->h_out) cudaFreeHost(ei->h_out);
+  free(ei->h_border_slot);
+  delete ei;
+}
+
+OCG_API int ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, const int32_t *mbfrags,
+                                 const int32_t *border_fragi, const int64_t *border_mask, int nborder) {
+  if (out == nullptr || ctx == nullptr || me == nullptr || mbfrags == nullptr || (nborder > 0 && (border_fragi == nullptr || border_mask == nullptr)))
+    return OCG_EFAULT;
+  *out = nullptr;
+  const ocg_geometry *g = ocg_ctx_geometry(ctx);
+  if (nborder < 0 || nborder > g->nfrags) return OCG_EINVAL;
+  if (ocg_set_device(ocg_ctx_device(ctx)) != cudaSuccess) return OCG_ECUDA;
+  ocg_enc_inter *ei = new (std::nothrow) ocg_enc_inter();
+  if (ei == nullptr) return OCG_ENOMEM;
+  ei->ctx = ctx;
+  ei->me = me;
+  ei->device = ocg_ctx_device(ctx);
+  ei->nfrags = g->nfrags;
+  ei->nluma = g->planes[0].nfrags;
+  ei->nmbs = me->nmbs;
+  const size_t nf = (size_t)g->nfrags, K = OCG_ENC_NCAND;
+  std::vector<int32_t> foff(nf);
+  ocg_geometry_frag_buf_offs(g, foff.data());
+  std::vector<ocg_enc_frag> all(nf), border((size_t)nborder);
+  for (size_t i = 0; i < nf; i++) all[i] = ocg_enc_frag{foff[i], foff[i], INT_MIN, 0};
+  ei->h_border_slot = (int32_t *)malloc(nf * sizeof(int32_t));
+  if (ei->h_border_slot == nullptr) { delete ei; return OCG_ENOMEM; }
+  for (size_t i = 0; i < nf; i++) ei->h_border_slot[i] = -1;
+  int nb = 0;
+  for (int pass = 0; pass < 2; pass++) { /* luma fragments first: the two classes differ in stride */
+    for (int i = 0; i < nborder; i++) {
+      const int fi = border_fragi[i];
+      if (fi < 0 || fi >= g->nfrags) { ocg_enc_inter_destroy(ei); return OCG_EINVAL; }
+      if ((fi < ei->nluma) != (pass == 0)) continue;
+      border[(size_t)nb] = ocg_enc_frag{foff[(size_t)fi], foff[(size_t)fi], (int32_t)(uint32_t)(uint64_t)border_mask[i],
+                                        (int32_t)(uint32_t)((uint64_t)border_mask[i] >> 32)};
+      ei->h_border_slot[fi] = nb++;
+    }
+    if (pass == 0) ei->nborder_y = nb;
+  }
+  ei->nborder_c = nb - ei->nborder_y;
+  size_t o = 0;
+  ei->off_isatd = o; o += nf * 4;
+  ei->off_idc = o; o += nf * 4;
+  ei->off_skip = o; o += nf * 4;
+  ei->off_border = o; o += ((size_t)nborder + 1) * 4;
+  o = (o + 255) & ~(size_t)255;
+  ei->off_csatd = o; o += K * nf * 4;
+  ei->off_cdc = o; o += K * nf * 4;
+  ei->out_sz = o;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(ctx);
+#define EI_CU(call) do { if ((call) != cudaSuccess) { cudaGetLastError(); ocg_enc_inter_destroy(ei); return OCG_ECUDA; } } while (0)
+  EI_CU(cudaMalloc(&ei->d_mbfrags, (size_t)ei->nmbs * 12 * sizeof(int32_t)));
+  EI_CU(cudaMalloc(&ei->d_frag_off, nf * sizeof(int32_t)));
+  EI_CU(cudaMalloc(&ei->d_all, nf * sizeof(ocg_enc_frag)));
+  EI_CU(cudaMalloc(&ei->d_border, ((size_t)nborder + 1) * sizeof(ocg_enc_frag)));
+  EI_CU(cudaMalloc(&ei->d_cand, K * nf * sizeof(ocg_enc_frag)));
+  EI_CU(cudaMalloc(&ei->d_out, ei->out_sz));
+  EI_CU(cudaHostAlloc(&ei->h_out, ei->out_sz + K * nf * sizeof(ocg_enc_frag), cudaHostAllocDefault));
+  EI_CU(cudaMemcpyAsync(ei->d_mbfrags, mbfrags, (size_t)ei->nmbs * 12 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  EI_CU(cudaMemcpyAsync(ei->d_frag_off, foff.data(), nf * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  EI_CU(cudaMemcpyAsync(ei->d_all, all.data(), nf * sizeof(ocg_enc_frag), cudaMemcpyHostToDevice, st));
+  if (nborder > 0) EI_CU(cudaMemcpyAsync(ei->d_border, border.data(), (size_t)nborder * sizeof(ocg_enc_frag), cudaMemcpyHostToDevice, st));
+  EI_CU(cudaMemsetAsync(ei->d_cand, 0, K * nf * sizeof(ocg_enc_frag), st));
+  EI_CU(cudaStreamSynchronize(st));
+#undef EI_CU
+  *out = ei;
+  return OCG_OK;
+}
+
+OCG_API int ocg_enc_inter_border_slot(const ocg_enc_inter *ei, int fragi) {
+  return ei != nullptr && fragi >= 0 && fragi < ei->nfrags ? ei->h_border_slot[fragi] : -1;
+}
+
+OCG_API int ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, int gold_buf, int with_cands,
+                                  ocg_enc_inter_tables *out) {
+  if (ei == nullptr || out == nullptr) return OCG_EFAULT;
+  const ocg_geometry *g = ocg_ctx_geometry(ei->ctx);
+  if (io_buf < 0 || io_buf >= g->nrefs || prev_buf < 0 || prev_buf >= g->nrefs || gold_buf < 0 || gold_buf >= g->nrefs) return OCG_EINVAL;
+  if (ocg_set_device(ei->device) != cudaSuccess) return OCG_ECUDA;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(ei->ctx);
+  const uint8_t *pool = (const uint8_t *)ocg_ctx_frame_devptr(ei->ctx, 0) + g->base_off;
+  const uint8_t *io = pool + (size_t)io_buf * g->ref_frame_sz, *prev = pool + (size_t)prev_buf * g->ref_frame_sz;
+  const int nl = ei->nluma, nc = ei->nfrags - nl, K = OCG_ENC_NCAND;
+  const int ys[2] = {g->planes[0].ystride, g->planes[1].ystride};
+  uint32_t *d_isatd = (uint32_t *)(ei->d_out + ei->off_isatd), *d_skip = (uint32_t *)(ei->d_out + ei->off_skip);
+  uint32_t *d_border = (uint32_t *)(ei->d_out + ei->off_border), *d_csatd = (uint32_t *)(ei->d_out + ei->off_csatd);
+  int32_t *d_idc = (int32_t *)(ei->d_out + ei->off_idc), *d_cdc = (int32_t *)(ei->d_out + ei->off_cdc);
+  const int first[2] = {0, nl}, count[2] = {nl, nc};
+  const int bfirst[2] = {0, ei->nborder_y}, bcount[2] = {ei->nborder_y, ei->nborder_c};
+  int r = OCG_OK;
+  for (int k = 0; k < 2 && r == OCG_OK; k++) {
+    /* oc_mb_intra_satd (analyze.c:1360-1400), oc_skip_cost (analyze.c:1968-2040) */
+    r = ocg_enc_metrics_batch(OCG_MET_INTRA_SATD, io, nullptr, ys[k], ei->d_all + first[k], count[k], d_isatd + first[k], d_idc + first[k], st);
+    if (r == OCG_OK) r = ocg_enc_metrics_batch(OCG_MET_SSD, io, prev, ys[k], ei->d_all + first[k], count[k], d_skip + first[k], nullptr, st);
+    if (r == OCG_OK && bcount[k] > 0)
+      r = ocg_enc_metrics_batch(OCG_MET_BORDER_SSD, io, prev, ys[k], ei->d_border + bfirst[k], bcount[k], d_border + bfirst[k], nullptr, st);
+  }
+  if (r != OCG_OK) return r;
+  if (with_cands) {
+    OcgCandJob J;
+    J.mb = ei->me->d_mb;
+    J.mbfrags = ei->d_mbfrags;
+    J.frag_off = ei->d_frag_off;
+    J.out = ei->d_cand;
+    J.nmbs = ei->nmbs;
+    J.nfrags = ei->nfrags;
+    J.nluma = nl;
+    J.ystride_y = ys[0];
+    J.ystride_c = ys[1];
+    J.qx = !(g->pixel_fmt & 1);
+    J.qy = !(g->pixel_fmt & 2);
+    J.fmt = g->pixel_fmt;
+    J.io_off = (int32_t)((int64_t)io_buf * g->ref_frame_sz);
+    J.prev_off = (int32_t)((int64_t)prev_buf * g->ref_frame_sz);
+    J.gold_off = (int32_t)((int64_t)gold_buf * g->ref_frame_sz);
+    ocg_enc_cand_kernel<<<(unsigned)((ei->nmbs + 127) / 128), 128, 0, st>>>(J);
+    ocg_count_launch(1);
+    r = ocg_enc_metrics_batch(OCG_MET_SATD, pool, pool, ys[0], ei->d_cand, K * nl, d_csatd, d_cdc, st);
+    if (r == OCG_OK && nc > 0)
+      r = ocg_enc_metrics_batch(OCG_MET_SATD, pool, pool, ys[1], ei->d_cand + (size_t)K * nl, K * nc, d_csatd + (size_t)K * nl, d_cdc + (size_t)K * nl, st);
+    if (r != OCG_OK) return r;
+  }
+  const size_t small = ei->off_border + ((size_t)(ei->nborder_y + ei->nborder_c) + 1) * 4;
+  if (cudaMemcpyAsync(ei->h_out, ei->d_out, with_cands ? ei->out_sz : small, cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
+  ocg_enc_frag *h_keys = (ocg_enc_frag *)(ei->h_out + ei->out_sz);
+  if (with_cands &&
+      cudaMemcpyAsync(h_keys, ei->d_cand, (size_t)K * ei->nfrags * sizeof(ocg_enc_frag), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    return OCG_ECUDA;
+  out->intra_satd = (const uint32_t *)(ei->h_out + ei->off_isatd);
+  out->intra_dc = (const int32_t *)(ei->h_out + ei->off_idc);
+  out->skip_ssd = (const uint32_t *)(ei->h_out + ei->off_skip);
+  out->border_ssd = (const uint32_t *)(ei->h_out + ei->off_border);
+  out->ncand = with_cands ? K : 0;
+  out->cand = h_keys;
+  out->cand_satd = (const uint32_t *)(ei->h_out + ei->off_csatd);
+  out->cand_dc = (const int32_t *)(ei->h_out + ei->off_cdc);
+  out->nluma = nl;
+  out->nfrags = ei->nfrags;
+  out->d2h_bytes = (long)((with_cands ? ei->out_sz + (size_t)K * ei->nfrags * sizeof(ocg_enc_frag) : small));
   return OCG_OK;
 }
 

@@ -40,6 +40,7 @@ struct OcgJobDev {
   const CUtensorMap  *lf_tmaps;  /* 3 tensor maps (one per plane) of the SELF buffer, or NULL: no TMA path */
   uint32_t            seq;       /* ocg_dec_flush: published in host memory when the frame is complete */
   int32_t             ncoeff_rows; /* ocg_dec_flush: rows to stage in */
+  uint8_t            *host_out;  /* ocg_dec_flush: the device's address of the page-locked destination buffer */
 };
 
 #define OCG_FRAGS_PER_BLOCK 64
@@ -59,10 +60,11 @@ void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, c
 /* flush graph (ocg_dec_flush): lists in / picture out through mapped host memory, kernels only */
 void ocg_launch_stage_in(const OcgJobDev *h_job, OcgJobDev *d_job, const ocg_frag_rec *h_recs, ocg_frag_rec *d_recs,
                          int nfrags, const int16_t *h_rows, int16_t *d_rows, cudaStream_t st);
-void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const uint8_t *src, uint8_t *host_dst, const OcgJobDev *job,
-                         uint32_t *counter, uint32_t *host_flag, cudaStream_t st);
+void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const OcgJobDev *job, uint32_t *counter, uint32_t *host_flag,
+                         cudaStream_t st);
 void ocg_init_device_tables(cudaStream_t st); /* idempotent; call once per context */
 
 void ocg_count_launch(int n);
+cudaError_t ocg_set_device(int device); /* cudaSetDevice unless it is already the thread's device */
 
 #endif

@@ -51,10 +51,13 @@ def main():
             rs = R.refh_decode_time(hr, threads, 1, C.byref(rh))
             assert rs > 0
             refs.append(rs)
+    prep, launch, nfl = C.c_double(), C.c_double(), C.c_long()
+    abi.lib().ocg_flush_profile(C.byref(prep), C.byref(launch), C.byref(nfl), 1)
     ours.sort()
     secs, h2d, d2h, flush, wait = ours[1]
     out = {"secs": secs, "frames": threads * nframes, "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
-           "flush_ms_per_frame": 1e3 * flush, "wait_ms_per_frame": 1e3 * wait, "hash": int(hsh.value), "threads": threads}
+           "flush_ms_per_frame": 1e3 * flush, "wait_ms_per_frame": 1e3 * wait, "hash": int(hsh.value), "threads": threads,
+           "flush_prepare_us": 1e6 * prep.value / max(nfl.value, 1), "graph_launch_us": 1e6 * launch.value / max(nfl.value, 1)}
     if refs:
         out["ref_secs"] = sorted(refs)[1]
         out["ref_hash"] = int(rh.value)

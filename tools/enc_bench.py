@@ -1,6 +1,8 @@
-"""BASELINE configs[2] through th_encode_ycbcr_in / th_encode_packetout, measured in a plain process
-(ctypes only: no torch, no second CUDA client in the process), ours and the reference interleaved.
-Prints one JSON object; bench.py embeds it as `encode_intra`."""
+"""BASELINE configs[2] (kf=1: intra-only) and configs[3] (kf=64, speed level 1: inter frames with the
+motion search) through th_encode_ycbcr_in / th_encode_packetout, measured in a plain process (ctypes only:
+no torch, no second CUDA client in the process), ours and the reference interleaved.
+Usage: enc_bench.py W H quality threads frames [kf [speed]].  Prints one JSON object; bench.py embeds it
+as `encode_intra` / `encode_inter`."""
 import ctypes as C
 import json
 import os
@@ -14,17 +16,20 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 def main():
     width, height, quality, threads, frames = (int(a) for a in sys.argv[1:6])
+    kf = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+    speed = int(sys.argv[7]) if len(sys.argv) > 7 else 1
     import support as S
     from theora_b200 import streams
     Lo = streams.lib()
     kind = "asm" if S.ref_available("asm") else "c"
     R = S.ref(kind)
-    out = {"workload": "%dx%d 4:2:0 intra-only encode (keyframe every frame), q=%d, speed 1, %d timed frames x %d threads"
-           % (width, height, quality, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
+    what = "intra-only encode (keyframe every frame)" if kf == 1 else "encode with inter frames (keyframe every %d, motion search)" % kf
+    out = {"workload": "%dx%d 4:2:0 %s, q=%d, speed %d, %d timed frames x %d threads"
+           % (width, height, what, quality, speed, frames - 1, threads), "host_threads": threads, "unit": "frames/s"}
 
     def one(L):
         h, b = C.c_uint64(), C.c_long()
-        secs = L.refh_encode_time_mt(width, height, frames, quality, 1, 1, 30, 12345, threads, C.byref(h), C.byref(b))
+        secs = L.refh_encode_time_mt(width, height, frames, quality, kf, speed, 30, 12345, threads, C.byref(h), C.byref(b))
         assert secs > 0, "encode failed"
         return secs, h.value, b.value
     st = streams.EncBackendStats()
@@ -45,6 +50,15 @@ def main():
     out["flush_ms_per_frame"] = 1e3 * st.flush_seconds / max(st.frames, 1)
     out["h2d_bytes_per_frame"] = int(st.h2d_bytes / max(st.prepass_frames, 1))
     out["d2h_bytes_per_frame"] = int(st.d2h_bytes / max(st.prepass_frames, 1))
+    if kf > 1:
+        calls = st.satd_lookups + st.satd_host
+        out["motion_analysis"] = {"device_passes": int(st.me_frames), "gold_refinements": int(st.me_gold_refines),
+                                  "gold_searches_redone": int(st.me_repairs)}
+        out["block_metric_calls"] = {"satd_from_device_tables": int(st.satd_lookups), "satd_on_host": int(st.satd_host),
+                                     "satd_table_hit_rate": st.satd_lookups / calls if calls else None,
+                                     "skip_ssd_from_device_table": int(st.ssd_lookups),
+                                     "coded_block_ssd_on_host": int(st.ssd_host),
+                                     "intra_satd_from_device_table": int(st.intra_satd_lookups)}
     out["cpu_baseline"] = {"value": (frames - 1) * threads / rsecs, "cores": threads,
                            "kind": "reference" if kind == "asm" else "reference (C path)"}
     out["timing"] = "median of 3 passes each, ours and the reference interleaved, in a process of its own"
