@@ -123,12 +123,12 @@ def load_peaks():
 
 
 def reference_lib():
-    tdir = os.path.join(ROOT, "tests")  # test infra: the compiled reference lives in oracle/_ref
+    """The compiled, unmodified reference (oracle/_ref) + harness; imports nothing of the product."""
+    tdir = os.path.join(ROOT, "tests")  # test infra
     if tdir not in sys.path:
         sys.path.insert(0, tdir)
-    import support as S
-    kind = "asm" if S.ref_available("asm") else "c"
-    return S.ref(kind), kind
+    import th_harness_abi as HA
+    return HA.load_reference()
 
 
 def stream_handle(L, blob):
@@ -447,13 +447,17 @@ def main():
         workload = "%dx%d 4:2:0 decode, %d synthetic frames (kf=%d, q=%d)" % (args.width, args.height, args.frames,
                                                                                args.kf, args.quality)
 
-    from theora_b200 import streams, workload as wl
+    tdir = os.path.join(ROOT, "tests")
+    if tdir not in sys.path:
+        sys.path.insert(0, tdir)
+    import th_workload as wl
 
     # ------------------------------------------------------------------ reference arm
+    # (loads oracle/_ref only: neither the product library nor the integrated build)
     if args.impl == "reference":
         if RANK != 0:
             return 0
-        blob = wl.synth_stream(args.width, args.height, args.frames, args.quality, args.kf)
+        blob = wl.synth_stream(args.width, args.height, args.frames, args.quality, args.kf, lib=reference_lib()[0])
         vals = []
         for i in range(args.warmup + args.steps):
             fps, secs, kind, _ = time_reference(blob, ncores, 1)
@@ -482,6 +486,7 @@ def main():
     import torch.distributed as dist
     import theora_b200 as T
     from theora_b200 import abi, sharding
+    import th_streams as streams
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
@@ -509,7 +514,8 @@ def main():
     Lo.ocg_backend_set_device(LOCAL_RANK)
     t0 = time.time()
     # resident packs are replayed, so they hold final DC values (DC_HOST, also the e2e default)
-    g, works, outs = streams.capture_stream_work(blob, streams.BACKEND_GPU, dc_mode=streams.DC_HOST)
+    g, works, outs = streams.capture_stream_work(blob, streams.BACKEND_GPU, dc_mode=streams.DC_HOST,
+                                                 expand=streams.EXPAND_REFERENCE)
     works = [w for w in works if w is not None]
     nframes = len(works)
     outs = None

@@ -193,7 +193,7 @@ OCG_API int  ocg_dec_submit(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_
 
 /* The same frame flush as ONE driver call: lists H2D, [DC un-prediction], reconstruction, loop filter,
    borders, copy-back and a completion flag in host memory are a CUDA graph that is instantiated once per
-   (staging slot, SELF buffer, destination) and replayed; ocg_dec_wait polls the flag without entering
+   staging slot and replayed (see ocg_ctx_set_flush_graph); ocg_dec_wait polls the flag without entering
    the driver.  host_out must be page-locked (ocg_host_register) and laid out like the reference's buffer;
    out_mode selects what is copied back.  dc_residual 0 or 1. */
 #define OCG_OUT_PICTURE 0   /* the coded-frame area of the three planes (what th_decode_ycbcr_out exposes) */
@@ -201,9 +201,44 @@ OCG_API int  ocg_dec_submit(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_
 #define OCG_OUT_NONE    2   /* nothing: the frame stays on the device */
 OCG_API int  ocg_dec_flush(ocg_ctx *ctx, const ocg_dec_frame *f, uint8_t *host_out, int out_mode);
 OCG_API int  ocg_dec_wait(ocg_ctx *ctx);   /* until the last ocg_dec_flush has completed */
+/* From which flush on the kernel sequence is replayed as a graph (default 16; earlier flushes are launched
+   kernel by kernel: instantiating a graph only pays off on a stream that lives long enough); < 0: never. */
+OCG_API void ocg_ctx_set_flush_graph(ocg_ctx *ctx, int after);
 /* Host time spent inside ocg_dec_flush since the last reset, process-wide: before the graph launch
    (seconds), inside cudaGraphLaunch (seconds), number of flushes. */
 OCG_API void ocg_flush_profile(double *prepare_s, double *launch_s, long *n, int reset);
+OCG_API void ocg_flush_profile_builds(double *build_s, long *nbuilds); /* graph instantiations so far (never reset) */
+
+/* ---- decode: one frame as the reference's decoder holds it after entropy decoding ------------------------
+    The token -> coefficient walk of oc_dec_frags_recon_mcu_plane (decode.c:1511-1586) runs on
+   the device: the caller hands over the decoder's own arrays -- no per-fragment host work at all.
+   ocg_dec_expand_setup, once per context:
+     coded_order     [nfrags] the fragments of each plane in coded (super-block Hilbert) order, planes back to
+                     back: state.sb_maps walked plane by plane (state.c:200-298)
+     dequant_tables  [64 qi][3 pli][2 qti][64] state.dequant_tables, gathered (AC entries are used)
+     frag_words      state.frags viewed as 32-bit words (state.h:297-322: bit 0 coded, bits 2-5 qii, bits 6-7
+                     refi, bits 8-10 mb_mode, bits 16-31 dc); frag_mvs: state.frag_mvs; dct_tokens:
+                     dec->dct_tokens (decode.c:1000-1190), token_capacity its allocated size.  These three stay
+                     where they are for the life of the context, must be page-locked (ocg_host_register) and
+                     are read in place by the device while a flush is in flight: do not modify them between
+                     ocg_dec_flush_tokens and ocg_dec_wait. */
+typedef struct ocg_dec_tokens {
+  int32_t  ref_idx[3];
+  int32_t  lf_limit;
+  int32_t  intra_frame;
+  int32_t  dc_residual;       /* 0: the words' DC fields are final; 1: residuals, the device undoes the prediction */
+  uint16_t dc_quant[3][2];    /* dequant[pli][0][qti][0] (decode.c:1534) */
+  int32_t  nqis;
+  int32_t  qis[3];            /* state.qis */
+  int32_t  ntoken_bytes;      /* dec->dct_tokens_count */
+  int32_t  ti0[3][64];        /* dec->ti0 */
+  int32_t  eob_runs[3][64];   /* dec->eob_runs, saturated to int32 */
+} ocg_dec_tokens;
+OCG_API int  ocg_dec_expand_setup(ocg_ctx *ctx, const int32_t *coded_order, const uint16_t *dequant_tables,
+                                  const uint32_t *frag_words, const int16_t *frag_mvs, const uint8_t *dct_tokens,
+                                  size_t token_capacity);
+/* As ocg_dec_flush (one graph launch, asynchronous, ocg_dec_wait for completion). */
+OCG_API int  ocg_dec_flush_tokens(ocg_ctx *ctx, const ocg_dec_tokens *t, uint8_t *host_out, int out_mode);
 
 /* ---- decode: device-resident frames, batched over independent streams ---- */
 OCG_API int  ocg_pack_create(ocg_pack **out, const ocg_dec_frame *frames, int nframes, int nfrags,

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import support as S
-from theora_b200 import abi, streams
+from theora_b200 import abi
+import th_streams as streams
 
 G = np.load(os.path.join(S.GOLDEN_DIR, "streams.npz"))
 pytestmark = pytest.mark.skipif(not streams.available(), reason="integrated build not present")

@@ -6,7 +6,7 @@ import ctypes as C
 
 import pytest
 
-from theora_b200 import streams
+import th_streams as streams
 
 pytestmark = pytest.mark.skipif(not streams.available(), reason="needs the integrated build")
 

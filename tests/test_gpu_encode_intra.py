@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 import support as S
-from theora_b200 import streams
+import th_streams as streams
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not (S.ref_available("c") and streams.available()),

@@ -10,7 +10,8 @@ import pytest
 import torch
 
 import support as S
-from theora_b200 import abi, streams
+from theora_b200 import abi
+import th_streams as streams
 
 pytestmark = pytest.mark.gpu
 

@@ -17,7 +17,8 @@ import pytest
 import megen
 import support as S
 import theora_b200 as T
-from theora_b200 import abi, streams
+from theora_b200 import abi
+import th_streams as streams
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not streams.available(), reason="needs the integrated build")]

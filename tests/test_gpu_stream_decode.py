@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import support as S
-from theora_b200 import streams
+import th_streams as streams
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not (S.ref_available("c") and streams.available()),
@@ -23,17 +23,23 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("expand", [streams.EXPAND_DEVICE, streams.EXPAND_REFERENCE])
 @pytest.mark.parametrize("dc_mode", [streams.DC_DEVICE, streams.DC_HOST, streams.DC_DEVICE_AHEAD])
 @pytest.mark.parametrize("case", CASES)
-def test_public_api_decode_matches_reference(case, dc_mode):
-    """DC_DEVICE: DC un-prediction by the wave-front kernel inside the flush graph; DC_DEVICE_AHEAD: the same
-    kernel started ahead of the lists; DC_HOST: on the host, in the hook."""
+def test_public_api_decode_matches_reference(case, dc_mode, expand):
+    """expand EXPAND_DEVICE (the default): the device walks the decoder's token lists (ocg_dec_flush_tokens);
+    EXPAND_REFERENCE: the reference's expansion loop with the per-fragment recorder hook.
+    DC_DEVICE: DC un-prediction by the wave-front kernel inside the flush; DC_DEVICE_AHEAD: the same kernel
+    started ahead of the lists (recorder path only); DC_HOST: on the host, in the hook."""
+    if expand == streams.EXPAND_DEVICE and dc_mode == streams.DC_DEVICE_AHEAD:
+        pytest.skip("the token path undoes the DC prediction inside its flush")
     w, h, n, q, kf, sp, ns = case
     R = S.ref("c")
     st = S.Stream.encode(R, w, h, n, quality=q, kf=kf, speed=sp, noise_shift=ns)
-    g, works, outs = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_GPU, dc_mode=dc_mode)
-    want = {streams.DC_DEVICE: 1, streams.DC_HOST: 0, streams.DC_DEVICE_AHEAD: 2}[dc_mode]
-    assert all(wk is None or wk.dc_residual == want for wk in works)
+    g, works, outs = streams.capture_stream_work(st.to_bytes(), streams.BACKEND_GPU, dc_mode=dc_mode, expand=expand)
+    if expand == streams.EXPAND_REFERENCE:
+        want = {streams.DC_DEVICE: 1, streams.DC_HOST: 0, streams.DC_DEVICE_AHEAD: 2}[dc_mode]
+        assert all(wk is None or wk.dc_residual == want for wk in works)
     dec = S.Decoder(R, st)
     assert len(outs) == n
     for i in range(n):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import support as S
-from theora_b200 import streams
+import th_streams as streams
 
 U = np.load(os.path.join(S.GOLDEN_DIR, "units.npz"))
 G = np.load(os.path.join(S.GOLDEN_DIR, "streams.npz"))

@@ -12,7 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import support as S
-from theora_b200 import sharding, streams
+from theora_b200 import sharding
+import th_streams as streams
 
 G = np.load(os.path.join(S.GOLDEN_DIR, "streams.npz"))
 

@@ -1,5 +1,6 @@
-"""Driver for the integrated library (theora_b200/backend/libth_ocg.so): the
-reference's own th_decode_* host code with the B200 vtable back-end plugged in.
+"""TEST / BENCH PLUMBING (not part of the product package).  Driver for the integrated library
+(theora_b200/backend/libth_ocg.so): the reference's own th_decode_* host code with the B200 vtable
+back-end plugged in, reached through the harness tools/th_harness.c (tools/libth_ocg_harness.so).
 
 Used by the tests and bench.py to (a) decode real Theora packets end to end on
 the GPU through the public API and (b) capture the per-frame block work lists
@@ -11,10 +12,12 @@ import os
 
 import numpy as np
 
-from . import abi
-from .abi import DecFrame, FrameWork, REC_DTYPE, Staging
+from theora_b200 import abi
+from theora_b200.abi import DecFrame, FrameWork, REC_DTYPE, Staging
 
 OCG_LIB = os.path.join(abi.PKG_DIR, "backend", "libth_ocg.so")
+# the test/bench harness (tools/th_harness.c) built against the integrated library: NOT part of it
+OCG_HARNESS = os.path.join(os.path.dirname(abi.PKG_DIR), "tools", "libth_ocg_harness.so")
 BACKEND_GPU, BACKEND_RECORD = 0, 1
 
 CAPTURE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(DecFrame), C.POINTER(Staging))
@@ -37,13 +40,13 @@ class EncBackendStats(C.Structure):
 
 ENC_AUTO, ENC_HOST = 0, 1
 DC_DEVICE, DC_HOST, DC_DEVICE_AHEAD = 0, 1, 2
-EXPAND_BACKEND, EXPAND_REFERENCE = 0, 1
+EXPAND_DEVICE, EXPAND_REFERENCE = 0, 1
 
 _lib = None
 
 
 def available():
-    return os.path.exists(OCG_LIB) and os.path.exists(abi.LIB_PATH)
+    return os.path.exists(OCG_LIB) and os.path.exists(OCG_HARNESS) and os.path.exists(abi.LIB_PATH)
 
 
 def lib():
@@ -54,7 +57,9 @@ def lib():
             raise RuntimeError("%s not built (needs the reference sources at build time): "
                                "make -C theora_b200/backend" % OCG_LIB)
         abi.lib()  # make sure the product library is resolvable first
-        L = C.CDLL(OCG_LIB)
+        # refh_*; th_* and the back-end controls resolve through its dependency on libth_ocg.so (local scope:
+        # the compiled reference under oracle/_ref defines the same th_* names and must keep its own)
+        L = C.CDLL(OCG_HARNESS)
         L.ocg_backend_set_mode.argtypes = [C.c_int]
         L.ocg_backend_set_device.argtypes = [C.c_int]
         L.ocg_backend_set_dc_mode.argtypes = [C.c_int]
@@ -68,39 +73,7 @@ def lib():
     return _lib
 
 
-def _bind_harness(L):
-    L.refh_encode_synth.restype = C.c_void_p
-    L.refh_encode_synth.argtypes = [C.c_int] * 8 + [C.c_uint]
-    L.refh_encode_synth_recon.restype = C.c_void_p
-    L.refh_encode_synth_recon.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_void_p]
-    L.refh_encode_synth_fmt.restype = C.c_void_p
-    L.refh_encode_synth_fmt.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_int, C.c_void_p]
-    L.refh_encode_time_mt.restype = C.c_double
-    L.refh_encode_time_mt.argtypes = [C.c_int] * 7 + [C.c_uint, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_long)]
-    L.refh_stream_free.argtypes = [C.c_void_p]
-    L.refh_stream_npackets.argtypes = [C.c_void_p]
-    L.refh_stream_packet_size.argtypes = [C.c_void_p, C.c_int]
-    L.refh_stream_packet_size.restype = C.c_long
-    L.refh_stream_blob_size.argtypes = [C.c_void_p]
-    L.refh_stream_blob_size.restype = C.c_long
-    L.refh_stream_to_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
-    L.refh_stream_to_blob.restype = C.c_long
-    L.refh_stream_from_blob.argtypes = [C.c_void_p, C.c_long]
-    L.refh_stream_from_blob.restype = C.c_void_p
-    L.refh_stream_append_data.argtypes = [C.c_void_p, C.c_void_p]
-    L.refh_dec_open.restype = C.c_void_p
-    L.refh_dec_open.argtypes = [C.c_void_p]
-    L.refh_dec_close.argtypes = [C.c_void_p]
-    L.refh_dec_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
-    L.refh_dec_next.argtypes = [C.c_void_p]
-    L.refh_dec_rewind.argtypes = [C.c_void_p]
-    L.refh_dec_set_pplevel.argtypes = [C.c_void_p, C.c_int]
-    L.refh_dec_hash.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    L.refh_dec_copy_frame.argtypes = [C.c_void_p, C.c_void_p]
-    L.refh_dec_copy_frame.restype = C.c_long
-    L.refh_decode_time.restype = C.c_double
-    L.refh_decode_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
-    return L
+from th_harness_abi import bind_harness as _bind_harness  # noqa: E402
 
 
 def _copy(ptr, nbytes, dtype):
@@ -134,14 +107,20 @@ class Capture:
         lib().ocg_backend_set_capture(C.cast(None, CAPTURE_FN), None)
 
 
-def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None, dc_mode=DC_HOST):
+def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None, dc_mode=DC_HOST, expand=None):
     """Decodes `stream_blob` (tools/th_harness.c serialisation) through the
     integrated library and returns (info, [FrameWork per decoded frame],
     [decoded frame bytes per frame or None in record mode]).  dc_mode: DC_DEVICE
-    = the lists carry DC residuals (FrameWork.dc_residual), DC_HOST = final DCs."""
+    = the lists carry DC residuals (FrameWork.dc_residual), DC_HOST = final DCs.
+    expand: EXPAND_REFERENCE = the host records per-fragment lists (what FrameWork holds);
+    EXPAND_DEVICE (the product default on the GPU) = the device walks the token lists itself, there are no
+    host lists and every FrameWork is None.  Default: lists in record mode, the product path on the GPU."""
     L = lib()
+    if expand is None:
+        expand = EXPAND_REFERENCE if mode == BACKEND_RECORD else EXPAND_DEVICE
     L.ocg_backend_set_mode(mode)
     L.ocg_backend_set_dc_mode(dc_mode)
+    L.ocg_backend_set_expand_mode(expand)
     buf = (C.c_uint8 * len(stream_blob)).from_buffer_copy(stream_blob)
     sh = L.refh_stream_from_blob(buf, len(stream_blob))
     assert sh, "bad stream blob"
@@ -157,7 +136,8 @@ def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None, dc_mo
     g = abi.Geometry()
     abi.check(abi.lib().ocg_geometry_init(C.byref(g), fw, fh, fmt, 3))
     cap = Capture(g.nfrags)
-    cap.install()
+    if expand == EXPAND_REFERENCE:
+        cap.install()
     outs = []
     try:
         n = 0
@@ -167,7 +147,7 @@ def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None, dc_mo
             if ret == 1000:
                 break
             assert ret >= 0, "th_decode_packetin returned %d" % ret
-            if len(cap.frames) == before:  # TH_DUPFRAME: nothing to flush
+            if len(cap.frames) == before:  # TH_DUPFRAME: nothing to flush / no host lists
                 cap.frames.append(None)
             if mode == BACKEND_GPU:
                 cw = fw >> (0 if fmt & 1 else 1)
@@ -184,4 +164,5 @@ def capture_stream_work(stream_blob, mode=BACKEND_RECORD, max_frames=None, dc_mo
         L.refh_stream_free(sh)
         L.ocg_backend_set_mode(BACKEND_GPU)
         L.ocg_backend_set_dc_mode(DC_HOST)
+        L.ocg_backend_set_expand_mode(EXPAND_DEVICE)
     return g, cap.frames, outs

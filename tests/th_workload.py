@@ -1,4 +1,4 @@
-"""Synthetic benchmark workload: a deterministic
+"""TEST / BENCH PLUMBING (not part of the product package).  Synthetic benchmark workload: a deterministic
 1080p/2160p 4:2:0 Theora stream produced by the reference ENCODER host code in
 the integrated library (C kernels; input synthesis, never timed), GOP segments
 encoded in parallel and cached under /tmp.  Used by bench.py and the tests."""
@@ -7,7 +7,6 @@ import ctypes as C
 import hashlib
 import os
 
-from . import streams
 
 CACHE_DIR = os.environ.get("THEORA_B200_CACHE", "/tmp/theora_b200_cache")
 
@@ -26,7 +25,11 @@ def synth_stream(w=1920, h=1080, nframes=300, quality=32, kf=64, speed=1, noise_
     same headers).  The result is a valid stream with ceil(nframes/kf) intra
     frames; it is not byte-identical to a serial encode (rate-control history
     differs), which does not matter for a decode workload."""
-    L = lib or streams.lib()
+    if lib is None:
+        import th_streams as streams
+        L = streams.lib()
+    else:
+        L = lib
     path = os.path.join(CACHE_DIR, "synth_%s.ogs" % _key(w, h, nframes, quality, kf, speed, noise_shift, seed))
     if use_cache and os.path.exists(path):
         with open(path, "rb") as f:
@@ -41,14 +44,15 @@ def synth_stream(w=1920, h=1080, nframes=300, quality=32, kf=64, speed=1, noise_
 
     # stream synthesis is tooling: keep the reference's host encoder even for
     # intra-only streams (the device encoder is what tests/bench measure)
-    if hasattr(L, "ocg_backend_set_enc_mode"):
-        L.ocg_backend_set_enc_mode(streams.ENC_HOST)
+    integrated = lib is None
+    if integrated:
+        L.ocg_backend_set_enc_mode(1)  # OCG_ENC_HOST
     try:
         with cf.ThreadPoolExecutor(max_workers=threads) as ex:
             handles = list(ex.map(enc, segs))
     finally:
-        if hasattr(L, "ocg_backend_set_enc_mode"):
-            L.ocg_backend_set_enc_mode(streams.ENC_AUTO)
+        if integrated:
+            L.ocg_backend_set_enc_mode(0)  # OCG_ENC_AUTO
     first = handles[0]
     for hnd in handles[1:]:
         L.refh_stream_append_data(first, hnd)

@@ -152,6 +152,10 @@ _PROTOS = {
     "ocg_dec_submit": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p]),
     "ocg_dec_flush": (C.c_int, [C.c_void_p, C.POINTER(DecFrame), C.c_void_p, C.c_int]),
     "ocg_dec_wait": (C.c_int, [C.c_void_p]),
+    "ocg_dec_expand_setup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ocg_dec_flush_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "ocg_ctx_set_flush_graph": (None, [C.c_void_p, C.c_int]),
+    "ocg_flush_profile_builds": (None, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "ocg_flush_profile": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),
     "ocg_pack_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecFrame), C.c_int, C.c_int, C.c_int]),
     "ocg_pack_destroy": (None, [C.c_void_p]),

@@ -41,9 +41,6 @@ int oc_refimpl_decode_ycbcr_out(th_dec_ctx *_dec, th_ycbcr_buffer _ycbcr);
 void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_dec_host.c */
 void oc_state_accel_init_ocg(oc_theora_state *_state);
 void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli); /* ocg_dec_host.c */
-int ocg_host_expand_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli, ptrdiff_t _ncoded,
-                              ptrdiff_t _nuncoded, ocg_frag_rec *_recs, ogg_int16_t *_rows, int _nrows0,
-                              ogg_uint16_t _dcq_out[2], unsigned *_stray); /* ocg_dec_host.c */
 
 typedef struct ocg_backend {
   th_dec_ctx        *dec;
@@ -61,29 +58,30 @@ typedef struct ocg_backend {
   unsigned char      dev_valid[6];
   int                pinned;
   int                dc_device;   /* DC prediction is undone on the device (records carry residuals) */
-  int                expand;      /* the back-end expands the tokens itself (ocg_host_expand_mcu_plane) */
-  unsigned           stray;       /* see ocg_host_expand_mcu_plane */
+  int                expand;      /* the device expands the tokens (ocg_dec_flush_tokens): the hooks record nothing */
+  int                regs;        /* bit i: host array i (frags, frag_mvs, dct_tokens) is page-locked by us */
   int                dc_ahead;    /* ocg_dec_dc_begin was called for the frame being assembled */
   int                dc_ahead_used;
   int                pending;     /* a flushed frame's kernels / copy-back may still be running */
   int                failed;      /* a device call failed: the decoder is unusable, the API returns TH_EFAULT */
   int                out_mode;
   th_stripe_callback user_cb;
+  ocg_backend_stats  stats;       /* this decoder's share; summed by ocg_backend_get_stats (no shared lock per frame) */
   struct ocg_backend *next;
 } ocg_backend;
 
+static void backend_unregister(ocg_backend *b);
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static ocg_backend *g_list;
 static int g_mode = OCG_BACKEND_GPU;
 static int g_dc_mode = OCG_DC_HOST;
-static int g_expand_mode = OCG_EXPAND_BACKEND;
+static int g_expand_mode = OCG_EXPAND_DEVICE;
 static int g_out_mode = OCG_OUT_PICTURE;
 static ocg_capture_fn g_capture;
 static void *g_capture_user;
 static int g_device; /* one process per GPU: process-wide */
 static __thread ocg_backend *t_cur;
-static ocg_backend_stats g_stats; /* process-wide, updated with atomics */
-static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
+static ocg_backend_stats g_stats_retired; /* of decoders that no longer exist; under g_lock */
 
 OCG_API void ocg_backend_set_mode(int mode) { g_mode = mode; }
 OCG_API void ocg_backend_set_device(int device) { g_device = device; }
@@ -91,11 +89,31 @@ OCG_API void ocg_backend_set_dc_mode(int mode) { g_dc_mode = mode; }
 OCG_API void ocg_backend_set_expand_mode(int mode) { g_expand_mode = mode; }
 OCG_API void ocg_backend_set_output_mode(int mode) { g_out_mode = mode; }
 OCG_API void ocg_backend_set_capture(ocg_capture_fn fn, void *user) { g_capture = fn; g_capture_user = user; }
+static void stats_sum(ocg_backend_stats *a, const ocg_backend_stats *b) {
+  a->frames += b->frames;
+  a->coded_frags += b->coded_frags;
+  a->uncoded_frags += b->uncoded_frags;
+  a->coeff_rows += b->coeff_rows;
+  a->h2d_bytes += b->h2d_bytes;
+  a->d2h_bytes += b->d2h_bytes;
+  a->flush_seconds += b->flush_seconds;
+  a->wait_seconds += b->wait_seconds;
+}
+
+/* Every decoder counts for itself (its own thread, no lock on the per-frame path); the totals are put
+   together here.  Call it while no decoder is inside th_decode_packetin for exact figures. */
 OCG_API void ocg_backend_get_stats(ocg_backend_stats *out, int reset) {
-  pthread_mutex_lock(&g_stats_lock);
-  if (out) *out = g_stats;
-  if (reset) memset(&g_stats, 0, sizeof(g_stats));
-  pthread_mutex_unlock(&g_stats_lock);
+  ocg_backend *b;
+  ocg_backend_stats t;
+  pthread_mutex_lock(&g_lock);
+  t = g_stats_retired;
+  for (b = g_list; b != NULL; b = b->next) stats_sum(&t, &b->stats);
+  if (reset) {
+    memset(&g_stats_retired, 0, sizeof(g_stats_retired));
+    for (b = g_list; b != NULL; b = b->next) memset(&b->stats, 0, sizeof(b->stats));
+  }
+  pthread_mutex_unlock(&g_lock);
+  if (out) *out = t;
 }
 
 static double now_s(void) {
@@ -136,22 +154,18 @@ static void backend_wait(ocg_backend *b) {
     double t0 = now_s();
     b->pending = 0;
     if ((b->dc_ahead_used ? ocg_ctx_sync(b->ctx) : ocg_dec_wait(b->ctx)) < 0) { backend_fail(b, "waiting for the frame failed"); return; }
-    pthread_mutex_lock(&g_stats_lock);
-    g_stats.wait_seconds += now_s() - t0;
-    pthread_mutex_unlock(&g_stats_lock);
+    b->stats.wait_seconds += now_s() - t0;
   }
 }
 
-static void stats_add(const ocg_backend *b, long h2d, long d2h, double secs) {
-  pthread_mutex_lock(&g_stats_lock);
-  g_stats.frames++;
-  g_stats.coded_frags += b->ncoded;
-  g_stats.uncoded_frags += b->geom.nfrags - b->ncoded;
-  g_stats.coeff_rows += b->nrows;
-  g_stats.h2d_bytes += h2d;
-  g_stats.d2h_bytes += d2h;
-  g_stats.flush_seconds += secs;
-  pthread_mutex_unlock(&g_stats_lock);
+static void stats_add(ocg_backend *b, long h2d, long d2h, double secs) {
+  b->stats.frames++;
+  b->stats.coded_frags += b->ncoded;
+  b->stats.uncoded_frags += b->geom.nfrags - b->ncoded;
+  b->stats.coeff_rows += b->nrows;
+  b->stats.h2d_bytes += h2d;
+  b->stats.d2h_bytes += d2h;
+  b->stats.flush_seconds += secs;
 }
 
 /* ---- frame life cycle ---------------------------------------------------- */
@@ -161,9 +175,8 @@ static void backend_begin_frame(ocg_backend *b) {
   /* staging records keep buf_off/plane from context creation; every fragment
      is visited once per frame by exactly one of the recon and copy-list hooks
      (decode.c:1584,1601), which refresh the rest */
-  if (b->ctx != NULL && ocg_dec_staging(b->ctx, &b->st) < 0) { backend_fail(b, "ocg_dec_staging failed"); return; }
+  if (b->ctx != NULL && !b->expand && ocg_dec_staging(b->ctx, &b->st) < 0) { backend_fail(b, "ocg_dec_staging failed"); return; }
   b->ncoded = b->nrows = 0;
-  b->stray = 0;
   /* decode.c:2790-2794 has already picked SELF; GOLD/PREV are still the
      references this frame predicts from (they rotate at 2947-2962). */
   for (i = 0; i < 3; i++) b->ref_idx[i] = st->ref_frame_idx[i];
@@ -195,7 +208,7 @@ static void backend_flush(ocg_backend *b) {
   b->dc_ahead_used = b->dc_ahead;
   b->dc_ahead = 0;
   b->frame_open = 0;
-  if (g_capture != NULL) (*g_capture)(g_capture_user, &f, &b->st);
+  if (g_capture != NULL && !b->expand) (*g_capture)(g_capture_user, &f, &b->st);
   if (b->ctx == NULL) { stats_add(b, 0, 0, 0.0); return; } /* record mode */
   {
     const int self = f.ref_idx[OCG_FRAME_SELF];
@@ -227,6 +240,29 @@ static void backend_flush(ocg_backend *b) {
       r = b->out_mode == OCG_OUT_PADDED ? ocg_ctx_download_frame(b->ctx, self, host_self)
                                         : ocg_ctx_download_picture(b->ctx, self, host_self);
       if (r < 0) { backend_fail(b, "frame copy-back failed"); return; }
+    } else if (b->expand) {
+      /* the frame as the entropy decoder left it (decode.c:2822): the device does the rest */
+      const oc_dec_ctx *dec = b->dec;
+      ocg_dec_tokens t;
+      int pli, zzi;
+      memset(&t, 0, sizeof(t));
+      for (i = 0; i < 3; i++) t.ref_idx[i] = f.ref_idx[i];
+      t.lf_limit = f.lf_limit;
+      t.intra_frame = f.intra_frame;
+      t.dc_residual = b->dc_device ? 1 : 0;
+      t.nqis = st->nqis;
+      for (i = 0; i < 3; i++) t.qis[i] = st->qis[i < st->nqis ? i : 0];
+      for (pli = 0; pli < 3; pli++) {
+        for (k = 0; k < 2; k++) t.dc_quant[pli][k] = st->dequant_tables[st->qis[0]][pli][k][0]; /* decode.c:1366, 1534 */
+        for (zzi = 0; zzi < 64; zzi++) {
+          const ptrdiff_t e = dec->eob_runs[pli][zzi];
+          t.ti0[pli][zzi] = (ogg_int32_t)dec->ti0[pli][zzi];
+          t.eob_runs[pli][zzi] = e < 0 || e > 0x40000000 ? 0x40000000 : (ogg_int32_t)e;
+        }
+      }
+      t.ntoken_bytes = dec->dct_tokens_count;
+      if (ocg_dec_flush_tokens(b->ctx, &t, host_self, b->out_mode) < 0) { backend_fail(b, "ocg_dec_flush_tokens failed"); return; }
+      extra_h2d += (long)b->geom.nfrags * 6 + t.ntoken_bytes - (long)b->geom.nfrags * 16;
     } else if (ocg_dec_flush(b->ctx, &f, host_self, b->out_mode) < 0) { backend_fail(b, "ocg_dec_flush failed"); return; }
     d2h = b->out_mode == OCG_OUT_PADDED ? (long)b->geom.ref_frame_sz : ocg_picture_bytes(&b->geom);
     b->pending = 1;
@@ -268,7 +304,7 @@ static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *
     for (; fragi < end; fragi++) ncoded += frags[fragi].coded;
     _pipe->ncoded_fragis[_pli] = ncoded;
     _pipe->nuncoded_fragis[_pli] = (fragy_end - fragy0) * (ptrdiff_t)fplane->nhfrags - ncoded;
-  } else if (b != NULL && b->expand) {
+  } else if (b != NULL) {
     ocg_host_dc_unpredict_mcu_plane(_dec, _pipe, _pli); /* same contract, restated for speed */
   } else {
     oc_dec_dc_unpredict_mcu_plane_c(_dec, _pipe, _pli);
@@ -276,14 +312,10 @@ static void ocg_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *
   if (b != NULL && !b->frame_open) backend_begin_frame(b);
   if (b != NULL && b->failed) return;
   if (b != NULL && b->expand) {
-    /* claim the MCU's fragments: expand their tokens straight into the flush lists and leave
-       oc_dec_frags_recon_mcu_plane (decode.c:1511) an empty range */
-    const ptrdiff_t ncoded = _pipe->ncoded_fragis[_pli], nuncoded = _pipe->nuncoded_fragis[_pli];
-    ogg_uint16_t dcq[2];
-    b->nrows += ocg_host_expand_mcu_plane(_dec, _pipe, _pli, ncoded, nuncoded, b->st.recs, b->st.coeff_rows, b->nrows,
-                                          dcq, &b->stray);
-    if (ncoded > 0) { b->dcq[_pli][0] = dcq[0]; b->dcq[_pli][1] = dcq[1]; }
-    b->ncoded += (int)ncoded;
+    /* The device walks the token lists itself (ocg_dec_flush_tokens): this hook owns the trip count of the
+       reference's expansion loop (it computes pipe->ncoded_fragis / nuncoded_fragis, decode.c:1496-1499),
+       so it leaves oc_dec_frags_recon_mcu_plane (decode.c:1511) an empty range. */
+    b->ncoded += (int)_pipe->ncoded_fragis[_pli];
     _pipe->ncoded_fragis[_pli] = 0;
     _pipe->nuncoded_fragis[_pli] = 0;
   }
@@ -390,15 +422,72 @@ static void backend_destroy(ocg_backend *b) {
   pthread_mutex_lock(&g_lock);
   for (pp = &g_list; *pp != NULL && *pp != b; pp = &(*pp)->next) {}
   if (*pp == b) *pp = b->next;
+  stats_sum(&g_stats_retired, &b->stats);
   pthread_mutex_unlock(&g_lock);
   if (t_cur == b) t_cur = NULL;
   if (b->ctx != NULL) {
     ocg_ctx_sync(b->ctx);
+    backend_unregister(b);
     if (b->pinned) ocg_host_unregister(b->dec->state.ref_frame_handle);
     ocg_ctx_destroy(b->ctx);
   }
   free(b->heap_staging);
   free(b);
+}
+
+/* ---- device-side token expansion: one-time set-up ------------------------------------------------- */
+static void backend_unregister(ocg_backend *b) {
+  oc_theora_state *st = &b->dec->state;
+  if (b->regs & 1) ocg_host_unregister(st->frags);
+  if (b->regs & 2) ocg_host_unregister(st->frag_mvs);
+  if (b->regs & 4) ocg_host_unregister(b->dec->dct_tokens);
+  b->regs = 0;
+}
+
+static int backend_expand_setup(ocg_backend *b) {
+  oc_dec_ctx *dec = b->dec;
+  oc_theora_state *st = &dec->state;
+  const size_t nf = (size_t)st->nfrags, token_cap = (64 + 64 + 1) * nf; /* decode.c:386 */
+  ogg_int32_t *order = (ogg_int32_t *)malloc(nf * sizeof(*order));
+  ogg_uint16_t *deq = (ogg_uint16_t *)malloc(64 * 3 * 2 * 64 * sizeof(*deq));
+  size_t n = 0;
+  unsigned sbi;
+  int qi, pli, qti, quadi, bi, r = -1;
+  oc_fragment probe;
+  ogg_uint32_t w = 0;
+  /* the device reads oc_fragment as a 32-bit word (state.h:297-322 as this compiler lays the bit-fields out) */
+  memset(&probe, 0, sizeof(probe));
+  probe.coded = 1; probe.qii = 5; probe.refi = 2; probe.mb_mode = 6; probe.dc = -3;
+  if (sizeof(probe) == 4) memcpy(&w, &probe, 4);
+  if (order == NULL || deq == NULL || sizeof(probe) != 4 ||
+      w != (1u | 5u << 2 | 2u << 6 | 6u << 8 | 0xFFFDu << 16) || sizeof(st->frag_mvs[0]) != 2) {
+    free(order);
+    free(deq);
+    return -1;
+  }
+  /* coded order: super blocks of a plane in raster order, Hilbert order inside (decode.c:548-600, 626-700) */
+  for (sbi = 0; sbi < st->nsbs; sbi++)
+    for (quadi = 0; quadi < 4; quadi++)
+      for (bi = 0; bi < 4; bi++) {
+        const ptrdiff_t fragi = st->sb_maps[sbi][quadi][bi];
+        if (fragi >= 0 && n < nf) order[n++] = (ogg_int32_t)fragi;
+      }
+  for (qi = 0; qi < 64; qi++)
+    for (pli = 0; pli < 3; pli++)
+      for (qti = 0; qti < 2; qti++)
+        memcpy(deq + (((size_t)qi * 3 + pli) * 2 + qti) * 64, st->dequant_tables[qi][pli][qti], 64 * sizeof(*deq));
+  if (n == nf) {
+    if (ocg_host_register(st->frags, nf * sizeof(st->frags[0])) == 0) b->regs |= 1;
+    if (ocg_host_register(st->frag_mvs, nf * sizeof(st->frag_mvs[0])) == 0) b->regs |= 2;
+    if (ocg_host_register(dec->dct_tokens, token_cap) == 0) b->regs |= 4;
+    if (b->regs == 7)
+      r = ocg_dec_expand_setup(b->ctx, order, deq, (const ogg_uint32_t *)st->frags, (const ogg_int16_t *)st->frag_mvs,
+                               dec->dct_tokens, token_cap);
+    if (r < 0) backend_unregister(b);
+  }
+  free(order);
+  free(deq);
+  return r;
 }
 
 void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
@@ -427,11 +516,12 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
     free(b);
     return;
   }
-  b->expand = g_expand_mode == OCG_EXPAND_BACKEND;
+  /* the token walk moves to the device unless someone wants to see the lists (capture hook, record mode) */
+  b->expand = g_expand_mode == OCG_EXPAND_DEVICE && b->mode == OCG_BACKEND_GPU && g_capture == NULL;
   b->out_mode = g_out_mode;
   b->dc_device = (g_dc_mode == OCG_DC_DEVICE || g_dc_mode == OCG_DC_DEVICE_AHEAD) &&
                  (b->mode != OCG_BACKEND_GPU || ocg_dc_unpredict_supported(&b->geom));
-  if (b->dc_device && g_dc_mode == OCG_DC_DEVICE_AHEAD) b->dc_device = 2;
+  if (b->dc_device && g_dc_mode == OCG_DC_DEVICE_AHEAD && !b->expand) b->dc_device = 2;
   if (b->dc_device && b->mode == OCG_BACKEND_GPU) {
     /* the device reads oc_fragment as a 32-bit word: bit 0 coded, bits 6-7 refi, bits 16-31 dc (state.h:297-322
        as this compiler lays the bit-fields out); verify instead of assuming */
@@ -449,6 +539,21 @@ void oc_dec_accel_init_ocg(th_dec_ctx *_dec) {
       return; /* th_decode_alloc (below) reports the failure; there is no CPU fallback */
     }
     b->pinned = ocg_host_register(st->ref_frame_handle, (size_t)b->geom.ref_frame_sz * 3) == 0;
+    if (!b->pinned) {
+      /* the flush writes the finished frame straight into the decoder's own buffer */
+      fprintf(stderr, "theora_b200 back-end: cannot page-lock the frame buffers (%s)\n", ocg_last_error());
+      ocg_ctx_destroy(b->ctx);
+      free(b);
+      return;
+    }
+    if (b->expand && backend_expand_setup(b) < 0) {
+      fprintf(stderr, "theora_b200 back-end: %s\n", ocg_last_error());
+      backend_unregister(b);
+      ocg_host_unregister(st->ref_frame_handle);
+      ocg_ctx_destroy(b->ctx);
+      free(b);
+      return;
+    }
   } else {
     size_t nf = (size_t)b->geom.nfrags, i;
     unsigned char *p = (unsigned char *)malloc(nf * (16 + 16 + 128) + 64);
@@ -497,6 +602,9 @@ th_dec_ctx *th_decode_alloc(const th_info *_info, const th_setup_info *_setup) {
 int th_decode_packetin(th_dec_ctx *_dec, const ogg_packet *_op, ogg_int64_t *_granpos) {
   ocg_backend *b = _dec != NULL ? backend_of(_dec) : NULL;
   int ret;
+  if (b != NULL && b->failed) return TH_EFAULT;
+  /* the device reads frags[] / frag_mvs[] / dct_tokens[] in place while a flush is in flight */
+  if (b != NULL && b->expand) backend_wait(b);
   if (b != NULL && b->failed) return TH_EFAULT;
   ret = oc_refimpl_decode_packetin(_dec, _op, _granpos);
   if (b != NULL && b->failed) return TH_EFAULT;

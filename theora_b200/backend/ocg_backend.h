@@ -37,11 +37,12 @@ OCG_API void ocg_backend_set_device(int device);  /* CUDA device for decoders al
 OCG_API void ocg_backend_set_dc_mode(int mode);   /* applies to decoders allocated afterwards */
 
 /* Who expands a coded fragment's tokens into coefficients (decode.c:1531-1586):
-   OCG_EXPAND_BACKEND (default): the back-end, inside the dc_unpredict_mcu_plane hook, straight into the
-   pinned flush lists (ocg_host_expand_mcu_plane); oc_dec_frags_recon_mcu_plane is left an empty range.
-   OCG_EXPAND_REFERENCE: the reference's loop, one state_frag_recon hook call per fragment (the recorder
-   then re-finds, copies and clears the non-zero rows).  Identical lists either way. */
-#define OCG_EXPAND_BACKEND   0
+   OCG_EXPAND_DEVICE (default): the device (ocg_dec_flush_tokens): the decoder's fragment words, vectors and
+   token lists are read in place and nothing is recorded per fragment on the host.
+   OCG_EXPAND_REFERENCE: the reference's loop, one state_frag_recon hook call per fragment, which records a
+   16-byte record and the non-zero coefficient rows (what the capture hook and record mode hand out; also
+   used whenever a capture hook is installed). */
+#define OCG_EXPAND_DEVICE    0
 #define OCG_EXPAND_REFERENCE 1
 OCG_API void ocg_backend_set_expand_mode(int mode);   /* applies to decoders allocated afterwards */
 

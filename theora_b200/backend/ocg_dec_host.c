@@ -1,7 +1,7 @@
 /* ocg_dec_host.c -- host-side pieces of the record-and-flush decoder back-end
  * that need decode.c's file-static tables and functions:
  *   (1) out-of-loop post-processing (TH_DECCTL_SET_PPLEVEL > 0);
- *   (2) the recorder's own token -> coefficient-row expansion.
+ *   (2) the hook's DC un-prediction and its self-test against the reference routine.
  *
  * (1)
  * The de-blocking / de-ringing filters (decode.c:1609-1957) are non-normative,
@@ -43,113 +43,7 @@ void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi) {
   }
 }
 
-/* (2) Token expansion straight into the flush lists.
- *
- * The reference expands a fragment's tokens into pipe->dct_coeffs[64]
- * (decode.c:1531-1586) and hands the block to the state_frag_recon hook, whose
- * recorder then has to find the non-zero rows again, copy them and clear the
- * block.  The hook that runs just before that loop, dc_unpredict_mcu_plane, owns
- * the loop's trip count (it computes pipe->ncoded_fragis / nuncoded_fragis,
- * decode.c:1496-1499): the back-end claims the MCU's fragments there -- it
- * expands them itself, directly into the pinned records and coefficient rows,
- * advances the pipeline's list cursors the way decode.c:1587,1600 would, and
- * reports zero fragments left, so oc_dec_frags_recon_mcu_plane has nothing to
- * do.  Same token cursors (pipe->ti, pipe->eob_runs), same dequantisation, same
- * zig-zag table; the static token code-word table and its field macros are the
- * reference's own (this translation unit includes decode.c).
- * ncoded / nuncoded: the counts dc_unpredict_mcu_plane produced for this MCU.
- * Returns the number of 8-coefficient rows appended at rows + 8*nrows0. */
-int ocg_host_expand_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli, ptrdiff_t _ncoded,
-                              ptrdiff_t _nuncoded, ocg_frag_rec *_recs, ogg_int16_t *_rows, int _nrows0,
-                              ogg_uint16_t _dcq_out[2], unsigned *_stray) {
-  const unsigned char *dct_tokens = _dec->dct_tokens;
-  const unsigned char *dct_fzig_zag = _dec->state.opt_data.dct_fzig_zag;
-  const oc_fragment *frags = _dec->state.frags;
-  const oc_mv *frag_mvs = _dec->state.frag_mvs;
-  const ptrdiff_t *coded_fragis = _pipe->coded_fragis[_pli];
-  ptrdiff_t *ti = _pipe->ti[_pli];
-  ptrdiff_t *eob_runs = _pipe->eob_runs[_pli];
-  /* the pipeline's own block buffer (zero at frame start, decode.c:1385; entries 64.. swallow
-     writes past the block): what a transform's footprint does not cover stays in it for the next
-     block, exactly as with the per-block hook */
-  ogg_int16_t *blk = _pipe->dct_coeffs;
-  ogg_int16_t *out = _rows + (size_t)_nrows0 * 8;
-  unsigned stray = *_stray; /* rows holding left-overs from outside an earlier footprint */
-  ptrdiff_t fragii;
-  int nrows = _nrows0, r;
-  for (fragii = 0; fragii < _ncoded; fragii++) {
-    const ptrdiff_t fragi = coded_fragis[fragii];
-    const int qti = frags[fragi].mb_mode != OC_MODE_INTRA;
-    const ogg_uint16_t *ac_quant = _pipe->dequant[_pli][frags[fragi].qii][qti];
-    ocg_frag_rec *rec = _recs + fragi;
-    unsigned touched = 0, foot, scan; /* rows written by this fragment's tokens */
-    int last_zzi = 0, zzi, mask = 0;
-    for (zzi = 0; zzi < 64;) {
-      last_zzi = zzi;
-      if (eob_runs[zzi]) { eob_runs[zzi]--; break; }
-      else {
-        ptrdiff_t eob, lti = ti[zzi];
-        int token = dct_tokens[lti++], cw = OC_DCT_CODE_WORD[token], rlen, coeff, nat;
-        if (OC_DCT_TOKEN_NEEDS_MORE(token)) cw += dct_tokens[lti++] << OC_DCT_TOKEN_EB_POS(token);
-        eob = cw >> OC_DCT_CW_EOB_SHIFT & 0xFFF;
-        if (token == OC_DCT_TOKEN_FAT_EOB) {
-          eob += dct_tokens[lti++] << 8;
-          if (eob == 0) eob = OC_DCT_EOB_FINISH;
-        }
-        rlen = (unsigned char)(cw >> OC_DCT_CW_RLEN_SHIFT);
-        cw ^= -(cw & 1 << OC_DCT_CW_FLIP_BIT);
-        coeff = cw >> OC_DCT_CW_MAG_SHIFT;
-        eob_runs[zzi] = eob;
-        ti[zzi] = lti;
-        zzi += rlen;
-        nat = dct_fzig_zag[zzi];
-        blk[nat] = (ogg_int16_t)(coeff * (int)ac_quant[zzi]);
-        touched |= 1u << (nat >> 3);
-        zzi += !eob;
-      }
-    }
-    blk[0] = 0; /* the DC travels in the record (decode.c:1581) */
-    rec->coeff_row = (ogg_uint32_t)nrows;
-    /* footprint of the transform the reference would run (state.c:967, idct.c:327-329) */
-    foot = last_zzi < 2 ? 0u : (last_zzi <= 3 ? 0x03u : (last_zzi <= 10 ? 0x0Fu : 0xFFu));
-    scan = (touched | stray) & foot;
-    stray = (stray | (touched & 0xFFu)) & ~foot;
-    for (r = 0; scan != 0; r++, scan >>= 1) {
-      ogg_uint64_t a, c;
-      if (!(scan & 1)) continue;
-      memcpy(&a, blk + r * 8, 8);
-      memcpy(&c, blk + r * 8 + 4, 8);
-      if ((a | c) != 0) {
-        memcpy(out, &a, 8);
-        memcpy(out + 4, &c, 8);
-        out += 8;
-        nrows++;
-        mask |= 1 << r;
-        memset(blk + r * 8, 0, 16);
-      }
-    }
-    rec->mv = frag_mvs[fragi];
-    rec->dc = (ogg_int16_t)frags[fragi].dc;
-    rec->rowmask = (unsigned char)mask;
-    rec->last_zzi = (unsigned char)last_zzi;
-    rec->refi = (unsigned char)frags[fragi].refi;
-    rec->pli_qti = (unsigned char)(_pli | qti << 2);
-  }
-  *_stray = stray;
-  for (r = 0; r < 2; r++) _dcq_out[r] = _pipe->dequant[_pli][0][r][0];
-  /* what decode.c:1587 and 1600-1605 do to the list cursors */
-  _pipe->coded_fragis[_pli] += _ncoded;
-  if (_nuncoded > 0) {
-    const ptrdiff_t *unc;
-    ptrdiff_t i;
-    _pipe->uncoded_fragis[_pli] -= _nuncoded;
-    unc = _pipe->uncoded_fragis[_pli];
-    for (i = 0; i < _nuncoded; i++) _recs[unc[i]].refi = OCG_FRAG_UNCODED;
-  }
-  return nrows - _nrows0;
-}
-
-/* (3) DC un-prediction in the hook, restated for speed.
+/* (2) DC un-prediction in the hook, restated for speed.
  *
  * Same contract as oc_dec_dc_unpredict_mcu_plane_c (decode.c:1392-1500): undoes
  * the DC prediction of fragment rows [fragy0,fragy_end) of one plane in place

@@ -90,6 +90,7 @@ typedef struct ocg_enc_backend {
   ogg_int32_t         *border_slot;    /* [nfrags] index into itab.border_ssd, or -1 */
   ogg_int64_t         *border_mask;    /* [nfrags] the mask that slot was computed with */
   const unsigned char *pool0;          /* ref_frame_handle + base_off: what the candidates' tap offsets are relative to */
+  long                 n_me_repairs, n_gold_refines;
   long                 n_satd_hit, n_satd_miss, n_ssd_hit, n_ssd_host, n_isatd_hit; /* per pass, folded into the stats at the flush */
   /* quantiser tables in the layout of ocg_enc_fdct_quant_batch */
   ogg_uint16_t         dequant[3][2][3][64];
@@ -387,6 +388,9 @@ static void enc_flush(ocg_enc_backend *b) {
   b->self_on_device = b->inter_capable ? -1 : self;
   pthread_mutex_lock(&g_estats_lock);
   g_estats.frames++;
+  g_estats.me_repairs += b->n_me_repairs;
+  g_estats.me_gold_refines += b->n_gold_refines;
+  b->n_me_repairs = b->n_gold_refines = 0;
   g_estats.satd_lookups += b->n_satd_hit;
   g_estats.satd_host += b->n_satd_miss;
   g_estats.ssd_lookups += b->n_ssd_hit;
@@ -789,9 +793,7 @@ void oc_mcenc_search(oc_enc_ctx *_enc, int _mbi) {
       b->gold_fix[_mbi].satd = ro.satd;
       /* later macro blocks were fed the speculative values of this one */
       if (gold_mv != m->analysis_mv[0][OC_FRAME_GOLD] || gold_err != m->error[OC_FRAME_GOLD]) b->gold_dirty[_mbi] = 1;
-      pthread_mutex_lock(&g_estats_lock);
-      g_estats.me_repairs++;
-      pthread_mutex_unlock(&g_estats_lock);
+      b->n_me_repairs++;
     }
   }
   /* history as the reference leaves it (mcenc.c:534, 546-547): a function of this macro block alone */
@@ -831,9 +833,7 @@ void oc_mcenc_refine1mv(oc_enc_ctx *_enc, int _mbi, int _frame) {
     }
     /* the device's chain handed the unrefined vector to this macro block's later neighbours */
     if (e->analysis_mv[0][OC_FRAME_GOLD] != before) b->gold_dirty[_mbi] = 1;
-    pthread_mutex_lock(&g_estats_lock);
-    g_estats.me_gold_refines++;
-    pthread_mutex_unlock(&g_estats_lock);
+    b->n_gold_refines++;
   }
 }
 
@@ -984,6 +984,8 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
     free(b);
     return; /* th_encode_alloc (below) reports the failure: there is no CPU fallback encoder */
   }
+  /* an encoder flushes a few times per second: kernel-by-kernel launches, no graph to instantiate */
+  ocg_ctx_set_flush_graph(b->ctx, -1);
   b->pinned = ocg_host_register(st->ref_frame_handle, (size_t)b->geom.ref_frame_sz * 6) == 0;
   if (b->inter_capable && !b->pinned) {
     /* the flush graph copies the finished frame straight into the encoder's own buffer */

@@ -57,11 +57,12 @@ struct Slot {
   ocg_frag_rec *m_recs = nullptr;
   int16_t *m_rows = nullptr;
   OcgJobDev *m_job = nullptr;
+  OcgExpandDev *xjob = nullptr, *m_xjob = nullptr; /* token path header: pinned / its device address */
 };
 
 /* One instantiated CUDA graph of a whole frame flush (ocg_dec_flush). */
 struct FlushGraph {
-  int slot, out_mode, dc, lf;
+  int slot, out_mode, dc, lf, tokens; /* tokens: the ocg_dec_flush_tokens variant */
   cudaGraphExec_t exec;
   int kernels;
 };
@@ -110,6 +111,23 @@ struct ocg_ctx {
   uint32_t *d_done = nullptr;          /* the device's address of the same word */
   uint32_t *d_out_counter = nullptr;   /* copy-out kernel: CTAs finished */
   uint32_t flush_seq = 0;
+  /* device-side token expansion (ocg_dec_expand_setup / ocg_dec_flush_tokens) */
+  struct Expand {
+    int32_t *d_order = nullptr, *d_buf_off = nullptr, *d_ntok = nullptr;
+    uint16_t *d_dequant = nullptr;
+    uint8_t *d_words_raw = nullptr, *d_mvs_raw = nullptr, *d_tokens_raw = nullptr; /* + up to 15 bytes of host misalignment */
+    uint32_t *d_tok = nullptr, *d_cov = nullptr;
+    int16_t *d_coef = nullptr;
+    uint8_t *d_nextz = nullptr, *d_lastz = nullptr, *d_rmask = nullptr;
+    OcgExpandDev *d_xjob = nullptr;
+    size_t token_cap = 0;
+    /* the caller's page-locked arrays and their device addresses (fixed for the context's life) */
+    const uint32_t *h_words = nullptr; const int16_t *h_mvs = nullptr; const uint8_t *h_tokens = nullptr;
+    const uint8_t *m_words = nullptr, *m_mvs = nullptr, *m_tokens = nullptr;
+    bool ready = false;
+  } x;
+  long nflush = 0;            /* ocg_dec_flush calls so far */
+  int graph_after = 16;       /* replay a CUDA graph from this flush on; < 0: never */
 };
 
 struct ocg_pack {
@@ -163,6 +181,7 @@ static void fill_job(OcgJobDev &j, const ocg_ctx *c, const ocg_dec_frame &f, con
   j.xlist = c->d_xlist;
   j.xcount = c->d_xlist + c->geom.nfrags;
   j.lf_limit = f.lf_limit;
+  j.intra_frame = f.intra_frame;
   j.dc_residual = f.dc_residual == 1;
   j.dc_tmp = c->d_dc_tmp;
   j.lf_tmaps = c->d_tmaps ? c->d_tmaps + (size_t)f.ref_idx[OCG_FRAME_SELF] * 3 : nullptr;
@@ -382,6 +401,7 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
     if (s.recs) cudaFreeHost(s.recs);
     if (s.rows) cudaFreeHost(s.rows);
     if (s.job) cudaFreeHost(s.job);
+    if (s.xjob) cudaFreeHost(s.xjob);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
   if (c->enc != nullptr) {
@@ -395,6 +415,10 @@ OCG_API void ocg_ctx_destroy(ocg_ctx *c) {
   }
   if (c->done) cudaEventDestroy(c->done);
   for (FlushGraph &fg : c->graphs) cudaGraphExecDestroy(fg.exec);
+  cudaFree(c->x.d_order); cudaFree(c->x.d_buf_off); cudaFree(c->x.d_ntok); cudaFree(c->x.d_dequant);
+  cudaFree(c->x.d_words_raw); cudaFree(c->x.d_mvs_raw); cudaFree(c->x.d_tokens_raw);
+  cudaFree(c->x.d_tok); cudaFree(c->x.d_cov); cudaFree(c->x.d_coef);
+  cudaFree(c->x.d_nextz); cudaFree(c->x.d_lastz); cudaFree(c->x.d_rmask); cudaFree(c->x.d_xjob);
   if (c->h_done) cudaFreeHost((void *)c->h_done);
   cudaFree(c->d_out_counter);
   cudaFree(c->frames);
@@ -467,6 +491,8 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
     CUX(cudaHostGetDevicePointer((void **)&s.m_recs, s.recs, 0));
     CUX(cudaHostGetDevicePointer((void **)&s.m_rows, s.rows, 0));
     CUX(cudaHostGetDevicePointer((void **)&s.m_job, s.job, 0));
+    CUX(cudaHostAlloc(&s.xjob, sizeof(OcgExpandDev), cudaHostAllocMapped));
+    CUX(cudaHostGetDevicePointer((void **)&s.m_xjob, s.xjob, 0));
   }
   /* record template: every fragment uncoded, offsets and planes filled in */
   c->tmpl = (ocg_frag_rec *)calloc(nf, sizeof(ocg_frag_rec));
@@ -678,21 +704,56 @@ OCG_API int ocg_dec_submit(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out
   return OCG_OK;
 }
 
-/* Captures and instantiates the flush of one staging slot: kernels only (see ocg_dec_flush). */
-static int build_flush_graph(ocg_ctx *c, int si, int out_mode, int dc, int lf, bool tma) {
+static OcgExpandBufs expand_bufs(const ocg_ctx *c) {
+  OcgExpandBufs B;
+  B.order = c->x.d_order;
+  B.buf_off = c->x.d_buf_off;
+  B.dequant = c->x.d_dequant;
+  B.words = (const uint32_t *)(c->x.d_words_raw + ((uintptr_t)c->x.h_words & 15));
+  B.mvs = (const int16_t *)(c->x.d_mvs_raw + ((uintptr_t)c->x.h_mvs & 15));
+  B.tokens = c->x.d_tokens_raw + ((uintptr_t)c->x.h_tokens & 15);
+  B.tok = c->x.d_tok;
+  B.cov = c->x.d_cov;
+  B.ntok = c->x.d_ntok;
+  B.coef = c->x.d_coef;
+  B.nextz = c->x.d_nextz;
+  B.lastz = c->x.d_lastz;
+  B.rmask = c->x.d_rmask;
+  return B;
+}
+
+/* The kernel sequence of one frame flush on the context's stream (directly, or under capture).
+   tokens: the frame comes as the decoder's token lists (ocg_dec_flush_tokens) instead of records. */
+static void launch_flush_sequence(ocg_ctx *c, int si, int out_mode, int dc, int lf, int tokens, bool tma) {
   Slot &s = c->slots[si];
   cudaStream_t st = c->stream;
-  cudaGraph_t graph = nullptr;
-  /* thread-local capture: other threads' contexts keep working meanwhile */
-  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  ocg_launch_stage_in(s.m_job, c->d_job, s.m_recs, c->d_recs, c->geom.nfrags, s.m_rows, c->d_rows, st);
-  if (dc) ocg_launch_dc_unpredict(c->gdev, c->d_job, 1, st);
+  if (tokens) {
+    const OcgExpandBufs B = expand_bufs(c);
+    ocg_launch_stage_tokens(s.m_job, c->d_job, s.m_xjob, c->x.d_xjob, c->x.m_words, (void *)B.words, c->geom.nfrags * 4,
+                            c->x.m_mvs, (void *)B.mvs, c->geom.nfrags * 2, c->x.m_tokens, (void *)B.tokens, st);
+    if (dc) ocg_launch_dc_unpredict_words(c->gdev, B.words, c->d_dc_final, c->d_dc_tmp, st);
+    ocg_launch_expand(c->gdev, c->x.d_xjob, B, dc ? c->d_dc_final : nullptr, c->d_job, c->d_recs, st);
+  } else {
+    ocg_launch_stage_in(s.m_job, c->d_job, s.m_recs, c->d_recs, c->geom.nfrags, s.m_rows, c->d_rows, st);
+    if (dc) ocg_launch_dc_unpredict(c->gdev, c->d_job, 1, st);
+  }
   ocg_launch_recon(c->gdev, c->d_job, 1, st);
   if (lf) ocg_launch_loop_filter(c->gdev, c->d_job, 1, tma, st);
   ocg_launch_borders(c->gdev, c->d_job, 1, st);
   ocg_launch_copy_out(c->geom, out_mode, c->d_job, c->d_out_counter, c->d_done, st);
+}
+
+/* Captures and instantiates the flush of one staging slot: kernels only (see ocg_dec_flush). */
+static int build_flush_graph(ocg_ctx *c, int si, int out_mode, int dc, int lf, int tokens, bool tma) {
+  cudaStream_t st = c->stream;
+  cudaGraph_t graph = nullptr;
+  const long k0 = g_launches.load();
+  /* thread-local capture: other threads' contexts keep working meanwhile */
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  launch_flush_sequence(c, si, out_mode, dc, lf, tokens, tma);
   cudaError_t e = cudaStreamEndCapture(st, &graph);
   if (e != cudaSuccess || graph == nullptr) { cudaGetLastError(); return fail(OCG_ECUDA, "flush graph capture failed", e); }
+  (void)k0;
   size_t nnodes = 0;
   cudaGraphGetNodes(graph, nullptr, &nnodes); /* all of them kernels */
   const int kernels = (int)nnodes;
@@ -701,11 +762,11 @@ static int build_flush_graph(ocg_ctx *c, int si, int out_mode, int dc, int lf, b
   e = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) return fail(OCG_ECUDA, "cudaGraphInstantiate", e);
-  c->graphs.push_back(FlushGraph{si, out_mode, dc, lf, exec, kernels});
+  c->graphs.push_back(FlushGraph{si, out_mode, dc, lf, tokens, exec, kernels});
   return OCG_OK;
 }
 
-static std::atomic<long> g_flush_prep_ns{0}, g_flush_launch_ns{0}, g_flush_n{0};
+static std::atomic<long> g_flush_prep_ns{0}, g_flush_launch_ns{0}, g_flush_n{0}, g_flush_build_ns{0}, g_flush_builds{0};
 static inline long now_ns() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -719,6 +780,78 @@ static inline long now_ns() {
    one stream thread per decoder the eleven driver calls of ocg_dec_submit + copy-back + sync serialise
    on the driver's locks (measured: 0.25 ms of host time per frame at 16 threads); a graph launch plus a
    flag in host memory needs one. */
+/* Shared tail of ocg_dec_flush / ocg_dec_flush_tokens: the slot's job header is filled in except for the
+   destination and the sequence number. */
+static int flush_core(ocg_ctx *c, int si, uint8_t *host_out, int out_mode, int dc, int lf, int tokens, long t_in) {
+  Slot &s = c->slots[si];
+  cudaStream_t st = c->stream;
+  int r;
+  const bool tma = c->d_tmaps != nullptr && g_use_tma.load();
+  /* the destination's device address (one driver call per distinct buffer, then remembered) */
+  uint8_t *d_out_mapped = nullptr;
+  if (out_mode != OCG_OUT_NONE) {
+    for (const MappedOut &m : c->outs) if (m.host == host_out) d_out_mapped = m.dev;
+    if (d_out_mapped == nullptr) {
+      if (((uintptr_t)host_out & 15) != 0) return fail(OCG_EINVAL, "output buffer must be 16-byte aligned");
+      if (cudaHostGetDevicePointer((void **)&d_out_mapped, host_out, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCG_EINVAL, "output buffer is not page-locked (ocg_host_register)");
+      }
+      if (c->outs.size() >= 16) c->outs.clear();
+      c->outs.push_back(MappedOut{host_out, d_out_mapped});
+    }
+  }
+  s.job->host_out = d_out_mapped;
+  /* A stream's first flushes are launched kernel by kernel; from flush `graph_after` on the sequence is
+     replayed as a CUDA graph (one driver call per frame instead of six or more).  Instantiating a graph
+     costs ~0.3 ms, and tens of ms when many threads do it at once, so short-lived contexts never pay for it
+     and the builds of a process are serialised here rather than inside the driver. */
+  FlushGraph *fg = nullptr;
+  long t_build = 0;
+  if (c->graph_after >= 0 && c->nflush >= c->graph_after) {
+    for (int pass = 0; pass < 2 && fg == nullptr; pass++) {
+      for (FlushGraph &g : c->graphs)
+        if (g.slot == si && g.out_mode == out_mode && g.dc == dc && g.lf == lf && g.tokens == tokens) fg = &g;
+      if (fg == nullptr) {
+        const long tb = now_ns();
+        {
+          static std::mutex build_lock;
+          std::lock_guard<std::mutex> lk(build_lock);
+          for (int k = 0; k < kSlots; k++) {
+            r = build_flush_graph(c, k, out_mode, dc, lf, tokens, tma);
+            if (r < 0) return r;
+          }
+        }
+        t_build = now_ns() - tb;
+        g_flush_build_ns.fetch_add(t_build, std::memory_order_relaxed);
+        g_flush_builds.fetch_add(kSlots, std::memory_order_relaxed);
+      }
+    }
+    if (fg == nullptr) return fail(OCG_ECUDA, "flush graph missing");
+  }
+  /* the stage-in kernel reads the host memory when it runs: everything it reads is final now */
+  c->flush_seq++;
+  s.job->seq = c->flush_seq;
+  s.flush_seq = c->flush_seq;
+  s.flush_busy = true;
+  c->nflush++;
+  const long t_launch = now_ns();
+  int nk = 0;
+  if (fg != nullptr) {
+    CU(cudaGraphLaunch(fg->exec, st));
+    nk = fg->kernels;
+  } else {
+    launch_flush_sequence(c, si, out_mode, dc, lf, tokens, tma); /* the launch helpers count their kernels */
+    CU(cudaGetLastError());
+  }
+  const long t_out = now_ns();
+  g_flush_prep_ns.fetch_add(t_launch - t_in - t_build, std::memory_order_relaxed);
+  g_flush_launch_ns.fetch_add(t_out - t_launch, std::memory_order_relaxed);
+  g_flush_n.fetch_add(1, std::memory_order_relaxed);
+  g_launches.fetch_add(nk, std::memory_order_relaxed);
+  return OCG_OK;
+}
+
 OCG_API int ocg_dec_flush(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out, int out_mode) {
   if (c == nullptr || f == nullptr) return fail(OCG_EFAULT, "NULL argument");
   int r = check_frame(c->geom, *f);
@@ -736,7 +869,6 @@ OCG_API int ocg_dec_flush(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out,
   const int si = c->cur_slot;
   Slot &s = c->slots[si];
   c->staged = false;
-  cudaStream_t st = c->stream;
   const size_t nf = (size_t)c->geom.nfrags;
   if (!from_staging) {
     memcpy(s.recs, f->recs, nf * sizeof(ocg_frag_rec));
@@ -744,50 +876,123 @@ OCG_API int ocg_dec_flush(ocg_ctx *c, const ocg_dec_frame *f, uint8_t *host_out,
   }
   fill_job(*s.job, c, *f, c->d_recs, c->d_rows);
   s.job->ncoeff_rows = f->ncoeff_rows;
-  const int dc = f->dc_residual == 1, lf = f->lf_limit != 0;
-  const bool tma = c->d_tmaps != nullptr && g_use_tma.load();
-  /* the destination's device address (one driver call per distinct buffer, then remembered) */
-  uint8_t *d_out_mapped = nullptr;
-  if (out_mode != OCG_OUT_NONE) {
-    for (const MappedOut &m : c->outs) if (m.host == host_out) d_out_mapped = m.dev;
-    if (d_out_mapped == nullptr) {
-      if (((uintptr_t)host_out & 15) != 0) return fail(OCG_EINVAL, "output buffer must be 16-byte aligned");
-      if (cudaHostGetDevicePointer((void **)&d_out_mapped, host_out, 0) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(OCG_EINVAL, "output buffer is not page-locked (ocg_host_register)");
-      }
-      if (c->outs.size() >= 16) c->outs.clear();
-      c->outs.push_back(MappedOut{host_out, d_out_mapped});
+  return flush_core(c, si, host_out, out_mode, f->dc_residual == 1, f->lf_limit != 0, 0, t_in);
+}
+
+/* ---- device-side token expansion ------------------------------------------------------------------ */
+OCG_API int ocg_dec_expand_setup(ocg_ctx *c, const int32_t *coded_order, const uint16_t *dequant_tables,
+                                 const uint32_t *frag_words, const int16_t *frag_mvs, const uint8_t *dct_tokens,
+                                 size_t token_capacity) {
+  if (c == nullptr || coded_order == nullptr || dequant_tables == nullptr || frag_words == nullptr || frag_mvs == nullptr ||
+      dct_tokens == nullptr)
+    return fail(OCG_EFAULT, "NULL argument");
+  if (c->x.ready) return fail(OCG_EINVAL, "token expansion is already set up for this context");
+  if (token_capacity == 0 || token_capacity > ((size_t)1 << 30)) return fail(OCG_EINVAL, "bad token capacity");
+  CU(ocg_set_device(c->device));
+  const size_t nf = (size_t)c->geom.nfrags;
+  std::vector<uint8_t> seen(nf, 0);
+  for (int pli = 0; pli < 3; pli++) {
+    const ocg_plane_geom &p = c->geom.planes[pli];
+    for (int i = 0; i < p.nfrags; i++) {
+      const int32_t f = coded_order[p.froffset + i];
+      if (f < p.froffset || f >= p.froffset + p.nfrags || seen[(size_t)f]) return fail(OCG_EINVAL, "coded order is not a permutation of each plane's fragments");
+      seen[(size_t)f] = 1;
     }
   }
-  s.job->host_out = d_out_mapped;
-  /* both staging slots' graphs are made the first time a variant is seen (a stream alternates between
-     them from its second frame on) */
-  FlushGraph *fg = nullptr;
-  for (int pass = 0; pass < 2 && fg == nullptr; pass++) {
-    for (FlushGraph &g : c->graphs)
-      if (g.slot == si && g.out_mode == out_mode && g.dc == dc && g.lf == lf) fg = &g;
-    if (fg == nullptr) {
-      for (int k = 0; k < kSlots; k++) {
-        r = build_flush_graph(c, k, out_mode, dc, lf, tma);
-        if (r < 0) return r;
-      }
-    }
+  ocg_ctx::Expand &x = c->x;
+  cudaStream_t st = c->stream;
+  ocg_expand_init_tables(st);
+  std::vector<int32_t> offs(nf);
+  ocg_geometry_frag_buf_offs(&c->geom, offs.data());
+  const size_t tokb = (token_capacity + 63) & ~(size_t)15;
+  CU(cudaMalloc(&x.d_order, nf * 4));
+  CU(cudaMalloc(&x.d_buf_off, nf * 4));
+  CU(cudaMalloc(&x.d_ntok, 192 * 4));
+  CU(cudaMalloc(&x.d_dequant, 64 * 3 * 2 * 64 * 2));
+  CU(cudaMalloc(&x.d_words_raw, nf * 4 + 64));
+  CU(cudaMalloc(&x.d_mvs_raw, nf * 2 + 64));
+  CU(cudaMalloc(&x.d_tokens_raw, tokb + 64));
+  CU(cudaMalloc(&x.d_tok, tokb * 4));
+  CU(cudaMalloc(&x.d_cov, tokb * 4));
+  CU(cudaMalloc(&x.d_coef, nf * 128));
+  CU(cudaMalloc(&x.d_nextz, nf));
+  CU(cudaMalloc(&x.d_lastz, nf));
+  CU(cudaMalloc(&x.d_rmask, nf));
+  CU(cudaMalloc(&x.d_xjob, sizeof(OcgExpandDev)));
+  CU(cudaMemcpyAsync(x.d_order, coded_order, nf * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(x.d_buf_off, offs.data(), nf * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(x.d_dequant, dequant_tables, 64 * 3 * 2 * 64 * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(x.d_coef, 0, nf * 128, st));
+  CU(cudaStreamSynchronize(st));
+  x.token_cap = token_capacity;
+  x.h_words = frag_words;
+  x.h_mvs = frag_mvs;
+  x.h_tokens = dct_tokens;
+  if (cudaHostGetDevicePointer((void **)&x.m_words, (void *)frag_words, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer((void **)&x.m_mvs, (void *)frag_mvs, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer((void **)&x.m_tokens, (void *)dct_tokens, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OCG_EINVAL, "the fragment / vector / token arrays must be page-locked (ocg_host_register)");
   }
-  if (fg == nullptr) return fail(OCG_ECUDA, "flush graph missing");
-  /* the stage-in kernel reads the staging memory when it runs: everything it reads is final now */
-  c->flush_seq++;
-  s.job->seq = c->flush_seq;
-  s.flush_seq = c->flush_seq;
-  s.flush_busy = true;
-  const long t_launch = now_ns();
-  CU(cudaGraphLaunch(fg->exec, st));
-  const long t_out = now_ns();
-  g_flush_prep_ns.fetch_add(t_launch - t_in, std::memory_order_relaxed);
-  g_flush_launch_ns.fetch_add(t_out - t_launch, std::memory_order_relaxed);
-  g_flush_n.fetch_add(1, std::memory_order_relaxed);
-  g_launches.fetch_add(fg->kernels, std::memory_order_relaxed);
+  x.ready = true;
   return OCG_OK;
+}
+
+OCG_API int ocg_dec_flush_tokens(ocg_ctx *c, const ocg_dec_tokens *t, uint8_t *host_out, int out_mode) {
+  if (c == nullptr || t == nullptr) return fail(OCG_EFAULT, "NULL argument");
+  if (!c->x.ready) return fail(OCG_EINVAL, "ocg_dec_expand_setup has not been called");
+  if (out_mode != OCG_OUT_NONE && host_out == nullptr) return fail(OCG_EFAULT, "NULL output buffer");
+  if (t->ntoken_bytes < 0 || (size_t)t->ntoken_bytes > c->x.token_cap) return fail(OCG_EINVAL, "token count out of range");
+  if (t->nqis < 1 || t->nqis > 3) return fail(OCG_EINVAL, "nqis must be 1..3");
+  for (int i = 0; i < t->nqis; i++) if (t->qis[i] < 0 || t->qis[i] > 63) return fail(OCG_EINVAL, "qi out of range");
+  if (t->dc_residual != 0 && t->dc_residual != 1) return fail(OCG_EINVAL, "dc_residual must be 0 or 1");
+  ocg_dec_frame f;
+  memset(&f, 0, sizeof(f));
+  for (int i = 0; i < 3; i++) f.ref_idx[i] = t->ref_idx[i];
+  f.lf_limit = t->lf_limit;
+  f.intra_frame = t->intra_frame;
+  f.dc_residual = t->dc_residual;
+  memcpy(f.dc_quant, t->dc_quant, sizeof(f.dc_quant));
+  int r = check_frame(c->geom, f);
+  if (r < 0) return r;
+  if (!t->intra_frame && (t->ref_idx[OCG_FRAME_PREV] < 0 || t->ref_idx[OCG_FRAME_GOLD] < 0)) return fail(OCG_EINVAL, "inter frame without reference buffers");
+  for (int p = 0; p < 3; p++) {
+    int prev = -1;
+    for (int z = 0; z < 64; z++) {
+      const int v = t->ti0[p][z];
+      if (v < 0 || v > t->ntoken_bytes || (z > 0 && v < prev)) return fail(OCG_EINVAL, "token list offsets out of order");
+      prev = v;
+    }
+  }
+  const long t_in = now_ns();
+  CU(ocg_set_device(c->device));
+  r = acquire_slot(c);
+  if (r < 0) return r;
+  const int si = c->cur_slot;
+  Slot &s = c->slots[si];
+  c->staged = false;
+  f.dc_residual = 0; /* the records the reconstruction reads are final either way */
+  fill_job(*s.job, c, f, c->d_recs, c->x.d_coef);
+  s.job->dense_rows = 1;
+  OcgExpandDev &X = *s.xjob;
+  for (int p = 0; p < 3; p++)
+    for (int z = 0; z < 64; z++) {
+      X.ti0[p][z] = t->ti0[p][z];
+      X.eob_runs[p][z] = t->eob_runs[p][z] < 0 ? 0 : t->eob_runs[p][z];
+    }
+  X.ntoken_bytes = t->ntoken_bytes;
+  X.nqis = t->nqis;
+  for (int i = 0; i < 3; i++) X.qis[i] = i < t->nqis ? t->qis[i] : t->qis[0];
+  return flush_core(c, si, host_out, out_mode, t->dc_residual == 1, t->lf_limit != 0, 1, t_in);
+}
+
+OCG_API void ocg_ctx_set_flush_graph(ocg_ctx *c, int after) {
+  if (c != nullptr) c->graph_after = after;
+}
+
+OCG_API void ocg_flush_profile_builds(double *build_s, long *nbuilds) {
+  if (build_s) *build_s = 1e-9 * (double)g_flush_build_ns.load();
+  if (nbuilds) *nbuilds = g_flush_builds.load();
 }
 
 OCG_API void ocg_flush_profile(double *prepare_s, double *launch_s, long *n, int reset) {

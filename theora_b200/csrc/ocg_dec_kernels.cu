@@ -220,7 +220,20 @@ __device__ __forceinline__ void xform_group(const OcgGeomDev &g, const OcgJobDev
     const int ra = 2 * l, rb = 2 * l + 1;
     const unsigned rowmask = ((unsigned)it.w >> 16) & 0xFFu;
     uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-    if (ra < nfoot) {
+    if (job.dense_rows) {
+      /* device-side expansion: row r of the block at coeff_row + r; whatever was stored is cleared again
+         (the blocks are all-zero between frames, idct.c:245,276,295 does the same to its input) */
+      uint4 *rows = (uint4 *)job.rows + (unsigned)it.z;
+      const uint4 zero = make_uint4(0, 0, 0, 0);
+      if (my != WC_NONE) {
+        if (rowmask >> ra & 1) { if (ra < nfoot) wa = rows[ra]; rows[ra] = zero; }
+        if (rowmask >> rb & 1) { if (rb < nfoot) wb = rows[rb]; rows[rb] = zero; }
+      }
+      if (my != WC_FULL) {
+        wa = keep_first(wa, max(0, nfoot - ra));
+        wb = keep_first(wb, max(0, nfoot - rb));
+      }
+    } else if (ra < nfoot) {
       const uint4 *rows = (const uint4 *)job.rows + (unsigned)it.z;
       if (rowmask >> ra & 1) wa = __ldg(rows + __popc(rowmask & ((1u << ra) - 1u)));
       if (rowmask >> rb & 1) wb = __ldg(rows + __popc(rowmask & ((1u << rb) - 1u)));

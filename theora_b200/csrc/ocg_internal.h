@@ -41,7 +41,39 @@ struct OcgJobDev {
   uint32_t            seq;       /* ocg_dec_flush: published in host memory when the frame is complete */
   int32_t             ncoeff_rows; /* ocg_dec_flush: rows to stage in */
   uint8_t            *host_out;  /* ocg_dec_flush: the device's address of the page-locked destination buffer */
+  int32_t             dense_rows; /* rows live at coeff_row + r (device-side expansion) and are cleared once read */
+  int32_t             intra_frame;
 };
+
+/* One frame's token lists as the reference's decoder holds them (ocg_dec_flush_tokens); device copy. */
+struct OcgExpandDev {
+  int32_t ti0[3][64];       /* byte offset of each (plane, zig-zag index) list in the token array */
+  int32_t eob_runs[3][64];  /* EOB run reaching into each list (saturated) */
+  int32_t ntoken_bytes;
+  int32_t qis[3];
+  int32_t nqis;
+  int32_t pad[3];
+};
+
+struct OcgExpandBufs {
+  const int32_t  *order;    /* [nfrags] coded order (per plane, planes back to back) -> fragment index */
+  const int32_t  *buf_off;  /* [nfrags] */
+  const uint16_t *dequant;  /* [64 qi][3][2][64] */
+  const uint32_t *words;    /* device copies of the frame's arrays */
+  const int16_t  *mvs;
+  const uint8_t  *tokens;
+  uint32_t *tok, *cov;      /* decoded tokens / fragments served before each, indexed from the list's byte offset */
+  int32_t  *ntok;           /* [192] */
+  int16_t  *coef;           /* [nfrags][64] dense blocks, all-zero between frames */
+  uint8_t  *nextz, *lastz, *rmask;
+};
+
+void ocg_expand_init_tables(cudaStream_t st);
+void ocg_launch_stage_tokens(const OcgJobDev *h_job, OcgJobDev *d_job, const OcgExpandDev *h_x, OcgExpandDev *d_x,
+                             const void *h_words, void *d_words, int words_bytes, const void *h_mvs, void *d_mvs, int mvs_bytes,
+                             const void *h_tok, void *d_tok, cudaStream_t st);
+void ocg_launch_expand(const OcgGeomDev &g, const OcgExpandDev *d_x, const OcgExpandBufs &B, const int16_t *dc_final,
+                       const OcgJobDev *d_job, ocg_frag_rec *d_recs, cudaStream_t st);
 
 #define OCG_FRAGS_PER_BLOCK 64
 #define OCG_RECON_THREADS   256

@@ -10,14 +10,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import theora_b200 as T  # noqa: E402
-from theora_b200 import streams, workload as wl  # noqa: E402
+import th_streams as streams  # noqa: E402
+import th_workload as wl  # noqa: E402
 
 
 def main():
     w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
     blob = wl.synth_stream(w, h, 24, 32, 64)
     for name, mode in (("host-DC lists", streams.DC_HOST), ("device-DC lists", streams.DC_DEVICE)):
-        g, works, _ = streams.capture_stream_work(blob, streams.BACKEND_GPU, dc_mode=mode)
+        g, works, _ = streams.capture_stream_work(blob, streams.BACKEND_GPU, dc_mode=mode, expand=streams.EXPAND_REFERENCE)
         ctx = T.Context(g, 0)
         stream = torch.cuda.ExternalStream(ctx.stream)
         per = []

@@ -16,9 +16,9 @@ def main():
     path, threads, with_ref = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     dc_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1   # streams.DC_HOST
     blocking = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-    expand = int(sys.argv[6]) if len(sys.argv) > 6 else 0     # OCG_EXPAND_BACKEND
+    expand = int(sys.argv[6]) if len(sys.argv) > 6 else 0     # OCG_EXPAND_DEVICE
     import support as S
-    from theora_b200 import streams
+    import th_streams as streams
     blob = open(path, "rb").read()
     Lo = streams.lib()
     buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
@@ -53,11 +53,14 @@ def main():
             refs.append(rs)
     prep, launch, nfl = C.c_double(), C.c_double(), C.c_long()
     abi.lib().ocg_flush_profile(C.byref(prep), C.byref(launch), C.byref(nfl), 1)
+    bs, nb = C.c_double(), C.c_long()
+    abi.lib().ocg_flush_profile_builds(C.byref(bs), C.byref(nb))
     ours.sort()
     secs, h2d, d2h, flush, wait = ours[1]
     out = {"secs": secs, "frames": threads * nframes, "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
            "flush_ms_per_frame": 1e3 * flush, "wait_ms_per_frame": 1e3 * wait, "hash": int(hsh.value), "threads": threads,
-           "flush_prepare_us": 1e6 * prep.value / max(nfl.value, 1), "graph_launch_us": 1e6 * launch.value / max(nfl.value, 1)}
+           "flush_prepare_us": 1e6 * prep.value / max(nfl.value, 1), "graph_launch_us": 1e6 * launch.value / max(nfl.value, 1),
+           "graph_builds": nb.value, "graph_build_ms_each": 1e3 * bs.value / max(nb.value, 1)}
     if refs:
         out["ref_secs"] = sorted(refs)[1]
         out["ref_hash"] = int(rh.value)

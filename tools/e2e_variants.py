@@ -13,7 +13,7 @@ def main():
     w, h = (int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1920x1080").split("x"))
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     q = int(sys.argv[3]) if len(sys.argv) > 3 else 32
-    from theora_b200 import workload as wl
+    import th_workload as wl
     blob = wl.synth_stream(w, h, frames, q, 64)
     path = "/tmp/e2e_variants.ogs"
     open(path, "wb").write(blob)

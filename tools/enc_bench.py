@@ -19,7 +19,7 @@ def main():
     kf = int(sys.argv[6]) if len(sys.argv) > 6 else 1
     speed = int(sys.argv[7]) if len(sys.argv) > 7 else 1
     import support as S
-    from theora_b200 import streams
+    import th_streams as streams
     Lo = streams.lib()
     kind = "asm" if S.ref_available("asm") else "c"
     R = S.ref(kind)
@@ -59,6 +59,12 @@ def main():
                                      "skip_ssd_from_device_table": int(st.ssd_lookups),
                                      "coded_block_ssd_on_host": int(st.ssd_host),
                                      "intra_satd_from_device_table": int(st.intra_satd_lookups)}
+    from theora_b200 import abi
+    prep, launch, nfl, bs, nb = C.c_double(), C.c_double(), C.c_long(), C.c_double(), C.c_long()
+    abi.lib().ocg_flush_profile(C.byref(prep), C.byref(launch), C.byref(nfl), 0)
+    abi.lib().ocg_flush_profile_builds(C.byref(bs), C.byref(nb))
+    out["flush_profile"] = {"prepare_us": 1e6 * prep.value / max(nfl.value, 1), "graph_launch_us": 1e6 * launch.value / max(nfl.value, 1),
+                            "flushes": nfl.value, "graph_builds": nb.value, "graph_build_ms_each": 1e3 * bs.value / max(nb.value, 1)}
     out["cpu_baseline"] = {"value": (frames - 1) * threads / rsecs, "cores": threads,
                            "kind": "reference" if kind == "asm" else "reference (C path)"}
     out["timing"] = "median of 3 passes each, ours and the reference interleaved, in a process of its own"
