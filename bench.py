@@ -398,6 +398,45 @@ def bench_me_frame(torch, dev, ncores, streams_n=64, nframes=4):
     return out
 
 
+
+def stage_roofline(T, L, abi, ctxs, packs, nframes, S, stage_bytes, peak, peak_src, traffic_files=()):
+    """Per-kernel device time (CUDA events on the launching stream; all S streams in one launch set on one
+    CUDA stream, so the event pairs bracket one kernel group each) -> roofline object."""
+    L.ocg_profile_enable(1)
+    for f in range(nframes):
+        T.run_batch(ctxs, packs, [f] * S, ctxs[0].stream)
+    ms3, n3 = (C.c_double * 3)(), (C.c_long * 3)()
+    abi.check(L.ocg_profile_collect(ms3, n3))
+    L.ocg_profile_enable(0)
+    stage_names = ["recon+copy", "loop_filter", "borders"]
+    kern = {}
+    for i in range(3):
+        if n3[i]:
+            avg_ms = ms3[i] / n3[i]
+            kern[stage_names[i]] = {"avg_ms": avg_ms, "launches_per_step": int(n3[i]),
+                                    "share": ms3[i] / max(sum(ms3), 1e-9),
+                                    "alg_GBps": stage_bytes[i] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}
+    dom = max(range(3), key=lambda i: ms3[i])
+    achieved = stage_bytes[dom] / (ms3[dom] / n3[dom] * 1e-3) / 1e9 if n3[dom] and stage_bytes[dom] else 0.0
+    traffic = None
+    for name in traffic_files:
+        # measured DRAM bytes per launch from the committed ncu captures (same streams-per-launch only)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if int(tj["streams_per_launch"]) == S:
+                traffic = tj["dram_bytes_per_launch"].get(stage_names[dom])
+                break
+        except Exception:
+            continue
+    out = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+           "alg_bytes_per_launch": stage_bytes[dom], "kernels": kern}
+    if traffic:
+        # bytes that actually crossed the HBM interface per launch / launch time / peak
+        out["frac_dram"] = traffic / (ms3[dom] / n3[dom] * 1e-3) / 1e9 / peak
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -432,9 +471,14 @@ def main():
     ap.add_argument("--quality", type=int, default=32)
     ap.add_argument("--kf", type=int, default=64)
     ap.add_argument("--threads", type=int, default=0, help="host threads for e2e / CPU arms (0 = all cores)")
-    ap.add_argument("--e2e-oversub", type=int, default=1, help="stream threads per core of the second e2e pass (1 = off)")
-    ap.add_argument("--e2e-variants", action="store_true", help="also time the opt-in e2e variants (device DC un-prediction)")
+    ap.add_argument("--e2e-threads-per-core", type=int, default=3,
+                    help="decoder stream threads per host core of the e2e pass (the flush is asynchronous: a thread "
+                         "that waits for its frame yields the core to another stream's entropy decode)")
+    ap.add_argument("--e2e-dc", default="device", choices=["device", "host"], help="where the e2e pass undoes the DC prediction")
+    ap.add_argument("--e2e-variants", action="store_true", help="also time other e2e configurations (reported as alternatives)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-noisy", action="store_true", help="skip the dense-coefficient roofline workload")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 3840x2160 decode+encode section (BASELINE configs[4])")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-encode-kernels", action="store_true")
     args = ap.parse_args()
@@ -587,44 +631,41 @@ def main():
     ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     value = WORLD * S * nframes * args.steps / (ms_total * 1e-3)
 
-    # per-kernel device time (CUDA events on the launching stream) for the roofline
-    # (all S streams in one launch set on one CUDA stream, so the event pairs bracket one kernel each)
     torch.cuda.synchronize()
-    L.ocg_profile_enable(1)
-    for f in range(nframes):
-        T.run_batch(ctxs, packs, [f] * S, ctxs[0].stream)
-    ms3, n3 = (C.c_double * 3)(), (C.c_long * 3)()
-    abi.check(L.ocg_profile_collect(ms3, n3))
-    L.ocg_profile_enable(0)
     peak, peak_src = load_peaks()
-    stage_names = ["recon+copy", "loop_filter", "borders"]
-    stage_bytes = [recon_bytes_frame * S, lf_bytes_frame * S, 0.0]
-    kern = {}
-    for i in range(3):
-        if n3[i]:
-            avg_ms = ms3[i] / n3[i]
-            kern[stage_names[i]] = {"avg_ms": avg_ms, "launches_per_step": int(n3[i]),
-                                    "share": ms3[i] / max(sum(ms3), 1e-9),
-                                    "alg_GBps": stage_bytes[i] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}
-    dom = max(range(3), key=lambda i: ms3[i])
-    achieved = stage_bytes[dom] / (ms3[dom] / n3[dom] * 1e-3) / 1e9 if n3[dom] and stage_bytes[dom] else 0.0
-    traffic = None
-    for name in ("r1b_traffic.json", "r1_final_traffic.json"):
-        # measured DRAM bytes per launch from the committed ncu captures (same streams-per-launch only)
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
-            if int(tj["streams_per_launch"]) == S:
-                traffic = tj["dram_bytes_per_launch"].get(stage_names[dom])
-                break
-        except Exception:
-            continue
-    roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                "alg_bytes_per_launch": stage_bytes[dom], "kernels": kern}
-    for c in ctxs:
-        c.close()
+    roofline = stage_roofline(T, L, abi, ctxs, packs, nframes, S, [recon_bytes_frame * S, lf_bytes_frame * S, 0.0], peak, peak_src,
+                              ("r2_traffic.json", "r1b_traffic.json", "r1_final_traffic.json"))
     for p in packs:
         p.close()
+    packs = None
+    # second workload for the kernel roofline only: a dense-coefficient stream (SURVEY 8(d) "high-noise"
+    # variant), where the transform pass (pass B) carries the reconstruction stage instead of the copy pass
+    roofline_noisy = None
+    if not args.no_noisy:
+        try:
+            nblob = sharding.broadcast_bytes(
+                wl.synth_stream(args.width, args.height, 32, 48, 64, noise_shift=26, lib=reference_lib()[0]) if RANK == 0 else b"", 0, dev)
+            _, nworks, _ = streams.capture_stream_work(nblob, streams.BACKEND_GPU, dc_mode=streams.DC_HOST,
+                                                       expand=streams.EXPAND_REFERENCE)
+            nworks = [w for w in nworks if w is not None]
+            nalg = [wl.algorithmic_bytes(w) for w in nworks]
+            npacks = [T.Pack(nworks, g.nfrags, LOCAL_RANK) for _ in range(S)]
+            for f in range(len(nworks)):  # warm-up
+                T.run_batch(ctxs, npacks, [f] * S, ctxs[0].stream)
+            torch.cuda.synchronize()
+            roofline_noisy = stage_roofline(T, L, abi, ctxs, npacks, len(nworks), S,
+                                            [float(np.mean([a[0] for a in nalg])) * S, float(np.mean([a[1] for a in nalg])) * S, 0.0],
+                                            peak, peak_src, ("r2_traffic_noisy.json",))
+            roofline_noisy["workload"] = ("%dx%d, %d frames, q=48 (loop filter off), noise_shift=26: %.0f KB of packets per frame, "
+                                          "%.0f %% of the coded fragments need a transform" % (
+                                              args.width, args.height, len(nworks), len(nblob) / len(nworks) / 1e3,
+                                              100.0 * float(np.mean([1.0 - (w.ncls[0] / max(w.ncoded, 1)) for w in nworks]))))
+            for p in npacks:
+                p.close()
+        except Exception as e:  # informational: never take the headline down
+            roofline_noisy = {"error": repr(e)}
+    for c in ctxs:
+        c.close()
 
     # e2e through the public API: T host threads, packets in RAM -> frames in RAM.  Measured by
     # tools/dec_e2e_bench.py in a process of its own per rank (ctypes only, the way a C program uses the
@@ -643,14 +684,14 @@ def main():
 
         npass = [0]
 
-        def e2e_pass(nthreads, blocking, dc_mode, ref):
+        def e2e_pass(nthreads, blocking, dc_mode, ref_threads):
             # ranks start together and finished ranks SLEEP until the last one is done (a NCCL barrier would
             # spin a host core per waiting rank and slow the ranks that are still measuring)
             npass[0] += 1
             barrier()
             p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dec_e2e_bench.py"), blob_path, str(nthreads),
-                                str(int(ref)), str(dc_mode), str(int(blocking))], capture_output=True, text=True, env=env,
-                               timeout=1200)
+                                str(int(ref_threads)), str(dc_mode), str(int(blocking))], capture_output=True, text=True,
+                               env=env, timeout=1200)
             if p.returncode != 0:
                 raise RuntimeError("dec_e2e_bench failed: " + p.stderr[-400:])
             d = json.loads(p.stdout.strip().splitlines()[-1])
@@ -659,32 +700,35 @@ def main():
             r = {"value": WORLD * nthreads * nframes / secs, "unit": "frames/s",
                  "h2d_bytes_per_step": int(d["h2d_bytes"]), "d2h_bytes_per_step": int(d["d2h_bytes"]),
                  "host_threads": nthreads, "host_cores": ncores,
-                 "sync": "blocking event (thread sleeps during a flush)" if blocking else "spin",
-                 "dc_unprediction": "device (wave-front kernel)" if dc_mode == streams.DC_DEVICE else "host (reference C routine in the hook)",
-                 "token_expansion": "back-end, inside the dc_unpredict_mcu_plane hook (ocg_host_expand_mcu_plane)",
+                 "wait": "yield (a waiting stream thread gives its core away)" if blocking else "spin",
+                 "dc_unprediction": "device (wave-front kernel inside the flush)" if dc_mode == streams.DC_DEVICE else "host (table-driven routine in the hook)",
+                 "token_expansion": "device (ocg_dec_flush_tokens: fragment words, vectors and token lists read in place)",
+                 "flush": "one CUDA graph of kernels per frame, asynchronous until th_decode_ycbcr_out",
                  "api": "th_decode_packetin + th_decode_ycbcr_out (reference host code, B200 back-end)",
-                 "flush_ms_per_frame": d["flush_ms_per_frame"], "final_frame_hash": d["hash"],
+                 "flush_ms_per_frame": d["flush_ms_per_frame"], "wait_ms_per_frame": d["wait_ms_per_frame"],
+                 "d2h_GBps": WORLD * d["d2h_bytes"] / secs / 1e9, "final_frame_hash": d["hash"],
                  "timing": "median of 3 passes, in a process of its own per rank"}
             return r, d
-        main_pass, raw = e2e_pass(ncores, False, streams.DC_HOST, with_ref)
-        cands = [main_pass]
+        # THE e2e configuration (fixed, not picked from measurements): stream threads per core and wait policy
+        tpc = max(1, args.e2e_threads_per_core)
+        dcm = streams.DC_DEVICE if args.e2e_dc == "device" else streams.DC_HOST
+        e2e, raw = e2e_pass(ncores * tpc, tpc > 1, dcm, ncores if with_ref else 0)
+        alts = []
         if args.e2e_variants:
-            cands.append(e2e_pass(ncores, False, streams.DC_DEVICE, 0)[0])
-        if args.e2e_oversub > 1:
-            cands.append(e2e_pass(ncores * args.e2e_oversub, True, streams.DC_HOST, 0)[0])
-        hashes = {c["final_frame_hash"] for c in cands}
-        cands.sort(key=lambda r: -r["value"])
-        e2e = cands[0]
-        e2e["alternatives"] = [{k: c[k] for k in ("value", "host_threads", "sync", "dc_unprediction", "flush_ms_per_frame")}
-                               for c in cands[1:]]
-        e2e["all_variants_same_output"] = len(hashes) == 1
+            for nthr, blk, dm in ((ncores, False, streams.DC_HOST), (ncores, False, streams.DC_DEVICE),
+                                  (2 * ncores, True, dcm), (4 * ncores, True, dcm)):
+                a = e2e_pass(nthr, blk, dm, 0)[0]
+                alts.append({k: a[k] for k in ("value", "host_threads", "wait", "dc_unprediction", "flush_ms_per_frame",
+                                               "wait_ms_per_frame", "final_frame_hash")})
+        e2e["alternatives"] = alts
+        e2e["all_variants_same_output"] = all(a["final_frame_hash"] == e2e["final_frame_hash"] for a in alts)
         if "ref_secs" in raw:
             rfps = ncores * nframes / raw["ref_secs"]
             cpu = {"value": rfps, "unit": "frames/s", "cores": ncores,
                    "kind": "reference" if raw["ref_kind"] == "asm" else "reference (C path)",
                    "sample": "%d streams x %d frames via th_decode_packetin, %.1fs; median of 3 passes interleaved with ours"
                    % (ncores, nframes, raw["ref_secs"]), "final_frame_hash": raw["ref_hash"]}
-            e2e["parity_with_cpu_baseline"] = bool(main_pass["final_frame_hash"] == raw["ref_hash"])
+            e2e["parity_with_cpu_baseline"] = bool(e2e["final_frame_hash"] == raw["ref_hash"])
         try:
             os.remove(blob_path)
         except OSError:
@@ -722,6 +766,39 @@ def main():
         except Exception as e:
             enc_inter = {"error": repr(e)}
 
+    # BASELINE configs[4]: one 3840x2160 stream per GPU, decode and encode through the public API, every rank
+    config4 = None
+    if not args.no_e2e and not args.no_config4:
+        try:
+            env = dict(os.environ)
+            vis = env.get("CUDA_VISIBLE_DEVICES", "")
+            env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[LOCAL_RANK] if vis else str(LOCAL_RANK)
+            barrier()
+            c4_frames, c4_enc = 24, 4
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config4_bench.py"), str(RANK), str(c4_frames),
+                                str(c4_enc), str(WORLD if RANK == 0 and not args.no_cpu else 0)], capture_output=True, text=True,
+                               env=env, timeout=1200)
+            if p.returncode != 0:
+                raise RuntimeError("config4_bench failed: " + p.stderr[-400:])
+            d = json.loads(p.stdout.strip().splitlines()[-1])
+            sharding.quiet_barrier("config4")
+            dsecs = sharding.max_over_ranks(d["decode_secs"], dev)
+            esecs = sharding.max_over_ranks(d["encode_secs"], dev)
+            config4 = {"workload": "%d independent 3840x2160 4:2:0 streams, one per GPU: %d frames decoded and %d frames "
+                       "encoded (key frame + inter frames, speed 1) per stream through th_decode_* / th_encode_*, one host "
+                       "thread per stream" % (WORLD, c4_frames, c4_enc - 1),
+                       "decode_frames_per_s": WORLD * c4_frames / dsecs, "encode_frames_per_s": WORLD * (c4_enc - 1) / esecs,
+                       "unit": "frames/s", "n_gpus": WORLD}
+            if "ref_decode_secs" in d:
+                config4["cpu_baseline"] = {"decode_frames_per_s": WORLD * c4_frames / d["ref_decode_secs"],
+                                           "encode_frames_per_s": WORLD * (c4_enc - 1) / d["ref_encode_secs"],
+                                           "cores": WORLD, "kind": "reference" if d["ref_kind"] == "asm" else "reference (C path)",
+                                           "sample": "the same %d streams on %d host cores" % (WORLD, WORLD)}
+                config4["identical_to_reference"] = bool(d["decode_hash"] == d["ref_decode_hash"] and
+                                                         d["encode_hash"] == d["ref_encode_hash"])
+        except Exception as e:
+            config4 = {"error": repr(e)}
+
     if RANK == 0:
         line = {"metric": "1080p decode frames/sec", "value": value, "unit": "frames/s", "n_gpus": WORLD,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -731,7 +808,8 @@ def main():
                            "frame_units_per_step": S * nframes, "l2": "working set of a launch (%d streams x 3 x %.1f MB "
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
                            "parallelism": "independent streams, %d per GPU on %d CUDA stream(s)" % (S, G)},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encode_kernels": enc,
+                "roofline": roofline, "roofline_dense_coefficients": roofline_noisy, "cpu_baseline": cpu, "e2e": e2e,
+                "config4_2160p": config4, "encode_kernels": enc,
                 "encode_intra": enc_intra, "encode_inter": enc_inter, "motion_analysis": me_frame,
                 "gpu_launches": int(launches),
                 "clocks": clocks}

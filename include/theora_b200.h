@@ -259,11 +259,14 @@ OCG_API long ocg_launch_count(void);   /* kernels launched by this library so fa
    (67 vs 48 us per 32-frame launch: 4 KB boxes are too small to amortise the
    TMA issue cost), so it is opt-in.  Call before creating contexts. */
 OCG_API void ocg_set_lf_tma(int on);
-/* ocg_ctx_sync wait policy: 0 (default) = cudaStreamSynchronize (the driver
-   spins), 1 = record + wait on a cudaEventBlockingSync event, so the calling
-   thread sleeps and a host that runs more stream threads than cores keeps the
-   cores busy with other streams' entropy decoding during a flush. */
-OCG_API void ocg_set_blocking_sync(int on);
+/* Wait policy of ocg_dec_wait (and of ocg_ctx_sync: 0 = cudaStreamSynchronize, non-zero = a blocking event):
+   0 (default) spin on the completion flag; 1 sched_yield between looks; 2 SLEEP: one poller thread per
+   process watches the flags of every sleeping waiter and wakes it (semaphore).  With more stream threads
+   than cores -- the flush is asynchronous, so a thread mostly waits while the device works on its frame --
+   2 keeps the cores on entropy decoding. */
+OCG_API void ocg_set_blocking_sync(int policy);
+/* Test hook for policy 2 (no device involved): sleeps until *flag has reached seq; 1 = it has, 0 = timed out. */
+OCG_API int  ocg_test_sleep_until(volatile uint32_t *flag, uint32_t seq, int timeout_s);
 /* Per-stage device timing with CUDA events on the launching stream.  While
    enabled every stage launch (0 recon+copy, 1 loop filter, 2 borders) is
    bracketed by an event pair; collect() waits for them and returns the summed

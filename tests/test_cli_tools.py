@@ -238,3 +238,52 @@ def test_large_packets_span_pages_and_damage_is_survived(tmp_path):
     assert 1 <= len(frames2) < n
     for a, b in zip(frames2, frames):
         assert np.array_equal(a, b)
+
+
+def _page(serial, pageno, flags, granule, packet):
+    """One Ogg page (RFC 3533 section 6) holding one complete packet shorter than 255 bytes."""
+    hdr = struct.pack("<4sBBqIIIB", b"OggS", 0, flags, granule, serial, pageno, 0, 1) + bytes([len(packet)])
+    crc = ogg_crc(hdr + packet)
+    return hdr[:22] + struct.pack("<I", crc) + hdr[26:] + packet
+
+
+@pytest.mark.skipif(not have("ref_encoder_example", "ref_dump_video"), reason="tools/cli not built (needs the reference)")
+def test_reader_follows_the_theora_stream_of_a_multiplexed_file_and_resyncs_inside_a_damaged_page(tmp_path):
+    """(1) A multiplexed file begins with one beginning-of-stream page per logical stream; the reader must follow
+    the one whose first packet is a Theora identification header even if another stream's comes first (the
+    reference's dump_video probes every stream, examples/dump_video.c:330-370).  (2) When a page's SEGMENT TABLE
+    is damaged the page length read from it is garbage: the reader restarts the capture-pattern search right
+    behind the failed page's first byte instead of skipping what the header claimed (ogg_sync_pageseek does the
+    same), so the intact pages that follow are not swallowed."""
+    w, h, n = 176, 144, 6
+    y4m, ogv, out = str(tmp_path / "in.y4m"), str(tmp_path / "a.ogv"), str(tmp_path / "out.y4m")
+    write_y4m(y4m, w, h, n)
+    run(os.path.join(BIN, "ref_encoder_example"), "-o", ogv, "-v", "6", "-k", "3", y4m)
+    blob = open(ogv, "rb").read()
+    run(os.path.join(BIN, "ref_dump_video"), "-o", out, ogv)
+    _, _, want = read_y4m(out)
+    assert len(want) == n
+    # (1) another logical stream's BOS page in front, one of its data pages somewhere behind the headers
+    other_bos = _page(0x1234, 0, 2, 0, b"\x01vorbis" + bytes(23))
+    other_data = _page(0x1234, 1, 0, 0, bytes(40))
+    first_len = 27 + 1 + blob[27]  # the Theora BOS page: one packet, one lacing value
+    open(ogv, "wb").write(other_bos + blob[:first_len] + other_data + blob[first_len:])
+    run(os.path.join(BIN, "ref_dump_video"), "-o", out, ogv)
+    _, _, got = read_y4m(out)
+    assert len(got) == n and all(np.array_equal(a, b) for a, b in zip(got, want))
+    # (2) damage the segment COUNT of a late page so that it claims far more than it holds
+    packets, pages = parse_ogg(blob)
+    pos, starts = 0, []
+    while pos < len(blob):
+        nsegs = blob[pos + 26]
+        starts.append(pos)
+        pos += 27 + nsegs + sum(blob[pos + 27:pos + 27 + nsegs])
+    victim = starts[-3]
+    bad = bytearray(blob)
+    bad[victim + 26] = 255
+    open(ogv, "wb").write(bytes(bad))
+    log = run(os.path.join(BIN, "ref_dump_video"), "-o", out, ogv)
+    assert "bad CRC" in log
+    _, _, got = read_y4m(out)
+    # only the frames carried by the damaged page may be missing: the pages behind it must still be read
+    assert len(got) >= n - 3 and len(got) < n

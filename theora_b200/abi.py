@@ -166,6 +166,7 @@ _PROTOS = {
     "ocg_launch_count": (C.c_long, []),
     "ocg_set_lf_tma": (None, [C.c_int]),
     "ocg_set_blocking_sync": (None, [C.c_int]),
+    "ocg_test_sleep_until": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int]),
     "ocg_me_nmbs": (C.c_int, [C.POINTER(Geometry)]),
     "ocg_me_topology": (C.c_int, [C.POINTER(Geometry), C.c_void_p]),
     "ocg_me_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),

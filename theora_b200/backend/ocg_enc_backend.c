@@ -238,7 +238,7 @@ static int enc_me_prepass(ocg_enc_backend *b) {
     bufs[i] = st->ref_frame_idx[ROLE[i]];
     if (bufs[i] < 0) wanted = 0;
   }
-  if (!wanted) return 0;
+  /* device objects are made on the encoder's first pass (frame 0), whoever wants them first */
   if (b->me == NULL) {
     /* the reference's own tables: mb_maps (state.c:300-330), cneighbors (encode.c:967-1048) */
     ocg_me_topo *topo = (ocg_me_topo *)calloc(st->nmbs, sizeof(*topo));
@@ -264,6 +264,7 @@ static int enc_me_prepass(ocg_enc_backend *b) {
     }
     if (enc_inter_setup(b) < 0) return -1;
   }
+  if (!wanted) return 0;
   for (mbi = 0; mbi < st->nmbs; mbi++) {
     const oc_mb_enc_info *e = enc->mb_info + mbi;
     ocg_me_mb *m = b->me_tab + mbi;

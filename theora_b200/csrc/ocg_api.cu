@@ -9,6 +9,9 @@
 #include <vector>
 #include <stdint.h>
 #include <sched.h>
+#include <semaphore.h>
+#include <pthread.h>
+#include <condition_variable>
 #include <time.h>
 #include "ocg_internal.h"
 
@@ -202,8 +205,11 @@ static int check_frame(const ocg_geometry &g, const ocg_dec_frame &f) {
   if (f.ncoded < 0 || f.ncoded > g.nfrags) return fail(OCG_EINVAL, "coded fragment count out of range");
   if (f.ncoeff_rows < 0 || f.ncoeff_rows > (long)g.nfrags * 8) return fail(OCG_EINVAL, "coefficient row count out of range");
   if (f.ref_idx[OCG_FRAME_SELF] < 0 || f.ref_idx[OCG_FRAME_SELF] >= g.nrefs) return fail(OCG_EINVAL, "bad SELF buffer index");
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 2; i++) {
     if (f.ref_idx[i] >= g.nrefs) return fail(OCG_EINVAL, "bad reference buffer index");
+    /* the kernels form base pointers from these: a frame that may copy or predict needs both */
+    if (!f.intra_frame && f.ref_idx[i] < 0) return fail(OCG_EINVAL, "inter frame without a GOLD/PREV reference buffer");
+  }
   if (f.lf_limit < 0 || f.lf_limit > 127) return fail(OCG_EINVAL, "loop filter limit out of range");
   if (f.dc_residual && !ocg_dc_unpredict_supported(&g)) return fail(OCG_EIMPL, "DC un-prediction on the device does not support this frame size");
   return OCG_OK;
@@ -316,7 +322,7 @@ OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
 
 OCG_API void ocg_set_lf_tma(int on) { g_use_tma.store(on ? 1 : 0); }
 
-OCG_API void ocg_set_blocking_sync(int on) { g_blocking_sync.store(on ? 1 : 0); }
+OCG_API void ocg_set_blocking_sync(int policy) { g_blocking_sync.store(policy < 0 ? 0 : (policy > 2 ? 2 : policy)); }
 
 OCG_API void ocg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 
@@ -612,13 +618,119 @@ OCG_API int ocg_host_unregister(void *p) {
    memory) has reached `seq`: no driver call on the way, so stream threads do not meet in the driver's
    locks.  Wait policy as for ocg_ctx_sync: spin, or -- ocg_set_blocking_sync(1) -- give the core away
    between looks so that a host running more stream threads than cores keeps them busy. */
+/* ---- sleeping waits -----------------------------------------------------------------------------------
+   ocg_set_blocking_sync(2): a waiting stream thread SLEEPS (semaphore) and one poller thread per process
+   watches the completion flags of everybody who sleeps, so a host running several stream threads per core
+   spends its cycles on entropy decoding instead of on spinning or yielding waiters.  The poller itself
+   sleeps when nobody waits. */
+namespace {
+struct WaitSlot {
+  std::atomic<int> state{0}; /* 0 free, 1 being filled, 2 armed */
+  volatile uint32_t *flag = nullptr;
+  uint32_t seq = 0;
+  sem_t sem;
+};
+constexpr int kWaitSlots = 512;
+WaitSlot g_wait[kWaitSlots];
+std::atomic<int> g_wait_armed{0};
+/* never destroyed: the poller may be asleep on the condition variable when the process exits, and
+   destroying a condition variable that has a waiter blocks (glibc) */
+std::mutex &g_wait_mu = *new std::mutex;
+std::condition_variable &g_wait_cv = *new std::condition_variable;
+
+void *poller_main(void *) {
+  for (;;) {
+    if (g_wait_armed.load(std::memory_order_acquire) == 0) {
+      std::unique_lock<std::mutex> lk(g_wait_mu);
+      g_wait_cv.wait(lk, [] { return g_wait_armed.load(std::memory_order_acquire) > 0; });
+    }
+    for (int i = 0; i < kWaitSlots; i++) {
+      WaitSlot &w = g_wait[i];
+      if (w.state.load(std::memory_order_acquire) != 2) continue;
+      if ((int32_t)(*w.flag - w.seq) >= 0) {
+        /* claim (a waiter that times out at this moment loses the race and takes the wake-up), wake, then
+           release the slot: it belongs to one thread, which re-arms it only once it is free again */
+        int expect = 2;
+        if (!w.state.compare_exchange_strong(expect, 3, std::memory_order_acq_rel)) continue;
+        sem_post(&w.sem);
+        g_wait_armed.fetch_sub(1, std::memory_order_acq_rel);
+        w.state.store(0, std::memory_order_release);
+      }
+    }
+    __builtin_ia32_pause();
+  }
+  return nullptr;
+}
+
+void start_poller() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (int i = 0; i < kWaitSlots; i++) sem_init(&g_wait[i].sem, 0, 0);
+    pthread_t th;
+    pthread_attr_t at;
+    pthread_attr_init(&at);
+    pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+    pthread_create(&th, &at, poller_main, nullptr);
+    pthread_attr_destroy(&at);
+  });
+}
+
+/* returns false if there is no slot for this thread (the caller polls instead) or the wait timed out */
+bool sleep_until(volatile uint32_t *flag, uint32_t seq, int timeout_s) {
+  static std::atomic<int> next_slot{0};
+  static thread_local int my = -1; /* a thread keeps its slot: nobody else ever waits on its semaphore */
+  start_poller();
+  if (my < 0) {
+    const int i = next_slot.fetch_add(1);
+    if (i >= kWaitSlots) { next_slot.store(kWaitSlots); return false; }
+    my = i;
+  }
+  WaitSlot &w = g_wait[my];
+  /* the poller releases the slot right after waking us (unless it was descheduled in between) */
+  while (w.state.load(std::memory_order_acquire) != 0) sched_yield();
+  while (sem_trywait(&w.sem) == 0) {} /* a stale post from a wait that timed out */
+  w.flag = flag;
+  w.seq = seq;
+  w.state.store(2, std::memory_order_release);
+  if (g_wait_armed.fetch_add(1, std::memory_order_acq_rel) == 0) {
+    std::lock_guard<std::mutex> lk(g_wait_mu);
+    g_wait_cv.notify_one();
+  }
+  struct timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  ts.tv_sec += timeout_s;
+  if (sem_timedwait(&w.sem, &ts) == 0) return true;
+  /* timed out: disarm -- unless the poller has just claimed the slot: then its wake-up is on the way */
+  int expect = 2;
+  if (w.state.compare_exchange_strong(expect, 0, std::memory_order_acq_rel)) {
+    g_wait_armed.fetch_sub(1, std::memory_order_acq_rel);
+    return false;
+  }
+  while (sem_wait(&w.sem) != 0) {}
+  return true;
+}
+} /* namespace */
+
+/* Waits until the context's done flag (written by the last kernel of a flush into mapped host memory) has
+   reached `seq`: no driver call on the way, so stream threads do not meet in the driver's locks.  Wait
+   policy (ocg_set_blocking_sync): 0 spin, 1 yield the core between looks, 2 sleep until the poller thread
+   sees the flag. */
 static int wait_done(ocg_ctx *c, uint32_t seq) {
-  const bool yield = g_blocking_sync.load() != 0;
+  const int policy = g_blocking_sync.load();
   struct timespec t0;
   long spins = 0;
   bool timed = false;
   while ((int32_t)(*c->h_done - seq) < 0) {
-    if (yield) sched_yield();
+    if (policy == 2 && spins >= 64) {
+      if (!sleep_until(c->h_done, seq, 1) && (int32_t)(*c->h_done - seq) < 0) {
+        /* a faulted kernel never writes the flag: look at the stream */
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return fail(OCG_ECUDA, "flush failed on the device", e);
+        if (e == cudaSuccess && (int32_t)(*c->h_done - seq) < 0) return fail(OCG_ECUDA, "flush finished without its completion flag");
+      }
+      continue;
+    }
+    if (policy == 1) sched_yield();
     else __builtin_ia32_pause();
     if ((++spins & 0xFFF) == 0) {
       /* a faulted kernel never writes the flag: look at the stream now and then */
@@ -915,7 +1027,13 @@ OCG_API int ocg_dec_expand_setup(ocg_ctx *c, const int32_t *coded_order, const u
   CU(cudaMalloc(&x.d_tok, tokb * 4));
   CU(cudaMalloc(&x.d_cov, tokb * 4));
   CU(cudaMalloc(&x.d_coef, nf * 128));
-  CU(cudaMalloc(&x.d_nextz, nf));
+  {
+    /* ocg_tok_expand_kernel's global fall-back: per plane, whole words per thread (ocg_dec_expand.cu) */
+    size_t nmax = 0;
+    for (int pli = 0; pli < 3; pli++) nmax = nmax > (size_t)c->geom.planes[pli].nfrags ? nmax : (size_t)c->geom.planes[pli].nfrags;
+    const size_t need = ((((nmax + 1023) / 1024) + 3) & ~(size_t)3) * 1024;
+    CU(cudaMalloc(&x.d_nextz, 3 * need));
+  }
   CU(cudaMalloc(&x.d_lastz, nf));
   CU(cudaMalloc(&x.d_rmask, nf));
   CU(cudaMalloc(&x.d_xjob, sizeof(OcgExpandDev)));
@@ -1000,6 +1118,16 @@ OCG_API void ocg_flush_profile(double *prepare_s, double *launch_s, long *n, int
   if (launch_s) *launch_s = 1e-9 * (double)g_flush_launch_ns.load();
   if (n) *n = g_flush_n.load();
   if (reset) { g_flush_prep_ns.store(0); g_flush_launch_ns.store(0); g_flush_n.store(0); }
+}
+
+/* Test hook (no device involved): the sleeping wait on a caller-owned flag word; 1 = woken with the flag
+   at or past seq, 0 = timed out / no slot. */
+OCG_API int ocg_test_sleep_until(volatile uint32_t *flag, uint32_t seq, int timeout_s) {
+  if (flag == nullptr) return 0;
+  while ((int32_t)(*flag - seq) < 0) {
+    if (!sleep_until(flag, seq, timeout_s)) return (int32_t)(*flag - seq) >= 0;
+  }
+  return 1;
 }
 
 OCG_API int ocg_dec_wait(ocg_ctx *c) {

@@ -97,7 +97,29 @@ __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) { const uint
 
 /* ---- K1: one CTA per (zig-zag index, plane) list ------------------------------------------------- */
 #define TP_THREADS 256
-#define TP_CHUNK 16
+#define TP_CHUNK 32
+
+/* A chunk of token bytes as a map of the offset at which its first token starts (0..2: a token is at most
+   3 bytes long): exit offset into the next chunk (2 bits each, bits 0..5) and tokens started (16 bits each,
+   from bit 8).  Maps compose associatively, so token boundaries come out of a scan. */
+typedef unsigned long long cmap_t;
+__device__ __forceinline__ int cm_exit(cmap_t m, int s) { return (int)(m >> (2 * s)) & 3; }
+__device__ __forceinline__ unsigned cm_cnt(cmap_t m, int s) { return (unsigned)(m >> (8 + 16 * s)) & 0xFFFFu; }
+__device__ __forceinline__ cmap_t cm_make(const int ex[3], const unsigned cn[3]) {
+  return (cmap_t)(ex[0] | ex[1] << 2 | ex[2] << 4) | (cmap_t)cn[0] << 8 | (cmap_t)cn[1] << 24 | (cmap_t)cn[2] << 40;
+}
+__device__ __forceinline__ cmap_t cm_compose(cmap_t a, cmap_t b) { /* a first, then b */
+  int ex[3];
+  unsigned cn[3];
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    const int mid = cm_exit(a, s);
+    ex[s] = cm_exit(b, mid);
+    cn[s] = cm_cnt(a, s) + cm_cnt(b, mid);
+  }
+  return cm_make(ex, cn);
+}
+#define CM_IDENTITY ((cmap_t)(0 | 1 << 2 | 2 << 4))
 
 __global__ void __launch_bounds__(TP_THREADS)
 ocg_tok_parse_kernel(const OcgExpandDev *__restrict__ X, const uint8_t *__restrict__ bytes, uint32_t *__restrict__ tok,
@@ -106,58 +128,56 @@ ocg_tok_parse_kernel(const OcgExpandDev *__restrict__ X, const uint8_t *__restri
   const int z = list / 3, p = list - 3 * z;
   const int b0 = X->ti0[p][z];
   const int b1 = list == 191 ? X->ntoken_bytes : X->ti0[(p + 1) % 3][z + (p == 2)];
-  const int t = (int)threadIdx.x;
-  __shared__ uint32_t s_exit[TP_THREADS];   /* composed maps: exit offset for entry 0..2 (2 bits each) */
-  __shared__ uint32_t s_cnt[TP_THREADS][3]; /* ... and token counts */
-  __shared__ uint32_t s_cov[TP_THREADS];
+  const int t = (int)threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ cmap_t s_wmap[TP_THREADS / 32];
+  __shared__ uint32_t s_wcov[TP_THREADS / 32];
   __shared__ int s_carry[3];                /* entry offset, tokens so far, coverage so far */
   if (t == 0) { s_carry[0] = 0; s_carry[1] = 0; s_carry[2] = 0; }
   __syncthreads();
   for (int tile = b0; tile < b1; tile += TP_THREADS * TP_CHUNK) {
     const int c0 = tile + t * TP_CHUNK;
+    const int clen = min(TP_CHUNK, max(0, b1 - c0));
     uint8_t loc[TP_CHUNK + 2];
 #pragma unroll
-    for (int i = 0; i < TP_CHUNK + 2; i++) loc[i] = c0 + i < b1 ? bytes[c0 + i] : (uint8_t)15;
-    const int clen = min(TP_CHUNK, max(0, b1 - c0));
+    for (int i = 0; i < TP_CHUNK + 2; i++) loc[i] = (uint8_t)15;
+    if (clen > 0) {
+      for (int i = 0; i < TP_CHUNK + 2 && c0 + i < b1; i++) loc[i] = bytes[c0 + i];
+    }
     /* this chunk as a map of the entry offset */
-    int ex[3], cn[3];
+    cmap_t mine = CM_IDENTITY;
+    if (clen > 0) {
+      int ex[3];
+      unsigned cn[3];
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      int pos = s, n = 0;
-      while (pos < clen) { pos += tok_len(loc[pos]); n++; }
-      ex[s] = clen == TP_CHUNK ? pos - TP_CHUNK : 0;
-      cn[s] = n;
-    }
-    if (clen <= 0) { ex[0] = 0; ex[1] = 1; ex[2] = 2; cn[0] = cn[1] = cn[2] = 0; } /* identity */
-    else if (clen < TP_CHUNK) { /* last chunk of the list: the exit is never used; offsets past the end hold no token */ }
-    s_exit[t] = (uint32_t)ex[0] | (uint32_t)ex[1] << 2 | (uint32_t)ex[2] << 4;
-    s_cnt[t][0] = (uint32_t)cn[0]; s_cnt[t][1] = (uint32_t)cn[1]; s_cnt[t][2] = (uint32_t)cn[2];
-    __syncthreads();
-    /* inclusive scan of map composition (apply earlier chunk first) */
-    for (int d = 1; d < TP_THREADS; d <<= 1) {
-      uint32_t ne = 0, nc[3] = {0, 0, 0};
-      const bool act = t >= d;
-      if (act) {
-        const uint32_t ea = s_exit[t - d], eb = s_exit[t];
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-          const int mid = (int)(ea >> (2 * s)) & 3;
-          ne |= ((eb >> (2 * mid)) & 3u) << (2 * s);
-          nc[s] = s_cnt[t - d][s] + s_cnt[t][mid];
-        }
+      for (int s = 0; s < 3; s++) {
+        int pos = s;
+        unsigned n = 0;
+        while (pos < clen) { pos += tok_len(loc[pos]); n++; }
+        ex[s] = clen == TP_CHUNK ? pos - TP_CHUNK : 0; /* the exit of a list's last chunk is never used */
+        cn[s] = n;
       }
-      __syncthreads();
-      if (act) { s_exit[t] = ne; s_cnt[t][0] = nc[0]; s_cnt[t][1] = nc[1]; s_cnt[t][2] = nc[2]; }
-      __syncthreads();
+      mine = cm_make(ex, cn);
     }
+    /* inclusive scan of the composition: inside the warp by shuffles, across the 8 warps serially */
+    cmap_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const cmap_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc = cm_compose(o, inc);
+    }
+    if (lane == 31) s_wmap[warp] = inc;
+    __syncthreads();
     const int entry0 = s_carry[0], tok0 = s_carry[1];
-    /* my entry offset / token index: the composition of the chunks before me, applied to the tile's entry */
-    int my_entry = entry0, my_tok = tok0;
-    if (t > 0) {
-      my_entry = (int)(s_exit[t - 1] >> (2 * entry0)) & 3;
-      my_tok = tok0 + (int)s_cnt[t - 1][entry0];
+    const uint32_t cov0 = (uint32_t)s_carry[2];
+    cmap_t before = CM_IDENTITY; /* everything in this tile before my chunk */
+    for (int w = 0; w < warp; w++) before = cm_compose(before, s_wmap[w]);
+    {
+      const cmap_t prev = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+      if (lane > 0) before = cm_compose(before, prev);
     }
-    /* decode my tokens; coverage (fragments served) of my chunk */
+    const int my_entry = cm_exit(before, entry0);
+    const int my_tok = tok0 + (int)cm_cnt(before, entry0);
+    /* fragments served by my chunk's tokens */
     uint32_t mycov = 0;
     {
       int pos = my_entry;
@@ -167,18 +187,21 @@ ocg_tok_parse_kernel(const OcgExpandDev *__restrict__ X, const uint8_t *__restri
         pos += tok_len(loc[pos]);
       }
     }
-    s_cov[t] = mycov;
+    uint32_t cinc = mycov;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, cinc, d);
+      if (lane >= d) cinc = sat_add(o, cinc);
+    }
+    if (lane == 31) s_wcov[warp] = cinc;
     __syncthreads();
-    for (int d = 1; d < TP_THREADS; d <<= 1) {
-      uint32_t v = 0;
-      const bool act = t >= d;
-      if (act) v = sat_add(s_cov[t - d], s_cov[t]);
-      __syncthreads();
-      if (act) s_cov[t] = v;
-      __syncthreads();
+    uint32_t run = cov0;
+    for (int w = 0; w < warp; w++) run = sat_add(run, s_wcov[w]);
+    {
+      const uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, cinc, 1); /* lanes before me in this warp */
+      if (lane > 0) run = sat_add(run, excl);
     }
     {
-      uint32_t run = sat_add((uint32_t)s_carry[2], t > 0 ? s_cov[t - 1] : 0u);
       int pos = my_entry, j = my_tok;
       while (pos < clen) {
         const uint32_t w = tok_decode(loc + pos);
@@ -191,9 +214,13 @@ ocg_tok_parse_kernel(const OcgExpandDev *__restrict__ X, const uint8_t *__restri
     }
     __syncthreads();
     if (t == TP_THREADS - 1) {
-      s_carry[0] = (int)(s_exit[t] >> (2 * entry0)) & 3;
-      s_carry[1] = tok0 + (int)s_cnt[t][entry0];
-      s_carry[2] = (int)sat_add((uint32_t)s_carry[2], s_cov[t]);
+      cmap_t all = before;
+      all = cm_compose(all, mine);
+      uint32_t tot = cov0;
+      for (int w = 0; w < TP_THREADS / 32; w++) tot = sat_add(tot, s_wcov[w]);
+      s_carry[0] = cm_exit(all, entry0);
+      s_carry[1] = tok0 + (int)cm_cnt(all, entry0);
+      s_carry[2] = (int)tot;
     }
     __syncthreads();
   }
@@ -207,25 +234,47 @@ __global__ void __launch_bounds__(TX_THREADS)
 ocg_tok_expand_kernel(const OcgGeomDev g, const OcgExpandDev *__restrict__ X, const int32_t *__restrict__ order,
                       const uint32_t *__restrict__ words, const uint32_t *__restrict__ tok, const uint32_t *__restrict__ cov,
                       const int32_t *__restrict__ ntok, const uint16_t *__restrict__ dequant, int16_t *__restrict__ coef,
-                      uint8_t *nextz, uint8_t *__restrict__ lastz, uint8_t *__restrict__ rmask) {
+                      uint8_t *nextz_global, size_t nextz_stride, uint8_t *__restrict__ lastz, uint8_t *__restrict__ rmask,
+                      int nextz_in_smem) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
   const int p = (int)blockIdx.x;
   const OcgPlaneDev &P = g.p[p];
   const int n = P.nhfrags * P.nvfrags;
   const int t = (int)threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int per = (n + TX_THREADS - 1) / TX_THREADS;
-  const int pos0 = P.froffset + min(n, t * per), pos1 = P.froffset + min(n, (t + 1) * per);
+  /* a thread owns `per` consecutive positions of the plane's coded order (a multiple of 4: the step state
+     of four positions is one word) */
+  const int per = (((n + TX_THREADS - 1) / TX_THREADS) + 3) & ~3;
+  const int l0 = min(n, t * per), l1 = min(n, (t + 1) * per);
+  uint8_t *nextz = nextz_in_smem ? s_dyn : nextz_global + (size_t)p * nextz_stride; /* padded to whole words per thread */
+  const int32_t *ord = order + P.froffset;
   __shared__ int s_warp[32];
   __shared__ int s_total;
-  for (int i = pos0; i < pos1; i++) {
-    const int f = order[i];
-    const uint32_t w = words[f];
-    nextz[i] = (w & 1u) ? (uint8_t)0 : (uint8_t)255;
-    lastz[f] = 0;
-    rmask[f] = 0;
+  __shared__ int s_cntz[64 + 1]; /* positions waiting at each index */
+  if (t < 65) s_cntz[t] = 0;
+  __syncthreads();
+  {
+    int mine = 0;
+    for (int i = t * per; i < (t + 1) * per; i++) {
+      uint8_t v = 255;
+      if (i < n) {
+        const int f = ord[i];
+        if (words[f] & 1u) { v = 0; mine++; }
+        lastz[f] = 0;
+        rmask[f] = 0;
+      }
+      nextz[i] = v;
+    }
+    if (mine) atomicAdd(&s_cntz[0], mine);
   }
+  __syncthreads();
   for (int z = 0; z < 64; z++) {
+    if (s_cntz[z] == 0) continue; /* block-uniform: written before the previous step's barrier */
     int cnt = 0;
-    for (int i = pos0; i < pos1; i++) cnt += nextz[i] == z;
+    {
+      const uint32_t zz = 0x01010101u * (uint32_t)z;
+      const uint32_t *wz = (const uint32_t *)(nextz + t * per);
+      for (int k = 0; k < per / 4; k++) cnt += __popc(__vcmpeq4(wz[k], zz)) >> 3;
+    }
     /* exclusive block scan of cnt */
     int inc = cnt;
 #pragma unroll
@@ -246,54 +295,54 @@ ocg_tok_expand_kernel(const OcgGeomDev g, const OcgExpandDev *__restrict__ X, co
       if (lane == 31) s_total = w2;
     }
     __syncthreads();
-    const int total = s_total;
     int r = s_warp[warp] + inc - cnt;
-    __syncthreads(); /* s_warp / s_total are rewritten by the next step */
-    if (total == 0) continue;
-    if (cnt == 0) continue;
-    const int list = z * 3 + p;
-    const int b0 = X->ti0[p][z];
-    const int nt = ntok[list];
-    const uint32_t eob0 = (uint32_t)min(X->eob_runs[p][z], (int)COV_SAT);
-    const uint32_t *ltok = tok + b0, *lcov = cov + b0;
-    int j = -1;
-    for (int i = pos0; i < pos1; i++) {
-      if (nextz[i] != z) continue;
-      const int f = order[i];
-      int nz = 255;
-      if ((uint32_t)r >= eob0) {
-        const uint32_t rr = (uint32_t)r - eob0;
-        if (j < 0) { /* largest j with cov[j] <= rr */
-          int lo = 0, hi = nt;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (lcov[mid] <= rr) lo = mid + 1; else hi = mid; }
-          j = lo - 1;
-        } else {
-          while (j + 1 < nt && lcov[j + 1] <= rr) j++;
-        }
-        if (j >= 0 && j < nt) {
-          const uint32_t w = ltok[j];
-          if (!(w & TOK_EOB)) {
-            const int pos2 = z + (int)((w >> 16) & 127u);
-            if (pos2 > 0 && pos2 < 64) {
-              const uint32_t fw = words[f];
-              const int qii = (int)(fw >> 2) & 15, qti = ((fw >> 8) & 7u) != 1u; /* mb_mode != OC_MODE_INTRA */
-              const int qi = X->qis[qii < X->nqis ? qii : 0];
-              const int q = dequant[(((size_t)qi * 3 + p) * 2 + qti) * 64 + pos2];
-              const int v = (int)(int16_t)(w & 0xFFFFu) * q; /* decode.c:1573 */
-              if (v != 0) {
-                const int nat = c_zigzag[pos2];
-                coef[(size_t)f * 64 + nat] = (int16_t)v;
-                rmask[f] |= (uint8_t)(1u << (nat >> 3));
+    if (cnt != 0) {
+      const int list = z * 3 + p;
+      const int b0 = X->ti0[p][z];
+      const int nt = ntok[list];
+      const uint32_t eob0 = (uint32_t)min(X->eob_runs[p][z], (int)COV_SAT);
+      const uint32_t *ltok = tok + b0, *lcov = cov + b0;
+      int j = -1;
+      for (int i = l0; i < l1; i++) {
+        if (nextz[i] != z) continue;
+        const int f = ord[i];
+        int nz = 255;
+        if ((uint32_t)r >= eob0) {
+          const uint32_t rr = (uint32_t)r - eob0;
+          if (j < 0) { /* largest j with cov[j] <= rr */
+            int lo = 0, hi = nt;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (lcov[mid] <= rr) lo = mid + 1; else hi = mid; }
+            j = lo - 1;
+          } else {
+            while (j + 1 < nt && lcov[j + 1] <= rr) j++;
+          }
+          if (j >= 0 && j < nt) {
+            const uint32_t w = ltok[j];
+            if (!(w & TOK_EOB)) {
+              const int pos2 = z + (int)((w >> 16) & 127u);
+              if (pos2 > 0 && pos2 < 64) {
+                const uint32_t fw = words[f];
+                const int qii = (int)(fw >> 2) & 15, qti = ((fw >> 8) & 7u) != 1u; /* mb_mode != OC_MODE_INTRA */
+                const int qi = X->qis[qii < X->nqis ? qii : 0];
+                const int q = dequant[(((size_t)qi * 3 + p) * 2 + qti) * 64 + pos2];
+                const int v = (int)(int16_t)(w & 0xFFFFu) * q; /* decode.c:1573 */
+                if ((int16_t)v != 0) {
+                  const int nat = c_zigzag[pos2];
+                  coef[(size_t)f * 64 + nat] = (int16_t)v;
+                  rmask[f] |= (uint8_t)(1u << (nat >> 3));
+                }
               }
+              if (pos2 + 1 < 64) nz = pos2 + 1;
             }
-            if (pos2 + 1 < 64) nz = pos2 + 1;
           }
         }
+        nextz[i] = (uint8_t)nz;
+        if (nz == 255) lastz[f] = (uint8_t)z;
+        else atomicAdd(&s_cntz[nz], 1);
+        r++;
       }
-      nextz[i] = (uint8_t)nz;
-      if (nz == 255) lastz[f] = (uint8_t)z;
-      r++;
     }
+    __syncthreads(); /* s_cntz of later steps is complete; s_warp / s_total may be rewritten */
   }
 }
 
@@ -406,8 +455,17 @@ void ocg_launch_stage_tokens(const OcgJobDev *h_job, OcgJobDev *d_job, const Ocg
 void ocg_launch_expand(const OcgGeomDev &g, const OcgExpandDev *d_x, const OcgExpandBufs &B, const int16_t *dc_final,
                        const OcgJobDev *d_job, ocg_frag_rec *d_recs, cudaStream_t st) {
   ocg_tok_parse_kernel<<<192, TP_THREADS, 0, st>>>(d_x, B.tokens, B.tok, B.cov, B.ntok);
-  ocg_tok_expand_kernel<<<3, TX_THREADS, 0, st>>>(g, d_x, B.order, B.words, B.tok, B.cov, B.ntok, B.dequant, B.coef, B.nextz,
-                                                  B.lastz, B.rmask);
+  {
+    /* the per-position step state lives in shared memory when the largest plane fits (4K luma: 130 KB) */
+    int nmax = 0;
+    for (int p = 0; p < 3; p++) nmax = nmax > g.p[p].nhfrags * g.p[p].nvfrags ? nmax : g.p[p].nhfrags * g.p[p].nvfrags;
+    const size_t need = (size_t)((((nmax + TX_THREADS - 1) / TX_THREADS) + 3) & ~3) * TX_THREADS;
+    const int in_smem = need <= 200 * 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(ocg_tok_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    ocg_tok_expand_kernel<<<3, TX_THREADS, in_smem ? need : 0, st>>>(g, d_x, B.order, B.words, B.tok, B.cov, B.ntok, B.dequant,
+                                                                     B.coef, B.nextz, need, B.lastz, B.rmask, in_smem);
+  }
   ocg_rec_build_kernel<<<(unsigned)((g.nfrags + 255) / 256), 256, 0, st>>>(g, B.words, B.mvs, B.buf_off, B.lastz, B.rmask, B.coef,
                                                                          dc_final, d_job, d_recs);
   ocg_count_launch(3);

@@ -140,8 +140,8 @@ int main(int argc, char **argv) {
   if (!headers_done) { fprintf(stderr, "no Theora data packets found\n"); return 1; }
   {
     double secs = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
-    fprintf(stderr, "%ld frames, %ld pages (%ld bad CRC, %ld lost), %.2f fps\n", frames, rd.pages_read, rd.crc_errors,
-            rd.lost_pages, secs > 0 ? frames / secs : 0.0);
+    fprintf(stderr, "%ld frames, %ld pages (%ld bad CRC, %ld lost%s), %.2f fps\n", frames, rd.pages_read, rd.crc_errors,
+            rd.lost_pages, rd.truncated ? ", file truncated inside a page" : "", secs > 0 ? frames / secs : 0.0);
   }
   th_decode_free(td);
   th_comment_clear(&tc);

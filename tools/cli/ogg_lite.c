@@ -124,6 +124,7 @@ static int load_page(oggl_reader *r) {
   for (;;) {
     size_t blen = 0;
     uint32_t crc, want, serial, pageno;
+    long cap_pos;
     int i, c, matched = 0;
     /* resynchronise on the capture pattern (RFC 3533 section 6.1) */
     while (matched < 4) {
@@ -132,11 +133,12 @@ static int load_page(oggl_reader *r) {
       if (c == "OggS"[matched]) matched++;
       else matched = c == 'O' ? 1 : 0;
     }
+    cap_pos = ftell(r->f); /* just behind the capture pattern; -1 on a pipe */
     memcpy(r->hdr, "OggS", 4);
-    if (fread(r->hdr + 4, 1, 23, r->f) != 23) return 0;
+    if (fread(r->hdr + 4, 1, 23, r->f) != 23) { r->truncated = 1; return 0; }
     if (r->hdr[4] != 0) return -2; /* stream structure version */
     r->nsegs = r->hdr[26];
-    if (fread(r->hdr + 27, 1, (size_t)r->nsegs, r->f) != (size_t)r->nsegs) return 0;
+    if (fread(r->hdr + 27, 1, (size_t)r->nsegs, r->f) != (size_t)r->nsegs) { r->truncated = 1; return 0; }
     for (i = 0; i < r->nsegs; i++) blen += r->hdr[27 + i];
     if (blen > r->body_cap) {
       unsigned char *nb = (unsigned char *)realloc(r->body, blen);
@@ -144,17 +146,34 @@ static int load_page(oggl_reader *r) {
       r->body = nb;
       r->body_cap = blen;
     }
-    if (fread(r->body, 1, blen, r->f) != blen) return 0;
+    if (fread(r->body, 1, blen, r->f) != blen) {
+      /* a damaged segment table can claim more than the file holds: look for a page behind the pattern
+         first, and call the file truncated only if there is none */
+      r->truncated = 1;
+      if (cap_pos >= 4 && fseek(r->f, cap_pos - 3, SEEK_SET) == 0) { r->crc_errors++; continue; }
+      return 0;
+    }
+    r->truncated = 0;
     want = get32(r->hdr + 22);
     put32(r->hdr + 22, 0);
     crc = oggl_crc(r->hdr, (size_t)(27 + r->nsegs), 0);
     crc = oggl_crc(r->body, blen, crc);
-    if (crc != want) { r->crc_errors++; continue; } /* damaged page: drop it, stay in sync */
+    if (crc != want) {
+      /* damaged page.  Its header (segment count, lacing values) may be what is damaged, so the size just
+         skipped cannot be trusted: search again from the byte after this capture pattern's first byte, the
+         way libogg's ogg_sync_pageseek does.  (On a pipe: carry on behind the page.) */
+      r->crc_errors++;
+      if (cap_pos >= 4) fseek(r->f, cap_pos - 3, SEEK_SET);
+      continue;
+    }
     serial = get32(r->hdr + 14);
     pageno = get32(r->hdr + 18);
     r->flags = r->hdr[5];
     if (!r->have_serial) {
       if (!(r->flags & 2)) continue; /* wait for a beginning-of-stream page */
+      /* a multiplexed file starts with one BOS page per logical stream: follow the Theora one (its first
+         packet is the identification header, 0x80 "theora", spec section 6.2) */
+      if (blen < 7 || r->body[0] != 0x80 || memcmp(r->body + 1, "theora", 6) != 0) { r->other_streams++; continue; }
       r->have_serial = 1;
       r->serial = serial;
       r->next_pageno = pageno;

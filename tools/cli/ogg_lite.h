@@ -43,7 +43,7 @@ typedef struct oggl_packet {
 typedef struct oggl_reader {
   FILE *f;
   int have_serial;
-  uint32_t serial;         /* logical stream being followed (the first one that begins) */
+  uint32_t serial;         /* logical stream being followed: the first Theora stream that begins */
   uint32_t next_pageno;
   unsigned char *pkt;      /* packet being assembled */
   size_t pkt_len, pkt_cap;
@@ -58,6 +58,8 @@ typedef struct oggl_reader {
   int last_packet_seg;     /* index of the segment that ends the last complete packet of the page */
   int page_loaded, first_packet_done;
   long pages_read, crc_errors, lost_pages;
+  long other_streams;      /* beginning-of-stream pages of other (non-Theora) logical streams seen before ours */
+  int truncated;           /* the file ended inside a page */
 } oggl_reader;
 
 int  oggl_reader_init(oggl_reader *r, FILE *f);

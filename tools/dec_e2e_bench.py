@@ -13,7 +13,8 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def main():
-    path, threads, with_ref = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    path, threads, ref_threads = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])  # ref_threads 0: no reference pass
+    with_ref = ref_threads > 0
     dc_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1   # streams.DC_HOST
     blocking = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     expand = int(sys.argv[6]) if len(sys.argv) > 6 else 0     # OCG_EXPAND_DEVICE
@@ -48,7 +49,7 @@ def main():
         ours.append((secs, s2.h2d_bytes, s2.d2h_bytes, s2.flush_seconds / max(s2.frames, 1),
                      s2.wait_seconds / max(s2.frames, 1)))
         if R is not None:
-            rs = R.refh_decode_time(hr, threads, 1, C.byref(rh))
+            rs = R.refh_decode_time(hr, ref_threads, 1, C.byref(rh))
             assert rs > 0
             refs.append(rs)
     prep, launch, nfl = C.c_double(), C.c_double(), C.c_long()
@@ -65,6 +66,7 @@ def main():
         out["ref_secs"] = sorted(refs)[1]
         out["ref_hash"] = int(rh.value)
         out["ref_kind"] = kind
+        out["ref_threads"] = ref_threads
     print(json.dumps(out))
 
 

@@ -7,6 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
@@ -18,11 +19,12 @@ def main():
     path = "/tmp/e2e_variants.ogs"
     open(path, "wb").write(blob)
     cores = len(os.sched_getaffinity(0))
-    grid = [(1, 0, 1, 1), (4, 0, 1, 1), (8, 0, 1, 1), (cores, 0, 1, 1), (2 * cores, 1, 1, 0), (3 * cores, 1, 1, 0),
-            (4 * cores, 1, 1, 0), (cores, 0, 0, 0), (3 * cores, 1, 0, 0)]
+    # (threads, wait policy 0 spin / 1 yield / 2 sleep, dc 1 host / 0 device, reference pass)
+    grid = [(1, 0, 1, 1), (cores, 0, 1, 1), (2 * cores, 2, 1, 0), (3 * cores, 2, 1, 0), (4 * cores, 2, 1, 0),
+            (3 * cores, 1, 1, 0), (2 * cores, 2, 0, 0), (3 * cores, 2, 0, 0), (4 * cores, 2, 0, 0), (6 * cores, 2, 0, 0)]
     for threads, blocking, dc_mode, ref in grid:
-        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dec_e2e_bench.py"), path, str(threads), str(ref),
-                            str(dc_mode), str(blocking)], capture_output=True, text=True, timeout=900)
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dec_e2e_bench.py"), path, str(threads), str(threads if ref else 0),
+                            str(dc_mode), str(blocking)], capture_output=True, text=True, timeout=150)
         if p.returncode != 0:
             print(json.dumps({"threads": threads, "error": p.stderr[-300:]}), flush=True)
             continue
