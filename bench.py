@@ -474,7 +474,7 @@ def main():
     ap.add_argument("--e2e-threads-per-core", type=int, default=3,
                     help="decoder stream threads per host core of the e2e pass (the flush is asynchronous: a thread "
                          "that waits for its frame yields the core to another stream's entropy decode)")
-    ap.add_argument("--e2e-dc", default="device", choices=["device", "host"], help="where the e2e pass undoes the DC prediction")
+    ap.add_argument("--e2e-dc", default="host", choices=["device", "host"], help="where the e2e pass undoes the DC prediction")
     ap.add_argument("--e2e-variants", action="store_true", help="also time other e2e configurations (reported as alternatives)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-noisy", action="store_true", help="skip the dense-coefficient roofline workload")

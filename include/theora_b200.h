@@ -485,7 +485,23 @@ typedef struct ocg_enc_inter_tables {
   const uint32_t *cand_satd;    /* same indexing                                                */
   const int32_t  *cand_dc;
   long            d2h_bytes;
+  /* speculative frag_sub + fDCT + quantiser (oc_enc_block_transform_quantize, analyze.c:704-782) against the
+     predictors of candidates OCG_ENC_FQ_CAND0/1, for every fragment and each of the frame's fq_nqis inter
+     quantisers (0: not produced).  fq_desc[sel * nfrags + fragi]; the arrays of an entry sit back to back in
+     fq_pool at 8 * off int16: (count+7)/8*8 coefficients of the transform output, then as many per
+     quantiser; everything beyond `count` is zero for every quantiser.  off == UINT32_MAX: not available. */
+  int32_t         fq_nqis;
+  const struct ocg_enc_fq_desc *fq_desc;
+  const int16_t  *fq_pool;
 } ocg_enc_inter_tables;
+typedef struct ocg_enc_fq_desc {
+  uint32_t off;
+  uint8_t  count;      /* leading zig-zag coefficients stored (1..64) */
+  uint8_t  nz[3];      /* oc_enc_quantize's return value per quantiser */
+} ocg_enc_fq_desc;
+#define OCG_ENC_FQ_NSEL  2
+#define OCG_ENC_FQ_CAND0 0   /* PREV (0,0)              */
+#define OCG_ENC_FQ_CAND1 3   /* PREV, refined vector    */
 static inline size_t ocg_enc_cand_index(const ocg_enc_inter_tables *t, int k, int fragi) {
   return fragi < t->nluma ? (size_t)k * (size_t)t->nluma + (size_t)fragi
                           : (size_t)t->ncand * (size_t)t->nluma + (size_t)k * (size_t)(t->nfrags - t->nluma) + (size_t)(fragi - t->nluma);
@@ -496,8 +512,13 @@ OCG_API int  ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me,
                                   const int32_t *border_fragi, const int64_t *border_mask, int nborder);
 OCG_API void ocg_enc_inter_destroy(ocg_enc_inter *ei);
 OCG_API int  ocg_enc_inter_border_slot(const ocg_enc_inter *ei, int fragi);
+/* The frame's inter quantiser tables for the speculative transform (layout of ocg_enc_fdct_quant_batch; qti 1
+   is read); NULL / nqis 0 switches it off for the next prepass.  Call before ocg_enc_inter_prepass. */
+OCG_API int  ocg_enc_inter_quant_tables(ocg_enc_inter *ei, const uint16_t *dequant, const int16_t *enquant, int nqis);
 OCG_API int  ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, int gold_buf, int with_cands,
                                    ocg_enc_inter_tables *out);
+/* After the stream has drained (ocg_ctx_sync): fetches the filled part of the coefficient pool.  Synchronous. */
+OCG_API int  ocg_enc_inter_finish(ocg_enc_inter *ei, ocg_enc_inter_tables *out);
 
 /* Intra-frame analysis pre-pass (BASELINE config "intra-only encode").  The
    per-block encoder hooks return their result synchronously to serial host

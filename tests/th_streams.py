@@ -35,7 +35,9 @@ class EncBackendStats(C.Structure):
                 ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long), ("prepass_seconds", C.c_double),
                 ("flush_seconds", C.c_double), ("me_frames", C.c_long), ("me_gold_refines", C.c_long),
                 ("me_repairs", C.c_long), ("satd_lookups", C.c_long), ("satd_host", C.c_long),
-                ("ssd_lookups", C.c_long), ("ssd_host", C.c_long), ("intra_satd_lookups", C.c_long)]
+                ("ssd_lookups", C.c_long), ("ssd_host", C.c_long), ("intra_satd_lookups", C.c_long),
+                ("fdct_quant_lookups", C.c_long), ("fdct_quant_host", C.c_long),
+                ("me_queue_seconds", C.c_double), ("me_sync_seconds", C.c_double)]
 
 
 ENC_AUTO, ENC_HOST = 0, 1

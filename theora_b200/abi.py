@@ -193,6 +193,8 @@ _PROTOS = {
                                        C.c_int]),
     "ocg_enc_inter_destroy": (None, [C.c_void_p]),
     "ocg_enc_inter_border_slot": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocg_enc_inter_quant_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "ocg_enc_inter_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ocg_enc_inter_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ocg_enc_intra_reserve": (C.c_int, [C.c_void_p]),
     "ocg_enc_intra_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

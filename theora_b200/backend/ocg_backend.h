@@ -100,6 +100,10 @@ typedef struct ocg_enc_backend_stats {
   long   ssd_lookups;       /* frag_ssd / frag_border_ssd of oc_skip_cost answered from the device table   */
   long   ssd_host;          /* ... of the block just reconstructed (analyze.c:829-835): host               */
   long   intra_satd_lookups;
+  long   fdct_quant_lookups; /* inter blocks whose frag_sub + fdct8x8 + quantize came from the device tables */
+  long   fdct_quant_host;    /* ... computed by the reference's C kernels (another predictor, pool exhausted) */
+  double me_queue_seconds;  /* host time queueing the inter-frame pre-pass (copies + kernels)       */
+  double me_sync_seconds;   /* ... and waiting for its results                                      */
 } ocg_enc_backend_stats;
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset);
 /* Test instrumentation: a snapshot at the start of every analysis pass of an encoder that runs on the

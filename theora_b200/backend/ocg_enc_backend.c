@@ -90,6 +90,13 @@ typedef struct ocg_enc_backend {
   ogg_int32_t         *border_slot;    /* [nfrags] index into itab.border_ssd, or -1 */
   ogg_int64_t         *border_mask;    /* [nfrags] the mask that slot was computed with */
   const unsigned char *pool0;          /* ref_frame_handle + base_off: what the candidates' tap offsets are relative to */
+  /* speculative sub + fDCT + quantiser tables (itab.fq_*) */
+  int                  fq_ok;          /* they serve the pass in progress (same quantisers as when they were made) */
+  int                  fq_qis[3], fq_nq;
+  long                 fq_cur;         /* entry serving the block in flight (frag_sub -> fdct8x8 -> quantize), or -1 */
+  int                  fq_pli;
+  const unsigned char *c2_dst, *c2_r1, *c2_r2; /* the last frag_copy2 */
+  long                 n_fq_hit, n_fq_miss;
   long                 n_me_repairs, n_gold_refines;
   long                 n_satd_hit, n_satd_miss, n_ssd_hit, n_ssd_host, n_isatd_hit; /* per pass, folded into the stats at the flush */
   /* quantiser tables in the layout of ocg_enc_fdct_quant_batch */
@@ -278,12 +285,41 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   else if (b->inter_frame) flags |= OCG_ME_REFINE_4MV;
   if (enc->prevframe_dropped) flags |= OCG_ME_DROPPED;
   b->itab_valid = 0;
-  if (ocg_me_write_async(b->me, b->me_tab) < 0 || ocg_me_frame(b->me, bufs, flags, NULL) < 0 ||
-      ocg_me_read_async(b->me, b->me_tab) < 0 ||
-      (b->inter_frame && ocg_enc_inter_prepass(b->ei, bufs[0], bufs[3], bufs[4], 1, &b->itab) < 0) ||
-      ocg_ctx_sync(b->ctx) < 0) {
-    enc_fail(b, "motion analysis on the device failed");
-    return -1;
+  b->fq_nq = 0;
+  {
+    const double tq0 = enc_now_s();
+    double tq1;
+    int pli, qii, zzi, r = 0;
+    if (b->inter_frame) {
+      /* the frame's inter quantisers, condensed by analyze.c:544-564 just before this hook */
+      for (pli = 0; pli < 3; pli++)
+        for (qii = 0; qii < b->nqis; qii++) {
+          const oc_iquant *iq = (const oc_iquant *)enc->enquant[pli][qii][1];
+          memcpy(b->dequant[pli][1][qii], enc->dequant[pli][qii][1], 64 * sizeof(ogg_uint16_t));
+          for (zzi = 0; zzi < 64; zzi++) {
+            b->enquant[pli][1][qii][zzi][0] = iq[zzi].m;
+            b->enquant[pli][1][qii][zzi][1] = iq[zzi].l;
+          }
+        }
+      r = ocg_enc_inter_quant_tables(b->ei, &b->dequant[0][0][0][0], &b->enquant[0][0][0][0][0], b->nqis);
+      for (qii = 0; qii < 3; qii++) b->fq_qis[qii] = st->qis[qii < st->nqis ? qii : 0];
+      b->fq_nq = b->nqis;
+    }
+    if (r < 0 || ocg_me_write_async(b->me, b->me_tab) < 0 || ocg_me_frame(b->me, bufs, flags, NULL) < 0 ||
+        ocg_me_read_async(b->me, b->me_tab) < 0 ||
+        (b->inter_frame && ocg_enc_inter_prepass(b->ei, bufs[0], bufs[3], bufs[4], 1, &b->itab) < 0)) {
+      enc_fail(b, "motion analysis on the device failed");
+      return -1;
+    }
+    tq1 = enc_now_s();
+    if (ocg_ctx_sync(b->ctx) < 0 || (b->inter_frame && ocg_enc_inter_finish(b->ei, &b->itab) < 0)) {
+      enc_fail(b, "motion analysis on the device failed");
+      return -1;
+    }
+    pthread_mutex_lock(&g_estats_lock);
+    g_estats.me_queue_seconds += tq1 - tq0;
+    g_estats.me_sync_seconds += enc_now_s() - tq1;
+    pthread_mutex_unlock(&g_estats_lock);
   }
   b->itab_valid = b->inter_frame;
   memset(b->gold_dirty, 0, st->nmbs);
@@ -324,7 +360,17 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
   b->idct_pending = 0;
   b->nqis = nqis;
   b->n_satd_hit = b->n_satd_miss = b->n_ssd_hit = b->n_ssd_host = b->n_isatd_hit = 0;
+  b->n_fq_hit = b->n_fq_miss = 0;
   if (b->inter_capable && enc_me_prepass(b) < 0) return;
+  /* the speculative transform tables were made for one set of quantisers: a re-analysis with another uses
+     the C kernels */
+  b->fq_cur = -1;
+  b->c2_dst = NULL;
+  b->fq_ok = b->inter_frame && b->itab_valid && b->itab.fq_nqis > 0 && b->fq_nq == nqis;
+  if (b->fq_ok) {
+    int qii;
+    for (qii = 0; qii < nqis; qii++) if (b->fq_qis[qii] != st->qis[qii]) b->fq_ok = 0;
+  }
   if (!b->inter_frame) {
     /* analyze.c:544-564 has just condensed the tables for this frame */
     for (pli = 0; pli < 3; pli++)
@@ -397,6 +443,8 @@ static void enc_flush(ocg_enc_backend *b) {
   g_estats.ssd_lookups += b->n_ssd_hit;
   g_estats.ssd_host += b->n_ssd_host;
   g_estats.intra_satd_lookups += b->n_isatd_hit;
+  g_estats.fdct_quant_lookups += b->n_fq_hit;
+  g_estats.fdct_quant_host += b->n_fq_miss;
   g_estats.coeff_rows += b->nrows;
   g_estats.h2d_bytes += (long)b->geom.nfrags * 16 + (long)b->nrows * 16;
   if (b->inter_capable) g_estats.d2h_bytes += (long)b->geom.ref_frame_sz;
@@ -531,6 +579,7 @@ static void ocge_frag_sub_128(ogg_int16_t _diff[64], const unsigned char *_src, 
   if (b != NULL) {
     b->idct_pending = 0;
     b->cur_fragi = -1;
+    b->fq_cur = -1;
     if (b->tables) {
       /* the residual itself stays on the device; its only consumer is fdct8x8 */
       b->cur_fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
@@ -541,14 +590,59 @@ static void ocge_frag_sub_128(ogg_int16_t _diff[64], const unsigned char *_src, 
   oc_enc_frag_sub_128_c(_diff, _src, _ystride);
 }
 
+/* oc_enc_frag_copy2 (analyze.c:741): the two-tap predictor is built in the block's place in SELF, then used
+   as frag_sub's reference; remembered so that the subtraction can be recognised by its taps. */
+static void ocge_frag_copy2(unsigned char *_dst, const unsigned char *_src1, const unsigned char *_src2, int _ystride) {
+  ocg_enc_backend *b = enc_live();
+  if (b != NULL) { b->c2_dst = _dst; b->c2_r1 = _src1; b->c2_r2 = _src2; }
+  oc_enc_frag_copy2_c(_dst, _src1, _src2, _ystride);
+}
+
 static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, const unsigned char *_ref, int _ystride) {
   ocg_enc_backend *b = enc_live();
-  if (b != NULL) { b->idct_pending = 0; b->cur_fragi = -1; }
+  if (b != NULL) {
+    b->idct_pending = 0;
+    b->cur_fragi = -1;
+    b->fq_cur = -1;
+    if (b->fq_ok) {
+      /* served from the speculative tables iff the predictor is one they were computed with */
+      ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
+      if (fragi >= 0) {
+        static const int SEL_CAND[OCG_ENC_FQ_NSEL] = {OCG_ENC_FQ_CAND0, OCG_ENC_FQ_CAND1};
+        ptrdiff_t r1, r2 = INT32_MIN;
+        int sel;
+        if (_ref == b->c2_dst) { r1 = b->c2_r1 - b->pool0; r2 = b->c2_r2 - b->pool0; }
+        else r1 = _ref - b->pool0;
+        for (sel = 0; sel < OCG_ENC_FQ_NSEL; sel++) {
+          const ocg_enc_frag *c = b->itab.cand + ocg_enc_cand_index(&b->itab, SEL_CAND[sel], (int)fragi);
+          if ((c->ref_off0 == r1 && c->ref_off1 == r2) || (r2 != INT32_MIN && c->ref_off0 == r2 && c->ref_off1 == r1)) {
+            const long at = (long)sel * b->geom.nfrags + (long)fragi;
+            if (b->itab.fq_desc[at].off != 0xFFFFFFFFu) {
+              b->fq_cur = at;
+              b->fq_pli = b->st.recs[fragi].pli_qti & 3;
+              b->n_fq_hit++;
+              b->c2_dst = NULL;
+              return; /* the residual's only consumer is fdct8x8 */
+            }
+          }
+        }
+      }
+      b->n_fq_miss++;
+    }
+    b->c2_dst = NULL;
+  }
   oc_enc_frag_sub_c(_diff, _src, _ref, _ystride);
 }
 
 static void ocge_fdct8x8(ogg_int16_t _y[64], const ogg_int16_t _x[64]) {
   ocg_enc_backend *b = enc_live();
+  if (b != NULL && b->fq_cur >= 0) {
+    const ocg_enc_fq_desc *d = b->itab.fq_desc + b->fq_cur;
+    const int n8 = (d->count + 7) & ~7;
+    memcpy(_y, b->itab.fq_pool + (size_t)d->off * 8, (size_t)n8 * sizeof(ogg_int16_t));
+    memset(_y + n8, 0, (size_t)(64 - n8) * sizeof(ogg_int16_t));
+    return;
+  }
   if (b != NULL && b->tables && b->cur_fragi >= 0) {
     memcpy(_y, b->tab.dct + (size_t)b->cur_fragi * 64, 64 * sizeof(ogg_int16_t));
     return;
@@ -559,6 +653,18 @@ static void ocge_fdct8x8(ogg_int16_t _y[64], const ogg_int16_t _x[64]) {
 static int ocge_quantize(ogg_int16_t _qdct[64], const ogg_int16_t _dct[64], const ogg_uint16_t _dequant[64],
                          const void *_enquant) {
   ocg_enc_backend *b = enc_live();
+  if (b != NULL && b->fq_cur >= 0) {
+    const ocg_enc_fq_desc *d = b->itab.fq_desc + b->fq_cur;
+    const int n8 = (d->count + 7) & ~7;
+    int qii;
+    for (qii = 0; qii < b->fq_nq && b->enc->enquant[b->fq_pli][qii][1] != _enquant; qii++) {}
+    if (qii < b->fq_nq) {
+      memcpy(_qdct, b->itab.fq_pool + (size_t)d->off * 8 + (size_t)(1 + qii) * n8, (size_t)n8 * sizeof(ogg_int16_t));
+      memset(_qdct + n8, 0, (size_t)(64 - n8) * sizeof(ogg_int16_t));
+      return d->nz[qii];
+    }
+    /* _dct came from the table, so the C quantiser below is still exact */
+  }
   if (b != NULL && b->tables && b->cur_fragi >= 0) {
     oc_enc_ctx *enc = b->enc;
     int pli = b->st.recs[b->cur_fragi].pli_qti & 3, qii;
@@ -1007,6 +1113,7 @@ void oc_enc_accel_init_ocg(oc_enc_ctx *_enc) {
     _enc->opt_vtable.frag_satd2 = ocge_frag_satd2;
     _enc->opt_vtable.frag_ssd = ocge_frag_ssd;
     _enc->opt_vtable.frag_border_ssd = ocge_frag_border_ssd;
+    _enc->opt_vtable.frag_copy2 = ocge_frag_copy2;
   }
   _enc->opt_vtable.fdct8x8 = ocge_fdct8x8;
   _enc->opt_vtable.quantize = ocge_quantize;

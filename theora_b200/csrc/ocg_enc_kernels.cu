@@ -330,6 +330,74 @@ ocg_enc_cand_kernel(const OcgCandJob J) {
   }
 }
 
+/* ---- speculative frag_sub + fDCT + quantiser for the likeliest predictors ------------------------------
+   oc_enc_block_transform_quantize (analyze.c:667-882) transforms a block against the predictor of the mode
+   the serial decision picked; for the two predictors most macro blocks end up with -- the co-located block
+   of PREV (OC_MODE_INTER_NOMV) and PREV displaced by the refined vector (OC_MODE_INTER_MV, and LAST/LAST2
+   whenever they repeat it) -- the whole chain is computed ahead for every fragment and every quantiser of
+   the frame, and handed over in compact form: only the leading `count` zig-zag coefficients, beyond which
+   every quantiser's output is zero. */
+#define OCG_FQ_NSEL 2
+__constant__ int c_fq_sel[OCG_FQ_NSEL] = {0, 3};
+
+__global__ void __launch_bounds__(256)
+ocg_enc_fq_list_kernel(const ocg_enc_frag *__restrict__ cand, ocg_enc_frag *__restrict__ fq, int nfrags, int nluma, int nqis) {
+  const int f = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (f >= nfrags) return;
+  const int nchroma = nfrags - nluma;
+  const bool luma = f < nluma;
+  /* plane of a chroma fragment: first half Cb, second half Cr (same quantiser class layout [pli]) */
+  const int pli = luma ? 0 : (f - nluma < nchroma / 2 ? 1 : 2);
+  for (int sel = 0; sel < OCG_FQ_NSEL; sel++) {
+    const int k = c_fq_sel[sel];
+    const size_t cat = luma ? (size_t)k * nluma + f : (size_t)OCG_ENC_NCAND * nluma + (size_t)k * nchroma + (f - nluma);
+    ocg_enc_frag e = cand[cat];
+    for (int q = 0; q < nqis; q++) {
+      e.aux = pli | 1 << 2 | q << 3; /* inter tables */
+      const int slot = q * OCG_FQ_NSEL + sel;
+      const size_t at = luma ? (size_t)slot * nluma + f : (size_t)3 * OCG_FQ_NSEL * nluma + (size_t)slot * nchroma + (f - nluma);
+      fq[at] = e;
+    }
+  }
+}
+
+struct ocg_fq_desc_dev { uint32_t off; uint8_t count, nz[3]; };
+
+__global__ void __launch_bounds__(256)
+ocg_enc_fq_compact_kernel(const int16_t *__restrict__ dct, const int16_t *__restrict__ qdct, const int32_t *__restrict__ nonzero,
+                          int nfrags, int nluma, int nqis, ocg_fq_desc_dev *__restrict__ desc, uint4 *__restrict__ pool,
+                          uint32_t pool_units, uint32_t *__restrict__ counter) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= nfrags * OCG_FQ_NSEL) return;
+  const int sel = i / nfrags, f = i - sel * nfrags;
+  const int nchroma = nfrags - nluma;
+  const bool luma = f < nluma;
+  size_t at[3];
+  int nz[3] = {0, 0, 0}, cnt = 0;
+  for (int q = 0; q < nqis; q++) {
+    const int slot = q * OCG_FQ_NSEL + sel;
+    at[q] = luma ? (size_t)slot * nluma + f : (size_t)3 * OCG_FQ_NSEL * nluma + (size_t)slot * nchroma + (f - nluma);
+    nz[q] = nonzero[at[q]];
+    cnt = max(cnt, nz[q] + 1);
+  }
+  cnt = min(cnt, 64);
+  const uint32_t rows = (uint32_t)(cnt + 7) >> 3;          /* 16-byte units per array */
+  const uint32_t need = rows * (uint32_t)(1 + nqis);
+  const uint32_t off = atomicAdd(counter, need);
+  ocg_fq_desc_dev d;
+  d.off = off + need <= pool_units ? off : 0xFFFFFFFFu;     /* pool exhausted: the host computes this one itself */
+  d.count = (uint8_t)cnt;
+  d.nz[0] = (uint8_t)nz[0]; d.nz[1] = (uint8_t)nz[1]; d.nz[2] = (uint8_t)nz[2];
+  desc[i] = d;
+  if (d.off == 0xFFFFFFFFu) return;
+  const uint4 *sd = (const uint4 *)(dct + at[0] * 64);
+  for (uint32_t r = 0; r < rows; r++) pool[off + r] = sd[r];
+  for (int q = 0; q < nqis; q++) {
+    const uint4 *sq = (const uint4 *)(qdct + at[q] * 64);
+    for (uint32_t r = 0; r < rows; r++) pool[off + (uint32_t)(1 + q) * rows + r] = sq[r];
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* oc_mb_activity (analyze.c:1152-1237) per luma block, one lane per block:
    pixel sum and sum of squares -> variance-like activity, and for non-flat
@@ -1507,6 +1575,18 @@ struct ocg_enc_inter {
   uint8_t *d_out = nullptr, *h_out = nullptr;
   size_t off_isatd = 0, off_idc = 0, off_skip = 0, off_border = 0, off_key = 0, off_csatd = 0, off_cdc = 0, out_sz = 0;
   int32_t *h_border_slot = nullptr; /* [nfrags] index into border_ssd or -1 */
+  /* speculative sub + fDCT + quantiser (ocg_enc_fq_*) */
+  ocg_enc_frag *d_fq = nullptr;          /* [3 qii][OCG_FQ_NSEL][nfrags], luma block then chroma block */
+  int16_t *d_fq_dct = nullptr, *d_fq_qdct = nullptr;
+  int32_t *d_fq_nz = nullptr;
+  uint16_t *d_dequant = nullptr;
+  int16_t *d_enquant = nullptr;
+  uint8_t *h_qtab = nullptr;             /* pinned staging of the two quantiser tables */
+  ocg_fq_desc_dev *d_fq_desc = nullptr, *h_fq_desc = nullptr;
+  uint4 *d_fq_pool = nullptr, *h_fq_pool = nullptr;
+  uint32_t *d_fq_counter = nullptr, *h_fq_counter = nullptr;
+  uint32_t fq_pool_units = 0;
+  int fq_nqis = 0;                       /* > 0: the last prepass produced the speculative tables */
 };
 
 OCG_API void ocg_enc_inter_destroy(ocg_enc_inter *ei) {
@@ -1520,6 +1600,12 @@ OCG_API void ocg_enc_inter_destroy(ocg_enc_inter *ei) {
   cudaFree(ei->d_cand);
   cudaFree(ei->d_out);
   if (ei->h_out) cudaFreeHost(ei->h_out);
+  cudaFree(ei->d_fq); cudaFree(ei->d_fq_dct); cudaFree(ei->d_fq_qdct); cudaFree(ei->d_fq_nz);
+  cudaFree(ei->d_dequant); cudaFree(ei->d_enquant); cudaFree(ei->d_fq_desc); cudaFree(ei->d_fq_pool); cudaFree(ei->d_fq_counter);
+  if (ei->h_qtab) cudaFreeHost(ei->h_qtab);
+  if (ei->h_fq_desc) cudaFreeHost(ei->h_fq_desc);
+  if (ei->h_fq_pool) cudaFreeHost(ei->h_fq_pool);
+  if (ei->h_fq_counter) cudaFreeHost(ei->h_fq_counter);
   free(ei->h_border_slot);
   delete ei;
 }
@@ -1584,6 +1670,23 @@ OCG_API int ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, 
   EI_CU(cudaMemcpyAsync(ei->d_all, all.data(), nf * sizeof(ocg_enc_frag), cudaMemcpyHostToDevice, st));
   if (nborder > 0) EI_CU(cudaMemcpyAsync(ei->d_border, border.data(), (size_t)nborder * sizeof(ocg_enc_frag), cudaMemcpyHostToDevice, st));
   EI_CU(cudaMemsetAsync(ei->d_cand, 0, K * nf * sizeof(ocg_enc_frag), st));
+  {
+    const size_t nfq = 3 * OCG_FQ_NSEL * nf;
+    ei->fq_pool_units = (uint32_t)((12u << 20) / 16);
+    EI_CU(cudaMalloc(&ei->d_fq, nfq * sizeof(ocg_enc_frag)));
+    EI_CU(cudaMalloc(&ei->d_fq_dct, nfq * 128));
+    EI_CU(cudaMalloc(&ei->d_fq_qdct, nfq * 128));
+    EI_CU(cudaMalloc(&ei->d_fq_nz, nfq * 4));
+    EI_CU(cudaMalloc(&ei->d_dequant, 3 * 2 * 3 * 64 * 2));
+    EI_CU(cudaMalloc(&ei->d_enquant, 3 * 2 * 3 * 64 * 2 * 2));
+    EI_CU(cudaMalloc(&ei->d_fq_desc, OCG_FQ_NSEL * nf * sizeof(ocg_fq_desc_dev)));
+    EI_CU(cudaMalloc(&ei->d_fq_pool, (size_t)ei->fq_pool_units * 16));
+    EI_CU(cudaMalloc(&ei->d_fq_counter, 4));
+    EI_CU(cudaHostAlloc(&ei->h_qtab, 3 * 2 * 3 * 64 * 2 * 3, cudaHostAllocDefault));
+    EI_CU(cudaHostAlloc(&ei->h_fq_desc, OCG_FQ_NSEL * nf * sizeof(ocg_fq_desc_dev), cudaHostAllocDefault));
+    EI_CU(cudaHostAlloc(&ei->h_fq_pool, (size_t)ei->fq_pool_units * 16, cudaHostAllocDefault));
+    EI_CU(cudaHostAlloc(&ei->h_fq_counter, 64, cudaHostAllocDefault));
+  }
   EI_CU(cudaStreamSynchronize(st));
 #undef EI_CU
   *out = ei;
@@ -1592,6 +1695,23 @@ OCG_API int ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, 
 
 OCG_API int ocg_enc_inter_border_slot(const ocg_enc_inter *ei, int fragi) {
   return ei != nullptr && fragi >= 0 && fragi < ei->nfrags ? ei->h_border_slot[fragi] : -1;
+}
+
+OCG_API int ocg_enc_inter_quant_tables(ocg_enc_inter *ei, const uint16_t *dequant, const int16_t *enquant, int nqis) {
+  if (ei == nullptr) return OCG_EFAULT;
+  ei->fq_nqis = 0;
+  if (dequant == nullptr || enquant == nullptr || nqis <= 0) return OCG_OK; /* no speculative transform this frame */
+  if (nqis > 3) return OCG_EINVAL;
+  if (ocg_set_device(ei->device) != cudaSuccess) return OCG_ECUDA;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(ei->ctx);
+  const size_t nd = 3 * 2 * 3 * 64 * 2, ne = nd * 2;
+  memcpy(ei->h_qtab, dequant, nd);
+  memcpy(ei->h_qtab + nd, enquant, ne);
+  if (cudaMemcpyAsync(ei->d_dequant, ei->h_qtab, nd, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(ei->d_enquant, ei->h_qtab + nd, ne, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return OCG_ECUDA;
+  ei->fq_nqis = nqis;
+  return OCG_OK;
 }
 
 OCG_API int ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, int gold_buf, int with_cands,
@@ -1642,6 +1762,26 @@ OCG_API int ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, i
     if (r == OCG_OK && nc > 0)
       r = ocg_enc_metrics_batch(OCG_MET_SATD, pool, pool, ys[1], ei->d_cand + (size_t)K * nl, K * nc, d_csatd + (size_t)K * nl, d_cdc + (size_t)K * nl, st);
     if (r != OCG_OK) return r;
+    if (ei->fq_nqis > 0) {
+      /* sub + fDCT + quantiser against the predictors of candidates 0 and 3, every quantiser of the frame */
+      const int nq = ei->fq_nqis;
+      ocg_enc_fq_list_kernel<<<(unsigned)((ei->nfrags + 255) / 256), 256, 0, st>>>(ei->d_cand, ei->d_fq, ei->nfrags, nl, nq);
+      ocg_count_launch(1);
+      const size_t cbase = (size_t)3 * OCG_FQ_NSEL * nl;
+      r = ocg_enc_fdct_quant_batch(pool, pool, ys[0], ei->d_fq, nq * OCG_FQ_NSEL * nl, ei->d_dequant, ei->d_enquant, ei->d_fq_dct,
+                                   ei->d_fq_qdct, ei->d_fq_nz, st);
+      if (r == OCG_OK && nc > 0)
+        r = ocg_enc_fdct_quant_batch(pool, pool, ys[1], ei->d_fq + cbase, nq * OCG_FQ_NSEL * nc, ei->d_dequant, ei->d_enquant,
+                                     ei->d_fq_dct + cbase * 64, ei->d_fq_qdct + cbase * 64, ei->d_fq_nz + cbase, st);
+      if (r != OCG_OK) return r;
+      if (cudaMemsetAsync(ei->d_fq_counter, 0, 4, st) != cudaSuccess) return OCG_ECUDA;
+      ocg_enc_fq_compact_kernel<<<(unsigned)((ei->nfrags * OCG_FQ_NSEL + 255) / 256), 256, 0, st>>>(
+          ei->d_fq_dct, ei->d_fq_qdct, ei->d_fq_nz, ei->nfrags, nl, nq, ei->d_fq_desc, ei->d_fq_pool, ei->fq_pool_units, ei->d_fq_counter);
+      ocg_count_launch(1);
+      if (cudaMemcpyAsync(ei->h_fq_counter, ei->d_fq_counter, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(ei->h_fq_desc, ei->d_fq_desc, (size_t)OCG_FQ_NSEL * ei->nfrags * sizeof(ocg_fq_desc_dev), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return OCG_ECUDA;
+    }
   }
   const size_t small = ei->off_border + ((size_t)(ei->nborder_y + ei->nborder_c) + 1) * 4;
   if (cudaMemcpyAsync(ei->h_out, ei->d_out, with_cands ? ei->out_sz : small, cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
@@ -1660,6 +1800,24 @@ OCG_API int ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, i
   out->nluma = nl;
   out->nfrags = ei->nfrags;
   out->d2h_bytes = (long)((with_cands ? ei->out_sz + (size_t)K * ei->nfrags * sizeof(ocg_enc_frag) : small));
+  out->fq_nqis = with_cands ? ei->fq_nqis : 0;
+  out->fq_desc = (const ocg_enc_fq_desc *)ei->h_fq_desc;
+  out->fq_pool = (const int16_t *)ei->h_fq_pool;
+  return OCG_OK;
+}
+
+/* Second half of the pre-pass, after the caller has waited for the first: fetches exactly the part of the
+   coefficient pool that was filled.  Synchronous. */
+OCG_API int ocg_enc_inter_finish(ocg_enc_inter *ei, ocg_enc_inter_tables *out) {
+  if (ei == nullptr || out == nullptr) return OCG_EFAULT;
+  if (out->fq_nqis <= 0) return OCG_OK;
+  if (ocg_set_device(ei->device) != cudaSuccess) return OCG_ECUDA;
+  cudaStream_t st = (cudaStream_t)ocg_ctx_stream(ei->ctx);
+  uint32_t used = *ei->h_fq_counter;
+  if (used > ei->fq_pool_units) used = ei->fq_pool_units;
+  if (used > 0 && cudaMemcpyAsync(ei->h_fq_pool, ei->d_fq_pool, (size_t)used * 16, cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return OCG_ECUDA;
+  out->d2h_bytes += (long)used * 16 + (long)OCG_FQ_NSEL * ei->nfrags * (long)sizeof(ocg_fq_desc_dev);
   return OCG_OK;
 }
 

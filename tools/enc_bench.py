@@ -52,13 +52,17 @@ def main():
     out["d2h_bytes_per_frame"] = int(st.d2h_bytes / max(st.prepass_frames, 1))
     if kf > 1:
         calls = st.satd_lookups + st.satd_host
+        out["prepass_breakdown_ms"] = {"queue": 1e3 * st.me_queue_seconds / max(st.me_frames, 1),
+                                       "wait_for_results": 1e3 * st.me_sync_seconds / max(st.me_frames, 1)}
         out["motion_analysis"] = {"device_passes": int(st.me_frames), "gold_refinements": int(st.me_gold_refines),
                                   "gold_searches_redone": int(st.me_repairs)}
         out["block_metric_calls"] = {"satd_from_device_tables": int(st.satd_lookups), "satd_on_host": int(st.satd_host),
                                      "satd_table_hit_rate": st.satd_lookups / calls if calls else None,
                                      "skip_ssd_from_device_table": int(st.ssd_lookups),
                                      "coded_block_ssd_on_host": int(st.ssd_host),
-                                     "intra_satd_from_device_table": int(st.intra_satd_lookups)}
+                                     "intra_satd_from_device_table": int(st.intra_satd_lookups),
+                                     "sub_fdct_quant_from_device_tables": int(st.fdct_quant_lookups),
+                                     "sub_fdct_quant_on_host": int(st.fdct_quant_host)}
     from theora_b200 import abi
     prep, launch, nfl, bs, nb = C.c_double(), C.c_double(), C.c_long(), C.c_double(), C.c_long()
     abi.lib().ocg_flush_profile(C.byref(prep), C.byref(launch), C.byref(nfl), 0)
