@@ -531,6 +531,8 @@ def main():
     import theora_b200 as T
     from theora_b200 import abi, sharding
     import th_streams as streams
+    if os.environ.get("OCG_LF_VARIANT"):  # A/B of the loop-filter kernels (diagnostic; 0 = default)
+        T.lib().ocg_set_lf_tma(int(os.environ["OCG_LF_VARIANT"]))
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")

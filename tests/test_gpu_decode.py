@@ -78,11 +78,12 @@ def test_each_sparsity_class(cls):
     assert np.array_equal(want, got), first_diff(g, want, got)
 
 
-@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("tma", [0, 1, 2])
 @pytest.mark.parametrize("dims", [(96, 80, 0), (1040, 48, 0), (1024, 32, 2), (560, 64, 3), (80, 96, 3)])
 def test_loop_filter_only_all_limits(tma, dims):
     """Loop filter + borders on random pixels, every coded pattern, many limits,
-    both kernel variants (TMA tiles through shared memory / per-thread accesses)."""
+    every kernel variant (0: strip kernel, the default; 1: TMA tiles through shared memory; 2: one cell per
+    thread)."""
     rng = np.random.default_rng(5)
     g = S.make_geometry(dims[0], dims[1], dims[2], 3)
     T.lib().ocg_set_lf_tma(tma)  # before the contexts are created: they build the tensor maps

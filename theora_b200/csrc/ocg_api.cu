@@ -320,7 +320,8 @@ OCG_API int ocg_device_count(void) {
 
 OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
 
-OCG_API void ocg_set_lf_tma(int on) { g_use_tma.store(on ? 1 : 0); }
+extern int g_ocg_lf_legacy;
+OCG_API void ocg_set_lf_tma(int on) { g_use_tma.store(on == 1 ? 1 : 0); g_ocg_lf_legacy = on == 2; }
 
 OCG_API void ocg_set_blocking_sync(int policy) { g_blocking_sync.store(policy < 0 ? 0 : (policy > 2 ? 2 : policy)); }
 

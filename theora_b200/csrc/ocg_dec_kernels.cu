@@ -292,12 +292,11 @@ __device__ __forceinline__ void xform_group(const OcgGeomDev &g, const OcgJobDev
    loop filter reads. */
 #define OCG_SIMPLE_THREADS 128
 
-#define OCG_A_ROWS 4 /* rows moved per step: 2 steps of 4 keep the kernel at ~32 registers (full occupancy) */
-
-struct RowsN { uint2 r[OCG_A_ROWS]; };
+template <int OCG_A_ROWS> struct RowsN { uint2 r[OCG_A_ROWS]; };
 
 /* rows p, p+ystride, ... : 8 bytes each at an arbitrary byte address */
-__device__ __forceinline__ void load_rows(const uint8_t *p, int ystride, RowsN &o) {
+template <int OCG_A_ROWS>
+__device__ __forceinline__ void load_rows(const uint8_t *p, int ystride, RowsN<OCG_A_ROWS> &o) {
   const uintptr_t a = (uintptr_t)p;
   const unsigned sh = (unsigned)(a & 7);
   const uint8_t *base = (const uint8_t *)(a & ~(uintptr_t)7);
@@ -328,7 +327,9 @@ __device__ __forceinline__ void load_rows(const uint8_t *p, int ystride, RowsN &
   }
 }
 
-__global__ void __launch_bounds__(OCG_SIMPLE_THREADS, 12)
+/* OCG_A_ROWS: rows moved per step (2 steps of 4 keep the kernel at 40 registers) */
+template <int OCG_A_ROWS, int MINB>
+__global__ void __launch_bounds__(OCG_SIMPLE_THREADS, MINB)
 ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const OcgJobDev &job = jobs[blockIdx.y];
   const int lane = (int)threadIdx.x & 31;
@@ -371,14 +372,14 @@ ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) 
   const uint32_t pp = pack16(p, p);
 #pragma unroll 1
   for (int r0 = 0; r0 < 8; r0 += OCG_A_ROWS) {
-    RowsN px;
+    RowsN<OCG_A_ROWS> px;
     if (ref == nullptr) {
 #pragma unroll
       for (int i = 0; i < OCG_A_ROWS; i++) px.r[i] = make_uint2(0x80808080u, 0x80808080u);
     } else {
       load_rows(ref + r0 * ystride, ystride, px);
       if (two) {
-        RowsN t2;
+        RowsN<OCG_A_ROWS> t2;
         load_rows(ref + r0 * ystride + tap2, ystride, t2);
 #pragma unroll
         for (int i = 0; i < OCG_A_ROWS; i++) {
@@ -647,6 +648,204 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   uint8_t *o = job.base[OCG_FRAME_SELF] + P.plane_off + (cy * 8 - 4) * ystride + (cx * 8 - 4);
   if (inl && inr && ind && inu) lf_cell<true>(o, ystride, bv, true, true, true, true, vd, vu, hl, hr, B, Cc, D);
   else lf_cell<false>(o, ystride, bv, inl, inr, ind, inu, vd, vu, hl, hr, B, Cc, D);
+}
+
+/* ---- loop filter, strip form (the default) ---------------------------------------------------------
+   The one-cell-per-thread kernel above is bound by the ALU pipe (ncu: 67 % busy at 45 % of the DRAM rate).
+   This form first trims instructions:
+   * lines ACROSS a vertical edge (loop_filter_h, state.c:1002) have their four samples in four adjacent
+     bytes of one pixel row: one PRMT funnels them into a word and one IDP.4A (dp4a, weights 4,-12,12,-4,
+     bias 4*1020) yields 4*(a-d+3(c-b)+1020) -- directly the byte offset into a 2048-entry table in shared
+     memory whose 32-bit entries hold the bounded correction as a halfword pair (+f for b, -f for c), so the
+     whole update is PRMT, VIADDMNMX.S16x2.RELU and two PRMT inserts;
+   * lines ALONG columns (loop_filter_v, state.c:1018) stay two-per-operation on halfword pairs, but index
+     the same table (two LDS, two PRMT give the +f and -f pairs);
+   * a thread walks R vertically adjacent cells, so the plane look-up and the address set-up are paid once
+     per strip, and the coded flags of all R+1 fragment rows are requested up front (no flag -> row
+     dependency per cell);
+   * the eight lines through the central 4x4 patch are issued as six blocks instead of eight: only the
+     relative order of a vertical and a horizontal group matters, and of those only two pairs are not fixed
+     (left edge before the lower edge iff B and not C; right edge before the upper edge iff not D);
+   * every active cell moves whole rows (the cells of the plane's rim reach into the apron, which is
+     allocated, read and written back unchanged), so there is no second code path for the rim;
+   * row addresses are one IMAD.WIDE each (FMA pipe) instead of eight hoisted 64-bit offsets: 40 registers.
+   ALU pipe 67 % -> 37 %; 94 -> 78 us per 64-stream launch.  What bounds it now is the movement itself: a
+   probe that only loads and stores the cells takes 86 us with these 32-bit accesses (70 us with 64-bit ones,
+   which a cell -- 4 bytes off the 8-byte grid -- cannot use directly).  Tried and measured slower: exchanging
+   halves between lanes by shuffle to move aligned 64-bit words (97-108 us), one cell of prefetch (85 us at
+   62 registers), fetching each cell row's 8 pixel rows as one linear cp.async.bulk block into a double-
+   buffered shared-memory tile (88 us); CTA shapes from 32x4 to 256x1 cells and R = 1..8 all land within
+   78-87 us. */
+#define OCG_LF2_TAB 2048
+
+/* g_lf_tab2[lim][i], i = a-d+3(c-b)+1020 in 0..2040: f = lflim((i-1016)>>3, lim) as (f & 0xFFFF) | (-f << 16) */
+__device__ uint32_t g_lf_tab2[128][OCG_LF2_TAB];
+
+__global__ void ocg_lf_tab2_kernel() {
+  const int lim = (int)blockIdx.x;
+  for (int i = (int)threadIdx.x; i < OCG_LF2_TAB; i += (int)blockDim.x) {
+    const int f = lflim((i - 1016) >> 3, lim);
+    g_lf_tab2[lim][i] = ((uint32_t)f & 0xFFFFu) | ((uint32_t)(-f) << 16);
+  }
+}
+
+__device__ __forceinline__ uint32_t lf2_entry(const uint32_t *tab, uint32_t byte_off) {
+  return *(const uint32_t *)((const unsigned char *)tab + byte_off);
+}
+
+/* one line across the vertical edge in the middle of a cell row: w0 = cell columns 0..3, w1 = 4..7 */
+__device__ __forceinline__ void lf2_vline(uint32_t &w0, uint32_t &w1, const uint32_t *tab) {
+  const uint32_t s = __byte_perm(w0, w1, 0x5432); /* columns 2,3,4,5 = a,b,c,d */
+  int off;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(off) : "r"(s), "r"(0xFC0CF404u), "r"(4 * 1020));
+  const uint32_t e = lf2_entry(tab, (uint32_t)off);
+  const uint32_t bc = __byte_perm(s, 0, 0x4241); /* (b, c) as halfwords */
+  const uint32_t r = __viaddmin_s16x2_relu(bc, e, 0x00FF00FFu);
+  w0 = __byte_perm(w0, r, 0x4210);
+  w1 = __byte_perm(w1, r, 0x3216);
+}
+
+/* two lines along cell columns COL, COL+1 across the horizontal edge in the middle of the cell (rows 2..5) */
+template <int COL>
+__device__ __forceinline__ void lf2_hpair(uint32_t (&w)[8][2], const uint32_t *tab) {
+  constexpr int h = COL >> 2, i = COL & 3; /* i is 0 or 2 */
+  constexpr unsigned ext = i == 0 ? 0x4140u : 0x4342u;
+  const uint32_t a = __byte_perm(w[2][h], 0, ext);
+  const uint32_t b = __byte_perm(w[3][h], 0, ext);
+  const uint32_t c = __byte_perm(w[4][h], 0, ext);
+  const uint32_t d = __byte_perm(w[5][h], 0, ext);
+  /* per halfword 4*(a-d+3(c-b)+1020) in 0..8160: no borrow between the halves of the final value */
+  const uint32_t v = (c * 12u + a * 4u + 0x0FF00FF0u) - (b * 12u + d * 4u);
+  const uint32_t e0 = lf2_entry(tab, v & 0xFFFFu), e1 = lf2_entry(tab, v >> 16);
+  const uint32_t pf = __byte_perm(e0, e1, 0x5410), nf = __byte_perm(e0, e1, 0x7632);
+  const uint32_t b2 = __viaddmin_s16x2_relu(b, pf, 0x00FF00FFu);
+  const uint32_t c2 = __viaddmin_s16x2_relu(c, nf, 0x00FF00FFu);
+  constexpr unsigned ins = i == 0 ? 0x3264u : 0x6410u;
+  w[3][h] = __byte_perm(w[3][h], b2, ins);
+  w[4][h] = __byte_perm(w[4][h], c2, ins);
+}
+
+/* o + r*ystride as one IMAD.WIDE (FMA pipe) instead of a hoisted 64-bit offset per row (16 registers) */
+__device__ __forceinline__ uint32_t *lf2_row(uint8_t *o, int ystride, int r) {
+  unsigned long long a;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(a) : "r"(ystride), "r"(r), "l"((unsigned long long)o));
+  return (uint32_t *)a;
+}
+
+/* which lines of a cell run, from the coded flags of the fragment rows below (AB) and above (CD) the corner:
+   bit 0 vd, 1 vu, 2 hl, 3 hr (vertical edge below/above the corner, horizontal edge left/right of it) */
+__device__ __forceinline__ unsigned lf2_lines(unsigned AB, unsigned CD, bool both, bool mid) {
+  unsigned m = 0;
+  if (both && AB != 0) m |= 1u;
+  if (both && CD != 0) m |= 2u;
+  if (mid && ((AB | CD) & 1u)) m |= 4u;
+  if (mid && ((AB | CD) & 2u)) m |= 8u;
+  return m;
+}
+
+__device__ __forceinline__ void lf2_load(uint32_t (&w)[8][2], uint8_t *o, int ystride, unsigned lines) {
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const bool need = lines != 0 && (r < 2 ? (lines & 1u) != 0 : (r >= 6 ? (lines & 2u) != 0 : true));
+    w[r][0] = w[r][1] = 0;
+    if (need) {
+      const uint32_t *rw = lf2_row(o, ystride, r);
+      w[r][0] = rw[0];
+      w[r][1] = rw[1];
+    }
+  }
+}
+
+__device__ __forceinline__ void lf2_filter(uint32_t (&w)[8][2], unsigned lines, unsigned AB, unsigned CD, const uint32_t *tab) {
+  const bool vd = lines & 1u, vu = lines & 2u, hl = lines & 4u, hr = lines & 8u;
+  const bool B = (AB & 2u) != 0, Cc = (CD & 1u) != 0, D = (CD & 2u) != 0;
+  /* lines that touch nothing another line touches */
+  if (vd) { lf2_vline(w[0][0], w[0][1], tab); lf2_vline(w[1][0], w[1][1], tab); }
+  if (vu) { lf2_vline(w[6][0], w[6][1], tab); lf2_vline(w[7][0], w[7][1], tab); }
+  if (hl) lf2_hpair<0>(w, tab);
+  if (hr) lf2_hpair<6>(w, tab);
+  /* the central patch, in an order equivalent to the raster scan's (state.c:1083-1104) */
+  const bool hl_first = B && !Cc;
+  if (hl && hl_first) lf2_hpair<2>(w, tab);
+  if (vd) { lf2_vline(w[2][0], w[2][1], tab); lf2_vline(w[3][0], w[3][1], tab); }
+  if (hl && !hl_first) lf2_hpair<2>(w, tab);
+  if (hr && !D) lf2_hpair<4>(w, tab);
+  if (vu) { lf2_vline(w[4][0], w[4][1], tab); lf2_vline(w[5][0], w[5][1], tab); }
+  if (hr && D) lf2_hpair<4>(w, tab);
+}
+
+__device__ __forceinline__ void lf2_filter_store(uint32_t (&w)[8][2], uint8_t *o, int ystride, unsigned lines, unsigned AB,
+                                                 unsigned CD, const uint32_t *tab) {
+  lf2_filter(w, lines, AB, CD, tab);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const bool need = r < 2 ? (lines & 1u) != 0 : (r >= 6 ? (lines & 2u) != 0 : true);
+    if (need) {
+      uint32_t *rw = lf2_row(o, ystride, r);
+      rw[0] = w[r][0];
+      rw[1] = w[r][1];
+    }
+  }
+}
+
+template <int TX, int TY, int R, int MINB>
+__global__ void __launch_bounds__(TX * TY, MINB)
+ocg_lf2_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  __shared__ __align__(16) uint32_t tab[OCG_LF2_TAB];
+  const OcgJobDev &job = jobs[blockIdx.z];
+  const int lim = job.lf_limit;
+  if (lim == 0) return;
+  /* strip group -> plane: groups of TY*R cell rows, aligned per plane */
+  constexpr int GR = TY * R;
+  int grp = (int)blockIdx.y, pli = 0;
+  {
+    const int n0 = (g.p[0].nvfrags + GR) / GR, n1 = (g.p[1].nvfrags + GR) / GR;
+    if (grp >= n0) { grp -= n0; pli = 1; if (grp >= n1) { grp -= n1; pli = 2; } }
+  }
+  const OcgPlaneDev &P = g.p[pli];
+  const int nh = P.nhfrags, nv = P.nvfrags;
+  const int cx = (int)(blockIdx.x * TX + threadIdx.x);
+  const int cy0 = grp * GR + (int)threadIdx.y * R;
+  const bool live = cx <= nh && cy0 <= nv;
+  const bool inl = cx > 0, inr = cx < nh;
+  /* coded flags of the R+1 fragment rows around the strip's corners, all requested before the table is
+     staged: 2 bits per row (bit 0 left of the corner, bit 1 right of it) */
+  unsigned coded = 0;
+  if (live) {
+    const uint8_t *cm = job.coded + P.froffset + cx;
+    unsigned char fl[R + 1][2];
+#pragma unroll
+    for (int k = 0; k <= R; k++) {
+      const int fy = cy0 - 1 + k;
+      const bool in = fy >= 0 && fy < nv;
+      fl[k][0] = in && inl ? cm[fy * nh - 1] : (unsigned char)0;
+      fl[k][1] = in && inr ? cm[fy * nh] : (unsigned char)0;
+    }
+#pragma unroll
+    for (int k = 0; k <= R; k++) coded |= ((fl[k][0] ? 1u : 0u) | (fl[k][1] ? 2u : 0u)) << (2 * k);
+  }
+  {
+    const int tid = (int)(threadIdx.y * TX + threadIdx.x);
+    const uint4 *src = (const uint4 *)g_lf_tab2[lim];
+#pragma unroll
+    for (int k = 0; k < OCG_LF2_TAB / 4 / (TX * TY); k++) ((uint4 *)tab)[tid + k * TX * TY] = src[tid + k * TX * TY];
+  }
+  __syncthreads();
+  if (!live) return;
+  const int ystride = P.ystride;
+  const bool both = inl && inr;
+  uint8_t *o = job.base[OCG_FRAME_SELF] + P.plane_off + (ptrdiff_t)(cy0 * 8 - 4) * ystride + (cx * 8 - 4);
+  const int n = min(R, nv + 1 - cy0);
+#pragma unroll 1
+  for (int i = 0; i < n; i++, o += 8 * (ptrdiff_t)ystride) {
+    const int cy = cy0 + i;
+    const unsigned AB = (coded >> (2 * i)) & 3u, CD = (coded >> (2 * i + 2)) & 3u;
+    const unsigned lines = lf2_lines(AB, CD, both, cy > 0 && cy < nv);
+    if (lines == 0) continue;
+    uint32_t w[8][2];
+    lf2_load(w, o, ystride, lines);
+    lf2_filter_store(w, o, ystride, lines, AB, CD, tab);
+  }
 }
 
 /* ---- TMA variant ----------------------------------------------------------
@@ -989,7 +1188,9 @@ ocg_dc_patch_kernel(ocg_frag_rec *__restrict__ recs, const int16_t *__restrict__
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return;
   dim3 ga((unsigned)((g.nfrags + OCG_SIMPLE_THREADS - 1) / OCG_SIMPLE_THREADS), (unsigned)njobs);
-  ocg_recon_simple_kernel<<<ga, OCG_SIMPLE_THREADS, 0, st>>>(g, jobs);
+  /* 4 rows per step at 12 CTAs per SM: 8 rows per step (64 registers, or 40-48 with spills) and 2 rows per step
+     were measured 1-20 % slower */
+  ocg_recon_simple_kernel<4, 12><<<ga, OCG_SIMPLE_THREADS, 0, st>>>(g, jobs);
   /* pass B: about six CTAs per SM in total, each striding over its job's list */
   int per_job = (148 * 6 + njobs - 1) / njobs;
   const int tiles = (g.nfrags + OCG_FRAGS_PER_BLOCK - 1) / OCG_FRAGS_PER_BLOCK;
@@ -1191,11 +1392,24 @@ void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const OcgJobDev *j
 
 void ocg_init_device_tables(cudaStream_t st) {
   ocg_lf_table_kernel<<<128, 128, 0, st>>>();
+  ocg_lf_tab2_kernel<<<128, 256, 0, st>>>();
 }
+
+int g_ocg_lf_legacy = 0; /* A/B switch (ocg_set_lf_tma(2)): the one-cell-per-thread kernel */
 
 void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, bool use_tma, cudaStream_t st) {
   if (njobs <= 0) return;
-  if (use_tma) {
+  const int variant = use_tma ? 1 : (g_ocg_lf_legacy ? 2 : 0);
+  if (variant == 0) {
+    constexpr int TX = 128, R = 4; /* 128 cells x 4 cell rows per CTA: the best of the shapes tried */
+    int groups = 0;
+    for (int pli = 0; pli < 3; pli++) groups += (g.p[pli].nvfrags + R) / R;
+    dim3 grid((unsigned)((g.max_cells_x + TX - 1) / TX), (unsigned)groups, (unsigned)njobs);
+    ocg_lf2_kernel<TX, 1, R, 12><<<grid, dim3(TX, 1), 0, st>>>(g, jobs);
+    ocg_count_launch(1);
+    return;
+  }
+  if (variant == 1) {
     dim3 grid((unsigned)((g.max_cells_x + 63) / 64), (unsigned)g.cell_rows, (unsigned)njobs);
     ocg_lf_tma_kernel<<<grid, 64, 0, st>>>(g, jobs);
     ocg_count_launch(1);
