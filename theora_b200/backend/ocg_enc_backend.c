@@ -231,19 +231,20 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   b->me_frame_num = st->curframe_num;
   b->me_valid = 0;
   b->itab_valid = 0;
-  /* the input frame joins the device's frame pool (an intra frame's pre-pass uploads it itself) */
-  if (b->inter_frame &&
-      ocg_ctx_upload_frame(b->ctx, st->ref_frame_idx[OC_FRAME_IO],
-                           st->ref_frame_handle + (size_t)st->ref_frame_idx[OC_FRAME_IO] * (size_t)b->geom.ref_frame_sz) < 0) {
-    enc_fail(b, "input frame upload failed");
-    return -1;
-  }
   /* who will call oc_mcenc_search in this pass: analyze.c:1723-1726 (key frames), 2402 (inter frames) */
   wanted = enc->sp_level < OC_SP_LEVEL_NOSATD &&
            (b->inter_frame ? 1 : st->curframe_num > 0 && enc->keyframe_frequency_force > 1);
   for (i = 0; i < 5; i++) {
     bufs[i] = st->ref_frame_idx[ROLE[i]];
     if (bufs[i] < 0) wanted = 0;
+  }
+  /* the input frame joins the device's frame pool.  A key frame's own pre-pass uploads it too, but only
+     after this hook: a key frame that is searched (every key frame but the first) needs it here already */
+  if ((b->inter_frame || wanted) &&
+      ocg_ctx_upload_frame(b->ctx, st->ref_frame_idx[OC_FRAME_IO],
+                           st->ref_frame_handle + (size_t)st->ref_frame_idx[OC_FRAME_IO] * (size_t)b->geom.ref_frame_sz) < 0) {
+    enc_fail(b, "input frame upload failed");
+    return -1;
   }
   /* device objects are made on the encoder's first pass (frame 0), whoever wants them first */
   if (b->me == NULL) {
@@ -366,7 +367,7 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
      the C kernels */
   b->fq_cur = -1;
   b->c2_dst = NULL;
-  b->fq_ok = b->inter_frame && b->itab_valid && b->itab.fq_nqis > 0 && b->fq_nq == nqis;
+  b->fq_ok = b->inter_frame && b->itab_valid && b->itab.fq_nqis > 0 && b->fq_nq == nqis && getenv("OCG_ENC_NO_FQ") == NULL;
   if (b->fq_ok) {
     int qii;
     for (qii = 0; qii < nqis; qii++) if (b->fq_qis[qii] != st->qis[qii]) b->fq_ok = 0;
