@@ -548,6 +548,25 @@ OCG_API int ocg_enc_intra_prepass(ocg_ctx *ctx, int io_buf, const uint8_t *host_
                                   const uint16_t *dequant, const int16_t *enquant, int nqis,
                                   ocg_enc_intra_tables *out);
 
+/* ---- decoder post-processing --------------------------------------------------------------
+   The reference's out-of-loop filters, lib/decode.c:1609-1957 -- oc_filter_hedge / oc_filter_vedge under
+   oc_dec_deblock_frag_rows (:1700) and oc_dering_block under oc_dec_dering_frag_rows (:1892) -- applied on
+   the device to the frame a flush left in buffer `self_buf`, into a frame of the layout of the reference's
+   pp_frame_data (planes back to back, W x H each, top row first; decode.c:1283-1315).
+   level is the reference's pp_level (decint.h: 2 de-block luma, 3 + de-ring luma, 4 strong de-ringing, 5..7
+   the same for chroma on top); dc_scale / sharp_mod are its pp_dc_scale[64] / pp_sharp_mod[64]; dc_qis[nfrags]
+   is the per-fragment DC quantiser index it tracks (decode.c:1204-1243) and qis[nfrags] state.qis[frag.qii].
+   ocg_pp_run queues the kernels on the context's stream; ocg_pp_download waits and copies the planes the level
+   processed (luma; chroma from level 5) to host_dst. */
+typedef struct ocg_pp ocg_pp;
+OCG_API int  ocg_pp_create(ocg_pp **out, ocg_ctx *ctx);
+OCG_API void ocg_pp_destroy(ocg_pp *pp);
+OCG_API int  ocg_pp_run(ocg_pp *pp, int self_buf, int level, const int32_t *dc_scale, const int32_t *sharp_mod,
+                        const uint8_t *dc_qis, const uint8_t *qis);
+OCG_API int  ocg_pp_download(ocg_pp *pp, uint8_t *host_dst);
+/* test hook: the per-fragment variances of the last run (the reference's dec->variances) */
+OCG_API int  ocg_pp_download_variances(ocg_pp *pp, int32_t *host_dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,6 +196,11 @@ _PROTOS = {
     "ocg_enc_inter_quant_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "ocg_enc_inter_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ocg_enc_inter_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ocg_pp_create": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocg_pp_destroy": (None, [C.c_void_p]),
+    "ocg_pp_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocg_pp_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocg_pp_download_variances": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ocg_enc_intra_reserve": (C.c_int, [C.c_void_p]),
     "ocg_enc_intra_prepass": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p]),

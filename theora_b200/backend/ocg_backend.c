@@ -38,7 +38,6 @@ void oc_refimpl_decode_free(th_dec_ctx *_dec);
 int oc_refimpl_decode_ctl(th_dec_ctx *_dec, int _req, void *_buf, size_t _buf_sz);
 int oc_refimpl_decode_packetin(th_dec_ctx *_dec, const ogg_packet *_op, ogg_int64_t *_granpos);
 int oc_refimpl_decode_ycbcr_out(th_dec_ctx *_dec, th_ycbcr_buffer _ycbcr);
-void ocg_pp_host_whole_frame(oc_dec_ctx *_dec, int _refi); /* ocg_dec_host.c */
 void oc_state_accel_init_ocg(oc_theora_state *_state);
 void ocg_host_dc_unpredict_mcu_plane(oc_dec_ctx *_dec, oc_dec_pipeline_state *_pipe, int _pli); /* ocg_dec_host.c */
 
@@ -65,6 +64,10 @@ typedef struct ocg_backend {
   int                pending;     /* a flushed frame's kernels / copy-back may still be running */
   int                failed;      /* a device call failed: the decoder is unusable, the API returns TH_EFAULT */
   int                out_mode;
+  ocg_pp            *pp;          /* post-processing on the device (made when a frame first asks for it) */
+  int                pp_pending;  /* the last flushed frame's post-processed planes are still on the device */
+  int                pp_level;    /* the frame's post-processing level (taken from the pipeline at the first hook) */
+  unsigned char     *pp_qis;      /* [nfrags] state.qis[frag.qii] of the frame being flushed */
   th_stripe_callback user_cb;
   ocg_backend_stats  stats;       /* this decoder's share; summed by ocg_backend_get_stats (no shared lock per frame) */
   struct ocg_backend *next;
@@ -154,6 +157,15 @@ static void backend_wait(ocg_backend *b) {
     double t0 = now_s();
     b->pending = 0;
     if ((b->dc_ahead_used ? ocg_ctx_sync(b->ctx) : ocg_dec_wait(b->ctx)) < 0) { backend_fail(b, "waiting for the frame failed"); return; }
+    if (b->pp_pending) {
+      /* the planes the filters produced go where the reference's own filters would have left them
+         (pp_frame_data: luma first, the chroma planes behind it; decode.c:1283-1315) */
+      b->pp_pending = 0;
+      if (b->dec->pp_frame_data == NULL || ocg_pp_download(b->pp, b->dec->pp_frame_data) < 0) {
+        backend_fail(b, "fetching the post-processed frame failed");
+        return;
+      }
+    }
     b->stats.wait_seconds += now_s() - t0;
   }
 }
@@ -183,6 +195,15 @@ static void backend_begin_frame(ocg_backend *b) {
   memset(b->dcq, 0, sizeof(b->dcq));
   b->frame_open = 1;
   b->dc_ahead = 0;
+  /* The reference would run its de-blocking / de-ringing filters inside the MCU loop (decode.c:2899-2914) on
+     host pixels that are not there: the level is taken over here -- this is the frame's first hook, ahead of
+     the loop's first look at it -- and the filters run on the device at the flush instead.  pp_frame_buf
+     (decode.c:1283-1322) already points where th_decode_ycbcr_out will look. */
+  b->pp_level = 0;
+  if (b->ctx != NULL) {
+    b->pp_level = b->dec->pipe.pp_level;
+    b->dec->pipe.pp_level = 0; /* OC_PP_LEVEL_DISABLED */
+  }
   if (b->dc_device == 2 && b->ctx != NULL) {
     /* Every input of the DC recurrence (coded flags, reference types, residuals) is in frags[] once the
        tokens are unpacked (decode.c:2822), i.e. now: the device starts on it while the host expands
@@ -271,10 +292,24 @@ static void backend_flush(ocg_backend *b) {
   }
   /* Out-of-loop post-processing (non-normative, decode.c:2899-2914) ran inside the MCU loop on a host
      frame that was not there yet; now that it is, run it again over the whole frame. */
-  if (b->ctx != NULL && b->dec->pipe.pp_level > 0 /* OC_PP_LEVEL_DISABLED */) {
-    backend_wait(b);
-    if (b->failed) return;
-    ocg_pp_host_whole_frame(b->dec, f.ref_idx[OCG_FRAME_SELF]);
+  if (b->ctx != NULL && b->pp_level >= 2 /* OC_PP_LEVEL_DEBLOCKY */) {
+    /* on the device, behind the frame's reconstruction on the same stream (ocg_dec_postproc.cu); fetched
+       with the frame in backend_wait */
+    const oc_fragment *frags = st->frags;
+    const ptrdiff_t nfrags = st->nfrags;
+    ptrdiff_t fragi;
+    ogg_int32_t dc_scale[64], sharp_mod[64];
+    if (b->pp == NULL) {
+      b->pp_qis = (unsigned char *)malloc((size_t)nfrags);
+      if (b->pp_qis == NULL || ocg_pp_create(&b->pp, b->ctx) < 0) { backend_fail(b, "post-processing set-up failed"); return; }
+    }
+    for (fragi = 0; fragi < nfrags; fragi++) b->pp_qis[fragi] = (unsigned char)st->qis[frags[fragi].qii]; /* decode.c:1926 */
+    for (i = 0; i < 64; i++) { dc_scale[i] = b->dec->pp_dc_scale[i]; sharp_mod[i] = b->dec->pp_sharp_mod[i]; }
+    if (ocg_pp_run(b->pp, f.ref_idx[OCG_FRAME_SELF], b->pp_level, dc_scale, sharp_mod, b->dec->dc_qis, b->pp_qis) < 0) {
+      backend_fail(b, "post-processing on the device failed");
+      return;
+    }
+    b->pp_pending = 1;
   }
   /* the stripe callback, once, with the whole (now final) frame:
      decode.c:2936-2940 flips the row range, the telemetry path at 2975 already
@@ -427,11 +462,13 @@ static void backend_destroy(ocg_backend *b) {
   if (t_cur == b) t_cur = NULL;
   if (b->ctx != NULL) {
     ocg_ctx_sync(b->ctx);
+    if (b->pp != NULL) ocg_pp_destroy(b->pp);
     backend_unregister(b);
     if (b->pinned) ocg_host_unregister(b->dec->state.ref_frame_handle);
     ocg_ctx_destroy(b->ctx);
   }
   free(b->heap_staging);
+  free(b->pp_qis);
   free(b);
 }
 
