@@ -398,10 +398,10 @@ ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) 
 }
 
 /* ---- recon pass B: fragments with an 8x8 iDCT ------------------------------
-   A CTA takes 64 entries of the compact list pass A produced, turns their
+   A warp takes 32 entries of the compact list pass A produced, turns their
    records into work items (MV -> tap offsets, state.c:846-957; DC dequant,
-   state.c:978), partitions them by footprint class in shared memory (stable,
-   so neighbours stay neighbours) and runs 4 lanes per fragment.
+   state.c:978), partitions them by footprint class (stable, so neighbours
+   stay neighbours) and runs 4 lanes per fragment.
      item.x  buf_off                 item.y  buf_off + first-tap offset
      item.z  coeff_row
      item.w  [15:0] dequantised DC  [23:16] rowmask  [26:24] class
@@ -410,61 +410,64 @@ ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) 
    The list counter is cleared by the border kernel (or ocg_xlist_reset_kernel),
    which always follows in stream order. */
 __global__ void __launch_bounds__(OCG_RECON_THREADS, 6)
-ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
-  __shared__ int4 sitem[OCG_FRAGS_PER_BLOCK];
-  __shared__ unsigned char stap[OCG_FRAGS_PER_BLOCK];
-  __shared__ unsigned char sorder[OCG_FRAGS_PER_BLOCK];
-  __shared__ int scnt[2][WC_COUNT];
-  const OcgJobDev &job = jobs[blockIdx.y];
-  const int t = (int)threadIdx.x;
-  const int lane = t & 31;
+ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs, int njobs) {
+  /* Every warp works on its own: 32 list entries per round, partitioned by footprint class inside the
+     warp (ballots, stable), then four sub-rounds of 8 fragments x 4 lanes.  No CTA-wide barrier (the
+     CTA-wide 64-entry partition this replaces spent most of its stall cycles in __syncthreads on
+     dense-coefficient frames). */
+  __shared__ int4 sitem[OCG_RECON_THREADS / 32][32];
+  __shared__ unsigned char stap[OCG_RECON_THREADS / 32][32];
+  const int t = (int)threadIdx.x, lane = t & 31, w = t >> 5;
+  /* the grid is one resident wave; CTA b serves job b % njobs as that job's rank b / njobs */
+  const int jobi = (int)blockIdx.x % njobs, rank = (int)blockIdx.x / njobs;
+  const int nranks = ((int)gridDim.x - 1 - jobi) / njobs + 1;
+  const OcgJobDev &job = jobs[jobi];
   const int nx = *(volatile const int *)job.xcount;
-  /* the list length is only known on the device: a fixed, small grid strides over it */
-  for (int e0 = (int)blockIdx.x * OCG_FRAGS_PER_BLOCK; e0 < nx; e0 += (int)gridDim.x * OCG_FRAGS_PER_BLOCK) {
-    const int nvalid = min(OCG_FRAGS_PER_BLOCK, nx - e0);
+  constexpr int NW = OCG_RECON_THREADS / 32;
+  for (int e0 = (rank * NW + w) * 32; e0 < nx; e0 += nranks * NW * 32) {
+    const int nvalid = min(32, nx - e0);
     int cls = WC_NONE;
-    unsigned mine = 0;
-    if (t < OCG_FRAGS_PER_BLOCK) {
-      if (t < nvalid) {
-        const int fragi = job.xlist[e0 + t];
-        const int4 rw = __ldg((const int4 *)(job.recs + fragi));
-        cls = work_class(rw);
-        const int refi = (rw.w >> 16) & 3, pli = (rw.w >> 24) & 3, qti = (rw.w >> 26) & 1;
-        const int dcv = (rw.y >> 16) * (int)job.dcq[pli][qti];
-        int off0 = 0, fx = 0, fy = 0;
-        if (refi != OCG_FRAME_SELF) mv_taps(rw.y << 16 >> 16, pli ? g.qx : 0, pli ? g.qy : 0, g.p[pli].ystride, off0, fx, fy);
-        int4 it;
-        it.x = rw.x;
-        it.y = rw.x + off0;
-        it.z = rw.z;
-        it.w = (dcv & 0xFFFF) | ((rw.w & 0xFF) << 16) | (cls << 24) | (refi << 27) | (pli << 29);
-        sitem[t] = it;
-        stap[t] = (unsigned char)((unsigned)(fx & 3) | ((unsigned)(fy & 3) << 2));
-      }
-#pragma unroll
-      for (int c = WC_3; c < WC_COUNT; c++) {
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
-        if (cls == c) mine = m;
-        if (lane == 0) scnt[t >> 5][c] = __popc(m);
-      }
-    }
-    __syncthreads();
-    if (cls != WC_NONE) {
-      int pos = __popc(mine & ((1u << lane) - 1u)) + ((t >> 5) ? scnt[0][cls] : 0);
-      for (int c = WC_3; c < cls; c++) pos += scnt[0][c] + scnt[1][c];
-      sorder[pos] = (unsigned char)t;
-    }
-    __syncthreads();
-    const int gi = t >> 2;
     int4 it = make_int4(0, 0, 0, 0);
     unsigned tap = 0;
-    if (gi < nvalid) {
-      const int slot = (int)sorder[gi];
-      it = sitem[slot];
-      tap = stap[slot];
+    if (lane < nvalid) {
+      const int fragi = job.xlist[e0 + lane];
+      const int4 rw = __ldg((const int4 *)(job.recs + fragi));
+      cls = work_class(rw);
+      const int refi = (rw.w >> 16) & 3, pli = (rw.w >> 24) & 3, qti = (rw.w >> 26) & 1;
+      const int dcv = (rw.y >> 16) * (int)job.dcq[pli][qti];
+      int off0 = 0, fx = 0, fy = 0;
+      if (refi != OCG_FRAME_SELF) mv_taps(rw.y << 16 >> 16, pli ? g.qx : 0, pli ? g.qy : 0, g.p[pli].ystride, off0, fx, fy);
+      it.x = rw.x;
+      it.y = rw.x + off0;
+      it.z = rw.z;
+      it.w = (dcv & 0xFFFF) | ((rw.w & 0xFF) << 16) | (cls << 24) | (refi << 27) | (pli << 29);
+      tap = (unsigned)(fx & 3) | ((unsigned)(fy & 3) << 2);
     }
-    xform_group(g, job, it, tap, lane & 3);
-    __syncthreads(); /* shared arrays are rewritten by the next chunk */
+    int base = 0, pos = 0;
+#pragma unroll
+    for (int c = WC_3; c < WC_COUNT; c++) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+      if (cls == c) pos = base + __popc(m & ((1u << lane) - 1u));
+      base += __popc(m);
+    }
+    if (cls != WC_NONE) {
+      sitem[w][pos] = it;
+      stap[w][pos] = (unsigned char)tap;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < 32; r += 8) {
+      if (r >= nvalid) break; /* warp-uniform */
+      const int gi = r + (lane >> 2);
+      int4 gt = make_int4(0, 0, 0, 0);
+      unsigned gtap = 0;
+      if (gi < nvalid) {
+        gt = sitem[w][gi];
+        gtap = stap[w][gi];
+      }
+      xform_group(g, job, gt, gtap, lane & 3);
+    }
+    __syncwarp(); /* the staging rows are rewritten by the next round */
   }
 }
 
@@ -1191,13 +1194,19 @@ void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cud
   /* 4 rows per step at 12 CTAs per SM: 8 rows per step (64 registers, or 40-48 with spills) and 2 rows per step
      were measured 1-20 % slower */
   ocg_recon_simple_kernel<4, 12><<<ga, OCG_SIMPLE_THREADS, 0, st>>>(g, jobs);
-  /* pass B: about six CTAs per SM in total, each striding over its job's list */
-  int per_job = (148 * 6 + njobs - 1) / njobs;
-  const int tiles = (g.nfrags + OCG_FRAGS_PER_BLOCK - 1) / OCG_FRAGS_PER_BLOCK;
-  if (per_job < 8) per_job = 8;
-  if (per_job > tiles) per_job = tiles;
-  dim3 gb((unsigned)per_job, (unsigned)njobs);
-  ocg_recon_xform_kernel<<<gb, OCG_RECON_THREADS, 0, st>>>(g, jobs);
+  /* pass B: one resident wave (6 CTAs of 256 threads per SM), CTA b striding over the list of job b % njobs;
+     never more CTAs than there can be work for */
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int tiles = (g.nfrags + OCG_RECON_THREADS - 1) / OCG_RECON_THREADS; /* a CTA takes 256 entries per round */
+  long nb = (long)sms * 6;
+  if (nb < njobs) nb = njobs;
+  if (nb > (long)tiles * njobs) nb = (long)tiles * njobs;
+  ocg_recon_xform_kernel<<<(unsigned)nb, OCG_RECON_THREADS, 0, st>>>(g, jobs, njobs);
   ocg_count_launch(2);
 }
 
