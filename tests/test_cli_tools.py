@@ -196,10 +196,13 @@ def test_gpu_tools_write_identical_files(case, tmp_path):
     write_y4m(y4m, w, h, n, chroma=chroma)
     run(os.path.join(BIN, "ref_encoder_example"), "-o", ogv, "-v", str(q), "-k", str(kf), y4m)
     for extra in ([], ["-c"], ["-p", "6"]):
-        a, b = str(tmp_path / "ref.y4m"), str(tmp_path / "gpu.y4m")
+        a, b, z = str(tmp_path / "ref.y4m"), str(tmp_path / "gpu.y4m"), str(tmp_path / "gpu_z.y4m")
         run(os.path.join(BIN, "ref_dump_video"), *extra, "-o", a, ogv)
         run(os.path.join(BIN, "ocg_dump_video"), *extra, "-o", b, ogv)
         assert open(a, "rb").read() == open(b, "rb").read(), "dump_video output differs (%r)" % (extra,)
+        # zero-copy hand-off: rows written straight out of the page-locked buffer the device filled
+        run(os.path.join(BIN, "ocg_dump_video"), "-z", *extra, "-o", z, ogv)
+        assert open(a, "rb").read() == open(z, "rb").read(), "zero-copy dump_video output differs (%r)" % (extra,)
     if chroma == "420jpeg" and w <= 352:
         a, b = str(tmp_path / "ref1.ogv"), str(tmp_path / "gpu1.ogv")
         run(os.path.join(BIN, "ref_encoder_example"), "-o", a, "-v", str(q), "-k", "1", y4m)

@@ -37,7 +37,8 @@ class EncBackendStats(C.Structure):
                 ("me_repairs", C.c_long), ("satd_lookups", C.c_long), ("satd_host", C.c_long),
                 ("ssd_lookups", C.c_long), ("ssd_host", C.c_long), ("intra_satd_lookups", C.c_long),
                 ("fdct_quant_lookups", C.c_long), ("fdct_quant_host", C.c_long),
-                ("me_queue_seconds", C.c_double), ("me_sync_seconds", C.c_double)]
+                ("me_queue_seconds", C.c_double), ("me_sync_seconds", C.c_double),
+                ("prev_wait_seconds", C.c_double), ("me_prep_seconds", C.c_double)]
 
 
 ENC_AUTO, ENC_HOST = 0, 1

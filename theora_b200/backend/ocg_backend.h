@@ -104,6 +104,8 @@ typedef struct ocg_enc_backend_stats {
   long   fdct_quant_host;    /* ... computed by the reference's C kernels (another predictor, pool exhausted) */
   double me_queue_seconds;  /* host time queueing the inter-frame pre-pass (copies + kernels)       */
   double me_sync_seconds;   /* ... and waiting for its results                                      */
+  double prev_wait_seconds; /* host time at the start of a pass waiting for the previous frame's flush */
+  double me_prep_seconds;   /* ... preparing the motion analysis state (copies of oc_mb_enc_info)       */
 } ocg_enc_backend_stats;
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset);
 /* Test instrumentation: a snapshot at the start of every analysis pass of an encoder that runs on the

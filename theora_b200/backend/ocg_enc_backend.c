@@ -118,10 +118,13 @@ static pthread_mutex_t g_estats_lock = PTHREAD_MUTEX_INITIALIZER;
 
 OCG_API void ocg_backend_set_enc_mode(int mode) { g_enc_mode = mode; }
 OCG_API void ocg_backend_set_enc_spy(ocg_enc_spy_fn fn, void *user) { g_enc_spy = fn; g_enc_spy_user = user; }
+static double g_dbg_t[8];
+static long g_dbg_n;
+
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset) {
   pthread_mutex_lock(&g_estats_lock);
   if (out) *out = g_estats;
-  if (reset) memset(&g_estats, 0, sizeof(g_estats));
+  if (reset) { memset(&g_estats, 0, sizeof(g_estats)); memset(g_dbg_t, 0, sizeof(g_dbg_t)); g_dbg_n = 0; }
   pthread_mutex_unlock(&g_estats_lock);
 }
 
@@ -224,6 +227,7 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   oc_theora_state *st = &enc->state;
   static const int ROLE[5] = {OC_FRAME_IO, OC_FRAME_PREV_ORIG, OC_FRAME_GOLD_ORIG, OC_FRAME_PREV, OC_FRAME_GOLD};
   const int first_pass = !(b->me_seen_frame && b->me_frame_num == st->curframe_num);
+  const double t_enter = enc_now_s();
   int bufs[5], i, k, flags, wanted;
   size_t mbi;
   if (!first_pass) return 0; /* itab too: functions of the frames and the first pass's vectors */
@@ -291,6 +295,9 @@ static int enc_me_prepass(ocg_enc_backend *b) {
     const double tq0 = enc_now_s();
     double tq1;
     int pli, qii, zzi, r = 0;
+    pthread_mutex_lock(&g_estats_lock);
+    g_dbg_t[4] += tq0 - t_enter;
+    pthread_mutex_unlock(&g_estats_lock);
     if (b->inter_frame) {
       /* the frame's inter quantisers, condensed by analyze.c:544-564 just before this hook */
       for (pli = 0; pli < 3; pli++)
@@ -335,6 +342,13 @@ static int enc_me_prepass(ocg_enc_backend *b) {
   return 0;
 }
 
+__attribute__((destructor)) static void enc_dbg_print(void) {
+  if (getenv("OCG_ENC_TIMING") != NULL && g_dbg_n > 0)
+    fprintf(stderr, "[enc timing, ms per pass over %ld passes] wait %.3f staging %.3f me_total %.3f (prep %.3f) rest %.3f\n", g_dbg_n,
+            1e3 * g_dbg_t[0] / g_dbg_n, 1e3 * g_dbg_t[1] / g_dbg_n, 1e3 * g_dbg_t[2] / g_dbg_n, 1e3 * g_dbg_t[4] / g_dbg_n,
+            1e3 * g_dbg_t[3] / g_dbg_n);
+}
+
 /* ---- frame life cycle ---------------------------------------------------- */
 /* enquant_table_fixup, analyze.c:564: the first hook of every analysis pass (oc_enc_pipeline_init); the
    input frame is in OC_FRAME_IO, the references are rotated, state.frame_type says which analysis runs. */
@@ -351,11 +365,19 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
      analysis read (and its staging slots are free again) */
   enc_wait(b);
   if (b->failed) return;
+  {
+    const double tw = enc_now_s() - t0;
+    pthread_mutex_lock(&g_estats_lock);
+    g_estats.prev_wait_seconds += tw;
+    pthread_mutex_unlock(&g_estats_lock);
+  }
   if (nqis < 1 || nqis > 3) { enc_fail(b, "unexpected quantiser count"); return; }
   b->inter_frame = st->frame_type != OC_INTRA_FRAME;
   if (b->inter_frame && !b->inter_capable) { enc_fail(b, "inter frame in an encoder that was set up as intra-only"); return; }
   /* a pass that was analysed but never packed (dry run, re-analysis as a key frame) is simply dropped */
+  const double tA = enc_now_s();
   if (ocg_dec_staging(b->ctx, &b->st) < 0) { enc_fail(b, "ocg_dec_staging failed"); return; }
+  const double tB = enc_now_s();
   b->ncoded = b->nrows = 0;
   b->cur_fragi = -1;
   b->idct_pending = 0;
@@ -363,6 +385,10 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
   b->n_satd_hit = b->n_satd_miss = b->n_ssd_hit = b->n_ssd_host = b->n_isatd_hit = 0;
   b->n_fq_hit = b->n_fq_miss = 0;
   if (b->inter_capable && enc_me_prepass(b) < 0) return;
+  const double tC = enc_now_s();
+  pthread_mutex_lock(&g_estats_lock);
+  g_dbg_t[0] += tA - t0; g_dbg_t[1] += tB - tA; g_dbg_t[2] += tC - tB; g_dbg_n++;
+  pthread_mutex_unlock(&g_estats_lock);
   /* the speculative transform tables were made for one set of quantisers: a re-analysis with another uses
      the C kernels */
   b->fq_cur = -1;
@@ -399,6 +425,7 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
   pthread_mutex_lock(&g_estats_lock);
   g_estats.prepass_frames++;
   g_estats.prepass_seconds += enc_now_s() - t0;
+  g_dbg_t[3] += enc_now_s() - tC;
   pthread_mutex_unlock(&g_estats_lock);
 }
 

@@ -1255,6 +1255,7 @@ OCG_API int ocg_enc_intra_prepass(ocg_ctx *c, int io_buf, const uint8_t *host_fr
 OCG_API void ocg_pack_destroy(ocg_pack *p) {
   if (p == nullptr) return;
   ocg_set_device(p->device);
+  cudaDeviceSynchronize(); /* a pack is read by launches on any stream; its block goes back to the cache */
   cudaFree(p->blob);
   delete p;
 }

@@ -96,6 +96,19 @@ void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const OcgJobDev *j
                          cudaStream_t st);
 void ocg_init_device_tables(cudaStream_t st); /* idempotent; call once per context */
 
+/* ocg_pool.cu: caching allocators.  The translation units of the library reach them through the CUDA
+   runtime's own names (below), so every block an instance owns comes from the cache. */
+cudaError_t ocg_pool_host_alloc(void **pp, size_t size, unsigned flags);
+cudaError_t ocg_pool_host_free(void *p);
+cudaError_t ocg_pool_dev_alloc(void **pp, size_t size);
+cudaError_t ocg_pool_dev_free(void *p);
+#ifndef OCG_POOL_IMPLEMENTATION
+#define cudaHostAlloc(pp, size, flags) ocg_pool_host_alloc((void **)(pp), (size), (flags))
+#define cudaFreeHost(p) ocg_pool_host_free((void *)(p))
+#define cudaMalloc(pp, size) ocg_pool_dev_alloc((void **)(pp), (size))
+#define cudaFree(p) ocg_pool_dev_free((void *)(p))
+#endif
+
 void ocg_count_launch(int n);
 cudaError_t ocg_set_device(int device); /* cudaSetDevice unless it is already the thread's device */
 

@@ -29,14 +29,16 @@ static void stripe_decoded(void *ctx, th_ycbcr_buffer src, int fragy0, int fragy
 }
 
 static void usage(void) {
-  fprintf(stderr, "usage: ocg_dump_video [-o out.y4m] [-c] [-r] [-f] [-p pplevel] in.ogv\n"
-                  "  -c crop to the picture region   -r raw planes, no YUV4MPEG2 framing   -f only report fps\n");
+  fprintf(stderr, "usage: ocg_dump_video [-o out.y4m] [-c] [-r] [-f] [-z] [-p pplevel] in.ogv\n"
+                  "  -c crop to the picture region   -r raw planes, no YUV4MPEG2 framing   -f only report fps\n"
+                  "  -z zero-copy: no stripe callback; rows are written straight out of the buffer th_decode_ycbcr_out\n"
+                  "     hands out (with the B200 back-end: the page-locked buffer the device wrote the frame into)\n");
   exit(1);
 }
 
 int main(int argc, char **argv) {
   const char *in = NULL, *out = NULL;
-  int crop = 0, raw = 0, fps_only = 0, pplevel = 0, i;
+  int crop = 0, raw = 0, fps_only = 0, pplevel = 0, zero_copy = 0, i;
   FILE *fin, *fout = NULL;
   oggl_reader rd;
   oggl_packet pk;
@@ -52,6 +54,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "-c")) crop = 1;
     else if (!strcmp(argv[i], "-r")) raw = 1;
     else if (!strcmp(argv[i], "-f")) fps_only = 1;
+    else if (!strcmp(argv[i], "-z")) zero_copy = 1;
     else if (!strcmp(argv[i], "-p") && i + 1 < argc) pplevel = atoi(argv[++i]);
     else if (argv[i][0] == '-') usage();
     else in = argv[i];
@@ -87,7 +90,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "post-processing level %d refused\n", pplevel);
         return 1;
       }
-      {
+      if (!zero_copy) {
         th_stripe_callback cb;
         int pli;
         for (pli = 0; pli < 3; pli++) {
@@ -122,6 +125,8 @@ int main(int argc, char **argv) {
       int dr = th_decode_packetin(td, &op, &gp);
       if (dr < 0 && dr != TH_DUPFRAME) { fprintf(stderr, "th_decode_packetin: %d\n", dr); return 1; }
       frames++;
+      /* dump_video.c:245-250 ("normal, non-striped decoding"): the decoder's own buffer, no copy in between */
+      if (zero_copy && (fout != NULL || fps_only) && th_decode_ycbcr_out(td, ycbcr) < 0) { fprintf(stderr, "th_decode_ycbcr_out failed\n"); return 1; }
       if (fout != NULL) { /* dump_video.c:203-241 */
         int x0 = 0, y0 = 0, xend = (int)ti.frame_width, yend = (int)ti.frame_height, hdec = 0, vdec = 0, pli, y;
         if (crop) { x0 = (int)ti.pic_x; y0 = (int)ti.pic_y; xend = x0 + (int)ti.pic_width; yend = y0 + (int)ti.pic_height; }
@@ -149,6 +154,6 @@ int main(int argc, char **argv) {
   oggl_reader_clear(&rd);
   if (fout != NULL && fout != stdout) fclose(fout);
   fclose(fin);
-  for (i = 0; i < 3; i++) free(ycbcr[i].data);
+  if (!zero_copy) for (i = 0; i < 3; i++) free(ycbcr[i].data);
   return 0;
 }

@@ -53,7 +53,8 @@ def main():
     if kf > 1:
         calls = st.satd_lookups + st.satd_host
         out["prepass_breakdown_ms"] = {"queue": 1e3 * st.me_queue_seconds / max(st.me_frames, 1),
-                                       "wait_for_results": 1e3 * st.me_sync_seconds / max(st.me_frames, 1)}
+                                       "wait_for_results": 1e3 * st.me_sync_seconds / max(st.me_frames, 1),
+                                       "wait_for_previous_flush": 1e3 * st.prev_wait_seconds / max(st.prepass_frames, 1)}
         out["motion_analysis"] = {"device_passes": int(st.me_frames), "gold_refinements": int(st.me_gold_refines),
                                   "gold_searches_redone": int(st.me_repairs)}
         out["block_metric_calls"] = {"satd_from_device_tables": int(st.satd_lookups), "satd_on_host": int(st.satd_host),
