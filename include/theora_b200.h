@@ -486,7 +486,7 @@ typedef struct ocg_enc_inter_tables {
   const int32_t  *cand_dc;
   long            d2h_bytes;
   /* speculative frag_sub + fDCT + quantiser (oc_enc_block_transform_quantize, analyze.c:704-782) against the
-     predictors of candidates OCG_ENC_FQ_CAND0/1, for every fragment and each of the frame's fq_nqis inter
+     predictors of candidates OCG_ENC_FQ_CAND0/1/2, for every fragment and each of the frame's fq_nqis inter
      quantisers (0: not produced).  fq_desc[sel * nfrags + fragi]; the arrays of an entry sit back to back in
      fq_pool at 8 * off int16: (count+7)/8*8 coefficients of the transform output, then as many per
      quantiser; everything beyond `count` is zero for every quantiser.  off == UINT32_MAX: not available. */
@@ -499,9 +499,10 @@ typedef struct ocg_enc_fq_desc {
   uint8_t  count;      /* leading zig-zag coefficients stored (1..64) */
   uint8_t  nz[3];      /* oc_enc_quantize's return value per quantiser */
 } ocg_enc_fq_desc;
-#define OCG_ENC_FQ_NSEL  2
+#define OCG_ENC_FQ_NSEL  3
 #define OCG_ENC_FQ_CAND0 0   /* PREV (0,0)              */
 #define OCG_ENC_FQ_CAND1 3   /* PREV, refined vector    */
+#define OCG_ENC_FQ_CAND2 2   /* PREV, unrefined vector  */
 static inline size_t ocg_enc_cand_index(const ocg_enc_inter_tables *t, int k, int fragi) {
   return fragi < t->nluma ? (size_t)k * (size_t)t->nluma + (size_t)fragi
                           : (size_t)t->ncand * (size_t)t->nluma + (size_t)k * (size_t)(t->nfrags - t->nluma) + (size_t)(fragi - t->nluma);

@@ -120,6 +120,7 @@ OCG_API void ocg_backend_set_enc_mode(int mode) { g_enc_mode = mode; }
 OCG_API void ocg_backend_set_enc_spy(ocg_enc_spy_fn fn, void *user) { g_enc_spy = fn; g_enc_spy_user = user; }
 static double g_dbg_t[8];
 static long g_dbg_n;
+static long g_dbg_miss[10]; /* fq misses by the candidate that would have served them; [8] none; [9] sub_128 in inter frames */
 
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset) {
   pthread_mutex_lock(&g_estats_lock);
@@ -347,6 +348,10 @@ __attribute__((destructor)) static void enc_dbg_print(void) {
     fprintf(stderr, "[enc timing, ms per pass over %ld passes] wait %.3f staging %.3f me_total %.3f (prep %.3f) rest %.3f\n", g_dbg_n,
             1e3 * g_dbg_t[0] / g_dbg_n, 1e3 * g_dbg_t[1] / g_dbg_n, 1e3 * g_dbg_t[2] / g_dbg_n, 1e3 * g_dbg_t[4] / g_dbg_n,
             1e3 * g_dbg_t[3] / g_dbg_n);
+  if (getenv("OCG_ENC_TIMING") != NULL)
+    fprintf(stderr, "[enc fq misses by candidate] %ld %ld %ld %ld %ld %ld %ld %ld none %ld; sub_128 in inter frames %ld\n", g_dbg_miss[0],
+            g_dbg_miss[1], g_dbg_miss[2], g_dbg_miss[3], g_dbg_miss[4], g_dbg_miss[5], g_dbg_miss[6], g_dbg_miss[7], g_dbg_miss[8],
+            g_dbg_miss[9]);
 }
 
 /* ---- frame life cycle ---------------------------------------------------- */
@@ -615,6 +620,7 @@ static void ocge_frag_sub_128(ogg_int16_t _diff[64], const unsigned char *_src, 
       enc_fail(b, "frag_sub_128: not a fragment of the input frame");
     }
   }
+  if (b != NULL && b->inter_frame) __sync_fetch_and_add(&g_dbg_miss[9], 1);
   oc_enc_frag_sub_128_c(_diff, _src, _ystride);
 }
 
@@ -636,7 +642,7 @@ static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, cons
       /* served from the speculative tables iff the predictor is one they were computed with */
       ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
       if (fragi >= 0) {
-        static const int SEL_CAND[OCG_ENC_FQ_NSEL] = {OCG_ENC_FQ_CAND0, OCG_ENC_FQ_CAND1};
+        static const int SEL_CAND[OCG_ENC_FQ_NSEL] = {OCG_ENC_FQ_CAND0, OCG_ENC_FQ_CAND1, OCG_ENC_FQ_CAND2};
         ptrdiff_t r1, r2 = INT32_MIN;
         int sel;
         if (_ref == b->c2_dst) { r1 = b->c2_r1 - b->pool0; r2 = b->c2_r2 - b->pool0; }
@@ -656,6 +662,17 @@ static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, cons
         }
       }
       b->n_fq_miss++;
+      if (fragi >= 0 && getenv("OCG_ENC_TIMING") != NULL) {
+        ptrdiff_t r1, r2 = INT32_MIN;
+        int k, hit = 8;
+        if (_ref == b->c2_dst) { r1 = b->c2_r1 - b->pool0; r2 = b->c2_r2 - b->pool0; }
+        else r1 = _ref - b->pool0;
+        for (k = 0; k < 8 && hit == 8; k++) {
+          const ocg_enc_frag *c = b->itab.cand + ocg_enc_cand_index(&b->itab, k, (int)fragi);
+          if ((c->ref_off0 == r1 && c->ref_off1 == r2) || (r2 != INT32_MIN && c->ref_off0 == r2 && c->ref_off1 == r1)) hit = k;
+        }
+        __sync_fetch_and_add(&g_dbg_miss[hit], 1);
+      }
     }
     b->c2_dst = NULL;
   }

@@ -376,8 +376,9 @@ ocg_enc_cand_kernel(const OcgCandJob J) {
    whenever they repeat it) -- the whole chain is computed ahead for every fragment and every quantiser of
    the frame, and handed over in compact form: only the leading `count` zig-zag coefficients, beyond which
    every quantiser's output is zero. */
-#define OCG_FQ_NSEL 2
-__constant__ int c_fq_sel[OCG_FQ_NSEL] = {0, 3};
+#define OCG_FQ_NSEL 3
+__constant__ int c_fq_sel[OCG_FQ_NSEL] = {0, 3, 2}; /* measured on the benchmark encode: 80 % of the blocks the first two
+                                                       missed were coded against PREV displaced by the UNREFINED vector */
 
 __global__ void __launch_bounds__(256)
 ocg_enc_fq_list_kernel(const ocg_enc_frag *__restrict__ cand, ocg_enc_frag *__restrict__ fq, int nfrags, int nluma, int nqis) {
@@ -403,37 +404,52 @@ ocg_enc_fq_list_kernel(const ocg_enc_frag *__restrict__ cand, ocg_enc_frag *__re
 struct ocg_fq_desc_dev { uint32_t off; uint8_t count, nz[3]; };
 
 __global__ void __launch_bounds__(256)
-ocg_enc_fq_compact_kernel(const int16_t *__restrict__ dct, const int16_t *__restrict__ qdct, const int32_t *__restrict__ nonzero,
-                          int nfrags, int nluma, int nqis, ocg_fq_desc_dev *__restrict__ desc, uint4 *__restrict__ pool,
-                          uint32_t pool_units, uint32_t *__restrict__ counter) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (i >= nfrags * OCG_FQ_NSEL) return;
-  const int sel = i / nfrags, f = i - sel * nfrags;
+ocg_enc_fq_compact_kernel(const ocg_enc_frag *__restrict__ cand, const int16_t *__restrict__ dct, const int16_t *__restrict__ qdct,
+                          const int32_t *__restrict__ nonzero, int nfrags, int nluma, int nqis, ocg_fq_desc_dev *__restrict__ desc,
+                          uint4 *__restrict__ pool, uint32_t pool_units, uint32_t *__restrict__ counter) {
+  const int f = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (f >= nfrags) return;
   const int nchroma = nfrags - nluma;
   const bool luma = f < nluma;
-  size_t at[3];
-  int nz[3] = {0, 0, 0}, cnt = 0;
-  for (int q = 0; q < nqis; q++) {
-    const int slot = q * OCG_FQ_NSEL + sel;
-    at[q] = luma ? (size_t)slot * nluma + f : (size_t)3 * OCG_FQ_NSEL * nluma + (size_t)slot * nchroma + (f - nluma);
-    nz[q] = nonzero[at[q]];
-    cnt = max(cnt, nz[q] + 1);
-  }
-  cnt = min(cnt, 64);
-  const uint32_t rows = (uint32_t)(cnt + 7) >> 3;          /* 16-byte units per array */
-  const uint32_t need = rows * (uint32_t)(1 + nqis);
-  const uint32_t off = atomicAdd(counter, need);
-  ocg_fq_desc_dev d;
-  d.off = off + need <= pool_units ? off : 0xFFFFFFFFu;     /* pool exhausted: the host computes this one itself */
-  d.count = (uint8_t)cnt;
-  d.nz[0] = (uint8_t)nz[0]; d.nz[1] = (uint8_t)nz[1]; d.nz[2] = (uint8_t)nz[2];
-  desc[i] = d;
-  if (d.off == 0xFFFFFFFFu) return;
-  const uint4 *sd = (const uint4 *)(dct + at[0] * 64);
-  for (uint32_t r = 0; r < rows; r++) pool[off + r] = sd[r];
-  for (int q = 0; q < nqis; q++) {
-    const uint4 *sq = (const uint4 *)(qdct + at[q] * 64);
-    for (uint32_t r = 0; r < rows; r++) pool[off + (uint32_t)(1 + q) * rows + r] = sq[r];
+  ocg_enc_frag tap[OCG_FQ_NSEL];
+  ocg_fq_desc_dev done[OCG_FQ_NSEL];
+  for (int sel = 0; sel < OCG_FQ_NSEL; sel++) {
+    const int k = c_fq_sel[sel];
+    tap[sel] = cand[luma ? (size_t)k * nluma + f : (size_t)OCG_ENC_NCAND * nluma + (size_t)k * nchroma + (f - nluma)];
+    /* a predictor that repeats an earlier one (a refinement that moved nothing) shares its entry */
+    int same = -1;
+    for (int e = 0; e < sel; e++)
+      if (tap[e].ref_off0 == tap[sel].ref_off0 && tap[e].ref_off1 == tap[sel].ref_off1) same = e;
+    if (same >= 0) {
+      done[sel] = done[same];
+      desc[(size_t)sel * nfrags + f] = done[sel];
+      continue;
+    }
+    size_t at[3];
+    int nz[3] = {0, 0, 0}, cnt = 0;
+    for (int q = 0; q < nqis; q++) {
+      const int slot = q * OCG_FQ_NSEL + sel;
+      at[q] = luma ? (size_t)slot * nluma + f : (size_t)3 * OCG_FQ_NSEL * nluma + (size_t)slot * nchroma + (f - nluma);
+      nz[q] = nonzero[at[q]];
+      cnt = max(cnt, nz[q] + 1);
+    }
+    cnt = min(cnt, 64);
+    const uint32_t rows = (uint32_t)(cnt + 7) >> 3;          /* 16-byte units per array */
+    const uint32_t need = rows * (uint32_t)(1 + nqis);
+    const uint32_t off = atomicAdd(counter, need);
+    ocg_fq_desc_dev d;
+    d.off = off + need <= pool_units ? off : 0xFFFFFFFFu;     /* pool exhausted: the host computes this one itself */
+    d.count = (uint8_t)cnt;
+    d.nz[0] = (uint8_t)nz[0]; d.nz[1] = (uint8_t)nz[1]; d.nz[2] = (uint8_t)nz[2];
+    done[sel] = d;
+    desc[(size_t)sel * nfrags + f] = d;
+    if (d.off == 0xFFFFFFFFu) continue;
+    const uint4 *sd = (const uint4 *)(dct + at[0] * 64);
+    for (uint32_t r = 0; r < rows; r++) pool[off + r] = sd[r];
+    for (int q = 0; q < nqis; q++) {
+      const uint4 *sq = (const uint4 *)(qdct + at[q] * 64);
+      for (uint32_t r = 0; r < rows; r++) pool[off + (uint32_t)(1 + q) * rows + r] = sq[r];
+    }
   }
 }
 
@@ -1711,7 +1727,7 @@ OCG_API int ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, 
   EI_CU(cudaMemsetAsync(ei->d_cand, 0, K * nf * sizeof(ocg_enc_frag), st));
   {
     const size_t nfq = 3 * OCG_FQ_NSEL * nf;
-    ei->fq_pool_units = (uint32_t)((12u << 20) / 16);
+    ei->fq_pool_units = (uint32_t)((16u << 20) / 16);
     EI_CU(cudaMalloc(&ei->d_fq, nfq * sizeof(ocg_enc_frag)));
     EI_CU(cudaMalloc(&ei->d_fq_dct, nfq * 128));
     EI_CU(cudaMalloc(&ei->d_fq_qdct, nfq * 128));
@@ -1814,8 +1830,8 @@ OCG_API int ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, i
                                      ei->d_fq_dct + cbase * 64, ei->d_fq_qdct + cbase * 64, ei->d_fq_nz + cbase, st);
       if (r != OCG_OK) return r;
       if (cudaMemsetAsync(ei->d_fq_counter, 0, 4, st) != cudaSuccess) return OCG_ECUDA;
-      ocg_enc_fq_compact_kernel<<<(unsigned)((ei->nfrags * OCG_FQ_NSEL + 255) / 256), 256, 0, st>>>(
-          ei->d_fq_dct, ei->d_fq_qdct, ei->d_fq_nz, ei->nfrags, nl, nq, ei->d_fq_desc, ei->d_fq_pool, ei->fq_pool_units, ei->d_fq_counter);
+      ocg_enc_fq_compact_kernel<<<(unsigned)((ei->nfrags + 255) / 256), 256, 0, st>>>(
+          ei->d_cand, ei->d_fq_dct, ei->d_fq_qdct, ei->d_fq_nz, ei->nfrags, nl, nq, ei->d_fq_desc, ei->d_fq_pool, ei->fq_pool_units, ei->d_fq_counter);
       ocg_count_launch(1);
       if (cudaMemcpyAsync(ei->h_fq_counter, ei->d_fq_counter, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaMemcpyAsync(ei->h_fq_desc, ei->d_fq_desc, (size_t)OCG_FQ_NSEL * ei->nfrags * sizeof(ocg_fq_desc_dev), cudaMemcpyDeviceToHost, st) != cudaSuccess)
