@@ -480,6 +480,7 @@ def main():
     ap.add_argument("--no-noisy", action="store_true", help="skip the dense-coefficient roofline workload")
     ap.add_argument("--no-config4", action="store_true", help="skip the 3840x2160 decode+encode section (BASELINE configs[4])")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-postproc", action="store_true", help="skip the post-processing (pp level 6) e2e section")
     ap.add_argument("--no-encode-kernels", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -675,6 +676,7 @@ def main():
     # the stream threads), ours and -- on a single GPU -- the reference interleaved pass by pass.
     e2e = None
     cpu = None
+    postproc = None
     if not args.no_e2e:
         blob_path = os.path.join("/tmp", "theora_b200_bench_rank%d.ogs" % RANK)
         with open(blob_path, "wb") as f:
@@ -686,13 +688,14 @@ def main():
 
         npass = [0]
 
-        def e2e_pass(nthreads, blocking, dc_mode, ref_threads):
+        def e2e_pass(nthreads, blocking, dc_mode, ref_threads, pplevel=0):
             # ranks start together and finished ranks SLEEP until the last one is done (a NCCL barrier would
             # spin a host core per waiting rank and slow the ranks that are still measuring)
             npass[0] += 1
             barrier()
             p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dec_e2e_bench.py"), blob_path, str(nthreads),
-                                str(int(ref_threads)), str(dc_mode), str(int(blocking))], capture_output=True, text=True,
+                                str(int(ref_threads)), str(dc_mode), str(int(blocking)), "0", str(int(pplevel))],
+                               capture_output=True, text=True,
                                env=env, timeout=1200)
             if p.returncode != 0:
                 raise RuntimeError("dec_e2e_bench failed: " + p.stderr[-400:])
@@ -722,6 +725,18 @@ def main():
                 a = e2e_pass(nthr, blk, dm, 0)[0]
                 alts.append({k: a[k] for k in ("value", "host_threads", "wait", "dc_unprediction", "flush_ms_per_frame",
                                                "wait_ms_per_frame", "final_frame_hash")})
+        # the same streams with the out-of-loop de-blocking + de-ringing filters on (TH_DECCTL_SET_PPLEVEL 6:
+        # luma and chroma), device filters vs the reference's host filters
+        if with_ref and not args.no_postproc:
+            try:
+                ppr, ppraw = e2e_pass(ncores * tpc, tpc > 1, dcm, ncores, pplevel=6)
+                postproc = {"workload": workload + ", post-processing level 6 (de-blocking + de-ringing, luma and chroma)",
+                            "value": ppr["value"], "unit": "frames/s", "host_threads": ppr["host_threads"],
+                            "api": "th_decode_ctl(TH_DECCTL_SET_PPLEVEL) + th_decode_packetin + th_decode_ycbcr_out",
+                            "cpu_baseline": {"value": ncores * nframes / ppraw["ref_secs"], "cores": ncores, "kind": "reference"},
+                            "identical_to_reference": bool(ppraw["hash"] == ppraw["ref_hash"])}
+            except Exception as e:
+                postproc = {"error": repr(e)}
         e2e["alternatives"] = alts
         e2e["all_variants_same_output"] = all(a["final_frame_hash"] == e2e["final_frame_hash"] for a in alts)
         if "ref_secs" in raw:
@@ -811,6 +826,7 @@ def main():
                            "frames + lists) exceeds the 126 MB L2" % (S, g.ref_frame_sz / 1e6),
                            "parallelism": "independent streams, %d per GPU on %d CUDA stream(s)" % (S, G)},
                 "roofline": roofline, "roofline_dense_coefficients": roofline_noisy, "cpu_baseline": cpu, "e2e": e2e,
+                "postprocess": postproc,
                 "config4_2160p": config4, "encode_kernels": enc,
                 "encode_intra": enc_intra, "encode_inter": enc_inter, "motion_analysis": me_frame,
                 "gpu_launches": int(launches),

@@ -18,6 +18,7 @@ def main():
     dc_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1   # streams.DC_HOST
     blocking = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     expand = int(sys.argv[6]) if len(sys.argv) > 6 else 0     # OCG_EXPAND_DEVICE
+    pplevel = int(sys.argv[7]) if len(sys.argv) > 7 else 0    # TH_DECCTL_SET_PPLEVEL for every timed decoder
     import support as S
     import th_streams as streams
     blob = open(path, "rb").read()
@@ -30,6 +31,7 @@ def main():
     Lo.ocg_backend_set_expand_mode(expand)
     from theora_b200 import abi
     abi.lib().ocg_set_blocking_sync(blocking)
+    Lo.refh_set_timed_pplevel(pplevel)
     Lo.refh_decode_time(h, min(threads, 2), 1, None)  # warm-up
     R = hr = None
     kind = None
@@ -37,6 +39,7 @@ def main():
         kind = "asm" if S.ref_available("asm") else "c"
         R = S.ref(kind)
         hr = R.refh_stream_from_blob(buf, len(blob))
+        R.refh_set_timed_pplevel(pplevel)
     st = streams.BackendStats()
     ours, refs = [], []
     hsh, rh = C.c_uint64(0), C.c_uint64(0)

@@ -414,9 +414,14 @@ typedef struct refh_job {
   int fail;
 } refh_job;
 
+/* post-processing level the timed decoders run with (TH_DECCTL_SET_PPLEVEL; 0 = none) */
+static int refh_timed_pplevel;
+REFH_API void refh_set_timed_pplevel(int level) { refh_timed_pplevel = level; }
+
 static void *refh_decode_worker(void *arg) {
   refh_job *j = (refh_job *)arg;
   refh_dec *d = refh_dec_open(j->s);
+  if (d != NULL && refh_timed_pplevel > 0) refh_dec_set_pplevel(d, refh_timed_pplevel);
   double t0;
   int p;
   /* every worker finishes its set-up (decoder, device context, warm-up packet)
