@@ -259,6 +259,10 @@ OCG_API long ocg_launch_count(void);   /* kernels launched by this library so fa
    (67 vs 48 us per 32-frame launch: 4 KB boxes are too small to amortise the
    TMA issue cost), so it is opt-in.  Call before creating contexts. */
 OCG_API void ocg_set_lf_tma(int on);
+/* How ocg_dec_flush / ocg_dec_flush_tokens hand the picture (OCG_OUT_PICTURE) to the host: 0 = a kernel
+   writes it through mapped host memory (the whole flush stays one graph of kernels), 1 = three 2-D copies
+   by the copy engines behind the graph, then the completion flag. */
+OCG_API void ocg_set_out_dma(int on);
 /* Wait policy of ocg_dec_wait (and of ocg_ctx_sync: 0 = cudaStreamSynchronize, non-zero = a blocking event):
    0 (default) spin on the completion flag; 1 sched_yield between looks; 2 SLEEP: one poller thread per
    process watches the flags of every sleeping waiter and wakes it (semaphore).  With more stream threads

@@ -165,6 +165,7 @@ _PROTOS = {
     "ocg_set_stage_mask": (None, [C.c_int]),
     "ocg_launch_count": (C.c_long, []),
     "ocg_set_lf_tma": (None, [C.c_int]),
+    "ocg_set_out_dma": (None, [C.c_int]),
     "ocg_set_blocking_sync": (None, [C.c_int]),
     "ocg_test_sleep_until": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int]),
     "ocg_me_nmbs": (C.c_int, [C.POINTER(Geometry)]),

@@ -21,6 +21,7 @@ thread_local char g_err[512] = "";
 std::atomic<long> g_launches{0};
 std::atomic<int> g_stage_mask{7};
 std::atomic<int> g_blocking_sync{0};
+std::atomic<int> g_out_dma{0}; /* ocg_set_out_dma: the picture leaves through the copy engines instead of the copy-out kernel */
 std::atomic<int> g_use_tma{0}; /* measured slower than per-thread loads on B200 (67 vs 48 us): opt-in */
 
 int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -320,6 +321,7 @@ OCG_API int ocg_device_count(void) {
 
 OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
 
+OCG_API void ocg_set_out_dma(int on) { g_out_dma.store(on ? 1 : 0); }
 extern int g_ocg_lf_legacy;
 OCG_API void ocg_set_lf_tma(int on) { g_use_tma.store(on == 1 ? 1 : 0); g_ocg_lf_legacy = on == 2; }
 
@@ -895,10 +897,12 @@ static inline long now_ns() {
    flag in host memory needs one. */
 /* Shared tail of ocg_dec_flush / ocg_dec_flush_tokens: the slot's job header is filled in except for the
    destination and the sequence number. */
+static const int kOutDeferred = 3; /* internal out_mode: no copy-out kernel in the sequence */
 static int flush_core(ocg_ctx *c, int si, uint8_t *host_out, int out_mode, int dc, int lf, int tokens, long t_in) {
   Slot &s = c->slots[si];
   cudaStream_t st = c->stream;
   int r;
+  if (out_mode == OCG_OUT_PICTURE && g_out_dma.load(std::memory_order_relaxed)) out_mode = kOutDeferred;
   const bool tma = c->d_tmaps != nullptr && g_use_tma.load();
   /* the destination's device address (one driver call per distinct buffer, then remembered) */
   uint8_t *d_out_mapped = nullptr;
@@ -956,6 +960,19 @@ static int flush_core(ocg_ctx *c, int si, uint8_t *host_out, int out_mode, int d
   } else {
     launch_flush_sequence(c, si, out_mode, dc, lf, tokens, tma); /* the launch helpers count their kernels */
     CU(cudaGetLastError());
+  }
+  if (out_mode == kOutDeferred) {
+    /* the picture by the copy engines (three 2-D copies, one per plane), then the completion flag */
+    const ocg_geometry &g = c->geom;
+    const uint8_t *dev_frame = s.job->base[OCG_FRAME_SELF] - g.base_off;
+    for (int pli = 0; pli < 3; pli++) {
+      const ocg_plane_geom &p = g.planes[pli];
+      const int64_t off = g.base_off + p.plane_off + (int64_t)(p.height - 1) * p.ystride; /* top-left pixel */
+      CU(cudaMemcpy2DAsync(host_out + off, (size_t)-p.ystride, dev_frame + off, (size_t)-p.ystride, (size_t)p.width, (size_t)p.height,
+                           cudaMemcpyDeviceToHost, st));
+    }
+    ocg_launch_copy_out(c->geom, OCG_OUT_NONE, c->d_job, c->d_out_counter, c->d_done, st);
+    nk++;
   }
   const long t_out = now_ns();
   g_flush_prep_ns.fetch_add(t_launch - t_in - t_build, std::memory_order_relaxed);

@@ -1375,6 +1375,7 @@ ocg_copy_out_kernel(const OcgOutPlan plan, const OcgJobDev *__restrict__ job, ui
 /* out_mode: OCG_OUT_PICTURE / OCG_OUT_PADDED / OCG_OUT_NONE (flag only) */
 void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const OcgJobDev *job, uint32_t *counter, uint32_t *host_flag,
                          cudaStream_t st) {
+  if (out_mode == 3) return; /* OCG_OUT_DEFERRED (internal): the caller moves the picture itself and flags afterwards */
   OcgOutPlan plan;
   memset(&plan, 0, sizeof(plan));
   plan.base_off = g.base_off;

@@ -31,6 +31,8 @@ def main():
     Lo.ocg_backend_set_expand_mode(expand)
     from theora_b200 import abi
     abi.lib().ocg_set_blocking_sync(blocking)
+    if os.environ.get("OCG_OUT_DMA"):  # A/B of the hand-over path (diagnostic)
+        abi.lib().ocg_set_out_dma(int(os.environ["OCG_OUT_DMA"]))
     Lo.refh_set_timed_pplevel(pplevel)
     Lo.refh_decode_time(h, min(threads, 2), 1, None)  # warm-up
     R = hr = None
