@@ -424,8 +424,11 @@ ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs, i
   const OcgJobDev &job = jobs[jobi];
   const int nx = *(volatile const int *)job.xcount;
   constexpr int NW = OCG_RECON_THREADS / 32;
-  for (int e0 = (rank * NW + w) * 32; e0 < nx; e0 += nranks * NW * 32) {
-    const int nvalid = min(32, nx - e0);
+  /* entries per warp and round: 32, or -- when the list is short for the warps that serve it -- just enough
+     (a multiple of 8) that one round covers it: a short list is latency, not throughput */
+  const int E = min(32, max(8, (((nx + nranks * NW - 1) / (nranks * NW)) + 7) & ~7));
+  for (int e0 = (rank * NW + w) * E; e0 < nx; e0 += nranks * NW * E) {
+    const int nvalid = min(E, nx - e0);
     int cls = WC_NONE;
     int4 it = make_int4(0, 0, 0, 0);
     unsigned tap = 0;
