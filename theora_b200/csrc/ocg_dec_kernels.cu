@@ -28,6 +28,15 @@
 
 namespace {
 
+/* Programmatic dependent launch: a kernel launched with ocg_launch_pdl may become resident while the kernel
+   before it in the stream is still running; it must call pdl_wait() before it touches anything that kernel
+   wrote (the wait returns when the predecessor has completed and its writes are visible).  pdl_release()
+   lets the NEXT kernel's CTAs in; it is placed behind pdl_wait(), so a kernel's successor never runs ahead
+   of the kernel's own predecessor.  Hides the launch latency and the prologue (table staging, flag loads)
+   of the four kernels of a frame behind the tail of the one before. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int K1 = 64277, K2 = 60547, K3 = 54491, K4 = 46341, K5 = 36410, K6 = 25080, K7 = 12785;
 
 __device__ __forceinline__ int sext16(int v) { return (int)(short)v; }
@@ -331,6 +340,8 @@ __device__ __forceinline__ void load_rows(const uint8_t *p, int ystride, RowsN<O
 template <int OCG_A_ROWS, int MINB>
 __global__ void __launch_bounds__(OCG_SIMPLE_THREADS, MINB)
 ocg_recon_simple_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
+  pdl_wait(); /* the records (built by the kernel before, in the token path) and the previous frame's pixels */
+  pdl_release();
   const OcgJobDev &job = jobs[blockIdx.y];
   const int lane = (int)threadIdx.x & 31;
   const int fragi = (int)(blockIdx.x * OCG_SIMPLE_THREADS + threadIdx.x);
@@ -422,6 +433,8 @@ ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs, i
   const int jobi = (int)blockIdx.x % njobs, rank = (int)blockIdx.x / njobs;
   const int nranks = ((int)gridDim.x - 1 - jobi) / njobs + 1;
   const OcgJobDev &job = jobs[jobi];
+  pdl_wait(); /* pass A's list, counter and pixels */
+  pdl_release();
   const int nx = *(volatile const int *)job.xcount;
   constexpr int NW = OCG_RECON_THREADS / 32;
   /* entries per warp and round: 32, or -- when the list is short for the warps that serve it -- just enough
@@ -814,8 +827,17 @@ ocg_lf2_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const int cy0 = grp * GR + (int)threadIdx.y * R;
   const bool live = cx <= nh && cy0 <= nv;
   const bool inl = cx > 0, inr = cx < nh;
-  /* coded flags of the R+1 fragment rows around the strip's corners, all requested before the table is
-     staged: 2 bits per row (bit 0 left of the corner, bit 1 right of it) */
+  {
+    /* the table does not depend on the frame: staged while the reconstruction kernels drain */
+    const int tid = (int)(threadIdx.y * TX + threadIdx.x);
+    const uint4 *src = (const uint4 *)g_lf_tab2[lim];
+#pragma unroll
+    for (int k = 0; k < OCG_LF2_TAB / 4 / (TX * TY); k++) ((uint4 *)tab)[tid + k * TX * TY] = src[tid + k * TX * TY];
+  }
+  pdl_wait(); /* the coded map and the pixels of the reconstruction kernels */
+  pdl_release();
+  /* coded flags of the R+1 fragment rows around the strip's corners, all requested up front: 2 bits per row
+     (bit 0 left of the corner, bit 1 right of it) */
   unsigned coded = 0;
   if (live) {
     const uint8_t *cm = job.coded + P.froffset + cx;
@@ -829,12 +851,6 @@ ocg_lf2_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
     }
 #pragma unroll
     for (int k = 0; k <= R; k++) coded |= ((fl[k][0] ? 1u : 0u) | (fl[k][1] ? 2u : 0u)) << (2 * k);
-  }
-  {
-    const int tid = (int)(threadIdx.y * TX + threadIdx.x);
-    const uint4 *src = (const uint4 *)g_lf_tab2[lim];
-#pragma unroll
-    for (int k = 0; k < OCG_LF2_TAB / 4 / (TX * TY); k++) ((uint4 *)tab)[tid + k * TX * TY] = src[tid + k * TX * TY];
   }
   __syncthreads();
   if (!live) return;
@@ -978,43 +994,48 @@ ocg_lf_tma_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
 /* ------------------------------------------------------------------------ */
 /* Apron replication, state.c:770-835: every apron byte takes the nearest
    picture pixel (rows first, then full-width caps == clamp in both axes).
-   One thread per 8-byte work item, items enumerated linearly per job:
-     side items  every picture row x {left,right} x hpad/8
-     cap items   every apron row above/below x padded width/8            */
+   Items are enumerated linearly per job:
+     side items  every picture row x {left,right}: one thread reads the edge pixel and writes the whole
+                 apron row (hpad bytes)
+     cap items   every 8-byte column chunk of the padded width x {below,above}: one thread reads its 8 source
+                 bytes of the edge row once and writes all vpad apron rows */
 __global__ void __launch_bounds__(256)
 ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   const OcgJobDev &job = jobs[blockIdx.y];
   int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  pdl_wait(); /* the filtered picture; pass B is done with the work list */
+  pdl_release();
   if (t == 0) job.xcount[0] = 0; /* recon pass B is done with this frame's work list */
 #pragma unroll
   for (int pli = 0; pli < 3; pli++) {
     const OcgPlaneDev &P = g.p[pli];
-    const int hq = P.hpad >> 3;
-    const int nside = P.height * 2 * hq;
+    const int nside = P.height * 2;
     const int capw = (P.width + 2 * P.hpad) >> 3;
-    const int ncap = 2 * P.vpad * capw;
+    const int ncap = 2 * capw;
     uint8_t *base = job.base[OCG_FRAME_SELF] + P.plane_off;
     if (t < nside) {
-      const int y = t / (2 * hq), k = t - y * 2 * hq;
-      const bool right = k >= hq;
-      const uint8_t *srow = base + y * P.ystride;
+      const int y = t >> 1;
+      const bool right = (t & 1) != 0;
+      uint8_t *srow = base + (ptrdiff_t)y * P.ystride;
       const uint32_t v = 0x01010101u * (right ? srow[P.width - 1] : srow[0]);
-      uint8_t *d = base + y * P.ystride + (right ? P.width + 8 * (k - hq) : -P.hpad + 8 * k);
-      *(uint2 *)d = make_uint2(v, v);
+      uint2 *d = (uint2 *)(srow + (right ? P.width : -P.hpad));
+      for (int k = 0; k < (P.hpad >> 3); k++) d[k] = make_uint2(v, v);
       return;
     }
     t -= nside;
     if (t < ncap) {
-      const int r = t / capw, c = t - r * capw;
-      /* rows 0..vpad-1 below the picture (y=-1-r), the rest above it */
-      const int y = r < P.vpad ? -1 - r : P.height + (r - P.vpad);
-      const uint8_t *srow = base + (r < P.vpad ? 0 : P.height - 1) * P.ystride;
+      const bool above = t >= capw;
+      const int c = above ? t - capw : t;
+      const uint8_t *srow = base + (ptrdiff_t)(above ? P.height - 1 : 0) * P.ystride;
       const int x = -P.hpad + 8 * c;
       uint2 v;
       if (x < 0) { const uint32_t e = 0x01010101u * srow[0]; v = make_uint2(e, e); }
       else if (x >= P.width) { const uint32_t e = 0x01010101u * srow[P.width - 1]; v = make_uint2(e, e); }
       else v = *(const uint2 *)(srow + x);
-      *(uint2 *)(base + y * P.ystride + x) = v;
+      /* rows -1..-vpad below the picture, rows height..height+vpad-1 above it */
+      uint8_t *d = base + (ptrdiff_t)(above ? P.height : -1) * P.ystride + x;
+      const ptrdiff_t step = above ? P.ystride : -(ptrdiff_t)P.ystride;
+      for (int r = 0; r < P.vpad; r++) *(uint2 *)(d + r * step) = v;
       return;
     }
     t -= ncap;
@@ -1191,12 +1212,29 @@ ocg_dc_patch_kernel(ocg_frag_rec *__restrict__ recs, const int16_t *__restrict__
 
 } /* namespace */
 
+/* launch with the programmatic-stream-serialisation attribute (see pdl_wait above) */
+template <typename... KArgs, typename... Args>
+static void ocg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return;
   dim3 ga((unsigned)((g.nfrags + OCG_SIMPLE_THREADS - 1) / OCG_SIMPLE_THREADS), (unsigned)njobs);
   /* 4 rows per step at 12 CTAs per SM: 8 rows per step (64 registers, or 40-48 with spills) and 2 rows per step
      were measured 1-20 % slower */
-  ocg_recon_simple_kernel<4, 12><<<ga, OCG_SIMPLE_THREADS, 0, st>>>(g, jobs);
+  ocg_launch_pdl(ocg_recon_simple_kernel<4, 12>, ga, dim3(OCG_SIMPLE_THREADS), 0, st, g, jobs);
   /* pass B: one resident wave (6 CTAs of 256 threads per SM), CTA b striding over the list of job b % njobs;
      never more CTAs than there can be work for */
   static int sms = 0;
@@ -1209,7 +1247,7 @@ void ocg_launch_recon(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cud
   long nb = (long)sms * 6;
   if (nb < njobs) nb = njobs;
   if (nb > (long)tiles * njobs) nb = (long)tiles * njobs;
-  ocg_recon_xform_kernel<<<(unsigned)nb, OCG_RECON_THREADS, 0, st>>>(g, jobs, njobs);
+  ocg_launch_pdl(ocg_recon_xform_kernel, dim3((unsigned)nb), dim3(OCG_RECON_THREADS), 0, st, g, jobs, njobs);
   ocg_count_launch(2);
 }
 
@@ -1355,6 +1393,7 @@ __device__ __forceinline__ void copy_rect(const uint8_t *src, uint8_t *dst, cons
 
 __global__ void __launch_bounds__(256)
 ocg_copy_out_kernel(const OcgOutPlan plan, const OcgJobDev *__restrict__ job, uint32_t *counter, uint32_t *host_flag) {
+  pdl_wait(); /* the finished frame (and, in the token path, the job header staged at the head of the chain) */
   /* source and destination travel in the job header, so one graph serves every SELF buffer */
   const uint8_t *__restrict__ src = job->base[OCG_FRAME_SELF] - plan.base_off;
   uint8_t *__restrict__ host_dst = job->host_out;
@@ -1399,7 +1438,7 @@ void ocg_launch_copy_out(const ocg_geometry &g, int out_mode, const OcgJobDev *j
     }
   }
   const unsigned grid = out_mode == OCG_OUT_NONE ? 1u : 96u;
-  ocg_copy_out_kernel<<<grid, 256, 0, st>>>(plan, job, counter, host_flag);
+  ocg_launch_pdl(ocg_copy_out_kernel, dim3(grid), dim3(256), 0, st, plan, job, counter, host_flag);
   ocg_count_launch(1);
 }
 
@@ -1418,7 +1457,7 @@ void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njob
     int groups = 0;
     for (int pli = 0; pli < 3; pli++) groups += (g.p[pli].nvfrags + R) / R;
     dim3 grid((unsigned)((g.max_cells_x + TX - 1) / TX), (unsigned)groups, (unsigned)njobs);
-    ocg_lf2_kernel<TX, 1, R, 12><<<grid, dim3(TX, 1), 0, st>>>(g, jobs);
+    ocg_launch_pdl(ocg_lf2_kernel<TX, 1, R, 12>, grid, dim3(TX, 1), 0, st, g, jobs);
     ocg_count_launch(1);
     return;
   }
@@ -1437,9 +1476,8 @@ void ocg_launch_loop_filter(const OcgGeomDev &g, const OcgJobDev *jobs, int njob
 void ocg_launch_borders(const OcgGeomDev &g, const OcgJobDev *jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return;
   int items = 0;
-  for (int pli = 0; pli < 3; pli++)
-    items += g.p[pli].height * 2 * (g.p[pli].hpad >> 3) + 2 * g.p[pli].vpad * ((g.p[pli].width + 2 * g.p[pli].hpad) >> 3);
+  for (int pli = 0; pli < 3; pli++) items += g.p[pli].height * 2 + 2 * ((g.p[pli].width + 2 * g.p[pli].hpad) >> 3);
   dim3 grid((unsigned)((items + 255) / 256), (unsigned)njobs);
-  ocg_border_kernel<<<grid, 256, 0, st>>>(g, jobs);
+  ocg_launch_pdl(ocg_border_kernel, grid, dim3(256), 0, st, g, jobs);
   ocg_count_launch(1);
 }
