@@ -440,7 +440,15 @@ ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs, i
   /* entries per warp and round: 32, or -- when the list is short for the warps that serve it -- just enough
      (a multiple of 8) that one round covers it: a short list is latency, not throughput */
   const int E = min(32, max(8, (((nx + nranks * NW - 1) / (nranks * NW)) + 7) & ~7));
-  for (int e0 = (rank * NW + w) * E; e0 < nx; e0 += nranks * NW * E) {
+  /* rounds are claimed from a per-job counter, not dealt statically: with programmatic dependent launch the
+     CTAs of this grid become resident as the kernel before drains, unevenly over the SMs, and a static
+     deal made the slowest SM's share the kernel's time (dense frames: 292 -> 342 us) */
+  (void)rank;
+  for (;;) {
+    int e0 = 0;
+    if (lane == 0) e0 = atomicAdd(job.xcount + 1, E);
+    e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+    if (e0 >= nx) break;
     const int nvalid = min(E, nx - e0);
     int cls = WC_NONE;
     int4 it = make_int4(0, 0, 0, 0);
@@ -491,7 +499,7 @@ ocg_recon_xform_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs, i
    pass B); used when the border kernel, which normally does it, is not run. */
 __global__ void ocg_xlist_reset_kernel(const OcgJobDev *__restrict__ jobs, int njobs) {
   const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (j < njobs) jobs[j].xcount[0] = 0;
+  if (j < njobs) { jobs[j].xcount[0] = 0; jobs[j].xcount[1] = 0; }
 }
 
 /* Only the coded map (for running the loop filter stage on its own). */
@@ -1005,7 +1013,7 @@ ocg_border_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
   int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   pdl_wait(); /* the filtered picture; pass B is done with the work list */
   pdl_release();
-  if (t == 0) job.xcount[0] = 0; /* recon pass B is done with this frame's work list */
+  if (t == 0) { job.xcount[0] = 0; job.xcount[1] = 0; } /* recon pass B is done with this frame's work list and its claim counter */
 #pragma unroll
   for (int pli = 0; pli < 3; pli++) {
     const OcgPlaneDev &P = g.p[pli];
@@ -1225,7 +1233,7 @@ static void ocg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("OCG_NO_PDL") != nullptr ? 0 : 1; /* A/B switch */
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
