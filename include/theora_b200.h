@@ -299,6 +299,9 @@ typedef struct ocg_enc_frag {
 #define OCG_MET_ACTIVITY   6  /* oc_mb_activity per luma block (analyze.c:1167-1234): out = activity (flat clamp,
                                  edge test, act_th*(act/act_th)^0.7 via mathops.c:294-313), dc = pixel sum (the
                                  block's share of the function's `luma` return value); reads a 10x10 window */
+#define OCG_MET_SAD_THRESH 7  /* oc_enc_frag_sad_thresh_c / sad2_thresh_c (encfrag.c:55-84) with the early out: the
+                                 running sum after the first row that takes it above the threshold (aux, unsigned),
+                                 the whole sum if none does                                                      */
 
 /* All encoder entry points take DEVICE pointers for frames and lists (the
    caller owns residency) and run on `stream`. */

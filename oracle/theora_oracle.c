@@ -754,6 +754,10 @@ OCO_EXPORT void oco_enc_metrics_batch(int metric, const uint8_t *src_base, const
                                 (int64_t)(((uint64_t)(uint32_t)frags[i].aux << 32) | (uint32_t)frags[i].ref_off1));
         break;
       case OCG_MET_ACTIVITY: v = oco_block_activity(src, ystride, &dc); break;
+      case OCG_MET_SAD_THRESH:
+        v = r1 ? oco_frag_sad2_thresh(src, r0, r1, ystride, (unsigned)frags[i].aux)
+               : oco_frag_sad_thresh(src, r0, ystride, (unsigned)frags[i].aux);
+        break;
       default: break;
     }
     out_val[i] = v;

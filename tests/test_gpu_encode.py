@@ -104,6 +104,34 @@ def test_border_ssd_batch(mode):
     assert want_v[0] == 0
 
 
+@pytest.mark.parametrize("taps", [1, 2])
+def test_sad_thresh_batch(taps):
+    """OCG_MET_SAD_THRESH: oc_enc_frag_sad_thresh_c / sad2_thresh_c with their early out (threshold in aux)."""
+    rng = np.random.default_rng(900 + taps)
+    a, b, st = make_frames(rng, 0)
+    n = 6000
+    fr, base, ystride = make_frags(rng, st, n, taps)
+    th = rng.integers(0, 6000, size=n).astype(np.uint32)
+    th[:4] = [0, 1, 0xFFFFFFFF, 16320]
+    fr["aux"] = th.view(np.int32)
+    want_v, want_dc = np.zeros(n, np.uint32), np.zeros(n, np.int32)
+    S.oracle().oco_enc_metrics_batch(abi.OCG_MET_SAD_THRESH, a.ctypes.data + base, b.ctypes.data + base, ystride, fr.ctypes.data, n,
+                                     S.ptr(want_v, S.u32p), S.ptr(want_dc, S.i32p))
+    full = np.zeros(n, np.uint32)
+    fr0 = fr.copy()
+    S.oracle().oco_enc_metrics_batch(abi.OCG_MET_SAD, a.ctypes.data + base, b.ctypes.data + base, ystride, fr0.ctypes.data, n,
+                                     S.ptr(full, S.u32p), S.ptr(want_dc, S.i32p))
+    assert np.any(want_v < full), "no block took the early out"
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dfr = torch.from_numpy(fr.view(np.int32).reshape(n, 4)).cuda()
+    ov = torch.zeros(n, dtype=torch.int32, device="cuda")
+    abi.check(abi.lib().ocg_enc_metrics_batch(abi.OCG_MET_SAD_THRESH, da.data_ptr() + base, db.data_ptr() + base, ystride,
+                                              dfr.data_ptr(), n, ov.data_ptr(), None,
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(ov.cpu().numpy().view(np.uint32), want_v)
+
+
 @pytest.mark.parametrize("taps", [0, 1, 2])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_fdct_quant_batch(taps, mode):

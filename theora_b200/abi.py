@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libtheora_b200.so")
 OCG_FRAME_GOLD, OCG_FRAME_PREV, OCG_FRAME_SELF = 0, 1, 2
 OCG_CLS_DC, OCG_CLS_3, OCG_CLS_10, OCG_CLS_FULL, OCG_NCLS = 0, 1, 2, 3, 4
 OCG_MET_SAD, OCG_MET_SATD, OCG_MET_INTRA_SATD, OCG_MET_SSD, OCG_MET_INTRA_SAD = 0, 1, 2, 3, 4
-OCG_MET_BORDER_SSD, OCG_MET_ACTIVITY = 5, 6
+OCG_MET_BORDER_SSD, OCG_MET_ACTIVITY, OCG_MET_SAD_THRESH = 5, 6, 7
 INT32_MIN = -2 ** 31
 
 

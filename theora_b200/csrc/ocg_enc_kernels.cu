@@ -216,6 +216,17 @@ ocg_enc_metrics_kernel(const uint8_t *__restrict__ src_base, const uint8_t *__re
     load_pred8(ref_base, f, ystride, p);
 #pragma unroll
     for (int i = 0; i < 8; i++) val += __vsadu4(s.r[i].x, p.r[i].x) + __vsadu4(s.r[i].y, p.r[i].y);
+  } else if (METRIC == OCG_MET_SAD_THRESH) {
+    /* encfrag.c:55-84: rows are added in order and the sum is returned as soon as it exceeds the threshold */
+    const uint32_t thresh = (uint32_t)f.aux;
+    load_pred8(ref_base, f, ystride, p);
+    bool out = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t next = val + __vsadu4(s.r[i].x, p.r[i].x) + __vsadu4(s.r[i].y, p.r[i].y);
+      if (!out) val = next;
+      out = out || val > thresh;
+    }
   } else if (METRIC == OCG_MET_SSD) {
     /* sum (a-b)^2 = sum a^2 + sum b^2 - 2 sum ab, four pixels per IDP.4A;
        oc_enc_frag_ssd has no two-tap form (encfrag.c:338) */
@@ -1892,7 +1903,7 @@ OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uin
                                   const ocg_enc_frag *frags, int n, uint32_t *out_val, int32_t *out_dc,
                                   void *stream) {
   if (src_base == nullptr || frags == nullptr || out_val == nullptr) return OCG_EFAULT;
-  if (metric < OCG_MET_SAD || metric > OCG_MET_ACTIVITY || n < 0) return OCG_EINVAL;
+  if (metric < OCG_MET_SAD || metric > OCG_MET_SAD_THRESH || n < 0) return OCG_EINVAL;
   if (n == 0) return OCG_OK;
   const unsigned grid = (unsigned)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1903,6 +1914,7 @@ OCG_API int ocg_enc_metrics_batch(int metric, const uint8_t *src_base, const uin
     case OCG_MET_INTRA_SATD: ocg_enc_metrics_kernel<OCG_MET_INTRA_SATD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_SSD: ocg_enc_metrics_kernel<OCG_MET_SSD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     case OCG_MET_BORDER_SSD: ocg_enc_metrics_kernel<OCG_MET_BORDER_SSD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
+    case OCG_MET_SAD_THRESH: ocg_enc_metrics_kernel<OCG_MET_SAD_THRESH><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
     default: ocg_enc_metrics_kernel<OCG_MET_INTRA_SAD><<<grid, 128, 0, st>>>(src_base, ref_base, ystride, frags, n, out_val, out_dc); break;
   }
   ocg_count_launch(1);
