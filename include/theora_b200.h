@@ -261,7 +261,8 @@ OCG_API long ocg_launch_count(void);   /* kernels launched by this library so fa
 OCG_API void ocg_set_lf_tma(int on);
 /* How ocg_dec_flush / ocg_dec_flush_tokens hand the picture (OCG_OUT_PICTURE) to the host: 0 = a kernel
    writes it through mapped host memory (the whole flush stays one graph of kernels), 1 = three 2-D copies
-   by the copy engines behind the graph, then the completion flag. */
+   by the copy engines behind the graph, then the completion flag; n > 1 = one context in n does (the others
+   keep the kernel).  Measured: no variant beats the kernel. */
 OCG_API void ocg_set_out_dma(int on);
 /* Wait policy of ocg_dec_wait (and of ocg_ctx_sync: 0 = cudaStreamSynchronize, non-zero = a blocking event):
    0 (default) spin on the completion flag; 1 sched_yield between looks; 2 SLEEP: one poller thread per

@@ -86,6 +86,7 @@ struct EncPre {
 };
 
 struct ocg_ctx {
+  int serial = 0; /* creation order in the process */
   EncPre *enc = nullptr;
   ocg_geometry geom;
   OcgGeomDev gdev;
@@ -321,7 +322,7 @@ OCG_API int ocg_device_count(void) {
 
 OCG_API void ocg_set_stage_mask(int mask) { g_stage_mask.store(mask & 7); }
 
-OCG_API void ocg_set_out_dma(int on) { g_out_dma.store(on ? 1 : 0); }
+OCG_API void ocg_set_out_dma(int on) { g_out_dma.store(on < 0 ? 0 : on); }
 extern int g_ocg_lf_legacy;
 OCG_API void ocg_set_lf_tma(int on) { g_use_tma.store(on == 1 ? 1 : 0); g_ocg_lf_legacy = on == 2; }
 
@@ -461,6 +462,10 @@ OCG_API int ocg_ctx_create(ocg_ctx **out, const ocg_geometry *g, int device) {
   if (c == nullptr) return fail(OCG_ENOMEM, "out of memory");
   c->geom = *g;
   c->device = device;
+  {
+    static std::atomic<int> next_serial{0};
+    c->serial = next_serial.fetch_add(1);
+  }
   geom_to_dev(*g, c->gdev);
   const size_t nf = (size_t)g->nfrags;
   const size_t pool = (size_t)g->ref_frame_sz * g->nrefs + 256;
@@ -902,7 +907,11 @@ static int flush_core(ocg_ctx *c, int si, uint8_t *host_out, int out_mode, int d
   Slot &s = c->slots[si];
   cudaStream_t st = c->stream;
   int r;
-  if (out_mode == OCG_OUT_PICTURE && g_out_dma.load(std::memory_order_relaxed)) out_mode = kOutDeferred;
+  {
+    /* 1: every context; n > 1: one context in n (by creation order) -- the rest keep the copy-out kernel */
+    const int dma = g_out_dma.load(std::memory_order_relaxed);
+    if (out_mode == OCG_OUT_PICTURE && dma > 0 && (dma == 1 || c->serial % dma == 0)) out_mode = kOutDeferred;
+  }
   const bool tma = c->d_tmaps != nullptr && g_use_tma.load();
   /* the destination's device address (one driver call per distinct buffer, then remembered) */
   uint8_t *d_out_mapped = nullptr;
