@@ -120,6 +120,13 @@ OCG_API void ocg_backend_set_enc_mode(int mode) { g_enc_mode = mode; }
 OCG_API void ocg_backend_set_enc_spy(ocg_enc_spy_fn fn, void *user) { g_enc_spy = fn; g_enc_spy_user = user; }
 static double g_dbg_t[8];
 static long g_dbg_n;
+/* diagnostic switches, read once: OCG_ENC_TIMING (pass timing + miss histogram at exit), OCG_ENC_NO_FQ (no
+   speculative transform tables) */
+static int enc_dbg_flag(int which) {
+  static int flags = -1;
+  if (flags < 0) flags = (getenv("OCG_ENC_TIMING") != NULL ? 1 : 0) | (getenv("OCG_ENC_NO_FQ") != NULL ? 2 : 0);
+  return (flags >> which) & 1;
+}
 static long g_dbg_miss[10]; /* fq misses by the candidate that would have served them; [8] none; [9] sub_128 in inter frames */
 
 OCG_API void ocg_backend_get_enc_stats(ocg_enc_backend_stats *out, int reset) {
@@ -344,11 +351,11 @@ static int enc_me_prepass(ocg_enc_backend *b) {
 }
 
 __attribute__((destructor)) static void enc_dbg_print(void) {
-  if (getenv("OCG_ENC_TIMING") != NULL && g_dbg_n > 0)
+  if (enc_dbg_flag(0) && g_dbg_n > 0)
     fprintf(stderr, "[enc timing, ms per pass over %ld passes] wait %.3f staging %.3f me_total %.3f (prep %.3f) rest %.3f\n", g_dbg_n,
             1e3 * g_dbg_t[0] / g_dbg_n, 1e3 * g_dbg_t[1] / g_dbg_n, 1e3 * g_dbg_t[2] / g_dbg_n, 1e3 * g_dbg_t[4] / g_dbg_n,
             1e3 * g_dbg_t[3] / g_dbg_n);
-  if (getenv("OCG_ENC_TIMING") != NULL)
+  if (enc_dbg_flag(0))
     fprintf(stderr, "[enc fq misses by candidate] %ld %ld %ld %ld %ld %ld %ld %ld none %ld; sub_128 in inter frames %ld\n", g_dbg_miss[0],
             g_dbg_miss[1], g_dbg_miss[2], g_dbg_miss[3], g_dbg_miss[4], g_dbg_miss[5], g_dbg_miss[6], g_dbg_miss[7], g_dbg_miss[8],
             g_dbg_miss[9]);
@@ -398,7 +405,7 @@ static void enc_begin_pass(ocg_enc_backend *b, int nqis) {
      the C kernels */
   b->fq_cur = -1;
   b->c2_dst = NULL;
-  b->fq_ok = b->inter_frame && b->itab_valid && b->itab.fq_nqis > 0 && b->fq_nq == nqis && getenv("OCG_ENC_NO_FQ") == NULL;
+  b->fq_ok = b->inter_frame && b->itab_valid && b->itab.fq_nqis > 0 && b->fq_nq == nqis && !enc_dbg_flag(1);
   if (b->fq_ok) {
     int qii;
     for (qii = 0; qii < nqis; qii++) if (b->fq_qis[qii] != st->qis[qii]) b->fq_ok = 0;
@@ -662,7 +669,7 @@ static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, cons
         }
       }
       b->n_fq_miss++;
-      if (fragi >= 0 && getenv("OCG_ENC_TIMING") != NULL) {
+      if (fragi >= 0 && enc_dbg_flag(0)) {
         ptrdiff_t r1, r2 = INT32_MIN;
         int k, hit = 8;
         if (_ref == b->c2_dst) { r1 = b->c2_r1 - b->pool0; r2 = b->c2_r2 - b->pool0; }

@@ -1233,7 +1233,8 @@ static void ocg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = getenv("OCG_NO_PDL") != nullptr ? 0 : 1; /* A/B switch */
+  static const int no_pdl = getenv("OCG_NO_PDL") != nullptr; /* A/B switch, read once */
+  cfg.numAttrs = no_pdl ? 0 : 1;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
