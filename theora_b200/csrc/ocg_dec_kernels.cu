@@ -699,7 +699,7 @@ ocg_lf_kernel(const OcgGeomDev g, const OcgJobDev *__restrict__ jobs) {
    ALU pipe 67 % -> 37 %; 94 -> 78 us per 64-stream launch.  What bounds it now is the movement itself: a
    probe that only loads and stores the cells takes 86 us with these 32-bit accesses (70 us with 64-bit ones,
    which a cell -- 4 bytes off the 8-byte grid -- cannot use directly).  Tried and measured slower: exchanging
-   halves between lanes by shuffle to move aligned 64-bit words (97-108 us), one cell of prefetch (85 us at
+   halves between lanes by shuffle to move aligned 64-bit words (97-108 us; stores only: 87 us), one cell of prefetch (85 us at
    62 registers), fetching each cell row's 8 pixel rows as one linear cp.async.bulk block into a double-
    buffered shared-memory tile (88 us); CTA shapes from 32x4 to 256x1 cells and R = 1..8 all land within
    78-87 us. */
