@@ -297,3 +297,24 @@ REFH_API void refh_me_frame(void *h, const unsigned char *const frames[5], int f
     }
   }
 }
+
+/* The post-processing inputs the reference decoder holds after a th_decode_packetin (decode.c:1204-1243,
+   397-409): per fragment the tracked DC quantiser index and state.qis[frag.qii], the two tables, the
+   variances its own filters accumulated for the frame, and the level the frame was processed at.  Returns
+   the fragment count, or -1 while the decoder is not tracking (pp level 0 / no key frame seen yet). */
+#include "decint.h"
+REFH_API long refh_dec_pp_state(th_dec_ctx *dec_, unsigned char *dc_qis, unsigned char *qis, int *dc_scale, int *sharp_mod,
+                                int *variances, int *level) {
+  oc_dec_ctx *dec = (oc_dec_ctx *)dec_;
+  ptrdiff_t i, n;
+  if (dec == NULL || dec->dc_qis == NULL) return -1;
+  n = dec->state.nfrags;
+  for (i = 0; i < n; i++) {
+    dc_qis[i] = dec->dc_qis[i];
+    qis[i] = (unsigned char)dec->state.qis[dec->state.frags[i].qii];
+    if (variances != NULL) variances[i] = dec->variances != NULL ? dec->variances[i] : 0;
+  }
+  for (i = 0; i < 64; i++) { dc_scale[i] = dec->pp_dc_scale[i]; sharp_mod[i] = dec->pp_sharp_mod[i]; }
+  if (level != NULL) *level = dec->pipe.pp_level;
+  return (long)n;
+}

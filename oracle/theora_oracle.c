@@ -1183,3 +1183,128 @@ OCO_EXPORT void oco_me_frame(const uint8_t *src, const uint8_t *ref_full_gold, c
     }
   }
 }
+
+/* ==========================================================================
+ * Out-of-loop post-processing (decode.c:1609-1957), restated for a whole plane.
+ * Planes are given in the decoder's internal orientation: row 0 is the row the
+ * reference processes first (the displayed image's bottom row), `stride` bytes
+ * from one row to the next.  W and H are multiples of 8.  dc_qis / qis are per
+ * block of the plane (nh x nv, row-major in the same orientation).
+ * ========================================================================== */
+static int oco_pp_edge_sums(const int r[10], int *sum0, int *sum1) {
+  int k, a = 0, b = 0;
+  for (k = 0; k < 4; k++) { a += abs(r[k + 1] - r[k]); b += abs(r[k + 5] - r[k + 6]); }
+  *sum0 = a;
+  *sum1 = b;
+  return 0;
+}
+
+static void oco_pp_edge_filter(const int r[10], int out[8]) {
+  int k;
+  out[0] = (r[0] * 3 + r[1] * 2 + r[2] + r[3] + r[4] + 4) >> 3;
+  out[1] = (r[0] * 2 + r[1] + r[2] * 2 + r[3] + r[4] + r[5] + 4) >> 3;
+  for (k = 0; k < 4; k++) out[2 + k] = (r[k] + r[k + 1] + r[k + 2] + r[k + 3] * 2 + r[k + 4] + r[k + 5] + r[k + 6] + 4) >> 3;
+  out[6] = (r[4] + r[5] + r[6] + r[7] * 2 + r[8] + r[9] * 2 + 4) >> 3;
+  out[7] = (r[5] + r[6] + r[7] + r[8] * 2 + r[9] * 3 + 4) >> 3;
+}
+
+/* oc_dec_deblock_frag_rows over the whole plane: dst <- filtered src; variances[nh*nv] accumulated from 0 */
+OCO_EXPORT void oco_pp_deblock_plane(uint8_t *dst, int dstride, const uint8_t *src, int sstride, int W, int H,
+                                     const uint8_t *dc_qis, const int *dc_scale, int32_t *variances) {
+  const int nh = W >> 3, nv = H >> 3;
+  int x, y, e, bx, by, k;
+  memset(variances, 0, (size_t)nh * nv * sizeof(*variances));
+  /* rows no horizontal edge reaches */
+  for (y = 0; y < 4; y++) memcpy(dst + (size_t)y * dstride, src + (size_t)y * sstride, (size_t)W);
+  for (y = H - 4; y < H; y++) memcpy(dst + (size_t)y * dstride, src + (size_t)y * sstride, (size_t)W);
+  /* horizontal edges between block rows e-1 and e: 10 source rows in, 8 rows out (decode.c:1610-1660) */
+  for (e = 1; e < nv; e++) {
+    for (x = 0; x < W; x++) {
+      const int qstep = dc_scale[dc_qis[(e - 1) * nh + (x >> 3)]], flimit = (qstep * 3) >> 2;
+      int r[10], o[8], s0, s1;
+      for (k = 0; k < 10; k++) r[k] = src[(size_t)(8 * e - 5 + k) * sstride + x];
+      oco_pp_edge_sums(r, &s0, &s1);
+      variances[(e - 1) * nh + (x >> 3)] += s0 < 255 ? s0 : 255;
+      variances[e * nh + (x >> 3)] += s1 < 255 ? s1 : 255;
+      if (s0 < flimit && s1 < flimit && r[5] - r[4] < qstep && r[4] - r[5] < qstep) oco_pp_edge_filter(r, o);
+      else for (k = 0; k < 8; k++) o[k] = r[k + 1];
+      for (k = 0; k < 8; k++) dst[(size_t)(8 * e - 4 + k) * dstride + x] = (uint8_t)o[k];
+    }
+  }
+  /* vertical edges, in place, left to right along every row (decode.c:1663-1699, 1750-1790) */
+  for (by = 0; by < nv; by++) {
+    for (bx = 1; bx < nh; bx++) {
+      const int qstep = dc_scale[dc_qis[by * nh + bx]], flimit = (qstep * 3) >> 2;
+      for (y = 8 * by; y < 8 * by + 8; y++) {
+        uint8_t *p = dst + (size_t)y * dstride + 8 * bx - 5;
+        int r[10], o[8], s0, s1;
+        for (k = 0; k < 10; k++) r[k] = p[k];
+        oco_pp_edge_sums(r, &s0, &s1);
+        variances[by * nh + bx - 1] += s0 < 255 ? s0 : 255;
+        variances[by * nh + bx] += s1 < 255 ? s1 : 255;
+        if (s0 < flimit && s1 < flimit && r[5] - r[4] < qstep && r[4] - r[5] < qstep) {
+          oco_pp_edge_filter(r, o);
+          for (k = 0; k < 8; k++) p[1 + k] = (uint8_t)o[k];
+        }
+      }
+    }
+  }
+}
+
+/* oc_dering_block (decode.c:1788-1886) on the block at (x0,y0) of a W x H plane, with neighbour pixels
+   clamped into the plane */
+static void oco_pp_dering_block(uint8_t *img, int stride, int W, int H, int x0, int y0, int dc_scale, int sharp_mod,
+                                int strong) {
+  const int mod_hi = 3 * dc_scale < (strong ? 32 : 24) ? 3 * dc_scale : (strong ? 32 : 24);
+  const int shift = strong ? 0 : 1;
+  int vmod[9][8], hmod[9][8];
+  int bx, by;
+#define OCO_PIX(xx, yy) ((int)img[(size_t)((yy) < 0 ? 0 : ((yy) >= H ? H - 1 : (yy))) * stride + ((xx) < 0 ? 0 : ((xx) >= W ? W - 1 : (xx)))])
+#define OCO_MOD(d) (32 + dc_scale - (abs(d) << shift))
+  for (by = 0; by < 9; by++)
+    for (bx = 0; bx < 8; bx++) {
+      const int m = OCO_MOD(OCO_PIX(x0 + bx, y0 + by) - OCO_PIX(x0 + bx, y0 + by - 1));
+      vmod[by][bx] = m < -64 ? sharp_mod : (m < 0 ? 0 : (m > mod_hi ? mod_hi : m));
+    }
+  for (bx = 0; bx < 9; bx++)
+    for (by = 0; by < 8; by++) {
+      const int m = OCO_MOD(OCO_PIX(x0 + bx, y0 + by) - OCO_PIX(x0 + bx - 1, y0 + by));
+      hmod[bx][by] = m < -64 ? sharp_mod : (m < 0 ? 0 : (m > mod_hi ? mod_hi : m));
+    }
+  /* at the frame border the reference compares a row/column with itself (the pointer does not advance),
+     which the clamped coordinates above reproduce except for row/column 8 against 7: both clamp to the
+     same pixel there too */
+  for (by = 0; by < 8; by++)
+    for (bx = 0; bx < 8; bx++) {
+      int a = 128, b = 64, w, v;
+      w = hmod[bx][by]; a -= w; b += w * OCO_PIX(x0 + bx - 1, y0 + by);
+      w = vmod[by][bx]; a -= w; b += w * OCO_PIX(x0 + bx, y0 + by - 1);
+      w = vmod[by + 1][bx]; a -= w; b += w * OCO_PIX(x0 + bx, y0 + by + 1);
+      w = hmod[bx + 1][by]; a -= w; b += w * OCO_PIX(x0 + bx + 1, y0 + by);
+      v = (a * OCO_PIX(x0 + bx, y0 + by) + b) >> 7;
+      img[(size_t)(y0 + by) * stride + x0 + bx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+#undef OCO_PIX
+#undef OCO_MOD
+}
+
+/* oc_dec_dering_frag_rows over the whole plane (decode.c:1892-1957) */
+OCO_EXPORT void oco_pp_dering_plane(uint8_t *img, int stride, int W, int H, int pli, int strong_level, const uint8_t *qis,
+                                    const int *dc_scale, const int *sharp_mod, const int32_t *variances) {
+  const int nh = W >> 3, nv = H >> 3;
+  const int t1 = 384, t2 = 4 * 384, t3 = 5 * 384, t4 = 10 * 384;
+  const int sthresh = pli ? t4 : t3;
+  int bx, by;
+  for (by = 0; by < nv; by++)
+    for (bx = 0; bx < nh; bx++) {
+      const int i = by * nh + bx, var = variances[i], qi = qis[i];
+      if (strong_level && var > sthresh) {
+        int passes = 1, k;
+        if (pli || (bx > 0 && variances[i - 1] > t4) || (bx + 1 < nh && variances[i + 1] > t4) ||
+            (by > 0 && variances[i - nh] > t4) || (by + 1 < nv && variances[i + nh] > t4))
+          passes = 3;
+        for (k = 0; k < passes; k++) oco_pp_dering_block(img, stride, W, H, 8 * bx, 8 * by, dc_scale[qi], sharp_mod[qi], 1);
+      } else if (var > t2) oco_pp_dering_block(img, stride, W, H, 8 * bx, 8 * by, dc_scale[qi], sharp_mod[qi], 1);
+      else if (var > t1) oco_pp_dering_block(img, stride, W, H, 8 * bx, 8 * by, dc_scale[qi], sharp_mod[qi], 0);
+    }
+}

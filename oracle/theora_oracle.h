@@ -87,6 +87,13 @@ void oco_me_frame(const uint8_t *src, const uint8_t *ref_full_gold, const uint8_
                   const uint8_t *ref_satd_gold, const uint8_t *ref_satd_prev, int ystride,
                   const ocg_me_topo *topo, ocg_me_mb *mb, int nmbs, int flags, const uint8_t *gold_refine);
 
+/* ---- out-of-loop post-processing (decode.c:1609-1957), whole plane, internal orientation (row 0 = the row
+   the reference processes first) ---- */
+void oco_pp_deblock_plane(uint8_t *dst, int dstride, const uint8_t *src, int sstride, int W, int H,
+                          const uint8_t *dc_qis, const int *dc_scale, int32_t *variances);   /* decode.c:1700 */
+void oco_pp_dering_plane(uint8_t *img, int stride, int W, int H, int pli, int strong_level, const uint8_t *qis,
+                         const int *dc_scale, const int *sharp_mod, const int32_t *variances); /* decode.c:1892 */
+
 #ifdef __cplusplus
 }
 #endif

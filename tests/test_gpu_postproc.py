@@ -92,3 +92,85 @@ def test_level_changes_between_frames():
     got = run(G)
     for i in range(len(levels)):
         assert np.array_equal(got[i], want[i]), "frame %d (level %d) differs" % (i, levels[i])
+
+
+def _smoothish_frame(g, rng):
+    """A padded buffer whose picture has regions of every variance class: smooth ramps, mild and heavy noise."""
+    import workgen as W
+    buf = W.random_frames(g, rng)[:g.ref_frame_sz].copy()
+    for pli in range(3):
+        p = g.planes[pli]
+        w, h, stride = p.width, p.height, -p.ystride
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = (xx * 3 + yy * 2) % 256
+        amp = np.choose(((xx // 32) + (yy // 24)) % 4, [0, 3, 12, 60])
+        img = np.clip(base + rng.integers(-1, 2, size=(h, w)) * amp + ((xx // 8 + yy // 8) % 2) * (amp // 2), 0, 255).astype(np.uint8)
+        top = g.base_off + p.plane_off + (h - 1) * p.ystride  # top-left pixel of the picture
+        for y in range(h):  # memory row y (top-down) = internal row h-1-y
+            buf[top + y * stride: top + y * stride + w] = img[h - 1 - y]
+    return buf
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("dims", [(176, 144, 0), (320, 64, 3), (64, 256, 2), (1920, 1088, 0)])
+def test_device_filters_match_the_oracle_on_synthetic_frames(dims, level):
+    """ocg_pp_run through the C ABI against the oracle's restatement (itself pinned to the reference by
+    tests/test_oracle_postproc.py): random quantiser indices and tables, frames with every variance class."""
+    import theora_b200 as T
+    from theora_b200 import abi
+    rng = np.random.default_rng(1000 * level + dims[0])
+    g = S.make_geometry(dims[0], dims[1], dims[2], 3)
+    buf = _smoothish_frame(g, rng)
+    nf = g.nfrags
+    dc_qis = rng.integers(0, 64, nf).astype(np.uint8)
+    qis = rng.integers(0, 64, nf).astype(np.uint8)
+    dc_scale = rng.integers(1, 120, 64).astype(np.int32)
+    sharp_mod = (-rng.integers(0, 64, 64)).astype(np.int32)
+    O = S.oracle()
+    O.oco_pp_deblock_plane.restype = None
+    O.oco_pp_dering_plane.restype = None
+    O.oco_pp_deblock_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.oco_pp_dering_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    want, want_var = [], []
+    for pli in range(3):
+        p = g.planes[pli]
+        w, h, stride = p.width, p.height, -p.ystride
+        top = g.base_off + p.plane_off + (h - 1) * p.ystride
+        img = np.stack([buf[top + y * stride: top + y * stride + w] for y in range(h)])  # top-down
+        off = 3 * (pli != 0)
+        if level >= 2 + off:
+            s = np.ascontiguousarray(img[::-1])
+            d = np.empty_like(s)
+            var = np.zeros(p.nfrags, np.int32)
+            dq = np.ascontiguousarray(dc_qis[p.froffset:p.froffset + p.nfrags])
+            qq = np.ascontiguousarray(qis[p.froffset:p.froffset + p.nfrags])
+            O.oco_pp_deblock_plane(d.ctypes.data, w, s.ctypes.data, w, w, h, dq.ctypes.data, dc_scale.ctypes.data, var.ctypes.data)
+            if level >= 3 + off:
+                O.oco_pp_dering_plane(d.ctypes.data, w, w, h, pli, int(level >= 4 + off), qq.ctypes.data, dc_scale.ctypes.data,
+                                      sharp_mod.ctypes.data, var.ctypes.data)
+            want.append(np.ascontiguousarray(d[::-1]).ravel())
+            want_var.append(var)
+    L = abi.lib()
+    ctx = T.Context(g, 0)
+    ctx.upload_frame(0, buf)
+    pp = C.c_void_p()
+    abi.check(L.ocg_pp_create(C.byref(pp), ctx.h))
+    try:
+        abi.check(L.ocg_pp_run(pp, 0, level, dc_scale.ctypes.data, sharp_mod.ctypes.data, dc_qis.ctypes.data, qis.ctypes.data))
+        total = sum(g.planes[i].width * g.planes[i].height for i in range(3))
+        out = np.zeros(total, np.uint8)
+        abi.check(L.ocg_pp_download(pp, out.ctypes.data))
+        var = np.zeros(nf, np.int32)
+        abi.check(L.ocg_pp_download_variances(pp, var.ctypes.data))
+    finally:
+        L.ocg_pp_destroy(pp)
+        ctx.close()
+    at = 0
+    for k, wnt in enumerate(want):
+        got = out[at:at + wnt.size]
+        assert np.array_equal(got, wnt), "plane %d differs at %s" % (k, np.flatnonzero(got != wnt)[:5])
+        p = g.planes[k]
+        assert np.array_equal(var[p.froffset:p.froffset + p.nfrags], want_var[k]), "variances of plane %d differ" % k
+        at += wnt.size
+    classes = np.concatenate(want_var)
+    assert (classes > 3840).any() and (classes <= 384).any(), "the frame does not exercise the variance classes"
