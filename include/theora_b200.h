@@ -489,9 +489,9 @@ typedef struct ocg_enc_inter_tables {
   const uint32_t *border_ssd;   /* [nborder] masked SSD vs PREV, indexed by ocg_enc_inter_border_slot */
   int32_t         ncand;        /* OCG_ENC_NCAND, or 0 when the candidates were not requested   */
   int32_t         nluma, nfrags;
-  const ocg_enc_frag *cand;     /* candidate k of fragment f at ocg_enc_cand_index(t,k,f): ref_off0 / ref_off1 (INT32_MIN: one tap) */
-  const uint32_t *cand_satd;    /* same indexing                                                */
-  const int32_t  *cand_dc;
+  const struct ocg_enc_cand_rec *cand; /* candidate k of fragment f at cand[f * ncand + k]: a fragment's candidates
+                                   sit together (two cache lines), because the analysis loop asks for several
+                                   predictors of the same fragment in a row                              */
   long            d2h_bytes;
   /* speculative frag_sub + fDCT + quantiser (oc_enc_block_transform_quantize, analyze.c:704-782) against the
      predictors of candidates OCG_ENC_FQ_CAND0/1/2, for every fragment and each of the frame's fq_nqis inter
@@ -502,6 +502,11 @@ typedef struct ocg_enc_inter_tables {
   const struct ocg_enc_fq_desc *fq_desc;
   const int16_t  *fq_pool;
 } ocg_enc_inter_tables;
+typedef struct ocg_enc_cand_rec {
+  int32_t  ref_off0, ref_off1;  /* predictor tap offsets relative to the frame pool (INT32_MIN: one tap) */
+  uint32_t satd;                /* oc_enc_frag_satd / satd2 against that predictor                      */
+  int32_t  dc;
+} ocg_enc_cand_rec;
 typedef struct ocg_enc_fq_desc {
   uint32_t off;
   uint8_t  count;      /* leading zig-zag coefficients stored (1..64) */
@@ -511,10 +516,6 @@ typedef struct ocg_enc_fq_desc {
 #define OCG_ENC_FQ_CAND0 0   /* PREV (0,0)              */
 #define OCG_ENC_FQ_CAND1 3   /* PREV, refined vector    */
 #define OCG_ENC_FQ_CAND2 2   /* PREV, unrefined vector  */
-static inline size_t ocg_enc_cand_index(const ocg_enc_inter_tables *t, int k, int fragi) {
-  return fragi < t->nluma ? (size_t)k * (size_t)t->nluma + (size_t)fragi
-                          : (size_t)t->ncand * (size_t)t->nluma + (size_t)k * (size_t)(t->nfrags - t->nluma) + (size_t)(fragi - t->nluma);
-}
 /* mbfrags: [ocg_me_nmbs][12] = state.mb_maps[mbi][pli][bi] (-1: absent); border_fragi/border_mask: the
    fragments with a border mask (state.borders[frags[i].borderi].mask). */
 OCG_API int  ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, const int32_t *mbfrags,

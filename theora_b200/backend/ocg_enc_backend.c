@@ -545,13 +545,13 @@ static unsigned ocge_frag_satd(int *_dc, const unsigned char *_src, const unsign
     ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
     const ptrdiff_t roff = _ref - b->pool0;
     if (fragi >= 0) {
+      const ocg_enc_cand_rec *c = b->itab.cand + (size_t)fragi * (size_t)b->itab.ncand;
       int k;
       for (k = 0; k < b->itab.ncand; k++) {
-        const size_t at = ocg_enc_cand_index(&b->itab, k, (int)fragi);
-        if (b->itab.cand[at].ref_off0 == roff && b->itab.cand[at].ref_off1 == INT32_MIN) {
+        if (c[k].ref_off0 == roff && c[k].ref_off1 == INT32_MIN) {
           b->n_satd_hit++;
-          *_dc = b->itab.cand_dc[at];
-          return b->itab.cand_satd[at];
+          *_dc = c[k].dc;
+          return c[k].satd;
         }
       }
     }
@@ -567,15 +567,14 @@ static unsigned ocge_frag_satd2(int *_dc, const unsigned char *_src, const unsig
     ptrdiff_t fragi = enc_fragi_of(b, _src, OC_FRAME_IO);
     const ptrdiff_t r1 = _ref1 - b->pool0, r2 = _ref2 - b->pool0;
     if (fragi >= 0) {
+      const ocg_enc_cand_rec *c = b->itab.cand + (size_t)fragi * (size_t)b->itab.ncand;
       int k;
-      for (k = 0; k < b->itab.ncand; k++) {
-        const size_t at = ocg_enc_cand_index(&b->itab, k, (int)fragi);
-        const ocg_enc_frag *c = b->itab.cand + at;
+      for (k = 0; k < b->itab.ncand; k++, c++) {
         /* the two-tap average is symmetric in its taps */
         if ((c->ref_off0 == r1 && c->ref_off1 == r2) || (c->ref_off0 == r2 && c->ref_off1 == r1)) {
           b->n_satd_hit++;
-          *_dc = b->itab.cand_dc[at];
-          return b->itab.cand_satd[at];
+          *_dc = c->dc;
+          return c->satd;
         }
       }
     }
@@ -655,7 +654,7 @@ static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, cons
         if (_ref == b->c2_dst) { r1 = b->c2_r1 - b->pool0; r2 = b->c2_r2 - b->pool0; }
         else r1 = _ref - b->pool0;
         for (sel = 0; sel < OCG_ENC_FQ_NSEL; sel++) {
-          const ocg_enc_frag *c = b->itab.cand + ocg_enc_cand_index(&b->itab, SEL_CAND[sel], (int)fragi);
+          const ocg_enc_cand_rec *c = b->itab.cand + (size_t)fragi * (size_t)b->itab.ncand + SEL_CAND[sel];
           if ((c->ref_off0 == r1 && c->ref_off1 == r2) || (r2 != INT32_MIN && c->ref_off0 == r2 && c->ref_off1 == r1)) {
             const long at = (long)sel * b->geom.nfrags + (long)fragi;
             if (b->itab.fq_desc[at].off != 0xFFFFFFFFu) {
@@ -675,7 +674,7 @@ static void ocge_frag_sub(ogg_int16_t _diff[64], const unsigned char *_src, cons
         if (_ref == b->c2_dst) { r1 = b->c2_r1 - b->pool0; r2 = b->c2_r2 - b->pool0; }
         else r1 = _ref - b->pool0;
         for (k = 0; k < 8 && hit == 8; k++) {
-          const ocg_enc_frag *c = b->itab.cand + ocg_enc_cand_index(&b->itab, k, (int)fragi);
+          const ocg_enc_cand_rec *c = b->itab.cand + (size_t)fragi * (size_t)b->itab.ncand + k;
           if ((c->ref_off0 == r1 && c->ref_off1 == r2) || (r2 != INT32_MIN && c->ref_off0 == r2 && c->ref_off1 == r1)) hit = k;
         }
         __sync_fetch_and_add(&g_dbg_miss[hit], 1);

@@ -414,6 +414,24 @@ ocg_enc_fq_list_kernel(const ocg_enc_frag *__restrict__ cand, ocg_enc_frag *__re
 
 struct ocg_fq_desc_dev { uint32_t off; uint8_t count, nz[3]; };
 
+/* the candidates of a fragment side by side for the host: [k][fragment] arrays -> [fragment][k] records */
+__global__ void __launch_bounds__(256)
+ocg_enc_cand_pack_kernel(const ocg_enc_frag *__restrict__ cand, const uint32_t *__restrict__ satd, const int32_t *__restrict__ dc,
+                         int nfrags, int nluma, ocg_enc_cand_rec *__restrict__ out) {
+  const int f = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (f >= nfrags) return;
+  const int nchroma = nfrags - nluma;
+  const bool luma = f < nluma;
+#pragma unroll
+  for (int k = 0; k < OCG_ENC_NCAND; k++) {
+    const size_t at = luma ? (size_t)k * nluma + f : (size_t)OCG_ENC_NCAND * nluma + (size_t)k * nchroma + (f - nluma);
+    const ocg_enc_frag e = cand[at];
+    ocg_enc_cand_rec r;
+    r.ref_off0 = e.ref_off0; r.ref_off1 = e.ref_off1; r.satd = satd[at]; r.dc = dc[at];
+    out[(size_t)f * OCG_ENC_NCAND + k] = r;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ocg_enc_fq_compact_kernel(const ocg_enc_frag *__restrict__ cand, const int16_t *__restrict__ dct, const int16_t *__restrict__ qdct,
                           const int32_t *__restrict__ nonzero, int nfrags, int nluma, int nqis, ocg_fq_desc_dev *__restrict__ desc,
@@ -1642,6 +1660,7 @@ struct ocg_enc_inter {
   size_t off_isatd = 0, off_idc = 0, off_skip = 0, off_border = 0, off_key = 0, off_csatd = 0, off_cdc = 0, out_sz = 0;
   int32_t *h_border_slot = nullptr; /* [nfrags] index into border_ssd or -1 */
   /* speculative sub + fDCT + quantiser (ocg_enc_fq_*) */
+  ocg_enc_cand_rec *d_rec = nullptr, *h_rec = nullptr; /* [nfrags][K] candidate records for the host (h_rec pinned) */
   ocg_enc_frag *d_fq = nullptr;          /* [3 qii][OCG_FQ_NSEL][nfrags], luma block then chroma block */
   int16_t *d_fq_dct = nullptr, *d_fq_qdct = nullptr;
   int32_t *d_fq_nz = nullptr;
@@ -1666,6 +1685,8 @@ OCG_API void ocg_enc_inter_destroy(ocg_enc_inter *ei) {
   cudaFree(ei->d_cand);
   cudaFree(ei->d_out);
   if (ei->h_out) cudaFreeHost(ei->h_out);
+  cudaFree(ei->d_rec);
+  if (ei->h_rec) cudaFreeHost(ei->h_rec);
   cudaFree(ei->d_fq); cudaFree(ei->d_fq_dct); cudaFree(ei->d_fq_qdct); cudaFree(ei->d_fq_nz);
   cudaFree(ei->d_dequant); cudaFree(ei->d_enquant); cudaFree(ei->d_fq_desc); cudaFree(ei->d_fq_pool); cudaFree(ei->d_fq_counter);
   if (ei->h_qtab) cudaFreeHost(ei->h_qtab);
@@ -1730,7 +1751,9 @@ OCG_API int ocg_enc_inter_create(ocg_enc_inter **out, ocg_ctx *ctx, ocg_me *me, 
   EI_CU(cudaMalloc(&ei->d_border, ((size_t)nborder + 1) * sizeof(ocg_enc_frag)));
   EI_CU(cudaMalloc(&ei->d_cand, K * nf * sizeof(ocg_enc_frag)));
   EI_CU(cudaMalloc(&ei->d_out, ei->out_sz));
-  EI_CU(cudaHostAlloc(&ei->h_out, ei->out_sz + K * nf * sizeof(ocg_enc_frag), cudaHostAllocDefault));
+  EI_CU(cudaHostAlloc(&ei->h_out, ei->out_sz, cudaHostAllocDefault));
+  EI_CU(cudaMalloc(&ei->d_rec, K * nf * sizeof(ocg_enc_cand_rec)));
+  EI_CU(cudaHostAlloc(&ei->h_rec, K * nf * sizeof(ocg_enc_cand_rec), cudaHostAllocDefault));
   EI_CU(cudaMemcpyAsync(ei->d_mbfrags, mbfrags, (size_t)ei->nmbs * 12 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   EI_CU(cudaMemcpyAsync(ei->d_frag_off, foff.data(), nf * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   EI_CU(cudaMemcpyAsync(ei->d_all, all.data(), nf * sizeof(ocg_enc_frag), cudaMemcpyHostToDevice, st));
@@ -1850,22 +1873,22 @@ OCG_API int ocg_enc_inter_prepass(ocg_enc_inter *ei, int io_buf, int prev_buf, i
     }
   }
   const size_t small = ei->off_border + ((size_t)(ei->nborder_y + ei->nborder_c) + 1) * 4;
-  if (cudaMemcpyAsync(ei->h_out, ei->d_out, with_cands ? ei->out_sz : small, cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
-  ocg_enc_frag *h_keys = (ocg_enc_frag *)(ei->h_out + ei->out_sz);
-  if (with_cands &&
-      cudaMemcpyAsync(h_keys, ei->d_cand, (size_t)K * ei->nfrags * sizeof(ocg_enc_frag), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-    return OCG_ECUDA;
+  if (cudaMemcpyAsync(ei->h_out, ei->d_out, small, cudaMemcpyDeviceToHost, st) != cudaSuccess) return OCG_ECUDA;
+  if (with_cands) {
+    ocg_enc_cand_pack_kernel<<<(unsigned)((ei->nfrags + 255) / 256), 256, 0, st>>>(ei->d_cand, d_csatd, d_cdc, ei->nfrags, nl, ei->d_rec);
+    ocg_count_launch(1);
+    if (cudaMemcpyAsync(ei->h_rec, ei->d_rec, (size_t)K * ei->nfrags * sizeof(ocg_enc_cand_rec), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      return OCG_ECUDA;
+  }
   out->intra_satd = (const uint32_t *)(ei->h_out + ei->off_isatd);
   out->intra_dc = (const int32_t *)(ei->h_out + ei->off_idc);
   out->skip_ssd = (const uint32_t *)(ei->h_out + ei->off_skip);
   out->border_ssd = (const uint32_t *)(ei->h_out + ei->off_border);
   out->ncand = with_cands ? K : 0;
-  out->cand = h_keys;
-  out->cand_satd = (const uint32_t *)(ei->h_out + ei->off_csatd);
-  out->cand_dc = (const int32_t *)(ei->h_out + ei->off_cdc);
+  out->cand = ei->h_rec;
   out->nluma = nl;
   out->nfrags = ei->nfrags;
-  out->d2h_bytes = (long)((with_cands ? ei->out_sz + (size_t)K * ei->nfrags * sizeof(ocg_enc_frag) : small));
+  out->d2h_bytes = (long)(small + (with_cands ? (size_t)K * ei->nfrags * sizeof(ocg_enc_cand_rec) : 0));
   out->fq_nqis = with_cands ? ei->fq_nqis : 0;
   out->fq_desc = (const ocg_enc_fq_desc *)ei->h_fq_desc;
   out->fq_pool = (const int16_t *)ei->h_fq_pool;
