@@ -373,7 +373,9 @@ struct ocg_pp {
   uint8_t *d_pp = nullptr;
   int32_t *d_var = nullptr;
   uint8_t *d_q = nullptr;  /* [2][nfrags]: dc_qis, qis */
-  uint8_t *h_q = nullptr;  /* pinned staging of the same */
+  uint8_t *h_q = nullptr;  /* pinned staging of the same, two slots used in turn */
+  cudaEvent_t h_q_free[2] = {nullptr, nullptr}; /* recorded behind the upload that reads a slot */
+  int h_q_slot = 0;
   int nfrags = 0;
   int last_level = 0;
 };
@@ -388,6 +390,7 @@ OCG_API void ocg_pp_destroy(ocg_pp *pp) {
   cudaFree(pp->d_var);
   cudaFree(pp->d_q);
   if (pp->h_q) cudaFreeHost(pp->h_q);
+  for (int i = 0; i < 2; i++) if (pp->h_q_free[i]) cudaEventDestroy(pp->h_q_free[i]);
   delete pp;
 }
 
@@ -417,7 +420,8 @@ OCG_API int ocg_pp_create(ocg_pp **out, ocg_ctx *ctx) {
   PP_CU(cudaMalloc(&pp->d_pp, at + 64));
   PP_CU(cudaMalloc(&pp->d_var, (size_t)g->nfrags * sizeof(int32_t)));
   PP_CU(cudaMalloc(&pp->d_q, (size_t)g->nfrags * 2));
-  PP_CU(cudaHostAlloc(&pp->h_q, (size_t)g->nfrags * 2, cudaHostAllocDefault));
+  PP_CU(cudaHostAlloc(&pp->h_q, (size_t)g->nfrags * 4, cudaHostAllocDefault));
+  for (int i = 0; i < 2; i++) PP_CU(cudaEventCreateWithFlags(&pp->h_q_free[i], cudaEventDisableTiming));
 #undef PP_CU
   *out = pp;
   return OCG_OK;
@@ -435,14 +439,18 @@ OCG_API int ocg_pp_run(ocg_pp *pp, int self_buf, int level, const int32_t *dc_sc
   if (self_buf < 0 || self_buf >= g->nrefs) return OCG_EINVAL;
   if (ocg_set_device(pp->device) != cudaSuccess) return OCG_ECUDA;
   cudaStream_t st = (cudaStream_t)ocg_ctx_stream(pp->ctx);
-  /* the staging buffer is reused: the previous frame's copy must have been consumed */
-  if (cudaStreamSynchronize(st) != cudaSuccess) return OCG_ECUDA;
+  /* nothing is waited for here except the upload that last read this staging slot (two frames ago) */
+  const int slot = pp->h_q_slot;
+  pp->h_q_slot ^= 1;
+  uint8_t *hq = pp->h_q + (size_t)slot * 2 * pp->nfrags;
+  if (cudaEventSynchronize(pp->h_q_free[slot]) != cudaSuccess) return OCG_ECUDA;
   memcpy(pp->args.dc_scale, dc_scale, sizeof(pp->args.dc_scale));
   memcpy(pp->args.sharp_mod, sharp_mod, sizeof(pp->args.sharp_mod));
   pp->args.level = level;
-  memcpy(pp->h_q, dc_qis, (size_t)pp->nfrags);
-  memcpy(pp->h_q + pp->nfrags, qis, (size_t)pp->nfrags);
-  if (cudaMemcpyAsync(pp->d_q, pp->h_q, (size_t)pp->nfrags * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+  memcpy(hq, dc_qis, (size_t)pp->nfrags);
+  memcpy(hq + pp->nfrags, qis, (size_t)pp->nfrags);
+  if (cudaMemcpyAsync(pp->d_q, hq, (size_t)pp->nfrags * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaEventRecord(pp->h_q_free[slot], st) != cudaSuccess ||
       cudaMemsetAsync(pp->d_var, 0, (size_t)pp->nfrags * sizeof(int32_t), st) != cudaSuccess)
     return OCG_ECUDA;
   const uint8_t *src = (const uint8_t *)ocg_ctx_frame_devptr(pp->ctx, self_buf) + g->base_off;
