@@ -236,6 +236,9 @@ static void backend_flush(ocg_backend *b) {
     unsigned char *host_self = st->ref_frame_handle + (size_t)self * (size_t)b->geom.ref_frame_sz;
     long extra_h2d = 0, d2h;
     int r;
+    /* with luma AND chroma post-processing on, th_decode_ycbcr_out hands out the post-processed planes only
+       (decode.c:1299-1315): the reconstruction itself need not leave the device */
+    const int out_mode = b->pp_level >= 5 && b->out_mode == OCG_OUT_PICTURE ? OCG_OUT_NONE : b->out_mode;
     /* A reference the device has never produced (stream starting on an inter
        frame: oc_dec_init_dummy_frame, decode.c:2053) is taken from the host. */
     if (st->frame_type != OC_INTRA_FRAME) {
@@ -282,10 +285,10 @@ static void backend_flush(ocg_backend *b) {
         }
       }
       t.ntoken_bytes = dec->dct_tokens_count;
-      if (ocg_dec_flush_tokens(b->ctx, &t, host_self, b->out_mode) < 0) { backend_fail(b, "ocg_dec_flush_tokens failed"); return; }
+      if (ocg_dec_flush_tokens(b->ctx, &t, host_self, out_mode) < 0) { backend_fail(b, "ocg_dec_flush_tokens failed"); return; }
       extra_h2d += (long)b->geom.nfrags * 6 + t.ntoken_bytes - (long)b->geom.nfrags * 16;
-    } else if (ocg_dec_flush(b->ctx, &f, host_self, b->out_mode) < 0) { backend_fail(b, "ocg_dec_flush failed"); return; }
-    d2h = b->out_mode == OCG_OUT_PADDED ? (long)b->geom.ref_frame_sz : ocg_picture_bytes(&b->geom);
+    } else if (ocg_dec_flush(b->ctx, &f, host_self, out_mode) < 0) { backend_fail(b, "ocg_dec_flush failed"); return; }
+    d2h = b->out_mode == OCG_OUT_PADDED ? (long)b->geom.ref_frame_sz : ocg_picture_bytes(&b->geom); /* reconstruction or post-processed planes */
     b->pending = 1;
     b->dev_valid[self] = 1;
     stats_add(b, extra_h2d + (long)b->geom.nfrags * 16 + (long)b->nrows * 16, d2h, now_s() - t0);
